@@ -1,0 +1,1450 @@
+// context.cu — the C-ABI of include/fflins.h: device-resident session state (frames, keyframe
+// maps + hashes, features) and the stream-ordered launch sequences behind every entry point.
+// Host arithmetic here is limited to 3x3 pose algebra the reference also does on the host.
+// There is no CPU fallback: a missing CUDA device fails fflins_create.
+#include "../../include/fflins.h"
+#include "kernels.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+using namespace fflins;
+
+namespace {
+
+struct Cloud {
+    float4 *d = nullptr;
+    int n     = 0;
+    int cap   = 0;
+};
+
+struct Frame {
+    uint64_t id = 0;
+    Cloud c[5];
+    fflins_pose pose{};
+    double v[3] = {0, 0, 0}, w[3] = {0, 0, 0}, td = 0;
+    int n_raw = 0, n_fallback = 0;
+    bool is_key = false;
+    // keyframe hash (K4)
+    unsigned long long *hkeys = nullptr;
+    int *hvals                = nullptr;
+    int hcap                  = 0;
+    // features stored on this (ref) frame, indexed by the cur frame's points
+    FeatureSoA feat;
+    int feat_cap = 0, feat_q = 0;
+    int *feat_counts = nullptr;
+};
+
+struct Pool {
+    std::map<size_t, std::vector<void *>> free_lists;
+    std::unordered_map<void *, size_t> sizes;
+    size_t total = 0;
+    static size_t round(size_t b) {
+        size_t r = 256;
+        while (r < b) r <<= 1;
+        return r;
+    }
+    void *alloc(size_t bytes) {
+        size_t r  = round(bytes);
+        auto &lst = free_lists[r];
+        if (!lst.empty()) {
+            void *p = lst.back();
+            lst.pop_back();
+            return p;
+        }
+        void *p = nullptr;
+        if (cudaMalloc(&p, r) != cudaSuccess) return nullptr;
+        sizes[p] = r;
+        total += r;
+        return p;
+    }
+    void release(void *p) {
+        if (!p) return;
+        free_lists[sizes[p]].push_back(p);
+    }
+    void destroy() {
+        for (auto &kv : sizes) cudaFree(kv.first);
+        sizes.clear();
+        free_lists.clear();
+    }
+};
+
+struct ProfRec {
+    int name;
+    cudaEvent_t a, b;
+};
+
+} // namespace
+
+struct fflins_ctx : public Profiler {
+    fflins_config cfg;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::unordered_map<uint64_t, Frame *> frames;
+    std::deque<uint64_t> keyframes;
+    Pool pool;
+    std::string err;
+    int64_t launches = 0;
+    float cell_scale = 1.0f;
+
+    // staging (device)
+    void *d_stage = nullptr;
+    size_t stage_cap = 0;
+    double *d_ins = nullptr; // t[w] p[3w] q[4w]
+    int ins_cap = 0;
+    double *d_tab = nullptr;
+    Pose12 *d_frame_pose = nullptr; // [2]
+    int *d_counters = nullptr;      // [64]
+    VoxelWork vox;
+    void *vox_base = nullptr;
+    // factor scratch
+    double *d_partial = nullptr, *d_red = nullptr;
+    unsigned int *d_tickets = nullptr;
+    int *d_outliers = nullptr;
+    size_t partial_cap = 0;
+    // pinned host scratch
+    unsigned char *h_pin = nullptr;
+    size_t h_pin_cap = 0;
+
+    // profiler
+    bool prof_on = false;
+    std::vector<std::string> prof_names;
+    std::vector<double> prof_ms;
+    std::vector<int64_t> prof_cnt;
+    std::vector<ProfRec> prof_open;
+    std::vector<cudaEvent_t> ev_free;
+    int prof_cur = -1;
+    cudaEvent_t prof_a = nullptr;
+
+    void begin(const char *name, cudaStream_t s) override {
+        if (!prof_on) return;
+        int id = -1;
+        for (size_t i = 0; i < prof_names.size(); i++)
+            if (prof_names[i] == name) id = (int) i;
+        if (id < 0) {
+            id = (int) prof_names.size();
+            prof_names.push_back(name);
+            prof_ms.push_back(0);
+            prof_cnt.push_back(0);
+        }
+        prof_cur = id;
+        prof_a   = get_event();
+        cudaEventRecord(prof_a, s);
+    }
+    void end(cudaStream_t s) override {
+        if (!prof_on || prof_cur < 0) return;
+        cudaEvent_t b = get_event();
+        cudaEventRecord(b, s);
+        prof_open.push_back({prof_cur, prof_a, b});
+        prof_cur = -1;
+    }
+    cudaEvent_t get_event() {
+        if (!ev_free.empty()) {
+            cudaEvent_t e = ev_free.back();
+            ev_free.pop_back();
+            return e;
+        }
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        return e;
+    }
+    void prof_collect() {
+        cudaStreamSynchronize(stream);
+        for (auto &r : prof_open) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, r.a, r.b);
+            prof_ms[r.name] += ms;
+            prof_cnt[r.name] += 1;
+            ev_free.push_back(r.a);
+            ev_free.push_back(r.b);
+        }
+        prof_open.clear();
+    }
+    Profiler *prof() { return prof_on ? this : nullptr; }
+};
+
+namespace {
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                               \
+            return FFLINS_E_CUDA;                                                                        \
+        }                                                                                                \
+    } while (0)
+
+#define REQUIRE(cond, msg)               \
+    do {                                 \
+        if (!(cond)) {                   \
+            ctx->err = msg;              \
+            return FFLINS_E_INVALID;     \
+        }                                \
+    } while (0)
+
+int fail(fflins_ctx *ctx, int code, const std::string &msg) {
+    ctx->err = msg;
+    return code;
+}
+
+Pose12 to12(const fflins_pose &p) {
+    Pose12 o;
+    std::memcpy(o.R, p.R, sizeof(o.R));
+    std::memcpy(o.t, p.t, sizeof(o.t));
+    return o;
+}
+
+// 3x3 helpers, evaluated ((a0*b0 + a1*b1) + a2*b2) like the oracle; nvcc's host pass targets
+// baseline x86-64, which has no FMA, so products and sums round separately.
+void mat_tn(const double *A, const double *B, double *C) { // A^T B
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) C[3 * i + j] = (A[i] * B[j] + A[3 + i] * B[3 + j]) + A[6 + i] * B[6 + j];
+}
+void mat_tv(const double *A, const double *v, double *o) { // A^T v
+    for (int i = 0; i < 3; i++) o[i] = (A[i] * v[0] + A[3 + i] * v[1]) + A[6 + i] * v[2];
+}
+
+Frame *find_frame(fflins_ctx *ctx, uint64_t id) {
+    auto it = ctx->frames.find(id);
+    return it == ctx->frames.end() ? nullptr : it->second;
+}
+Frame *get_frame(fflins_ctx *ctx, uint64_t id) {
+    Frame *f = find_frame(ctx, id);
+    if (!f) {
+        f     = new Frame();
+        f->id = id;
+        for (int i = 0; i < 9; i++) f->pose.R[i] = (i % 4 == 0) ? 1.0 : 0.0;
+        ctx->frames[id] = f;
+    }
+    return f;
+}
+
+int ensure_cloud(fflins_ctx *ctx, Cloud &c, int n, bool keep = false) {
+    if (n <= c.cap) return FFLINS_OK;
+    size_t want = Pool::round((size_t) std::max(n, 256) * sizeof(float4));
+    float4 *p   = (float4 *) ctx->pool.alloc(want);
+    if (!p) return fail(ctx, FFLINS_E_NOMEM, "device allocation failed");
+    if (keep && c.d && c.n > 0)
+        cudaMemcpyAsync(p, c.d, (size_t) c.n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream);
+    if (c.d) {
+        if (keep) cudaStreamSynchronize(ctx->stream);
+        ctx->pool.release(c.d);
+    }
+    c.d   = p;
+    c.cap = (int) (want / sizeof(float4));
+    return FFLINS_OK;
+}
+
+void free_frame(fflins_ctx *ctx, Frame *f) {
+    for (auto &c : f->c) ctx->pool.release(c.d);
+    ctx->pool.release(f->hkeys);
+    ctx->pool.release(f->hvals);
+    ctx->pool.release(f->feat.type);
+    ctx->pool.release(f->feat.covered);
+    ctx->pool.release(f->feat.outlier);
+    ctx->pool.release(f->feat.nn_idx);
+    ctx->pool.release(f->feat.nn_d2);
+    ctx->pool.release(f->feat.normal);
+    ctx->pool.release(f->feat.d);
+    ctx->pool.release(f->feat_counts);
+    delete f;
+}
+
+int ensure_stage(fflins_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->stage_cap) return FFLINS_OK;
+    ctx->pool.release(ctx->d_stage);
+    ctx->d_stage = ctx->pool.alloc(bytes);
+    if (!ctx->d_stage) {
+        ctx->stage_cap = 0;
+        return fail(ctx, FFLINS_E_NOMEM, "device allocation failed");
+    }
+    ctx->stage_cap = Pool::round(bytes);
+    return FFLINS_OK;
+}
+
+int ensure_ins(fflins_ctx *ctx, int w) {
+    if (w <= ctx->ins_cap) return FFLINS_OK;
+    ctx->pool.release(ctx->d_ins);
+    ctx->pool.release(ctx->d_tab);
+    int cap    = std::max(w, 2048);
+    ctx->d_ins = (double *) ctx->pool.alloc((size_t) cap * 8 * sizeof(double));
+    ctx->d_tab = (double *) ctx->pool.alloc((size_t) cap * 6 * sizeof(double));
+    if (!ctx->d_ins || !ctx->d_tab) return fail(ctx, FFLINS_E_NOMEM, "device allocation failed");
+    ctx->ins_cap = cap;
+    return FFLINS_OK;
+}
+
+int ensure_voxel(fflins_ctx *ctx, int n) {
+    if (n <= ctx->vox.cap) return FFLINS_OK;
+    ctx->pool.release(ctx->vox_base);
+    int cap = (int) (Pool::round((size_t) std::max(n, 4096)));
+    size_t off[8];
+    size_t bytes  = voxel_work_bytes(cap, off);
+    ctx->vox_base = ctx->pool.alloc(bytes);
+    if (!ctx->vox_base) {
+        ctx->vox.cap = 0;
+        return fail(ctx, FFLINS_E_NOMEM, "device allocation failed");
+    }
+    char *b              = (char *) ctx->vox_base;
+    ctx->vox.keys[0]     = (uint32_t *) (b + off[0]);
+    ctx->vox.keys[1]     = (uint32_t *) (b + off[1]);
+    ctx->vox.idx[0]      = (uint32_t *) (b + off[2]);
+    ctx->vox.idx[1]      = (uint32_t *) (b + off[3]);
+    ctx->vox.block_hist  = (uint32_t *) (b + off[4]);
+    ctx->vox.block_heads = (uint32_t *) (b + off[5]);
+    ctx->vox.meta        = (int *) (b + off[6]);
+    ctx->vox.cap         = cap;
+    return FFLINS_OK;
+}
+
+unsigned char *pin(fflins_ctx *ctx, size_t bytes) {
+    if (bytes > ctx->h_pin_cap) {
+        if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+        size_t cap = std::max<size_t>(bytes, 1 << 20);
+        if (cudaMallocHost((void **) &ctx->h_pin, cap) != cudaSuccess) {
+            ctx->h_pin     = nullptr;
+            ctx->h_pin_cap = 0;
+            return nullptr;
+        }
+        ctx->h_pin_cap = cap;
+    }
+    return ctx->h_pin;
+}
+
+void fill_info(Frame *f, fflins_frame_info *out) {
+    if (!out) return;
+    out->id         = f->id;
+    out->n_raw      = f->n_raw;
+    out->n_dec      = f->c[FFLINS_CLOUD_LIDAR_FULL].n;
+    out->n_down     = f->c[FFLINS_CLOUD_LIDAR].n;
+    out->n_map      = f->c[FFLINS_CLOUD_MAP].n;
+    out->n_fallback = f->n_fallback;
+    out->reserved   = 0;
+    out->pose       = f->pose;
+}
+
+// Shared tail of the two lidarFrameProcessing overloads: voxel filter of the decimated cloud,
+// world projection, result read-back (one synchronisation per frame).
+int frame_tail(fflins_ctx *ctx, Frame *f, int n, int ndec, bool pose_on_device, fflins_frame_info *out) {
+    cudaStream_t s = ctx->stream;
+    int rc;
+    if ((rc = ensure_voxel(ctx, ndec))) return rc;
+    int *d_ndown = ctx->d_counters + 1;
+    launch_voxel_downsample(s, ctx->vox, f->c[FFLINS_CLOUD_LIDAR_FULL].d, ndec, (float) ctx->cfg.downsample_size,
+                            f->c[FFLINS_CLOUD_LIDAR].d, d_ndown, nullptr, &ctx->launches, ctx->prof(), "voxel_frame");
+    {
+        ProfScope ps(ctx->prof(), "project_world", s);
+        if (pose_on_device)
+            launch_project_dev(s, ctx->d_frame_pose, f->c[FFLINS_CLOUD_LIDAR].d, f->c[FFLINS_CLOUD_WORLD].d, ndec, d_ndown);
+        else
+            launch_project(s, to12(f->pose), f->c[FFLINS_CLOUD_LIDAR].d, f->c[FFLINS_CLOUD_WORLD].d, ndec, d_ndown);
+        ctx->launches++;
+    }
+    unsigned char *h = pin(ctx, 256);
+    if (!h) return fail(ctx, FFLINS_E_NOMEM, "pinned allocation failed");
+    CK(cudaMemcpyAsync(h, ctx->d_counters, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (pose_on_device) CK(cudaMemcpyAsync(h + 16, ctx->d_frame_pose, sizeof(Pose12), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    int cnt[2];
+    std::memcpy(cnt, h, sizeof(cnt));
+    if (pose_on_device) {
+        Pose12 p;
+        std::memcpy(&p, h + 16, sizeof(p));
+        std::memcpy(f->pose.R, p.R, sizeof(p.R));
+        std::memcpy(f->pose.t, p.t, sizeof(p.t));
+    }
+    f->n_raw                        = n;
+    f->n_fallback                   = cnt[0];
+    f->c[FFLINS_CLOUD_MAP_FULL].n   = n;
+    f->c[FFLINS_CLOUD_LIDAR_FULL].n = ndec;
+    f->c[FFLINS_CLOUD_LIDAR].n      = cnt[1];
+    f->c[FFLINS_CLOUD_WORLD].n      = cnt[1];
+    f->c[FFLINS_CLOUD_MAP].n        = 0;
+    fill_info(f, out);
+    return FFLINS_OK;
+}
+
+int process_core(fflins_ctx *ctx, uint64_t id, const float4 *d_xyzi, const double *d_time, const void *d_aos, int n,
+                 const double *d_ins_t, const double *d_ins_p, const double *d_ins_q, int w,
+                 const fflins_pose *pose_b_l, double stamp, double td, fflins_frame_info *out) {
+    cudaStream_t s = ctx->stream;
+    Frame *f       = get_frame(ctx, id);
+    const int F    = ctx->cfg.point_filter_num;
+    const int ndec = (n + F - 1) / F;
+    int rc;
+    if ((rc = ensure_cloud(ctx, f->c[FFLINS_CLOUD_MAP_FULL], n))) return rc;
+    if ((rc = ensure_cloud(ctx, f->c[FFLINS_CLOUD_LIDAR_FULL], ndec))) return rc;
+    if ((rc = ensure_cloud(ctx, f->c[FFLINS_CLOUD_LIDAR], ndec))) return rc;
+    if ((rc = ensure_cloud(ctx, f->c[FFLINS_CLOUD_WORLD], ndec))) return rc;
+    if ((rc = ensure_ins(ctx, w))) return rc;
+    CK(cudaMemsetAsync(ctx->d_counters, 0, 4 * sizeof(int), s));
+    Pose12 ext = to12(*pose_b_l);
+    {
+        ProfScope ps(ctx->prof(), "ins_prep", s);
+        launch_ins_prep(s, d_ins_t, d_ins_p, d_ins_q, w, ext, stamp, ctx->d_tab, ctx->d_frame_pose);
+        ctx->launches++;
+    }
+    {
+        ProfScope ps(ctx->prof(), "undistort", s);
+        launch_undistort(s, d_xyzi, d_time, d_aos, n, d_ins_t, d_ins_p, d_ins_q, w, ctx->d_tab, ctx->d_frame_pose, ext,
+                         td, F, f->c[FFLINS_CLOUD_MAP_FULL].d, f->c[FFLINS_CLOUD_LIDAR_FULL].d, ctx->d_counters);
+        if (n > 0) ctx->launches++;
+    }
+    f->td = td;
+    return frame_tail(ctx, f, n, ndec, true, out);
+}
+
+int check_window(fflins_ctx *ctx, const double *ins_t, int w) {
+    REQUIRE(w >= 2 && w <= 65536, "INS window must hold 2..65536 entries");
+    for (int i = 1; i < w; i++) REQUIRE(ins_t[i] > ins_t[i - 1], "INS window times must be strictly increasing");
+    return FFLINS_OK;
+}
+
+int upload_ins(fflins_ctx *ctx, const double *ins_t, const double *ins_p, const double *ins_q, int w) {
+    int rc;
+    if ((rc = ensure_ins(ctx, w))) return rc;
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->d_ins, ins_t, (size_t) w * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->d_ins + w, ins_p, (size_t) w * 24, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->d_ins + 4 * (size_t) w, ins_q, (size_t) w * 32, cudaMemcpyHostToDevice, s));
+    return FFLINS_OK;
+}
+
+int next_pow2(int v) {
+    int r = 1024;
+    while (r < v) r <<= 1;
+    return r;
+}
+
+int ensure_features(fflins_ctx *ctx, Frame *f, int q) {
+    if (q <= f->feat_cap && f->feat.type) return FFLINS_OK;
+    int cap = std::max(q, 1024);
+    Pool &P = ctx->pool;
+    P.release(f->feat.type);
+    P.release(f->feat.covered);
+    P.release(f->feat.outlier);
+    P.release(f->feat.nn_idx);
+    P.release(f->feat.nn_d2);
+    P.release(f->feat.normal);
+    P.release(f->feat.d);
+    f->feat.type    = (int8_t *) P.alloc(cap);
+    f->feat.covered = (uint8_t *) P.alloc(cap);
+    f->feat.outlier = (uint8_t *) P.alloc(cap);
+    f->feat.nn_idx  = (int32_t *) P.alloc((size_t) cap * 20);
+    f->feat.nn_d2   = (float *) P.alloc((size_t) cap * 20);
+    f->feat.normal  = (double *) P.alloc((size_t) cap * 24);
+    f->feat.d       = (double *) P.alloc((size_t) cap * 8);
+    if (!f->feat_counts) f->feat_counts = (int *) P.alloc(256);
+    if (!f->feat.type || !f->feat.covered || !f->feat.outlier || !f->feat.nn_idx || !f->feat.nn_d2 || !f->feat.normal ||
+        !f->feat.d || !f->feat_counts)
+        return fail(ctx, FFLINS_E_NOMEM, "device allocation failed");
+    f->feat_cap = cap;
+    return FFLINS_OK;
+}
+
+float search_cell(const fflins_ctx *ctx) { return (float) ctx->cfg.downsample_size * ctx->cell_scale; }
+
+int build_hash(fflins_ctx *ctx, Frame *f) {
+    const Cloud &m = f->c[FFLINS_CLOUD_MAP];
+    int hcap       = next_pow2(2 * std::max(m.n, 1));
+    if (hcap > f->hcap) {
+        ctx->pool.release(f->hkeys);
+        ctx->pool.release(f->hvals);
+        f->hkeys = (unsigned long long *) ctx->pool.alloc((size_t) hcap * 8);
+        f->hvals = (int *) ctx->pool.alloc((size_t) hcap * 4);
+        if (!f->hkeys || !f->hvals) return fail(ctx, FFLINS_E_NOMEM, "device allocation failed");
+    }
+    f->hcap = hcap;
+    ProfScope ps(ctx->prof(), "hash_build", ctx->stream);
+    launch_hash_build(ctx->stream, m.d, m.n, 1.0f / search_cell(ctx), f->hkeys, f->hvals, hcap);
+    ctx->launches += (m.n > 0) ? 2 : 1;
+    return FFLINS_OK;
+}
+
+void fill_assoc_common(const fflins_ctx *ctx, AssocParams &P) {
+    float cell      = search_cell(ctx);
+    P.inv_cell      = 1.0f / cell;
+    P.cell          = cell;
+    double max_dist = ctx->cfg.max_search_square_distance; // passed as max_dist and squared (ikd_Tree.cc:902)
+    P.r_max         = (int) std::ceil(max_dist / cell) + 1;
+    P.max_d2        = (float) (max_dist * max_dist);
+    P.plane_d2_gate = (float) ctx->cfg.max_search_square_distance;
+    P.plane_thr     = ctx->cfg.plane_estimation_threshold;
+    P.sigma         = ctx->cfg.point_to_plane_std;
+    P.scalar_thr    = ctx->cfg.plane_scalar_threshold;
+    P.sigma_gate    = ctx->cfg.plane_sigma_gate;
+}
+
+// world -> ref transform as formed at lidar_map.cc:343-345: R^T and (-R^T) t
+Pose12 ref_world(const fflins_pose &pose) {
+    Pose12 T;
+    double neg[9];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            T.R[3 * i + j] = pose.R[3 * j + i];
+            neg[3 * i + j] = -T.R[3 * i + j];
+        }
+    for (int i = 0; i < 3; i++)
+        T.t[i] = (neg[3 * i] * pose.t[0] + neg[3 * i + 1] * pose.t[1]) + neg[3 * i + 2] * pose.t[2];
+    return T;
+}
+
+int run_associate(fflins_ctx *ctx, const std::vector<Frame *> &refs, Frame *cur, int32_t *nf, int32_t *nc) {
+    cudaStream_t s = ctx->stream;
+    const int q    = cur->c[FFLINS_CLOUD_LIDAR].n;
+    AssocParams P{};
+    fill_assoc_common(ctx, P);
+    P.n_refs = (int) refs.size();
+    P.q      = q;
+    int rc;
+    for (size_t i = 0; i < refs.size(); i++) {
+        Frame *r = refs[i];
+        if ((rc = ensure_features(ctx, r, q))) return rc;
+        if (!r->hkeys && r->c[FFLINS_CLOUD_MAP].n > 0) return fail(ctx, FFLINS_E_INVALID, "reference frame has no map index (fflins_keyframe_add not called)");
+        AssocRef &a   = P.ref[i];
+        a.map         = r->c[FFLINS_CLOUD_MAP].d;
+        a.hkeys       = r->hkeys;
+        a.hvals       = r->hvals;
+        a.hmask       = r->hcap - 1;
+        a.m           = r->c[FFLINS_CLOUD_MAP].n;
+        a.T_ref_world = ref_world(r->pose);
+        a.feat        = r->feat;
+        a.counts      = r->feat_counts;
+        r->feat_q     = q;
+        CK(cudaMemsetAsync(r->feat_counts, 0, 2 * sizeof(int), s));
+    }
+    {
+        ProfScope ps(ctx->prof(), "associate", s);
+        launch_associate(s, P, cur->c[FFLINS_CLOUD_WORLD].d, cur->c[FFLINS_CLOUD_LIDAR].d);
+        if (q > 0 && !refs.empty()) ctx->launches++;
+    }
+    unsigned char *h = pin(ctx, 1024);
+    if (!h) return fail(ctx, FFLINS_E_NOMEM, "pinned allocation failed");
+    for (size_t i = 0; i < refs.size(); i++)
+        CK(cudaMemcpyAsync(h + 8 * i, refs[i]->feat_counts, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    for (size_t i = 0; i < refs.size(); i++) {
+        int c[2];
+        std::memcpy(c, h + 8 * i, 8);
+        if (q == 0) c[0] = c[1] = 0;
+        nf[i] = c[0];
+        nc[i] = c[1];
+    }
+    return FFLINS_OK;
+}
+
+int ensure_factor_scratch(fflins_ctx *ctx, int n_pairs, int q) {
+    size_t blocks = (size_t) (q + kFactorBlock - 1) / kFactorBlock + 1;
+    size_t need   = (size_t) kMaxRefs * blocks * kRedSize * sizeof(double);
+    (void) n_pairs;
+    if (need > ctx->partial_cap) {
+        ctx->pool.release(ctx->d_partial);
+        ctx->d_partial = (double *) ctx->pool.alloc(need);
+        if (!ctx->d_partial) {
+            ctx->partial_cap = 0;
+            return fail(ctx, FFLINS_E_NOMEM, "device allocation failed");
+        }
+        ctx->partial_cap = Pool::round(need);
+    }
+    return FFLINS_OK;
+}
+
+void unpack_red(const double *red, double *H, double *b, double *cost, int32_t *n_res) {
+    if (H) {
+        int e = 0;
+        for (int i = 0; i < 19; i++)
+            for (int j = i; j < 19; j++) {
+                H[19 * i + j] = red[e];
+                H[19 * j + i] = red[e];
+                e++;
+            }
+    }
+    if (b)
+        for (int i = 0; i < 19; i++) b[i] = red[190 + i];
+    if (cost) {
+        cost[0] = 0.5 * red[209];
+        cost[1] = red[210];
+    }
+    if (n_res) *n_res = (int32_t) std::llround(red[211]);
+}
+
+int fill_factor_pairs(fflins_ctx *ctx, FactorParams &P, int n_pairs, const uint64_t *ref_ids, const double *pose_refs,
+                      Frame *cur, const double *pose_cur, const double *ext, double td, uint32_t flags) {
+    REQUIRE(n_pairs >= 0 && n_pairs <= kMaxRefs, "too many pairs");
+    P.n_pairs = n_pairs;
+    P.q       = cur->c[FFLINS_CLOUD_LIDAR].n;
+    P.flags   = flags;
+    std::memcpy(P.pose_cur, pose_cur, 7 * sizeof(double));
+    std::memcpy(P.ext, ext, 7 * sizeof(double));
+    P.td = td;
+    std::memcpy(P.v1, cur->v, sizeof(P.v1));
+    std::memcpy(P.w1, cur->w, sizeof(P.w1));
+    P.td1         = cur->td;
+    P.sigma       = ctx->cfg.point_to_plane_std;
+    P.huber_delta = ctx->cfg.huber_delta;
+    for (int i = 0; i < n_pairs; i++) {
+        Frame *r = find_frame(ctx, ref_ids[i]);
+        if (!r) return fail(ctx, FFLINS_E_NOTFOUND, "unknown ref frame");
+        if (!r->feat.type || r->feat_q != P.q)
+            return fail(ctx, FFLINS_E_INVALID, "ref frame holds no features for the current frame (associate first)");
+        FactorPair &p = P.pair[i];
+        p.type        = r->feat.type;
+        p.outlier     = r->feat.outlier;
+        p.normal      = r->feat.normal;
+        p.d           = r->feat.d;
+        p.std         = nullptr;
+        std::memcpy(p.pose_ref, pose_refs + 7 * i, 7 * sizeof(double));
+        std::memcpy(p.v0, r->v, sizeof(p.v0));
+        std::memcpy(p.w0, r->w, sizeof(p.w0));
+        p.td0 = r->td;
+    }
+    return FFLINS_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *fflins_version(void) { return "fflins-b200 0.1 (sm_100a)"; }
+
+void fflins_config_default(fflins_config *c) {
+    if (!c) return;
+    std::memset(c, 0, sizeof(*c));
+    c->point_to_plane_std           = 0.1;
+    c->window_size                  = 10;
+    c->point_filter_num             = 10;
+    c->downsample_size              = 0.5;
+    c->frame_rate                   = 10;
+    c->plane_estimation_threshold   = 0.1;
+    c->minimum_keyframe_translation = 0.4;
+    c->max_search_square_distance   = 5.0;
+    c->max_keyframe_interval        = 0.5 * 0.95;
+    c->min_keyframe_rotation        = 10.0 * M_PI / 180.0;
+    c->plane_scalar_threshold       = 0.1;
+    c->plane_sigma_gate             = 4.5;
+    c->huber_delta                  = 1.0;
+    c->max_points_per_frame         = 0;
+    c->max_merge_frames             = 0;
+}
+
+int fflins_create(const fflins_config *cfg, int device, fflins_ctx **out) {
+    if (!cfg || !out) return FFLINS_E_INVALID;
+    *out      = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) return FFLINS_E_NODEVICE;
+    if (cfg->point_filter_num < 1 || cfg->downsample_size <= 0 || cfg->point_to_plane_std <= 0 ||
+        cfg->window_size < 1 || cfg->window_size >= kMaxRefs)
+        return FFLINS_E_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return FFLINS_E_NODEVICE;
+    fflins_ctx *ctx = new fflins_ctx();
+    ctx->cfg        = *cfg;
+    ctx->device     = device;
+    if (const char *e = getenv("FFLINS_CELL_SCALE")) {
+        float v = (float) atof(e);
+        if (v >= 0.5f && v <= 8.f) ctx->cell_scale = v;
+    }
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return FFLINS_E_CUDA;
+    }
+    ctx->d_frame_pose = (Pose12 *) ctx->pool.alloc(2 * sizeof(Pose12));
+    ctx->d_counters   = (int *) ctx->pool.alloc(64 * sizeof(int));
+    ctx->d_red        = (double *) ctx->pool.alloc((size_t) kMaxRefs * kRedSize * sizeof(double));
+    ctx->d_tickets    = (unsigned int *) ctx->pool.alloc(kMaxRefs * sizeof(unsigned int));
+    ctx->d_outliers   = (int *) ctx->pool.alloc(kMaxRefs * sizeof(int));
+    if (!ctx->d_frame_pose || !ctx->d_counters || !ctx->d_red || !ctx->d_tickets || !ctx->d_outliers) {
+        fflins_destroy(ctx);
+        return FFLINS_E_NOMEM;
+    }
+    cudaMemsetAsync(ctx->d_tickets, 0, kMaxRefs * sizeof(unsigned int), ctx->stream);
+    int n = cfg->max_points_per_frame > 0 ? cfg->max_points_per_frame : 262144;
+    int k = cfg->max_merge_frames > 0 ? cfg->max_merge_frames : 8;
+    if (ensure_voxel(ctx, n * k) != FFLINS_OK || ensure_stage(ctx, (size_t) n * 32) != FFLINS_OK ||
+        ensure_ins(ctx, 4096) != FFLINS_OK || !pin(ctx, 1 << 20)) {
+        fflins_destroy(ctx);
+        return FFLINS_E_NOMEM;
+    }
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        fflins_destroy(ctx);
+        return FFLINS_E_CUDA;
+    }
+    *out = ctx;
+    return FFLINS_OK;
+}
+
+void fflins_destroy(fflins_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto &kv : ctx->frames) {
+        Frame *f = kv.second;
+        delete f;
+    }
+    ctx->frames.clear();
+    ctx->pool.destroy();
+    if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+    for (auto &r : ctx->prof_open) {
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    for (auto e : ctx->ev_free) cudaEventDestroy(e);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *fflins_last_error(const fflins_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int fflins_synchronize(fflins_ctx *ctx) {
+    if (!ctx) return FFLINS_E_INVALID;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FFLINS_OK;
+}
+
+int fflins_host_register(void *ptr, uint64_t bytes) {
+    if (!ptr || !bytes) return FFLINS_E_INVALID;
+    return cudaHostRegister(ptr, bytes, cudaHostRegisterDefault) == cudaSuccess ? FFLINS_OK : FFLINS_E_CUDA;
+}
+int fflins_host_unregister(void *ptr) {
+    if (!ptr) return FFLINS_E_INVALID;
+    return cudaHostUnregister(ptr) == cudaSuccess ? FFLINS_OK : FFLINS_E_CUDA;
+}
+
+int fflins_frame_process(fflins_ctx *ctx, uint64_t frame_id, const float *xyzi, const double *time, int32_t n,
+                         const double *ins_t, const double *ins_p, const double *ins_q, int32_t w,
+                         const fflins_pose *pose_b_l, double stamp, double td, fflins_frame_info *out) {
+    if (!ctx) return FFLINS_E_INVALID;
+    REQUIRE(n >= 0 && (n == 0 || (xyzi && time)) && ins_t && ins_p && ins_q && pose_b_l, "null argument");
+    int rc;
+    if ((rc = check_window(ctx, ins_t, w))) return rc;
+    if ((rc = ensure_stage(ctx, (size_t) std::max(n, 1) * 24))) return rc;
+    cudaStream_t s = ctx->stream;
+    float4 *d_xyzi = (float4 *) ctx->d_stage;
+    double *d_time = (double *) ((char *) ctx->d_stage + (size_t) n * 16);
+    if (n > 0) {
+        CK(cudaMemcpyAsync(d_xyzi, xyzi, (size_t) n * 16, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(d_time, time, (size_t) n * 8, cudaMemcpyHostToDevice, s));
+    }
+    if ((rc = upload_ins(ctx, ins_t, ins_p, ins_q, w))) return rc;
+    return process_core(ctx, frame_id, d_xyzi, d_time, nullptr, n, ctx->d_ins, ctx->d_ins + w, ctx->d_ins + 4 * (size_t) w,
+                        w, pose_b_l, stamp, td, out);
+}
+
+int fflins_frame_process_aos(fflins_ctx *ctx, uint64_t frame_id, const void *points32, int32_t n, const double *ins_t,
+                             const double *ins_p, const double *ins_q, int32_t w, const fflins_pose *pose_b_l,
+                             double stamp, double td, fflins_frame_info *out) {
+    if (!ctx) return FFLINS_E_INVALID;
+    REQUIRE(n >= 0 && (n == 0 || points32) && ins_t && ins_p && ins_q && pose_b_l, "null argument");
+    int rc;
+    if ((rc = check_window(ctx, ins_t, w))) return rc;
+    if ((rc = ensure_stage(ctx, (size_t) std::max(n, 1) * 32))) return rc;
+    cudaStream_t s = ctx->stream;
+    if (n > 0) CK(cudaMemcpyAsync(ctx->d_stage, points32, (size_t) n * 32, cudaMemcpyHostToDevice, s));
+    if ((rc = upload_ins(ctx, ins_t, ins_p, ins_q, w))) return rc;
+    return process_core(ctx, frame_id, nullptr, nullptr, ctx->d_stage, n, ctx->d_ins, ctx->d_ins + w,
+                        ctx->d_ins + 4 * (size_t) w, w, pose_b_l, stamp, td, out);
+}
+
+int fflins_frame_process_dev(fflins_ctx *ctx, uint64_t frame_id, const float *d_xyzi, const double *d_time, int32_t n,
+                             const double *d_ins_t, const double *d_ins_p, const double *d_ins_q, int32_t w,
+                             const fflins_pose *pose_b_l, double stamp, double td, fflins_frame_info *out) {
+    if (!ctx) return FFLINS_E_INVALID;
+    REQUIRE(n >= 0 && (n == 0 || (d_xyzi && d_time)) && d_ins_t && d_ins_p && d_ins_q && pose_b_l, "null argument");
+    REQUIRE(w >= 2 && w <= 65536, "INS window must hold 2..65536 entries");
+    return process_core(ctx, frame_id, (const float4 *) d_xyzi, d_time, nullptr, n, d_ins_t, d_ins_p, d_ins_q, w, pose_b_l,
+                        stamp, td, out);
+}
+
+int fflins_frame_process_static(fflins_ctx *ctx, uint64_t frame_id, const float *xyzi, int32_t n, const double state_p[3],
+                                const double state_q[4], const fflins_pose *pose_b_l, fflins_frame_info *out) {
+    if (!ctx) return FFLINS_E_INVALID;
+    REQUIRE(n >= 0 && (n == 0 || xyzi) && state_p && state_q && pose_b_l, "null argument");
+    cudaStream_t s = ctx->stream;
+    Frame *f       = get_frame(ctx, frame_id);
+    const int F    = ctx->cfg.point_filter_num;
+    const int ndec = (n + F - 1) / F;
+    int rc;
+    if ((rc = ensure_cloud(ctx, f->c[FFLINS_CLOUD_MAP_FULL], n))) return rc;
+    if ((rc = ensure_cloud(ctx, f->c[FFLINS_CLOUD_LIDAR_FULL], ndec))) return rc;
+    if ((rc = ensure_cloud(ctx, f->c[FFLINS_CLOUD_LIDAR], ndec))) return rc;
+    if ((rc = ensure_cloud(ctx, f->c[FFLINS_CLOUD_WORLD], ndec))) return rc;
+    if ((rc = ensure_stage(ctx, (size_t) std::max(n, 1) * 16))) return rc;
+    // MISC::stateToPoseWithExtrinsic (misc.cc:99-105), host fp64
+    {
+        Q4 q{state_q[0], state_q[1], state_q[2], state_q[3]};
+        M3 R = quat_to_R(q);
+        for (int i = 0; i < 3; i++)
+            f->pose.t[i] = state_p[i] + ((R.m[3 * i] * pose_b_l->t[0] + R.m[3 * i + 1] * pose_b_l->t[1]) + R.m[3 * i + 2] * pose_b_l->t[2]);
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++)
+                f->pose.R[3 * i + j] = (R.m[3 * i] * pose_b_l->R[j] + R.m[3 * i + 1] * pose_b_l->R[3 + j]) + R.m[3 * i + 2] * pose_b_l->R[6 + j];
+    }
+    CK(cudaMemsetAsync(ctx->d_counters, 0, 4 * sizeof(int), s));
+    if (n > 0) {
+        CK(cudaMemcpyAsync(ctx->d_stage, xyzi, (size_t) n * 16, cudaMemcpyHostToDevice, s));
+        ProfScope ps(ctx->prof(), "copy_decimate", s);
+        launch_copy_decimate(s, (const float4 *) ctx->d_stage, n, F, f->c[FFLINS_CLOUD_MAP_FULL].d,
+                             f->c[FFLINS_CLOUD_LIDAR_FULL].d);
+        ctx->launches++;
+    }
+    return frame_tail(ctx, f, n, ndec, false, out);
+}
+
+int fflins_frame_info_get(fflins_ctx *ctx, uint64_t frame_id, fflins_frame_info *out) {
+    if (!ctx || !out) return FFLINS_E_INVALID;
+    Frame *f = find_frame(ctx, frame_id);
+    if (!f) return fail(ctx, FFLINS_E_NOTFOUND, "unknown frame");
+    fill_info(f, out);
+    return FFLINS_OK;
+}
+
+int fflins_frame_download(fflins_ctx *ctx, uint64_t frame_id, int which, float *xyzi, int32_t cap, int32_t *n) {
+    if (!ctx) return FFLINS_E_INVALID;
+    REQUIRE(which >= 0 && which < 5, "bad cloud selector");
+    Frame *f = find_frame(ctx, frame_id);
+    if (!f) return fail(ctx, FFLINS_E_NOTFOUND, "unknown frame");
+    const Cloud &c = f->c[which];
+    if (n) *n = c.n;
+    if (!xyzi) return FFLINS_OK;
+    if (cap < c.n) return fail(ctx, FFLINS_E_CAPACITY, "output buffer too small");
+    if (c.n > 0) {
+        CK(cudaMemcpyAsync(xyzi, c.d, (size_t) c.n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return FFLINS_OK;
+}
+
+int fflins_frame_upload(fflins_ctx *ctx, uint64_t frame_id, int which, const float *xyzi, int32_t n) {
+    if (!ctx) return FFLINS_E_INVALID;
+    REQUIRE(which >= 0 && which < 5 && n >= 0 && (n == 0 || xyzi), "bad argument");
+    Frame *f = get_frame(ctx, frame_id);
+    int rc;
+    if ((rc = ensure_cloud(ctx, f->c[which], n))) return rc;
+    if (n > 0) {
+        CK(cudaMemcpyAsync(f->c[which].d, xyzi, (size_t) n * 16, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    f->c[which].n = n;
+    if (which == FFLINS_CLOUD_MAP_FULL) f->n_raw = n;
+    return FFLINS_OK;
+}
+
+int fflins_frame_set_pose(fflins_ctx *ctx, uint64_t frame_id, const fflins_pose *pose) {
+    if (!ctx || !pose) return FFLINS_E_INVALID;
+    Frame *f = get_frame(ctx, frame_id);
+    f->pose  = *pose;
+    return FFLINS_OK;
+}
+
+int fflins_frame_get_pose(fflins_ctx *ctx, uint64_t frame_id, fflins_pose *pose) {
+    if (!ctx || !pose) return FFLINS_E_INVALID;
+    Frame *f = find_frame(ctx, frame_id);
+    if (!f) return fail(ctx, FFLINS_E_NOTFOUND, "unknown frame");
+    *pose = f->pose;
+    return FFLINS_OK;
+}
+
+int fflins_frame_set_motion(fflins_ctx *ctx, uint64_t frame_id, const double v[3], const double omega[3], double td) {
+    if (!ctx || !v || !omega) return FFLINS_E_INVALID;
+    Frame *f = get_frame(ctx, frame_id);
+    std::memcpy(f->v, v, sizeof(f->v));
+    std::memcpy(f->w, omega, sizeof(f->w));
+    f->td = td;
+    return FFLINS_OK;
+}
+
+int fflins_frame_release(fflins_ctx *ctx, uint64_t frame_id) {
+    if (!ctx) return FFLINS_E_INVALID;
+    auto it = ctx->frames.find(frame_id);
+    if (it == ctx->frames.end()) return fail(ctx, FFLINS_E_NOTFOUND, "unknown frame");
+    for (auto k : ctx->keyframes)
+        if (k == frame_id) return fail(ctx, FFLINS_E_INVALID, "frame is a keyframe: remove it from the window first");
+    CK(cudaStreamSynchronize(ctx->stream));
+    free_frame(ctx, it->second);
+    ctx->frames.erase(it);
+    return FFLINS_OK;
+}
+
+int fflins_reproject(fflins_ctx *ctx, uint64_t frame_id, const fflins_pose *pose) {
+    if (!ctx || !pose) return FFLINS_E_INVALID;
+    Frame *f = find_frame(ctx, frame_id);
+    if (!f) return fail(ctx, FFLINS_E_NOTFOUND, "unknown frame");
+    f->pose = *pose;
+    int n   = f->c[FFLINS_CLOUD_LIDAR].n;
+    int rc;
+    if ((rc = ensure_cloud(ctx, f->c[FFLINS_CLOUD_WORLD], n))) return rc;
+    {
+        ProfScope ps(ctx->prof(), "reproject", ctx->stream);
+        launch_project(ctx->stream, to12(*pose), f->c[FFLINS_CLOUD_LIDAR].d, f->c[FFLINS_CLOUD_WORLD].d, n, nullptr);
+        if (n > 0) ctx->launches++;
+    }
+    f->c[FFLINS_CLOUD_WORLD].n = n;
+    return FFLINS_OK;
+}
+
+int fflins_keyframe_selection(fflins_ctx *ctx, uint64_t frame_id, double frame_stamp, double last_key_stamp,
+                              int *is_keyframe, double stats[3]) {
+    if (!ctx || !is_keyframe) return FFLINS_E_INVALID;
+    Frame *f = find_frame(ctx, frame_id);
+    if (!f) return fail(ctx, FFLINS_E_NOTFOUND, "unknown frame");
+    REQUIRE(!ctx->keyframes.empty(), "no keyframe in the window");
+    Frame *k = find_frame(ctx, ctx->keyframes.back());
+    // lidar_map.cc:77-98: interval, translation, rotation angle of R_f^T R_k
+    double interval = frame_stamp - last_key_stamp;
+    double dt[3]    = {f->pose.t[0] - k->pose.t[0], f->pose.t[1] - k->pose.t[1], f->pose.t[2] - k->pose.t[2]};
+    double trans    = std::sqrt(dt[0] * dt[0] + dt[1] * dt[1] + dt[2] * dt[2]);
+    double Rr[9];
+    mat_tn(f->pose.R, k->pose.R, Rr);
+    // AngleAxisd(R): via quaternion; angle = 2 atan2(|vec|, |w|)
+    double tr = Rr[0] + Rr[4] + Rr[8];
+    double vx = Rr[7] - Rr[5], vy = Rr[2] - Rr[6], vz = Rr[3] - Rr[1];
+    double sn = 0.5 * std::sqrt(vx * vx + vy * vy + vz * vz), cs = 0.5 * (tr - 1.0);
+    double rot = std::fabs(std::atan2(sn, cs));
+    if (stats) {
+        stats[0] = interval;
+        stats[1] = trans;
+        stats[2] = rot;
+    }
+    *is_keyframe = (interval > ctx->cfg.max_keyframe_interval) || (trans > ctx->cfg.minimum_keyframe_translation) ||
+                   (rot > ctx->cfg.min_keyframe_rotation);
+    return FFLINS_OK;
+}
+
+int fflins_voxel_downsample(fflins_ctx *ctx, const float *xyzi, int32_t n, double leaf, float *out_xyzi, int32_t cap,
+                            int32_t *n_out, int32_t *keys) {
+    if (!ctx) return FFLINS_E_INVALID;
+    REQUIRE(n >= 0 && (n == 0 || xyzi) && n_out && leaf > 0, "bad argument");
+    if (n == 0) {
+        *n_out = 0;
+        return FFLINS_OK;
+    }
+    int rc;
+    if ((rc = ensure_voxel(ctx, n))) return rc;
+    cudaStream_t s = ctx->stream;
+    float4 *d_in   = (float4 *) ctx->pool.alloc((size_t) n * 16);
+    float4 *d_out  = (float4 *) ctx->pool.alloc((size_t) n * 16);
+    int32_t *d_keys = keys ? (int32_t *) ctx->pool.alloc((size_t) n * 4) : nullptr;
+    auto cleanup = [&]() {
+        ctx->pool.release(d_in);
+        ctx->pool.release(d_out);
+        ctx->pool.release(d_keys);
+    };
+    if (!d_in || !d_out || (keys && !d_keys)) {
+        cleanup();
+        return fail(ctx, FFLINS_E_NOMEM, "device allocation failed");
+    }
+    cudaMemcpyAsync(d_in, xyzi, (size_t) n * 16, cudaMemcpyHostToDevice, s);
+    launch_voxel_downsample(s, ctx->vox, d_in, n, (float) leaf, d_out, ctx->d_counters + 2, d_keys, &ctx->launches,
+                            ctx->prof(), "voxel");
+    int m = 0;
+    cudaMemcpyAsync(&m, ctx->d_counters + 2, sizeof(int), cudaMemcpyDeviceToHost, s);
+    if (keys) cudaMemcpyAsync(keys, d_keys, (size_t) n * 4, cudaMemcpyDeviceToHost, s);
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) {
+        cleanup();
+        return fail(ctx, FFLINS_E_CUDA, cudaGetErrorString(e));
+    }
+    *n_out = m;
+    if (out_xyzi) {
+        if (cap < m) {
+            cleanup();
+            return fail(ctx, FFLINS_E_CAPACITY, "output buffer too small");
+        }
+        cudaMemcpyAsync(out_xyzi, d_out, (size_t) m * 16, cudaMemcpyDeviceToHost, s);
+        e = cudaStreamSynchronize(s);
+    }
+    cleanup();
+    if (e != cudaSuccess) return fail(ctx, FFLINS_E_CUDA, cudaGetErrorString(e));
+    return FFLINS_OK;
+}
+
+int fflins_cloud_projection(fflins_ctx *ctx, const fflins_pose *pose, const float *src, int32_t n, float *dst) {
+    if (!ctx) return FFLINS_E_INVALID;
+    REQUIRE(pose && n >= 0 && (n == 0 || (src && dst)), "bad argument");
+    if (n == 0) return FFLINS_OK;
+    cudaStream_t s = ctx->stream;
+    float4 *d      = (float4 *) ctx->pool.alloc((size_t) n * 16);
+    if (!d) return fail(ctx, FFLINS_E_NOMEM, "device allocation failed");
+    cudaMemcpyAsync(d, src, (size_t) n * 16, cudaMemcpyHostToDevice, s);
+    launch_project(s, to12(*pose), d, d, n, nullptr);
+    ctx->launches++;
+    cudaMemcpyAsync(dst, d, (size_t) n * 16, cudaMemcpyDeviceToHost, s);
+    cudaError_t e = cudaStreamSynchronize(s);
+    ctx->pool.release(d);
+    if (e != cudaSuccess) return fail(ctx, FFLINS_E_CUDA, cudaGetErrorString(e));
+    return FFLINS_OK;
+}
+
+int fflins_plane_estimation(fflins_ctx *ctx, const float *pts, int32_t n, double threshold, double *unit_normal,
+                            double *norm_inverse, double *distance, uint8_t *is_plane) {
+    if (!ctx) return FFLINS_E_INVALID;
+    REQUIRE(n >= 0 && (n == 0 || (pts && unit_normal && norm_inverse && distance && is_plane)), "bad argument");
+    if (n == 0) return FFLINS_OK;
+    cudaStream_t s = ctx->stream;
+    size_t bytes   = (size_t) n * (80 + 24 + 8 + 40 + 8);
+    char *d        = (char *) ctx->pool.alloc(bytes);
+    if (!d) return fail(ctx, FFLINS_E_NOMEM, "device allocation failed");
+    float4 *d_pts  = (float4 *) d;
+    double *d_unit = (double *) (d + (size_t) n * 80);
+    double *d_ninv = d_unit + 3 * (size_t) n;
+    double *d_dist = d_ninv + n;
+    uint8_t *d_ok  = (uint8_t *) (d_dist + 5 * (size_t) n);
+    cudaMemcpyAsync(d_pts, pts, (size_t) n * 80, cudaMemcpyHostToDevice, s);
+    launch_plane_estimation(s, d_pts, n, threshold, d_unit, d_ninv, d_dist, d_ok);
+    ctx->launches++;
+    cudaMemcpyAsync(unit_normal, d_unit, (size_t) n * 24, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(norm_inverse, d_ninv, (size_t) n * 8, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(distance, d_dist, (size_t) n * 40, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(is_plane, d_ok, (size_t) n, cudaMemcpyDeviceToHost, s);
+    cudaError_t e = cudaStreamSynchronize(s);
+    ctx->pool.release(d);
+    if (e != cudaSuccess) return fail(ctx, FFLINS_E_CUDA, cudaGetErrorString(e));
+    return FFLINS_OK;
+}
+
+int fflins_knn5(fflins_ctx *ctx, const float *map_xyzi, int32_t m, const float *query_xyzi, int32_t q, double max_dist,
+                int32_t *nn_idx, float *nn_d2, int32_t *nn_count) {
+    if (!ctx) return FFLINS_E_INVALID;
+    REQUIRE(m >= 0 && q >= 0 && (m == 0 || map_xyzi) && (q == 0 || (query_xyzi && nn_idx && nn_d2 && nn_count)) && max_dist > 0,
+            "bad argument");
+    if (q == 0) return FFLINS_OK;
+    cudaStream_t s = ctx->stream;
+    int hcap       = next_pow2(2 * std::max(m, 1));
+    float4 *d_map  = (float4 *) ctx->pool.alloc((size_t) std::max(m, 1) * 16);
+    float4 *d_q    = (float4 *) ctx->pool.alloc((size_t) q * 16);
+    unsigned long long *hk = (unsigned long long *) ctx->pool.alloc((size_t) hcap * 8);
+    int *hv        = (int *) ctx->pool.alloc((size_t) hcap * 4);
+    int32_t *d_idx = (int32_t *) ctx->pool.alloc((size_t) q * 20);
+    float *d_d2    = (float *) ctx->pool.alloc((size_t) q * 20);
+    int32_t *d_cnt = (int32_t *) ctx->pool.alloc((size_t) q * 4);
+    auto cleanup = [&]() {
+        ctx->pool.release(d_map);
+        ctx->pool.release(d_q);
+        ctx->pool.release(hk);
+        ctx->pool.release(hv);
+        ctx->pool.release(d_idx);
+        ctx->pool.release(d_d2);
+        ctx->pool.release(d_cnt);
+    };
+    if (!d_map || !d_q || !hk || !hv || !d_idx || !d_d2 || !d_cnt) {
+        cleanup();
+        return fail(ctx, FFLINS_E_NOMEM, "device allocation failed");
+    }
+    if (m > 0) cudaMemcpyAsync(d_map, map_xyzi, (size_t) m * 16, cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(d_q, query_xyzi, (size_t) q * 16, cudaMemcpyHostToDevice, s);
+    float cell = search_cell(ctx);
+    launch_hash_build(s, d_map, m, 1.0f / cell, hk, hv, hcap);
+    launch_knn5(s, d_map, hk, hv, hcap - 1, m, d_q, q, 1.0f / cell, cell, (int) std::ceil(max_dist / cell) + 1,
+                (float) (max_dist * max_dist), d_idx, d_d2, d_cnt);
+    ctx->launches += 3;
+    cudaMemcpyAsync(nn_idx, d_idx, (size_t) q * 20, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(nn_d2, d_d2, (size_t) q * 20, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(nn_count, d_cnt, (size_t) q * 4, cudaMemcpyDeviceToHost, s);
+    cudaError_t e = cudaStreamSynchronize(s);
+    cleanup();
+    if (e != cudaSuccess) return fail(ctx, FFLINS_E_CUDA, cudaGetErrorString(e));
+    return FFLINS_OK;
+}
+
+int fflins_keyframe_merge(fflins_ctx *ctx, uint64_t key_id, const uint64_t *nonkey_ids, int32_t n, fflins_frame_info *out) {
+    if (!ctx) return FFLINS_E_INVALID;
+    REQUIRE(n >= 0 && (n == 0 || nonkey_ids), "bad argument");
+    Frame *key = find_frame(ctx, key_id);
+    if (!key) return fail(ctx, FFLINS_E_NOTFOUND, "unknown keyframe");
+    cudaStream_t s = ctx->stream;
+    int total      = key->c[FFLINS_CLOUD_MAP_FULL].n;
+    std::vector<Frame *> nk(n);
+    for (int i = 0; i < n; i++) {
+        nk[i] = find_frame(ctx, nonkey_ids[i]);
+        if (!nk[i]) return fail(ctx, FFLINS_E_NOTFOUND, "unknown non-keyframe");
+        total += nk[i]->c[FFLINS_CLOUD_MAP_FULL].n;
+    }
+    int rc;
+    if ((rc = ensure_cloud(ctx, key->c[FFLINS_CLOUD_MAP_FULL], total, true))) return rc;
+    if ((rc = ensure_cloud(ctx, key->c[FFLINS_CLOUD_MAP], total))) return rc;
+    if ((rc = ensure_voxel(ctx, total))) return rc;
+    int off = key->c[FFLINS_CLOUD_MAP_FULL].n;
+    for (int i = 0; i < n; i++) {
+        // relative pose non-keyframe -> keyframe (lidar_map.cc:198-199); the projected cloud is written
+        // straight behind the keyframe's own points (the reference projects in place, then appends: :201-205)
+        Pose12 T;
+        mat_tn(key->pose.R, nk[i]->pose.R, T.R);
+        double dt[3] = {nk[i]->pose.t[0] - key->pose.t[0], nk[i]->pose.t[1] - key->pose.t[1], nk[i]->pose.t[2] - key->pose.t[2]};
+        mat_tv(key->pose.R, dt, T.t);
+        int m = nk[i]->c[FFLINS_CLOUD_MAP_FULL].n;
+        ProfScope ps(ctx->prof(), "merge_project", s);
+        launch_project(s, T, nk[i]->c[FFLINS_CLOUD_MAP_FULL].d, key->c[FFLINS_CLOUD_MAP_FULL].d + off, m, nullptr);
+        if (m > 0) ctx->launches++;
+        off += m;
+    }
+    key->c[FFLINS_CLOUD_MAP_FULL].n = total;
+    launch_voxel_downsample(s, ctx->vox, key->c[FFLINS_CLOUD_MAP_FULL].d, total, (float) ctx->cfg.downsample_size,
+                            key->c[FFLINS_CLOUD_MAP].d, ctx->d_counters + 3, nullptr, &ctx->launches, ctx->prof(),
+                            "voxel_map");
+    unsigned char *h = pin(ctx, 64);
+    if (!h) return fail(ctx, FFLINS_E_NOMEM, "pinned allocation failed");
+    CK(cudaMemcpyAsync(h, ctx->d_counters + 3, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    int m;
+    std::memcpy(&m, h, sizeof(int));
+    key->c[FFLINS_CLOUD_MAP].n = m;
+    fill_info(key, out);
+    return FFLINS_OK;
+}
+
+int fflins_keyframe_add(fflins_ctx *ctx, uint64_t key_id) {
+    if (!ctx) return FFLINS_E_INVALID;
+    Frame *f = find_frame(ctx, key_id);
+    if (!f) return fail(ctx, FFLINS_E_NOTFOUND, "unknown frame");
+    REQUIRE((int) ctx->keyframes.size() < kMaxRefs, "keyframe window is full");
+    int rc;
+    if ((rc = build_hash(ctx, f))) return rc;
+    f->is_key = true;
+    ctx->keyframes.push_back(key_id);
+    return FFLINS_OK;
+}
+
+static int remove_key(fflins_ctx *ctx, bool oldest, uint64_t *removed_id) {
+    REQUIRE(!ctx->keyframes.empty(), "no keyframe in the window");
+    uint64_t id = oldest ? ctx->keyframes.front() : ctx->keyframes.back();
+    if (oldest)
+        ctx->keyframes.pop_front();
+    else
+        ctx->keyframes.pop_back();
+    if (removed_id) *removed_id = id;
+    auto it = ctx->frames.find(id);
+    if (it != ctx->frames.end()) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        free_frame(ctx, it->second);
+        ctx->frames.erase(it);
+    }
+    return FFLINS_OK;
+}
+
+int fflins_keyframe_remove_oldest(fflins_ctx *ctx, uint64_t *removed_id) {
+    if (!ctx) return FFLINS_E_INVALID;
+    return remove_key(ctx, true, removed_id);
+}
+int fflins_keyframe_remove_newest(fflins_ctx *ctx, uint64_t *removed_id) {
+    if (!ctx) return FFLINS_E_INVALID;
+    return remove_key(ctx, false, removed_id);
+}
+int fflins_keyframe_count(fflins_ctx *ctx, int32_t *n) {
+    if (!ctx || !n) return FFLINS_E_INVALID;
+    *n = (int32_t) ctx->keyframes.size();
+    return FFLINS_OK;
+}
+int fflins_keyframe_ids(fflins_ctx *ctx, uint64_t *ids, int32_t cap, int32_t *n) {
+    if (!ctx || !n) return FFLINS_E_INVALID;
+    *n = (int32_t) ctx->keyframes.size();
+    if (ids) {
+        if (cap < *n) return fail(ctx, FFLINS_E_CAPACITY, "output buffer too small");
+        for (size_t i = 0; i < ctx->keyframes.size(); i++) ids[i] = ctx->keyframes[i];
+    }
+    return FFLINS_OK;
+}
+
+int fflins_associate(fflins_ctx *ctx, fflins_assoc_stats *out) {
+    if (!ctx) return FFLINS_E_INVALID;
+    REQUIRE(ctx->keyframes.size() >= 1, "no keyframe in the window");
+    Frame *cur = find_frame(ctx, ctx->keyframes.back());
+    std::vector<Frame *> refs;
+    for (size_t i = 0; i + 1 < ctx->keyframes.size(); i++) refs.push_back(find_frame(ctx, ctx->keyframes[i]));
+    int32_t nf[kMaxRefs] = {0}, nc[kMaxRefs] = {0};
+    int rc = run_associate(ctx, refs, cur, nf, nc);
+    if (rc) return rc;
+    if (out) {
+        std::memset(out, 0, sizeof(*out));
+        out->n_refs    = (int32_t) refs.size();
+        out->n_queries = cur->c[FFLINS_CLOUD_LIDAR].n;
+        for (size_t i = 0; i < refs.size(); i++) {
+            out->num_features[i] = nf[i];
+            out->num_covered[i]  = nc[i];
+            out->ref_ids[i]      = refs[i]->id;
+        }
+    }
+    return FFLINS_OK;
+}
+
+int fflins_associate_pair(fflins_ctx *ctx, uint64_t ref_id, uint64_t cur_id, int32_t *num_features, int32_t *num_covered) {
+    if (!ctx) return FFLINS_E_INVALID;
+    Frame *ref = find_frame(ctx, ref_id), *cur = find_frame(ctx, cur_id);
+    if (!ref || !cur) return fail(ctx, FFLINS_E_NOTFOUND, "unknown frame");
+    int rc;
+    if (!ref->hkeys || ref->hcap < next_pow2(2 * std::max(ref->c[FFLINS_CLOUD_MAP].n, 1)))
+        if ((rc = build_hash(ctx, ref))) return rc;
+    int32_t nf[kMaxRefs] = {0}, nc[kMaxRefs] = {0};
+    std::vector<Frame *> refs{ref};
+    rc = run_associate(ctx, refs, cur, nf, nc);
+    if (rc) return rc;
+    if (num_features) *num_features = nf[0];
+    if (num_covered) *num_covered = nc[0];
+    return FFLINS_OK;
+}
+
+int fflins_features_download(fflins_ctx *ctx, uint64_t ref_id, int32_t cap, int32_t *q, int8_t *type, uint8_t *covered,
+                             uint8_t *outlier, int32_t *nn_idx, float *nn_d2, float *nn_points, double *unit_normal,
+                             double *norm_inverse) {
+    if (!ctx) return FFLINS_E_INVALID;
+    Frame *r = find_frame(ctx, ref_id);
+    if (!r) return fail(ctx, FFLINS_E_NOTFOUND, "unknown frame");
+    int n = r->feat_q;
+    if (q) *q = n;
+    if (!(type || covered || outlier || nn_idx || nn_d2 || nn_points || unit_normal || norm_inverse)) return FFLINS_OK;
+    if (cap < n) return fail(ctx, FFLINS_E_CAPACITY, "output buffer too small");
+    if (n == 0) return FFLINS_OK;
+    cudaStream_t s = ctx->stream;
+    std::vector<int32_t> idx_tmp;
+    if (nn_points && !nn_idx) {
+        idx_tmp.resize((size_t) 5 * n);
+        nn_idx = idx_tmp.data();
+    }
+    if (type) CK(cudaMemcpyAsync(type, r->feat.type, n, cudaMemcpyDeviceToHost, s));
+    if (covered) CK(cudaMemcpyAsync(covered, r->feat.covered, n, cudaMemcpyDeviceToHost, s));
+    if (outlier) CK(cudaMemcpyAsync(outlier, r->feat.outlier, n, cudaMemcpyDeviceToHost, s));
+    if (nn_idx) CK(cudaMemcpyAsync(nn_idx, r->feat.nn_idx, (size_t) n * 20, cudaMemcpyDeviceToHost, s));
+    if (nn_d2) CK(cudaMemcpyAsync(nn_d2, r->feat.nn_d2, (size_t) n * 20, cudaMemcpyDeviceToHost, s));
+    if (unit_normal) CK(cudaMemcpyAsync(unit_normal, r->feat.normal, (size_t) n * 24, cudaMemcpyDeviceToHost, s));
+    if (norm_inverse) CK(cudaMemcpyAsync(norm_inverse, r->feat.d, (size_t) n * 8, cudaMemcpyDeviceToHost, s));
+    std::vector<float> map;
+    if (nn_points) {
+        map.resize((size_t) 4 * std::max(r->c[FFLINS_CLOUD_MAP].n, 1));
+        if (r->c[FFLINS_CLOUD_MAP].n > 0)
+            CK(cudaMemcpyAsync(map.data(), r->c[FFLINS_CLOUD_MAP].d, (size_t) r->c[FFLINS_CLOUD_MAP].n * 16, cudaMemcpyDeviceToHost, s));
+    }
+    CK(cudaStreamSynchronize(s));
+    if (nn_points) {
+        for (size_t i = 0; i < (size_t) 5 * n; i++) {
+            int id = nn_idx[i];
+            if (id >= 0)
+                std::memcpy(nn_points + 4 * i, map.data() + 4 * (size_t) id, 16);
+            else
+                std::memset(nn_points + 4 * i, 0, 16);
+        }
+    }
+    return FFLINS_OK;
+}
+
+int fflins_features_set_outlier(fflins_ctx *ctx, uint64_t ref_id, const uint8_t *outlier, int32_t q) {
+    if (!ctx || !outlier) return FFLINS_E_INVALID;
+    Frame *r = find_frame(ctx, ref_id);
+    if (!r) return fail(ctx, FFLINS_E_NOTFOUND, "unknown frame");
+    REQUIRE(q == r->feat_q, "feature count mismatch");
+    if (q > 0) {
+        CK(cudaMemcpyAsync(r->feat.outlier, outlier, q, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return FFLINS_OK;
+}
+
+int fflins_factor_eval_batch(fflins_ctx *ctx, int32_t n, const float *point, const double *unit_normal,
+                             const double *norm_inverse, const double *std, const double motion[14],
+                             const double pose_ref[7], const double pose_cur[7], const double ext[7], double td,
+                             uint32_t flags, double *r, double *J) {
+    if (!ctx) return FFLINS_E_INVALID;
+    REQUIRE(n >= 0 && (n == 0 || (point && unit_normal && norm_inverse && std)) && motion && pose_ref && pose_cur && ext,
+            "bad argument");
+    if (n == 0) return FFLINS_OK;
+    cudaStream_t s = ctx->stream;
+    size_t bytes   = (size_t) n * (12 + 24 + 8 + 8 + 8 + 176) + 1024;
+    char *d        = (char *) ctx->pool.alloc(bytes);
+    if (!d) return fail(ctx, FFLINS_E_NOMEM, "device allocation failed");
+    double *d_n   = (double *) d;
+    double *d_d   = d_n + 3 * (size_t) n;
+    double *d_std = d_d + n;
+    double *d_r   = d_std + n;
+    double *d_J   = d_r + n;
+    float *d_p    = (float *) (d_J + 22 * (size_t) n);
+    cudaMemcpyAsync(d_n, unit_normal, (size_t) n * 24, cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(d_d, norm_inverse, (size_t) n * 8, cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(d_std, std, (size_t) n * 8, cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(d_p, point, (size_t) n * 12, cudaMemcpyHostToDevice, s);
+    FactorParams P{};
+    P.n_pairs = 1;
+    P.q       = n;
+    P.flags   = flags;
+    std::memcpy(P.pose_cur, pose_cur, 56);
+    std::memcpy(P.ext, ext, 56);
+    P.td = td;
+    std::memcpy(P.pair[0].pose_ref, pose_ref, 56);
+    std::memcpy(P.pair[0].v0, motion, 24);
+    std::memcpy(P.pair[0].w0, motion + 3, 24);
+    P.pair[0].td0 = motion[6];
+    std::memcpy(P.v1, motion + 7, 24);
+    std::memcpy(P.w1, motion + 10, 24);
+    P.td1            = motion[13];
+    P.sigma          = ctx->cfg.point_to_plane_std;
+    P.huber_delta    = ctx->cfg.huber_delta;
+    P.pair[0].type   = nullptr;
+    P.pair[0].outlier = nullptr;
+    P.pair[0].normal = d_n;
+    P.pair[0].d      = d_d;
+    P.pair[0].std    = d_std;
+    launch_factor_eval(s, P, d_p, 0, r ? d_r : nullptr, J ? d_J : nullptr, nullptr, nullptr, nullptr, ctx->d_tickets);
+    ctx->launches++;
+    if (r) cudaMemcpyAsync(r, d_r, (size_t) n * 8, cudaMemcpyDeviceToHost, s);
+    if (J) cudaMemcpyAsync(J, d_J, (size_t) n * 176, cudaMemcpyDeviceToHost, s);
+    cudaError_t e = cudaStreamSynchronize(s);
+    ctx->pool.release(d);
+    if (e != cudaSuccess) return fail(ctx, FFLINS_E_CUDA, cudaGetErrorString(e));
+    return FFLINS_OK;
+}
+
+int fflins_factor_eval(fflins_ctx *ctx, uint64_t ref_id, uint64_t cur_id, const double pose_ref[7], const double pose_cur[7],
+                       const double ext[7], double td, uint32_t flags, int32_t cap, int32_t *n_res, uint8_t *valid,
+                       double *r, double *J, double *H, double *b, double *cost) {
+    if (!ctx) return FFLINS_E_INVALID;
+    REQUIRE(pose_ref && pose_cur && ext, "bad argument");
+    Frame *cur = find_frame(ctx, cur_id);
+    if (!cur) return fail(ctx, FFLINS_E_NOTFOUND, "unknown cur frame");
+    FactorParams P{};
+    int rc;
+    if ((rc = fill_factor_pairs(ctx, P, 1, &ref_id, pose_ref, cur, pose_cur, ext, td, flags))) return rc;
+    const int q = P.q;
+    if ((valid || r || J) && cap < q) return fail(ctx, FFLINS_E_CAPACITY, "output buffer too small");
+    cudaStream_t s = ctx->stream;
+    if (q == 0) {
+        if (n_res) *n_res = 0;
+        if (H) std::memset(H, 0, 361 * 8);
+        if (b) std::memset(b, 0, 19 * 8);
+        if (cost) cost[0] = cost[1] = 0;
+        return FFLINS_OK;
+    }
+    if ((rc = ensure_factor_scratch(ctx, 1, q))) return rc;
+    char *d = nullptr;
+    double *d_r = nullptr, *d_J = nullptr;
+    uint8_t *d_valid = nullptr;
+    if (valid || r || J) {
+        d = (char *) ctx->pool.alloc((size_t) q * (8 + 176 + 1) + 256);
+        if (!d) return fail(ctx, FFLINS_E_NOMEM, "device allocation failed");
+        d_r     = (double *) d;
+        d_J     = d_r + q;
+        d_valid = (uint8_t *) (d_J + 22 * (size_t) q);
+    }
+    {
+        ProfScope ps(ctx->prof(), "factor_eval", s);
+        launch_factor_eval(s, P, (const float *) cur->c[FFLINS_CLOUD_LIDAR].d, 1, r ? d_r : nullptr, J ? d_J : nullptr,
+                           valid ? d_valid : nullptr, ctx->d_partial, ctx->d_red, ctx->d_tickets);
+        ctx->launches++;
+    }
+    unsigned char *h = pin(ctx, kRedSize * 8);
+    if (!h) {
+        ctx->pool.release(d);
+        return fail(ctx, FFLINS_E_NOMEM, "pinned allocation failed");
+    }
+    cudaMemcpyAsync(h, ctx->d_red, kRedSize * 8, cudaMemcpyDeviceToHost, s);
+    if (r) cudaMemcpyAsync(r, d_r, (size_t) q * 8, cudaMemcpyDeviceToHost, s);
+    if (J) cudaMemcpyAsync(J, d_J, (size_t) q * 176, cudaMemcpyDeviceToHost, s);
+    if (valid) cudaMemcpyAsync(valid, d_valid, (size_t) q, cudaMemcpyDeviceToHost, s);
+    cudaError_t e = cudaStreamSynchronize(s);
+    ctx->pool.release(d);
+    if (e != cudaSuccess) return fail(ctx, FFLINS_E_CUDA, cudaGetErrorString(e));
+    unpack_red((const double *) h, H, b, cost, n_res);
+    return FFLINS_OK;
+}
+
+int fflins_window_eval(fflins_ctx *ctx, int32_t n_pairs, const uint64_t *ref_ids, const double *pose_refs,
+                       const double pose_cur[7], const double ext[7], double td, uint32_t flags, double *H, double *b,
+                       double *cost, int32_t *n_res) {
+    if (!ctx) return FFLINS_E_INVALID;
+    REQUIRE(n_pairs >= 0 && (n_pairs == 0 || (ref_ids && pose_refs)) && pose_cur && ext, "bad argument");
+    REQUIRE(!ctx->keyframes.empty(), "no keyframe in the window");
+    if (n_pairs == 0) return FFLINS_OK;
+    Frame *cur = find_frame(ctx, ctx->keyframes.back());
+    FactorParams P{};
+    int rc;
+    if ((rc = fill_factor_pairs(ctx, P, n_pairs, ref_ids, pose_refs, cur, pose_cur, ext, td, flags))) return rc;
+    if (P.q == 0) {
+        for (int i = 0; i < n_pairs; i++) unpack_red(std::vector<double>(kRedSize, 0.0).data(), H ? H + 361 * i : nullptr,
+                                                     b ? b + 19 * i : nullptr, cost ? cost + 2 * i : nullptr, n_res ? n_res + i : nullptr);
+        return FFLINS_OK;
+    }
+    if ((rc = ensure_factor_scratch(ctx, n_pairs, P.q))) return rc;
+    cudaStream_t s = ctx->stream;
+    {
+        ProfScope ps(ctx->prof(), "factor_eval", s);
+        launch_factor_eval(s, P, (const float *) cur->c[FFLINS_CLOUD_LIDAR].d, 1, nullptr, nullptr, nullptr, ctx->d_partial,
+                           ctx->d_red, ctx->d_tickets);
+        ctx->launches++;
+    }
+    unsigned char *h = pin(ctx, (size_t) n_pairs * kRedSize * 8);
+    if (!h) return fail(ctx, FFLINS_E_NOMEM, "pinned allocation failed");
+    CK(cudaMemcpyAsync(h, ctx->d_red, (size_t) n_pairs * kRedSize * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const double *red = (const double *) h;
+    for (int i = 0; i < n_pairs; i++)
+        unpack_red(red + (size_t) i * kRedSize, H ? H + 361 * i : nullptr, b ? b + 19 * i : nullptr,
+                   cost ? cost + 2 * i : nullptr, n_res ? n_res + i : nullptr);
+    return FFLINS_OK;
+}
+
+int fflins_window_chi2(fflins_ctx *ctx, int32_t n_pairs, const uint64_t *ref_ids, const double *pose_refs,
+                       const double pose_cur[7], const double ext[7], double td, double threshold, int32_t *n_outliers) {
+    if (!ctx) return FFLINS_E_INVALID;
+    REQUIRE(n_pairs >= 0 && (n_pairs == 0 || (ref_ids && pose_refs)) && pose_cur && ext, "bad argument");
+    REQUIRE(!ctx->keyframes.empty(), "no keyframe in the window");
+    if (n_pairs == 0) return FFLINS_OK;
+    Frame *cur = find_frame(ctx, ctx->keyframes.back());
+    FactorParams P{};
+    int rc;
+    if ((rc = fill_factor_pairs(ctx, P, n_pairs, ref_ids, pose_refs, cur, pose_cur, ext, td, 0))) return rc;
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemsetAsync(ctx->d_outliers, 0, kMaxRefs * sizeof(int), s));
+    if (P.q > 0) {
+        ProfScope ps(ctx->prof(), "chi2", s);
+        launch_chi2(s, P, (const float *) cur->c[FFLINS_CLOUD_LIDAR].d, 1, threshold, ctx->d_outliers);
+        ctx->launches++;
+    }
+    unsigned char *h = pin(ctx, 256);
+    if (!h) return fail(ctx, FFLINS_E_NOMEM, "pinned allocation failed");
+    CK(cudaMemcpyAsync(h, ctx->d_outliers, n_pairs * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (n_outliers) std::memcpy(n_outliers, h, n_pairs * sizeof(int));
+    return FFLINS_OK;
+}
+
+int fflins_profile_enable(fflins_ctx *ctx, int on) {
+    if (!ctx) return FFLINS_E_INVALID;
+    if (!on && ctx->prof_on) ctx->prof_collect();
+    ctx->prof_on = on != 0;
+    return FFLINS_OK;
+}
+
+int fflins_profile_reset(fflins_ctx *ctx) {
+    if (!ctx) return FFLINS_E_INVALID;
+    ctx->prof_collect();
+    std::fill(ctx->prof_ms.begin(), ctx->prof_ms.end(), 0.0);
+    std::fill(ctx->prof_cnt.begin(), ctx->prof_cnt.end(), 0);
+    return FFLINS_OK;
+}
+
+int fflins_profile_get(fflins_ctx *ctx, char *names, int32_t names_cap, double *ms, int64_t *launches, int32_t cap,
+                       int32_t *n) {
+    if (!ctx || !n) return FFLINS_E_INVALID;
+    ctx->prof_collect();
+    *n = (int32_t) ctx->prof_names.size();
+    if (!names && !ms && !launches) return FFLINS_OK;
+    if (cap < *n) return fail(ctx, FFLINS_E_CAPACITY, "output buffer too small");
+    std::string all;
+    for (size_t i = 0; i < ctx->prof_names.size(); i++) {
+        all += ctx->prof_names[i];
+        all += '\n';
+        if (ms) ms[i] = ctx->prof_ms[i];
+        if (launches) launches[i] = ctx->prof_cnt[i];
+    }
+    if (names) {
+        if ((int32_t) all.size() + 1 > names_cap) return fail(ctx, FFLINS_E_CAPACITY, "name buffer too small");
+        std::memcpy(names, all.c_str(), all.size() + 1);
+    }
+    return FFLINS_OK;
+}
+
+int64_t fflins_launch_count(const fflins_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+} // extern "C"

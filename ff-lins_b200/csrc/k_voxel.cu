@@ -1,0 +1,406 @@
+// k_voxel.cu — K2 voxel-grid downsample: bbox -> voxel key -> stable LSD radix sort -> segmented
+// centroid, bit-exact with pcl::VoxelGrid<PointXYZI>::applyFilter as FF-LINS uses it
+// (call sites ff_lins/lidar/lidar_map.cc:71,209-210,260-261,311-312; arithmetic restated in
+// SURVEY.md Appendix A.1).
+//
+// Bit-exactness rules:
+//   - keys: int(floorf(x * inv_leaf) - float(min_b)) with a separately rounded fp32 multiply;
+//   - output order: ascending key;
+//   - centroid: fp32 accumulators walked in ASCENDING ORIGINAL INDEX (the sort is stable and
+//     carries the index as payload), one lane per voxel, then divided by float(count). A tree
+//     reduction would change the rounding, so the walk is sequential by construction.
+//
+// B200 mapping: every stage is a streaming pass over 8-byte (key, index) pairs; the digit passes
+// that the realised key width does not need exit immediately (the width is decided on the device
+// from the bounding box, the host never synchronises inside the chain).
+#include "kernels.h"
+
+#include <cfloat>
+#include <cstdio>
+
+namespace fflins {
+
+namespace {
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS   = 16;
+constexpr int RS_TILE    = RS_THREADS * RS_ITEMS; // 4096
+constexpr int RS_WARPS   = RS_THREADS / 32;
+constexpr int SEG_THREADS = 256;
+constexpr int SEG_ITEMS   = 4;
+constexpr int SEG_TILE    = SEG_THREADS * SEG_ITEMS;
+
+// meta layout (ints)
+enum { M_BBOX = 0, M_OVERFLOW = 6, M_NBITS = 7, M_NOUT = 8, M_PARITY = 9 /* 9..13 */, M_SIZE = 16 };
+
+__device__ __forceinline__ int f2ord(float f) {
+    int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+__global__ void vox_init_kernel(int *meta) {
+    int t = threadIdx.x;
+    if (t < 3) meta[M_BBOX + t] = f2ord(FLT_MAX);
+    else if (t < 6) meta[M_BBOX + t] = f2ord(-FLT_MAX);
+    else if (t < M_SIZE) meta[t] = 0;
+}
+
+__global__ void __launch_bounds__(256) vox_bbox_kernel(const float4 *__restrict__ in, int n, int *__restrict__ meta) {
+    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 p = __ldg(in + i);
+        mn[0] = fminf(mn[0], p.x); mx[0] = fmaxf(mx[0], p.x);
+        mn[1] = fminf(mn[1], p.y); mx[1] = fmaxf(mx[1], p.y);
+        mn[2] = fminf(mn[2], p.z); mx[2] = fmaxf(mx[2], p.z);
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+            mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            atomicMin(meta + M_BBOX + a, f2ord(mn[a]));
+            atomicMax(meta + M_BBOX + 3 + a, f2ord(mx[a]));
+        }
+    }
+}
+
+struct Grid3 {
+    int min_b[3];
+    int mul1, mul2;
+    bool overflow;
+    int nbits;
+};
+
+__device__ __forceinline__ Grid3 make_grid(const int *__restrict__ meta, float inv) {
+    Grid3 g;
+    float mn[3], mx[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        mn[a] = ord2f(meta[M_BBOX + a]);
+        mx[a] = ord2f(meta[M_BBOX + 3 + a]);
+    }
+    long long d[3];
+    int div_b[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        d[a]       = (long long) (__fmul_rn(__fsub_rn(mx[a], mn[a]), inv)) + 1;
+        g.min_b[a] = (int) floorf(__fmul_rn(mn[a], inv));
+        int max_b  = (int) floorf(__fmul_rn(mx[a], inv));
+        div_b[a]   = max_b - g.min_b[a] + 1;
+    }
+    g.overflow = (d[0] * d[1] * d[2]) > 2147483647LL;
+    g.mul1     = div_b[0];
+    g.mul2     = div_b[0] * div_b[1];
+    long long cells = (long long) div_b[0] * div_b[1] * div_b[2];
+    int nb = 0;
+    while (nb < 32 && (1LL << nb) < cells) nb++;
+    g.nbits = g.overflow ? 0 : (nb < 1 ? 1 : nb);
+    return g;
+}
+
+__global__ void __launch_bounds__(256)
+vox_keys_kernel(const float4 *__restrict__ in, int n, float inv, int *__restrict__ meta, uint32_t *__restrict__ keys,
+                int32_t *__restrict__ keys_out) {
+    Grid3 g = make_grid(meta, inv);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        meta[M_OVERFLOW] = g.overflow ? 1 : 0;
+        meta[M_NBITS]    = g.nbits;
+        meta[M_PARITY]   = 0;
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 p = __ldg(in + i);
+        int i0   = (int) (floorf(__fmul_rn(p.x, inv)) - (float) g.min_b[0]);
+        int i1   = (int) (floorf(__fmul_rn(p.y, inv)) - (float) g.min_b[1]);
+        int i2   = (int) (floorf(__fmul_rn(p.z, inv)) - (float) g.min_b[2]);
+        int key  = i0 + i1 * g.mul1 + i2 * g.mul2;
+        keys[i]  = (uint32_t) key;
+        if (keys_out) keys_out[i] = key;
+    }
+}
+
+// ---- stable LSD radix sort, 8-bit digits ---------------------------------------------------------
+__global__ void __launch_bounds__(RS_THREADS)
+rs_hist_kernel(const uint32_t *__restrict__ k0, const uint32_t *__restrict__ k1, const int *__restrict__ meta, int pass,
+               int n, uint32_t *__restrict__ block_hist, int nb) {
+    if (pass * 8 >= meta[M_NBITS]) return;
+    const uint32_t *keys = meta[M_PARITY + pass] ? k1 : k0;
+    __shared__ uint32_t hist[256];
+    hist[threadIdx.x] = 0;
+    __syncthreads();
+    const int shift = pass * 8;
+    int base        = blockIdx.x * RS_TILE;
+#pragma unroll 4
+    for (int r = 0; r < RS_ITEMS; r++) {
+        int i = base + r * RS_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&hist[(keys[i] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    block_hist[threadIdx.x * nb + blockIdx.x] = hist[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(1024)
+rs_scan_kernel(int *__restrict__ meta, int pass, uint32_t *__restrict__ block_hist, int total) {
+    const bool active = pass * 8 < meta[M_NBITS];
+    if (threadIdx.x == 0) meta[M_PARITY + pass + 1] = meta[M_PARITY + pass] ^ (active ? 1 : 0);
+    if (!active) return;
+    __shared__ uint32_t warp_sums[32];
+    const int per = (total + 1023) / 1024;
+    const int lo  = threadIdx.x * per;
+    const int hi  = min(total, lo + per);
+    uint32_t sum  = 0;
+    for (int i = lo; i < hi; i++) sum += block_hist[i];
+    // block exclusive scan of `sum`
+    uint32_t incl = sum;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_sums[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t w = warp_sums[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t v = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += v;
+        }
+        warp_sums[lane] = wi - w;
+    }
+    __syncthreads();
+    uint32_t run = warp_sums[wid] + incl - sum;
+    for (int i = lo; i < hi; i++) {
+        uint32_t v    = block_hist[i];
+        block_hist[i] = run;
+        run += v;
+    }
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+rs_scatter_kernel(uint32_t *k0, uint32_t *k1, uint32_t *x0, uint32_t *x1, const int *__restrict__ meta, int pass, int n,
+                  const uint32_t *__restrict__ block_hist, int nb) {
+    if (pass * 8 >= meta[M_NBITS]) return;
+    // ping-pong buffers: no __restrict__ here, the in/out roles are picked at run time
+    const int parity       = meta[M_PARITY + pass];
+    const uint32_t *keys   = parity ? k1 : k0;
+    const uint32_t *idx    = parity ? x1 : x0;
+    uint32_t *keys_out     = parity ? k0 : k1;
+    uint32_t *idx_out      = parity ? x0 : x1;
+    __shared__ uint32_t warp_hist[RS_WARPS][256];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&warp_hist[0][0])[i] = 0;
+    __syncthreads();
+    const int shift = pass * 8;
+    const int chunk = blockIdx.x * RS_TILE + wid * (RS_TILE / RS_WARPS);
+    uint32_t key[RS_ITEMS], val[RS_ITEMS], rank[RS_ITEMS];
+    const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; r++) {
+        int i      = chunk + r * 32 + lane;
+        bool valid = i < n;
+        key[r]     = valid ? keys[i] : 0xffffffffu;
+        val[r]     = valid ? (pass == 0 ? (uint32_t) i : idx[i]) : 0u;
+        uint32_t digit = (key[r] >> shift) & 255u;
+        unsigned m     = __match_any_sync(0xffffffffu, valid ? digit : 256u + lane);
+        uint32_t prev  = warp_hist[wid][digit];
+        __syncwarp();
+        uint32_t rk = __popc(m & lt);
+        if (valid && rk == 0) warp_hist[wid][digit] = prev + __popc(m);
+        __syncwarp();
+        rank[r] = prev + rk;
+    }
+    __syncthreads();
+    {
+        // exclusive prefix over the warps of this block, seeded with the block's global offset
+        int d        = threadIdx.x;
+        uint32_t run = block_hist[d * nb + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; w++) {
+            uint32_t c      = warp_hist[w][d];
+            warp_hist[w][d] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; r++) {
+        int i = chunk + r * 32 + lane;
+        if (i < n) {
+            uint32_t digit = (key[r] >> shift) & 255u;
+            uint32_t dst   = warp_hist[wid][digit] + rank[r];
+            keys_out[dst]  = key[r];
+            idx_out[dst]   = val[r];
+        }
+    }
+}
+
+// ---- segment heads + ordered centroid ---------------------------------------------------------------
+__device__ __forceinline__ bool is_head(const uint32_t *__restrict__ keys, int i) { return i == 0 || keys[i] != keys[i - 1]; }
+
+__global__ void __launch_bounds__(SEG_THREADS)
+seg_count_kernel(const uint32_t *__restrict__ k0, const uint32_t *__restrict__ k1, const int *__restrict__ meta, int n,
+                 uint32_t *__restrict__ block_heads) {
+    const uint32_t *keys = meta[M_PARITY + 4] ? k1 : k0;
+    int base             = blockIdx.x * SEG_TILE + threadIdx.x * SEG_ITEMS;
+    int c                = 0;
+    if (!meta[M_OVERFLOW]) {
+#pragma unroll
+        for (int j = 0; j < SEG_ITEMS; j++) {
+            int i = base + j;
+            if (i < n && is_head(keys, i)) c++;
+        }
+    }
+    __shared__ int ws[SEG_THREADS / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int s = 0;
+        for (int w = 0; w < SEG_THREADS / 32; w++) s += ws[w];
+        block_heads[blockIdx.x] = s;
+    }
+}
+
+__global__ void __launch_bounds__(SEG_THREADS)
+seg_centroid_kernel(const float4 *__restrict__ in, const uint32_t *__restrict__ k0, const uint32_t *__restrict__ k1,
+                    const uint32_t *__restrict__ x0, const uint32_t *__restrict__ x1, int *__restrict__ meta, int n,
+                    const uint32_t *__restrict__ block_heads, float4 *__restrict__ out, int *__restrict__ d_nout) {
+    const int parity = meta[M_PARITY + 4];
+    const uint32_t *keys = parity ? k1 : k0;
+    const uint32_t *idx  = parity ? x1 : x0;
+    if (meta[M_OVERFLOW]) {
+        // PCL: "leaf size too small": the input cloud is returned unchanged
+        for (int i = blockIdx.x * SEG_TILE + threadIdx.x; i < min(n, (blockIdx.x + 1) * SEG_TILE); i += SEG_THREADS)
+            out[i] = in[i];
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            *d_nout      = n;
+            meta[M_NOUT] = n;
+        }
+        return;
+    }
+    __shared__ int s_base;
+    __shared__ int ws[SEG_THREADS / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (wid == 0) {
+        int s = 0;
+        for (int b = lane; b < (int) blockIdx.x; b += 32) s += block_heads[b];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) s_base = s;
+    }
+    const int base = blockIdx.x * SEG_TILE + threadIdx.x * SEG_ITEMS;
+    bool head[SEG_ITEMS];
+    int c = 0;
+#pragma unroll
+    for (int j = 0; j < SEG_ITEMS; j++) {
+        int i   = base + j;
+        head[j] = (i < n) && is_head(keys, i);
+        c += head[j] ? 1 : 0;
+    }
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) ws[wid] = incl;
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < wid; w++) woff += ws[w];
+    int slot = s_base + woff + incl - c;
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == SEG_THREADS - 1) {
+        int total = s_base + woff + incl;
+        *d_nout      = total;
+        meta[M_NOUT] = total;
+    }
+#pragma unroll
+    for (int j = 0; j < SEG_ITEMS; j++) {
+        if (!head[j]) continue;
+        int i        = base + j;
+        uint32_t key = keys[i];
+        float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+        int e = i;
+        // ascending original index inside the voxel: sequential fp32 adds (Appendix A.1 step 7)
+        while (e < n && keys[e] == key) {
+            float4 p = __ldg(in + idx[e]);
+            sx += p.x;
+            sy += p.y;
+            sz += p.z;
+            si += p.w;
+            e++;
+        }
+        float cnt = (float) (e - i);
+        out[slot] = make_float4(sx / cnt, sy / cnt, sz / cnt, si / cnt);
+        slot++;
+    }
+}
+
+} // namespace
+
+size_t voxel_work_bytes(int cap, size_t *off) {
+    auto al = [](size_t x) { return (x + 255) & ~(size_t) 255; };
+    size_t nb  = (size_t) (cap + RS_TILE - 1) / RS_TILE + 1;
+    size_t nb2 = (size_t) (cap + SEG_TILE - 1) / SEG_TILE + 1;
+    size_t o   = 0;
+    off[0] = o; o += al((size_t) cap * 4);
+    off[1] = o; o += al((size_t) cap * 4);
+    off[2] = o; o += al((size_t) cap * 4);
+    off[3] = o; o += al((size_t) cap * 4);
+    off[4] = o; o += al(256 * nb * 4);
+    off[5] = o; o += al(nb2 * 4);
+    off[6] = o; o += al(M_SIZE * 4);
+    return o;
+}
+
+int launch_voxel_downsample(cudaStream_t s, const VoxelWork &w, const float4 *in, int n, float leaf, float4 *out,
+                            int *d_nout, int32_t *keys_out, int64_t *launches, Profiler *prof, const char *tag) {
+    if (n <= 0) {
+        cudaMemsetAsync(d_nout, 0, sizeof(int), s);
+        return 0;
+    }
+    if (n > w.cap) return -1;
+    const float inv = 1.0f / leaf;
+    int g           = (n + 255) / 256;
+    if (g > 148 * 8) g = 148 * 8;
+    char name[64];
+    auto nm = [&](const char *k) {
+        snprintf(name, sizeof(name), "%s.%s", tag, k);
+        return name;
+    };
+    {
+        ProfScope ps(prof, nm("bbox_keys"), s);
+        vox_init_kernel<<<1, 32, 0, s>>>(w.meta);
+        vox_bbox_kernel<<<g, 256, 0, s>>>(in, n, w.meta);
+        vox_keys_kernel<<<g, 256, 0, s>>>(in, n, inv, w.meta, w.keys[0], keys_out);
+    }
+    const int nb = (n + RS_TILE - 1) / RS_TILE;
+    {
+        ProfScope ps(prof, nm("radix_sort"), s);
+        for (int pass = 0; pass < 4; pass++) {
+            rs_hist_kernel<<<nb, RS_THREADS, 0, s>>>(w.keys[0], w.keys[1], w.meta, pass, n, w.block_hist, nb);
+            rs_scan_kernel<<<1, 1024, 0, s>>>(w.meta, pass, w.block_hist, 256 * nb);
+            rs_scatter_kernel<<<nb, RS_THREADS, 0, s>>>(w.keys[0], w.keys[1], w.idx[0], w.idx[1], w.meta, pass, n,
+                                                        w.block_hist, nb);
+        }
+    }
+    const int nb2 = (n + SEG_TILE - 1) / SEG_TILE;
+    {
+        ProfScope ps(prof, nm("centroid"), s);
+        seg_count_kernel<<<nb2, SEG_THREADS, 0, s>>>(w.keys[0], w.keys[1], w.meta, n, w.block_heads);
+        seg_centroid_kernel<<<nb2, SEG_THREADS, 0, s>>>(in, w.keys[0], w.keys[1], w.idx[0], w.idx[1], w.meta, n,
+                                                        w.block_heads, out, d_nout);
+    }
+    if (launches) *launches += 3 + 12 + 2;
+    return 0;
+}
+
+} // namespace fflins

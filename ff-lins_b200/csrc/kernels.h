@@ -1,0 +1,133 @@
+// kernels.h — launchers of the hand-written sm_100a kernels (definitions in k_*.cu).
+#pragma once
+#include "common.cuh"
+
+namespace fflins {
+
+constexpr int kMaxRefs = 16;
+
+// Optional per-kernel CUDA-event timing hook (implemented by the context, off by default).
+struct Profiler {
+    virtual void begin(const char *name, cudaStream_t s) = 0;
+    virtual void end(cudaStream_t s)                     = 0;
+    virtual ~Profiler() {}
+};
+struct ProfScope {
+    Profiler *p;
+    cudaStream_t s;
+    ProfScope(Profiler *p_, const char *name, cudaStream_t s_) : p(p_), s(s_) {
+        if (p) p->begin(name, s);
+    }
+    ~ProfScope() {
+        if (p) p->end(s);
+    }
+};
+
+// ---- K1 undistort (lidar_map.cc:223-256, misc.cc:27-105, pointcloud.cc:30-59) -------------------
+// Per-IMU-interval invariants of MISC::statePoseInterpolation (misc.cc:86-88): dp, rvec.
+// interval_tab: 6 doubles per window entry i (interval [i-1, i]); frame_pose[0] = lidar pose at
+// `stamp`, frame_pose[1] = pose of window.back() (the out-of-window fallback, misc.cc:76-79).
+void launch_ins_prep(cudaStream_t s, const double *ins_t, const double *ins_p, const double *ins_q, int w,
+                     Pose12 ext, double stamp, double *interval_tab, Pose12 *frame_pose);
+// aos != nullptr: raw 32-byte PointXYZIT records; else xyzi + time arrays.
+void launch_undistort(cudaStream_t s, const float4 *xyzi, const double *time, const void *aos, int n,
+                      const double *ins_t, const double *ins_p, const double *ins_q, int w,
+                      const double *interval_tab, const Pose12 *frame_pose, Pose12 ext, double td, int filter_num,
+                      float4 *out_full, float4 *out_dec, int *n_fallback);
+// static overload (lidar_map.cc:275-324): copy + decimate
+void launch_copy_decimate(cudaStream_t s, const float4 *xyzi, int n, int filter_num, float4 *out_full,
+                          float4 *out_dec);
+
+// ---- K3 rigid projection (pointcloud.cc:38-59). n_dev (optional) overrides n with a device count.
+void launch_project(cudaStream_t s, Pose12 T, const float4 *src, float4 *dst, int n, const int *n_dev);
+// same with the pose read from device memory (the frame pose produced by launch_ins_prep)
+void launch_project_dev(cudaStream_t s, const Pose12 *T_dev, const float4 *src, float4 *dst, int n, const int *n_dev);
+
+// ---- K2 voxel downsample (pcl::VoxelGrid) --------------------------------------
+struct VoxelWork {
+    uint32_t *keys[2]   = {nullptr, nullptr};
+    uint32_t *idx[2]    = {nullptr, nullptr};
+    uint32_t *block_hist = nullptr; // 256 * nblocks
+    uint32_t *block_heads = nullptr;
+    int      *meta      = nullptr;  // see k_voxel.cu
+    int       cap       = 0;        // points capacity
+};
+size_t voxel_work_bytes(int cap, size_t *offsets /*8*/);
+// out must hold n points; *d_nout (device int) receives the voxel count, d_flag receives 1 on the
+// PCL "leaf too small" overflow (output = input). keys_out optional (n).
+int launch_voxel_downsample(cudaStream_t s, const VoxelWork &w, const float4 *in, int n, float leaf, float4 *out,
+                            int *d_nout, int32_t *keys_out, int64_t *launches, Profiler *prof, const char *tag);
+
+// ---- K4 keyframe hash insert (replaces ikd_Tree::build, lidar_map.cc:100-118) -------------------------
+void launch_hash_build(cudaStream_t s, const float4 *map, int m, float inv_cell, unsigned long long *hkeys,
+                       int *hvals, int hcap);
+
+// ---- K5 association (lidar_map.cc:326-408, pointcloud.cc:61-93, ikd_Tree.cc:897-924) -------------------
+struct FeatureSoA {
+    int8_t  *type    = nullptr; // FEATURE_NONE / PLANE
+    uint8_t *covered = nullptr;
+    uint8_t *outlier = nullptr;
+    int32_t *nn_idx  = nullptr; // 5 per query
+    float   *nn_d2   = nullptr; // 5 per query
+    double  *normal  = nullptr; // 3 per query
+    double  *d       = nullptr; // norm_inverse
+};
+struct AssocRef {
+    const float4 *map;
+    const unsigned long long *hkeys;
+    const int *hvals;
+    int hmask;
+    int m;
+    Pose12 T_ref_world;
+    FeatureSoA feat;
+    int *counts; // [2]: num_features, num_covered
+};
+struct AssocParams {
+    int n_refs;
+    int q;
+    float inv_cell;
+    float cell;
+    int r_max;
+    float max_d2;          // (max_search_square_distance)^2, ikd_Tree.cc:902
+    float plane_d2_gate;   // max_search_square_distance, lidar_map.cc:374
+    double plane_thr, sigma, scalar_thr, sigma_gate;
+    AssocRef ref[kMaxRefs];
+};
+void launch_associate(cudaStream_t s, const AssocParams &p, const float4 *cur_world, const float4 *cur_lidar);
+// brute-force-free stand-alone 5-NN against a hash (fflins_knn5)
+void launch_knn5(cudaStream_t s, const float4 *map, const unsigned long long *hkeys, const int *hvals, int hmask,
+                 int m, const float4 *query, int q, float inv_cell, float cell, int r_max, float max_d2,
+                 int32_t *nn_idx, float *nn_d2, int32_t *nn_count);
+void launch_plane_estimation(cudaStream_t s, const float4 *pts, int n, double thr, double *unit, double *ninv,
+                             double *dist, uint8_t *ok);
+
+// ---- K6 / K7 factors (lidar_factor.cc:41-118, residual_block_info.cc:49-77, marginalization_info.cc:181-210)
+struct FactorPair {
+    const int8_t *type;     // nullptr => every residual valid (stateless batch)
+    uint8_t *outlier;       // read by K6, written by K7
+    const double *normal;
+    const double *d;
+    const double *std;      // nullptr => sigma below
+    double pose_ref[7];
+    double v0[3], w0[3], td0;
+};
+struct FactorParams {
+    int n_pairs;
+    int q;                  // features per pair
+    uint32_t flags;
+    double pose_cur[7], ext[7], td;
+    double v1[3], w1[3], td1;
+    double sigma, huber_delta;
+    FactorPair pair[kMaxRefs];
+};
+constexpr int kFactorBlock = 256;
+constexpr int kRedSize     = 212; // 190 upper-tri H + 19 b + cost0 + cost1 + count
+// points: xyz of cur-frame points as float4 (stride4=1) or packed float3 (stride4=0).
+// r/J/valid (optional) are per (pair, feature): r[pair*q+k], J[22*(pair*q+k)].
+// partial: n_pairs * blocks_per_pair * kRedSize doubles; out_red: n_pairs * kRedSize doubles.
+void launch_factor_eval(cudaStream_t s, const FactorParams &p, const float *points, int stride4, double *r, double *J,
+                        uint8_t *valid, double *partial, double *out_red, unsigned int *tickets);
+void launch_chi2(cudaStream_t s, const FactorParams &p, const float *points, int stride4, double threshold,
+                 int *n_outliers);
+
+} // namespace fflins

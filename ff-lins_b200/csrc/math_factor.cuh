@@ -1,0 +1,113 @@
+// math_factor.cuh — fp64 point-to-plane factor algebra shared by the K6/K7 kernels (k_factor.cu).
+// __host__ __device__ so that tests can run the very same code on the CPU against the oracle
+// before any GPU time is spent (tests/host_math_check.cu).
+#pragma once
+#include "kernels.h"
+#include <cfloat>
+#include <cmath>
+
+namespace fflins {
+
+struct PairConst {
+    M3 R0, B0, Rt0, R1, B1, Rt1, Rbl, D, E;
+    V3 tt0, tt1, tbl, w0, w1, dv;
+};
+
+__host__ __device__ __forceinline__ M3 skew_plus_I(V3 v) { return M3{{1.0, -v.z, v.y, v.z, 1.0, -v.x, -v.y, v.x, 1.0}}; }
+
+__host__ __device__ inline void make_pair_const(const FactorParams &P, const FactorPair &pr, PairConst &c) {
+    V3 t0  = v3(pr.pose_ref[0], pr.pose_ref[1], pr.pose_ref[2]);
+    Q4 q0  = Q4{pr.pose_ref[3], pr.pose_ref[4], pr.pose_ref[5], pr.pose_ref[6]};
+    V3 t1  = v3(P.pose_cur[0], P.pose_cur[1], P.pose_cur[2]);
+    Q4 q1  = Q4{P.pose_cur[3], P.pose_cur[4], P.pose_cur[5], P.pose_cur[6]};
+    c.tbl  = v3(P.ext[0], P.ext[1], P.ext[2]);
+    Q4 qbl = Q4{P.ext[3], P.ext[4], P.ext[5], P.ext[6]};
+    c.w0   = v3(pr.w0[0], pr.w0[1], pr.w0[2]);
+    c.w1   = v3(P.w1[0], P.w1[1], P.w1[2]);
+    V3 v0  = v3(pr.v0[0], pr.v0[1], pr.v0[2]);
+    V3 v1  = v3(P.v1[0], P.v1[1], P.v1[2]);
+    c.dv   = v1 - v0;
+    double dt0 = P.td - pr.td0, dt1 = P.td - P.td1;
+    c.R0  = quat_to_R(q0);
+    c.B0  = skew_plus_I(c.w0 * dt0);   // I + [w0 dt0]x   (lidar_factor.cc:59)
+    c.Rt0 = mul(c.R0, c.B0);
+    c.tt0 = t0 + v0 * dt0;
+    c.R1  = quat_to_R(q1);
+    c.B1  = skew_plus_I(c.w1 * dt1);
+    c.Rt1 = mul(c.R1, c.B1);
+    c.tt1 = t1 + v1 * dt1;
+    c.Rbl = quat_to_R(qbl);
+    M3 A  = mul(transpose(c.Rbl), transpose(c.Rt0));
+    M3 C  = mul(A, c.Rt1);             // `common` (lidar_factor.cc:102)
+    M3 Rblt = transpose(c.Rbl);
+#pragma unroll
+    for (int i = 0; i < 9; i++) c.D.m[i] = C.m[i] - Rblt.m[i];
+    c.E = mul(C, c.Rbl);
+}
+
+// r and the 19 tangent-space Jacobian entries [ref t, ref th, cur t, cur th, ext t, ext th, td].
+template <bool JAC>
+__host__ __device__ __forceinline__ double eval_residual(const PairConst &c, V3 p, V3 n, double d, double s, double *J) {
+    V3 pb1 = mul(c.Rbl, p) + c.tbl;
+    V3 pw  = mul(c.Rt1, pb1) + c.tt1;
+    V3 u   = pw - c.tt0;
+    V3 pb0 = mulT(c.Rt0, u);
+    V3 pl0 = mulT(c.Rbl, pb0 - c.tbl);
+    double r = s * (dot(n, pl0) + d);
+    if (JAC) {
+        V3 sn = n * s;
+        V3 sc = mul(c.Rbl, sn);           // (s n^T Rbl^T)^T
+        V3 g0 = mul(c.Rt0, sc);           // (sc^T Rt0^T)^T
+        V3 w  = mulT(c.R0, u);            // R0^T (pw - tt0)
+        V3 a  = mul(c.B0, sc);
+        V3 jr = cross(a, w);              // sc^T B0^T [w]x
+        V3 h  = mulT(c.R1, g0);
+        V3 m  = mul(c.B1, pb1);
+        V3 jc = cross(m, h);              // -g0^T R1 [B1 pb1]x
+        V3 je = mulT(c.D, sn);            // s n^T (C - Rbl^T)
+        V3 kk = mulT(c.E, sn);
+        V3 jf = cross(sn, pl0) - cross(kk, p); // s n^T ([pl0]x - C Rbl [p]x)
+        V3 z  = mul(c.R1, cross(c.w1, pb1)) + c.dv;
+        double jt = dot(sc, cross(w, c.w0) + mulT(c.Rt0, z));
+        J[0] = -g0.x; J[1] = -g0.y; J[2] = -g0.z;
+        J[3] = jr.x;  J[4] = jr.y;  J[5] = jr.z;
+        J[6] = g0.x;  J[7] = g0.y;  J[8] = g0.z;
+        J[9] = jc.x;  J[10] = jc.y; J[11] = jc.z;
+        J[12] = je.x; J[13] = je.y; J[14] = je.z;
+        J[15] = jf.x; J[16] = jf.y; J[17] = jf.z;
+        J[18] = jt;
+    }
+    return r;
+}
+
+// Ceres HuberLoss + corrector for a 1-dim residual (residual_block_info.cc:49-77). Returns rho(s).
+__host__ __device__ __forceinline__ double huber_correct(double delta, double &r, double *J) {
+    double sq = r * r, b = delta * delta;
+    double rho0, rho1, rho2;
+    if (sq > b) {
+        double rr = sqrt(sq);
+        rho0 = 2.0 * delta * rr - b;
+        rho1 = fmax(DBL_MIN, delta / rr);
+        rho2 = -rho1 / (2.0 * sq);
+    } else {
+        rho0 = sq; rho1 = 1.0; rho2 = 0.0;
+    }
+    double sqrt_rho1 = sqrt(rho1), scaling, alpha_sq;
+    if (sq == 0.0 || rho2 <= 0.0) {
+        scaling = sqrt_rho1;
+        alpha_sq = 0.0;
+    } else {
+        double D     = 1.0 + 2.0 * sq * rho2 / rho1;
+        double alpha = 1.0 - sqrt(D);
+        scaling  = sqrt_rho1 / (1.0 - alpha);
+        alpha_sq = alpha / sq;
+    }
+    if (J) {
+#pragma unroll
+        for (int i = 0; i < 19; i++) J[i] = sqrt_rho1 * (J[i] - alpha_sq * r * (r * J[i]));
+    }
+    r *= scaling;
+    return rho0;
+}
+
+} // namespace fflins

@@ -1,0 +1,84 @@
+"""The LiDAR call sequence of LINS::runFusion (ff_lins/ff_lins/ff_lins.cc:236-262) and of
+Optimizer::optimization / marginalization (ff_lins/ff_lins/optimizer.cc:85-185, 221-404) as far as
+they touch the hot path, driven through the C-ABI.
+
+Per frame:      fflins_frame_process                        (lidarFrameProcessing)
+Per keyframe:   fflins_keyframe_merge -> fflins_keyframe_add -> fflins_frame_set_motion
+                -> fflins_associate -> n_eval x fflins_window_eval (+ fflins_window_chi2 between the
+                two solves) -> fflins_reproject of every keyframe -> fflins_keyframe_remove_oldest
+                when the window is full.
+Keyframes are chosen every `frames_per_key` frames (the synthetic trajectory makes the reference's
+own keyframeSelection fire at that cadence; the selection call is exercised separately)."""
+import numpy as np
+
+from . import api
+
+
+class Session:
+    def __init__(self, ctx, seq, frames_per_key=5, n_eval=(5, 10), flags=api.HUBER):
+        self.ctx = ctx
+        self.seq = seq
+        self.K = frames_per_key
+        self.n_eval = n_eval
+        self.flags = flags
+        self.nonkeys = []
+        self.key_stamps = {}
+        self.next_id = 0
+        self.window = ctx.cfg.window_size
+        self.pose_bl = api.Pose.make(seq.R_bl, seq.t_bl)
+        self.ext7 = seq.ext7()
+        self.last = {}
+
+    # -- inputs are host numpy arrays (the e2e path) --------------------------------------------------
+    def process_frame(self, fr):
+        fid = self.next_id
+        self.next_id += 1
+        info = self.ctx.frame_process(fid, fr["xyzi"], fr["time"], fr["ins_t"], fr["ins_p"], fr["ins_q"],
+                                      self.seq.R_bl, self.seq.t_bl, fr["stamp"], fr["td"])
+        return fid, info
+
+    def process_frame_dev(self, fr_dev):
+        """fr_dev: dict of raw device pointers + scalars (inputs resident in HBM)."""
+        fid = self.next_id
+        self.next_id += 1
+        info = self.ctx.frame_process_dev(fid, fr_dev["xyzi"], fr_dev["time"], fr_dev["n"], fr_dev["ins_t"],
+                                          fr_dev["ins_p"], fr_dev["ins_q"], fr_dev["w"], self.pose_bl,
+                                          fr_dev["stamp"], fr_dev["td"])
+        return fid, info
+
+    def after_frame(self, fid, fr, force_key=None):
+        """Keyframe bookkeeping after a frame was processed. Returns True if it became a keyframe."""
+        is_key = force_key if force_key is not None else (len(self.nonkeys) + 1 >= self.K)
+        if not is_key:
+            self.nonkeys.append(fid)
+            return False
+        ctx = self.ctx
+        self.last["merge"] = ctx.keyframe_merge(fid, self.nonkeys)
+        for nk in self.nonkeys:
+            ctx.release(nk)
+        self.nonkeys = []
+        ctx.keyframe_add(fid)
+        ctx.set_motion(fid, fr["v"], fr["omega"], fr["td"])
+        self.key_stamps[fid] = fr["stamp"]
+        ids = ctx.keyframe_ids()
+        if len(ids) >= 2:
+            self.last["assoc"] = ctx.associate()
+            refs = ids[:-1]
+            pose_refs = np.stack([self.seq.imu_pose7(self.key_stamps[r]) for r in refs])
+            pose_cur = self.seq.imu_pose7(self.key_stamps[fid])
+            out = None
+            # first solve: n_eval[0] LM iterations' worth of evaluations
+            for _ in range(self.n_eval[0]):
+                out = ctx.window_eval(refs, pose_refs, pose_cur, self.ext7, fr["td"], self.flags, out)
+            self.last["chi2"] = ctx.window_chi2(refs, pose_refs, pose_cur, self.ext7, fr["td"])
+            for _ in range(self.n_eval[1]):
+                out = ctx.window_eval(refs, pose_refs, pose_cur, self.ext7, fr["td"], self.flags, out)
+            self.last["eval"] = out
+            # updateParametersFromOptimizer: re-project every keyframe (optimizer.cc:203-218)
+            for k in ids:
+                R, t = ctx.get_pose(k)
+                ctx.reproject(k, R, t)
+        if len(ids) > self.window:
+            rid = ctx.keyframe_remove_oldest()
+            self.key_stamps.pop(rid, None)
+        return True

@@ -1,0 +1,502 @@
+"""GPU-vs-oracle parity, stage by stage, through the C-ABI (SURVEY.md §7 kernel/parity map).
+
+Bit-exact stages are fed the ORACLE's output of the previous stage, so a 1-ulp difference in an
+upstream transcendental cannot leak into a bit-exact claim. Tolerances (BASELINE.json north_star):
+voxel keys / output sets / kNN index sets bit-exact; fp64 residuals, Jacobians, H, b <= 1e-9
+relative per block; fp32 undistortion output within 1 ulp."""
+import numpy as np
+import pytest
+
+from util import bits_equal, block_rel, rand_pose, random_scene_cloud, ulp_diff
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def robot():
+    from fflins import synth
+    return synth.Sequence("robot")
+
+
+# ---------------------------------------------------------------- K1 undistortion
+@pytest.mark.parametrize("name,frame", [("robot", 3), ("lili", 2), ("ouster64", 1), ("at128", 4)])
+def test_undistort_parity(ctx, oracle, name, frame):
+    from fflins import api, synth
+    seq = synth.Sequence(name)
+    fr = seq.frame(frame)
+    c = api.Context(api.default_config(point_filter_num=seq.filter_num))
+    info = c.frame_process(7, fr["xyzi"], fr["time"], fr["ins_t"], fr["ins_p"], fr["ins_q"], seq.R_bl, seq.t_bl,
+                           fr["stamp"], fr["td"])
+    und, R, t, fb = oracle.undistort(fr["xyzi"], fr["time"], fr["ins_t"], fr["ins_p"], fr["ins_q"], seq.R_bl,
+                                     seq.t_bl, fr["stamp"], fr["td"], threads=8)
+    Rg, tg = info.pose.numpy()
+    assert np.max(np.abs(Rg - R)) < 1e-12 and np.max(np.abs(tg - t)) < 1e-9
+    assert info.n_fallback == fb == 0
+    full = c.download(7, api.CLOUD_MAP_FULL)
+    assert full.shape == und.shape
+    ulps = ulp_diff(full[:, :3], und[:, :3])
+    frac = float(np.mean(ulps > 0))
+    print(f"{name}: undistort ulp histogram: 0:{np.sum(ulps == 0)} 1:{np.sum(ulps == 1)} >1:{np.sum(ulps > 1)}")
+    assert ulps.max() <= 1, "fp32 undistorted coordinates must agree within 1 ulp"
+    assert frac < 1e-3
+    assert bits_equal(full[:, 3], und[:, 3])
+    # index decimation (lidar_map.cc:249-256): identical set by construction
+    dec = c.download(7, api.CLOUD_LIDAR_FULL)
+    assert bits_equal(dec, full[::seq.filter_num])
+    assert info.n_dec == len(dec)
+    # the frame chain downstream of the GPU's own undistorted cloud is bit-exact with the oracle
+    down = c.download(7, api.CLOUD_LIDAR)
+    assert bits_equal(down, oracle.voxel_filter(dec, 0.5))
+    world = c.download(7, api.CLOUD_WORLD)
+    assert bits_equal(world, oracle.project(Rg, tg, down))
+    c.close()
+
+
+def test_undistort_aos_matches_soa(ctx, robot):
+    from fflins import api, synth
+    fr = robot.frame(1)
+    a = ctx.frame_process(100, fr["xyzi"], fr["time"], fr["ins_t"], fr["ins_p"], fr["ins_q"], robot.R_bl,
+                          robot.t_bl, fr["stamp"], fr["td"])
+    rec = synth.pack_aos(fr["xyzi"], fr["time"])
+    b = ctx.frame_process_aos(101, rec, fr["ins_t"], fr["ins_p"], fr["ins_q"], robot.R_bl, robot.t_bl,
+                              fr["stamp"], fr["td"])
+    assert a.n_down == b.n_down
+    for which in range(3):
+        assert bits_equal(ctx.download(100, which), ctx.download(101, which))
+    assert bits_equal(ctx.download(100, api.CLOUD_MAP_FULL), ctx.download(101, api.CLOUD_MAP_FULL))
+    ctx.release(100)
+    ctx.release(101)
+
+
+def test_undistort_outside_window_falls_back(ctx, oracle, robot):
+    """Points outside the INS window use window.back() (misc.cc:76-79)."""
+    from fflins import api
+    fr = robot.frame(2)
+    time = fr["time"].copy()
+    time[::7] += 100.0      # far beyond the window
+    time[3::11] -= 100.0    # before the window
+    info = ctx.frame_process(102, fr["xyzi"], time, fr["ins_t"], fr["ins_p"], fr["ins_q"], robot.R_bl, robot.t_bl,
+                             fr["stamp"], fr["td"])
+    und, R, t, fb = oracle.undistort(fr["xyzi"], time, fr["ins_t"], fr["ins_p"], fr["ins_q"], robot.R_bl,
+                                     robot.t_bl, fr["stamp"], fr["td"])
+    assert info.n_fallback == fb > 0
+    full = ctx.download(102, api.CLOUD_MAP_FULL)
+    assert ulp_diff(full[:, :3], und[:, :3]).max() <= 1
+    ctx.release(102)
+
+
+def test_identity_motion_is_identity(ctx):
+    """KAT: a static INS window and identity extrinsic leave every point untouched bit for bit."""
+    from fflins import api
+    rng = np.random.default_rng(5)
+    n, w = 5000, 50
+    xyzi = rng.uniform(-50, 50, (n, 4)).astype(np.float32)
+    ins_t = 1000.0 + 0.005 * np.arange(w)
+    ins_p = np.zeros((w, 3))
+    ins_q = np.tile(np.array([0, 0, 0, 1.0]), (w, 1))
+    time = rng.uniform(ins_t[1], ins_t[-2], n)
+    info = ctx.frame_process(103, xyzi, time, ins_t, ins_p, ins_q, np.eye(3), np.zeros(3), ins_t[-2], 0.0)
+    assert bits_equal(ctx.download(103, api.CLOUD_MAP_FULL), xyzi)
+    assert info.n_fallback == 0
+    ctx.release(103)
+
+
+def test_static_overload(ctx, oracle, robot):
+    from fflins import api
+    fr = robot.frame(0)
+    p, q = fr["ins_p"][-1], fr["ins_q"][-1]
+    info = ctx.frame_process_static(104, fr["xyzi"], p, q, robot.R_bl, robot.t_bl)
+    R, t = oracle.state_to_pose(p, q, robot.R_bl, robot.t_bl)
+    Rg, tg = info.pose.numpy()
+    assert bits_equal(Rg, R) and bits_equal(tg, t)
+    assert bits_equal(ctx.download(104, api.CLOUD_MAP_FULL), fr["xyzi"])
+    dec = oracle.decimate(fr["xyzi"], ctx.cfg.point_filter_num)
+    down = oracle.voxel_filter(dec, 0.5)
+    assert bits_equal(ctx.download(104, api.CLOUD_LIDAR), down)
+    assert bits_equal(ctx.download(104, api.CLOUD_WORLD), oracle.project(R, t, down))
+    ctx.release(104)
+
+
+def test_empty_frame(ctx, robot):
+    fr = robot.frame(0)
+    info = ctx.frame_process(105, np.zeros((0, 4), np.float32), np.zeros(0), fr["ins_t"], fr["ins_p"], fr["ins_q"],
+                             robot.R_bl, robot.t_bl, fr["stamp"], fr["td"])
+    assert (info.n_raw, info.n_dec, info.n_down) == (0, 0, 0)
+    ctx.release(105)
+
+
+def test_bad_window_is_rejected(ctx, robot):
+    from fflins import api
+    fr = robot.frame(0)
+    bad = fr["ins_t"].copy()
+    bad[10] = bad[9]
+    with pytest.raises(api.FflinsError):
+        ctx.frame_process(106, fr["xyzi"], fr["time"], bad, fr["ins_p"], fr["ins_q"], robot.R_bl, robot.t_bl,
+                          fr["stamp"], fr["td"])
+
+
+# ---------------------------------------------------------------- K2 voxel downsample
+@pytest.mark.parametrize("n", [1, 2, 5, 257, 4096, 4097, 20000, 150001, 768000])
+def test_voxel_bit_exact(ctx, oracle, n):
+    rng = np.random.default_rng(1000 + n)
+    pts = random_scene_cloud(rng, n, extent=30.0 if n > 1000 else 3.0)
+    out, keys = ctx.voxel_downsample(pts, 0.5, want_keys=True)
+    ref, rkeys, _ = oracle.voxel_filter(pts, 0.5, want_keys=True)
+    assert bits_equal(keys, rkeys), "voxel keys must be bit-exact"
+    assert len(out) == len(ref)
+    assert bits_equal(out, ref), "centroids must be bit-exact (ascending key, index-ordered fp32 sums)"
+
+
+def test_voxel_other_leaf_and_dense_voxels(ctx, oracle):
+    rng = np.random.default_rng(77)
+    pts = random_scene_cloud(rng, 60000, extent=2.0)   # thousands of points per voxel
+    for leaf in (0.3, 0.5, 1.0):
+        assert bits_equal(ctx.voxel_downsample(pts, leaf), oracle.voxel_filter(pts, leaf))
+
+
+def test_voxel_cell_centres_identity_set(ctx):
+    """KAT: points at distinct cell centres come back unchanged, sorted by key (z, y, x major)."""
+    g = np.arange(-3, 4, dtype=np.float32) * 0.5 + 0.25
+    xx, yy, zz = np.meshgrid(g, g, g, indexing="ij")
+    pts = np.stack([xx.ravel(), yy.ravel(), zz.ravel(), np.arange(xx.size, dtype=np.float32)], 1)
+    rng = np.random.default_rng(3)
+    out = ctx.voxel_downsample(pts[rng.permutation(len(pts))], 0.5)
+    order = np.lexsort((pts[:, 0], pts[:, 1], pts[:, 2]))
+    assert bits_equal(out, pts[order])
+
+
+def test_voxel_overflow_returns_input(ctx, oracle):
+    """PCL: when the index would overflow int32 the input cloud is returned unchanged."""
+    rng = np.random.default_rng(4)
+    pts = rng.uniform(-1e4, 1e4, (1000, 4)).astype(np.float32)
+    with pytest.raises(OverflowError):
+        oracle.voxel_filter(pts, 0.01)
+    out = ctx.voxel_downsample(pts, 0.01)
+    assert bits_equal(out, pts)
+
+
+# ---------------------------------------------------------------- K3 projection
+def test_projection_bit_exact(ctx, oracle):
+    rng = np.random.default_rng(11)
+    pts = rng.uniform(-100, 100, (100003, 4)).astype(np.float32)
+    R, t = rand_pose(rng)
+    assert bits_equal(ctx.cloud_projection(R, t, pts), oracle.project(R, t, pts))
+
+
+# ---------------------------------------------------------------- A2 plane fit
+def test_plane_estimation_parity(ctx, oracle):
+    rng = np.random.default_rng(12)
+    n = 4000
+    pts = np.zeros((n, 5, 4), np.float32)
+    for i in range(n):
+        mode = i % 4
+        nrm = rng.normal(size=3)
+        a, b = rng.uniform(-5, 5, 5), rng.uniform(-5, 5, 5)
+        if mode == 2:
+            p = rng.uniform(-5, 5, (5, 3))
+        elif mode == 3:
+            p = np.stack([a, 2 * a + 1e-4 * rng.normal(size=5), 1 - a + 1e-4 * rng.normal(size=5)], 1)
+        else:
+            z = (-4 - nrm[0] * a - nrm[1] * b) / (abs(nrm[2]) + 0.3) + (0.03 * rng.normal(size=5) if mode == 1 else 0)
+            p = np.stack([a, b, z], 1)
+        pts[i, :, :3] = p
+    ok, unit, ninv, dist = ctx.plane_estimation(pts, 0.1)
+    n_ok = 0
+    for i in range(n):
+        o, u, d, ds = oracle.plane_estimation(pts[i], 0.1)
+        assert o == ok[i]
+        if i % 4 != 3:   # well conditioned: 1e-9 relative (observed: bit-identical)
+            assert block_rel(unit[i], u) <= 1e-9 and abs(ninv[i] - d) <= 1e-9 * abs(d)
+            assert block_rel(dist[i], ds) <= 1e-9 or np.max(np.abs(dist[i] - ds)) < 1e-12
+        n_ok += o
+    assert 0 < n_ok < n
+
+
+def test_plane_kat_z_equals_one(ctx):
+    """KAT: five points on z = 1 give unit normal (0,0,-1), d = 1, all distances 0."""
+    pts = np.zeros((1, 5, 4), np.float32)
+    pts[0, :, :3] = [[0, 0, 1], [1, 0, 1], [0, 1, 1], [1, 1, 1], [0.3, 0.6, 1]]
+    ok, unit, ninv, dist = ctx.plane_estimation(pts, 0.1)
+    assert ok[0]
+    assert np.allclose(unit[0], [0, 0, -1], atol=1e-15) and abs(ninv[0] - 1.0) < 1e-15
+    assert np.max(np.abs(dist[0])) < 1e-15
+
+
+# ---------------------------------------------------------------- A1 kNN
+@pytest.mark.parametrize("m,q,extent", [(0, 10, 5.0), (3, 50, 2.0), (5, 50, 1.0), (2000, 500, 8.0), (60000, 3000, 30.0)])
+def test_knn5_exact(ctx, oracle, m, q, extent):
+    rng = np.random.default_rng(2000 + m)
+    mp = random_scene_cloud(rng, m, extent) if m else np.zeros((0, 4), np.float32)
+    qs = random_scene_cloud(rng, q, extent * 1.2)
+    cnt, idx, d2 = ctx.knn5(mp, qs)
+    for k in range(q):
+        n, ri, rd = oracle.knn5(mp, qs[k, :3])
+        assert cnt[k] == n
+        assert np.array_equal(idx[k, :n], ri[:n]), f"query {k}: kNN index set must be exact"
+        assert bits_equal(d2[k, :n], rd[:n])
+        assert np.all(idx[k, n:] == -1)
+
+
+def test_knn5_ties_broken_by_index(ctx, oracle):
+    """Lattice map + queries at lattice centres: many exactly equidistant neighbours."""
+    g = np.arange(-4, 5, dtype=np.float32)
+    xx, yy, zz = np.meshgrid(g, g, g, indexing="ij")
+    mp = np.stack([xx.ravel(), yy.ravel(), zz.ravel(), np.zeros(xx.size, np.float32)], 1)
+    rng = np.random.default_rng(9)
+    mp = mp[rng.permutation(len(mp))]
+    qs = np.zeros((200, 4), np.float32)
+    qs[:, :3] = rng.integers(-3, 3, (200, 3)) + 0.5
+    cnt, idx, d2 = ctx.knn5(mp, qs)
+    for k in range(len(qs)):
+        n, ri, rd = oracle.knn5(mp, qs[k, :3])
+        assert cnt[k] == n == 5
+        assert np.array_equal(idx[k], ri) and bits_equal(d2[k], rd)
+        assert len(set(d2[k].tolist())) == 1   # all five are equidistant: pure index tie-break
+
+
+# ---------------------------------------------------------------- M1 merge + A3/A4 association
+def _build_window(ctx, oracle, seq, n_keys, frames_per_key, first_id=1000):
+    """Drive GPU and oracle side by side over the same frames; the GPU side is fed the ORACLE's
+    undistorted clouds (staged parity)."""
+    from fflins import api
+    leaf = 0.5
+    F = seq.filter_num
+    keys = []
+    fid = first_id
+    fi = 0
+    for k in range(n_keys):
+        group = []
+        for j in range(frames_per_key):
+            fr = seq.frame(fi)
+            fi += 1
+            und, R, t, _ = oracle.undistort(fr["xyzi"], fr["time"], fr["ins_t"], fr["ins_p"], fr["ins_q"], seq.R_bl,
+                                            seq.t_bl, fr["stamp"], fr["td"], threads=8)
+            dec = oracle.decimate(und, F)
+            down = oracle.voxel_filter(dec, leaf)
+            world = oracle.project(R, t, down)
+            ctx.upload(fid, api.CLOUD_MAP_FULL, und)
+            ctx.upload(fid, api.CLOUD_LIDAR_FULL, dec)
+            ctx.upload(fid, api.CLOUD_LIDAR, down)
+            ctx.upload(fid, api.CLOUD_WORLD, world)
+            ctx.set_pose(fid, R, t)
+            group.append(dict(id=fid, und=und, down=down, world=world, R=R, t=t, fr=fr))
+            fid += 1
+        key = group[-1]
+        # oracle merge (lidar_map.cc:190-211)
+        clouds = [key["und"]]
+        for g in group[:-1]:
+            Rr, tr = oracle.relative_pose(key["R"], key["t"], g["R"], g["t"])
+            clouds.append(oracle.project(Rr, tr, g["und"]))
+        full = np.concatenate(clouds)
+        key["map_full"] = full
+        key["map"] = oracle.voxel_filter(full, leaf)
+        info = ctx.keyframe_merge(key["id"], [g["id"] for g in group[:-1]])
+        assert info.n_map == len(key["map"])
+        for g in group[:-1]:
+            ctx.release(g["id"])
+        ctx.keyframe_add(key["id"])
+        ctx.set_motion(key["id"], key["fr"]["v"], key["fr"]["omega"], key["fr"]["td"])
+        keys.append(key)
+    return keys
+
+
+@pytest.fixture(scope="module")
+def window():
+    from fflins import api, synth
+    from oracle import pyoracle
+    seq = synth.Sequence("robot")
+    c = api.Context(api.default_config(point_filter_num=seq.filter_num))
+    keys = _build_window(c, pyoracle, seq, n_keys=4, frames_per_key=3)
+    yield c, seq, keys
+    c.close()
+
+
+def test_merge_bit_exact(window):
+    from fflins import api
+    c, seq, keys = window
+    for key in keys:
+        assert bits_equal(c.download(key["id"], api.CLOUD_MAP_FULL), key["map_full"])
+        assert bits_equal(c.download(key["id"], api.CLOUD_MAP), key["map"])
+
+
+def test_association_parity(window, oracle):
+    c, seq, keys = window
+    st = c.associate()
+    cur = keys[-1]
+    assert st.n_refs == len(keys) - 1 and st.n_queries == len(cur["down"])
+    total_plane = 0
+    for i, ref in enumerate(keys[:-1]):
+        o = oracle.associate(ref["R"], ref["t"], cur["world"], cur["down"], ref["map"], threads=8)
+        g = c.features(ref["id"], nn_points=True)
+        assert np.array_equal(g["nn_idx"], o["nn_idx"]), "kNN index 5-tuples must be bit-exact"
+        assert bits_equal(g["nn_d2"], o["nn_d2"])
+        assert np.array_equal(g["covered"], o["covered"])
+        assert np.array_equal(g["type"], o["type"]), "feature type flags must be identical"
+        assert block_rel(g["normal"], o["normal"]) <= 1e-9 and block_rel(g["d"], o["d"]) <= 1e-9
+        assert bits_equal(g["normal"], o["normal"]) and bits_equal(g["d"], o["d"])   # observed: identical
+        assert not g["outlier"].any()
+        assert st.num_features[i] == o["num_features"] and st.num_covered[i] == o["num_covered"]
+        found = g["nn_idx"] >= 0
+        assert bits_equal(g["nn_points"][found], ref["map"][g["nn_idx"][found]])
+        total_plane += o["num_features"]
+    assert total_plane > 100, "the synthetic scene must produce plane features"
+
+
+def test_association_empty_map(ctx, oracle):
+    """a keyframe whose map is empty yields FEATURE_NONE everywhere."""
+    from fflins import api
+    rng = np.random.default_rng(8)
+    down = random_scene_cloud(rng, 300, 5.0)
+    ctx.upload(2000, api.CLOUD_MAP, np.zeros((0, 4), np.float32))
+    ctx.set_pose(2000, np.eye(3), np.zeros(3))
+    ctx.upload(2001, api.CLOUD_LIDAR, down)
+    ctx.upload(2001, api.CLOUD_WORLD, down)
+    nf, nc = ctx.associate_pair(2000, 2001)
+    assert (nf, nc) == (0, 0)
+    g = ctx.features(2000)
+    assert np.all(g["type"] == -1) and np.all(g["nn_idx"] == -1)
+    ctx.release(2000)
+    ctx.release(2001)
+
+
+# ---------------------------------------------------------------- F1/F4 factors
+def _factor_inputs(rng, n):
+    p = rng.uniform(-20, 20, (n, 3)).astype(np.float32)
+    nrm = rng.normal(size=(n, 3))
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    d = rng.uniform(-5, 5, n)
+    std = np.full(n, 0.1)
+
+    def pose7(scale_t):
+        q = rng.normal(size=4)
+        q /= np.linalg.norm(q) * (1 + 1e-3 * rng.uniform(-1, 1))
+        return np.concatenate([rng.uniform(-10, 10, 3) * scale_t, q])
+    motion = np.concatenate([rng.normal(0, 3, 3), rng.normal(0, 0.3, 3), [rng.uniform(-0.02, 0.02)],
+                             rng.normal(0, 3, 3), rng.normal(0, 0.3, 3), [rng.uniform(-0.02, 0.02)]])
+    return p, nrm, d, std, motion, pose7(1), pose7(1), pose7(0.02), rng.uniform(-0.02, 0.02)
+
+
+@pytest.mark.parametrize("flags", [0, 1, 1 | 8 | 16, 2, 4])
+def test_factor_batch_parity(ctx, oracle, flags):
+    rng = np.random.default_rng(31 + flags)
+    n = 3001
+    p, nrm, d, std, motion, pr, pc, ext, td = _factor_inputs(rng, n)
+    # make residuals O(1) so that Huber sees both branches
+    r0, _, _, _, _ = oracle.factor_batch(p, nrm, d, std, None, motion, pr, pc, ext, td, reduce=False)
+    d = d - 0.1 * r0 + 0.2 * rng.normal(size=n) * (rng.random(n) < 0.5)
+    r, J = ctx.factor_eval_batch(p, nrm, d, std, motion, pr, pc, ext, td, flags)
+    ro, Jo, _, _, _ = oracle.factor_batch(p, nrm, d, std, None, motion, pr, pc, ext, td, flags=flags, reduce=False)
+    assert (np.abs(ro) > 1).any() and (np.abs(ro) < 1).any()
+    assert block_rel(r, ro) <= 1e-9
+    for lo, hi in ((0, 7), (7, 14), (14, 21), (21, 22)):
+        assert block_rel(J[:, lo:hi], Jo[:, lo:hi]) <= 1e-9
+    assert np.all(J[:, [6, 13, 20]] == 0)
+
+
+def test_factor_kat_coincident_poses(ctx):
+    """KAT: coincident ref/cur poses and a point on the plane give r = 0 and equal-and-opposite
+    position Jacobians (lidar_factor.cc:84,93)."""
+    p = np.array([[1.0, 2.0, 3.0]], np.float32)
+    nrm = np.array([[0.0, 0.0, 1.0]])
+    d = np.array([-3.0])
+    pose = np.array([1.0, -2.0, 0.5, 0, 0, 0, 1.0])
+    ext = np.array([0, 0, 0, 0, 0, 0, 1.0])
+    r, J = ctx.factor_eval_batch(p, nrm, d, np.array([0.1]), np.zeros(14), pose, pose, ext, 0.0)
+    assert abs(r[0]) < 1e-12
+    assert np.allclose(J[0, 0:3], -J[0, 7:10], atol=0, rtol=0)
+    assert np.allclose(J[0, 7:10], [0, 0, 10.0], atol=1e-12)
+
+
+def _window_params(seq, keys, rng):
+    cur = keys[-1]
+    pose_refs = np.stack([seq.imu_pose7(k["fr"]["stamp"], rng, 0.01, 0.002) for k in keys[:-1]])
+    pose_cur = seq.imu_pose7(cur["fr"]["stamp"], rng, 0.01, 0.002)
+    return pose_refs, pose_cur, seq.ext7(), cur["fr"]["td"] + 0.003
+
+
+@pytest.mark.parametrize("flags", [0, 1, 1 | 8 | 16])
+def test_factor_reduce_parity(window, oracle, flags):
+    """K6: per-pair H = sum J^T J, b = -sum J^T r, cost vs. the oracle's sequential sums."""
+    c, seq, keys = window
+    c.associate()
+    rng = np.random.default_rng(50)
+    pose_refs, pose_cur, ext, td = _window_params(seq, keys, rng)
+    cur = keys[-1]
+    refs = [k["id"] for k in keys[:-1]]
+    out = c.window_eval(refs, pose_refs, pose_cur, ext, td, flags)
+    motion_cur = np.concatenate([cur["fr"]["v"], cur["fr"]["omega"], [cur["fr"]["td"]]])
+    for i, ref in enumerate(keys[:-1]):
+        f = c.features(ref["id"])
+        valid = ((f["type"] == 0) & (f["outlier"] == 0)).astype(np.uint8)
+        motion = np.concatenate([ref["fr"]["v"], ref["fr"]["omega"], [ref["fr"]["td"]], motion_cur])
+        q = len(valid)
+        ro, Jo, Ho, bo, co = oracle.factor_batch(cur["down"][:, :3], f["normal"], f["d"], np.full(q, 0.1), valid, motion,
+                                                 pose_refs[i], pose_cur, ext, td, flags=flags)
+        assert out["n_res"][i] == valid.sum() > 50
+        assert block_rel(out["H"][i], Ho) <= 1e-9
+        assert block_rel(out["b"][i], bo) <= 1e-9
+        assert block_rel(out["cost"][i], co) <= 1e-9
+        assert np.array_equal(out["H"][i], out["H"][i].T)
+        # the single-pair entry point returns the same block plus per-residual r, J
+        one = c.factor_eval(ref["id"], cur["id"], pose_refs[i], pose_cur, ext, td, flags)
+        assert bits_equal(one["H"], out["H"][i]) and bits_equal(one["b"], out["b"][i])
+        assert np.array_equal(one["valid"], valid)
+        assert block_rel(one["r"], ro) <= 1e-9 and block_rel(one["J"], Jo) <= 1e-9
+        if flags & 8:
+            assert np.all(out["H"][i][12:19, :] == 0) and np.all(out["b"][i][12:19] == 0)
+
+
+def test_factor_reduce_is_deterministic(window):
+    c, seq, keys = window
+    c.associate()
+    rng = np.random.default_rng(51)
+    pose_refs, pose_cur, ext, td = _window_params(seq, keys, rng)
+    refs = [k["id"] for k in keys[:-1]]
+    a = c.window_eval(refs, pose_refs, pose_cur, ext, td, 1)
+    b = c.window_eval(refs, pose_refs, pose_cur, ext, td, 1)
+    assert bits_equal(a["H"], b["H"]) and bits_equal(a["b"], b["b"])
+
+
+def test_chi2_cull_parity(window, oracle):
+    c, seq, keys = window
+    c.associate()
+    rng = np.random.default_rng(52)
+    pose_refs, pose_cur, ext, td = _window_params(seq, keys, rng)
+    cur = keys[-1]
+    refs = [k["id"] for k in keys[:-1]]
+    before = [c.features(r) for r in refs]
+    cnt = c.window_chi2(refs, pose_refs, pose_cur, ext, td, 3.841)
+    motion_cur = np.concatenate([cur["fr"]["v"], cur["fr"]["omega"], [cur["fr"]["td"]]])
+    for i, ref in enumerate(keys[:-1]):
+        f = before[i]
+        valid = (f["type"] == 0).astype(np.uint8)
+        motion = np.concatenate([ref["fr"]["v"], ref["fr"]["omega"], [ref["fr"]["td"]], motion_cur])
+        mask, n = oracle.chi2(cur["down"][:, :3], f["normal"], f["d"], np.full(len(valid), 0.1), valid, motion,
+                              pose_refs[i], pose_cur, ext, td, 3.841)
+        after = c.features(ref["id"])
+        assert np.array_equal(after["outlier"], mask), "outlier mask must be identical"
+        assert cnt[i] == n
+    # culled residuals drop out of the next evaluation (optimizer.cc:149-153,468)
+    out = c.window_eval(refs, pose_refs, pose_cur, ext, td, 1)
+    for i, r in enumerate(refs):
+        f = c.features(r)
+        assert out["n_res"][i] == ((f["type"] == 0) & (f["outlier"] == 0)).sum()
+
+
+def test_reproject_and_keyframe_window(window, oracle):
+    from fflins import api
+    c, seq, keys = window
+    rng = np.random.default_rng(53)
+    R, t = rand_pose(rng)
+    key = keys[1]
+    c.reproject(key["id"], R, t)
+    assert bits_equal(c.download(key["id"], api.CLOUD_WORLD), oracle.project(R, t, key["down"]))
+    Rg, tg = c.get_pose(key["id"])
+    assert bits_equal(Rg, R) and bits_equal(tg, t)
+    c.reproject(key["id"], key["R"], key["t"])
+    ids = c.keyframe_ids()
+    assert ids == [k["id"] for k in keys]
+    is_key, st = c.keyframe_selection(keys[-1]["id"], 10.0, 9.9)
+    assert not is_key and st[1] == 0 and st[2] < 1e-7
+    is_key, st = c.keyframe_selection(keys[0]["id"], 10.0, 9.9)
+    assert is_key and st[1] > 0.4
