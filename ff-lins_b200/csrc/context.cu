@@ -122,6 +122,7 @@ struct fflins_ctx : public Profiler {
     std::vector<cudaEvent_t> ev_free;
     int prof_cur = -1;
     cudaEvent_t prof_a = nullptr;
+    cudaEvent_t timer_a = nullptr, timer_b = nullptr;
 
     void begin(const char *name, cudaStream_t s) override {
         if (!prof_on) return;
@@ -695,6 +696,8 @@ void fflins_destroy(fflins_ctx *ctx) {
         cudaEventDestroy(r.b);
     }
     for (auto e : ctx->ev_free) cudaEventDestroy(e);
+    if (ctx->timer_a) cudaEventDestroy(ctx->timer_a);
+    if (ctx->timer_b) cudaEventDestroy(ctx->timer_b);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1442,6 +1445,26 @@ int fflins_profile_get(fflins_ctx *ctx, char *names, int32_t names_cap, double *
         if ((int32_t) all.size() + 1 > names_cap) return fail(ctx, FFLINS_E_CAPACITY, "name buffer too small");
         std::memcpy(names, all.c_str(), all.size() + 1);
     }
+    return FFLINS_OK;
+}
+
+int fflins_timer_start(fflins_ctx *ctx) {
+    if (!ctx) return FFLINS_E_INVALID;
+    if (!ctx->timer_a) {
+        CK(cudaEventCreate(&ctx->timer_a));
+        CK(cudaEventCreate(&ctx->timer_b));
+    }
+    CK(cudaEventRecord(ctx->timer_a, ctx->stream));
+    return FFLINS_OK;
+}
+
+int fflins_timer_stop(fflins_ctx *ctx, double *ms) {
+    if (!ctx || !ms || !ctx->timer_a) return FFLINS_E_INVALID;
+    CK(cudaEventRecord(ctx->timer_b, ctx->stream));
+    CK(cudaEventSynchronize(ctx->timer_b));
+    float f = 0;
+    CK(cudaEventElapsedTime(&f, ctx->timer_a, ctx->timer_b));
+    *ms = f;
     return FFLINS_OK;
 }
 

@@ -24,7 +24,7 @@ EXPORTS = [
     "fflins_keyframe_count", "fflins_keyframe_ids", "fflins_associate", "fflins_associate_pair",
     "fflins_features_download", "fflins_features_set_outlier", "fflins_factor_eval_batch", "fflins_factor_eval",
     "fflins_window_eval", "fflins_window_chi2", "fflins_profile_enable", "fflins_profile_reset", "fflins_profile_get",
-    "fflins_launch_count",
+    "fflins_launch_count", "fflins_timer_start", "fflins_timer_stop",
 ]
 
 
@@ -377,6 +377,14 @@ class Context:
         self._ck(self.L.fflins_profile_get(self.h, names, len(names), _p(ms), _p(cnt), k, C.byref(n)))
         nm = names.value.decode().strip().split("\n")
         return {nm[i]: (float(ms[i]), int(cnt[i])) for i in range(k)}
+
+    def timer_start(self):
+        self._ck(self.L.fflins_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self._ck(self.L.fflins_timer_stop(self.h, C.byref(ms)))
+        return ms.value
 
     def launch_count(self):
         return int(self.L.fflins_launch_count(self.h))

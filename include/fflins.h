@@ -220,6 +220,10 @@ int fflins_profile_reset(fflins_ctx *ctx);
 /* names: '\n'-separated kernel names; ms/launches: arrays of `cap`. */
 int fflins_profile_get(fflins_ctx *ctx, char *names, int32_t names_cap, double *ms, int64_t *launches, int32_t cap,
                        int32_t *n);
+/* CUDA-event stopwatch on the context's stream: start records an event, stop records a second
+ * one, waits for it and returns the elapsed device time in milliseconds. */
+int fflins_timer_start(fflins_ctx *ctx);
+int fflins_timer_stop(fflins_ctx *ctx, double *ms);
 /* Total kernels launched by this context so far. */
 int64_t fflins_launch_count(const fflins_ctx *ctx);
 
