@@ -33,7 +33,7 @@ struct Frame {
     int n_raw = 0, n_fallback = 0;
     bool is_key = false;
     // keyframe hash (K4)
-    unsigned long long *hkeys = nullptr;
+    unsigned long long *hkeys = nullptr, *ckeys = nullptr, *cmask = nullptr;
     int *hvals                = nullptr;
     int hcap                  = 0;
     // features stored on this (ref) frame, indexed by the cur frame's points
@@ -247,6 +247,8 @@ void free_frame(fflins_ctx *ctx, Frame *f) {
     for (auto &c : f->c) ctx->pool.release(c.d);
     ctx->pool.release(f->hkeys);
     ctx->pool.release(f->hvals);
+    ctx->pool.release(f->ckeys);
+    ctx->pool.release(f->cmask);
     ctx->pool.release(f->feat.type);
     ctx->pool.release(f->feat.covered);
     ctx->pool.release(f->feat.outlier);
@@ -301,6 +303,7 @@ int ensure_voxel(fflins_ctx *ctx, int n) {
     ctx->vox.block_hist  = (uint32_t *) (b + off[4]);
     ctx->vox.block_heads = (uint32_t *) (b + off[5]);
     ctx->vox.meta        = (int *) (b + off[6]);
+    ctx->vox.seg_start   = (uint32_t *) (b + off[7]);
     ctx->vox.cap         = cap;
     return FFLINS_OK;
 }
@@ -458,13 +461,17 @@ int build_hash(fflins_ctx *ctx, Frame *f) {
     if (hcap > f->hcap) {
         ctx->pool.release(f->hkeys);
         ctx->pool.release(f->hvals);
+        ctx->pool.release(f->ckeys);
+        ctx->pool.release(f->cmask);
         f->hkeys = (unsigned long long *) ctx->pool.alloc((size_t) hcap * 8);
         f->hvals = (int *) ctx->pool.alloc((size_t) hcap * 4);
-        if (!f->hkeys || !f->hvals) return fail(ctx, FFLINS_E_NOMEM, "device allocation failed");
+        f->ckeys = (unsigned long long *) ctx->pool.alloc((size_t) hcap * 8);
+        f->cmask = (unsigned long long *) ctx->pool.alloc((size_t) hcap * 8);
+        if (!f->hkeys || !f->hvals || !f->ckeys || !f->cmask) return fail(ctx, FFLINS_E_NOMEM, "device allocation failed");
     }
     f->hcap = hcap;
     ProfScope ps(ctx->prof(), "hash_build", ctx->stream);
-    launch_hash_build(ctx->stream, m.d, m.n, 1.0f / search_cell(ctx), f->hkeys, f->hvals, hcap);
+    launch_hash_build(ctx->stream, m.d, m.n, 1.0f / search_cell(ctx), f->hkeys, f->hvals, f->ckeys, f->cmask, hcap);
     ctx->launches += (m.n > 0) ? 2 : 1;
     return FFLINS_OK;
 }
@@ -513,6 +520,8 @@ int run_associate(fflins_ctx *ctx, const std::vector<Frame *> &refs, Frame *cur,
         a.map         = r->c[FFLINS_CLOUD_MAP].d;
         a.hkeys       = r->hkeys;
         a.hvals       = r->hvals;
+        a.ckeys       = r->ckeys;
+        a.cmask       = r->cmask;
         a.hmask       = r->hcap - 1;
         a.m           = r->c[FFLINS_CLOUD_MAP].n;
         a.T_ref_world = ref_world(r->pose);
@@ -891,6 +900,30 @@ int fflins_reproject(fflins_ctx *ctx, uint64_t frame_id, const fflins_pose *pose
     return FFLINS_OK;
 }
 
+int fflins_reproject_window(fflins_ctx *ctx, int32_t n, const uint64_t *frame_ids, const fflins_pose *poses) {
+    if (!ctx) return FFLINS_E_INVALID;
+    REQUIRE(n >= 0 && n <= kMaxRefs && (n == 0 || (frame_ids && poses)), "bad argument");
+    ProjectBatch B{};
+    B.count = n;
+    int rc;
+    for (int i = 0; i < n; i++) {
+        Frame *f = find_frame(ctx, frame_ids[i]);
+        if (!f) return fail(ctx, FFLINS_E_NOTFOUND, "unknown frame");
+        f->pose = poses[i];
+        int m   = f->c[FFLINS_CLOUD_LIDAR].n;
+        if ((rc = ensure_cloud(ctx, f->c[FFLINS_CLOUD_WORLD], m))) return rc;
+        f->c[FFLINS_CLOUD_WORLD].n = m;
+        B.n[i]   = m;
+        B.src[i] = f->c[FFLINS_CLOUD_LIDAR].d;
+        B.dst[i] = f->c[FFLINS_CLOUD_WORLD].d;
+        B.T[i]   = to12(poses[i]);
+    }
+    ProfScope ps(ctx->prof(), "reproject", ctx->stream);
+    launch_project_batch(ctx->stream, B);
+    ctx->launches++;
+    return FFLINS_OK;
+}
+
 int fflins_keyframe_selection(fflins_ctx *ctx, uint64_t frame_id, double frame_stamp, double last_key_stamp,
                               int *is_keyframe, double stats[3]) {
     if (!ctx || !is_keyframe) return FFLINS_E_INVALID;
@@ -1022,6 +1055,8 @@ int fflins_knn5(fflins_ctx *ctx, const float *map_xyzi, int32_t m, const float *
     float4 *d_map  = (float4 *) ctx->pool.alloc((size_t) std::max(m, 1) * 16);
     float4 *d_q    = (float4 *) ctx->pool.alloc((size_t) q * 16);
     unsigned long long *hk = (unsigned long long *) ctx->pool.alloc((size_t) hcap * 8);
+    unsigned long long *ck = (unsigned long long *) ctx->pool.alloc((size_t) hcap * 8);
+    unsigned long long *cm = (unsigned long long *) ctx->pool.alloc((size_t) hcap * 8);
     int *hv        = (int *) ctx->pool.alloc((size_t) hcap * 4);
     int32_t *d_idx = (int32_t *) ctx->pool.alloc((size_t) q * 20);
     float *d_d2    = (float *) ctx->pool.alloc((size_t) q * 20);
@@ -1030,20 +1065,22 @@ int fflins_knn5(fflins_ctx *ctx, const float *map_xyzi, int32_t m, const float *
         ctx->pool.release(d_map);
         ctx->pool.release(d_q);
         ctx->pool.release(hk);
+        ctx->pool.release(ck);
+        ctx->pool.release(cm);
         ctx->pool.release(hv);
         ctx->pool.release(d_idx);
         ctx->pool.release(d_d2);
         ctx->pool.release(d_cnt);
     };
-    if (!d_map || !d_q || !hk || !hv || !d_idx || !d_d2 || !d_cnt) {
+    if (!d_map || !d_q || !hk || !ck || !cm || !hv || !d_idx || !d_d2 || !d_cnt) {
         cleanup();
         return fail(ctx, FFLINS_E_NOMEM, "device allocation failed");
     }
     if (m > 0) cudaMemcpyAsync(d_map, map_xyzi, (size_t) m * 16, cudaMemcpyHostToDevice, s);
     cudaMemcpyAsync(d_q, query_xyzi, (size_t) q * 16, cudaMemcpyHostToDevice, s);
     float cell = search_cell(ctx);
-    launch_hash_build(s, d_map, m, 1.0f / cell, hk, hv, hcap);
-    launch_knn5(s, d_map, hk, hv, hcap - 1, m, d_q, q, 1.0f / cell, cell, (int) std::ceil(max_dist / cell) + 1,
+    launch_hash_build(s, d_map, m, 1.0f / cell, hk, hv, ck, cm, hcap);
+    launch_knn5(s, d_map, hk, hv, ck, cm, hcap - 1, m, d_q, q, 1.0f / cell, cell, (int) std::ceil(max_dist / cell) + 1,
                 (float) (max_dist * max_dist), d_idx, d_d2, d_cnt);
     ctx->launches += 3;
     cudaMemcpyAsync(nn_idx, d_idx, (size_t) q * 20, cudaMemcpyDeviceToHost, s);

@@ -45,21 +45,40 @@ __device__ __forceinline__ unsigned hash_cell(u64 k) {
     return (unsigned) k;
 }
 
-__global__ void hash_clear_kernel(u64 *__restrict__ hkeys, int hcap) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hcap; i += gridDim.x * blockDim.x) hkeys[i] = kEmpty;
+// ckeys/cmask: coarse occupancy hash. One entry per 4x4x4 block of fine cells; the 64-bit mask says
+// which of the 64 fine cells hold at least one map point.
+__global__ void hash_clear_kernel(u64 *__restrict__ hkeys, u64 *__restrict__ ckeys, u64 *__restrict__ cmask, int hcap) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hcap; i += gridDim.x * blockDim.x) {
+        hkeys[i] = kEmpty;
+        ckeys[i] = kEmpty;
+        cmask[i] = 0ull;
+    }
 }
 
 // One slot per map point; points sharing a cell occupy consecutive probe positions with equal keys.
 __global__ void hash_insert_kernel(const float4 *__restrict__ map, int m, float inv_cell, u64 *__restrict__ hkeys,
-                                   int *__restrict__ hvals, int hmask) {
+                                   int *__restrict__ hvals, u64 *__restrict__ ckeys, u64 *__restrict__ cmask, int hmask) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
         float4 p = __ldg(map + i);
-        u64 key  = pack_cell((int) floorf(p.x * inv_cell), (int) floorf(p.y * inv_cell), (int) floorf(p.z * inv_cell));
+        int ix = (int) floorf(p.x * inv_cell), iy = (int) floorf(p.y * inv_cell), iz = (int) floorf(p.z * inv_cell);
+        u64 key    = pack_cell(ix, iy, iz);
         unsigned h = hash_cell(key) & hmask;
         while (true) {
             u64 old = atomicCAS(hkeys + h, kEmpty, key);
             if (old == kEmpty) {
                 hvals[h] = i;
+                break;
+            }
+            h = (h + 1) & hmask;
+        }
+        // coarse occupancy: insert-or-find the 4x4x4 block, set the bit of this fine cell
+        u64 ck  = pack_cell(ix >> 2, iy >> 2, iz >> 2);
+        int sub = (ix & 3) | ((iy & 3) << 2) | ((iz & 3) << 4);
+        h       = hash_cell(ck) & hmask;
+        while (true) {
+            u64 old = atomicCAS(ckeys + h, kEmpty, ck);
+            if (old == kEmpty || old == ck) {
+                atomicOr(cmask + h, 1ull << sub);
                 break;
             }
             h = (h + 1) & hmask;
@@ -77,16 +96,61 @@ __device__ __forceinline__ void ins5(u64 &a0, u64 &a1, u64 &a2, u64 &a3, u64 &a4
     }
 }
 
+struct HashView {
+    const float4 *map;
+    const u64 *hkeys;
+    const int *hvals;
+    const u64 *ckeys;
+    const u64 *cmask;
+    int hmask;
+};
+
+// probe one fine cell, push every map point stored under it
+__device__ __forceinline__ void probe_cell(const HashView &H, int fx, int fy, int fz, float qx, float qy, float qz,
+                                           float max_d2, u64 &a0, u64 &a1, u64 &a2, u64 &a3, u64 &a4) {
+    u64 key    = pack_cell(fx, fy, fz);
+    unsigned h = hash_cell(key) & H.hmask;
+    while (true) {
+        u64 k = __ldg(H.hkeys + h);
+        if (k == kEmpty) break;
+        if (k == key) {
+            int idx  = __ldg(H.hvals + h);
+            float4 b = __ldg(H.map + idx);
+            float ex = qx - b.x, ey = qy - b.y, ez = qz - b.z;
+            float d2 = (ex * ex + ey * ey) + ez * ez; // ikd_Tree.cc:1427-1431 (no FMA: -fmad=false)
+            if (d2 <= max_d2) ins5(a0, a1, a2, a3, a4, ((u64) __float_as_uint(d2) << 32) | (unsigned) idx);
+        }
+        h = (h + 1) & H.hmask;
+    }
+}
+
+__device__ __forceinline__ void warp_merge5(u64 a0, u64 a1, u64 a2, u64 a3, u64 a4, u64 best[5]) {
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        u64 mn  = warp_min_u64(a0);
+        best[k] = mn;
+        if (a0 == mn && mn != kInf) { a0 = a1; a1 = a2; a2 = a3; a3 = a4; a4 = kInf; }
+    }
+}
+
+constexpr int kNearShells = 3; // phase A: Chebyshev shells 1..3 of fine cells (7^3 = 343 cells)
+
 // Warp-cooperative exact 5-NN. best[] is warp-uniform on return (kInf = not found).
-__device__ __forceinline__ void warp_knn5(const float4 *__restrict__ map, const u64 *__restrict__ hkeys,
-                                          const int *__restrict__ hvals, int hmask, float qx, float qy, float qz,
-                                          float inv_cell, float cell, int r_max, float max_d2, u64 best[5]) {
+//   Phase A (near): shells r = 1..3 of fine cells, 32 cells per round; stop after the first shell r with
+//     d5 < (r*cell - 1mm)^2 — every unvisited point is then strictly farther than the current 5th.
+//   Phase B (far, only for queries phase A could not close): every 4x4x4 block of the coarse occupancy
+//     hash that intersects the +-r_max search cube, one block per lane; only fine cells whose mask bit is
+//     set are probed. Exhaustive within the cube, so the result stays exact while empty space costs one
+//     coarse probe per 64 cells.
+__device__ __forceinline__ void warp_knn5(const HashView &H, float qx, float qy, float qz, float inv_cell, float cell,
+                                          int r_max, float max_d2, u64 best[5]) {
     const int lane = threadIdx.x & 31;
     const int cx = (int) floorf(qx * inv_cell), cy = (int) floorf(qy * inv_cell), cz = (int) floorf(qz * inv_cell);
     u64 a0 = kInf, a1 = kInf, a2 = kInf, a3 = kInf, a4 = kInf;
-    int r_prev = -1;
+    int r_prev      = -1;
+    const int r_near = min(kNearShells, r_max);
 #pragma unroll 1
-    for (int r = 1; r <= r_max; r++) {
+    for (int r = 1; r <= r_near; r++) {
         const int side = 2 * r + 1, side2 = side * side, total = side2 * side;
 #pragma unroll 1
         for (int t = lane; t < total; t += 32) {
@@ -96,36 +160,47 @@ __device__ __forceinline__ void warp_knn5(const float4 *__restrict__ map, const 
             int dx  = rem - dy * side;
             dx -= r; dy -= r; dz -= r;
             if (max(abs(dx), max(abs(dy), abs(dz))) <= r_prev) continue; // shell interior: already visited
-            u64 key    = pack_cell(cx + dx, cy + dy, cz + dz);
-            unsigned h = hash_cell(key) & hmask;
-            while (true) {
-                u64 k = __ldg(hkeys + h);
-                if (k == kEmpty) break;
-                if (k == key) {
-                    int idx  = __ldg(hvals + h);
-                    float4 b = __ldg(map + idx);
-                    float ex = qx - b.x, ey = qy - b.y, ez = qz - b.z;
-                    float d2 = (ex * ex + ey * ey) + ez * ez; // ikd_Tree.cc:1427-1431 (no FMA: -fmad=false)
-                    if (d2 <= max_d2) ins5(a0, a1, a2, a3, a4, ((u64) __float_as_uint(d2) << 32) | (unsigned) idx);
-                }
-                h = (h + 1) & hmask;
-            }
+            probe_cell(H, cx + dx, cy + dy, cz + dz, qx, qy, qz, max_d2, a0, a1, a2, a3, a4);
         }
         r_prev = r;
-        // warp merge (non-destructive)
-        u64 t0 = a0, t1 = a1, t2 = a2, t3 = a3, t4 = a4;
-#pragma unroll
-        for (int k = 0; k < 5; k++) {
-            u64 mn  = warp_min_u64(t0);
-            best[k] = mn;
-            if (t0 == mn && mn != kInf) { t0 = t1; t1 = t2; t2 = t3; t3 = t4; t4 = kInf; }
-        }
+        warp_merge5(a0, a1, a2, a3, a4, best);
         if (best[4] != kInf) {
             float d5    = __uint_as_float((unsigned) (best[4] >> 32));
             float bound = (float) r * cell - 1e-3f;
-            if (bound > 0.f && d5 < bound * bound) break;
+            if (bound > 0.f && d5 < bound * bound) return;
         }
     }
+    if (r_near >= r_max) return;
+    // ---- phase B
+    const int lox = (cx - r_max) >> 2, loy = (cy - r_max) >> 2, loz = (cz - r_max) >> 2;
+    const int nx = ((cx + r_max) >> 2) - lox + 1, ny = ((cy + r_max) >> 2) - loy + 1, nz = ((cz + r_max) >> 2) - loz + 1;
+    const int total = nx * ny * nz;
+#pragma unroll 1
+    for (int t = lane; t < total; t += 32) {
+        int bz  = t / (nx * ny);
+        int rem = t - bz * (nx * ny);
+        int by  = rem / nx;
+        int bx  = rem - by * nx;
+        bx += lox; by += loy; bz += loz;
+        u64 ck     = pack_cell(bx, by, bz);
+        unsigned h = hash_cell(ck) & H.hmask;
+        u64 mask   = 0ull;
+        while (true) {
+            u64 k = __ldg(H.ckeys + h);
+            if (k == kEmpty) break;
+            if (k == ck) { mask = __ldg(H.cmask + h); break; }
+            h = (h + 1) & H.hmask;
+        }
+        while (mask) {
+            int sub = __ffsll((long long) mask) - 1;
+            mask &= mask - 1;
+            int fx = bx * 4 + (sub & 3), fy = by * 4 + ((sub >> 2) & 3), fz = bz * 4 + (sub >> 4);
+            int ch = max(abs(fx - cx), max(abs(fy - cy), abs(fz - cz)));
+            if (ch <= r_prev || ch > r_max) continue;
+            probe_cell(H, fx, fy, fz, qx, qy, qz, max_d2, a0, a1, a2, a3, a4);
+        }
+    }
+    warp_merge5(a0, a1, a2, a3, a4, best);
 }
 
 __global__ void __launch_bounds__(256)
@@ -142,7 +217,10 @@ associate_kernel(const __grid_constant__ AssocParams P, const float4 *__restrict
     float4 wp  = __ldg(cur_world + k);
     float4 rp  = project_rn(ref.T_ref_world.R, ref.T_ref_world.t, wp);
     u64 best[5] = {kInf, kInf, kInf, kInf, kInf};
-    if (ref.m > 0) warp_knn5(ref.map, ref.hkeys, ref.hvals, ref.hmask, rp.x, rp.y, rp.z, P.inv_cell, P.cell, P.r_max, P.max_d2, best);
+    if (ref.m > 0) {
+        HashView H{ref.map, ref.hkeys, ref.hvals, ref.ckeys, ref.cmask, ref.hmask};
+        warp_knn5(H, rp.x, rp.y, rp.z, P.inv_cell, P.cell, P.r_max, P.max_d2, best);
+    }
 
     int found = 0;
 #pragma unroll
@@ -189,7 +267,8 @@ associate_kernel(const __grid_constant__ AssocParams P, const float4 *__restrict
 }
 
 __global__ void __launch_bounds__(256)
-knn5_kernel(const float4 *__restrict__ map, const u64 *__restrict__ hkeys, const int *__restrict__ hvals, int hmask, int m,
+knn5_kernel(const float4 *__restrict__ map, const u64 *__restrict__ hkeys, const int *__restrict__ hvals,
+            const u64 *__restrict__ ckeys, const u64 *__restrict__ cmask, int hmask, int m,
             const float4 *__restrict__ query, int q, float inv_cell, float cell, int r_max, float max_d2,
             int32_t *__restrict__ nn_idx, float *__restrict__ nn_d2, int32_t *__restrict__ nn_count) {
     const int lane  = threadIdx.x & 31;
@@ -197,7 +276,10 @@ knn5_kernel(const float4 *__restrict__ map, const u64 *__restrict__ hkeys, const
     if (gwarp >= q) return;
     float4 qp   = __ldg(query + gwarp);
     u64 best[5] = {kInf, kInf, kInf, kInf, kInf};
-    if (m > 0) warp_knn5(map, hkeys, hvals, hmask, qp.x, qp.y, qp.z, inv_cell, cell, r_max, max_d2, best);
+    if (m > 0) {
+        HashView H{map, hkeys, hvals, ckeys, cmask, hmask};
+        warp_knn5(H, qp.x, qp.y, qp.z, inv_cell, cell, r_max, max_d2, best);
+    }
     int found = 0;
 #pragma unroll
     for (int j = 0; j < 5; j++) found += (best[j] != kInf) ? 1 : 0;
@@ -233,14 +315,14 @@ __global__ void plane_estimation_kernel(const float4 *__restrict__ pts, int n, d
 } // namespace
 
 void launch_hash_build(cudaStream_t s, const float4 *map, int m, float inv_cell, unsigned long long *hkeys, int *hvals,
-                       int hcap) {
+                       unsigned long long *ckeys, unsigned long long *cmask, int hcap) {
     int g = (hcap + 255) / 256;
     if (g > 148 * 8) g = 148 * 8;
-    hash_clear_kernel<<<g, 256, 0, s>>>(hkeys, hcap);
+    hash_clear_kernel<<<g, 256, 0, s>>>(hkeys, ckeys, cmask, hcap);
     if (m > 0) {
         int gi = (m + 255) / 256;
         if (gi > 148 * 8) gi = 148 * 8;
-        hash_insert_kernel<<<gi, 256, 0, s>>>(map, m, inv_cell, hkeys, hvals, hcap - 1);
+        hash_insert_kernel<<<gi, 256, 0, s>>>(map, m, inv_cell, hkeys, hvals, ckeys, cmask, hcap - 1);
     }
 }
 
@@ -251,11 +333,11 @@ void launch_associate(cudaStream_t s, const AssocParams &p, const float4 *cur_wo
     associate_kernel<<<grid, 256, 0, s>>>(p, cur_world, cur_lidar);
 }
 
-void launch_knn5(cudaStream_t s, const float4 *map, const unsigned long long *hkeys, const int *hvals, int hmask, int m,
-                 const float4 *query, int q, float inv_cell, float cell, int r_max, float max_d2, int32_t *nn_idx,
+void launch_knn5(cudaStream_t s, const float4 *map, const unsigned long long *hkeys, const int *hvals,
+                 const unsigned long long *ckeys, const unsigned long long *cmask, int hmask, int m, const float4 *query, int q, float inv_cell, float cell, int r_max, float max_d2, int32_t *nn_idx,
                  float *nn_d2, int32_t *nn_count) {
     if (q <= 0) return;
-    knn5_kernel<<<(q + 7) / 8, 256, 0, s>>>(map, hkeys, hvals, hmask, m, query, q, inv_cell, cell, r_max, max_d2, nn_idx,
+    knn5_kernel<<<(q + 7) / 8, 256, 0, s>>>(map, hkeys, hvals, ckeys, cmask, hmask, m, query, q, inv_cell, cell, r_max, max_d2, nn_idx,
                                             nn_d2, nn_count);
 }
 

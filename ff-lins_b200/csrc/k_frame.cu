@@ -156,6 +156,15 @@ project_dev_kernel(const Pose12 *__restrict__ Tp, const float4 *__restrict__ src
         dst[k] = project_rn(T.R, T.t, src[k]);
 }
 
+__global__ void __launch_bounds__(256) project_batch_kernel(const __grid_constant__ ProjectBatch B) {
+    const int c = blockIdx.y;
+    const int n = B.n[c];
+    const float4 *__restrict__ src = B.src[c];
+    float4 *__restrict__ dst       = B.dst[c];
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
+        dst[k] = project_rn(B.T[c].R, B.T[c].t, src[k]);
+}
+
 inline int grid_for(int n, int block, int per_sm = 8) {
     int g = (n + block - 1) / block;
     int cap = 148 * per_sm;
@@ -192,6 +201,14 @@ void launch_copy_decimate(cudaStream_t s, const float4 *xyzi, int n, int filter_
 void launch_project(cudaStream_t s, Pose12 T, const float4 *src, float4 *dst, int n, const int *n_dev) {
     if (n <= 0) return;
     project_kernel<<<grid_for(n, 256), 256, 0, s>>>(T, src, dst, n, n_dev);
+}
+
+void launch_project_batch(cudaStream_t s, const ProjectBatch &b) {
+    int nmax = 0;
+    for (int i = 0; i < b.count; i++) nmax = b.n[i] > nmax ? b.n[i] : nmax;
+    if (b.count <= 0 || nmax <= 0) return;
+    dim3 grid(grid_for(nmax, 256), b.count);
+    project_batch_kernel<<<grid, 256, 0, s>>>(b);
 }
 
 void launch_project_dev(cudaStream_t s, const Pose12 *T_dev, const float4 *src, float4 *dst, int n, const int *n_dev) {

@@ -270,17 +270,13 @@ seg_count_kernel(const uint32_t *__restrict__ k0, const uint32_t *__restrict__ k
     }
 }
 
+// Second pass over the head flags: every head learns its output slot (CTA base from the per-CTA
+// counts + in-CTA scan) and records where its segment starts.
 __global__ void __launch_bounds__(SEG_THREADS)
-seg_centroid_kernel(const float4 *__restrict__ in, const uint32_t *__restrict__ k0, const uint32_t *__restrict__ k1,
-                    const uint32_t *__restrict__ x0, const uint32_t *__restrict__ x1, int *__restrict__ meta, int n,
-                    const uint32_t *__restrict__ block_heads, float4 *__restrict__ out, int *__restrict__ d_nout) {
-    const int parity = meta[M_PARITY + 4];
-    const uint32_t *keys = parity ? k1 : k0;
-    const uint32_t *idx  = parity ? x1 : x0;
+seg_starts_kernel(const uint32_t *__restrict__ k0, const uint32_t *__restrict__ k1, int *__restrict__ meta, int n,
+                  const uint32_t *__restrict__ block_heads, uint32_t *__restrict__ seg_start, int *__restrict__ d_nout) {
+    const uint32_t *keys = meta[M_PARITY + 4] ? k1 : k0;
     if (meta[M_OVERFLOW]) {
-        // PCL: "leaf size too small": the input cloud is returned unchanged
-        for (int i = blockIdx.x * SEG_TILE + threadIdx.x; i < min(n, (blockIdx.x + 1) * SEG_TILE); i += SEG_THREADS)
-            out[i] = in[i];
         if (blockIdx.x == 0 && threadIdx.x == 0) {
             *d_nout      = n;
             meta[M_NOUT] = n;
@@ -318,30 +314,189 @@ seg_centroid_kernel(const float4 *__restrict__ in, const uint32_t *__restrict__ 
     for (int w = 0; w < wid; w++) woff += ws[w];
     int slot = s_base + woff + incl - c;
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == SEG_THREADS - 1) {
-        int total = s_base + woff + incl;
-        *d_nout      = total;
-        meta[M_NOUT] = total;
+        int total        = s_base + woff + incl;
+        *d_nout          = total;
+        meta[M_NOUT]     = total;
+        seg_start[total] = (uint32_t) n; // sentinel
     }
 #pragma unroll
-    for (int j = 0; j < SEG_ITEMS; j++) {
-        if (!head[j]) continue;
-        int i        = base + j;
-        uint32_t key = keys[i];
+    for (int j = 0; j < SEG_ITEMS; j++)
+        if (head[j]) seg_start[slot++] = (uint32_t) (base + j);
+}
+
+// One warp per voxel: the lanes gather 32 points of the segment at a time (coalesced index read,
+// 16-byte point gathers in flight together) into shared memory, then the fp32 sums are accumulated
+// in ascending original index — sequentially, because fp32 addition is not associative and the
+// result must equal PCL's (Appendix A.1 step 7). Every lane runs the same chain; lane 0 stores.
+constexpr int CEN_THREADS = 256;
+__global__ void __launch_bounds__(CEN_THREADS)
+seg_centroid_kernel(const float4 *__restrict__ in, const uint32_t *__restrict__ x0, const uint32_t *__restrict__ x1,
+                    const int *__restrict__ meta, int n, const uint32_t *__restrict__ seg_start, float4 *__restrict__ out) {
+    if (meta[M_OVERFLOW]) {
+        // PCL: "leaf size too small": the input cloud is returned unchanged
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = in[i];
+        return;
+    }
+    __shared__ float4 stage[CEN_THREADS / 32][32];
+    const uint32_t *idx = meta[M_PARITY + 4] ? x1 : x0;
+    const int n_seg     = meta[M_NOUT];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int warps = gridDim.x * (CEN_THREADS / 32);
+    for (int s = blockIdx.x * (CEN_THREADS / 32) + wid; s < n_seg; s += warps) {
+        const int start = (int) seg_start[s], end = (int) seg_start[s + 1];
+        float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+        for (int base = start; base < end; base += 32) {
+            int e = base + lane;
+            if (e < end) stage[wid][lane] = __ldg(in + idx[e]);
+            __syncwarp();
+            const int cnt = min(32, end - base);
+#pragma unroll 4
+            for (int j = 0; j < cnt; j++) {
+                float4 p = stage[wid][j];
+                sx += p.x;
+                sy += p.y;
+                sz += p.z;
+                si += p.w;
+            }
+            __syncwarp();
+        }
+        if (lane == 0) {
+            float cnt = (float) (end - start);
+            out[s]    = make_float4(sx / cnt, sy / cnt, sz / cnt, si / cnt);
+        }
+    }
+}
+
+// ---- small clouds (n <= SMALL_CAP): the whole filter in ONE CTA ---------------------------------------
+// bbox -> keys -> bitonic sort of 64-bit (key << 32 | index) composites in shared memory (unique, so
+// the unstable network yields exactly the stable order) -> heads -> ordered centroid. Replaces 18
+// launch-latency-bound launches for the per-frame filter of ~2-3 k decimated points.
+constexpr int SMALL_CAP     = 8192;
+constexpr int SMALL_THREADS = 1024;
+
+__global__ void __launch_bounds__(SMALL_THREADS)
+vox_small_kernel(const float4 *__restrict__ in, int n, float inv, int *__restrict__ meta, float4 *__restrict__ out,
+                 int *__restrict__ d_nout, int32_t *__restrict__ keys_out) {
+    extern __shared__ unsigned long long comp[]; // npad composites
+    __shared__ float s_mn[3][32], s_mx[3][32];
+    __shared__ int s_bbox[6];
+    __shared__ int s_ws[32];
+    __shared__ int s_total;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    int npad = 32;
+    while (npad < n) npad <<= 1;
+    // 1. bounding box
+    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int i = tid; i < n; i += SMALL_THREADS) {
+        float4 p = __ldg(in + i);
+        mn[0] = fminf(mn[0], p.x); mx[0] = fmaxf(mx[0], p.x);
+        mn[1] = fminf(mn[1], p.y); mx[1] = fmaxf(mx[1], p.y);
+        mn[2] = fminf(mn[2], p.z); mx[2] = fmaxf(mx[2], p.z);
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+            mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+        }
+        if (lane == 0) { s_mn[a][wid] = mn[a]; s_mx[a][wid] = mx[a]; }
+    }
+    __syncthreads();
+    if (wid == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            float v = s_mn[a][lane], u = s_mx[a][lane];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+                u = fmaxf(u, __shfl_xor_sync(0xffffffffu, u, o));
+            }
+            if (lane == 0) { s_bbox[a] = f2ord(v); s_bbox[3 + a] = f2ord(u); }
+        }
+    }
+    __syncthreads();
+    Grid3 g = make_grid(s_bbox, inv);
+    if (tid == 0) {
+        meta[M_OVERFLOW] = g.overflow ? 1 : 0;
+        meta[M_NBITS]    = g.nbits;
+    }
+    if (g.overflow) {
+        for (int i = tid; i < n; i += SMALL_THREADS) {
+            out[i] = in[i];
+            if (keys_out) keys_out[i] = 0;
+        }
+        if (tid == 0) { *d_nout = n; meta[M_NOUT] = n; }
+        return;
+    }
+    // 2. keys -> composites
+    for (int i = tid; i < npad; i += SMALL_THREADS) {
+        unsigned long long c = 0xffffffffffffffffull;
+        if (i < n) {
+            float4 p = __ldg(in + i);
+            int i0   = (int) (floorf(__fmul_rn(p.x, inv)) - (float) g.min_b[0]);
+            int i1   = (int) (floorf(__fmul_rn(p.y, inv)) - (float) g.min_b[1]);
+            int i2   = (int) (floorf(__fmul_rn(p.z, inv)) - (float) g.min_b[2]);
+            int key  = i0 + i1 * g.mul1 + i2 * g.mul2;
+            if (keys_out) keys_out[i] = key;
+            c = ((unsigned long long) (uint32_t) key << 32) | (uint32_t) i;
+        }
+        comp[i] = c;
+    }
+    __syncthreads();
+    // 3. bitonic sort, ascending
+    for (int k = 2; k <= npad; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < (npad >> 1); t += SMALL_THREADS) {
+                int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                int hi = lo | j;
+                unsigned long long a = comp[lo], b = comp[hi];
+                bool up = (lo & k) == 0;
+                if ((a > b) == up) { comp[lo] = b; comp[hi] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    // 4. heads -> slots (blocked: thread t owns items [t*per, (t+1)*per))
+    const int per = (npad + SMALL_THREADS - 1) / SMALL_THREADS;
+    const int lo  = tid * per, hi = min(n, lo + per);
+    int c = 0;
+    for (int i = lo; i < hi; i++) c += (i == 0 || (comp[i] >> 32) != (comp[i - 1] >> 32)) ? 1 : 0;
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_ws[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        int w = s_ws[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int v = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += v;
+        }
+        s_ws[lane] = wi - w;
+        if (lane == 31) s_total = wi;
+    }
+    __syncthreads();
+    int slot = s_ws[wid] + incl - c;
+    // 5. ordered centroid: one thread per head, sequential fp32 adds in ascending index
+    for (int i = lo; i < hi; i++) {
+        uint32_t key = (uint32_t) (comp[i] >> 32);
+        if (!(i == 0 || (uint32_t) (comp[i - 1] >> 32) != key)) continue;
         float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
         int e = i;
-        // ascending original index inside the voxel: sequential fp32 adds (Appendix A.1 step 7)
-        while (e < n && keys[e] == key) {
-            float4 p = __ldg(in + idx[e]);
-            sx += p.x;
-            sy += p.y;
-            sz += p.z;
-            si += p.w;
+        while (e < n && (uint32_t) (comp[e] >> 32) == key) {
+            float4 p = __ldg(in + (uint32_t) (comp[e] & 0xffffffffu));
+            sx += p.x; sy += p.y; sz += p.z; si += p.w;
             e++;
         }
-        float cnt = (float) (e - i);
-        out[slot] = make_float4(sx / cnt, sy / cnt, sz / cnt, si / cnt);
-        slot++;
+        float cnt   = (float) (e - i);
+        out[slot++] = make_float4(sx / cnt, sy / cnt, sz / cnt, si / cnt);
     }
+    if (tid == 0) { *d_nout = s_total; meta[M_NOUT] = s_total; }
 }
 
 } // namespace
@@ -358,6 +513,7 @@ size_t voxel_work_bytes(int cap, size_t *off) {
     off[4] = o; o += al(256 * nb * 4);
     off[5] = o; o += al(nb2 * 4);
     off[6] = o; o += al(M_SIZE * 4);
+    off[7] = o; o += al(((size_t) cap + 1) * 4);
     return o;
 }
 
@@ -369,13 +525,28 @@ int launch_voxel_downsample(cudaStream_t s, const VoxelWork &w, const float4 *in
     }
     if (n > w.cap) return -1;
     const float inv = 1.0f / leaf;
-    int g           = (n + 255) / 256;
-    if (g > 148 * 8) g = 148 * 8;
     char name[64];
     auto nm = [&](const char *k) {
         snprintf(name, sizeof(name), "%s.%s", tag, k);
         return name;
     };
+    if (n <= SMALL_CAP) {
+        static bool attr_set[64] = {false};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!attr_set[dev & 63]) {
+            cudaFuncSetAttribute(vox_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_CAP * 8);
+            attr_set[dev & 63] = true;
+        }
+        int npad = 32;
+        while (npad < n) npad <<= 1;
+        ProfScope ps(prof, nm("one_cta"), s);
+        vox_small_kernel<<<1, SMALL_THREADS, (size_t) npad * 8, s>>>(in, n, inv, w.meta, out, d_nout, keys_out);
+        if (launches) *launches += 1;
+        return 0;
+    }
+    int g = (n + 255) / 256;
+    if (g > 148 * 8) g = 148 * 8;
     {
         ProfScope ps(prof, nm("bbox_keys"), s);
         vox_init_kernel<<<1, 32, 0, s>>>(w.meta);
@@ -396,10 +567,12 @@ int launch_voxel_downsample(cudaStream_t s, const VoxelWork &w, const float4 *in
     {
         ProfScope ps(prof, nm("centroid"), s);
         seg_count_kernel<<<nb2, SEG_THREADS, 0, s>>>(w.keys[0], w.keys[1], w.meta, n, w.block_heads);
-        seg_centroid_kernel<<<nb2, SEG_THREADS, 0, s>>>(in, w.keys[0], w.keys[1], w.idx[0], w.idx[1], w.meta, n,
-                                                        w.block_heads, out, d_nout);
+        seg_starts_kernel<<<nb2, SEG_THREADS, 0, s>>>(w.keys[0], w.keys[1], w.meta, n, w.block_heads, w.seg_start, d_nout);
+        int gc = (n + 7) / 8;
+        if (gc > 148 * 8) gc = 148 * 8;
+        seg_centroid_kernel<<<gc, CEN_THREADS, 0, s>>>(in, w.idx[0], w.idx[1], w.meta, n, w.seg_start, out);
     }
-    if (launches) *launches += 3 + 12 + 2;
+    if (launches) *launches += 3 + 12 + 3;
     return 0;
 }
 

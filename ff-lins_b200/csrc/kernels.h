@@ -41,6 +41,15 @@ void launch_copy_decimate(cudaStream_t s, const float4 *xyzi, int n, int filter_
 // ---- K3 rigid projection (pointcloud.cc:38-59). n_dev (optional) overrides n with a device count.
 void launch_project(cudaStream_t s, Pose12 T, const float4 *src, float4 *dst, int n, const int *n_dev);
 // same with the pose read from device memory (the frame pose produced by launch_ins_prep)
+// up to kMaxRefs clouds in one launch (blockIdx.y selects the cloud)
+struct ProjectBatch {
+    int count;
+    int n[kMaxRefs];
+    const float4 *src[kMaxRefs];
+    float4 *dst[kMaxRefs];
+    Pose12 T[kMaxRefs];
+};
+void launch_project_batch(cudaStream_t s, const ProjectBatch &b);
 void launch_project_dev(cudaStream_t s, const Pose12 *T_dev, const float4 *src, float4 *dst, int n, const int *n_dev);
 
 // ---- K2 voxel downsample (pcl::VoxelGrid) --------------------------------------
@@ -49,6 +58,7 @@ struct VoxelWork {
     uint32_t *idx[2]    = {nullptr, nullptr};
     uint32_t *block_hist = nullptr; // 256 * nblocks
     uint32_t *block_heads = nullptr;
+    uint32_t *seg_start  = nullptr; // cap + 1
     int      *meta      = nullptr;  // see k_voxel.cu
     int       cap       = 0;        // points capacity
 };
@@ -59,8 +69,10 @@ int launch_voxel_downsample(cudaStream_t s, const VoxelWork &w, const float4 *in
                             int *d_nout, int32_t *keys_out, int64_t *launches, Profiler *prof, const char *tag);
 
 // ---- K4 keyframe hash insert (replaces ikd_Tree::build, lidar_map.cc:100-118) -------------------------
+// hkeys/hvals: fine hash (cell -> map index, one slot per point); ckeys/cmask: coarse occupancy hash
+// (4x4x4 fine cells per entry, 64-bit mask). All four arrays have hcap entries.
 void launch_hash_build(cudaStream_t s, const float4 *map, int m, float inv_cell, unsigned long long *hkeys,
-                       int *hvals, int hcap);
+                       int *hvals, unsigned long long *ckeys, unsigned long long *cmask, int hcap);
 
 // ---- K5 association (lidar_map.cc:326-408, pointcloud.cc:61-93, ikd_Tree.cc:897-924) -------------------
 struct FeatureSoA {
@@ -76,6 +88,8 @@ struct AssocRef {
     const float4 *map;
     const unsigned long long *hkeys;
     const int *hvals;
+    const unsigned long long *ckeys;
+    const unsigned long long *cmask;
     int hmask;
     int m;
     Pose12 T_ref_world;
@@ -95,8 +109,8 @@ struct AssocParams {
 };
 void launch_associate(cudaStream_t s, const AssocParams &p, const float4 *cur_world, const float4 *cur_lidar);
 // brute-force-free stand-alone 5-NN against a hash (fflins_knn5)
-void launch_knn5(cudaStream_t s, const float4 *map, const unsigned long long *hkeys, const int *hvals, int hmask,
-                 int m, const float4 *query, int q, float inv_cell, float cell, int r_max, float max_d2,
+void launch_knn5(cudaStream_t s, const float4 *map, const unsigned long long *hkeys, const int *hvals,
+                 const unsigned long long *ckeys, const unsigned long long *cmask, int hmask, int m, const float4 *query, int q, float inv_cell, float cell, int r_max, float max_d2,
                  int32_t *nn_idx, float *nn_d2, int32_t *nn_count);
 void launch_plane_estimation(cudaStream_t s, const float4 *pts, int n, double thr, double *unit, double *ninv,
                              double *dist, uint8_t *ok);

@@ -24,7 +24,7 @@ EXPORTS = [
     "fflins_keyframe_count", "fflins_keyframe_ids", "fflins_associate", "fflins_associate_pair",
     "fflins_features_download", "fflins_features_set_outlier", "fflins_factor_eval_batch", "fflins_factor_eval",
     "fflins_window_eval", "fflins_window_chi2", "fflins_profile_enable", "fflins_profile_reset", "fflins_profile_get",
-    "fflins_launch_count", "fflins_timer_start", "fflins_timer_stop",
+    "fflins_launch_count", "fflins_timer_start", "fflins_timer_stop", "fflins_reproject_window",
 ]
 
 
@@ -205,6 +205,22 @@ class Context:
     def reproject(self, fid, R, t):
         pose = Pose.make(R, t)
         self._ck(self.L.fflins_reproject(self.h, C.c_uint64(fid), C.byref(pose)))
+
+    def reproject_window(self, ids, poses):
+        """poses: ctypes array (Pose * n) or list of (R, t)."""
+        ids = np.array(list(ids), np.uint64)
+        n = len(ids)
+        if not isinstance(poses, C.Array):
+            arr = (Pose * n)()
+            for i, (R, t) in enumerate(poses):
+                arr[i] = Pose.make(R, t)
+            poses = arr
+        self._ck(self.L.fflins_reproject_window(self.h, n, _p(ids), poses))
+
+    def get_pose_struct(self, fid):
+        pose = Pose()
+        self._ck(self.L.fflins_frame_get_pose(self.h, C.c_uint64(fid), C.byref(pose)))
+        return pose
 
     def keyframe_selection(self, fid, stamp, last_stamp):
         k = C.c_int()

@@ -23,6 +23,9 @@ class Session:
         self.flags = flags
         self.nonkeys = []
         self.key_stamps = {}
+        self.key_pose7 = {}
+        self.key_pose = {}
+        self.last_info = {}
         self.next_id = 0
         self.window = ctx.cfg.window_size
         self.pose_bl = api.Pose.make(seq.R_bl, seq.t_bl)
@@ -35,6 +38,7 @@ class Session:
         self.next_id += 1
         info = self.ctx.frame_process(fid, fr["xyzi"], fr["time"], fr["ins_t"], fr["ins_p"], fr["ins_q"],
                                       self.seq.R_bl, self.seq.t_bl, fr["stamp"], fr["td"])
+        self.last_info = {fid: info}
         return fid, info
 
     def process_frame_dev(self, fr_dev):
@@ -44,6 +48,7 @@ class Session:
         info = self.ctx.frame_process_dev(fid, fr_dev["xyzi"], fr_dev["time"], fr_dev["n"], fr_dev["ins_t"],
                                           fr_dev["ins_p"], fr_dev["ins_q"], fr_dev["w"], self.pose_bl,
                                           fr_dev["stamp"], fr_dev["td"])
+        self.last_info = {fid: info}
         return fid, info
 
     def after_frame(self, fid, fr, force_key=None):
@@ -60,12 +65,15 @@ class Session:
         ctx.keyframe_add(fid)
         ctx.set_motion(fid, fr["v"], fr["omega"], fr["td"])
         self.key_stamps[fid] = fr["stamp"]
+        self.key_pose7[fid] = fr["pose7"] if "pose7" in fr else self.seq.imu_pose7(fr["stamp"])
+        self.key_pose[fid] = self.last_info[fid].pose
         ids = ctx.keyframe_ids()
         if len(ids) >= 2:
             self.last["assoc"] = ctx.associate()
             refs = ids[:-1]
-            pose_refs = np.stack([self.seq.imu_pose7(self.key_stamps[r]) for r in refs])
-            pose_cur = self.seq.imu_pose7(self.key_stamps[fid])
+            # solver state: IMU pose blocks of the keyframes (precomputed per frame when available)
+            pose_refs = np.stack([self.key_pose7[r] for r in refs])
+            pose_cur = self.key_pose7[fid]
             out = None
             # first solve: n_eval[0] LM iterations' worth of evaluations
             for _ in range(self.n_eval[0]):
@@ -75,10 +83,11 @@ class Session:
                 out = ctx.window_eval(refs, pose_refs, pose_cur, self.ext7, fr["td"], self.flags, out)
             self.last["eval"] = out
             # updateParametersFromOptimizer: re-project every keyframe (optimizer.cc:203-218)
-            for k in ids:
-                R, t = ctx.get_pose(k)
-                ctx.reproject(k, R, t)
+            poses = (api.Pose * len(ids))(*[self.key_pose[k] for k in ids])
+            ctx.reproject_window(ids, poses)
         if len(ids) > self.window:
             rid = ctx.keyframe_remove_oldest()
             self.key_stamps.pop(rid, None)
+            self.key_pose7.pop(rid, None)
+            self.key_pose.pop(rid, None)
         return True

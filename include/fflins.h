@@ -146,6 +146,9 @@ int fflins_frame_set_motion(fflins_ctx *ctx, uint64_t frame_id, const double v[3
 int fflins_frame_release(fflins_ctx *ctx, uint64_t frame_id);
 /* setPose + pointCloudProjection(lidar -> world) (optimizer.cc:203-218). */
 int fflins_reproject(fflins_ctx *ctx, uint64_t frame_id, const fflins_pose *pose);
+/* The whole loop of Optimizer::updateParametersFromOptimizer (optimizer.cc:203-218) in one launch:
+ * setPose + lidar->world projection for n (<= 16) frames. */
+int fflins_reproject_window(fflins_ctx *ctx, int32_t n, const uint64_t *frame_ids, const fflins_pose *poses);
 /* LidarMap::keyframeSelection (lidar_map.cc:77-98): host arithmetic on stored poses. */
 int fflins_keyframe_selection(fflins_ctx *ctx, uint64_t frame_id, double frame_stamp, double last_key_stamp,
                               int *is_keyframe, double stats[3]);
