@@ -134,16 +134,17 @@ def run_ours(args, rank, world, local_rank):
     host, dev = [], []
     for fr in frames:
         h = {k: torch.from_numpy(np.ascontiguousarray(fr[k])).pin_memory() for k in ("xyzi", "time", "ins_t", "ins_p", "ins_q")}
-        d = {k: v.cuda() for k, v in h.items()}
+        d = {k: h[k].cuda() for k in ("xyzi", "time")}
         host.append({**{k: v.numpy() for k, v in h.items()}, "stamp": fr["stamp"], "td": fr["td"], "v": fr["v"],
                      "omega": fr["omega"], "_keep": h})
-        dev.append({"xyzi": d["xyzi"].data_ptr(), "time": d["time"].data_ptr(), "ins_t": d["ins_t"].data_ptr(),
-                    "ins_p": d["ins_p"].data_ptr(), "ins_q": d["ins_q"].data_ptr(), "n": n, "w": w,
-                    "stamp": fr["stamp"], "td": fr["td"], "_keep": d})
+        dev.append({"xyzi": d["xyzi"].data_ptr(), "time": d["time"].data_ptr(), "ins_t": h["ins_t"].numpy(),
+                    "ins_p": h["ins_p"].numpy(), "ins_q": h["ins_q"].numpy(), "n": n, "w": w,
+                    "stamp": fr["stamp"], "td": fr["td"], "_keep": (d, h)})
     torch.cuda.synchronize()
     input_bytes = P * (n * 24 + w * 64)
 
-    sess = Session(ctx, seq, FRAMES_PER_KEY, N_EVAL)
+    trace = {} if os.environ.get("FFLINS_TRACE") else None
+    sess = Session(ctx, seq, FRAMES_PER_KEY, N_EVAL, trace=trace)
     state = {"frame": 0}
 
     def step(mode):
@@ -189,6 +190,10 @@ def run_ours(args, rank, world, local_rank):
     sampler.start()
     dev_ms, wall_ms, launches = timed("dev", args.steps)
     clocks = sampler.stop()
+    if trace is not None and rank == 0:
+        for k, (t, c) in sorted(trace.items(), key=lambda kv: -kv[1][0]):
+            print(f"trace {k:24s} calls={c:6d} total={t * 1e3:9.2f} ms avg={t / c * 1e6:8.1f} us", file=sys.stderr)
+        trace.clear()
     for _ in range(warm):
         step("host")
     e2e_dev_ms, e2e_wall_ms, _ = timed("host", args.steps)

@@ -4,6 +4,7 @@
 // There is no CPU fallback: a missing CUDA device fails fflins_create.
 #include "../../include/fflins.h"
 #include "kernels.h"
+#include "math_undistort.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -234,10 +235,9 @@ int ensure_cloud(fflins_ctx *ctx, Cloud &c, int n, bool keep = false) {
     if (!p) return fail(ctx, FFLINS_E_NOMEM, "device allocation failed");
     if (keep && c.d && c.n > 0)
         cudaMemcpyAsync(p, c.d, (size_t) c.n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream);
-    if (c.d) {
-        if (keep) cudaStreamSynchronize(ctx->stream);
-        ctx->pool.release(c.d);
-    }
+    // single-stream context: handing the old block back to the pool right away is safe, every later
+    // use of it is ordered after the copy above
+    if (c.d) ctx->pool.release(c.d);
     c.d   = p;
     c.cap = (int) (want / sizeof(float4));
     return FFLINS_OK;
@@ -278,7 +278,7 @@ int ensure_ins(fflins_ctx *ctx, int w) {
     ctx->pool.release(ctx->d_tab);
     int cap    = std::max(w, 2048);
     ctx->d_ins = (double *) ctx->pool.alloc((size_t) cap * 8 * sizeof(double));
-    ctx->d_tab = (double *) ctx->pool.alloc((size_t) cap * 6 * sizeof(double));
+    ctx->d_tab = (double *) ctx->pool.alloc((size_t) cap * kRowSize * sizeof(double));
     if (!ctx->d_ins || !ctx->d_tab) return fail(ctx, FFLINS_E_NOMEM, "device allocation failed");
     ctx->ins_cap = cap;
     return FFLINS_OK;
@@ -336,7 +336,7 @@ void fill_info(Frame *f, fflins_frame_info *out) {
 
 // Shared tail of the two lidarFrameProcessing overloads: voxel filter of the decimated cloud,
 // world projection, result read-back (one synchronisation per frame).
-int frame_tail(fflins_ctx *ctx, Frame *f, int n, int ndec, bool pose_on_device, fflins_frame_info *out) {
+int frame_tail(fflins_ctx *ctx, Frame *f, int n, int ndec, fflins_frame_info *out) {
     cudaStream_t s = ctx->stream;
     int rc;
     if ((rc = ensure_voxel(ctx, ndec))) return rc;
@@ -345,25 +345,15 @@ int frame_tail(fflins_ctx *ctx, Frame *f, int n, int ndec, bool pose_on_device, 
                             f->c[FFLINS_CLOUD_LIDAR].d, d_ndown, nullptr, &ctx->launches, ctx->prof(), "voxel_frame");
     {
         ProfScope ps(ctx->prof(), "project_world", s);
-        if (pose_on_device)
-            launch_project_dev(s, ctx->d_frame_pose, f->c[FFLINS_CLOUD_LIDAR].d, f->c[FFLINS_CLOUD_WORLD].d, ndec, d_ndown);
-        else
-            launch_project(s, to12(f->pose), f->c[FFLINS_CLOUD_LIDAR].d, f->c[FFLINS_CLOUD_WORLD].d, ndec, d_ndown);
+        launch_project(s, to12(f->pose), f->c[FFLINS_CLOUD_LIDAR].d, f->c[FFLINS_CLOUD_WORLD].d, ndec, d_ndown);
         ctx->launches++;
     }
     unsigned char *h = pin(ctx, 256);
     if (!h) return fail(ctx, FFLINS_E_NOMEM, "pinned allocation failed");
     CK(cudaMemcpyAsync(h, ctx->d_counters, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
-    if (pose_on_device) CK(cudaMemcpyAsync(h + 16, ctx->d_frame_pose, sizeof(Pose12), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     int cnt[2];
     std::memcpy(cnt, h, sizeof(cnt));
-    if (pose_on_device) {
-        Pose12 p;
-        std::memcpy(&p, h + 16, sizeof(p));
-        std::memcpy(f->pose.R, p.R, sizeof(p.R));
-        std::memcpy(f->pose.t, p.t, sizeof(p.t));
-    }
     f->n_raw                        = n;
     f->n_fallback                   = cnt[0];
     f->c[FFLINS_CLOUD_MAP_FULL].n   = n;
@@ -373,36 +363,6 @@ int frame_tail(fflins_ctx *ctx, Frame *f, int n, int ndec, bool pose_on_device, 
     f->c[FFLINS_CLOUD_MAP].n        = 0;
     fill_info(f, out);
     return FFLINS_OK;
-}
-
-int process_core(fflins_ctx *ctx, uint64_t id, const float4 *d_xyzi, const double *d_time, const void *d_aos, int n,
-                 const double *d_ins_t, const double *d_ins_p, const double *d_ins_q, int w,
-                 const fflins_pose *pose_b_l, double stamp, double td, fflins_frame_info *out) {
-    cudaStream_t s = ctx->stream;
-    Frame *f       = get_frame(ctx, id);
-    const int F    = ctx->cfg.point_filter_num;
-    const int ndec = (n + F - 1) / F;
-    int rc;
-    if ((rc = ensure_cloud(ctx, f->c[FFLINS_CLOUD_MAP_FULL], n))) return rc;
-    if ((rc = ensure_cloud(ctx, f->c[FFLINS_CLOUD_LIDAR_FULL], ndec))) return rc;
-    if ((rc = ensure_cloud(ctx, f->c[FFLINS_CLOUD_LIDAR], ndec))) return rc;
-    if ((rc = ensure_cloud(ctx, f->c[FFLINS_CLOUD_WORLD], ndec))) return rc;
-    if ((rc = ensure_ins(ctx, w))) return rc;
-    CK(cudaMemsetAsync(ctx->d_counters, 0, 4 * sizeof(int), s));
-    Pose12 ext = to12(*pose_b_l);
-    {
-        ProfScope ps(ctx->prof(), "ins_prep", s);
-        launch_ins_prep(s, d_ins_t, d_ins_p, d_ins_q, w, ext, stamp, ctx->d_tab, ctx->d_frame_pose);
-        ctx->launches++;
-    }
-    {
-        ProfScope ps(ctx->prof(), "undistort", s);
-        launch_undistort(s, d_xyzi, d_time, d_aos, n, d_ins_t, d_ins_p, d_ins_q, w, ctx->d_tab, ctx->d_frame_pose, ext,
-                         td, F, f->c[FFLINS_CLOUD_MAP_FULL].d, f->c[FFLINS_CLOUD_LIDAR_FULL].d, ctx->d_counters);
-        if (n > 0) ctx->launches++;
-    }
-    f->td = td;
-    return frame_tail(ctx, f, n, ndec, true, out);
 }
 
 int check_window(fflins_ctx *ctx, const double *ins_t, int w) {
@@ -419,6 +379,43 @@ int upload_ins(fflins_ctx *ctx, const double *ins_t, const double *ins_p, const 
     CK(cudaMemcpyAsync(ctx->d_ins + w, ins_p, (size_t) w * 24, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->d_ins + 4 * (size_t) w, ins_q, (size_t) w * 32, cudaMemcpyHostToDevice, s));
     return FFLINS_OK;
+}
+
+// ins_* are HOST pointers (the window is small and produced by the CPU-side INS mechanisation); the
+// point buffers are device pointers. The frame pose at `stamp` (lidar_map.cc:223) is evaluated on the
+// host — one pose, the same fp64 chain as MISC::getPoseFromInsWindow — and handed to the kernels by value.
+int process_core(fflins_ctx *ctx, uint64_t id, const float4 *d_xyzi, const double *d_time, const void *d_aos, int n,
+                 const double *ins_t, const double *ins_p, const double *ins_q, int w, const fflins_pose *pose_b_l,
+                 double stamp, double td, fflins_frame_info *out) {
+    cudaStream_t s = ctx->stream;
+    Frame *f       = get_frame(ctx, id);
+    const int F    = ctx->cfg.point_filter_num;
+    const int ndec = (n + F - 1) / F;
+    int rc;
+    if ((rc = ensure_cloud(ctx, f->c[FFLINS_CLOUD_MAP_FULL], n))) return rc;
+    if ((rc = ensure_cloud(ctx, f->c[FFLINS_CLOUD_LIDAR_FULL], ndec))) return rc;
+    if ((rc = ensure_cloud(ctx, f->c[FFLINS_CLOUD_LIDAR], ndec))) return rc;
+    if ((rc = ensure_cloud(ctx, f->c[FFLINS_CLOUD_WORLD], ndec))) return rc;
+    if ((rc = upload_ins(ctx, ins_t, ins_p, ins_q, w))) return rc;
+    CK(cudaMemsetAsync(ctx->d_counters, 0, 4 * sizeof(int), s));
+    Pose12 ext = to12(*pose_b_l), frame;
+    pose_from_window(ins_t, ins_p, ins_q, w, ext, stamp, frame);
+    std::memcpy(f->pose.R, frame.R, sizeof(frame.R));
+    std::memcpy(f->pose.t, frame.t, sizeof(frame.t));
+    const double *d_ins_t = ctx->d_ins, *d_ins_p = ctx->d_ins + w, *d_ins_q = ctx->d_ins + 4 * (size_t) w;
+    {
+        ProfScope ps(ctx->prof(), "ins_prep", s);
+        launch_ins_prep(s, d_ins_t, d_ins_p, d_ins_q, w, ext, frame, ctx->d_tab);
+        ctx->launches++;
+    }
+    {
+        ProfScope ps(ctx->prof(), "undistort", s);
+        launch_undistort(s, d_xyzi, d_time, d_aos, n, d_ins_t, w, ctx->d_tab, td, F, f->c[FFLINS_CLOUD_MAP_FULL].d,
+                         f->c[FFLINS_CLOUD_LIDAR_FULL].d, ctx->d_counters);
+        if (n > 0) ctx->launches++;
+    }
+    f->td = td;
+    return frame_tail(ctx, f, n, ndec, out);
 }
 
 int next_pow2(int v) {
@@ -743,9 +740,7 @@ int fflins_frame_process(fflins_ctx *ctx, uint64_t frame_id, const float *xyzi, 
         CK(cudaMemcpyAsync(d_xyzi, xyzi, (size_t) n * 16, cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(d_time, time, (size_t) n * 8, cudaMemcpyHostToDevice, s));
     }
-    if ((rc = upload_ins(ctx, ins_t, ins_p, ins_q, w))) return rc;
-    return process_core(ctx, frame_id, d_xyzi, d_time, nullptr, n, ctx->d_ins, ctx->d_ins + w, ctx->d_ins + 4 * (size_t) w,
-                        w, pose_b_l, stamp, td, out);
+    return process_core(ctx, frame_id, d_xyzi, d_time, nullptr, n, ins_t, ins_p, ins_q, w, pose_b_l, stamp, td, out);
 }
 
 int fflins_frame_process_aos(fflins_ctx *ctx, uint64_t frame_id, const void *points32, int32_t n, const double *ins_t,
@@ -758,19 +753,18 @@ int fflins_frame_process_aos(fflins_ctx *ctx, uint64_t frame_id, const void *poi
     if ((rc = ensure_stage(ctx, (size_t) std::max(n, 1) * 32))) return rc;
     cudaStream_t s = ctx->stream;
     if (n > 0) CK(cudaMemcpyAsync(ctx->d_stage, points32, (size_t) n * 32, cudaMemcpyHostToDevice, s));
-    if ((rc = upload_ins(ctx, ins_t, ins_p, ins_q, w))) return rc;
-    return process_core(ctx, frame_id, nullptr, nullptr, ctx->d_stage, n, ctx->d_ins, ctx->d_ins + w,
-                        ctx->d_ins + 4 * (size_t) w, w, pose_b_l, stamp, td, out);
+    return process_core(ctx, frame_id, nullptr, nullptr, ctx->d_stage, n, ins_t, ins_p, ins_q, w, pose_b_l, stamp, td, out);
 }
 
 int fflins_frame_process_dev(fflins_ctx *ctx, uint64_t frame_id, const float *d_xyzi, const double *d_time, int32_t n,
-                             const double *d_ins_t, const double *d_ins_p, const double *d_ins_q, int32_t w,
+                             const double *ins_t, const double *ins_p, const double *ins_q, int32_t w,
                              const fflins_pose *pose_b_l, double stamp, double td, fflins_frame_info *out) {
     if (!ctx) return FFLINS_E_INVALID;
-    REQUIRE(n >= 0 && (n == 0 || (d_xyzi && d_time)) && d_ins_t && d_ins_p && d_ins_q && pose_b_l, "null argument");
-    REQUIRE(w >= 2 && w <= 65536, "INS window must hold 2..65536 entries");
-    return process_core(ctx, frame_id, (const float4 *) d_xyzi, d_time, nullptr, n, d_ins_t, d_ins_p, d_ins_q, w, pose_b_l,
-                        stamp, td, out);
+    REQUIRE(n >= 0 && (n == 0 || (d_xyzi && d_time)) && ins_t && ins_p && ins_q && pose_b_l, "null argument");
+    int rc;
+    if ((rc = check_window(ctx, ins_t, w))) return rc;
+    return process_core(ctx, frame_id, (const float4 *) d_xyzi, d_time, nullptr, n, ins_t, ins_p, ins_q, w, pose_b_l, stamp,
+                        td, out);
 }
 
 int fflins_frame_process_static(fflins_ctx *ctx, uint64_t frame_id, const float *xyzi, int32_t n, const double state_p[3],
@@ -805,7 +799,7 @@ int fflins_frame_process_static(fflins_ctx *ctx, uint64_t frame_id, const float 
                              f->c[FFLINS_CLOUD_LIDAR_FULL].d);
         ctx->launches++;
     }
-    return frame_tail(ctx, f, n, ndec, false, out);
+    return frame_tail(ctx, f, n, ndec, out);
 }
 
 int fflins_frame_info_get(fflins_ctx *ctx, uint64_t frame_id, fflins_frame_info *out) {
@@ -1110,18 +1104,25 @@ int fflins_keyframe_merge(fflins_ctx *ctx, uint64_t key_id, const uint64_t *nonk
     if ((rc = ensure_cloud(ctx, key->c[FFLINS_CLOUD_MAP], total))) return rc;
     if ((rc = ensure_voxel(ctx, total))) return rc;
     int off = key->c[FFLINS_CLOUD_MAP_FULL].n;
-    for (int i = 0; i < n; i++) {
-        // relative pose non-keyframe -> keyframe (lidar_map.cc:198-199); the projected cloud is written
-        // straight behind the keyframe's own points (the reference projects in place, then appends: :201-205)
-        Pose12 T;
-        mat_tn(key->pose.R, nk[i]->pose.R, T.R);
-        double dt[3] = {nk[i]->pose.t[0] - key->pose.t[0], nk[i]->pose.t[1] - key->pose.t[1], nk[i]->pose.t[2] - key->pose.t[2]};
-        mat_tv(key->pose.R, dt, T.t);
-        int m = nk[i]->c[FFLINS_CLOUD_MAP_FULL].n;
+    for (int i0 = 0; i0 < n; i0 += kMaxRefs) {
+        // relative pose non-keyframe -> keyframe (lidar_map.cc:198-199); the projected clouds are written
+        // straight behind the keyframe's own points (the reference projects in place, then appends: :201-205),
+        // up to 16 clouds per launch
+        ProjectBatch B{};
+        B.count = std::min(n - i0, (int) kMaxRefs);
+        for (int j = 0; j < B.count; j++) {
+            Frame *g = nk[i0 + j];
+            mat_tn(key->pose.R, g->pose.R, B.T[j].R);
+            double dt[3] = {g->pose.t[0] - key->pose.t[0], g->pose.t[1] - key->pose.t[1], g->pose.t[2] - key->pose.t[2]};
+            mat_tv(key->pose.R, dt, B.T[j].t);
+            B.n[j]   = g->c[FFLINS_CLOUD_MAP_FULL].n;
+            B.src[j] = g->c[FFLINS_CLOUD_MAP_FULL].d;
+            B.dst[j] = key->c[FFLINS_CLOUD_MAP_FULL].d + off;
+            off += B.n[j];
+        }
         ProfScope ps(ctx->prof(), "merge_project", s);
-        launch_project(s, T, nk[i]->c[FFLINS_CLOUD_MAP_FULL].d, key->c[FFLINS_CLOUD_MAP_FULL].d + off, m, nullptr);
-        if (m > 0) ctx->launches++;
-        off += m;
+        launch_project_batch(s, B);
+        ctx->launches++;
     }
     key->c[FFLINS_CLOUD_MAP_FULL].n = total;
     launch_voxel_downsample(s, ctx->vox, key->c[FFLINS_CLOUD_MAP_FULL].d, total, (float) ctx->cfg.downsample_size,

@@ -9,12 +9,14 @@
 //
 // The kd-tree is NOT reproduced, only its result: the exact 5 nearest map points by fp32
 // d2 = ((dx*dx + dy*dy) + dz*dz), cut-off d2 <= max_dist^2, ascending, ties broken by the lower
-// map index. B200 design: one warp per (ref keyframe, query); the 32 lanes probe 32 cells of the
-// current Chebyshev shell of an open-addressing hash (key = packed cell, value = map index) in
-// parallel; each lane keeps a sorted top-5 of 64-bit (d2 bits << 32 | index) keys in registers and
-// the warp merges them with shuffle min-reductions. The search stops after the first shell r whose
-// lower bound r*cell exceeds the current 5th distance (strictly, with a 1 mm guard), so the result
-// is provably the exact 5-NN. All (ref, query) pairs of a keyframe go in ONE launch.
+// map index. B200 design: one warp per (ref keyframe, query) over a two-level open-addressing hash
+// per keyframe map: a fine table (key = packed voxel cell, value = map index) and a coarse occupancy
+// table (one 64-bit mask per 4x4x4 block of cells). The warp sweeps Chebyshev stages of the search
+// cube; occupied cells are gathered from the masks into a shared-memory queue and probed 32 at a
+// time; each lane keeps a sorted top-5 of 64-bit (d2 bits << 32 | index) keys in registers and the
+// warp merges them with shuffle min-reductions. The search stops after the first stage whose lower
+// bound exceeds the current 5th distance (strictly, with a 1 mm guard), so the result is provably
+// the exact 5-NN. All (ref, query) pairs of a keyframe go in ONE launch.
 //
 // This translation unit is compiled with -fmad=false: every fp32/fp64 product and sum rounds
 // separately, like the reference's x86-64 build, so d2, the QR normals and the validity
@@ -133,79 +135,109 @@ __device__ __forceinline__ void warp_merge5(u64 a0, u64 a1, u64 a2, u64 a3, u64 
     }
 }
 
-constexpr int kNearShells = 3; // phase A: Chebyshev shells 1..3 of fine cells (7^3 = 343 cells)
+constexpr int kAssocWarps = 4;            // warps per CTA
+constexpr int kQueueCap   = 32 * 64;      // occupied fine cells of 32 coarse blocks
 
-// Warp-cooperative exact 5-NN. best[] is warp-uniform on return (kInf = not found).
-//   Phase A (near): shells r = 1..3 of fine cells, 32 cells per round; stop after the first shell r with
-//     d5 < (r*cell - 1mm)^2 — every unvisited point is then strictly farther than the current 5th.
-//   Phase B (far, only for queries phase A could not close): every 4x4x4 block of the coarse occupancy
-//     hash that intersects the +-r_max search cube, one block per lane; only fine cells whose mask bit is
-//     set are probed. Exhaustive within the cube, so the result stays exact while empty space costs one
-//     coarse probe per 64 cells.
+// Warp-cooperative exact 5-NN on the two-level hash. best[] is warp-uniform on return (kInf = not found).
+//
+// The search cube is swept in Chebyshev stages (lo, hi] = (0,2], (2,4], (4,8], (8,r_max] of fine cells.
+// In a stage every lane fetches the 64-bit occupancy mask of one 4x4x4 coarse block that intersects
+// the stage (empty space costs one probe per 64 cells), the set bits inside the stage are written to
+// a per-warp shared-memory queue, and the queue is drained 32 cells per round, one fine-hash probe
+// per lane — so the probes of a round are in flight together and the load is balanced no matter how
+// the points are distributed over the blocks. After a stage every unvisited map point is farther than
+// hi*cell, so the search stops as soon as d5 < (hi*cell - 1 mm)^2: the result is the exact 5-NN.
 __device__ __forceinline__ void warp_knn5(const HashView &H, float qx, float qy, float qz, float inv_cell, float cell,
-                                          int r_max, float max_d2, u64 best[5]) {
+                                          int r_max, float max_d2, unsigned *__restrict__ queue, u64 best[5]) {
     const int lane = threadIdx.x & 31;
     const int cx = (int) floorf(qx * inv_cell), cy = (int) floorf(qy * inv_cell), cz = (int) floorf(qz * inv_cell);
     u64 a0 = kInf, a1 = kInf, a2 = kInf, a3 = kInf, a4 = kInf;
-    int r_prev      = -1;
-    const int r_near = min(kNearShells, r_max);
+    int lo = -1, hi = 2; // stage (lo, hi]; the first stage includes the query's own cell (ch = 0)
 #pragma unroll 1
-    for (int r = 1; r <= r_near; r++) {
-        const int side = 2 * r + 1, side2 = side * side, total = side2 * side;
+    while (lo < r_max) {
+        hi = min(hi, r_max);
+        const int lox = (cx - hi) >> 2, loy = (cy - hi) >> 2, loz = (cz - hi) >> 2;
+        const int nx = ((cx + hi) >> 2) - lox + 1, ny = ((cy + hi) >> 2) - loy + 1, nz = ((cz + hi) >> 2) - loz + 1;
+        const int total = nx * ny * nz;
 #pragma unroll 1
-        for (int t = lane; t < total; t += 32) {
-            int dz  = t / side2;
-            int rem = t - dz * side2;
-            int dy  = rem / side;
-            int dx  = rem - dy * side;
-            dx -= r; dy -= r; dz -= r;
-            if (max(abs(dx), max(abs(dy), abs(dz))) <= r_prev) continue; // shell interior: already visited
-            probe_cell(H, cx + dx, cy + dy, cz + dz, qx, qy, qz, max_d2, a0, a1, a2, a3, a4);
+        for (int t0 = 0; t0 < total; t0 += 32) {
+            const int t = t0 + lane;
+            u64 mask = 0ull;
+            int bx = 0, by = 0, bz = 0;
+            if (t < total) {
+                bz      = t / (nx * ny);
+                int rem = t - bz * (nx * ny);
+                by      = rem / nx;
+                bx      = rem - by * nx;
+                bx += lox; by += loy; bz += loz;
+                // Chebyshev range of the block's cells relative to the query cell
+                int ax = bx * 4 - cx, ay = by * 4 - cy, az = bz * 4 - cz;   // offsets of the block's first cell
+                int mnx = max(0, max(ax, -(ax + 3))), mny = max(0, max(ay, -(ay + 3))), mnz = max(0, max(az, -(az + 3)));
+                int mxx = max(abs(ax), abs(ax + 3)), mxy = max(abs(ay), abs(ay + 3)), mxz = max(abs(az), abs(az + 3));
+                int ch_min = max(mnx, max(mny, mnz)), ch_max = max(mxx, max(mxy, mxz));
+                if (ch_max > lo && ch_min <= hi) {
+                    u64 ck     = pack_cell(bx, by, bz);
+                    unsigned h = hash_cell(ck) & H.hmask;
+                    while (true) {
+                        u64 k = __ldg(H.ckeys + h);
+                        if (k == kEmpty) break;
+                        if (k == ck) { mask = __ldg(H.cmask + h); break; }
+                        h = (h + 1) & H.hmask;
+                    }
+                }
+            }
+            // keep only the cells of this stage, count, and enqueue at the warp-wide exclusive offset
+            int cnt = 0;
+            u64 keep = 0ull;
+            {
+                u64 m = mask;
+                while (m) {
+                    int sub = __ffsll((long long) m) - 1;
+                    m &= m - 1;
+                    int dx = bx * 4 + (sub & 3) - cx, dy = by * 4 + ((sub >> 2) & 3) - cy, dz = bz * 4 + (sub >> 4) - cz;
+                    int ch = max(abs(dx), max(abs(dy), abs(dz)));
+                    if (ch > lo && ch <= hi) { keep |= 1ull << sub; cnt++; }
+                }
+            }
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const int T = __shfl_sync(0xffffffffu, incl, 31);
+            if (T == 0) continue;
+            int off = incl - cnt;
+            while (keep) {
+                int sub = __ffsll((long long) keep) - 1;
+                keep &= keep - 1;
+                int dx = bx * 4 + (sub & 3) - cx, dy = by * 4 + ((sub >> 2) & 3) - cy, dz = bz * 4 + (sub >> 4) - cz;
+                queue[off++] = (unsigned) (dx + 512) | ((unsigned) (dy + 512) << 10) | ((unsigned) (dz + 512) << 20);
+            }
+            __syncwarp();
+#pragma unroll 1
+            for (int k = lane; k < T; k += 32) {
+                unsigned e = queue[k];
+                int dx = (int) (e & 1023u) - 512, dy = (int) ((e >> 10) & 1023u) - 512, dz = (int) (e >> 20) - 512;
+                probe_cell(H, cx + dx, cy + dy, cz + dz, qx, qy, qz, max_d2, a0, a1, a2, a3, a4);
+            }
+            __syncwarp();
         }
-        r_prev = r;
         warp_merge5(a0, a1, a2, a3, a4, best);
         if (best[4] != kInf) {
             float d5    = __uint_as_float((unsigned) (best[4] >> 32));
-            float bound = (float) r * cell - 1e-3f;
+            float bound = (float) hi * cell - 1e-3f;
             if (bound > 0.f && d5 < bound * bound) return;
         }
+        lo = hi;
+        hi *= 2;
     }
-    if (r_near >= r_max) return;
-    // ---- phase B
-    const int lox = (cx - r_max) >> 2, loy = (cy - r_max) >> 2, loz = (cz - r_max) >> 2;
-    const int nx = ((cx + r_max) >> 2) - lox + 1, ny = ((cy + r_max) >> 2) - loy + 1, nz = ((cz + r_max) >> 2) - loz + 1;
-    const int total = nx * ny * nz;
-#pragma unroll 1
-    for (int t = lane; t < total; t += 32) {
-        int bz  = t / (nx * ny);
-        int rem = t - bz * (nx * ny);
-        int by  = rem / nx;
-        int bx  = rem - by * nx;
-        bx += lox; by += loy; bz += loz;
-        u64 ck     = pack_cell(bx, by, bz);
-        unsigned h = hash_cell(ck) & H.hmask;
-        u64 mask   = 0ull;
-        while (true) {
-            u64 k = __ldg(H.ckeys + h);
-            if (k == kEmpty) break;
-            if (k == ck) { mask = __ldg(H.cmask + h); break; }
-            h = (h + 1) & H.hmask;
-        }
-        while (mask) {
-            int sub = __ffsll((long long) mask) - 1;
-            mask &= mask - 1;
-            int fx = bx * 4 + (sub & 3), fy = by * 4 + ((sub >> 2) & 3), fz = bz * 4 + (sub >> 4);
-            int ch = max(abs(fx - cx), max(abs(fy - cy), abs(fz - cz)));
-            if (ch <= r_prev || ch > r_max) continue;
-            probe_cell(H, fx, fy, fz, qx, qy, qz, max_d2, a0, a1, a2, a3, a4);
-        }
-    }
-    warp_merge5(a0, a1, a2, a3, a4, best);
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kAssocWarps * 32)
 associate_kernel(const __grid_constant__ AssocParams P, const float4 *__restrict__ cur_world,
                  const float4 *__restrict__ cur_lidar) {
+    __shared__ unsigned s_queue[kAssocWarps][kQueueCap];
     const int lane  = threadIdx.x & 31;
     const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (gwarp >= P.n_refs * P.q) return;
@@ -219,7 +251,7 @@ associate_kernel(const __grid_constant__ AssocParams P, const float4 *__restrict
     u64 best[5] = {kInf, kInf, kInf, kInf, kInf};
     if (ref.m > 0) {
         HashView H{ref.map, ref.hkeys, ref.hvals, ref.ckeys, ref.cmask, ref.hmask};
-        warp_knn5(H, rp.x, rp.y, rp.z, P.inv_cell, P.cell, P.r_max, P.max_d2, best);
+        warp_knn5(H, rp.x, rp.y, rp.z, P.inv_cell, P.cell, P.r_max, P.max_d2, s_queue[threadIdx.x >> 5], best);
     }
 
     int found = 0;
@@ -266,11 +298,12 @@ associate_kernel(const __grid_constant__ AssocParams P, const float4 *__restrict
     }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kAssocWarps * 32)
 knn5_kernel(const float4 *__restrict__ map, const u64 *__restrict__ hkeys, const int *__restrict__ hvals,
             const u64 *__restrict__ ckeys, const u64 *__restrict__ cmask, int hmask, int m,
             const float4 *__restrict__ query, int q, float inv_cell, float cell, int r_max, float max_d2,
             int32_t *__restrict__ nn_idx, float *__restrict__ nn_d2, int32_t *__restrict__ nn_count) {
+    __shared__ unsigned s_queue[kAssocWarps][kQueueCap];
     const int lane  = threadIdx.x & 31;
     const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (gwarp >= q) return;
@@ -278,7 +311,7 @@ knn5_kernel(const float4 *__restrict__ map, const u64 *__restrict__ hkeys, const
     u64 best[5] = {kInf, kInf, kInf, kInf, kInf};
     if (m > 0) {
         HashView H{map, hkeys, hvals, ckeys, cmask, hmask};
-        warp_knn5(H, qp.x, qp.y, qp.z, inv_cell, cell, r_max, max_d2, best);
+        warp_knn5(H, qp.x, qp.y, qp.z, inv_cell, cell, r_max, max_d2, s_queue[threadIdx.x >> 5], best);
     }
     int found = 0;
 #pragma unroll
@@ -329,15 +362,15 @@ void launch_hash_build(cudaStream_t s, const float4 *map, int m, float inv_cell,
 void launch_associate(cudaStream_t s, const AssocParams &p, const float4 *cur_world, const float4 *cur_lidar) {
     long long warps = (long long) p.n_refs * p.q;
     if (warps <= 0) return;
-    int grid = (int) ((warps + 7) / 8);
-    associate_kernel<<<grid, 256, 0, s>>>(p, cur_world, cur_lidar);
+    int grid = (int) ((warps + kAssocWarps - 1) / kAssocWarps);
+    associate_kernel<<<grid, kAssocWarps * 32, 0, s>>>(p, cur_world, cur_lidar);
 }
 
 void launch_knn5(cudaStream_t s, const float4 *map, const unsigned long long *hkeys, const int *hvals,
                  const unsigned long long *ckeys, const unsigned long long *cmask, int hmask, int m, const float4 *query, int q, float inv_cell, float cell, int r_max, float max_d2, int32_t *nn_idx,
                  float *nn_d2, int32_t *nn_count) {
     if (q <= 0) return;
-    knn5_kernel<<<(q + 7) / 8, 256, 0, s>>>(map, hkeys, hvals, ckeys, cmask, hmask, m, query, q, inv_cell, cell, r_max, max_d2, nn_idx,
+    knn5_kernel<<<(q + kAssocWarps - 1) / kAssocWarps, kAssocWarps * 32, 0, s>>>(map, hkeys, hvals, ckeys, cmask, hmask, m, query, q, inv_cell, cell, r_max, max_d2, nn_idx,
                                             nn_d2, nn_count);
 }
 

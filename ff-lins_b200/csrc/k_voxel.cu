@@ -377,7 +377,7 @@ constexpr int SMALL_THREADS = 1024;
 __global__ void __launch_bounds__(SMALL_THREADS)
 vox_small_kernel(const float4 *__restrict__ in, int n, float inv, int *__restrict__ meta, float4 *__restrict__ out,
                  int *__restrict__ d_nout, int32_t *__restrict__ keys_out) {
-    extern __shared__ unsigned long long comp[]; // npad composites
+    extern __shared__ unsigned long long comp[]; // npad composites, then n staged points
     __shared__ float s_mn[3][32], s_mx[3][32];
     __shared__ int s_bbox[6];
     __shared__ int s_ws[32];
@@ -385,10 +385,12 @@ vox_small_kernel(const float4 *__restrict__ in, int n, float inv, int *__restric
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     int npad = 32;
     while (npad < n) npad <<= 1;
+    float4 *pts = reinterpret_cast<float4 *>(comp + npad); // points staged once, reused by keys and centroid
     // 1. bounding box
     float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
     for (int i = tid; i < n; i += SMALL_THREADS) {
         float4 p = __ldg(in + i);
+        pts[i]   = p;
         mn[0] = fminf(mn[0], p.x); mx[0] = fmaxf(mx[0], p.x);
         mn[1] = fminf(mn[1], p.y); mx[1] = fmaxf(mx[1], p.y);
         mn[2] = fminf(mn[2], p.z); mx[2] = fmaxf(mx[2], p.z);
@@ -433,7 +435,7 @@ vox_small_kernel(const float4 *__restrict__ in, int n, float inv, int *__restric
     for (int i = tid; i < npad; i += SMALL_THREADS) {
         unsigned long long c = 0xffffffffffffffffull;
         if (i < n) {
-            float4 p = __ldg(in + i);
+            float4 p = pts[i];
             int i0   = (int) (floorf(__fmul_rn(p.x, inv)) - (float) g.min_b[0]);
             int i1   = (int) (floorf(__fmul_rn(p.y, inv)) - (float) g.min_b[1]);
             int i2   = (int) (floorf(__fmul_rn(p.z, inv)) - (float) g.min_b[2]);
@@ -489,7 +491,7 @@ vox_small_kernel(const float4 *__restrict__ in, int n, float inv, int *__restric
         float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
         int e = i;
         while (e < n && (uint32_t) (comp[e] >> 32) == key) {
-            float4 p = __ldg(in + (uint32_t) (comp[e] & 0xffffffffu));
+            float4 p = pts[(uint32_t) (comp[e] & 0xffffffffu)];
             sx += p.x; sy += p.y; sz += p.z; si += p.w;
             e++;
         }
@@ -535,13 +537,13 @@ int launch_voxel_downsample(cudaStream_t s, const VoxelWork &w, const float4 *in
         int dev = 0;
         cudaGetDevice(&dev);
         if (!attr_set[dev & 63]) {
-            cudaFuncSetAttribute(vox_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_CAP * 8);
+            cudaFuncSetAttribute(vox_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_CAP * 24);
             attr_set[dev & 63] = true;
         }
         int npad = 32;
         while (npad < n) npad <<= 1;
         ProfScope ps(prof, nm("one_cta"), s);
-        vox_small_kernel<<<1, SMALL_THREADS, (size_t) npad * 8, s>>>(in, n, inv, w.meta, out, d_nout, keys_out);
+        vox_small_kernel<<<1, SMALL_THREADS, (size_t) npad * 8 + (size_t) n * 16, s>>>(in, n, inv, w.meta, out, d_nout, keys_out);
         if (launches) *launches += 1;
         return 0;
     }

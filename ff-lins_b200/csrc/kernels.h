@@ -24,16 +24,14 @@ struct ProfScope {
 };
 
 // ---- K1 undistort (lidar_map.cc:223-256, misc.cc:27-105, pointcloud.cc:30-59) -------------------
-// Per-IMU-interval invariants of MISC::statePoseInterpolation (misc.cc:86-88): dp, rvec.
-// interval_tab: 6 doubles per window entry i (interval [i-1, i]); frame_pose[0] = lidar pose at
-// `stamp`, frame_pose[1] = pose of window.back() (the out-of-window fallback, misc.cc:76-79).
+// rows: kRowSize (42) doubles per window entry, the closed-form relative pose of IMU interval
+// [i-1, i] w.r.t. the frame pose (math_undistort.cuh); row 0 = out-of-window fallback (misc.cc:76-79).
 void launch_ins_prep(cudaStream_t s, const double *ins_t, const double *ins_p, const double *ins_q, int w,
-                     Pose12 ext, double stamp, double *interval_tab, Pose12 *frame_pose);
+                     Pose12 ext, Pose12 frame_pose, double *rows);
 // aos != nullptr: raw 32-byte PointXYZIT records; else xyzi + time arrays.
 void launch_undistort(cudaStream_t s, const float4 *xyzi, const double *time, const void *aos, int n,
-                      const double *ins_t, const double *ins_p, const double *ins_q, int w,
-                      const double *interval_tab, const Pose12 *frame_pose, Pose12 ext, double td, int filter_num,
-                      float4 *out_full, float4 *out_dec, int *n_fallback);
+                      const double *ins_t, int w, const double *rows, double td, int filter_num, float4 *out_full,
+                      float4 *out_dec, int *n_fallback);
 // static overload (lidar_map.cc:275-324): copy + decimate
 void launch_copy_decimate(cudaStream_t s, const float4 *xyzi, int n, int filter_num, float4 *out_full,
                           float4 *out_dec);

@@ -91,4 +91,114 @@ __host__ __device__ __forceinline__ void interp_pose(const double *__restrict__ 
     state_to_pose(p, q, ext, R, t);
 }
 
+
+// ---- per-interval closed form of the relative pose ---------------------------------------------------
+// For a point time t inside IMU interval i (entries i-1, i), with s = (t - t0)/(t1 - t0),
+// K = [rvec]x, theta = |rvec|, the reference's chain (misc.cc:82-105, pointcloud.cc:30-36) is
+//   R(q)  = R(q0) exp(-s K),          p = p0 + s dp,
+//   R01   = R0f^T R(q) R_bl,          t01 = R0f^T (p + R(q) t_bl - t0f).
+// With exp(-sK) = I - s a(x) K + s^2 b(x) K^2, x = s theta, a = sin(x)/x, b = (1 - cos x)/x^2:
+//   R01 = G0 - (s a) G1 + (s^2 b) G2,     t01 = c0 + s c1 - (s a) c2 + (s^2 b) c3,
+// where G0 = A R_bl, G1 = A K R_bl, G2 = A K^2 R_bl, A = R0f^T R(q0), c0 = R0f^T (p0 - t0f) + A t_bl,
+// c1 = R0f^T dp, c2 = A K t_bl, c3 = A K^2 t_bl depend only on the interval. A row holds these 39
+// doubles plus t0, 1/(t1 - t0) and theta^2 (kRowSize = 42). Row 0 is the out-of-window fallback
+// (misc.cc:76-79): the constant pose of window.back().
+constexpr int kRowSize = 42;
+
+__host__ __device__ inline void interval_row(const double *__restrict__ ins_t, const double *__restrict__ ins_p,
+                                             const double *__restrict__ ins_q, int w, int i, const Pose12 &ext,
+                                             const Pose12 &frame, double *__restrict__ row) {
+    M3 R0f, Rbl;
+    for (int k = 0; k < 9; k++) {
+        R0f.m[k] = frame.R[k];
+        Rbl.m[k] = ext.R[k];
+    }
+    V3 t0f = V3{frame.t[0], frame.t[1], frame.t[2]}, tbl = V3{ext.t[0], ext.t[1], ext.t[2]};
+    for (int k = 0; k < kRowSize; k++) row[k] = 0.0;
+    int i0   = (i == 0) ? (w - 1) : (i - 1);
+    Q4 q0    = ldq(ins_q + 4 * i0);
+    double n = sqrt(q0.x * q0.x + q0.y * q0.y + q0.z * q0.z + q0.w * q0.w);
+    q0       = Q4{q0.x / n, q0.y / n, q0.z / n, q0.w / n};
+    V3 p0    = ld3(ins_p + 3 * i0);
+    M3 A     = mulTN(R0f, quat_to_R(q0));
+    M3 G0    = mul(A, Rbl);
+    V3 c0    = mulT(R0f, p0 - t0f) + mul(A, tbl);
+    for (int k = 0; k < 9; k++) row[k] = G0.m[k];
+    row[27] = c0.x;
+    row[28] = c0.y;
+    row[29] = c0.z;
+    if (i == 0) return; // constant pose: G1 = G2 = c1..c3 = 0, s = 0
+    V3 dp   = ld3(ins_p + 3 * i) - p0;
+    Q4 dq   = qmul(qinv(ldq(ins_q + 4 * i)), ldq(ins_q + 4 * (i - 1)));
+    V3 rv   = quat_log(dq);
+    M3 K    = M3{{0.0, -rv.z, rv.y, rv.z, 0.0, -rv.x, -rv.y, rv.x, 0.0}};
+    M3 AK   = mul(A, K);
+    M3 AKK  = mul(AK, K);
+    M3 G1   = mul(AK, Rbl), G2 = mul(AKK, Rbl);
+    V3 c1   = mulT(R0f, dp), c2 = mul(AK, tbl), c3 = mul(AKK, tbl);
+    for (int k = 0; k < 9; k++) {
+        row[9 + k]  = G1.m[k];
+        row[18 + k] = G2.m[k];
+    }
+    row[30] = c1.x; row[31] = c1.y; row[32] = c1.z;
+    row[33] = c2.x; row[34] = c2.y; row[35] = c2.z;
+    row[36] = c3.x; row[37] = c3.y; row[38] = c3.z;
+    row[39] = ins_t[i - 1];
+    row[40] = 1.0 / (ins_t[i] - ins_t[i - 1]);
+    row[41] = rv.x * rv.x + rv.y * rv.y + rv.z * rv.z;
+}
+
+// sin(x)/x and (1 - cos x)/x^2 from x^2
+__host__ __device__ __forceinline__ void sinc_cosc(double x2, double &a, double &b) {
+    if (x2 < 2.5e-3) { // |x| < 0.05: 6-term series, truncation error < 1e-25
+        a = 1.0 + x2 * (-1.0 / 6 + x2 * (1.0 / 120 + x2 * (-1.0 / 5040 + x2 * (1.0 / 362880 + x2 * (-1.0 / 39916800)))));
+        b = 0.5 + x2 * (-1.0 / 24 + x2 * (1.0 / 720 + x2 * (-1.0 / 40320 + x2 * (1.0 / 3628800 + x2 * (-1.0 / 479001600)))));
+    } else {
+        double x = sqrt(x2), sn, cs;
+        sincos(x, &sn, &cs);
+        a = sn / x;
+        // 1 - cos x = 2 sin^2(x/2): no cancellation
+        double sh = sin(0.5 * x);
+        b = 2.0 * sh * sh / x2;
+    }
+}
+
+// relative pose (R01, t01) of a point time from its interval row
+__host__ __device__ __forceinline__ void row_pose(const double *__restrict__ row, double time, double R01[9], double t01[3]) {
+    double s  = (time - row[39]) * row[40];
+    double a, b;
+    sinc_cosc(s * s * row[41], a, b);
+    double sa = s * a, sb = s * s * b;
+#pragma unroll
+    for (int k = 0; k < 9; k++) R01[k] = row[k] - sa * row[9 + k] + sb * row[18 + k];
+#pragma unroll
+    for (int k = 0; k < 3; k++) t01[k] = row[27 + k] + s * row[30 + k] - sa * row[33 + k] + sb * row[36 + k];
+}
+
+// MISC::getPoseFromInsWindow (misc.cc:64-80) for ONE time, written out in full (used on the host for the
+// frame pose at `stamp`, lidar_map.cc:223)
+__host__ __device__ inline bool pose_from_window(const double *ins_t, const double *ins_p, const double *ins_q, int w,
+                                                 const Pose12 &ext, double time, Pose12 &out) {
+    double inv_dt = (double) (w - 1) / (ins_t[w - 1] - ins_t[0]);
+    int idx       = window_index(ins_t, w, time, ins_t[0], ins_t[w - 1], inv_dt);
+    M3 R;
+    V3 t;
+    if (idx > 0) {
+        double tab[12];
+        V3 dp   = ld3(ins_p + 3 * idx) - ld3(ins_p + 3 * (idx - 1));
+        Q4 dq   = qmul(qinv(ldq(ins_q + 4 * idx)), ldq(ins_q + 4 * (idx - 1)));
+        V3 rvec = quat_log(dq);
+        tab[6] = dp.x; tab[7] = dp.y; tab[8] = dp.z;
+        tab[9] = rvec.x; tab[10] = rvec.y; tab[11] = rvec.z;
+        interp_pose(ins_t + (idx - 1), ins_p + 3 * (idx - 1), ins_q + 4 * (idx - 1), tab, 1, time, ext, R, t);
+    } else {
+        state_to_pose(ld3(ins_p + 3 * (w - 1)), ldq(ins_q + 4 * (w - 1)), ext, R, t);
+    }
+    for (int k = 0; k < 9; k++) out.R[k] = R.m[k];
+    out.t[0] = t.x;
+    out.t[1] = t.y;
+    out.t[2] = t.z;
+    return idx > 0;
+}
+
 } // namespace fflins

@@ -152,12 +152,12 @@ class Context:
                                                  C.c_double(td), C.byref(info)))
         return info
 
-    def frame_process_dev(self, fid, d_xyzi, d_time, n, d_ins_t, d_ins_p, d_ins_q, w, pose_bl, stamp, td, info=None):
-        """All pointers are raw device addresses (ints)."""
+    def frame_process_dev(self, fid, d_xyzi, d_time, n, ins_t, ins_p, ins_q, pose_bl, stamp, td, info=None):
+        """d_xyzi / d_time are raw device addresses (ints); the INS window arrays are host numpy arrays."""
         info = info or FrameInfo()
         self._ck(self.L.fflins_frame_process_dev(self.h, C.c_uint64(fid), C.c_void_p(d_xyzi), C.c_void_p(d_time), n,
-                                                 C.c_void_p(d_ins_t), C.c_void_p(d_ins_p), C.c_void_p(d_ins_q), w,
-                                                 C.byref(pose_bl), C.c_double(stamp), C.c_double(td), C.byref(info)))
+                                                 _p(ins_t), _p(ins_p), _p(ins_q), len(ins_t), C.byref(pose_bl),
+                                                 C.c_double(stamp), C.c_double(td), C.byref(info)))
         return info
 
     def frame_process_static(self, fid, xyzi, p, q, R_bl, t_bl):

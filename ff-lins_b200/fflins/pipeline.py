@@ -9,14 +9,37 @@ Per keyframe:   fflins_keyframe_merge -> fflins_keyframe_add -> fflins_frame_set
                 when the window is full.
 Keyframes are chosen every `frames_per_key` frames (the synthetic trajectory makes the reference's
 own keyframeSelection fire at that cadence; the selection call is exercised separately)."""
+import time
+
 import numpy as np
 
 from . import api
 
 
+class _Timed:
+    """Optional wall-clock trace of the host-side calls (FFLINS trace, off by default)."""
+
+    def __init__(self, ctx, sink):
+        self._ctx, self._sink = ctx, sink
+
+    def __getattr__(self, name):
+        fn = getattr(self._ctx, name)
+        if not callable(fn):
+            return fn
+
+        def wrap(*a, **k):
+            t0 = time.perf_counter()
+            r = fn(*a, **k)
+            e = self._sink.setdefault(name, [0.0, 0])
+            e[0] += time.perf_counter() - t0
+            e[1] += 1
+            return r
+        return wrap
+
+
 class Session:
-    def __init__(self, ctx, seq, frames_per_key=5, n_eval=(5, 10), flags=api.HUBER):
-        self.ctx = ctx
+    def __init__(self, ctx, seq, frames_per_key=5, n_eval=(5, 10), flags=api.HUBER, trace=None):
+        self.ctx = ctx if trace is None else _Timed(ctx, trace)
         self.seq = seq
         self.K = frames_per_key
         self.n_eval = n_eval
@@ -42,12 +65,12 @@ class Session:
         return fid, info
 
     def process_frame_dev(self, fr_dev):
-        """fr_dev: dict of raw device pointers + scalars (inputs resident in HBM)."""
+        """fr_dev: raw device pointers of the point data (resident in HBM) + host INS window + scalars."""
         fid = self.next_id
         self.next_id += 1
         info = self.ctx.frame_process_dev(fid, fr_dev["xyzi"], fr_dev["time"], fr_dev["n"], fr_dev["ins_t"],
-                                          fr_dev["ins_p"], fr_dev["ins_q"], fr_dev["w"], self.pose_bl,
-                                          fr_dev["stamp"], fr_dev["td"])
+                                          fr_dev["ins_p"], fr_dev["ins_q"], self.pose_bl, fr_dev["stamp"],
+                                          fr_dev["td"])
         self.last_info = {fid: info}
         return fid, info
 

@@ -126,9 +126,10 @@ int fflins_frame_process(fflins_ctx *ctx, uint64_t frame_id, const float *xyzi, 
 int fflins_frame_process_aos(fflins_ctx *ctx, uint64_t frame_id, const void *points32, int32_t n,
                              const double *ins_t, const double *ins_p, const double *ins_q, int32_t w,
                              const fflins_pose *pose_b_l, double stamp, double td, fflins_frame_info *out);
-/* Same, inputs already resident in device memory (all pointers are device pointers). */
+/* Same, point data already resident in device memory (d_xyzi, d_time are device pointers; the small
+ * INS window stays a host buffer — it is produced by the CPU-side INS mechanisation). */
 int fflins_frame_process_dev(fflins_ctx *ctx, uint64_t frame_id, const float *d_xyzi, const double *d_time, int32_t n,
-                             const double *d_ins_t, const double *d_ins_p, const double *d_ins_q, int32_t w,
+                             const double *ins_t, const double *ins_p, const double *ins_q, int32_t w,
                              const fflins_pose *pose_b_l, double stamp, double td, fflins_frame_info *out);
 /* Static overload used during initialisation (lidar_map.cc:275-324): no undistortion. */
 int fflins_frame_process_static(fflins_ctx *ctx, uint64_t frame_id, const float *xyzi, int32_t n,
