@@ -94,6 +94,21 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def max_over_ranks(values, dist, device="cuda"):
+    """Element-wise MAX over the ranks of a list of floats (the only cross-rank data step)."""
+    if dist is None:
+        return [float(v) for v in values]
+    import torch
+    t = torch.tensor(list(values), device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(v) for v in t]
+
+
+def aggregate_frames(steps, world):
+    """Whole-job frame count: every replica processes FRAMES_PER_KEY frames per step (weak scaling)."""
+    return FRAMES_PER_KEY * steps * world
+
+
 def make_sequence(name, n_frames=None):
     from fflins import synth
     seq = synth.Sequence(name)
@@ -124,7 +139,7 @@ def run_ours(args, rank, world, local_rank):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    seq, frames = make_sequence(args.config)
+    seq, frames = make_sequence(args.config, args.frames)
     P = len(frames)
     n, w = seq.n, seq.W
     cfg = fflins.default_config(point_filter_num=seq.filter_num, max_points_per_frame=max(n, 262144))
@@ -174,14 +189,11 @@ def run_ours(args, rank, world, local_rank):
         wall_ms = (time.perf_counter() - t0) * 1e3
         launches = ctx.launch_count() - l0
         barrier()
-        if dist is not None:
-            t = torch.tensor([dev_ms, wall_ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dev_ms, wall_ms = float(t[0]), float(t[1])
+        dev_ms, wall_ms = max_over_ranks([dev_ms, wall_ms], dist)
         return dev_ms, wall_ms, launches
 
     # setup: fill the sliding window (11 keyframes), then W warm-up steps per mode
-    for _ in range(PREFILL_KEYS):
+    for _ in range(args.prefill or PREFILL_KEYS):
         step("dev")
     warm = max(args.warmup, 3)
     for _ in range(warm):
@@ -198,7 +210,7 @@ def run_ours(args, rank, world, local_rank):
         step("host")
     e2e_dev_ms, e2e_wall_ms, _ = timed("host", args.steps)
 
-    frames_total = FRAMES_PER_KEY * args.steps * world
+    frames_total = aggregate_frames(args.steps, world)
     value = frames_total / (dev_ms / 1e3)
     e2e_value = frames_total / (e2e_dev_ms / 1e3)
 
@@ -331,11 +343,11 @@ def cpu_baseline(config, frames, seq, steps=2):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    seq, frames = make_sequence(args.config)
+    seq, frames = make_sequence(args.config, args.frames)
     warm = max(args.warmup, 0)
     steps = max(1, min(args.steps, 5))     # bounded sample: each CPU step costs ~0.2-0.5 s
     # warm-up steps are folded into the untimed window fill
-    dt, threads, stage_ms = cpu_run(args.config, frames, seq, steps, prefill=PREFILL_KEYS + min(warm, 3))
+    dt, threads, stage_ms = cpu_run(args.config, frames, seq, steps, prefill=(args.prefill or PREFILL_KEYS) + min(warm, 3))
     value = FRAMES_PER_KEY * steps / dt
     cpu = {"value": round(value, 3), "unit": "frames/s", "cores": threads, "kind": "port",
            "sample": f"{steps} timed steps ({FRAMES_PER_KEY * steps} frames); the reference cannot be compiled here "
@@ -364,6 +376,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="at128", choices=["robot", "lili", "ouster64", "at128"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--frames", type=int, default=None, help="distinct synthetic frames to cycle over (default: one lap)")
+    ap.add_argument("--prefill", type=int, default=None, help="untimed keyframes that fill the window (default 11)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
