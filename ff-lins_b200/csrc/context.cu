@@ -106,10 +106,8 @@ struct fflins_ctx : public Profiler {
     VoxelWork vox;
     void *vox_base = nullptr;
     // factor scratch
-    double *d_partial = nullptr, *d_red = nullptr;
-    unsigned int *d_tickets = nullptr;
+    double *d_red = nullptr;
     int *d_outliers = nullptr;
-    size_t partial_cap = 0;
     // pinned host scratch
     unsigned char *h_pin = nullptr;
     size_t h_pin_cap = 0;
@@ -547,22 +545,6 @@ int run_associate(fflins_ctx *ctx, const std::vector<Frame *> &refs, Frame *cur,
     return FFLINS_OK;
 }
 
-int ensure_factor_scratch(fflins_ctx *ctx, int n_pairs, int q) {
-    size_t blocks = (size_t) (q + kFactorBlock - 1) / kFactorBlock + 1;
-    size_t need   = (size_t) kMaxRefs * blocks * kRedSize * sizeof(double);
-    (void) n_pairs;
-    if (need > ctx->partial_cap) {
-        ctx->pool.release(ctx->d_partial);
-        ctx->d_partial = (double *) ctx->pool.alloc(need);
-        if (!ctx->d_partial) {
-            ctx->partial_cap = 0;
-            return fail(ctx, FFLINS_E_NOMEM, "device allocation failed");
-        }
-        ctx->partial_cap = Pool::round(need);
-    }
-    return FFLINS_OK;
-}
-
 void unpack_red(const double *red, double *H, double *b, double *cost, int32_t *n_res) {
     if (H) {
         int e = 0;
@@ -664,13 +646,11 @@ int fflins_create(const fflins_config *cfg, int device, fflins_ctx **out) {
     ctx->d_frame_pose = (Pose12 *) ctx->pool.alloc(2 * sizeof(Pose12));
     ctx->d_counters   = (int *) ctx->pool.alloc(64 * sizeof(int));
     ctx->d_red        = (double *) ctx->pool.alloc((size_t) kMaxRefs * kRedSize * sizeof(double));
-    ctx->d_tickets    = (unsigned int *) ctx->pool.alloc(kMaxRefs * sizeof(unsigned int));
     ctx->d_outliers   = (int *) ctx->pool.alloc(kMaxRefs * sizeof(int));
-    if (!ctx->d_frame_pose || !ctx->d_counters || !ctx->d_red || !ctx->d_tickets || !ctx->d_outliers) {
+    if (!ctx->d_frame_pose || !ctx->d_counters || !ctx->d_red || !ctx->d_outliers) {
         fflins_destroy(ctx);
         return FFLINS_E_NOMEM;
     }
-    cudaMemsetAsync(ctx->d_tickets, 0, kMaxRefs * sizeof(unsigned int), ctx->stream);
     int n = cfg->max_points_per_frame > 0 ? cfg->max_points_per_frame : 262144;
     int k = cfg->max_merge_frames > 0 ? cfg->max_merge_frames : 8;
     if (ensure_voxel(ctx, n * k) != FFLINS_OK || ensure_stage(ctx, (size_t) n * 32) != FFLINS_OK ||
@@ -1327,7 +1307,7 @@ int fflins_factor_eval_batch(fflins_ctx *ctx, int32_t n, const float *point, con
     P.pair[0].normal = d_n;
     P.pair[0].d      = d_d;
     P.pair[0].std    = d_std;
-    launch_factor_eval(s, P, d_p, 0, r ? d_r : nullptr, J ? d_J : nullptr, nullptr, nullptr, nullptr, ctx->d_tickets);
+    launch_factor_eval(s, P, d_p, 0, r ? d_r : nullptr, J ? d_J : nullptr, nullptr, nullptr);
     ctx->launches++;
     if (r) cudaMemcpyAsync(r, d_r, (size_t) n * 8, cudaMemcpyDeviceToHost, s);
     if (J) cudaMemcpyAsync(J, d_J, (size_t) n * 176, cudaMemcpyDeviceToHost, s);
@@ -1357,7 +1337,6 @@ int fflins_factor_eval(fflins_ctx *ctx, uint64_t ref_id, uint64_t cur_id, const 
         if (cost) cost[0] = cost[1] = 0;
         return FFLINS_OK;
     }
-    if ((rc = ensure_factor_scratch(ctx, 1, q))) return rc;
     char *d = nullptr;
     double *d_r = nullptr, *d_J = nullptr;
     uint8_t *d_valid = nullptr;
@@ -1371,7 +1350,7 @@ int fflins_factor_eval(fflins_ctx *ctx, uint64_t ref_id, uint64_t cur_id, const 
     {
         ProfScope ps(ctx->prof(), "factor_eval", s);
         launch_factor_eval(s, P, (const float *) cur->c[FFLINS_CLOUD_LIDAR].d, 1, r ? d_r : nullptr, J ? d_J : nullptr,
-                           valid ? d_valid : nullptr, ctx->d_partial, ctx->d_red, ctx->d_tickets);
+                           valid ? d_valid : nullptr, ctx->d_red);
         ctx->launches++;
     }
     unsigned char *h = pin(ctx, kRedSize * 8);
@@ -1406,12 +1385,10 @@ int fflins_window_eval(fflins_ctx *ctx, int32_t n_pairs, const uint64_t *ref_ids
                                                      b ? b + 19 * i : nullptr, cost ? cost + 2 * i : nullptr, n_res ? n_res + i : nullptr);
         return FFLINS_OK;
     }
-    if ((rc = ensure_factor_scratch(ctx, n_pairs, P.q))) return rc;
     cudaStream_t s = ctx->stream;
     {
         ProfScope ps(ctx->prof(), "factor_eval", s);
-        launch_factor_eval(s, P, (const float *) cur->c[FFLINS_CLOUD_LIDAR].d, 1, nullptr, nullptr, nullptr, ctx->d_partial,
-                           ctx->d_red, ctx->d_tickets);
+        launch_factor_eval(s, P, (const float *) cur->c[FFLINS_CLOUD_LIDAR].d, 1, nullptr, nullptr, nullptr, ctx->d_red);
         ctx->launches++;
     }
     unsigned char *h = pin(ctx, (size_t) n_pairs * kRedSize * 8);

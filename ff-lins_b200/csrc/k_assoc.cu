@@ -135,6 +135,28 @@ __device__ __forceinline__ void warp_merge5(u64 a0, u64 a1, u64 a2, u64 a3, u64 
     }
 }
 
+// 64-bit mask of the cells (sub = x | y<<2 | z<<4) of a 4x4x4 block whose Chebyshev distance to the query
+// cell is <= r; (ax, ay, az) is the offset of the block's first cell from the query cell.
+__device__ __forceinline__ unsigned axis_bits4(int a, int r) {
+    unsigned b = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) b |= (abs(a + i) <= r ? 1u : 0u) << i;
+    return b;
+}
+__device__ __forceinline__ u64 cube_mask(int ax, int ay, int az, int r) {
+    if (r < 0) return 0ull;
+    unsigned nx = axis_bits4(ax, r), ny = axis_bits4(ay, r), nz = axis_bits4(az, r);
+    u64 X = (u64) nx * 0x1111111111111111ull;
+    unsigned y16 = 0;
+#pragma unroll
+    for (int y = 0; y < 4; y++) y16 |= ((ny >> y) & 1u) ? (0xFu << (4 * y)) : 0u;
+    u64 Y = (u64) y16 * 0x0001000100010001ull;
+    u64 Z = 0ull;
+#pragma unroll
+    for (int z = 0; z < 4; z++) Z |= ((nz >> z) & 1u) ? (0xFFFFull << (16 * z)) : 0ull;
+    return X & Y & Z;
+}
+
 constexpr int kAssocWarps = 4;            // warps per CTA
 constexpr int kQueueCap   = 32 * 64;      // occupied fine cells of 32 coarse blocks
 
@@ -162,43 +184,30 @@ __device__ __forceinline__ void warp_knn5(const HashView &H, float qx, float qy,
 #pragma unroll 1
         for (int t0 = 0; t0 < total; t0 += 32) {
             const int t = t0 + lane;
-            u64 mask = 0ull;
-            int bx = 0, by = 0, bz = 0;
+            u64 keep = 0ull;
+            int ax = 0, ay = 0, az = 0; // offsets of the block's first cell from the query cell
             if (t < total) {
-                bz      = t / (nx * ny);
+                int bz  = t / (nx * ny);
                 int rem = t - bz * (nx * ny);
-                by      = rem / nx;
-                bx      = rem - by * nx;
-                bx += lox; by += loy; bz += loz;
-                // Chebyshev range of the block's cells relative to the query cell
-                int ax = bx * 4 - cx, ay = by * 4 - cy, az = bz * 4 - cz;   // offsets of the block's first cell
-                int mnx = max(0, max(ax, -(ax + 3))), mny = max(0, max(ay, -(ay + 3))), mnz = max(0, max(az, -(az + 3)));
-                int mxx = max(abs(ax), abs(ax + 3)), mxy = max(abs(ay), abs(ay + 3)), mxz = max(abs(az), abs(az + 3));
-                int ch_min = max(mnx, max(mny, mnz)), ch_max = max(mxx, max(mxy, mxz));
-                if (ch_max > lo && ch_min <= hi) {
-                    u64 ck     = pack_cell(bx, by, bz);
+                int by  = rem / nx;
+                int bx  = rem - by * nx;
+                ax = (bx + lox) * 4 - cx;
+                ay = (by + loy) * 4 - cy;
+                az = (bz + loz) * 4 - cz;
+                // cells of this block that belong to the stage (lo, hi]: pure bit arithmetic
+                u64 want = cube_mask(ax, ay, az, hi) & ~cube_mask(ax, ay, az, lo);
+                if (want) {
+                    u64 ck     = pack_cell(bx + lox, by + loy, bz + loz);
                     unsigned h = hash_cell(ck) & H.hmask;
                     while (true) {
                         u64 k = __ldg(H.ckeys + h);
                         if (k == kEmpty) break;
-                        if (k == ck) { mask = __ldg(H.cmask + h); break; }
+                        if (k == ck) { keep = __ldg(H.cmask + h) & want; break; }
                         h = (h + 1) & H.hmask;
                     }
                 }
             }
-            // keep only the cells of this stage, count, and enqueue at the warp-wide exclusive offset
-            int cnt = 0;
-            u64 keep = 0ull;
-            {
-                u64 m = mask;
-                while (m) {
-                    int sub = __ffsll((long long) m) - 1;
-                    m &= m - 1;
-                    int dx = bx * 4 + (sub & 3) - cx, dy = by * 4 + ((sub >> 2) & 3) - cy, dz = bz * 4 + (sub >> 4) - cz;
-                    int ch = max(abs(dx), max(abs(dy), abs(dz)));
-                    if (ch > lo && ch <= hi) { keep |= 1ull << sub; cnt++; }
-                }
-            }
+            const int cnt = __popcll(keep);
             int incl = cnt;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -211,7 +220,7 @@ __device__ __forceinline__ void warp_knn5(const HashView &H, float qx, float qy,
             while (keep) {
                 int sub = __ffsll((long long) keep) - 1;
                 keep &= keep - 1;
-                int dx = bx * 4 + (sub & 3) - cx, dy = by * 4 + ((sub >> 2) & 3) - cy, dz = bz * 4 + (sub >> 4) - cz;
+                int dx = ax + (sub & 3), dy = ay + ((sub >> 2) & 3), dz = az + (sub >> 4);
                 queue[off++] = (unsigned) (dx + 512) | ((unsigned) (dy + 512) << 10) | ((unsigned) (dz + 512) << 20);
             }
             __syncwarp();

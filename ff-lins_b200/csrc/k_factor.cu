@@ -18,6 +18,9 @@
 // No tensor cores: a 19-wide rank-1 update is not a dense contraction worth a tcgen05 tile.
 #include "math_factor.cuh"
 
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
 namespace fflins {
 
 namespace {
@@ -27,104 +30,100 @@ __constant__ unsigned char c_tri_b[190];
 
 constexpr int kRow = 22; // 19 J + r + rho0 + valid
 
+// Grid: (C, n_pairs) with the C CTAs of a pair forming ONE thread-block cluster (C = 1, 2, 4 or 8).
+// CTA c handles residual tiles c, c + C, ...; thread e keeps its reduction entry in a register across
+// tiles; the CTAs then exchange their 212 partial sums through distributed shared memory and rank 0
+// adds them in rank order — no global round trip, no atomics, a fixed summation order.
 __global__ void __launch_bounds__(kFactorBlock)
 factor_kernel(const __grid_constant__ FactorParams P, const float *__restrict__ points, int stride4,
               double *__restrict__ r_out, double *__restrict__ J_out, uint8_t *__restrict__ valid_out,
-              double *__restrict__ partial, double *__restrict__ out_red, unsigned int *__restrict__ tickets) {
-    __shared__ PairConst pc;
+              double *__restrict__ out_red) {
     __shared__ double rows[kFactorBlock][kRow + 1]; // +1: odd stride, conflict-free column reads
-    __shared__ bool s_last;
+    __shared__ double s_red[kRedSize];
+    cg::cluster_group cluster = cg::this_cluster();
     const int pair       = blockIdx.y;
     const FactorPair &pr = P.pair[pair];
-    if (threadIdx.x == 0) make_pair_const(P, pr, pc);
-    __syncthreads();
+    const PairConst &pc  = pr.pc;
+    const int e          = threadIdx.x;
+    int ca = 0, cb = -1;
+    double sign = 1.0;
+    if (e < 190) { ca = c_tri_a[e]; cb = c_tri_b[e]; }
+    else if (e < 209) { ca = e - 190; cb = 19; sign = -1.0; }   // b = -J^T r
+    else if (e == 209) { ca = 20; cb = -1; }                     // sum rho
+    else if (e == 210) { ca = 19; cb = 19; }                     // sum r'^2
+    else { ca = 21; cb = -1; }                                   // count
+    double acc = 0.0;
 
-    const int k = blockIdx.x * kFactorBlock + threadIdx.x;
-    bool valid  = k < P.q;
-    if (valid && pr.type) valid = (pr.type[k] == 0) && (pr.outlier[k] == 0); // optimizer.cc:468
-    double J[19], r = 0.0, rho0 = 0.0;
+    for (int tile = blockIdx.x; tile * kFactorBlock < P.q; tile += gridDim.x) {
+        const int k = tile * kFactorBlock + threadIdx.x;
+        bool valid  = k < P.q;
+        if (valid && pr.type) valid = (pr.type[k] == 0) && (pr.outlier[k] == 0); // optimizer.cc:468
+        double J[19], r = 0.0, rho0 = 0.0;
 #pragma unroll
-    for (int i = 0; i < 19; i++) J[i] = 0.0;
-    if (valid) {
-        const float *pp = points + (size_t) k * (stride4 ? 4 : 3);
-        V3 p = v3((double) pp[0], (double) pp[1], (double) pp[2]);
-        V3 n = v3(pr.normal[3 * k], pr.normal[3 * k + 1], pr.normal[3 * k + 2]);
-        double s = 1.0 / (pr.std ? pr.std[k] : P.sigma); // sqrt_info (lidar_factor.cc:38)
-        r = eval_residual<true>(pc, p, n, pr.d[k], s, J);
-        if (P.flags & 2u) { J[0] = J[1] = J[2] = J[3] = J[4] = J[5] = 0.0; }
-        if (P.flags & 4u) { J[6] = J[7] = J[8] = J[9] = J[10] = J[11] = 0.0; }
-        if (P.flags & 8u) { J[12] = J[13] = J[14] = J[15] = J[16] = J[17] = 0.0; }
-        if (P.flags & 16u) J[18] = 0.0;
-        if (P.flags & 1u) rho0 = huber_correct(P.huber_delta, r, J);
-        else rho0 = r * r;
-    }
-    if (k < P.q) {
-        size_t o = (size_t) pair * P.q + k;
-        if (valid_out) valid_out[o] = valid ? 1 : 0;
-        if (r_out) r_out[o] = r;
-        if (J_out) {
-            double *Jo = J_out + 22 * o;   // 1x7, 1x7, 1x7, 1x1 row-major; column 6 of each pose block is zero
+        for (int i = 0; i < 19; i++) J[i] = 0.0;
+        if (valid) {
+            const float *pp = points + (size_t) k * (stride4 ? 4 : 3);
+            V3 p = v3((double) pp[0], (double) pp[1], (double) pp[2]);
+            V3 n = v3(pr.normal[3 * k], pr.normal[3 * k + 1], pr.normal[3 * k + 2]);
+            double s = 1.0 / (pr.std ? pr.std[k] : P.sigma); // sqrt_info (lidar_factor.cc:38)
+            r = eval_residual<true>(pc, p, n, pr.d[k], s, J);
+            if (P.flags & 2u) { J[0] = J[1] = J[2] = J[3] = J[4] = J[5] = 0.0; }
+            if (P.flags & 4u) { J[6] = J[7] = J[8] = J[9] = J[10] = J[11] = 0.0; }
+            if (P.flags & 8u) { J[12] = J[13] = J[14] = J[15] = J[16] = J[17] = 0.0; }
+            if (P.flags & 16u) J[18] = 0.0;
+            if (P.flags & 1u) rho0 = huber_correct(P.huber_delta, r, J);
+            else rho0 = r * r;
+        }
+        if (k < P.q) {
+            size_t o = (size_t) pair * P.q + k;
+            if (valid_out) valid_out[o] = valid ? 1 : 0;
+            if (r_out) r_out[o] = r;
+            if (J_out) {
+                double *Jo = J_out + 22 * o;   // 1x7, 1x7, 1x7, 1x1 row-major; column 6 of each pose block is zero
 #pragma unroll
-            for (int b = 0; b < 3; b++) {
+                for (int b = 0; b < 3; b++) {
 #pragma unroll
-                for (int i = 0; i < 6; i++) Jo[7 * b + i] = J[6 * b + i];
-                Jo[7 * b + 6] = 0.0;
+                    for (int i = 0; i < 6; i++) Jo[7 * b + i] = J[6 * b + i];
+                    Jo[7 * b + 6] = 0.0;
+                }
+                Jo[21] = J[18];
             }
-            Jo[21] = J[18];
         }
-    }
-    if (partial == nullptr) return;
+        if (out_red == nullptr) continue;
 #pragma unroll
-    for (int i = 0; i < 19; i++) rows[threadIdx.x][i] = J[i];
-    rows[threadIdx.x][19] = r;
-    rows[threadIdx.x][20] = rho0;
-    rows[threadIdx.x][21] = valid ? 1.0 : 0.0;
-    __syncthreads();
-    const int e = threadIdx.x;
-    if (e < kRedSize) {
-        int ca, cb;
-        double sign = 1.0;
-        if (e < 190) { ca = c_tri_a[e]; cb = c_tri_b[e]; }
-        else if (e < 209) { ca = e - 190; cb = 19; sign = -1.0; }   // b = -J^T r
-        else if (e == 209) { ca = 20; cb = -1; }                     // sum rho
-        else if (e == 210) { ca = 19; cb = 19; }                     // sum r'^2
-        else { ca = 21; cb = -1; }                                   // count
-        double acc = 0.0;
-        if (cb >= 0) {
+        for (int i = 0; i < 19; i++) rows[threadIdx.x][i] = J[i];
+        rows[threadIdx.x][19] = r;
+        rows[threadIdx.x][20] = rho0;
+        rows[threadIdx.x][21] = valid ? 1.0 : 0.0;
+        __syncthreads();
+        if (e < kRedSize) {
+            if (cb >= 0) {
 #pragma unroll 8
-            for (int i = 0; i < kFactorBlock; i++) acc += rows[i][ca] * rows[i][cb];
-        } else {
+                for (int i = 0; i < kFactorBlock; i++) acc += rows[i][ca] * rows[i][cb];
+            } else {
 #pragma unroll 8
-            for (int i = 0; i < kFactorBlock; i++) acc += rows[i][ca];
+                for (int i = 0; i < kFactorBlock; i++) acc += rows[i][ca];
+            }
         }
-        partial[((size_t) pair * gridDim.x + blockIdx.x) * kRedSize + e] = sign * acc;
+        __syncthreads();
     }
-    // last CTA of the pair sums the CTA partials in CTA order
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned t = atomicAdd(tickets + pair, 1u);
-        s_last     = (t == gridDim.x - 1);
+    if (out_red == nullptr) return;
+    if (e < kRedSize) s_red[e] = sign * acc;
+    cluster.sync();
+    if (cluster.block_rank() == 0 && e < kRedSize) {
+        double total = 0.0;
+        for (unsigned rk = 0; rk < cluster.num_blocks(); rk++) total += cluster.map_shared_rank(s_red, rk)[e];
+        out_red[(size_t) pair * kRedSize + e] = total;
     }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    if (e < kRedSize) {
-        double acc = 0.0;
-        for (unsigned b = 0; b < gridDim.x; b++) acc += __ldcg(partial + ((size_t) pair * gridDim.x + b) * kRedSize + e);
-        out_red[(size_t) pair * kRedSize + e] = acc;
-    }
-    if (threadIdx.x == 0) tickets[pair] = 0;
+    cluster.sync(); // keep every CTA's shared memory alive until rank 0 has read it
 }
 
 __global__ void __launch_bounds__(256)
 chi2_kernel(const __grid_constant__ FactorParams P, const float *__restrict__ points, int stride4, double threshold,
             int *__restrict__ n_outliers) {
-    __shared__ PairConst pc;
     const int pair       = blockIdx.y;
     const FactorPair &pr = P.pair[pair];
-    if (threadIdx.x == 0) make_pair_const(P, pr, pc);
-    __syncthreads();
+    const PairConst &pc  = pr.pc;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     bool out    = false;
     if (k < P.q && pr.type[k] == 0 && pr.outlier[k] == 0) {
@@ -164,17 +163,32 @@ void init_tri() {
 
 } // namespace
 
-void launch_factor_eval(cudaStream_t s, const FactorParams &p, const float *points, int stride4, double *r, double *J,
-                        uint8_t *valid, double *partial, double *out_red, unsigned int *tickets) {
+void launch_factor_eval(cudaStream_t s, FactorParams &p, const float *points, int stride4, double *r, double *J,
+                        uint8_t *valid, double *out_red) {
     if (p.n_pairs <= 0 || p.q <= 0) return;
     init_tri();
-    dim3 grid((p.q + kFactorBlock - 1) / kFactorBlock, p.n_pairs);
-    factor_kernel<<<grid, kFactorBlock, 0, s>>>(p, points, stride4, r, J, valid, partial, out_red, tickets);
+    for (int i = 0; i < p.n_pairs; i++) make_pair_const(p, p.pair[i], p.pair[i].pc);
+    int tiles = (p.q + kFactorBlock - 1) / kFactorBlock;
+    int C     = 1;
+    while (C < tiles && C < 8) C <<= 1; // cluster of 1, 2, 4 or 8 CTAs per pair
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim          = dim3(C, p.n_pairs);
+    cfg.blockDim         = dim3(kFactorBlock);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream           = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id               = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs    = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, factor_kernel, p, points, stride4, r, J, valid, out_red);
 }
 
-void launch_chi2(cudaStream_t s, const FactorParams &p, const float *points, int stride4, double threshold,
-                 int *n_outliers) {
+void launch_chi2(cudaStream_t s, FactorParams &p, const float *points, int stride4, double threshold, int *n_outliers) {
     if (p.n_pairs <= 0 || p.q <= 0) return;
+    for (int i = 0; i < p.n_pairs; i++) make_pair_const(p, p.pair[i], p.pair[i].pc);
     dim3 grid((p.q + 255) / 256, p.n_pairs);
     chi2_kernel<<<grid, 256, 0, s>>>(p, points, stride4, threshold, n_outliers);
 }

@@ -23,8 +23,8 @@ namespace fflins {
 namespace {
 
 constexpr int RS_THREADS = 256;
-constexpr int RS_ITEMS   = 16;
-constexpr int RS_TILE    = RS_THREADS * RS_ITEMS; // 4096
+constexpr int RS_ITEMS   = 8;
+constexpr int RS_TILE    = RS_THREADS * RS_ITEMS; // 2048
 constexpr int RS_WARPS   = RS_THREADS / 32;
 constexpr int SEG_THREADS = 256;
 constexpr int SEG_ITEMS   = 4;
@@ -202,12 +202,17 @@ rs_scatter_kernel(uint32_t *k0, uint32_t *k1, uint32_t *x0, uint32_t *x1, const 
     const int chunk = blockIdx.x * RS_TILE + wid * (RS_TILE / RS_WARPS);
     uint32_t key[RS_ITEMS], val[RS_ITEMS], rank[RS_ITEMS];
     const unsigned lt = (1u << lane) - 1u;
+    // all loads of the tile first (independent, in flight together), ranking afterwards
 #pragma unroll
     for (int r = 0; r < RS_ITEMS; r++) {
-        int i      = chunk + r * 32 + lane;
-        bool valid = i < n;
-        key[r]     = valid ? keys[i] : 0xffffffffu;
-        val[r]     = valid ? (pass == 0 ? (uint32_t) i : idx[i]) : 0u;
+        int i  = chunk + r * 32 + lane;
+        key[r] = (i < n) ? keys[i] : 0xffffffffu;
+        val[r] = (i < n) ? (pass == 0 ? (uint32_t) i : idx[i]) : 0u;
+    }
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; r++) {
+        int i          = chunk + r * 32 + lane;
+        bool valid     = i < n;
         uint32_t digit = (key[r] >> shift) & 255u;
         unsigned m     = __match_any_sync(0xffffffffu, valid ? digit : 256u + lane);
         uint32_t prev  = warp_hist[wid][digit];
@@ -329,6 +334,7 @@ seg_starts_kernel(const uint32_t *__restrict__ k0, const uint32_t *__restrict__ 
 // in ascending original index — sequentially, because fp32 addition is not associative and the
 // result must equal PCL's (Appendix A.1 step 7). Every lane runs the same chain; lane 0 stores.
 constexpr int CEN_THREADS = 256;
+constexpr int CEN_ROUND   = 128; // points staged per warp round
 __global__ void __launch_bounds__(CEN_THREADS)
 seg_centroid_kernel(const float4 *__restrict__ in, const uint32_t *__restrict__ x0, const uint32_t *__restrict__ x1,
                     const int *__restrict__ meta, int n, const uint32_t *__restrict__ seg_start, float4 *__restrict__ out) {
@@ -337,7 +343,7 @@ seg_centroid_kernel(const float4 *__restrict__ in, const uint32_t *__restrict__ 
         for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = in[i];
         return;
     }
-    __shared__ float4 stage[CEN_THREADS / 32][32];
+    __shared__ float4 stage[CEN_THREADS / 32][CEN_ROUND];
     const uint32_t *idx = meta[M_PARITY + 4] ? x1 : x0;
     const int n_seg     = meta[M_NOUT];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -345,11 +351,15 @@ seg_centroid_kernel(const float4 *__restrict__ in, const uint32_t *__restrict__ 
     for (int s = blockIdx.x * (CEN_THREADS / 32) + wid; s < n_seg; s += warps) {
         const int start = (int) seg_start[s], end = (int) seg_start[s + 1];
         float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
-        for (int base = start; base < end; base += 32) {
-            int e = base + lane;
-            if (e < end) stage[wid][lane] = __ldg(in + idx[e]);
+        for (int base = start; base < end; base += CEN_ROUND) {
+            // up to 4 gathers per lane in flight before the ordered accumulation
+#pragma unroll
+            for (int c = 0; c < CEN_ROUND / 32; c++) {
+                int e = base + c * 32 + lane;
+                if (e < end) stage[wid][c * 32 + lane] = __ldg(in + idx[e]);
+            }
             __syncwarp();
-            const int cnt = min(32, end - base);
+            const int cnt = min(CEN_ROUND, end - base);
 #pragma unroll 4
             for (int j = 0; j < cnt; j++) {
                 float4 p = stage[wid][j];

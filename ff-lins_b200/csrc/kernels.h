@@ -114,6 +114,11 @@ void launch_plane_estimation(cudaStream_t s, const float4 *pts, int n, double th
                              double *dist, uint8_t *ok);
 
 // ---- K6 / K7 factors (lidar_factor.cc:41-118, residual_block_info.cc:49-77, marginalization_info.cc:181-210)
+// everything of LidarFactor::Evaluate that depends only on the (ref, cur) pair (math_factor.cuh)
+struct PairConst {
+    M3 R0, B0, Rt0, R1, B1, Rt1, Rbl, D, E;
+    V3 tt0, tt1, tbl, w0, w1, dv;
+};
 struct FactorPair {
     const int8_t *type;     // nullptr => every residual valid (stateless batch)
     uint8_t *outlier;       // read by K6, written by K7
@@ -122,6 +127,7 @@ struct FactorPair {
     const double *std;      // nullptr => sigma below
     double pose_ref[7];
     double v0[3], w0[3], td0;
+    PairConst pc;           // filled on the host by the launchers (make_pair_const)
 };
 struct FactorParams {
     int n_pairs;
@@ -136,10 +142,10 @@ constexpr int kFactorBlock = 256;
 constexpr int kRedSize     = 212; // 190 upper-tri H + 19 b + cost0 + cost1 + count
 // points: xyz of cur-frame points as float4 (stride4=1) or packed float3 (stride4=0).
 // r/J/valid (optional) are per (pair, feature): r[pair*q+k], J[22*(pair*q+k)].
-// partial: n_pairs * blocks_per_pair * kRedSize doubles; out_red: n_pairs * kRedSize doubles.
-void launch_factor_eval(cudaStream_t s, const FactorParams &p, const float *points, int stride4, double *r, double *J,
-                        uint8_t *valid, double *partial, double *out_red, unsigned int *tickets);
-void launch_chi2(cudaStream_t s, const FactorParams &p, const float *points, int stride4, double threshold,
-                 int *n_outliers);
+// out_red: n_pairs * kRedSize doubles (nullptr: no reduction). The params are completed in place
+// (PairConst per pair) before the launch.
+void launch_factor_eval(cudaStream_t s, FactorParams &p, const float *points, int stride4, double *r, double *J,
+                        uint8_t *valid, double *out_red);
+void launch_chi2(cudaStream_t s, FactorParams &p, const float *points, int stride4, double threshold, int *n_outliers);
 
 } // namespace fflins

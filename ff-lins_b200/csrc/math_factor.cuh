@@ -8,11 +8,6 @@
 
 namespace fflins {
 
-struct PairConst {
-    M3 R0, B0, Rt0, R1, B1, Rt1, Rbl, D, E;
-    V3 tt0, tt1, tbl, w0, w1, dv;
-};
-
 __host__ __device__ __forceinline__ M3 skew_plus_I(V3 v) { return M3{{1.0, -v.z, v.y, v.z, 1.0, -v.x, -v.y, v.x, 1.0}}; }
 
 __host__ __device__ inline void make_pair_const(const FactorParams &P, const FactorPair &pr, PairConst &c) {
