@@ -369,13 +369,18 @@ int check_window(fflins_ctx *ctx, const double *ins_t, int w) {
     return FFLINS_OK;
 }
 
+// one H2D copy per frame: t | p | q packed into the pinned staging area first (64 B per entry)
 int upload_ins(fflins_ctx *ctx, const double *ins_t, const double *ins_p, const double *ins_q, int w) {
     int rc;
     if ((rc = ensure_ins(ctx, w))) return rc;
-    cudaStream_t s = ctx->stream;
-    CK(cudaMemcpyAsync(ctx->d_ins, ins_t, (size_t) w * 8, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(ctx->d_ins + w, ins_p, (size_t) w * 24, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(ctx->d_ins + 4 * (size_t) w, ins_q, (size_t) w * 32, cudaMemcpyHostToDevice, s));
+    const size_t off = 65536;
+    unsigned char *h = pin(ctx, off + (size_t) w * 64);
+    if (!h) return fail(ctx, FFLINS_E_NOMEM, "pinned allocation failed");
+    double *hp = (double *) (h + off);
+    std::memcpy(hp, ins_t, (size_t) w * 8);
+    std::memcpy(hp + w, ins_p, (size_t) w * 24);
+    std::memcpy(hp + 4 * (size_t) w, ins_q, (size_t) w * 32);
+    CK(cudaMemcpyAsync(ctx->d_ins, hp, (size_t) w * 64, cudaMemcpyHostToDevice, ctx->stream));
     return FFLINS_OK;
 }
 
@@ -395,7 +400,6 @@ int process_core(fflins_ctx *ctx, uint64_t id, const float4 *d_xyzi, const doubl
     if ((rc = ensure_cloud(ctx, f->c[FFLINS_CLOUD_LIDAR], ndec))) return rc;
     if ((rc = ensure_cloud(ctx, f->c[FFLINS_CLOUD_WORLD], ndec))) return rc;
     if ((rc = upload_ins(ctx, ins_t, ins_p, ins_q, w))) return rc;
-    CK(cudaMemsetAsync(ctx->d_counters, 0, 4 * sizeof(int), s));
     Pose12 ext = to12(*pose_b_l), frame;
     pose_from_window(ins_t, ins_p, ins_q, w, ext, stamp, frame);
     std::memcpy(f->pose.R, frame.R, sizeof(frame.R));
@@ -403,7 +407,7 @@ int process_core(fflins_ctx *ctx, uint64_t id, const float4 *d_xyzi, const doubl
     const double *d_ins_t = ctx->d_ins, *d_ins_p = ctx->d_ins + w, *d_ins_q = ctx->d_ins + 4 * (size_t) w;
     {
         ProfScope ps(ctx->prof(), "ins_prep", s);
-        launch_ins_prep(s, d_ins_t, d_ins_p, d_ins_q, w, ext, frame, ctx->d_tab);
+        launch_ins_prep(s, d_ins_t, d_ins_p, d_ins_q, w, ext, frame, ctx->d_tab, ctx->d_counters);
         ctx->launches++;
     }
     {
@@ -528,7 +532,7 @@ int run_associate(fflins_ctx *ctx, const std::vector<Frame *> &refs, Frame *cur,
     {
         ProfScope ps(ctx->prof(), "associate", s);
         launch_associate(s, P, cur->c[FFLINS_CLOUD_WORLD].d, cur->c[FFLINS_CLOUD_LIDAR].d);
-        if (q > 0 && !refs.empty()) ctx->launches++;
+        if (q > 0 && !refs.empty()) ctx->launches += 2;
     }
     unsigned char *h = pin(ctx, 1024);
     if (!h) return fail(ctx, FFLINS_E_NOMEM, "pinned allocation failed");

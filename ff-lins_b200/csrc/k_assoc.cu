@@ -243,9 +243,9 @@ __device__ __forceinline__ void warp_knn5(const HashView &H, float qx, float qy,
     }
 }
 
+// K5a: one warp per (ref, query): exact 5-NN only. Writes nn_idx / nn_d2 (ascending, -1 padded).
 __global__ void __launch_bounds__(kAssocWarps * 32)
-associate_kernel(const __grid_constant__ AssocParams P, const float4 *__restrict__ cur_world,
-                 const float4 *__restrict__ cur_lidar) {
+associate_knn_kernel(const __grid_constant__ AssocParams P, const float4 *__restrict__ cur_world) {
     __shared__ unsigned s_queue[kAssocWarps][kQueueCap];
     const int lane  = threadIdx.x & 31;
     const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -253,49 +253,12 @@ associate_kernel(const __grid_constant__ AssocParams P, const float4 *__restrict
     const int ri = gwarp / P.q;
     const int k  = gwarp - ri * P.q;
     const AssocRef &ref = P.ref[ri];
-
     // world -> ref lidar frame (lidar_map.cc:343-345,355-357): fp64 math, fp32 store
-    float4 wp  = __ldg(cur_world + k);
-    float4 rp  = project_rn(ref.T_ref_world.R, ref.T_ref_world.t, wp);
+    float4 rp   = project_rn(ref.T_ref_world.R, ref.T_ref_world.t, __ldg(cur_world + k));
     u64 best[5] = {kInf, kInf, kInf, kInf, kInf};
     if (ref.m > 0) {
         HashView H{ref.map, ref.hkeys, ref.hvals, ref.ckeys, ref.cmask, ref.hmask};
         warp_knn5(H, rp.x, rp.y, rp.z, P.inv_cell, P.cell, P.r_max, P.max_d2, s_queue[threadIdx.x >> 5], best);
-    }
-
-    int found = 0;
-#pragma unroll
-    for (int j = 0; j < 5; j++) found += (best[j] != kInf) ? 1 : 0;
-    int8_t type     = -1;
-    uint8_t covered = 0;
-    double unit[3]  = {0, 0, 0}, ninv = 0;
-    if (found == 5) {
-        covered  = 1;
-        float d5 = __uint_as_float((unsigned) (best[4] >> 32));
-        if (d5 < P.plane_d2_gate) {
-            float4 pts[5];
-#pragma unroll
-            for (int j = 0; j < 5; j++) pts[j] = __ldg(ref.map + (unsigned) (best[j] & 0xffffffffu));
-            double dist[5];
-            if (plane_estimation(pts, P.plane_thr, unit, ninv, dist)) {
-                double dis = fabs(((unit[0] * (double) rp.x + unit[1] * (double) rp.y) + unit[2] * (double) rp.z) + ninv);
-                float4 lp  = __ldg(cur_lidar + k);
-                float nrm  = sqrtf((lp.x * lp.x + lp.y * lp.y) + lp.z * lp.z);
-                double scalar = dis / (double) sqrtf(nrm); // lidar_map.cc:384 (fp32 sqrt of the fp32 norm)
-                if (scalar < P.scalar_thr && dis < P.sigma_gate * P.sigma) type = 0;
-            }
-        }
-    }
-    if (lane == 0) {
-        ref.feat.type[k]    = type;
-        ref.feat.covered[k] = covered;
-        ref.feat.outlier[k] = 0; // updateFeature(..., is_outlier=false) lidar_map.cc:394
-        ref.feat.normal[3 * k + 0] = unit[0];
-        ref.feat.normal[3 * k + 1] = unit[1];
-        ref.feat.normal[3 * k + 2] = unit[2];
-        ref.feat.d[k] = ninv;
-        if (type == 0) atomicAdd(ref.counts + 0, 1);
-        if (covered) atomicAdd(ref.counts + 1, 1);
     }
     if (lane < 5) {
         u64 b = best[0];
@@ -304,6 +267,55 @@ associate_kernel(const __grid_constant__ AssocParams P, const float4 *__restrict
         bool have = b != kInf;
         ref.feat.nn_idx[5 * k + lane] = have ? (int) (unsigned) (b & 0xffffffffu) : -1;
         ref.feat.nn_d2[5 * k + lane]  = have ? __uint_as_float((unsigned) (b >> 32)) : 0.f;
+    }
+}
+
+// K5b: one THREAD per (ref, query): plane fit + validity tests + feature record (lidar_map.cc:371-395).
+// Split from the search so that the ~1,500-instruction fp64 QR runs once per lane instead of once per warp.
+__global__ void __launch_bounds__(128)
+associate_plane_kernel(const __grid_constant__ AssocParams P, const float4 *__restrict__ cur_world,
+                       const float4 *__restrict__ cur_lidar) {
+    const int ri = blockIdx.y;
+    const int k  = blockIdx.x * blockDim.x + threadIdx.x;
+    const AssocRef &ref = P.ref[ri];
+    int8_t type     = -1;
+    uint8_t covered = 0;
+    if (k < P.q) {
+        float4 rp = project_rn(ref.T_ref_world.R, ref.T_ref_world.t, __ldg(cur_world + k));
+        int idx[5];
+#pragma unroll
+        for (int j = 0; j < 5; j++) idx[j] = ref.feat.nn_idx[5 * k + j];
+        double unit[3] = {0, 0, 0}, ninv = 0;
+        if (idx[4] >= 0) { // five neighbours found (ascending, -1 padded)
+            covered  = 1;
+            float d5 = ref.feat.nn_d2[5 * k + 4];
+            if (d5 < P.plane_d2_gate) {
+                float4 pts[5];
+#pragma unroll
+                for (int j = 0; j < 5; j++) pts[j] = __ldg(ref.map + idx[j]);
+                double dist[5];
+                if (plane_estimation(pts, P.plane_thr, unit, ninv, dist)) {
+                    double dis = fabs(((unit[0] * (double) rp.x + unit[1] * (double) rp.y) + unit[2] * (double) rp.z) + ninv);
+                    float4 lp  = __ldg(cur_lidar + k);
+                    float nrm  = sqrtf((lp.x * lp.x + lp.y * lp.y) + lp.z * lp.z);
+                    double scalar = dis / (double) sqrtf(nrm); // lidar_map.cc:384 (fp32 sqrt of the fp32 norm)
+                    if (scalar < P.scalar_thr && dis < P.sigma_gate * P.sigma) type = 0;
+                }
+            }
+        }
+        ref.feat.type[k]    = type;
+        ref.feat.covered[k] = covered;
+        ref.feat.outlier[k] = 0; // updateFeature(..., is_outlier=false) lidar_map.cc:394
+        ref.feat.normal[3 * k + 0] = unit[0];
+        ref.feat.normal[3 * k + 1] = unit[1];
+        ref.feat.normal[3 * k + 2] = unit[2];
+        ref.feat.d[k] = ninv;
+    }
+    int nf = __syncthreads_count(type == 0);
+    int nc = __syncthreads_count(covered != 0);
+    if (threadIdx.x == 0) {
+        if (nf) atomicAdd(ref.counts + 0, nf);
+        if (nc) atomicAdd(ref.counts + 1, nc);
     }
 }
 
@@ -372,7 +384,9 @@ void launch_associate(cudaStream_t s, const AssocParams &p, const float4 *cur_wo
     long long warps = (long long) p.n_refs * p.q;
     if (warps <= 0) return;
     int grid = (int) ((warps + kAssocWarps - 1) / kAssocWarps);
-    associate_kernel<<<grid, kAssocWarps * 32, 0, s>>>(p, cur_world, cur_lidar);
+    associate_knn_kernel<<<grid, kAssocWarps * 32, 0, s>>>(p, cur_world);
+    dim3 g2((p.q + 127) / 128, p.n_refs);
+    associate_plane_kernel<<<g2, 128, 0, s>>>(p, cur_world, cur_lidar);
 }
 
 void launch_knn5(cudaStream_t s, const float4 *map, const unsigned long long *hkeys, const int *hvals,

@@ -52,7 +52,8 @@ factor_kernel(const __grid_constant__ FactorParams P, const float *__restrict__ 
     else if (e == 209) { ca = 20; cb = -1; }                     // sum rho
     else if (e == 210) { ca = 19; cb = 19; }                     // sum r'^2
     else { ca = 21; cb = -1; }                                   // count
-    double acc = 0.0;
+    // four interleaved partial sums shorten the dependent DFMA chain 4x; they are combined in a fixed order
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
 
     for (int tile = blockIdx.x; tile * kFactorBlock < P.q; tile += gridDim.x) {
         const int k = tile * kFactorBlock + threadIdx.x;
@@ -98,17 +99,27 @@ factor_kernel(const __grid_constant__ FactorParams P, const float *__restrict__ 
         __syncthreads();
         if (e < kRedSize) {
             if (cb >= 0) {
-#pragma unroll 8
-                for (int i = 0; i < kFactorBlock; i++) acc += rows[i][ca] * rows[i][cb];
+#pragma unroll 4
+                for (int i = 0; i < kFactorBlock; i += 4) {
+                    acc0 += rows[i][ca] * rows[i][cb];
+                    acc1 += rows[i + 1][ca] * rows[i + 1][cb];
+                    acc2 += rows[i + 2][ca] * rows[i + 2][cb];
+                    acc3 += rows[i + 3][ca] * rows[i + 3][cb];
+                }
             } else {
-#pragma unroll 8
-                for (int i = 0; i < kFactorBlock; i++) acc += rows[i][ca];
+#pragma unroll 4
+                for (int i = 0; i < kFactorBlock; i += 4) {
+                    acc0 += rows[i][ca];
+                    acc1 += rows[i + 1][ca];
+                    acc2 += rows[i + 2][ca];
+                    acc3 += rows[i + 3][ca];
+                }
             }
         }
         __syncthreads();
     }
     if (out_red == nullptr) return;
-    if (e < kRedSize) s_red[e] = sign * acc;
+    if (e < kRedSize) s_red[e] = sign * ((acc0 + acc1) + (acc2 + acc3));
     cluster.sync();
     if (cluster.block_rank() == 0 && e < kRedSize) {
         double total = 0.0;

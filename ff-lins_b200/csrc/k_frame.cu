@@ -25,8 +25,9 @@ namespace {
 // out-of-window fallback. The quaternion log (atan2 + divisions) happens here, once per interval.
 __global__ void ins_prep_kernel(const double *__restrict__ ins_t, const double *__restrict__ ins_p,
                                 const double *__restrict__ ins_q, int w, Pose12 ext, Pose12 frame,
-                                double *__restrict__ rows) {
+                                double *__restrict__ rows, int *__restrict__ counters) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 4) counters[i] = 0; // per-frame counters (fallbacks, voxel count): saves a memset in the stream
     if (i >= w) return;
     double row[kRowSize];
     interval_row(ins_t, ins_p, ins_q, w, i, ext, frame, row);
@@ -119,8 +120,8 @@ inline int grid_for(int n, int block, int per_sm = 8) {
 } // namespace
 
 void launch_ins_prep(cudaStream_t s, const double *ins_t, const double *ins_p, const double *ins_q, int w, Pose12 ext,
-                     Pose12 frame_pose, double *rows) {
-    ins_prep_kernel<<<(w + 63) / 64, 64, 0, s>>>(ins_t, ins_p, ins_q, w, ext, frame_pose, rows);
+                     Pose12 frame_pose, double *rows, int *counters) {
+    ins_prep_kernel<<<(w + 63) / 64, 64, 0, s>>>(ins_t, ins_p, ins_q, w, ext, frame_pose, rows, counters);
 }
 
 void launch_undistort(cudaStream_t s, const float4 *xyzi, const double *time, const void *aos, int n,

@@ -23,8 +23,8 @@ namespace fflins {
 namespace {
 
 constexpr int RS_THREADS = 256;
-constexpr int RS_ITEMS   = 8;
-constexpr int RS_TILE    = RS_THREADS * RS_ITEMS; // 2048
+constexpr int RS_ITEMS   = 16;
+constexpr int RS_TILE    = RS_THREADS * RS_ITEMS; // 4096
 constexpr int RS_WARPS   = RS_THREADS / 32;
 constexpr int SEG_THREADS = 256;
 constexpr int SEG_ITEMS   = 4;
@@ -54,6 +54,9 @@ __global__ void __launch_bounds__(256) vox_bbox_kernel(const float4 *__restrict_
         mn[1] = fminf(mn[1], p.y); mx[1] = fmaxf(mx[1], p.y);
         mn[2] = fminf(mn[2], p.z); mx[2] = fmaxf(mx[2], p.z);
     }
+    // warp shuffle -> shared memory -> 6 atomics per CTA
+    __shared__ float s_mn[3][8], s_mx[3][8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
     for (int a = 0; a < 3; a++) {
 #pragma unroll
@@ -61,12 +64,24 @@ __global__ void __launch_bounds__(256) vox_bbox_kernel(const float4 *__restrict_
             mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
             mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
         }
+        if (lane == 0) {
+            s_mn[a][wid] = mn[a];
+            s_mx[a][wid] = mx[a];
+        }
     }
-    if ((threadIdx.x & 31) == 0) {
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        const int a = threadIdx.x % 3;
+        if (threadIdx.x < 3) {
+            float v = s_mn[a][0];
 #pragma unroll
-        for (int a = 0; a < 3; a++) {
-            atomicMin(meta + M_BBOX + a, f2ord(mn[a]));
-            atomicMax(meta + M_BBOX + 3 + a, f2ord(mx[a]));
+            for (int w = 1; w < 8; w++) v = fminf(v, s_mn[a][w]);
+            atomicMin(meta + M_BBOX + a, f2ord(v));
+        } else {
+            float v = s_mx[a][0];
+#pragma unroll
+            for (int w = 1; w < 8; w++) v = fmaxf(v, s_mx[a][w]);
+            atomicMax(meta + M_BBOX + 3 + a, f2ord(v));
         }
     }
 }
@@ -145,42 +160,65 @@ rs_hist_kernel(const uint32_t *__restrict__ k0, const uint32_t *__restrict__ k1,
     block_hist[threadIdx.x * nb + blockIdx.x] = hist[threadIdx.x];
 }
 
+// Exclusive scan of the digit-major per-tile histogram (256 * nb entries), one CTA. Each warp owns a
+// contiguous chunk and reads it with coalesced 128-byte requests that are all in flight together
+// (values stay in registers), scans 32 values per shuffle round with a running carry, the 32 warp
+// totals are scanned through shared memory and the offsets written back in one pass.
+constexpr int SCAN_ITEMS = 16;                       // 32-value rounds per warp and super-chunk
+constexpr int SCAN_SUPER = 32 * 32 * SCAN_ITEMS;     // 16384 entries per super-chunk
 __global__ void __launch_bounds__(1024)
 rs_scan_kernel(int *__restrict__ meta, int pass, uint32_t *__restrict__ block_hist, int total) {
     const bool active = pass * 8 < meta[M_NBITS];
     if (threadIdx.x == 0) meta[M_PARITY + pass + 1] = meta[M_PARITY + pass] ^ (active ? 1 : 0);
     if (!active) return;
     __shared__ uint32_t warp_sums[32];
-    const int per = (total + 1023) / 1024;
-    const int lo  = threadIdx.x * per;
-    const int hi  = min(total, lo + per);
-    uint32_t sum  = 0;
-    for (int i = lo; i < hi; i++) sum += block_hist[i];
-    // block exclusive scan of `sum`
-    uint32_t incl = sum;
+    __shared__ uint32_t s_carry;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-    }
-    if (lane == 31) warp_sums[wid] = incl;
+    if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
-    if (wid == 0) {
-        uint32_t w = warp_sums[lane], wi = w;
+    for (int sbase = 0; sbase < total; sbase += SCAN_SUPER) {
+        const int wbase = sbase + wid * (32 * SCAN_ITEMS);
+        uint32_t v[SCAN_ITEMS];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t v = __shfl_up_sync(0xffffffffu, wi, o);
-            if (lane >= o) wi += v;
+        for (int r = 0; r < SCAN_ITEMS; r++) {
+            int i = wbase + r * 32 + lane;
+            v[r]  = (i < total) ? block_hist[i] : 0u;
         }
-        warp_sums[lane] = wi - w;
-    }
-    __syncthreads();
-    uint32_t run = warp_sums[wid] + incl - sum;
-    for (int i = lo; i < hi; i++) {
-        uint32_t v    = block_hist[i];
-        block_hist[i] = run;
-        run += v;
+        uint32_t run = 0; // running total of this warp's earlier rounds
+#pragma unroll
+        for (int r = 0; r < SCAN_ITEMS; r++) {
+            uint32_t incl = v[r];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += u;
+            }
+            uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+            v[r]         = run + incl - v[r]; // exclusive within the warp chunk
+            run += tot;
+        }
+        if (lane == 0) warp_sums[wid] = run;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t w = warp_sums[lane], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t u = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += u;
+            }
+            warp_sums[lane] = wi - w; // exclusive offset of each warp inside the super-chunk
+        }
+        __syncthreads();
+        const uint32_t base = s_carry + warp_sums[wid];
+#pragma unroll
+        for (int r = 0; r < SCAN_ITEMS; r++) {
+            int i = wbase + r * 32 + lane;
+            if (i < total) block_hist[i] = base + v[r];
+        }
+        __syncthreads();
+        // carry for the next super-chunk: offset of the last warp + its total
+        if (threadIdx.x == 1023) s_carry = base + run;
+        __syncthreads();
     }
 }
 

@@ -362,6 +362,25 @@ class Context:
                                            _p(out["cost"]), _p(out["n_res"])))
         return out
 
+    def window_eval_prepared(self, prep, td, flags, out):
+        """Same call with the argument arrays converted once (`prepare_window`): what a C++ caller pays."""
+        self._ck(self.L.fflins_window_eval(self.h, prep["n"], prep["ids_p"], prep["refs_p"], prep["cur_p"], prep["ext_p"],
+                                           C.c_double(td), C.c_uint32(flags), out["H_p"], out["b_p"], out["cost_p"],
+                                           out["n_res_p"]))
+        return out
+
+    @staticmethod
+    def prepare_window(ref_ids, pose_refs, pose_cur, ext):
+        ids = np.array(list(ref_ids), np.uint64)
+        n = len(ids)
+        refs = _c(pose_refs, np.float64).reshape(n, 7)
+        cur, ex = _pose7(pose_cur), _pose7(ext)
+        out = dict(H=np.zeros((n, 19, 19)), b=np.zeros((n, 19)), cost=np.zeros((n, 2)), n_res=np.zeros(n, np.int32))
+        for k in ("H", "b", "cost", "n_res"):
+            out[k + "_p"] = _p(out[k])
+        prep = dict(n=n, ids=ids, refs=refs, cur=cur, ext=ex, ids_p=_p(ids), refs_p=_p(refs), cur_p=_p(cur), ext_p=_p(ex))
+        return prep, out
+
     def window_chi2(self, ref_ids, pose_refs, pose_cur, ext, td, threshold=3.841):
         ids = np.array(list(ref_ids), np.uint64)
         n = len(ids)

@@ -97,13 +97,13 @@ class Session:
             # solver state: IMU pose blocks of the keyframes (precomputed per frame when available)
             pose_refs = np.stack([self.key_pose7[r] for r in refs])
             pose_cur = self.key_pose7[fid]
-            out = None
+            prep, out = api.Context.prepare_window(refs, pose_refs, pose_cur, self.ext7)
             # first solve: n_eval[0] LM iterations' worth of evaluations
             for _ in range(self.n_eval[0]):
-                out = ctx.window_eval(refs, pose_refs, pose_cur, self.ext7, fr["td"], self.flags, out)
+                ctx.window_eval_prepared(prep, fr["td"], self.flags, out)
             self.last["chi2"] = ctx.window_chi2(refs, pose_refs, pose_cur, self.ext7, fr["td"])
             for _ in range(self.n_eval[1]):
-                out = ctx.window_eval(refs, pose_refs, pose_cur, self.ext7, fr["td"], self.flags, out)
+                ctx.window_eval_prepared(prep, fr["td"], self.flags, out)
             self.last["eval"] = out
             # updateParametersFromOptimizer: re-project every keyframe (optimizer.cc:203-218)
             poses = (api.Pose * len(ids))(*[self.key_pose[k] for k in ids])
