@@ -341,14 +341,15 @@ int frame_tail(fflins_ctx *ctx, Frame *f, int n, int ndec, fflins_frame_info *ou
     int *d_ndown = ctx->d_counters + 1;
     launch_voxel_downsample(s, ctx->vox, f->c[FFLINS_CLOUD_LIDAR_FULL].d, ndec, (float) ctx->cfg.downsample_size,
                             f->c[FFLINS_CLOUD_LIDAR].d, d_ndown, nullptr, &ctx->launches, ctx->prof(), "voxel_frame");
-    {
-        ProfScope ps(ctx->prof(), "project_world", s);
-        launch_project(s, to12(f->pose), f->c[FFLINS_CLOUD_LIDAR].d, f->c[FFLINS_CLOUD_WORLD].d, ndec, d_ndown);
-        ctx->launches++;
-    }
     unsigned char *h = pin(ctx, 256);
     if (!h) return fail(ctx, FFLINS_E_NOMEM, "pinned allocation failed");
-    CK(cudaMemcpyAsync(h, ctx->d_counters, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    {
+        // the last kernel of the chain stores the two counts straight into pinned host memory
+        ProfScope ps(ctx->prof(), "project_world", s);
+        launch_project(s, to12(f->pose), f->c[FFLINS_CLOUD_LIDAR].d, f->c[FFLINS_CLOUD_WORLD].d, ndec, d_ndown, (int *) h,
+                       ctx->d_counters);
+        ctx->launches++;
+    }
     CK(cudaStreamSynchronize(s));
     int cnt[2];
     std::memcpy(cnt, h, sizeof(cnt));
@@ -1390,14 +1391,15 @@ int fflins_window_eval(fflins_ctx *ctx, int32_t n_pairs, const uint64_t *ref_ids
         return FFLINS_OK;
     }
     cudaStream_t s = ctx->stream;
-    {
-        ProfScope ps(ctx->prof(), "factor_eval", s);
-        launch_factor_eval(s, P, (const float *) cur->c[FFLINS_CLOUD_LIDAR].d, 1, nullptr, nullptr, nullptr, ctx->d_red);
-        ctx->launches++;
-    }
     unsigned char *h = pin(ctx, (size_t) n_pairs * kRedSize * 8);
     if (!h) return fail(ctx, FFLINS_E_NOMEM, "pinned allocation failed");
-    CK(cudaMemcpyAsync(h, ctx->d_red, (size_t) n_pairs * kRedSize * 8, cudaMemcpyDeviceToHost, s));
+    {
+        // the reduced blocks are stored by the kernel straight into pinned host memory (zero-copy):
+        // no device-to-host memcpy between the launch and the synchronisation
+        ProfScope ps(ctx->prof(), "factor_eval", s);
+        launch_factor_eval(s, P, (const float *) cur->c[FFLINS_CLOUD_LIDAR].d, 1, nullptr, nullptr, nullptr, (double *) h);
+        ctx->launches++;
+    }
     CK(cudaStreamSynchronize(s));
     const double *red = (const double *) h;
     for (int i = 0; i < n_pairs; i++)

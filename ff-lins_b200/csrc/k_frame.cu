@@ -85,8 +85,13 @@ __global__ void copy_decimate_kernel(const float4 *__restrict__ in, int n, int f
 }
 
 __global__ void __launch_bounds__(256)
-project_kernel(Pose12 T, const float4 *__restrict__ src, float4 *__restrict__ dst, int n, const int *__restrict__ n_dev) {
+project_kernel(Pose12 T, const float4 *__restrict__ src, float4 *__restrict__ dst, int n, const int *__restrict__ n_dev,
+               int *__restrict__ report, const int *__restrict__ counters) {
     if (n_dev) n = min(n, *n_dev);
+    if (report && blockIdx.x == 0 && threadIdx.x == 0) { // zero-copy result read-back (pinned host memory)
+        report[0] = counters ? counters[0] : 0;
+        report[1] = n;
+    }
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
         dst[k] = project_rn(T.R, T.t, src[k]);
 }
@@ -142,9 +147,10 @@ void launch_copy_decimate(cudaStream_t s, const float4 *xyzi, int n, int filter_
     copy_decimate_kernel<<<grid_for(n, 256), 256, 0, s>>>(xyzi, n, filter_num, out_full, out_dec);
 }
 
-void launch_project(cudaStream_t s, Pose12 T, const float4 *src, float4 *dst, int n, const int *n_dev) {
-    if (n <= 0) return;
-    project_kernel<<<grid_for(n, 256), 256, 0, s>>>(T, src, dst, n, n_dev);
+void launch_project(cudaStream_t s, Pose12 T, const float4 *src, float4 *dst, int n, const int *n_dev, int *report,
+                    const int *counters) {
+    if (n <= 0 && !report) return;
+    project_kernel<<<grid_for(n, 256), 256, 0, s>>>(T, src, dst, n, n_dev, report, counters);
 }
 
 void launch_project_batch(cudaStream_t s, const ProjectBatch &b) {
