@@ -100,10 +100,14 @@ __host__ __device__ __forceinline__ void interp_pose(const double *__restrict__ 
 // With exp(-sK) = I - s a(x) K + s^2 b(x) K^2, x = s theta, a = sin(x)/x, b = (1 - cos x)/x^2:
 //   R01 = G0 - (s a) G1 + (s^2 b) G2,     t01 = c0 + s c1 - (s a) c2 + (s^2 b) c3,
 // where G0 = A R_bl, G1 = A K R_bl, G2 = A K^2 R_bl, A = R0f^T R(q0), c0 = R0f^T (p0 - t0f) + A t_bl,
-// c1 = R0f^T dp, c2 = A K t_bl, c3 = A K^2 t_bl depend only on the interval. A row holds these 39
-// doubles plus t0, 1/(t1 - t0) and theta^2 (kRowSize = 42). Row 0 is the out-of-window fallback
-// (misc.cc:76-79): the constant pose of window.back().
-constexpr int kRowSize = 42;
+// c1 = R0f^T dp, c2 = A K t_bl, c3 = A K^2 t_bl depend only on the interval, so the undistorted point is
+//   out = (G0 p + c0) - (s a)(G1 p + c2) + (s^2 b)(G2 p + c3) + s c1.
+// Row layout (kRowSize = 44 doubles, 16-byte groups for 128-bit loads):
+//   [0] t0  [1] 1/(t1-t0)  [2] theta^2  [3] pad
+//   [4+4i ..]  G0 row i, c0[i]     [16+4i ..] G1 row i, c2[i]     [28+4i ..] G2 row i, c3[i]   (i = 0..2)
+//   [40..42] c1   [43] pad
+// Row 0 is the out-of-window fallback (misc.cc:76-79): the constant pose of window.back().
+constexpr int kRowSize = 44;
 
 __host__ __device__ inline void interval_row(const double *__restrict__ ins_t, const double *__restrict__ ins_p,
                                              const double *__restrict__ ins_q, int w, int i, const Pose12 &ext,
@@ -123,10 +127,11 @@ __host__ __device__ inline void interval_row(const double *__restrict__ ins_t, c
     M3 A     = mulTN(R0f, quat_to_R(q0));
     M3 G0    = mul(A, Rbl);
     V3 c0    = mulT(R0f, p0 - t0f) + mul(A, tbl);
-    for (int k = 0; k < 9; k++) row[k] = G0.m[k];
-    row[27] = c0.x;
-    row[28] = c0.y;
-    row[29] = c0.z;
+    const double c0v[3] = {c0.x, c0.y, c0.z};
+    for (int r = 0; r < 3; r++) {
+        for (int c = 0; c < 3; c++) row[4 + 4 * r + c] = G0.m[3 * r + c];
+        row[4 + 4 * r + 3] = c0v[r];
+    }
     if (i == 0) return; // constant pose: G1 = G2 = c1..c3 = 0, s = 0
     V3 dp   = ld3(ins_p + 3 * i) - p0;
     Q4 dq   = qmul(qinv(ldq(ins_q + 4 * i)), ldq(ins_q + 4 * (i - 1)));
@@ -136,16 +141,21 @@ __host__ __device__ inline void interval_row(const double *__restrict__ ins_t, c
     M3 AKK  = mul(AK, K);
     M3 G1   = mul(AK, Rbl), G2 = mul(AKK, Rbl);
     V3 c1   = mulT(R0f, dp), c2 = mul(AK, tbl), c3 = mul(AKK, tbl);
-    for (int k = 0; k < 9; k++) {
-        row[9 + k]  = G1.m[k];
-        row[18 + k] = G2.m[k];
+    const double c2v[3] = {c2.x, c2.y, c2.z}, c3v[3] = {c3.x, c3.y, c3.z};
+    for (int r = 0; r < 3; r++) {
+        for (int c = 0; c < 3; c++) {
+            row[16 + 4 * r + c] = G1.m[3 * r + c];
+            row[28 + 4 * r + c] = G2.m[3 * r + c];
+        }
+        row[16 + 4 * r + 3] = c2v[r];
+        row[28 + 4 * r + 3] = c3v[r];
     }
-    row[30] = c1.x; row[31] = c1.y; row[32] = c1.z;
-    row[33] = c2.x; row[34] = c2.y; row[35] = c2.z;
-    row[36] = c3.x; row[37] = c3.y; row[38] = c3.z;
-    row[39] = ins_t[i - 1];
-    row[40] = 1.0 / (ins_t[i] - ins_t[i - 1]);
-    row[41] = rv.x * rv.x + rv.y * rv.y + rv.z * rv.z;
+    row[40] = c1.x;
+    row[41] = c1.y;
+    row[42] = c1.z;
+    row[0]  = ins_t[i - 1];
+    row[1]  = 1.0 / (ins_t[i] - ins_t[i - 1]);
+    row[2]  = rv.x * rv.x + rv.y * rv.y + rv.z * rv.z;
 }
 
 // sin(x)/x and (1 - cos x)/x^2 from x^2
@@ -163,16 +173,28 @@ __host__ __device__ __forceinline__ void sinc_cosc(double x2, double &a, double 
     }
 }
 
-// relative pose (R01, t01) of a point time from its interval row
-__host__ __device__ __forceinline__ void row_pose(const double *__restrict__ row, double time, double R01[9], double t01[3]) {
-    double s  = (time - row[39]) * row[40];
+// interpolation weights (s, s a, s^2 b) of a point time
+__host__ __device__ __forceinline__ void row_weights(const double *__restrict__ row, double time, double &s, double &sa,
+                                                     double &sb) {
+    s = (time - row[0]) * row[1];
     double a, b;
-    sinc_cosc(s * s * row[41], a, b);
-    double sa = s * a, sb = s * s * b;
+    sinc_cosc(s * s * row[2], a, b);
+    sa = s * a;
+    sb = s * s * b;
+}
+
+// undistorted coordinates (fp64) of point (px, py, pz) taken at `time`, from its interval row
+__host__ __device__ __forceinline__ void row_apply(const double *__restrict__ row, double time, double px, double py,
+                                                   double pz, double out[3]) {
+    double s, sa, sb;
+    row_weights(row, time, s, sa, sb);
 #pragma unroll
-    for (int k = 0; k < 9; k++) R01[k] = row[k] - sa * row[9 + k] + sb * row[18 + k];
-#pragma unroll
-    for (int k = 0; k < 3; k++) t01[k] = row[27 + k] + s * row[30 + k] - sa * row[33 + k] + sb * row[36 + k];
+    for (int i = 0; i < 3; i++) {
+        double A0 = row[4 + 4 * i] * px + row[5 + 4 * i] * py + row[6 + 4 * i] * pz + row[7 + 4 * i];
+        double A1 = row[16 + 4 * i] * px + row[17 + 4 * i] * py + row[18 + 4 * i] * pz + row[19 + 4 * i];
+        double A2 = row[28 + 4 * i] * px + row[29 + 4 * i] * py + row[30 + 4 * i] * pz + row[31 + 4 * i];
+        out[i]    = A0 - sa * A1 + sb * A2 + s * row[40 + i];
+    }
 }
 
 // MISC::getPoseFromInsWindow (misc.cc:64-80) for ONE time, written out in full (used on the host for the

@@ -164,11 +164,13 @@ int main() {
             double R1[9], t1[3], R01o[9], t01o[3];
             orc_pose_from_ins_window(t.data(), p.data(), q.data(), W, ext.R, ext.t, time, R1, t1);
             orc_relative_pose(Rf, tf, R1, t1, R01o, t01o);
-            double R01[9], t01[3];
-            row_pose(&rows[(size_t) i1 * kRowSize], time, R01, t01);
-            // absolute error scaled by the magnitudes that matter for an fp32 output (|R| <= 1, |t| ~ metres)
-            for (int k = 0; k < 9; k++) worst = std::fmax(worst, std::fabs(R01[k] - R01o[k]));
-            for (int k = 0; k < 3; k++) worst = std::fmax(worst, std::fabs(t01[k] - t01o[k]));
+            // a point ~60 m away: the error is reported relative to the point's magnitude
+            double px = 40.0 * U(rng), py = 40.0 * U(rng), pz = 8.0 * U(rng), out[3];
+            row_apply(&rows[(size_t) i1 * kRowSize], time, px, py, pz, out);
+            for (int k = 0; k < 3; k++) {
+                double ref = R01o[3 * k] * px + R01o[3 * k + 1] * py + R01o[3 * k + 2] * pz + t01o[k];
+                worst = std::fmax(worst, std::fabs(out[k] - ref) / 60.0);
+            }
         }
         printf("frame_pose_bit_mismatch %d\n", frame_pose_bits);
         printf("undistort_pose_rel %.3e\nwindow_index_mismatch %d\n", worst, idx_mismatch);
