@@ -133,13 +133,14 @@ def run_ours(args, rank, world, local_rank):
     from fflins import api
     from fflins.pipeline import Session
 
+    # synthesise the frames first: the worker pool forks, which must happen before CUDA / NCCL start
+    seq, frames = make_sequence(args.config, args.frames)
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    seq, frames = make_sequence(args.config, args.frames)
     P = len(frames)
     n, w = seq.n, seq.W
     cfg = fflins.default_config(point_filter_num=seq.filter_num, max_points_per_frame=max(n, 262144))
