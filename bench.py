@@ -160,7 +160,7 @@ def run_ours(args, rank, world, local_rank):
     input_bytes = P * (n * 24 + w * 64)
 
     trace = {} if os.environ.get("FFLINS_TRACE") else None
-    sess = Session(ctx, seq, FRAMES_PER_KEY, N_EVAL, trace=trace)
+    sess = Session(ctx, seq, FRAMES_PER_KEY, N_EVAL, trace=trace, sync_frames=False)
     state = {"frame": 0}
 
     def step(mode):

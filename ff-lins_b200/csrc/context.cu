@@ -33,6 +33,7 @@ struct Frame {
     double v[3] = {0, 0, 0}, w[3] = {0, 0, 0}, td = 0;
     int n_raw = 0, n_fallback = 0;
     bool is_key = false;
+    int pending_slot = -1; // >= 0: counts of the last frame_process still sit in pinned slot (asynchronous mode)
     // keyframe hash (K4)
     unsigned long long *hkeys = nullptr, *ckeys = nullptr, *cmask = nullptr;
     int *hvals                = nullptr;
@@ -111,6 +112,15 @@ struct fflins_ctx : public Profiler {
     // pinned host scratch
     unsigned char *h_pin = nullptr;
     size_t h_pin_cap = 0;
+    // asynchronous frames: per-frame count slots (pinned, written by the last kernel of the frame chain)
+    int *h_slots = nullptr;       // kSlots x 2 ints
+    int next_slot = 0;
+    std::vector<uint64_t> pending; // frame ids whose counts are not read back yet
+    // ring of pinned INS-window staging areas (the CPU packs window k+1 while copy k may still be queued)
+    unsigned char *h_win = nullptr;
+    size_t h_win_slot = 0;
+    int win_next = 0;
+    cudaEvent_t win_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
     // profiler
     bool prof_on = false;
@@ -172,6 +182,9 @@ struct fflins_ctx : public Profiler {
 
 namespace {
 
+constexpr int kSlots = 64;
+constexpr int kWinRing = 8;
+
 #define CK(call)                                                                                         \
     do {                                                                                                 \
         cudaError_t e_ = (call);                                                                         \
@@ -224,6 +237,23 @@ Frame *get_frame(fflins_ctx *ctx, uint64_t id) {
         ctx->frames[id] = f;
     }
     return f;
+}
+
+// Read back the counts of every frame processed asynchronously (one synchronisation for all of them).
+int resolve_pending(fflins_ctx *ctx) {
+    if (ctx->pending.empty()) return FFLINS_OK;
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (uint64_t id : ctx->pending) {
+        Frame *f = find_frame(ctx, id);
+        if (!f || f->pending_slot < 0) continue;
+        const int *cnt                 = ctx->h_slots + 2 * f->pending_slot;
+        f->n_fallback                  = cnt[0];
+        f->c[FFLINS_CLOUD_LIDAR].n     = cnt[1];
+        f->c[FFLINS_CLOUD_WORLD].n     = cnt[1];
+        f->pending_slot                = -1;
+    }
+    ctx->pending.clear();
+    return FFLINS_OK;
 }
 
 int ensure_cloud(fflins_ctx *ctx, Cloud &c, int n, bool keep = false) {
@@ -341,25 +371,28 @@ int frame_tail(fflins_ctx *ctx, Frame *f, int n, int ndec, fflins_frame_info *ou
     int *d_ndown = ctx->d_counters + 1;
     launch_voxel_downsample(s, ctx->vox, f->c[FFLINS_CLOUD_LIDAR_FULL].d, ndec, (float) ctx->cfg.downsample_size,
                             f->c[FFLINS_CLOUD_LIDAR].d, d_ndown, nullptr, &ctx->launches, ctx->prof(), "voxel_frame");
-    unsigned char *h = pin(ctx, 256);
-    if (!h) return fail(ctx, FFLINS_E_NOMEM, "pinned allocation failed");
+    // the last kernel of the chain stores the two counts straight into a pinned host slot
+    if ((int) ctx->pending.size() >= kSlots - 1 && (rc = resolve_pending(ctx))) return rc;
+    const int slot = ctx->next_slot;
+    ctx->next_slot = (ctx->next_slot + 1) % kSlots;
+    int *h         = ctx->h_slots + 2 * slot;
     {
-        // the last kernel of the chain stores the two counts straight into pinned host memory
         ProfScope ps(ctx->prof(), "project_world", s);
-        launch_project(s, to12(f->pose), f->c[FFLINS_CLOUD_LIDAR].d, f->c[FFLINS_CLOUD_WORLD].d, ndec, d_ndown, (int *) h,
+        launch_project(s, to12(f->pose), f->c[FFLINS_CLOUD_LIDAR].d, f->c[FFLINS_CLOUD_WORLD].d, ndec, d_ndown, h,
                        ctx->d_counters);
         ctx->launches++;
     }
-    CK(cudaStreamSynchronize(s));
-    int cnt[2];
-    std::memcpy(cnt, h, sizeof(cnt));
     f->n_raw                        = n;
-    f->n_fallback                   = cnt[0];
+    f->n_fallback                   = 0;
     f->c[FFLINS_CLOUD_MAP_FULL].n   = n;
     f->c[FFLINS_CLOUD_LIDAR_FULL].n = ndec;
-    f->c[FFLINS_CLOUD_LIDAR].n      = cnt[1];
-    f->c[FFLINS_CLOUD_WORLD].n      = cnt[1];
+    f->c[FFLINS_CLOUD_LIDAR].n      = 0;
+    f->c[FFLINS_CLOUD_WORLD].n      = 0;
     f->c[FFLINS_CLOUD_MAP].n        = 0;
+    f->pending_slot                 = slot;
+    ctx->pending.push_back(f->id);
+    if (!out) return FFLINS_OK; // asynchronous mode: counts are read back by the next call that needs them
+    if ((rc = resolve_pending(ctx))) return rc;
     fill_info(f, out);
     return FFLINS_OK;
 }
@@ -370,18 +403,32 @@ int check_window(fflins_ctx *ctx, const double *ins_t, int w) {
     return FFLINS_OK;
 }
 
-// one H2D copy per frame: t | p | q packed into the pinned staging area first (64 B per entry)
+// one H2D copy per frame: t | p | q packed into a pinned staging slot first (64 B per entry). The slots
+// form a ring guarded by events so that packing window k+1 never overwrites a copy that is still queued.
 int upload_ins(fflins_ctx *ctx, const double *ins_t, const double *ins_p, const double *ins_q, int w) {
     int rc;
     if ((rc = ensure_ins(ctx, w))) return rc;
-    const size_t off = 65536;
-    unsigned char *h = pin(ctx, off + (size_t) w * 64);
-    if (!h) return fail(ctx, FFLINS_E_NOMEM, "pinned allocation failed");
-    double *hp = (double *) (h + off);
+    const size_t need = (size_t) w * 64;
+    if (need > ctx->h_win_slot) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->h_win) cudaFreeHost(ctx->h_win);
+        ctx->h_win_slot = std::max<size_t>(need, 4096 * 64);
+        if (cudaMallocHost((void **) &ctx->h_win, ctx->h_win_slot * kWinRing) != cudaSuccess) {
+            ctx->h_win      = nullptr;
+            ctx->h_win_slot = 0;
+            return fail(ctx, FFLINS_E_NOMEM, "pinned allocation failed");
+        }
+    }
+    const int k = ctx->win_next;
+    ctx->win_next = (k + 1) % kWinRing;
+    if (!ctx->win_ev[k]) CK(cudaEventCreateWithFlags(&ctx->win_ev[k], cudaEventDisableTiming));
+    else CK(cudaEventSynchronize(ctx->win_ev[k]));
+    double *hp = (double *) (ctx->h_win + (size_t) k * ctx->h_win_slot);
     std::memcpy(hp, ins_t, (size_t) w * 8);
     std::memcpy(hp + w, ins_p, (size_t) w * 24);
     std::memcpy(hp + 4 * (size_t) w, ins_q, (size_t) w * 32);
-    CK(cudaMemcpyAsync(ctx->d_ins, hp, (size_t) w * 64, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_ins, hp, need, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaEventRecord(ctx->win_ev[k], ctx->stream));
     return FFLINS_OK;
 }
 
@@ -506,6 +553,10 @@ Pose12 ref_world(const fflins_pose &pose) {
 
 int run_associate(fflins_ctx *ctx, const std::vector<Frame *> &refs, Frame *cur, int32_t *nf, int32_t *nc) {
     cudaStream_t s = ctx->stream;
+    {
+        int rcp = resolve_pending(ctx);
+        if (rcp) return rcp;
+    }
     const int q    = cur->c[FFLINS_CLOUD_LIDAR].n;
     AssocParams P{};
     fill_assoc_common(ctx, P);
@@ -572,6 +623,10 @@ void unpack_red(const double *red, double *H, double *b, double *cost, int32_t *
 int fill_factor_pairs(fflins_ctx *ctx, FactorParams &P, int n_pairs, const uint64_t *ref_ids, const double *pose_refs,
                       Frame *cur, const double *pose_cur, const double *ext, double td, uint32_t flags) {
     REQUIRE(n_pairs >= 0 && n_pairs <= kMaxRefs, "too many pairs");
+    {
+        int rcp = resolve_pending(ctx);
+        if (rcp) return rcp;
+    }
     P.n_pairs = n_pairs;
     P.q       = cur->c[FFLINS_CLOUD_LIDAR].n;
     P.flags   = flags;
@@ -663,6 +718,11 @@ int fflins_create(const fflins_config *cfg, int device, fflins_ctx **out) {
         fflins_destroy(ctx);
         return FFLINS_E_NOMEM;
     }
+    if (cudaMallocHost((void **) &ctx->h_slots, kSlots * 2 * sizeof(int)) != cudaSuccess) {
+        ctx->h_slots = nullptr;
+        fflins_destroy(ctx);
+        return FFLINS_E_NOMEM;
+    }
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
         fflins_destroy(ctx);
         return FFLINS_E_CUDA;
@@ -682,6 +742,10 @@ void fflins_destroy(fflins_ctx *ctx) {
     ctx->frames.clear();
     ctx->pool.destroy();
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+    if (ctx->h_slots) cudaFreeHost(ctx->h_slots);
+    if (ctx->h_win) cudaFreeHost(ctx->h_win);
+    for (auto e : ctx->win_ev)
+        if (e) cudaEventDestroy(e);
     for (auto &r : ctx->prof_open) {
         cudaEventDestroy(r.a);
         cudaEventDestroy(r.b);
@@ -698,7 +762,7 @@ const char *fflins_last_error(const fflins_ctx *ctx) { return ctx ? ctx->err.c_s
 int fflins_synchronize(fflins_ctx *ctx) {
     if (!ctx) return FFLINS_E_INVALID;
     CK(cudaStreamSynchronize(ctx->stream));
-    return FFLINS_OK;
+    return resolve_pending(ctx);
 }
 
 int fflins_host_register(void *ptr, uint64_t bytes) {
@@ -789,6 +853,10 @@ int fflins_frame_process_static(fflins_ctx *ctx, uint64_t frame_id, const float 
 
 int fflins_frame_info_get(fflins_ctx *ctx, uint64_t frame_id, fflins_frame_info *out) {
     if (!ctx || !out) return FFLINS_E_INVALID;
+    {
+        int rcp = resolve_pending(ctx);
+        if (rcp) return rcp;
+    }
     Frame *f = find_frame(ctx, frame_id);
     if (!f) return fail(ctx, FFLINS_E_NOTFOUND, "unknown frame");
     fill_info(f, out);
@@ -798,6 +866,10 @@ int fflins_frame_info_get(fflins_ctx *ctx, uint64_t frame_id, fflins_frame_info 
 int fflins_frame_download(fflins_ctx *ctx, uint64_t frame_id, int which, float *xyzi, int32_t cap, int32_t *n) {
     if (!ctx) return FFLINS_E_INVALID;
     REQUIRE(which >= 0 && which < 5, "bad cloud selector");
+    {
+        int rcp = resolve_pending(ctx);
+        if (rcp) return rcp;
+    }
     Frame *f = find_frame(ctx, frame_id);
     if (!f) return fail(ctx, FFLINS_E_NOTFOUND, "unknown frame");
     const Cloud &c = f->c[which];
@@ -814,6 +886,10 @@ int fflins_frame_download(fflins_ctx *ctx, uint64_t frame_id, int which, float *
 int fflins_frame_upload(fflins_ctx *ctx, uint64_t frame_id, int which, const float *xyzi, int32_t n) {
     if (!ctx) return FFLINS_E_INVALID;
     REQUIRE(which >= 0 && which < 5 && n >= 0 && (n == 0 || xyzi), "bad argument");
+    {
+        int rcp = resolve_pending(ctx);
+        if (rcp) return rcp;
+    }
     Frame *f = get_frame(ctx, frame_id);
     int rc;
     if ((rc = ensure_cloud(ctx, f->c[which], n))) return rc;
@@ -856,7 +932,7 @@ int fflins_frame_release(fflins_ctx *ctx, uint64_t frame_id) {
     if (it == ctx->frames.end()) return fail(ctx, FFLINS_E_NOTFOUND, "unknown frame");
     for (auto k : ctx->keyframes)
         if (k == frame_id) return fail(ctx, FFLINS_E_INVALID, "frame is a keyframe: remove it from the window first");
-    CK(cudaStreamSynchronize(ctx->stream));
+    // no synchronisation: the blocks go back to the pool and any reuse is ordered on the context's stream
     free_frame(ctx, it->second);
     ctx->frames.erase(it);
     return FFLINS_OK;
@@ -864,6 +940,10 @@ int fflins_frame_release(fflins_ctx *ctx, uint64_t frame_id) {
 
 int fflins_reproject(fflins_ctx *ctx, uint64_t frame_id, const fflins_pose *pose) {
     if (!ctx || !pose) return FFLINS_E_INVALID;
+    {
+        int rcp = resolve_pending(ctx);
+        if (rcp) return rcp;
+    }
     Frame *f = find_frame(ctx, frame_id);
     if (!f) return fail(ctx, FFLINS_E_NOTFOUND, "unknown frame");
     f->pose = *pose;
@@ -882,6 +962,10 @@ int fflins_reproject(fflins_ctx *ctx, uint64_t frame_id, const fflins_pose *pose
 int fflins_reproject_window(fflins_ctx *ctx, int32_t n, const uint64_t *frame_ids, const fflins_pose *poses) {
     if (!ctx) return FFLINS_E_INVALID;
     REQUIRE(n >= 0 && n <= kMaxRefs && (n == 0 || (frame_ids && poses)), "bad argument");
+    {
+        int rcp = resolve_pending(ctx);
+        if (rcp) return rcp;
+    }
     ProjectBatch B{};
     B.count = n;
     int rc;
@@ -1116,6 +1200,7 @@ int fflins_keyframe_merge(fflins_ctx *ctx, uint64_t key_id, const uint64_t *nonk
     unsigned char *h = pin(ctx, 64);
     if (!h) return fail(ctx, FFLINS_E_NOMEM, "pinned allocation failed");
     CK(cudaMemcpyAsync(h, ctx->d_counters + 3, sizeof(int), cudaMemcpyDeviceToHost, s));
+    if ((rc = resolve_pending(ctx))) return rc; // frames processed asynchronously are complete now, too
     CK(cudaStreamSynchronize(s));
     int m;
     std::memcpy(&m, h, sizeof(int));
@@ -1146,7 +1231,6 @@ static int remove_key(fflins_ctx *ctx, bool oldest, uint64_t *removed_id) {
     if (removed_id) *removed_id = id;
     auto it = ctx->frames.find(id);
     if (it != ctx->frames.end()) {
-        CK(cudaStreamSynchronize(ctx->stream));
         free_frame(ctx, it->second);
         ctx->frames.erase(it);
     }

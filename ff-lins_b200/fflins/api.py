@@ -131,15 +131,16 @@ class Context:
             raise FflinsError(rc, self.L.fflins_last_error(self.h).decode())
 
     # ---- frames -----------------------------------------------------------------------------
-    def frame_process(self, fid, xyzi, time, ins_t, ins_p, ins_q, R_bl, t_bl, stamp, td):
+    def frame_process(self, fid, xyzi, time, ins_t, ins_p, ins_q, R_bl, t_bl, stamp, td, sync=True):
+        """sync=False: asynchronous mode (out = NULL), returns None; counts via frame_info() later."""
         xyzi = _c(xyzi, np.float32)
         time = _c(time, np.float64)
         ins_t, ins_p, ins_q = _c(ins_t, np.float64), _c(ins_p, np.float64), _c(ins_q, np.float64)
-        info = FrameInfo()
-        pose = Pose.make(R_bl, t_bl)
+        info = FrameInfo() if sync else None
+        pose = R_bl if isinstance(R_bl, Pose) else Pose.make(R_bl, t_bl)
         self._ck(self.L.fflins_frame_process(self.h, C.c_uint64(fid), _p(xyzi), _p(time), len(time), _p(ins_t),
                                              _p(ins_p), _p(ins_q), len(ins_t), C.byref(pose), C.c_double(stamp),
-                                             C.c_double(td), C.byref(info)))
+                                             C.c_double(td), C.byref(info) if sync else None))
         return info
 
     def frame_process_aos(self, fid, rec, ins_t, ins_p, ins_q, R_bl, t_bl, stamp, td):
@@ -152,12 +153,13 @@ class Context:
                                                  C.c_double(td), C.byref(info)))
         return info
 
-    def frame_process_dev(self, fid, d_xyzi, d_time, n, ins_t, ins_p, ins_q, pose_bl, stamp, td, info=None):
-        """d_xyzi / d_time are raw device addresses (ints); the INS window arrays are host numpy arrays."""
-        info = info or FrameInfo()
+    def frame_process_dev(self, fid, d_xyzi, d_time, n, ins_t, ins_p, ins_q, pose_bl, stamp, td, sync=True):
+        """d_xyzi / d_time are raw device addresses (ints); the INS window arrays are host numpy arrays.
+        sync=False: asynchronous mode (out = NULL), returns None."""
+        info = FrameInfo() if sync else None
         self._ck(self.L.fflins_frame_process_dev(self.h, C.c_uint64(fid), C.c_void_p(d_xyzi), C.c_void_p(d_time), n,
                                                  _p(ins_t), _p(ins_p), _p(ins_q), len(ins_t), C.byref(pose_bl),
-                                                 C.c_double(stamp), C.c_double(td), C.byref(info)))
+                                                 C.c_double(stamp), C.c_double(td), C.byref(info) if sync else None))
         return info
 
     def frame_process_static(self, fid, xyzi, p, q, R_bl, t_bl):

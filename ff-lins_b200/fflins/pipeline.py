@@ -38,17 +38,17 @@ class _Timed:
 
 
 class Session:
-    def __init__(self, ctx, seq, frames_per_key=5, n_eval=(5, 10), flags=api.HUBER, trace=None):
+    def __init__(self, ctx, seq, frames_per_key=5, n_eval=(5, 10), flags=api.HUBER, trace=None, sync_frames=True):
         self.ctx = ctx if trace is None else _Timed(ctx, trace)
         self.seq = seq
         self.K = frames_per_key
+        self.sync_frames = sync_frames   # False: frames are enqueued asynchronously (out = NULL)
         self.n_eval = n_eval
         self.flags = flags
         self.nonkeys = []
         self.key_stamps = {}
         self.key_pose7 = {}
         self.key_pose = {}
-        self.last_info = {}
         self.next_id = 0
         self.window = ctx.cfg.window_size
         self.pose_bl = api.Pose.make(seq.R_bl, seq.t_bl)
@@ -60,8 +60,7 @@ class Session:
         fid = self.next_id
         self.next_id += 1
         info = self.ctx.frame_process(fid, fr["xyzi"], fr["time"], fr["ins_t"], fr["ins_p"], fr["ins_q"],
-                                      self.seq.R_bl, self.seq.t_bl, fr["stamp"], fr["td"])
-        self.last_info = {fid: info}
+                                      self.pose_bl, None, fr["stamp"], fr["td"], sync=self.sync_frames)
         return fid, info
 
     def process_frame_dev(self, fr_dev):
@@ -70,8 +69,7 @@ class Session:
         self.next_id += 1
         info = self.ctx.frame_process_dev(fid, fr_dev["xyzi"], fr_dev["time"], fr_dev["n"], fr_dev["ins_t"],
                                           fr_dev["ins_p"], fr_dev["ins_q"], self.pose_bl, fr_dev["stamp"],
-                                          fr_dev["td"])
-        self.last_info = {fid: info}
+                                          fr_dev["td"], sync=self.sync_frames)
         return fid, info
 
     def after_frame(self, fid, fr, force_key=None):
@@ -89,7 +87,7 @@ class Session:
         ctx.set_motion(fid, fr["v"], fr["omega"], fr["td"])
         self.key_stamps[fid] = fr["stamp"]
         self.key_pose7[fid] = fr["pose7"] if "pose7" in fr else self.seq.imu_pose7(fr["stamp"])
-        self.key_pose[fid] = self.last_info[fid].pose
+        self.key_pose[fid] = ctx.get_pose_struct(fid)   # host-evaluated, available without a sync
         ids = ctx.keyframe_ids()
         if len(ids) >= 2:
             self.last["assoc"] = ctx.associate()

@@ -116,7 +116,12 @@ int         fflins_host_register(void *ptr, uint64_t bytes);
 int         fflins_host_unregister(void *ptr);
 
 /* ---- per frame: LidarMap::lidarFrameProcessing (lidar_map.cc:213-273) ------------------ */
-/* SoA input. ins_* is the INS window (deque<pair<IMU,IntegrationState>>): strictly
+/* `out` may be NULL = ASYNCHRONOUS mode: the call only enqueues the frame's work on the context's stream
+ * and returns; the counts are read back by the next call that needs them (fflins_frame_info_get,
+ * fflins_keyframe_merge, fflins_associate, downloads, fflins_synchronize, ...). The frame pose is always
+ * available at once (fflins_frame_get_pose): it is evaluated on the host. In asynchronous mode page-locked
+ * input buffers must stay untouched until such a call returns (pageable buffers are staged by CUDA).
+ * SoA input. ins_* is the INS window (deque<pair<IMU,IntegrationState>>): strictly
  * increasing times, positions, quaternions; 2 <= w <= 65536 (misc.cc:27-62). stamp is
  * frame->stamp() (= end time + td, ff_lins.cc:352-353), td is frame->timeDelay(). */
 int fflins_frame_process(fflins_ctx *ctx, uint64_t frame_id, const float *xyzi, const double *time, int32_t n,

@@ -635,3 +635,36 @@ def test_end_to_end_vs_cpu_pipeline(oracle):
     print(f"end-to-end flips: voxel-count {flips_q}, feature-type {flips_type}")
     assert flips_q <= 2 and flips_type <= 5
     c.close()
+
+
+def test_async_frames_match_sync(robot):
+    """out = NULL (asynchronous) frame processing: counts are read back lazily and every cloud is
+    bit-identical to the synchronous call; the frame pose is available immediately."""
+    from fflins import api
+    c = api.Context(api.default_config(point_filter_num=robot.filter_num))
+    frames = [robot.frame(i) for i in range(6)]
+    sync_infos = []
+    for i, fr in enumerate(frames):
+        sync_infos.append(c.frame_process(100 + i, fr["xyzi"], fr["time"], fr["ins_t"], fr["ins_p"], fr["ins_q"], robot.R_bl,
+                                          robot.t_bl, fr["stamp"], fr["td"]))
+    for i, fr in enumerate(frames):
+        r = c.frame_process(200 + i, fr["xyzi"], fr["time"], fr["ins_t"], fr["ins_p"], fr["ins_q"], robot.R_bl, robot.t_bl,
+                            fr["stamp"], fr["td"], sync=False)
+        assert r is None
+        R, t = c.get_pose(200 + i)                      # no synchronisation needed for the pose
+        Rs, ts = sync_infos[i].pose.numpy()
+        assert bits_equal(R, Rs) and bits_equal(t, ts)
+    for i in range(6):
+        info = c.frame_info(200 + i)
+        assert (info.n_down, info.n_dec, info.n_fallback) == (sync_infos[i].n_down, sync_infos[i].n_dec, 0)
+        for which in (api.CLOUD_LIDAR_FULL, api.CLOUD_LIDAR, api.CLOUD_WORLD, api.CLOUD_MAP_FULL):
+            assert bits_equal(c.download(200 + i, which), c.download(100 + i, which))
+    # merge straight after asynchronous frames (the keyframe path of the benchmark)
+    for i, fr in enumerate(frames[:3]):
+        c.frame_process(300 + i, fr["xyzi"], fr["time"], fr["ins_t"], fr["ins_p"], fr["ins_q"], robot.R_bl, robot.t_bl,
+                        fr["stamp"], fr["td"], sync=False)
+    a = c.keyframe_merge(302, [300, 301])
+    b = c.keyframe_merge(102, [100, 101])
+    assert a.n_map == b.n_map and a.n_down == sync_infos[2].n_down
+    assert bits_equal(c.download(302, api.CLOUD_MAP), c.download(102, api.CLOUD_MAP))
+    c.close()
