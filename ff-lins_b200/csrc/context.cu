@@ -97,8 +97,13 @@ struct fflins_ctx : public Profiler {
     float cell_scale = 1.0f;
 
     // staging (device)
-    void *d_stage = nullptr;
+    // raw-input staging: a ring of device buffers filled by a dedicated copy stream, so that the H2D copy
+    // of frame k+1 overlaps the kernels of frame k (asynchronous mode)
+    void *d_stage = nullptr;      // kStageRing x stage_cap bytes
     size_t stage_cap = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t stage_copied[3] = {nullptr, nullptr, nullptr}, stage_consumed[3] = {nullptr, nullptr, nullptr};
+    int stage_next = 0, stage_cur = -1;
     double *d_ins = nullptr; // t[w] p[3w] q[4w]
     int ins_cap = 0;
     double *d_tab = nullptr;
@@ -288,15 +293,47 @@ void free_frame(fflins_ctx *ctx, Frame *f) {
     delete f;
 }
 
+constexpr int kStageRing = 3;
+
 int ensure_stage(fflins_ctx *ctx, size_t bytes) {
     if (bytes <= ctx->stage_cap) return FFLINS_OK;
+    if (ctx->d_stage) {
+        CK(cudaStreamSynchronize(ctx->copy_stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
     ctx->pool.release(ctx->d_stage);
-    ctx->d_stage = ctx->pool.alloc(bytes);
+    size_t cap   = Pool::round(bytes);
+    ctx->d_stage = ctx->pool.alloc(cap * kStageRing);
     if (!ctx->d_stage) {
         ctx->stage_cap = 0;
         return fail(ctx, FFLINS_E_NOMEM, "device allocation failed");
     }
-    ctx->stage_cap = Pool::round(bytes);
+    ctx->stage_cap = cap;
+    return FFLINS_OK;
+}
+
+// Next slot of the staging ring: the copy stream first waits until the kernels that read the slot's
+// previous content are done. Returns the device pointer; finish with stage_publish().
+int stage_acquire(fflins_ctx *ctx, size_t bytes, char **ptr) {
+    int rc;
+    if ((rc = ensure_stage(ctx, bytes))) return rc;
+    const int k     = ctx->stage_next;
+    ctx->stage_next = (k + 1) % kStageRing;
+    ctx->stage_cur  = k;
+    if (!ctx->stage_copied[k]) {
+        CK(cudaEventCreateWithFlags(&ctx->stage_copied[k], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->stage_consumed[k], cudaEventDisableTiming));
+    } else {
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->stage_consumed[k], 0));
+    }
+    *ptr = (char *) ctx->d_stage + (size_t) k * ctx->stage_cap;
+    return FFLINS_OK;
+}
+// the compute stream may read the slot once the copies are done
+int stage_publish(fflins_ctx *ctx) {
+    const int k = ctx->stage_cur;
+    CK(cudaEventRecord(ctx->stage_copied[k], ctx->copy_stream));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->stage_copied[k], 0));
     return FFLINS_OK;
 }
 
@@ -463,6 +500,10 @@ int process_core(fflins_ctx *ctx, uint64_t id, const float4 *d_xyzi, const doubl
         launch_undistort(s, d_xyzi, d_time, d_aos, n, d_ins_t, w, ctx->d_tab, td, F, f->c[FFLINS_CLOUD_MAP_FULL].d,
                          f->c[FFLINS_CLOUD_LIDAR_FULL].d, ctx->d_counters);
         if (n > 0) ctx->launches++;
+    }
+    if (ctx->stage_cur >= 0) { // the raw input of this frame has been consumed: its staging slot may be refilled
+        CK(cudaEventRecord(ctx->stage_consumed[ctx->stage_cur], s));
+        ctx->stage_cur = -1;
     }
     f->td = td;
     return frame_tail(ctx, f, n, ndec, out);
@@ -699,7 +740,8 @@ int fflins_create(const fflins_config *cfg, int device, fflins_ctx **out) {
         float v = (float) atof(e);
         if (v >= 0.5f && v <= 8.f) ctx->cell_scale = v;
     }
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete ctx;
         return FFLINS_E_CUDA;
     }
@@ -734,6 +776,7 @@ int fflins_create(const fflins_config *cfg, int device, fflins_ctx **out) {
 void fflins_destroy(fflins_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (auto &kv : ctx->frames) {
         Frame *f = kv.second;
@@ -753,6 +796,11 @@ void fflins_destroy(fflins_ctx *ctx) {
     for (auto e : ctx->ev_free) cudaEventDestroy(e);
     if (ctx->timer_a) cudaEventDestroy(ctx->timer_a);
     if (ctx->timer_b) cudaEventDestroy(ctx->timer_b);
+    for (int k = 0; k < 3; k++) {
+        if (ctx->stage_copied[k]) cudaEventDestroy(ctx->stage_copied[k]);
+        if (ctx->stage_consumed[k]) cudaEventDestroy(ctx->stage_consumed[k]);
+    }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -781,14 +829,15 @@ int fflins_frame_process(fflins_ctx *ctx, uint64_t frame_id, const float *xyzi, 
     REQUIRE(n >= 0 && (n == 0 || (xyzi && time)) && ins_t && ins_p && ins_q && pose_b_l, "null argument");
     int rc;
     if ((rc = check_window(ctx, ins_t, w))) return rc;
-    if ((rc = ensure_stage(ctx, (size_t) std::max(n, 1) * 24))) return rc;
-    cudaStream_t s = ctx->stream;
-    float4 *d_xyzi = (float4 *) ctx->d_stage;
-    double *d_time = (double *) ((char *) ctx->d_stage + (size_t) n * 16);
+    char *stage;
+    if ((rc = stage_acquire(ctx, (size_t) std::max(n, 1) * 24, &stage))) return rc;
+    float4 *d_xyzi = (float4 *) stage;
+    double *d_time = (double *) (stage + (size_t) n * 16);
     if (n > 0) {
-        CK(cudaMemcpyAsync(d_xyzi, xyzi, (size_t) n * 16, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(d_time, time, (size_t) n * 8, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(d_xyzi, xyzi, (size_t) n * 16, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CK(cudaMemcpyAsync(d_time, time, (size_t) n * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
     }
+    if ((rc = stage_publish(ctx))) return rc;
     return process_core(ctx, frame_id, d_xyzi, d_time, nullptr, n, ins_t, ins_p, ins_q, w, pose_b_l, stamp, td, out);
 }
 
@@ -799,10 +848,11 @@ int fflins_frame_process_aos(fflins_ctx *ctx, uint64_t frame_id, const void *poi
     REQUIRE(n >= 0 && (n == 0 || points32) && ins_t && ins_p && ins_q && pose_b_l, "null argument");
     int rc;
     if ((rc = check_window(ctx, ins_t, w))) return rc;
-    if ((rc = ensure_stage(ctx, (size_t) std::max(n, 1) * 32))) return rc;
-    cudaStream_t s = ctx->stream;
-    if (n > 0) CK(cudaMemcpyAsync(ctx->d_stage, points32, (size_t) n * 32, cudaMemcpyHostToDevice, s));
-    return process_core(ctx, frame_id, nullptr, nullptr, ctx->d_stage, n, ins_t, ins_p, ins_q, w, pose_b_l, stamp, td, out);
+    char *stage;
+    if ((rc = stage_acquire(ctx, (size_t) std::max(n, 1) * 32, &stage))) return rc;
+    if (n > 0) CK(cudaMemcpyAsync(stage, points32, (size_t) n * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
+    if ((rc = stage_publish(ctx))) return rc;
+    return process_core(ctx, frame_id, nullptr, nullptr, stage, n, ins_t, ins_p, ins_q, w, pose_b_l, stamp, td, out);
 }
 
 int fflins_frame_process_dev(fflins_ctx *ctx, uint64_t frame_id, const float *d_xyzi, const double *d_time, int32_t n,
@@ -829,7 +879,8 @@ int fflins_frame_process_static(fflins_ctx *ctx, uint64_t frame_id, const float 
     if ((rc = ensure_cloud(ctx, f->c[FFLINS_CLOUD_LIDAR_FULL], ndec))) return rc;
     if ((rc = ensure_cloud(ctx, f->c[FFLINS_CLOUD_LIDAR], ndec))) return rc;
     if ((rc = ensure_cloud(ctx, f->c[FFLINS_CLOUD_WORLD], ndec))) return rc;
-    if ((rc = ensure_stage(ctx, (size_t) std::max(n, 1) * 16))) return rc;
+    char *stage;
+    if ((rc = stage_acquire(ctx, (size_t) std::max(n, 1) * 16, &stage))) return rc;
     // MISC::stateToPoseWithExtrinsic (misc.cc:99-105), host fp64
     {
         Q4 q{state_q[0], state_q[1], state_q[2], state_q[3]};
@@ -842,11 +893,16 @@ int fflins_frame_process_static(fflins_ctx *ctx, uint64_t frame_id, const float 
     }
     CK(cudaMemsetAsync(ctx->d_counters, 0, 4 * sizeof(int), s));
     if (n > 0) {
-        CK(cudaMemcpyAsync(ctx->d_stage, xyzi, (size_t) n * 16, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(stage, xyzi, (size_t) n * 16, cudaMemcpyHostToDevice, ctx->copy_stream));
+        if ((rc = stage_publish(ctx))) return rc;
         ProfScope ps(ctx->prof(), "copy_decimate", s);
-        launch_copy_decimate(s, (const float4 *) ctx->d_stage, n, F, f->c[FFLINS_CLOUD_MAP_FULL].d,
+        launch_copy_decimate(s, (const float4 *) stage, n, F, f->c[FFLINS_CLOUD_MAP_FULL].d,
                              f->c[FFLINS_CLOUD_LIDAR_FULL].d);
         ctx->launches++;
+    }
+    if (ctx->stage_cur >= 0) {
+        CK(cudaEventRecord(ctx->stage_consumed[ctx->stage_cur], s));
+        ctx->stage_cur = -1;
     }
     return frame_tail(ctx, f, n, ndec, out);
 }
