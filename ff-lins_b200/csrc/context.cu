@@ -440,14 +440,13 @@ int check_window(fflins_ctx *ctx, const double *ins_t, int w) {
     return FFLINS_OK;
 }
 
-// one H2D copy per frame: t | p | q packed into a pinned staging slot first (64 B per entry). The slots
-// form a ring guarded by events so that packing window k+1 never overwrites a copy that is still queued.
-int upload_ins(fflins_ctx *ctx, const double *ins_t, const double *ins_p, const double *ins_q, int w) {
-    int rc;
-    if ((rc = ensure_ins(ctx, w))) return rc;
+// t | p | q packed into a pinned staging slot (64 B per entry). The slots form a ring guarded by events so
+// that packing window k+1 never overwrites a copy that is still queued on the copy stream.
+int pack_window(fflins_ctx *ctx, const double *ins_t, const double *ins_p, const double *ins_q, int w, double **hp_out,
+                int *slot_out) {
     const size_t need = (size_t) w * 64;
     if (need > ctx->h_win_slot) {
-        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaStreamSynchronize(ctx->copy_stream));
         if (ctx->h_win) cudaFreeHost(ctx->h_win);
         ctx->h_win_slot = std::max<size_t>(need, 4096 * 64);
         if (cudaMallocHost((void **) &ctx->h_win, ctx->h_win_slot * kWinRing) != cudaSuccess) {
@@ -456,7 +455,7 @@ int upload_ins(fflins_ctx *ctx, const double *ins_t, const double *ins_p, const 
             return fail(ctx, FFLINS_E_NOMEM, "pinned allocation failed");
         }
     }
-    const int k = ctx->win_next;
+    const int k   = ctx->win_next;
     ctx->win_next = (k + 1) % kWinRing;
     if (!ctx->win_ev[k]) CK(cudaEventCreateWithFlags(&ctx->win_ev[k], cudaEventDisableTiming));
     else CK(cudaEventSynchronize(ctx->win_ev[k]));
@@ -464,17 +463,56 @@ int upload_ins(fflins_ctx *ctx, const double *ins_t, const double *ins_p, const 
     std::memcpy(hp, ins_t, (size_t) w * 8);
     std::memcpy(hp + w, ins_p, (size_t) w * 24);
     std::memcpy(hp + 4 * (size_t) w, ins_q, (size_t) w * 32);
-    CK(cudaMemcpyAsync(ctx->d_ins, hp, need, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaEventRecord(ctx->win_ev[k], ctx->stream));
+    *hp_out   = hp;
+    *slot_out = k;
     return FFLINS_OK;
+}
+
+// Stage one frame's inputs in the next slot of the device ring: the INS window always, the points when they
+// are host-resident (xyzi + time, or 32-byte AoS records). EVERY host-to-device copy goes to the copy stream,
+// so the copies of frame k+1 never queue behind kernels of frame k.
+struct StagedFrame {
+    const float4 *d_xyzi = nullptr;
+    const double *d_time = nullptr;
+    const void *d_aos    = nullptr;
+    const double *d_win  = nullptr;
+};
+int stage_frame(fflins_ctx *ctx, const float *xyzi, const double *time, const void *aos, int n, const double *ins_t,
+                const double *ins_p, const double *ins_q, int w, StagedFrame *out) {
+    int rc;
+    const size_t win_bytes = ((size_t) w * 64 + 255) & ~(size_t) 255;
+    size_t pts_bytes       = aos ? (size_t) n * 32 : (xyzi ? (size_t) n * 24 : 0);
+    pts_bytes              = (pts_bytes + 255) & ~(size_t) 255;
+    char *stage;
+    if ((rc = stage_acquire(ctx, win_bytes + pts_bytes + 256, &stage))) return rc;
+    double *hp;
+    int wslot;
+    if ((rc = pack_window(ctx, ins_t, ins_p, ins_q, w, &hp, &wslot))) return rc;
+    cudaStream_t cs = ctx->copy_stream;
+    CK(cudaMemcpyAsync(stage, hp, (size_t) w * 64, cudaMemcpyHostToDevice, cs));
+    CK(cudaEventRecord(ctx->win_ev[wslot], cs));
+    out->d_win = (const double *) stage;
+    char *pts  = stage + win_bytes;
+    if (aos) {
+        if (n > 0) CK(cudaMemcpyAsync(pts, aos, (size_t) n * 32, cudaMemcpyHostToDevice, cs));
+        out->d_aos = pts;
+    } else if (xyzi) {
+        if (n > 0) {
+            CK(cudaMemcpyAsync(pts, xyzi, (size_t) n * 16, cudaMemcpyHostToDevice, cs));
+            CK(cudaMemcpyAsync(pts + (size_t) n * 16, time, (size_t) n * 8, cudaMemcpyHostToDevice, cs));
+        }
+        out->d_xyzi = (const float4 *) pts;
+        out->d_time = (const double *) (pts + (size_t) n * 16);
+    }
+    return stage_publish(ctx);
 }
 
 // ins_* are HOST pointers (the window is small and produced by the CPU-side INS mechanisation); the
 // point buffers are device pointers. The frame pose at `stamp` (lidar_map.cc:223) is evaluated on the
 // host — one pose, the same fp64 chain as MISC::getPoseFromInsWindow — and handed to the kernels by value.
 int process_core(fflins_ctx *ctx, uint64_t id, const float4 *d_xyzi, const double *d_time, const void *d_aos, int n,
-                 const double *ins_t, const double *ins_p, const double *ins_q, int w, const fflins_pose *pose_b_l,
-                 double stamp, double td, fflins_frame_info *out) {
+                 const double *d_win, const double *ins_t, const double *ins_p, const double *ins_q, int w,
+                 const fflins_pose *pose_b_l, double stamp, double td, fflins_frame_info *out) {
     cudaStream_t s = ctx->stream;
     Frame *f       = get_frame(ctx, id);
     const int F    = ctx->cfg.point_filter_num;
@@ -484,12 +522,12 @@ int process_core(fflins_ctx *ctx, uint64_t id, const float4 *d_xyzi, const doubl
     if ((rc = ensure_cloud(ctx, f->c[FFLINS_CLOUD_LIDAR_FULL], ndec))) return rc;
     if ((rc = ensure_cloud(ctx, f->c[FFLINS_CLOUD_LIDAR], ndec))) return rc;
     if ((rc = ensure_cloud(ctx, f->c[FFLINS_CLOUD_WORLD], ndec))) return rc;
-    if ((rc = upload_ins(ctx, ins_t, ins_p, ins_q, w))) return rc;
+    if ((rc = ensure_ins(ctx, w))) return rc;
     Pose12 ext = to12(*pose_b_l), frame;
     pose_from_window(ins_t, ins_p, ins_q, w, ext, stamp, frame);
     std::memcpy(f->pose.R, frame.R, sizeof(frame.R));
     std::memcpy(f->pose.t, frame.t, sizeof(frame.t));
-    const double *d_ins_t = ctx->d_ins, *d_ins_p = ctx->d_ins + w, *d_ins_q = ctx->d_ins + 4 * (size_t) w;
+    const double *d_ins_t = d_win, *d_ins_p = d_win + w, *d_ins_q = d_win + 4 * (size_t) w;
     {
         ProfScope ps(ctx->prof(), "ins_prep", s);
         launch_ins_prep(s, d_ins_t, d_ins_p, d_ins_q, w, ext, frame, ctx->d_tab, ctx->d_counters);
@@ -829,16 +867,10 @@ int fflins_frame_process(fflins_ctx *ctx, uint64_t frame_id, const float *xyzi, 
     REQUIRE(n >= 0 && (n == 0 || (xyzi && time)) && ins_t && ins_p && ins_q && pose_b_l, "null argument");
     int rc;
     if ((rc = check_window(ctx, ins_t, w))) return rc;
-    char *stage;
-    if ((rc = stage_acquire(ctx, (size_t) std::max(n, 1) * 24, &stage))) return rc;
-    float4 *d_xyzi = (float4 *) stage;
-    double *d_time = (double *) (stage + (size_t) n * 16);
-    if (n > 0) {
-        CK(cudaMemcpyAsync(d_xyzi, xyzi, (size_t) n * 16, cudaMemcpyHostToDevice, ctx->copy_stream));
-        CK(cudaMemcpyAsync(d_time, time, (size_t) n * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
-    }
-    if ((rc = stage_publish(ctx))) return rc;
-    return process_core(ctx, frame_id, d_xyzi, d_time, nullptr, n, ins_t, ins_p, ins_q, w, pose_b_l, stamp, td, out);
+    StagedFrame sf;
+    if ((rc = stage_frame(ctx, xyzi, time, nullptr, n, ins_t, ins_p, ins_q, w, &sf))) return rc;
+    return process_core(ctx, frame_id, sf.d_xyzi, sf.d_time, nullptr, n, sf.d_win, ins_t, ins_p, ins_q, w, pose_b_l, stamp, td,
+                        out);
 }
 
 int fflins_frame_process_aos(fflins_ctx *ctx, uint64_t frame_id, const void *points32, int32_t n, const double *ins_t,
@@ -848,11 +880,9 @@ int fflins_frame_process_aos(fflins_ctx *ctx, uint64_t frame_id, const void *poi
     REQUIRE(n >= 0 && (n == 0 || points32) && ins_t && ins_p && ins_q && pose_b_l, "null argument");
     int rc;
     if ((rc = check_window(ctx, ins_t, w))) return rc;
-    char *stage;
-    if ((rc = stage_acquire(ctx, (size_t) std::max(n, 1) * 32, &stage))) return rc;
-    if (n > 0) CK(cudaMemcpyAsync(stage, points32, (size_t) n * 32, cudaMemcpyHostToDevice, ctx->copy_stream));
-    if ((rc = stage_publish(ctx))) return rc;
-    return process_core(ctx, frame_id, nullptr, nullptr, stage, n, ins_t, ins_p, ins_q, w, pose_b_l, stamp, td, out);
+    StagedFrame sf;
+    if ((rc = stage_frame(ctx, nullptr, nullptr, points32, n, ins_t, ins_p, ins_q, w, &sf))) return rc;
+    return process_core(ctx, frame_id, nullptr, nullptr, sf.d_aos, n, sf.d_win, ins_t, ins_p, ins_q, w, pose_b_l, stamp, td, out);
 }
 
 int fflins_frame_process_dev(fflins_ctx *ctx, uint64_t frame_id, const float *d_xyzi, const double *d_time, int32_t n,
@@ -862,8 +892,10 @@ int fflins_frame_process_dev(fflins_ctx *ctx, uint64_t frame_id, const float *d_
     REQUIRE(n >= 0 && (n == 0 || (d_xyzi && d_time)) && ins_t && ins_p && ins_q && pose_b_l, "null argument");
     int rc;
     if ((rc = check_window(ctx, ins_t, w))) return rc;
-    return process_core(ctx, frame_id, (const float4 *) d_xyzi, d_time, nullptr, n, ins_t, ins_p, ins_q, w, pose_b_l, stamp,
-                        td, out);
+    StagedFrame sf;
+    if ((rc = stage_frame(ctx, nullptr, nullptr, nullptr, n, ins_t, ins_p, ins_q, w, &sf))) return rc;
+    return process_core(ctx, frame_id, (const float4 *) d_xyzi, d_time, nullptr, n, sf.d_win, ins_t, ins_p, ins_q, w, pose_b_l,
+                        stamp, td, out);
 }
 
 int fflins_frame_process_static(fflins_ctx *ctx, uint64_t frame_id, const float *xyzi, int32_t n, const double state_p[3],
