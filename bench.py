@@ -260,11 +260,17 @@ def run_ours(args, rank, world, local_rank):
                          "alg_bytes_per_call": alg.get(g, 0), "achieved_gbs": round(gbs, 2), "sub": a["sub"]}
         top = max(groups, key=lambda g: groups[g]["ms"])
         peak, peak_src = measured_peak()
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(top)
+        except Exception:
+            pass
         roof = {"kernel": top, "bound": "hbm", "achieved": stages[top]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": round(stages[top]["achieved_gbs"] / peak, 5), "traffic": None, "peak_source": peak_src,
+                "frac": round(stages[top]["achieved_gbs"] / peak, 5), "traffic": traffic, "peak_source": peak_src,
                 "alg_bytes_per_launch": stages[top]["alg_bytes_per_call"],
                 "avg_launch_ms": stages[top]["ms_per_call"],
-                "note": "single-frame launches are latency-bound (one AT128 frame moves ~6 MB); see DESIGN.md §5"}
+                "note": "dominant stage of the per-frame pipeline by summed CUDA-event time; at one 150k-point frame every "
+                        "launch is latency-bound (DESIGN.md §5) - bandwidth-bound launch sizes are in roofline_batched"}
 
     # D2H per step: 5 frame infos (2 ints + pose), merge count, assoc counts, 15 evals x refs x 212 doubles, chi2 counts
     n_refs = cfg.window_size
