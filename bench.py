@@ -225,9 +225,9 @@ def run_ours(args, rank, world, local_rank):
             step("dev")
         prof = ctx.profile_get()
         ctx.profile_enable(False)
-        merge_info = sess.last.get("merge")
         assoc = sess.last.get("assoc")
-        m_map = merge_info.n_map if merge_info else 0
+        kids = ctx.keyframe_ids()
+        m_map = ctx.frame_info(kids[-1]).n_map if kids else 0
         q = assoc.n_queries if assoc else 0
         n_refs = assoc.n_refs if assoc else 0
         n_map_in = FRAMES_PER_KEY * n
@@ -277,6 +277,10 @@ def run_ours(args, rank, world, local_rank):
     d2h = FRAMES_PER_KEY * (8 + 96) + 4 + 8 * n_refs + sum(N_EVAL) * n_refs * 212 * 8 + 4 * n_refs
     h2d = FRAMES_PER_KEY * (n * 24 + w * 64)
 
+    last_m = None
+    if rank == 0:
+        kids = ctx.keyframe_ids()
+        last_m = ctx.frame_info(kids[-1]).n_map if kids else None
     batched = None
     if rank == 0 and not args.no_batched:
         ctx.close()
@@ -311,7 +315,7 @@ def run_ours(args, rank, world, local_rank):
             "roofline_batched": batched,
             "cpu_baseline": cpu,
             "workload_sizes": {"Q": sess.last["assoc"].n_queries if "assoc" in sess.last else None,
-                               "M": sess.last["merge"].n_map if "merge" in sess.last else None},
+                               "M": last_m},
         }
         print(json.dumps(out))
     if ctx is not None:

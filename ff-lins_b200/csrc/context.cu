@@ -33,6 +33,7 @@ struct Frame {
     double v[3] = {0, 0, 0}, w[3] = {0, 0, 0}, td = 0;
     int n_raw = 0, n_fallback = 0;
     bool is_key = false;
+    bool hash_pending = false; // map still being built on the map stream: the hash is inserted at first use
     int pending_slot = -1; // >= 0: counts of the last frame_process still sit in pinned slot (asynchronous mode)
     // keyframe hash (K4)
     unsigned long long *hkeys = nullptr, *ckeys = nullptr, *cmask = nullptr;
@@ -111,6 +112,17 @@ struct fflins_ctx : public Profiler {
     int *d_counters = nullptr;      // [64]
     VoxelWork vox;
     void *vox_base = nullptr;
+    // keyframe-map construction (merge projection + map voxel filter) runs on its own stream, concurrently
+    // with association and factor evaluation of the same keyframe, which do not depend on the new map
+    cudaStream_t map_stream = nullptr;
+    VoxelWork vox_map;
+    void *vox_map_base = nullptr;
+    int *d_map_count = nullptr, *h_map_count = nullptr;
+    cudaEvent_t ev_main_done = nullptr, ev_map_done = nullptr;
+    bool map_job_active = false;
+    uint64_t map_job_key = 0;
+    std::vector<Frame *> deferred_frames; // released while the map job may still read them
+    std::vector<void *> deferred_blocks;
     // factor scratch
     double *d_red = nullptr;
     int *d_outliers = nullptr;
@@ -171,6 +183,7 @@ struct fflins_ctx : public Profiler {
         return e;
     }
     void prof_collect() {
+        if (map_stream) cudaStreamSynchronize(map_stream);
         cudaStreamSynchronize(stream);
         for (auto &r : prof_open) {
             float ms = 0;
@@ -258,6 +271,22 @@ int resolve_pending(fflins_ctx *ctx) {
         f->pending_slot                = -1;
     }
     ctx->pending.clear();
+    return FFLINS_OK;
+}
+
+void free_frame(fflins_ctx *ctx, Frame *f);
+
+// Wait for the keyframe-map job on the map stream (if any), adopt its voxel count and free what had to
+// outlive it. Called by everything that reads a map cloud, its size, or frees buffers the job may touch.
+int resolve_map(fflins_ctx *ctx) {
+    if (!ctx->map_job_active) return FFLINS_OK;
+    CK(cudaEventSynchronize(ctx->ev_map_done));
+    ctx->map_job_active = false;
+    if (Frame *key = find_frame(ctx, ctx->map_job_key)) key->c[FFLINS_CLOUD_MAP].n = ctx->h_map_count[0];
+    for (Frame *f : ctx->deferred_frames) free_frame(ctx, f);
+    ctx->deferred_frames.clear();
+    for (void *b : ctx->deferred_blocks) ctx->pool.release(b);
+    ctx->deferred_blocks.clear();
     return FFLINS_OK;
 }
 
@@ -349,29 +378,30 @@ int ensure_ins(fflins_ctx *ctx, int w) {
     return FFLINS_OK;
 }
 
-int ensure_voxel(fflins_ctx *ctx, int n) {
-    if (n <= ctx->vox.cap) return FFLINS_OK;
-    ctx->pool.release(ctx->vox_base);
+int ensure_voxel_work(fflins_ctx *ctx, VoxelWork &vw, void *&base, int n) {
+    if (n <= vw.cap) return FFLINS_OK;
+    ctx->pool.release(base);
     int cap = (int) (Pool::round((size_t) std::max(n, 4096)));
     size_t off[8];
-    size_t bytes  = voxel_work_bytes(cap, off);
-    ctx->vox_base = ctx->pool.alloc(bytes);
-    if (!ctx->vox_base) {
-        ctx->vox.cap = 0;
+    size_t bytes = voxel_work_bytes(cap, off);
+    base         = ctx->pool.alloc(bytes);
+    if (!base) {
+        vw.cap = 0;
         return fail(ctx, FFLINS_E_NOMEM, "device allocation failed");
     }
-    char *b              = (char *) ctx->vox_base;
-    ctx->vox.keys[0]     = (uint32_t *) (b + off[0]);
-    ctx->vox.keys[1]     = (uint32_t *) (b + off[1]);
-    ctx->vox.idx[0]      = (uint32_t *) (b + off[2]);
-    ctx->vox.idx[1]      = (uint32_t *) (b + off[3]);
-    ctx->vox.block_hist  = (uint32_t *) (b + off[4]);
-    ctx->vox.block_heads = (uint32_t *) (b + off[5]);
-    ctx->vox.meta        = (int *) (b + off[6]);
-    ctx->vox.seg_start   = (uint32_t *) (b + off[7]);
-    ctx->vox.cap         = cap;
+    char *b        = (char *) base;
+    vw.keys[0]     = (uint32_t *) (b + off[0]);
+    vw.keys[1]     = (uint32_t *) (b + off[1]);
+    vw.idx[0]      = (uint32_t *) (b + off[2]);
+    vw.idx[1]      = (uint32_t *) (b + off[3]);
+    vw.block_hist  = (uint32_t *) (b + off[4]);
+    vw.block_heads = (uint32_t *) (b + off[5]);
+    vw.meta        = (int *) (b + off[6]);
+    vw.seg_start   = (uint32_t *) (b + off[7]);
+    vw.cap         = cap;
     return FFLINS_OK;
 }
+int ensure_voxel(fflins_ctx *ctx, int n) { return ensure_voxel_work(ctx, ctx->vox, ctx->vox_base, n); }
 
 unsigned char *pin(fflins_ctx *ctx, size_t bytes) {
     if (bytes > ctx->h_pin_cap) {
@@ -644,6 +674,11 @@ int run_associate(fflins_ctx *ctx, const std::vector<Frame *> &refs, Frame *cur,
     int rc;
     for (size_t i = 0; i < refs.size(); i++) {
         Frame *r = refs[i];
+        if (r->hash_pending) { // map built on the map stream: insert its hash now (first use as a reference)
+            if (ctx->map_job_active && ctx->map_job_key == r->id && (rc = resolve_map(ctx))) return rc;
+            if ((rc = build_hash(ctx, r))) return rc;
+            r->hash_pending = false;
+        }
         if ((rc = ensure_features(ctx, r, q))) return rc;
         if (!r->hkeys && r->c[FFLINS_CLOUD_MAP].n > 0) return fail(ctx, FFLINS_E_INVALID, "reference frame has no map index (fflins_keyframe_add not called)");
         AssocRef &a   = P.ref[i];
@@ -779,7 +814,10 @@ int fflins_create(const fflins_config *cfg, int device, fflins_ctx **out) {
         if (v >= 0.5f && v <= 8.f) ctx->cell_scale = v;
     }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->map_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_main_done, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_map_done, cudaEventDisableTiming) != cudaSuccess) {
         delete ctx;
         return FFLINS_E_CUDA;
     }
@@ -787,18 +825,20 @@ int fflins_create(const fflins_config *cfg, int device, fflins_ctx **out) {
     ctx->d_counters   = (int *) ctx->pool.alloc(64 * sizeof(int));
     ctx->d_red        = (double *) ctx->pool.alloc((size_t) kMaxRefs * kRedSize * sizeof(double));
     ctx->d_outliers   = (int *) ctx->pool.alloc(kMaxRefs * sizeof(int));
-    if (!ctx->d_frame_pose || !ctx->d_counters || !ctx->d_red || !ctx->d_outliers) {
+    ctx->d_map_count  = (int *) ctx->pool.alloc(64);
+    if (!ctx->d_frame_pose || !ctx->d_counters || !ctx->d_red || !ctx->d_outliers || !ctx->d_map_count) {
         fflins_destroy(ctx);
         return FFLINS_E_NOMEM;
     }
     int n = cfg->max_points_per_frame > 0 ? cfg->max_points_per_frame : 262144;
     int k = cfg->max_merge_frames > 0 ? cfg->max_merge_frames : 8;
-    if (ensure_voxel(ctx, n * k) != FFLINS_OK || ensure_stage(ctx, (size_t) n * 32) != FFLINS_OK ||
+    if (ensure_voxel(ctx, n) != FFLINS_OK || ensure_voxel_work(ctx, ctx->vox_map, ctx->vox_map_base, n * k) != FFLINS_OK || ensure_stage(ctx, (size_t) n * 32) != FFLINS_OK ||
         ensure_ins(ctx, 4096) != FFLINS_OK || !pin(ctx, 1 << 20)) {
         fflins_destroy(ctx);
         return FFLINS_E_NOMEM;
     }
-    if (cudaMallocHost((void **) &ctx->h_slots, kSlots * 2 * sizeof(int)) != cudaSuccess) {
+    if (cudaMallocHost((void **) &ctx->h_slots, kSlots * 2 * sizeof(int)) != cudaSuccess ||
+        cudaMallocHost((void **) &ctx->h_map_count, 64) != cudaSuccess) {
         ctx->h_slots = nullptr;
         fflins_destroy(ctx);
         return FFLINS_E_NOMEM;
@@ -814,8 +854,11 @@ int fflins_create(const fflins_config *cfg, int device, fflins_ctx **out) {
 void fflins_destroy(fflins_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (ctx->map_stream) cudaStreamSynchronize(ctx->map_stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (Frame *f : ctx->deferred_frames) delete f;
+    ctx->deferred_frames.clear();
     for (auto &kv : ctx->frames) {
         Frame *f = kv.second;
         delete f;
@@ -824,6 +867,10 @@ void fflins_destroy(fflins_ctx *ctx) {
     ctx->pool.destroy();
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     if (ctx->h_slots) cudaFreeHost(ctx->h_slots);
+    if (ctx->h_map_count) cudaFreeHost(ctx->h_map_count);
+    if (ctx->ev_main_done) cudaEventDestroy(ctx->ev_main_done);
+    if (ctx->ev_map_done) cudaEventDestroy(ctx->ev_map_done);
+    if (ctx->map_stream) cudaStreamDestroy(ctx->map_stream);
     if (ctx->h_win) cudaFreeHost(ctx->h_win);
     for (auto e : ctx->win_ev)
         if (e) cudaEventDestroy(e);
@@ -847,6 +894,10 @@ const char *fflins_last_error(const fflins_ctx *ctx) { return ctx ? ctx->err.c_s
 
 int fflins_synchronize(fflins_ctx *ctx) {
     if (!ctx) return FFLINS_E_INVALID;
+    {
+        int rcm = resolve_map(ctx);
+        if (rcm) return rcm;
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     return resolve_pending(ctx);
 }
@@ -942,6 +993,10 @@ int fflins_frame_process_static(fflins_ctx *ctx, uint64_t frame_id, const float 
 int fflins_frame_info_get(fflins_ctx *ctx, uint64_t frame_id, fflins_frame_info *out) {
     if (!ctx || !out) return FFLINS_E_INVALID;
     {
+        int rcm = resolve_map(ctx);
+        if (rcm) return rcm;
+    }
+    {
         int rcp = resolve_pending(ctx);
         if (rcp) return rcp;
     }
@@ -954,6 +1009,10 @@ int fflins_frame_info_get(fflins_ctx *ctx, uint64_t frame_id, fflins_frame_info 
 int fflins_frame_download(fflins_ctx *ctx, uint64_t frame_id, int which, float *xyzi, int32_t cap, int32_t *n) {
     if (!ctx) return FFLINS_E_INVALID;
     REQUIRE(which >= 0 && which < 5, "bad cloud selector");
+    {
+        int rcm = resolve_map(ctx);
+        if (rcm) return rcm;
+    }
     {
         int rcp = resolve_pending(ctx);
         if (rcp) return rcp;
@@ -974,6 +1033,10 @@ int fflins_frame_download(fflins_ctx *ctx, uint64_t frame_id, int which, float *
 int fflins_frame_upload(fflins_ctx *ctx, uint64_t frame_id, int which, const float *xyzi, int32_t n) {
     if (!ctx) return FFLINS_E_INVALID;
     REQUIRE(which >= 0 && which < 5 && n >= 0 && (n == 0 || xyzi), "bad argument");
+    {
+        int rcm = resolve_map(ctx);
+        if (rcm) return rcm;
+    }
     {
         int rcp = resolve_pending(ctx);
         if (rcp) return rcp;
@@ -1020,8 +1083,19 @@ int fflins_frame_release(fflins_ctx *ctx, uint64_t frame_id) {
     if (it == ctx->frames.end()) return fail(ctx, FFLINS_E_NOTFOUND, "unknown frame");
     for (auto k : ctx->keyframes)
         if (k == frame_id) return fail(ctx, FFLINS_E_INVALID, "frame is a keyframe: remove it from the window first");
-    // no synchronisation: the blocks go back to the pool and any reuse is ordered on the context's stream
-    free_frame(ctx, it->second);
+    // no synchronisation: the blocks go back to the pool and any reuse is ordered on the context's stream;
+    // while a map job is in flight on the map stream the release is deferred until the job is done
+    if (ctx->map_job_active) {
+        if (ctx->map_job_key == frame_id) {
+            int rcm = resolve_map(ctx);
+            if (rcm) return rcm;
+            free_frame(ctx, it->second);
+        } else {
+            ctx->deferred_frames.push_back(it->second);
+        }
+    } else {
+        free_frame(ctx, it->second);
+    }
     ctx->frames.erase(it);
     return FFLINS_OK;
 }
@@ -1246,21 +1320,44 @@ int fflins_knn5(fflins_ctx *ctx, const float *map_xyzi, int32_t m, const float *
 int fflins_keyframe_merge(fflins_ctx *ctx, uint64_t key_id, const uint64_t *nonkey_ids, int32_t n, fflins_frame_info *out) {
     if (!ctx) return FFLINS_E_INVALID;
     REQUIRE(n >= 0 && (n == 0 || nonkey_ids), "bad argument");
+    int rc;
+    if ((rc = resolve_map(ctx))) return rc; // one map job in flight at a time
     Frame *key = find_frame(ctx, key_id);
     if (!key) return fail(ctx, FFLINS_E_NOTFOUND, "unknown keyframe");
-    cudaStream_t s = ctx->stream;
-    int total      = key->c[FFLINS_CLOUD_MAP_FULL].n;
+    cudaStream_t ms = ctx->map_stream;
+    int total       = key->c[FFLINS_CLOUD_MAP_FULL].n;
     std::vector<Frame *> nk(n);
     for (int i = 0; i < n; i++) {
         nk[i] = find_frame(ctx, nonkey_ids[i]);
         if (!nk[i]) return fail(ctx, FFLINS_E_NOTFOUND, "unknown non-keyframe");
         total += nk[i]->c[FFLINS_CLOUD_MAP_FULL].n;
     }
-    int rc;
-    if ((rc = ensure_cloud(ctx, key->c[FFLINS_CLOUD_MAP_FULL], total, true))) return rc;
-    if ((rc = ensure_cloud(ctx, key->c[FFLINS_CLOUD_MAP], total))) return rc;
-    if ((rc = ensure_voxel(ctx, total))) return rc;
-    int off = key->c[FFLINS_CLOUD_MAP_FULL].n;
+    if ((rc = ensure_voxel_work(ctx, ctx->vox_map, ctx->vox_map_base, total))) return rc;
+    // the map stream starts once everything enqueued so far on the compute stream (the undistortion of the
+    // frames being merged) is done
+    CK(cudaEventRecord(ctx->ev_main_done, ctx->stream));
+    CK(cudaStreamWaitEvent(ms, ctx->ev_main_done, 0));
+    // grow the keyframe's full cloud to K*N on the map stream; blocks the job may still read are freed later
+    Cloud &full = key->c[FFLINS_CLOUD_MAP_FULL];
+    if (total > full.cap) {
+        size_t want = Pool::round((size_t) std::max(total, 256) * sizeof(float4));
+        float4 *p   = (float4 *) ctx->pool.alloc(want);
+        if (!p) return fail(ctx, FFLINS_E_NOMEM, "device allocation failed");
+        if (full.d && full.n > 0) CK(cudaMemcpyAsync(p, full.d, (size_t) full.n * sizeof(float4), cudaMemcpyDeviceToDevice, ms));
+        if (full.d) ctx->deferred_blocks.push_back(full.d);
+        full.d   = p;
+        full.cap = (int) (want / sizeof(float4));
+    }
+    Cloud &map = key->c[FFLINS_CLOUD_MAP];
+    if (total > map.cap) {
+        size_t want = Pool::round((size_t) std::max(total, 256) * sizeof(float4));
+        float4 *p   = (float4 *) ctx->pool.alloc(want);
+        if (!p) return fail(ctx, FFLINS_E_NOMEM, "device allocation failed");
+        if (map.d) ctx->deferred_blocks.push_back(map.d);
+        map.d   = p;
+        map.cap = (int) (want / sizeof(float4));
+    }
+    int off = full.n;
     for (int i0 = 0; i0 < n; i0 += kMaxRefs) {
         // relative pose non-keyframe -> keyframe (lidar_map.cc:198-199); the projected clouds are written
         // straight behind the keyframe's own points (the reference projects in place, then appends: :201-205),
@@ -1274,25 +1371,24 @@ int fflins_keyframe_merge(fflins_ctx *ctx, uint64_t key_id, const uint64_t *nonk
             mat_tv(key->pose.R, dt, B.T[j].t);
             B.n[j]   = g->c[FFLINS_CLOUD_MAP_FULL].n;
             B.src[j] = g->c[FFLINS_CLOUD_MAP_FULL].d;
-            B.dst[j] = key->c[FFLINS_CLOUD_MAP_FULL].d + off;
+            B.dst[j] = full.d + off;
             off += B.n[j];
         }
-        ProfScope ps(ctx->prof(), "merge_project", s);
-        launch_project_batch(s, B);
+        ProfScope ps(ctx->prof(), "merge_project", ms);
+        launch_project_batch(ms, B);
         ctx->launches++;
     }
-    key->c[FFLINS_CLOUD_MAP_FULL].n = total;
-    launch_voxel_downsample(s, ctx->vox, key->c[FFLINS_CLOUD_MAP_FULL].d, total, (float) ctx->cfg.downsample_size,
-                            key->c[FFLINS_CLOUD_MAP].d, ctx->d_counters + 3, nullptr, &ctx->launches, ctx->prof(),
-                            "voxel_map");
-    unsigned char *h = pin(ctx, 64);
-    if (!h) return fail(ctx, FFLINS_E_NOMEM, "pinned allocation failed");
-    CK(cudaMemcpyAsync(h, ctx->d_counters + 3, sizeof(int), cudaMemcpyDeviceToHost, s));
-    if ((rc = resolve_pending(ctx))) return rc; // frames processed asynchronously are complete now, too
-    CK(cudaStreamSynchronize(s));
-    int m;
-    std::memcpy(&m, h, sizeof(int));
-    key->c[FFLINS_CLOUD_MAP].n = m;
+    full.n = total;
+    launch_voxel_downsample(ms, ctx->vox_map, full.d, total, (float) ctx->cfg.downsample_size, map.d, ctx->d_map_count,
+                            nullptr, &ctx->launches, ctx->prof(), "voxel_map");
+    CK(cudaMemcpyAsync(ctx->h_map_count, ctx->d_map_count, sizeof(int), cudaMemcpyDeviceToHost, ms));
+    CK(cudaEventRecord(ctx->ev_map_done, ms));
+    ctx->map_job_active = true;
+    ctx->map_job_key    = key_id;
+    map.n               = 0;
+    if (!out) return FFLINS_OK; // asynchronous: the map is adopted by the first call that needs it
+    if ((rc = resolve_map(ctx))) return rc;
+    if ((rc = resolve_pending(ctx))) return rc;
     fill_info(key, out);
     return FFLINS_OK;
 }
@@ -1303,7 +1399,11 @@ int fflins_keyframe_add(fflins_ctx *ctx, uint64_t key_id) {
     if (!f) return fail(ctx, FFLINS_E_NOTFOUND, "unknown frame");
     REQUIRE((int) ctx->keyframes.size() < kMaxRefs, "keyframe window is full");
     int rc;
-    if ((rc = build_hash(ctx, f))) return rc;
+    if (ctx->map_job_active && ctx->map_job_key == key_id) {
+        f->hash_pending = true; // its map is still being built: the hash insert happens at first use as a ref
+    } else if ((rc = build_hash(ctx, f))) {
+        return rc;
+    }
     f->is_key = true;
     ctx->keyframes.push_back(key_id);
     return FFLINS_OK;
@@ -1311,6 +1411,13 @@ int fflins_keyframe_add(fflins_ctx *ctx, uint64_t key_id) {
 
 static int remove_key(fflins_ctx *ctx, bool oldest, uint64_t *removed_id) {
     REQUIRE(!ctx->keyframes.empty(), "no keyframe in the window");
+    {
+        uint64_t victim = oldest ? ctx->keyframes.front() : ctx->keyframes.back();
+        if (ctx->map_job_active && ctx->map_job_key == victim) {
+            int rcm = resolve_map(ctx);
+            if (rcm) return rcm;
+        }
+    }
     uint64_t id = oldest ? ctx->keyframes.front() : ctx->keyframes.back();
     if (oldest)
         ctx->keyframes.pop_front();
@@ -1372,6 +1479,10 @@ int fflins_associate(fflins_ctx *ctx, fflins_assoc_stats *out) {
 
 int fflins_associate_pair(fflins_ctx *ctx, uint64_t ref_id, uint64_t cur_id, int32_t *num_features, int32_t *num_covered) {
     if (!ctx) return FFLINS_E_INVALID;
+    {
+        int rcm = resolve_map(ctx);
+        if (rcm) return rcm;
+    }
     Frame *ref = find_frame(ctx, ref_id), *cur = find_frame(ctx, cur_id);
     if (!ref || !cur) return fail(ctx, FFLINS_E_NOTFOUND, "unknown frame");
     int rc;
@@ -1390,6 +1501,10 @@ int fflins_features_download(fflins_ctx *ctx, uint64_t ref_id, int32_t cap, int3
                              uint8_t *outlier, int32_t *nn_idx, float *nn_d2, float *nn_points, double *unit_normal,
                              double *norm_inverse) {
     if (!ctx) return FFLINS_E_INVALID;
+    {
+        int rcm = resolve_map(ctx);
+        if (rcm) return rcm;
+    }
     Frame *r = find_frame(ctx, ref_id);
     if (!r) return fail(ctx, FFLINS_E_NOTFOUND, "unknown frame");
     int n = r->feat_q;

@@ -269,11 +269,12 @@ class Context:
         return cnt, idx, d2
 
     # ---- keyframes -------------------------------------------------------------------------------
-    def keyframe_merge(self, key_id, nonkey_ids):
+    def keyframe_merge(self, key_id, nonkey_ids, sync=True):
+        """sync=False: out = NULL, the map is built on the map stream and adopted at first use."""
         ids = np.array(list(nonkey_ids), np.uint64)
-        info = FrameInfo()
+        info = FrameInfo() if sync else None
         self._ck(self.L.fflins_keyframe_merge(self.h, C.c_uint64(key_id), _p(ids) if len(ids) else None, len(ids),
-                                              C.byref(info)))
+                                              C.byref(info) if sync else None))
         return info
 
     def keyframe_add(self, key_id):

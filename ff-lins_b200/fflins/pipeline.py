@@ -79,7 +79,7 @@ class Session:
             self.nonkeys.append(fid)
             return False
         ctx = self.ctx
-        self.last["merge"] = ctx.keyframe_merge(fid, self.nonkeys)
+        self.last["merge"] = ctx.keyframe_merge(fid, self.nonkeys, sync=self.sync_frames)
         for nk in self.nonkeys:
             ctx.release(nk)
         self.nonkeys = []

@@ -175,7 +175,10 @@ int fflins_knn5(fflins_ctx *ctx, const float *map_xyzi, int32_t m, const float *
                 double max_dist, int32_t *nn_idx, float *nn_d2, int32_t *nn_count);
 
 /* ---- keyframe map maintenance ---------------------------------------------------------- */
-/* LidarMap::mergeNonKeyframes (lidar_map.cc:190-211). */
+/* LidarMap::mergeNonKeyframes (lidar_map.cc:190-211). `out` may be NULL = asynchronous: projection and map
+ * voxel filter run on the context's map stream, concurrently with the association and factor evaluation of
+ * the same keyframe (which do not read the new map); the map and its voxel hash are adopted by the first
+ * call that needs them (the next fflins_associate, a download, fflins_frame_info_get, ...). */
 int fflins_keyframe_merge(fflins_ctx *ctx, uint64_t key_id, const uint64_t *nonkey_ids, int32_t n,
                           fflins_frame_info *out);
 /* LidarMap::addNewKeyFrame (lidar_map.cc:100-126): device hash insert of the map cloud. */

@@ -668,3 +668,31 @@ def test_async_frames_match_sync(robot):
     assert a.n_map == b.n_map and a.n_down == sync_infos[2].n_down
     assert bits_equal(c.download(302, api.CLOUD_MAP), c.download(102, api.CLOUD_MAP))
     c.close()
+
+
+def test_async_keyframe_pipeline_matches_sync(robot):
+    """The benchmark's asynchronous call sequence (frames and keyframe merge with out = NULL, map built on
+    the map stream and adopted at first use) produces bit-identical maps, features and H blocks."""
+    from fflins import api
+    from fflins.pipeline import Session
+    frames = [robot.frame(i) for i in range(15)]
+    res = []
+    for sync in (True, False):
+        c = api.Context(api.default_config(point_filter_num=robot.filter_num, window_size=3))
+        sess = Session(c, robot, frames_per_key=3, n_eval=(1, 1), sync_frames=sync)
+        for fr in frames:
+            fid, _ = sess.process_frame(fr)
+            sess.after_frame(fid, fr)
+        ids = c.keyframe_ids()
+        maps = [c.download(k, api.CLOUD_MAP) for k in ids]
+        feats = [c.features(k) for k in ids[:-1]]
+        res.append((ids, maps, feats, sess.last["eval"]["H"].copy(), [c.frame_info(k).n_map for k in ids]))
+        c.close()
+    (ids_a, maps_a, feats_a, H_a, nm_a), (ids_b, maps_b, feats_b, H_b, nm_b) = res
+    assert ids_a == ids_b and nm_a == nm_b and all(n > 0 for n in nm_a)
+    for ma, mb in zip(maps_a, maps_b):
+        assert bits_equal(ma, mb)
+    for fa, fb in zip(feats_a, feats_b):
+        for k in ("type", "nn_idx", "nn_d2", "normal", "d", "outlier"):
+            assert bits_equal(fa[k], fb[k])
+    assert bits_equal(H_a, H_b)
