@@ -274,7 +274,7 @@ def run_ours(args, rank, world, local_rank):
 
     # D2H per step: 5 frame infos (2 ints + pose), merge count, assoc counts, 15 evals x refs x 212 doubles, chi2 counts
     n_refs = cfg.window_size
-    d2h = FRAMES_PER_KEY * (8 + 96) + 4 + 8 * n_refs + sum(N_EVAL) * n_refs * 212 * 8 + 4 * n_refs
+    d2h = FRAMES_PER_KEY * 8 + 4 + 8 * n_refs + sum(N_EVAL) * n_refs * 212 * 8 + 4 * n_refs
     h2d = FRAMES_PER_KEY * (n * 24 + w * 64)
 
     last_m = None
@@ -302,6 +302,8 @@ def run_ours(args, rank, world, local_rank):
                        "points_per_frame": n, "frames_per_step": FRAMES_PER_KEY, "window": cfg.window_size,
                        "ins_window": w, "factor_evals_per_keyframe": sum(N_EVAL) + 1,
                        "replicas": world, "parallelism": f"{world} independent session(s), no collective",
+                       "call_mode": "frames and keyframe merge enqueued asynchronously (out = NULL); association, the 15 "
+                                    "factor evaluations and the chi2 cull return their results synchronously",
                        "l2": f"inputs cycle over {P} distinct frames ({input_bytes / 1e6:.0f} MB) > 126 MB L2"},
             "mpoints_per_s": round(value * n / 1e6, 2),
             "wall_ms_per_step": round(wall_ms / args.steps, 4),

@@ -25,35 +25,43 @@ namespace fflins {
 
 namespace {
 
-__constant__ unsigned char c_tri_a[190];
-__constant__ unsigned char c_tri_b[190];
-
-constexpr int kRow = 22; // 19 J + r + rho0 + valid
+constexpr int kRowStride = 24; // 19 J + r + rho0 + valid + 2 pad: 192-byte rows, 16-byte aligned groups of 2
 
 // Grid: (C, n_pairs) with the C CTAs of a pair forming ONE thread-block cluster (C = 1, 2, 4 or 8).
-// CTA c handles residual tiles c, c + C, ...; thread e keeps its reduction entry in a register across
-// tiles; the CTAs then exchange their 212 partial sums through distributed shared memory and rank 0
-// adds them in rank order — no global round trip, no atomics, a fixed summation order.
+// CTA c handles residual tiles c, c + C, ... Reduction = a register-tiled SYRK out of shared memory:
+// with v = [J(19) | r], G = sum v v^T is split into 5 x 5 blocks of 4 x 4; thread (slice s, block T) keeps
+// the 16 entries of one upper block in registers and walks the 16 rows s, s+16, ... of the tile with four
+// 16-byte shared-memory loads per row (0.25 loads per FMA instead of 2). The 16 slice partials are summed
+// in slice order, the CTAs then exchange their 212 sums through distributed shared memory and rank 0 adds
+// them in rank order: no global round trip, no atomics, a fixed summation order (bit-deterministic).
 __global__ void __launch_bounds__(kFactorBlock)
 factor_kernel(const __grid_constant__ FactorParams P, const float *__restrict__ points, int stride4,
               double *__restrict__ r_out, double *__restrict__ J_out, uint8_t *__restrict__ valid_out,
               double *__restrict__ out_red) {
-    __shared__ double rows[kFactorBlock][kRow + 1]; // +1: odd stride, conflict-free column reads
-    __shared__ double s_red[kRedSize];
+    extern __shared__ __align__(16) double smem[];
+    double (*rows)[kRowStride] = reinterpret_cast<double (*)[kRowStride]>(smem);          // [256][24]
+    double *s_red              = smem + kFactorBlock * kRowStride;                         // [kRedSize]
     cg::cluster_group cluster = cg::this_cluster();
     const int pair       = blockIdx.y;
     const FactorPair &pr = P.pair[pair];
     const PairConst &pc  = pr.pc;
-    const int e          = threadIdx.x;
-    int ca = 0, cb = -1;
-    double sign = 1.0;
-    if (e < 190) { ca = c_tri_a[e]; cb = c_tri_b[e]; }
-    else if (e < 209) { ca = e - 190; cb = 19; sign = -1.0; }   // b = -J^T r
-    else if (e == 209) { ca = 20; cb = -1; }                     // sum rho
-    else if (e == 210) { ca = 19; cb = 19; }                     // sum r'^2
-    else { ca = 21; cb = -1; }                                   // count
-    // four interleaved partial sums shorten the dependent DFMA chain 4x; they are combined in a fixed order
-    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+    const int tid        = threadIdx.x;
+    const int slice = tid >> 4, T = tid & 15;     // 16 row slices x 16 blocks (15 upper 4x4 blocks of G + 1 scalar block)
+    int bi = 0, bj = 0;                           // block coordinates (bi <= bj) of upper block T
+    {
+        int t = T;
+#pragma unroll
+        for (int i = 0; i < 5; i++) {
+            int len = 5 - i;
+            if (t >= 0 && t < len) { bi = i; bj = i + t; t = -1; }
+            else if (t >= len) t -= len;
+        }
+    }
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
 
     for (int tile = blockIdx.x; tile * kFactorBlock < P.q; tile += gridDim.x) {
         const int k = tile * kFactorBlock + threadIdx.x;
@@ -96,38 +104,84 @@ factor_kernel(const __grid_constant__ FactorParams P, const float *__restrict__ 
         rows[threadIdx.x][19] = r;
         rows[threadIdx.x][20] = rho0;
         rows[threadIdx.x][21] = valid ? 1.0 : 0.0;
+        rows[threadIdx.x][22] = 0.0;
+        rows[threadIdx.x][23] = 0.0;
         __syncthreads();
-        if (e < kRedSize) {
-            if (cb >= 0) {
+        if (T < 15) {
 #pragma unroll 4
-                for (int i = 0; i < kFactorBlock; i += 4) {
-                    acc0 += rows[i][ca] * rows[i][cb];
-                    acc1 += rows[i + 1][ca] * rows[i + 1][cb];
-                    acc2 += rows[i + 2][ca] * rows[i + 2][cb];
-                    acc3 += rows[i + 3][ca] * rows[i + 3][cb];
-                }
-            } else {
+            for (int kk = 0; kk < 16; kk++) {
+                const double2 *row = reinterpret_cast<const double2 *>(rows[slice + 16 * kk]);
+                double2 a01 = row[2 * bi], a23 = row[2 * bi + 1], b01 = row[2 * bj], b23 = row[2 * bj + 1];
+                const double av[4] = {a01.x, a01.y, a23.x, a23.y}, bv[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int b = 0; b < 4; b++) acc[a][b] += av[a] * bv[b];
+            }
+        } else { // scalar block: sum rho (entry 0) and the residual count (entry 1)
 #pragma unroll 4
-                for (int i = 0; i < kFactorBlock; i += 4) {
-                    acc0 += rows[i][ca];
-                    acc1 += rows[i + 1][ca];
-                    acc2 += rows[i + 2][ca];
-                    acc3 += rows[i + 3][ca];
-                }
+            for (int kk = 0; kk < 16; kk++) {
+                acc[0][0] += rows[slice + 16 * kk][20];
+                acc[0][1] += rows[slice + 16 * kk][21];
             }
         }
         __syncthreads();
     }
     if (out_red == nullptr) return;
-    if (e < kRedSize) s_red[e] = sign * ((acc0 + acc1) + (acc2 + acc3));
+    // slice partials -> shared memory (the row buffer is free now): part[slice][T][16]
+    double *part = smem;
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) part[(slice * 16 + T) * 16 + 4 * a + b] = acc[a][b];
+    __syncthreads();
+    {
+        // thread (T, q) sums entry q of block T over the 16 slices in slice order and files it under its
+        // place in the 212-vector [190 upper-triangle H | 19 b | sum rho | sum r'^2 | count]
+        const int Tq = tid >> 4, q = tid & 15;
+        double sum = 0.0;
+#pragma unroll
+        for (int s2 = 0; s2 < 16; s2++) sum += part[(s2 * 16 + Tq) * 16 + q];
+        int ti = 0, tj = 0;
+        {
+            int t = Tq;
+#pragma unroll
+            for (int i = 0; i < 5; i++) {
+                int len = 5 - i;
+                if (t >= 0 && t < len) { ti = i; tj = i + t; t = -1; }
+                else if (t >= len) t -= len;
+            }
+        }
+        int e = -1;
+        double sign = 1.0;
+        if (Tq < 15) {
+            const int ra = 4 * ti + (q >> 2), cb = 4 * tj + (q & 3);
+            if (ra < 19 && cb < 19) {
+                if (ra <= cb) e = ra * 19 - (ra * (ra - 1)) / 2 + (cb - ra);          // upper triangle of H
+            } else if (ra < 19 && cb == 19) {
+                e    = 190 + ra;                                                     // b = -J^T r
+                sign = -1.0;
+            } else if (ra == 19 && cb == 19) {
+                e = 210;                                                             // sum r'^2
+            }
+        } else if (q == 0) {
+            e = 209;                                                                 // sum rho
+        } else if (q == 1) {
+            e = 211;                                                                 // count
+        }
+        __syncthreads(); // everyone has read `part` before s_red (which lies behind the row buffer) is written
+        if (e >= 0) s_red[e] = sign * sum;
+    }
     cluster.sync();
-    if (cluster.block_rank() == 0 && e < kRedSize) {
+    if (cluster.block_rank() == 0 && tid < kRedSize) {
         double total = 0.0;
-        for (unsigned rk = 0; rk < cluster.num_blocks(); rk++) total += cluster.map_shared_rank(s_red, rk)[e];
-        out_red[(size_t) pair * kRedSize + e] = total;
+        for (unsigned rk = 0; rk < cluster.num_blocks(); rk++) total += cluster.map_shared_rank(s_red, rk)[tid];
+        out_red[(size_t) pair * kRedSize + tid] = total;
     }
     cluster.sync(); // keep every CTA's shared memory alive until rank 0 has read it
 }
+
+constexpr size_t kFactorSmem = (size_t) (kFactorBlock * kRowStride + kRedSize + 4) * sizeof(double);
 
 __global__ void __launch_bounds__(256)
 chi2_kernel(const __grid_constant__ FactorParams P, const float *__restrict__ points, int stride4, double threshold,
@@ -152,24 +206,15 @@ chi2_kernel(const __grid_constant__ FactorParams P, const float *__restrict__ po
     if (threadIdx.x == 0 && c) atomicAdd(n_outliers + pair, c);
 }
 
-bool g_tri_init[64] = {false};
+bool g_factor_init[64] = {false};
 
-void init_tri() {
+void init_factor() {
     int dev = 0;
     cudaGetDevice(&dev);
     dev &= 63;
-    if (g_tri_init[dev]) return;
-    unsigned char a[190], b[190];
-    int e = 0;
-    for (int i = 0; i < 19; i++)
-        for (int j = i; j < 19; j++) {
-            a[e] = (unsigned char) i;
-            b[e] = (unsigned char) j;
-            e++;
-        }
-    cudaMemcpyToSymbol(c_tri_a, a, sizeof(a));
-    cudaMemcpyToSymbol(c_tri_b, b, sizeof(b));
-    g_tri_init[dev] = true;
+    if (g_factor_init[dev]) return;
+    cudaFuncSetAttribute(factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kFactorSmem);
+    g_factor_init[dev] = true;
 }
 
 } // namespace
@@ -177,7 +222,7 @@ void init_tri() {
 void launch_factor_eval(cudaStream_t s, FactorParams &p, const float *points, int stride4, double *r, double *J,
                         uint8_t *valid, double *out_red) {
     if (p.n_pairs <= 0 || p.q <= 0) return;
-    init_tri();
+    init_factor();
     for (int i = 0; i < p.n_pairs; i++) make_pair_const(p, p.pair[i], p.pair[i].pc);
     int tiles = (p.q + kFactorBlock - 1) / kFactorBlock;
     int C     = 1;
@@ -185,7 +230,7 @@ void launch_factor_eval(cudaStream_t s, FactorParams &p, const float *points, in
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim          = dim3(C, p.n_pairs);
     cfg.blockDim         = dim3(kFactorBlock);
-    cfg.dynamicSmemBytes = 0;
+    cfg.dynamicSmemBytes = kFactorSmem;
     cfg.stream           = s;
     cudaLaunchAttribute attr[1];
     attr[0].id               = cudaLaunchAttributeClusterDimension;
