@@ -416,29 +416,37 @@ seg_centroid_kernel(const float4 *__restrict__ in, const uint32_t *__restrict__ 
 }
 
 // ---- small clouds (n <= SMALL_CAP): the whole filter in ONE CTA ---------------------------------------
-// bbox -> keys -> bitonic sort of 64-bit (key << 32 | index) composites in shared memory (unique, so
-// the unstable network yields exactly the stable order) -> heads -> ordered centroid. Replaces 18
-// launch-latency-bound launches for the per-frame filter of ~2-3 k decimated points.
-constexpr int SMALL_CAP     = 8192;
+// bbox -> keys -> stable LSD radix sort (8-bit digits, only the passes the key width needs) entirely in
+// shared memory -> heads -> ordered centroid. Replaces 18 launch-latency-bound launches for the per-frame
+// filter of ~2-3 k decimated points. (A first version sorted 64-bit composites with a bitonic network:
+// 66 barrier rounds, ~3,000 instructions per warp, issue-bound on its one SM; the radix passes need ~1/4.)
+constexpr int SMALL_CAP     = 4096;
 constexpr int SMALL_THREADS = 1024;
+constexpr int SMALL_ROUNDS  = SMALL_CAP / SMALL_THREADS; // 32-item rounds per warp
+
+struct SmallSmem {
+    float4 pts[SMALL_CAP];
+    uint32_t key[2][SMALL_CAP];
+    uint16_t idx[2][SMALL_CAP];
+    uint16_t warp_hist[32][256];
+    uint32_t digit_base[256];
+    float mn[3][32], mx[3][32];
+    int bbox[6];
+    int ws[32];
+    int total;
+};
 
 __global__ void __launch_bounds__(SMALL_THREADS)
 vox_small_kernel(const float4 *__restrict__ in, int n, float inv, int *__restrict__ meta, float4 *__restrict__ out,
                  int *__restrict__ d_nout, int32_t *__restrict__ keys_out) {
-    extern __shared__ unsigned long long comp[]; // npad composites, then n staged points
-    __shared__ float s_mn[3][32], s_mx[3][32];
-    __shared__ int s_bbox[6];
-    __shared__ int s_ws[32];
-    __shared__ int s_total;
+    extern __shared__ __align__(16) unsigned char small_raw[];
+    SmallSmem &S = *reinterpret_cast<SmallSmem *>(small_raw);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    int npad = 32;
-    while (npad < n) npad <<= 1;
-    float4 *pts = reinterpret_cast<float4 *>(comp + npad); // points staged once, reused by keys and centroid
-    // 1. bounding box
+    // 1. stage the points, bounding box
     float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
     for (int i = tid; i < n; i += SMALL_THREADS) {
         float4 p = __ldg(in + i);
-        pts[i]   = p;
+        S.pts[i] = p;
         mn[0] = fminf(mn[0], p.x); mx[0] = fmaxf(mx[0], p.x);
         mn[1] = fminf(mn[1], p.y); mx[1] = fmaxf(mx[1], p.y);
         mn[2] = fminf(mn[2], p.z); mx[2] = fmaxf(mx[2], p.z);
@@ -450,103 +458,158 @@ vox_small_kernel(const float4 *__restrict__ in, int n, float inv, int *__restric
             mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
             mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
         }
-        if (lane == 0) { s_mn[a][wid] = mn[a]; s_mx[a][wid] = mx[a]; }
+        if (lane == 0) { S.mn[a][wid] = mn[a]; S.mx[a][wid] = mx[a]; }
     }
     __syncthreads();
     if (wid == 0) {
 #pragma unroll
         for (int a = 0; a < 3; a++) {
-            float v = s_mn[a][lane], u = s_mx[a][lane];
+            float v = S.mn[a][lane], u = S.mx[a][lane];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
                 u = fmaxf(u, __shfl_xor_sync(0xffffffffu, u, o));
             }
-            if (lane == 0) { s_bbox[a] = f2ord(v); s_bbox[3 + a] = f2ord(u); }
+            if (lane == 0) { S.bbox[a] = f2ord(v); S.bbox[3 + a] = f2ord(u); }
         }
     }
     __syncthreads();
-    Grid3 g = make_grid(s_bbox, inv);
+    Grid3 g = make_grid(S.bbox, inv);
     if (tid == 0) {
         meta[M_OVERFLOW] = g.overflow ? 1 : 0;
         meta[M_NBITS]    = g.nbits;
     }
-    if (g.overflow) {
+    if (g.overflow) { // PCL: "leaf size too small": the input cloud is returned unchanged
         for (int i = tid; i < n; i += SMALL_THREADS) {
-            out[i] = in[i];
+            out[i] = S.pts[i];
             if (keys_out) keys_out[i] = 0;
         }
         if (tid == 0) { *d_nout = n; meta[M_NOUT] = n; }
         return;
     }
-    // 2. keys -> composites
-    for (int i = tid; i < npad; i += SMALL_THREADS) {
-        unsigned long long c = 0xffffffffffffffffull;
-        if (i < n) {
-            float4 p = pts[i];
-            int i0   = (int) (floorf(__fmul_rn(p.x, inv)) - (float) g.min_b[0]);
-            int i1   = (int) (floorf(__fmul_rn(p.y, inv)) - (float) g.min_b[1]);
-            int i2   = (int) (floorf(__fmul_rn(p.z, inv)) - (float) g.min_b[2]);
-            int key  = i0 + i1 * g.mul1 + i2 * g.mul2;
-            if (keys_out) keys_out[i] = key;
-            c = ((unsigned long long) (uint32_t) key << 32) | (uint32_t) i;
-        }
-        comp[i] = c;
+    // 2. keys
+    for (int i = tid; i < n; i += SMALL_THREADS) {
+        float4 p = S.pts[i];
+        int i0   = (int) (floorf(__fmul_rn(p.x, inv)) - (float) g.min_b[0]);
+        int i1   = (int) (floorf(__fmul_rn(p.y, inv)) - (float) g.min_b[1]);
+        int i2   = (int) (floorf(__fmul_rn(p.z, inv)) - (float) g.min_b[2]);
+        int key  = i0 + i1 * g.mul1 + i2 * g.mul2;
+        if (keys_out) keys_out[i] = key;
+        S.key[0][i] = (uint32_t) key;
+        S.idx[0][i] = (uint16_t) i;
     }
-    __syncthreads();
-    // 3. bitonic sort, ascending
-    for (int k = 2; k <= npad; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = tid; t < (npad >> 1); t += SMALL_THREADS) {
-                int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                int hi = lo | j;
-                unsigned long long a = comp[lo], b = comp[hi];
-                bool up = (lo & k) == 0;
-                if ((a > b) == up) { comp[lo] = b; comp[hi] = a; }
+    // 3. stable LSD radix sort in shared memory. Warp w owns the contiguous chunk [w*C, (w+1)*C).
+    const int C       = ((n + SMALL_THREADS - 1) / SMALL_THREADS) * 32;
+    const int rounds  = C / 32;
+    const unsigned lt = (1u << lane) - 1u;
+    int cur = 0;
+    for (int shift = 0; shift < g.nbits; shift += 8) {
+        for (int i = tid; i < 32 * 256; i += SMALL_THREADS) (&S.warp_hist[0][0])[i] = 0;
+        __syncthreads();
+        uint32_t key[SMALL_ROUNDS];
+        uint16_t val[SMALL_ROUNDS], rank[SMALL_ROUNDS];
+#pragma unroll
+        for (int r = 0; r < SMALL_ROUNDS; r++) {
+            if (r < rounds) {
+                const int i      = wid * C + r * 32 + lane;
+                const bool valid = i < n;
+                key[r]           = valid ? S.key[cur][i] : 0xffffffffu;
+                val[r]           = valid ? S.idx[cur][i] : (uint16_t) 0;
+                const uint32_t d = (key[r] >> shift) & 255u;
+                const unsigned m = __match_any_sync(0xffffffffu, valid ? d : 256u + lane);
+                const uint16_t prev = S.warp_hist[wid][d];
+                __syncwarp();
+                const unsigned rk = __popc(m & lt);
+                if (valid && rk == 0) S.warp_hist[wid][d] = (uint16_t) (prev + __popc(m));
+                __syncwarp();
+                rank[r] = (uint16_t) (prev + rk);
             }
-            __syncthreads();
         }
+        __syncthreads();
+        // per digit: exclusive prefix over the 32 warps, digit totals
+        uint32_t tot = 0;
+        if (tid < 256) {
+#pragma unroll 8
+            for (int w = 0; w < 32; w++) {
+                uint16_t c           = S.warp_hist[w][tid];
+                S.warp_hist[w][tid]  = (uint16_t) tot;
+                tot += c;
+            }
+            // exclusive scan of the 256 digit totals (8 warps)
+            uint32_t incl = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += u;
+            }
+            if (lane == 31) S.ws[wid] = (int) incl;
+            tot = incl - tot; // exclusive within the warp
+        }
+        __syncthreads();
+        if (tid < 256) {
+            uint32_t base = 0;
+            for (int w = 0; w < wid; w++) base += (uint32_t) S.ws[w];
+            S.digit_base[tid] = base + tot;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < SMALL_ROUNDS; r++) {
+            if (r < rounds) {
+                const int i = wid * C + r * 32 + lane;
+                if (i < n) {
+                    const uint32_t d   = (key[r] >> shift) & 255u;
+                    const uint32_t dst = S.digit_base[d] + S.warp_hist[wid][d] + rank[r];
+                    S.key[cur ^ 1][dst] = key[r];
+                    S.idx[cur ^ 1][dst] = val[r];
+                }
+            }
+        }
+        __syncthreads();
+        cur ^= 1;
     }
+    const uint32_t *skey = S.key[cur];
+    const uint16_t *sidx = S.idx[cur];
     // 4. heads -> slots (blocked: thread t owns items [t*per, (t+1)*per))
-    const int per = (npad + SMALL_THREADS - 1) / SMALL_THREADS;
+    const int per = (n + SMALL_THREADS - 1) / SMALL_THREADS;
     const int lo  = tid * per, hi = min(n, lo + per);
     int c = 0;
-    for (int i = lo; i < hi; i++) c += (i == 0 || (comp[i] >> 32) != (comp[i - 1] >> 32)) ? 1 : 0;
+    for (int i = lo; i < hi; i++) c += (i == 0 || skey[i] != skey[i - 1]) ? 1 : 0;
     int incl = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         int v = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += v;
     }
-    if (lane == 31) s_ws[wid] = incl;
+    __syncthreads(); // S.ws is reused
+    if (lane == 31) S.ws[wid] = incl;
     __syncthreads();
     if (wid == 0) {
-        int w = s_ws[lane], wi = w;
+        int w = S.ws[lane], wi = w;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             int v = __shfl_up_sync(0xffffffffu, wi, o);
             if (lane >= o) wi += v;
         }
-        s_ws[lane] = wi - w;
-        if (lane == 31) s_total = wi;
+        S.ws[lane] = wi - w;
+        if (lane == 31) S.total = wi;
     }
     __syncthreads();
-    int slot = s_ws[wid] + incl - c;
+    int slot = S.ws[wid] + incl - c;
     // 5. ordered centroid: one thread per head, sequential fp32 adds in ascending index
     for (int i = lo; i < hi; i++) {
-        uint32_t key = (uint32_t) (comp[i] >> 32);
-        if (!(i == 0 || (uint32_t) (comp[i - 1] >> 32) != key)) continue;
+        const uint32_t key = skey[i];
+        if (!(i == 0 || skey[i - 1] != key)) continue;
         float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
         int e = i;
-        while (e < n && (uint32_t) (comp[e] >> 32) == key) {
-            float4 p = pts[(uint32_t) (comp[e] & 0xffffffffu)];
+        while (e < n && skey[e] == key) {
+            float4 p = S.pts[sidx[e]];
             sx += p.x; sy += p.y; sz += p.z; si += p.w;
             e++;
         }
         float cnt   = (float) (e - i);
         out[slot++] = make_float4(sx / cnt, sy / cnt, sz / cnt, si / cnt);
     }
-    if (tid == 0) { *d_nout = s_total; meta[M_NOUT] = s_total; }
+    if (tid == 0) { *d_nout = S.total; meta[M_NOUT] = S.total; }
 }
 
 } // namespace
@@ -585,13 +648,11 @@ int launch_voxel_downsample(cudaStream_t s, const VoxelWork &w, const float4 *in
         int dev = 0;
         cudaGetDevice(&dev);
         if (!attr_set[dev & 63]) {
-            cudaFuncSetAttribute(vox_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_CAP * 24);
+            cudaFuncSetAttribute(vox_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(SmallSmem));
             attr_set[dev & 63] = true;
         }
-        int npad = 32;
-        while (npad < n) npad <<= 1;
         ProfScope ps(prof, nm("one_cta"), s);
-        vox_small_kernel<<<1, SMALL_THREADS, (size_t) npad * 8 + (size_t) n * 16, s>>>(in, n, inv, w.meta, out, d_nout, keys_out);
+        vox_small_kernel<<<1, SMALL_THREADS, sizeof(SmallSmem), s>>>(in, n, inv, w.meta, out, d_nout, keys_out);
         if (launches) *launches += 1;
         return 0;
     }
