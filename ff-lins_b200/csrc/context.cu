@@ -126,6 +126,7 @@ struct fflins_ctx : public Profiler {
     // factor scratch
     double *d_red = nullptr;
     int *d_outliers = nullptr;
+    int *d_assoc_counts = nullptr; // [kMaxRefs][2]: PLANE / covered counts of one association launch
     // pinned host scratch
     unsigned char *h_pin = nullptr;
     size_t h_pin_cap = 0;
@@ -436,14 +437,16 @@ int frame_tail(fflins_ctx *ctx, Frame *f, int n, int ndec, fflins_frame_info *ou
     int rc;
     if ((rc = ensure_voxel(ctx, ndec))) return rc;
     int *d_ndown = ctx->d_counters + 1;
-    launch_voxel_downsample(s, ctx->vox, f->c[FFLINS_CLOUD_LIDAR_FULL].d, ndec, (float) ctx->cfg.downsample_size,
-                            f->c[FFLINS_CLOUD_LIDAR].d, d_ndown, nullptr, &ctx->launches, ctx->prof(), "voxel_frame");
     // the last kernel of the chain stores the two counts straight into a pinned host slot
     if ((int) ctx->pending.size() >= kSlots - 1 && (rc = resolve_pending(ctx))) return rc;
     const int slot = ctx->next_slot;
     ctx->next_slot = (ctx->next_slot + 1) % kSlots;
     int *h         = ctx->h_slots + 2 * slot;
-    {
+    VoxelTail tail{to12(f->pose), f->c[FFLINS_CLOUD_WORLD].d, h, ctx->d_counters};
+    int fused = launch_voxel_downsample(s, ctx->vox, f->c[FFLINS_CLOUD_LIDAR_FULL].d, ndec, (float) ctx->cfg.downsample_size,
+                                        f->c[FFLINS_CLOUD_LIDAR].d, d_ndown, nullptr, &ctx->launches, ctx->prof(),
+                                        "voxel_frame", &tail);
+    if (fused <= 0) { // large decimated cloud (or empty frame): separate projection kernel
         ProfScope ps(ctx->prof(), "project_world", s);
         launch_project(s, to12(f->pose), f->c[FFLINS_CLOUD_LIDAR].d, f->c[FFLINS_CLOUD_WORLD].d, ndec, d_ndown, h,
                        ctx->d_counters);
@@ -691,10 +694,10 @@ int run_associate(fflins_ctx *ctx, const std::vector<Frame *> &refs, Frame *cur,
         a.m           = r->c[FFLINS_CLOUD_MAP].n;
         a.T_ref_world = ref_world(r->pose);
         a.feat        = r->feat;
-        a.counts      = r->feat_counts;
+        a.counts      = ctx->d_assoc_counts + 2 * i;
         r->feat_q     = q;
-        CK(cudaMemsetAsync(r->feat_counts, 0, 2 * sizeof(int), s));
     }
+    CK(cudaMemsetAsync(ctx->d_assoc_counts, 0, kMaxRefs * 2 * sizeof(int), s));
     {
         ProfScope ps(ctx->prof(), "associate", s);
         launch_associate(s, P, cur->c[FFLINS_CLOUD_WORLD].d, cur->c[FFLINS_CLOUD_LIDAR].d);
@@ -702,8 +705,7 @@ int run_associate(fflins_ctx *ctx, const std::vector<Frame *> &refs, Frame *cur,
     }
     unsigned char *h = pin(ctx, 1024);
     if (!h) return fail(ctx, FFLINS_E_NOMEM, "pinned allocation failed");
-    for (size_t i = 0; i < refs.size(); i++)
-        CK(cudaMemcpyAsync(h + 8 * i, refs[i]->feat_counts, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h, ctx->d_assoc_counts, kMaxRefs * 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     for (size_t i = 0; i < refs.size(); i++) {
         int c[2];
@@ -826,7 +828,8 @@ int fflins_create(const fflins_config *cfg, int device, fflins_ctx **out) {
     ctx->d_red        = (double *) ctx->pool.alloc((size_t) kMaxRefs * kRedSize * sizeof(double));
     ctx->d_outliers   = (int *) ctx->pool.alloc(kMaxRefs * sizeof(int));
     ctx->d_map_count  = (int *) ctx->pool.alloc(64);
-    if (!ctx->d_frame_pose || !ctx->d_counters || !ctx->d_red || !ctx->d_outliers || !ctx->d_map_count) {
+    ctx->d_assoc_counts = (int *) ctx->pool.alloc(kMaxRefs * 2 * sizeof(int));
+    if (!ctx->d_frame_pose || !ctx->d_counters || !ctx->d_red || !ctx->d_outliers || !ctx->d_map_count || !ctx->d_assoc_counts) {
         fflins_destroy(ctx);
         return FFLINS_E_NOMEM;
     }

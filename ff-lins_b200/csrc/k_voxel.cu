@@ -438,7 +438,7 @@ struct SmallSmem {
 
 __global__ void __launch_bounds__(SMALL_THREADS)
 vox_small_kernel(const float4 *__restrict__ in, int n, float inv, int *__restrict__ meta, float4 *__restrict__ out,
-                 int *__restrict__ d_nout, int32_t *__restrict__ keys_out) {
+                 int *__restrict__ d_nout, int32_t *__restrict__ keys_out, bool has_tail, const __grid_constant__ VoxelTail tail) {
     extern __shared__ __align__(16) unsigned char small_raw[];
     SmallSmem &S = *reinterpret_cast<SmallSmem *>(small_raw);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -482,9 +482,14 @@ vox_small_kernel(const float4 *__restrict__ in, int n, float inv, int *__restric
     if (g.overflow) { // PCL: "leaf size too small": the input cloud is returned unchanged
         for (int i = tid; i < n; i += SMALL_THREADS) {
             out[i] = S.pts[i];
+            if (has_tail) tail.world[i] = project_rn(tail.T.R, tail.T.t, S.pts[i]);
             if (keys_out) keys_out[i] = 0;
         }
-        if (tid == 0) { *d_nout = n; meta[M_NOUT] = n; }
+        if (tid == 0) {
+            *d_nout = n;
+            meta[M_NOUT] = n;
+            if (has_tail) { tail.report[0] = tail.counters ? tail.counters[0] : 0; tail.report[1] = n; }
+        }
         return;
     }
     // 2. keys
@@ -606,10 +611,21 @@ vox_small_kernel(const float4 *__restrict__ in, int n, float inv, int *__restric
             sx += p.x; sy += p.y; sz += p.z; si += p.w;
             e++;
         }
-        float cnt   = (float) (e - i);
-        out[slot++] = make_float4(sx / cnt, sy / cnt, sz / cnt, si / cnt);
+        float cnt = (float) (e - i);
+        float4 c4 = make_float4(sx / cnt, sy / cnt, sz / cnt, si / cnt);
+        out[slot] = c4;
+        // fused tail: world projection of the centroid (pointcloud.cc:38-59), exactly rounded
+        if (has_tail) tail.world[slot] = project_rn(tail.T.R, tail.T.t, c4);
+        slot++;
     }
-    if (tid == 0) { *d_nout = S.total; meta[M_NOUT] = S.total; }
+    if (tid == 0) {
+        *d_nout = S.total;
+        meta[M_NOUT] = S.total;
+        if (has_tail) { // zero-copy result read-back (pinned host memory)
+            tail.report[0] = tail.counters ? tail.counters[0] : 0;
+            tail.report[1] = S.total;
+        }
+    }
 }
 
 } // namespace
@@ -631,7 +647,8 @@ size_t voxel_work_bytes(int cap, size_t *off) {
 }
 
 int launch_voxel_downsample(cudaStream_t s, const VoxelWork &w, const float4 *in, int n, float leaf, float4 *out,
-                            int *d_nout, int32_t *keys_out, int64_t *launches, Profiler *prof, const char *tag) {
+                            int *d_nout, int32_t *keys_out, int64_t *launches, Profiler *prof, const char *tag,
+                            const VoxelTail *tail) {
     if (n <= 0) {
         cudaMemsetAsync(d_nout, 0, sizeof(int), s);
         return 0;
@@ -652,9 +669,11 @@ int launch_voxel_downsample(cudaStream_t s, const VoxelWork &w, const float4 *in
             attr_set[dev & 63] = true;
         }
         ProfScope ps(prof, nm("one_cta"), s);
-        vox_small_kernel<<<1, SMALL_THREADS, sizeof(SmallSmem), s>>>(in, n, inv, w.meta, out, d_nout, keys_out);
+        VoxelTail none{};
+        vox_small_kernel<<<1, SMALL_THREADS, sizeof(SmallSmem), s>>>(in, n, inv, w.meta, out, d_nout, keys_out, tail != nullptr,
+                                                                     tail ? *tail : none);
         if (launches) *launches += 1;
-        return 0;
+        return tail ? 1 : 0;
     }
     int g = (n + 255) / 256;
     if (g > 148 * 8) g = 148 * 8;

@@ -66,8 +66,18 @@ struct VoxelWork {
 size_t voxel_work_bytes(int cap, size_t *offsets /*8*/);
 // out must hold n points; *d_nout (device int) receives the voxel count, d_flag receives 1 on the
 // PCL "leaf too small" overflow (output = input). keys_out optional (n).
+// Optional fused tail (single-CTA path only, n <= 4096): world[i] = T * out[i] and report[0..1] =
+// {counters[0], voxel count} stored to pinned host memory. Returns 1 when the tail was fused, 0 when the
+// caller still has to project, < 0 on error.
+struct VoxelTail {
+    Pose12 T;
+    float4 *world;
+    int *report;
+    const int *counters;
+};
 int launch_voxel_downsample(cudaStream_t s, const VoxelWork &w, const float4 *in, int n, float leaf, float4 *out,
-                            int *d_nout, int32_t *keys_out, int64_t *launches, Profiler *prof, const char *tag);
+                            int *d_nout, int32_t *keys_out, int64_t *launches, Profiler *prof, const char *tag,
+                            const VoxelTail *tail = nullptr);
 
 // ---- K4 keyframe hash insert (replaces ikd_Tree::build, lidar_map.cc:100-118) -------------------------
 // hkeys/hvals: fine hash (cell -> map index, one slot per point); ckeys/cmask: coarse occupancy hash
