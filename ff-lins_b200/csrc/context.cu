@@ -7,6 +7,11 @@
 #include "math_undistort.cuh"
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -94,7 +99,7 @@ struct fflins_ctx : public Profiler {
     std::deque<uint64_t> keyframes;
     Pool pool;
     std::string err;
-    int64_t launches = 0;
+    std::atomic<int64_t> launches{0};
     float cell_scale = 1.0f;
 
     // staging (device)
@@ -122,6 +127,15 @@ struct fflins_ctx : public Profiler {
     bool map_job_active = false;
     uint64_t map_job_key = 0;
     std::vector<Frame *> deferred_frames; // released while the map job may still read them
+    // The ~20 launches of a map job are issued by a helper thread (the reference, too, hands its per-keyframe
+    // tree work to a tbb::task_group, lidar_map.cc:121-125,137), so the fusion thread goes straight on to the
+    // association. The helper only issues CUDA calls with arguments prepared by the caller.
+    std::thread map_worker;
+    std::mutex map_mu;
+    std::condition_variable map_cv;
+    std::function<void()> map_task;   // pending job (empty = none)
+    bool map_issued = true;           // the helper has issued every launch of the last job
+    bool map_quit   = false;
     std::vector<void *> deferred_blocks;
     // factor scratch
     double *d_red = nullptr;
@@ -281,6 +295,11 @@ void free_frame(fflins_ctx *ctx, Frame *f);
 // outlive it. Called by everything that reads a map cloud, its size, or frees buffers the job may touch.
 int resolve_map(fflins_ctx *ctx) {
     if (!ctx->map_job_active) return FFLINS_OK;
+    {
+        // the helper thread must have recorded the completion event before we can wait on it
+        std::unique_lock<std::mutex> lk(ctx->map_mu);
+        ctx->map_cv.wait(lk, [ctx] { return ctx->map_issued; });
+    }
     CK(cudaEventSynchronize(ctx->ev_map_done));
     ctx->map_job_active = false;
     if (Frame *key = find_frame(ctx, ctx->map_job_key)) key->c[FFLINS_CLOUD_MAP].n = ctx->h_map_count[0];
@@ -443,9 +462,10 @@ int frame_tail(fflins_ctx *ctx, Frame *f, int n, int ndec, fflins_frame_info *ou
     ctx->next_slot = (ctx->next_slot + 1) % kSlots;
     int *h         = ctx->h_slots + 2 * slot;
     VoxelTail tail{to12(f->pose), f->c[FFLINS_CLOUD_WORLD].d, h, ctx->d_counters};
-    int fused = launch_voxel_downsample(s, ctx->vox, f->c[FFLINS_CLOUD_LIDAR_FULL].d, ndec, (float) ctx->cfg.downsample_size,
-                                        f->c[FFLINS_CLOUD_LIDAR].d, d_ndown, nullptr, &ctx->launches, ctx->prof(),
-                                        "voxel_frame", &tail);
+    int64_t nl = 0;
+    int fused  = launch_voxel_downsample(s, ctx->vox, f->c[FFLINS_CLOUD_LIDAR_FULL].d, ndec, (float) ctx->cfg.downsample_size,
+                                         f->c[FFLINS_CLOUD_LIDAR].d, d_ndown, nullptr, &nl, ctx->prof(), "voxel_frame", &tail);
+    ctx->launches += nl;
     if (fused <= 0) { // large decimated cloud (or empty frame): separate projection kernel
         ProfScope ps(ctx->prof(), "project_world", s);
         launch_project(s, to12(f->pose), f->c[FFLINS_CLOUD_LIDAR].d, f->c[FFLINS_CLOUD_WORLD].d, ndec, d_ndown, h,
@@ -850,6 +870,26 @@ int fflins_create(const fflins_config *cfg, int device, fflins_ctx **out) {
         fflins_destroy(ctx);
         return FFLINS_E_CUDA;
     }
+    if (!getenv("FFLINS_NO_HELPER_THREAD")) {
+        ctx->map_worker = std::thread([ctx, device] {
+            cudaSetDevice(device);
+            std::unique_lock<std::mutex> lk(ctx->map_mu);
+            while (true) {
+                ctx->map_cv.wait(lk, [ctx] { return ctx->map_quit || (bool) ctx->map_task; });
+                if (ctx->map_task) {
+                    std::function<void()> task = std::move(ctx->map_task);
+                    ctx->map_task              = nullptr;
+                    lk.unlock();
+                    task();
+                    lk.lock();
+                    ctx->map_issued = true;
+                    ctx->map_cv.notify_all();
+                } else if (ctx->map_quit) {
+                    return;
+                }
+            }
+        });
+    }
     *out = ctx;
     return FFLINS_OK;
 }
@@ -857,6 +897,14 @@ int fflins_create(const fflins_config *cfg, int device, fflins_ctx **out) {
 void fflins_destroy(fflins_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (ctx->map_worker.joinable()) {
+        {
+            std::lock_guard<std::mutex> lk(ctx->map_mu);
+            ctx->map_quit = true;
+            ctx->map_cv.notify_all();
+        }
+        ctx->map_worker.join();
+    }
     if (ctx->map_stream) cudaStreamSynchronize(ctx->map_stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
@@ -1204,8 +1252,9 @@ int fflins_voxel_downsample(fflins_ctx *ctx, const float *xyzi, int32_t n, doubl
         return fail(ctx, FFLINS_E_NOMEM, "device allocation failed");
     }
     cudaMemcpyAsync(d_in, xyzi, (size_t) n * 16, cudaMemcpyHostToDevice, s);
-    launch_voxel_downsample(s, ctx->vox, d_in, n, (float) leaf, d_out, ctx->d_counters + 2, d_keys, &ctx->launches,
-                            ctx->prof(), "voxel");
+    int64_t nl = 0;
+    launch_voxel_downsample(s, ctx->vox, d_in, n, (float) leaf, d_out, ctx->d_counters + 2, d_keys, &nl, ctx->prof(), "voxel");
+    ctx->launches += nl;
     int m = 0;
     cudaMemcpyAsync(&m, ctx->d_counters + 2, sizeof(int), cudaMemcpyDeviceToHost, s);
     if (keys) cudaMemcpyAsync(keys, d_keys, (size_t) n * 4, cudaMemcpyDeviceToHost, s);
@@ -1361,6 +1410,7 @@ int fflins_keyframe_merge(fflins_ctx *ctx, uint64_t key_id, const uint64_t *nonk
         map.cap = (int) (want / sizeof(float4));
     }
     int off = full.n;
+    std::vector<ProjectBatch> batches;
     for (int i0 = 0; i0 < n; i0 += kMaxRefs) {
         // relative pose non-keyframe -> keyframe (lidar_map.cc:198-199); the projected clouds are written
         // straight behind the keyframe's own points (the reference projects in place, then appends: :201-205),
@@ -1377,15 +1427,34 @@ int fflins_keyframe_merge(fflins_ctx *ctx, uint64_t key_id, const uint64_t *nonk
             B.dst[j] = full.d + off;
             off += B.n[j];
         }
-        ProfScope ps(ctx->prof(), "merge_project", ms);
-        launch_project_batch(ms, B);
-        ctx->launches++;
+        batches.push_back(B);
     }
     full.n = total;
-    launch_voxel_downsample(ms, ctx->vox_map, full.d, total, (float) ctx->cfg.downsample_size, map.d, ctx->d_map_count,
-                            nullptr, &ctx->launches, ctx->prof(), "voxel_map");
-    CK(cudaMemcpyAsync(ctx->h_map_count, ctx->d_map_count, sizeof(int), cudaMemcpyDeviceToHost, ms));
-    CK(cudaEventRecord(ctx->ev_map_done, ms));
+    // everything below only issues CUDA work on the map stream with the arguments prepared above
+    const float4 *in_ptr = full.d;
+    float4 *out_ptr      = map.d;
+    const bool profiling = ctx->prof_on;
+    auto issue = [ctx, ms, batches, in_ptr, out_ptr, total, profiling]() {
+        int64_t nl = 0;
+        for (const ProjectBatch &B : batches) {
+            ProfScope ps(profiling ? ctx : nullptr, "merge_project", ms);
+            launch_project_batch(ms, B);
+            nl++;
+        }
+        launch_voxel_downsample(ms, ctx->vox_map, in_ptr, total, (float) ctx->cfg.downsample_size, out_ptr, ctx->d_map_count,
+                                nullptr, &nl, profiling ? ctx : nullptr, "voxel_map");
+        cudaMemcpyAsync(ctx->h_map_count, ctx->d_map_count, sizeof(int), cudaMemcpyDeviceToHost, ms);
+        cudaEventRecord(ctx->ev_map_done, ms);
+        ctx->launches += nl;
+    };
+    if (out || profiling || !ctx->map_worker.joinable()) {
+        issue(); // synchronous call, profiling pass (the event list is not thread-safe) or no helper thread
+    } else {
+        std::lock_guard<std::mutex> lk(ctx->map_mu);
+        ctx->map_task   = issue;
+        ctx->map_issued = false;
+        ctx->map_cv.notify_all();
+    }
     ctx->map_job_active = true;
     ctx->map_job_key    = key_id;
     map.n               = 0;
@@ -1779,6 +1848,6 @@ int fflins_timer_stop(fflins_ctx *ctx, double *ms) {
     return FFLINS_OK;
 }
 
-int64_t fflins_launch_count(const fflins_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int64_t fflins_launch_count(const fflins_ctx *ctx) { return ctx ? ctx->launches.load() : 0; }
 
 } // extern "C"
