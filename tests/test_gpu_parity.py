@@ -300,13 +300,15 @@ def _build_window(ctx, oracle, seq, n_keys, frames_per_key, first_id=1000):
     return keys
 
 
-@pytest.fixture(scope="module")
-def window():
+@pytest.fixture(scope="module", params=["robot", "ouster64", "lili"])
+def window(request):
+    """A small sliding window per sensor config: robot (identity extrinsic), ouster64 (65 k points, 400 Hz
+    IMU, td = -0.12 s, lever arm), lili (Horizon pattern, lever arm)."""
     from fflins import api, synth
     from oracle import pyoracle
-    seq = synth.Sequence("robot")
+    seq = synth.Sequence(request.param)
     c = api.Context(api.default_config(point_filter_num=seq.filter_num))
-    keys = _build_window(c, pyoracle, seq, n_keys=4, frames_per_key=3)
+    keys = _build_window(c, pyoracle, seq, n_keys=4 if request.param == "robot" else 3, frames_per_key=3)
     yield c, seq, keys
     c.close()
 
@@ -499,7 +501,7 @@ def test_reproject_and_keyframe_window(window, oracle):
     is_key, st = c.keyframe_selection(keys[-1]["id"], 10.0, 9.9)
     assert not is_key and st[1] == 0 and st[2] < 1e-7
     is_key, st = c.keyframe_selection(keys[0]["id"], 10.0, 9.9)
-    assert is_key and st[1] > 0.4
+    assert is_key and (st[1] > 0.4 or st[2] > np.radians(10))
 
 
 # ---------------------------------------------------------------- committed golden fixtures
@@ -581,7 +583,8 @@ def test_full_size_at128_properties(oracle):
     for r in ids[:-1]:
         f = c.features(r)
         found = f["nn_idx"] >= 0
-        assert np.all(np.diff(np.where(found, f["nn_d2"], np.inf), axis=1)[found[:, 1:]] >= 0), "neighbours ascending"
+        d2 = np.where(found, f["nn_d2"], np.float32(3e38))
+        assert np.all(np.diff(d2, axis=1)[found[:, 1:]] >= 0), "neighbours ascending"
         assert np.all(f["nn_d2"][found] <= 25.0)
         assert np.all(f["covered"] == found.all(1)) and np.all(f["covered"][f["type"] == 0] == 1)
         assert np.allclose(np.linalg.norm(f["normal"][f["type"] == 0], axis=1), 1.0, atol=1e-12)
