@@ -41,7 +41,7 @@ struct Frame {
     bool hash_pending = false; // map still being built on the map stream: the hash is inserted at first use
     int pending_slot = -1; // >= 0: counts of the last frame_process still sit in pinned slot (asynchronous mode)
     // keyframe hash (K4)
-    unsigned long long *hkeys = nullptr, *ckeys = nullptr, *cmask = nullptr;
+    unsigned long long *hkeys = nullptr, *ckeys = nullptr, *cmask = nullptr, *skeys = nullptr, *smask = nullptr;
     int *hvals                = nullptr;
     int hcap                  = 0;
     // features stored on this (ref) frame, indexed by the cur frame's points
@@ -331,6 +331,8 @@ void free_frame(fflins_ctx *ctx, Frame *f) {
     ctx->pool.release(f->hvals);
     ctx->pool.release(f->ckeys);
     ctx->pool.release(f->cmask);
+    ctx->pool.release(f->skeys);
+    ctx->pool.release(f->smask);
     ctx->pool.release(f->feat.type);
     ctx->pool.release(f->feat.covered);
     ctx->pool.release(f->feat.outlier);
@@ -642,15 +644,19 @@ int build_hash(fflins_ctx *ctx, Frame *f) {
         ctx->pool.release(f->hvals);
         ctx->pool.release(f->ckeys);
         ctx->pool.release(f->cmask);
+        ctx->pool.release(f->skeys);
+        ctx->pool.release(f->smask);
         f->hkeys = (unsigned long long *) ctx->pool.alloc((size_t) hcap * 8);
         f->hvals = (int *) ctx->pool.alloc((size_t) hcap * 4);
         f->ckeys = (unsigned long long *) ctx->pool.alloc((size_t) hcap * 8);
         f->cmask = (unsigned long long *) ctx->pool.alloc((size_t) hcap * 8);
-        if (!f->hkeys || !f->hvals || !f->ckeys || !f->cmask) return fail(ctx, FFLINS_E_NOMEM, "device allocation failed");
+        f->skeys = (unsigned long long *) ctx->pool.alloc((size_t) hcap * 8);
+        f->smask = (unsigned long long *) ctx->pool.alloc((size_t) hcap * 8);
+        if (!f->hkeys || !f->hvals || !f->ckeys || !f->cmask || !f->skeys || !f->smask) return fail(ctx, FFLINS_E_NOMEM, "device allocation failed");
     }
     f->hcap = hcap;
     ProfScope ps(ctx->prof(), "hash_build", ctx->stream);
-    launch_hash_build(ctx->stream, m.d, m.n, 1.0f / search_cell(ctx), f->hkeys, f->hvals, f->ckeys, f->cmask, hcap);
+    launch_hash_build(ctx->stream, m.d, m.n, 1.0f / search_cell(ctx), f->hkeys, f->hvals, f->ckeys, f->cmask, f->skeys, f->smask, hcap);
     ctx->launches += (m.n > 0) ? 2 : 1;
     return FFLINS_OK;
 }
@@ -710,6 +716,8 @@ int run_associate(fflins_ctx *ctx, const std::vector<Frame *> &refs, Frame *cur,
         a.hvals       = r->hvals;
         a.ckeys       = r->ckeys;
         a.cmask       = r->cmask;
+        a.skeys       = r->skeys;
+        a.smask       = r->smask;
         a.hmask       = r->hcap - 1;
         a.m           = r->c[FFLINS_CLOUD_MAP].n;
         a.T_ref_world = ref_world(r->pose);
@@ -1334,6 +1342,8 @@ int fflins_knn5(fflins_ctx *ctx, const float *map_xyzi, int32_t m, const float *
     unsigned long long *hk = (unsigned long long *) ctx->pool.alloc((size_t) hcap * 8);
     unsigned long long *ck = (unsigned long long *) ctx->pool.alloc((size_t) hcap * 8);
     unsigned long long *cm = (unsigned long long *) ctx->pool.alloc((size_t) hcap * 8);
+    unsigned long long *sk = (unsigned long long *) ctx->pool.alloc((size_t) hcap * 8);
+    unsigned long long *sm = (unsigned long long *) ctx->pool.alloc((size_t) hcap * 8);
     int *hv        = (int *) ctx->pool.alloc((size_t) hcap * 4);
     int32_t *d_idx = (int32_t *) ctx->pool.alloc((size_t) q * 20);
     float *d_d2    = (float *) ctx->pool.alloc((size_t) q * 20);
@@ -1344,20 +1354,22 @@ int fflins_knn5(fflins_ctx *ctx, const float *map_xyzi, int32_t m, const float *
         ctx->pool.release(hk);
         ctx->pool.release(ck);
         ctx->pool.release(cm);
+        ctx->pool.release(sk);
+        ctx->pool.release(sm);
         ctx->pool.release(hv);
         ctx->pool.release(d_idx);
         ctx->pool.release(d_d2);
         ctx->pool.release(d_cnt);
     };
-    if (!d_map || !d_q || !hk || !ck || !cm || !hv || !d_idx || !d_d2 || !d_cnt) {
+    if (!d_map || !d_q || !hk || !ck || !cm || !sk || !sm || !hv || !d_idx || !d_d2 || !d_cnt) {
         cleanup();
         return fail(ctx, FFLINS_E_NOMEM, "device allocation failed");
     }
     if (m > 0) cudaMemcpyAsync(d_map, map_xyzi, (size_t) m * 16, cudaMemcpyHostToDevice, s);
     cudaMemcpyAsync(d_q, query_xyzi, (size_t) q * 16, cudaMemcpyHostToDevice, s);
     float cell = search_cell(ctx);
-    launch_hash_build(s, d_map, m, 1.0f / cell, hk, hv, ck, cm, hcap);
-    launch_knn5(s, d_map, hk, hv, ck, cm, hcap - 1, m, d_q, q, 1.0f / cell, cell, (int) std::ceil(max_dist / cell) + 1,
+    launch_hash_build(s, d_map, m, 1.0f / cell, hk, hv, ck, cm, sk, sm, hcap);
+    launch_knn5(s, d_map, hk, hv, ck, cm, sk, sm, hcap - 1, m, d_q, q, 1.0f / cell, cell, (int) std::ceil(max_dist / cell) + 1,
                 (float) (max_dist * max_dist), d_idx, d_d2, d_cnt);
     ctx->launches += 3;
     cudaMemcpyAsync(nn_idx, d_idx, (size_t) q * 20, cudaMemcpyDeviceToHost, s);

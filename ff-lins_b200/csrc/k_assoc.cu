@@ -49,17 +49,23 @@ __device__ __forceinline__ unsigned hash_cell(u64 k) {
 
 // ckeys/cmask: coarse occupancy hash. One entry per 4x4x4 block of fine cells; the 64-bit mask says
 // which of the 64 fine cells hold at least one map point.
-__global__ void hash_clear_kernel(u64 *__restrict__ hkeys, u64 *__restrict__ ckeys, u64 *__restrict__ cmask, int hcap) {
+// skeys/smask: the same one level up — one entry per 4x4x4 block of COARSE blocks (16^3 cells), the mask
+// says which coarse blocks are occupied. Lets the wide search stages enumerate occupied blocks only.
+__global__ void hash_clear_kernel(u64 *__restrict__ hkeys, u64 *__restrict__ ckeys, u64 *__restrict__ cmask,
+                                  u64 *__restrict__ skeys, u64 *__restrict__ smask, int hcap) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hcap; i += gridDim.x * blockDim.x) {
         hkeys[i] = kEmpty;
         ckeys[i] = kEmpty;
         cmask[i] = 0ull;
+        skeys[i] = kEmpty;
+        smask[i] = 0ull;
     }
 }
 
 // One slot per map point; points sharing a cell occupy consecutive probe positions with equal keys.
 __global__ void hash_insert_kernel(const float4 *__restrict__ map, int m, float inv_cell, u64 *__restrict__ hkeys,
-                                   int *__restrict__ hvals, u64 *__restrict__ ckeys, u64 *__restrict__ cmask, int hmask) {
+                                   int *__restrict__ hvals, u64 *__restrict__ ckeys, u64 *__restrict__ cmask,
+                                   u64 *__restrict__ skeys, u64 *__restrict__ smask, int hmask) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
         float4 p = __ldg(map + i);
         int ix = (int) floorf(p.x * inv_cell), iy = (int) floorf(p.y * inv_cell), iz = (int) floorf(p.z * inv_cell);
@@ -85,6 +91,18 @@ __global__ void hash_insert_kernel(const float4 *__restrict__ map, int m, float 
             }
             h = (h + 1) & hmask;
         }
+        // super occupancy: the 4x4x4 block of coarse blocks, bit of this coarse block
+        u64 sk   = pack_cell(ix >> 4, iy >> 4, iz >> 4);
+        int csub = ((ix >> 2) & 3) | (((iy >> 2) & 3) << 2) | (((iz >> 2) & 3) << 4);
+        h        = hash_cell(sk) & hmask;
+        while (true) {
+            u64 old = atomicCAS(skeys + h, kEmpty, sk);
+            if (old == kEmpty || old == sk) {
+                atomicOr(smask + h, 1ull << csub);
+                break;
+            }
+            h = (h + 1) & hmask;
+        }
     }
 }
 
@@ -104,6 +122,8 @@ struct HashView {
     const int *hvals;
     const u64 *ckeys;
     const u64 *cmask;
+    const u64 *skeys;
+    const u64 *smask;
     int hmask;
 };
 
@@ -159,6 +179,7 @@ __device__ __forceinline__ u64 cube_mask(int ax, int ay, int az, int r) {
 
 constexpr int kAssocWarps = 4;            // warps per CTA
 constexpr int kQueueCap   = 32 * 64;      // occupied fine cells of 32 coarse blocks
+constexpr int kCQueueCap  = 32 * 64;      // occupied coarse blocks of 32 super blocks
 
 // Warp-cooperative exact 5-NN on the two-level hash. best[] is warp-uniform on return (kInf = not found).
 //
@@ -169,68 +190,145 @@ constexpr int kQueueCap   = 32 * 64;      // occupied fine cells of 32 coarse bl
 // per lane — so the probes of a round are in flight together and the load is balanced no matter how
 // the points are distributed over the blocks. After a stage every unvisited map point is farther than
 // hi*cell, so the search stops as soon as d5 < (hi*cell - 1 mm)^2: the result is the exact 5-NN.
+__device__ __forceinline__ u64 lookup_mask(const u64 *__restrict__ keys, const u64 *__restrict__ masks, int hmask, u64 key) {
+    unsigned h = hash_cell(key) & hmask;
+    while (true) {
+        u64 k = __ldg(keys + h);
+        if (k == kEmpty) return 0ull;
+        if (k == key) return __ldg(masks + h);
+        h = (h + 1) & hmask;
+    }
+}
+
+// Chebyshev range [mn, mx] of the cells of a block of `size` cells per axis whose first cell sits at offset
+// (ax, ay, az) from the query cell.
+__device__ __forceinline__ void block_range(int ax, int ay, int az, int size, int &mn, int &mx) {
+    const int e = size - 1;
+    int mnx = max(0, max(ax, -(ax + e))), mny = max(0, max(ay, -(ay + e))), mnz = max(0, max(az, -(az + e)));
+    int mxx = max(abs(ax), abs(ax + e)), mxy = max(abs(ay), abs(ay + e)), mxz = max(abs(az), abs(az + e));
+    mn = max(mnx, max(mny, mnz));
+    mx = max(mxx, max(mxy, mxz));
+}
+
+constexpr int kSparseFrom = 8; // stages reaching this far enumerate occupied coarse blocks through the super masks
+
 __device__ __forceinline__ void warp_knn5(const HashView &H, float qx, float qy, float qz, float inv_cell, float cell,
-                                          int r_max, float max_d2, unsigned *__restrict__ queue, u64 best[5]) {
+                                          int r_max, float max_d2, unsigned *__restrict__ queue,
+                                          unsigned *__restrict__ cqueue, u64 best[5]) {
     const int lane = threadIdx.x & 31;
     const int cx = (int) floorf(qx * inv_cell), cy = (int) floorf(qy * inv_cell), cz = (int) floorf(qz * inv_cell);
     u64 a0 = kInf, a1 = kInf, a2 = kInf, a3 = kInf, a4 = kInf;
     int lo = -1, hi = 2; // stage (lo, hi]; the first stage includes the query's own cell (ch = 0)
+
+    // One round: every lane may bring one coarse block (first-cell offset ax, ay, az from the query cell; have =
+    // false for idle lanes). Cells of the block inside the stage go to the queue, the queue is drained 32 at a time.
+    auto round = [&](bool have, int ax, int ay, int az) {
+        u64 keep = 0ull;
+        if (have) {
+            u64 want = cube_mask(ax, ay, az, hi) & ~cube_mask(ax, ay, az, lo); // pure bit arithmetic
+            if (want) keep = lookup_mask(H.ckeys, H.cmask, H.hmask, pack_cell((ax + cx) >> 2, (ay + cy) >> 2, (az + cz) >> 2)) & want;
+        }
+        const int cnt = __popcll(keep);
+        int incl      = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int T = __shfl_sync(0xffffffffu, incl, 31);
+        if (T == 0) return;
+        int off = incl - cnt;
+        while (keep) {
+            int sub = __ffsll((long long) keep) - 1;
+            keep &= keep - 1;
+            int dx = ax + (sub & 3), dy = ay + ((sub >> 2) & 3), dz = az + (sub >> 4);
+            queue[off++] = (unsigned) (dx + 512) | ((unsigned) (dy + 512) << 10) | ((unsigned) (dz + 512) << 20);
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int k = lane; k < T; k += 32) {
+            unsigned e = queue[k];
+            int dx = (int) (e & 1023u) - 512, dy = (int) ((e >> 10) & 1023u) - 512, dz = (int) (e >> 20) - 512;
+            probe_cell(H, cx + dx, cy + dy, cz + dz, qx, qy, qz, max_d2, a0, a1, a2, a3, a4);
+        }
+        __syncwarp();
+    };
+
 #pragma unroll 1
     while (lo < r_max) {
         hi = min(hi, r_max);
-        const int lox = (cx - hi) >> 2, loy = (cy - hi) >> 2, loz = (cz - hi) >> 2;
-        const int nx = ((cx + hi) >> 2) - lox + 1, ny = ((cy + hi) >> 2) - loy + 1, nz = ((cz + hi) >> 2) - loz + 1;
-        const int total = nx * ny * nz;
+        if (hi < kSparseFrom) {
+            // near stages: dense enumeration of the (<= 27) coarse blocks around the query
+            const int lox = (cx - hi) >> 2, loy = (cy - hi) >> 2, loz = (cz - hi) >> 2;
+            const int nx = ((cx + hi) >> 2) - lox + 1, ny = ((cy + hi) >> 2) - loy + 1, nz = ((cz + hi) >> 2) - loz + 1;
+            const int total = nx * ny * nz;
 #pragma unroll 1
-        for (int t0 = 0; t0 < total; t0 += 32) {
-            const int t = t0 + lane;
-            u64 keep = 0ull;
-            int ax = 0, ay = 0, az = 0; // offsets of the block's first cell from the query cell
-            if (t < total) {
+            for (int t0 = 0; t0 < total; t0 += 32) {
+                const int t = t0 + lane;
                 int bz  = t / (nx * ny);
                 int rem = t - bz * (nx * ny);
                 int by  = rem / nx;
                 int bx  = rem - by * nx;
-                ax = (bx + lox) * 4 - cx;
-                ay = (by + loy) * 4 - cy;
-                az = (bz + loz) * 4 - cz;
-                // cells of this block that belong to the stage (lo, hi]: pure bit arithmetic
-                u64 want = cube_mask(ax, ay, az, hi) & ~cube_mask(ax, ay, az, lo);
-                if (want) {
-                    u64 ck     = pack_cell(bx + lox, by + loy, bz + loz);
-                    unsigned h = hash_cell(ck) & H.hmask;
-                    while (true) {
-                        u64 k = __ldg(H.ckeys + h);
-                        if (k == kEmpty) break;
-                        if (k == ck) { keep = __ldg(H.cmask + h) & want; break; }
-                        h = (h + 1) & H.hmask;
+                round(t < total, (bx + lox) * 4 - cx, (by + loy) * 4 - cy, (bz + loz) * 4 - cz);
+            }
+        } else {
+            // wide stages: the super masks list the occupied coarse blocks, empty space costs one probe per
+            // 16^3 cells. Pass 1: lanes fetch super masks and queue the occupied coarse blocks that intersect
+            // the stage. Pass 2: one coarse block per lane and round.
+            const int lox = (cx - hi) >> 4, loy = (cy - hi) >> 4, loz = (cz - hi) >> 4;
+            const int nx = ((cx + hi) >> 4) - lox + 1, ny = ((cy + hi) >> 4) - loy + 1, nz = ((cz + hi) >> 4) - loz + 1;
+            const int total = nx * ny * nz;
+#pragma unroll 1
+            for (int t0 = 0; t0 < total; t0 += 32) {
+                const int t = t0 + lane;
+                u64 keep    = 0ull;
+                int sx = 0, sy = 0, sz = 0; // offset of the super block's first cell from the query cell
+                if (t < total) {
+                    int bz  = t / (nx * ny);
+                    int rem = t - bz * (nx * ny);
+                    int by  = rem / nx;
+                    int bx  = rem - by * nx;
+                    sx = (bx + lox) * 16 - cx;
+                    sy = (by + loy) * 16 - cy;
+                    sz = (bz + loz) * 16 - cz;
+                    int mn, mx;
+                    block_range(sx, sy, sz, 16, mn, mx);
+                    if (mx > lo && mn <= hi) {
+                        u64 m = lookup_mask(H.skeys, H.smask, H.hmask, pack_cell(bx + lox, by + loy, bz + loz));
+                        while (m) { // keep the occupied coarse blocks that intersect the stage
+                            int sub = __ffsll((long long) m) - 1;
+                            m &= m - 1;
+                            int cmn, cmx;
+                            block_range(sx + 4 * (sub & 3), sy + 4 * ((sub >> 2) & 3), sz + 4 * (sub >> 4), 4, cmn, cmx);
+                            if (cmx > lo && cmn <= hi) keep |= 1ull << sub;
+                        }
                     }
                 }
-            }
-            const int cnt = __popcll(keep);
-            int incl = cnt;
+                const int cnt = __popcll(keep);
+                int incl      = cnt;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += v;
-            }
-            const int T = __shfl_sync(0xffffffffu, incl, 31);
-            if (T == 0) continue;
-            int off = incl - cnt;
-            while (keep) {
-                int sub = __ffsll((long long) keep) - 1;
-                keep &= keep - 1;
-                int dx = ax + (sub & 3), dy = ay + ((sub >> 2) & 3), dz = az + (sub >> 4);
-                queue[off++] = (unsigned) (dx + 512) | ((unsigned) (dy + 512) << 10) | ((unsigned) (dz + 512) << 20);
-            }
-            __syncwarp();
+                for (int o = 1; o < 32; o <<= 1) {
+                    int v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                const int Tc = __shfl_sync(0xffffffffu, incl, 31); // coarse blocks of these 32 super blocks (<= 2048)
+                if (Tc == 0) continue;
+                int off = incl - cnt;
+                while (keep) {
+                    int sub = __ffsll((long long) keep) - 1;
+                    keep &= keep - 1;
+                    int ax = sx + 4 * (sub & 3), ay = sy + 4 * ((sub >> 2) & 3), az = sz + 4 * (sub >> 4);
+                    cqueue[off++] = (unsigned) (ax + 512) | ((unsigned) (ay + 512) << 10) | ((unsigned) (az + 512) << 20);
+                }
+                __syncwarp();
 #pragma unroll 1
-            for (int k = lane; k < T; k += 32) {
-                unsigned e = queue[k];
-                int dx = (int) (e & 1023u) - 512, dy = (int) ((e >> 10) & 1023u) - 512, dz = (int) (e >> 20) - 512;
-                probe_cell(H, cx + dx, cy + dy, cz + dz, qx, qy, qz, max_d2, a0, a1, a2, a3, a4);
+                for (int k0 = 0; k0 < Tc; k0 += 32) {
+                    const int k = k0 + lane;
+                    unsigned e  = k < Tc ? cqueue[k] : 0u;
+                    round(k < Tc, (int) (e & 1023u) - 512, (int) ((e >> 10) & 1023u) - 512, (int) (e >> 20) - 512);
+                }
+                __syncwarp();
             }
-            __syncwarp();
         }
         warp_merge5(a0, a1, a2, a3, a4, best);
         if (best[4] != kInf) {
@@ -246,7 +344,9 @@ __device__ __forceinline__ void warp_knn5(const HashView &H, float qx, float qy,
 // K5a: one warp per (ref, query): exact 5-NN only. Writes nn_idx / nn_d2 (ascending, -1 padded).
 __global__ void __launch_bounds__(kAssocWarps * 32)
 associate_knn_kernel(const __grid_constant__ AssocParams P, const float4 *__restrict__ cur_world) {
-    __shared__ unsigned s_queue[kAssocWarps][kQueueCap];
+    extern __shared__ unsigned smem_q[]; // per warp: fine-cell queue, then coarse-block queue
+    unsigned *my_queue  = smem_q + (threadIdx.x >> 5) * (kQueueCap + kCQueueCap);
+    unsigned *my_cqueue = my_queue + kQueueCap;
     const int lane  = threadIdx.x & 31;
     const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (gwarp >= P.n_refs * P.q) return;
@@ -257,8 +357,8 @@ associate_knn_kernel(const __grid_constant__ AssocParams P, const float4 *__rest
     float4 rp   = project_rn(ref.T_ref_world.R, ref.T_ref_world.t, __ldg(cur_world + k));
     u64 best[5] = {kInf, kInf, kInf, kInf, kInf};
     if (ref.m > 0) {
-        HashView H{ref.map, ref.hkeys, ref.hvals, ref.ckeys, ref.cmask, ref.hmask};
-        warp_knn5(H, rp.x, rp.y, rp.z, P.inv_cell, P.cell, P.r_max, P.max_d2, s_queue[threadIdx.x >> 5], best);
+        HashView H{ref.map, ref.hkeys, ref.hvals, ref.ckeys, ref.cmask, ref.skeys, ref.smask, ref.hmask};
+        warp_knn5(H, rp.x, rp.y, rp.z, P.inv_cell, P.cell, P.r_max, P.max_d2, my_queue, my_cqueue, best);
     }
     if (lane < 5) {
         u64 b = best[0];
@@ -321,18 +421,21 @@ associate_plane_kernel(const __grid_constant__ AssocParams P, const float4 *__re
 
 __global__ void __launch_bounds__(kAssocWarps * 32)
 knn5_kernel(const float4 *__restrict__ map, const u64 *__restrict__ hkeys, const int *__restrict__ hvals,
-            const u64 *__restrict__ ckeys, const u64 *__restrict__ cmask, int hmask, int m,
+            const u64 *__restrict__ ckeys, const u64 *__restrict__ cmask, const u64 *__restrict__ skeys,
+            const u64 *__restrict__ smask, int hmask, int m,
             const float4 *__restrict__ query, int q, float inv_cell, float cell, int r_max, float max_d2,
             int32_t *__restrict__ nn_idx, float *__restrict__ nn_d2, int32_t *__restrict__ nn_count) {
-    __shared__ unsigned s_queue[kAssocWarps][kQueueCap];
+    extern __shared__ unsigned smem_q[];
+    unsigned *my_queue  = smem_q + (threadIdx.x >> 5) * (kQueueCap + kCQueueCap);
+    unsigned *my_cqueue = my_queue + kQueueCap;
     const int lane  = threadIdx.x & 31;
     const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (gwarp >= q) return;
     float4 qp   = __ldg(query + gwarp);
     u64 best[5] = {kInf, kInf, kInf, kInf, kInf};
     if (m > 0) {
-        HashView H{map, hkeys, hvals, ckeys, cmask, hmask};
-        warp_knn5(H, qp.x, qp.y, qp.z, inv_cell, cell, r_max, max_d2, s_queue[threadIdx.x >> 5], best);
+        HashView H{map, hkeys, hvals, ckeys, cmask, skeys, smask, hmask};
+        warp_knn5(H, qp.x, qp.y, qp.z, inv_cell, cell, r_max, max_d2, my_queue, my_cqueue, best);
     }
     int found = 0;
 #pragma unroll
@@ -366,17 +469,31 @@ __global__ void plane_estimation_kernel(const float4 *__restrict__ pts, int n, d
     ok[i] = r ? 1 : 0;
 }
 
+constexpr size_t kKnnSmem = (size_t) kAssocWarps * (kQueueCap + kCQueueCap) * sizeof(unsigned);
+
+void init_knn_smem() {
+    static bool done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (done[dev]) return;
+    cudaFuncSetAttribute(associate_knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kKnnSmem);
+    cudaFuncSetAttribute(knn5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kKnnSmem);
+    done[dev] = true;
+}
+
 } // namespace
 
 void launch_hash_build(cudaStream_t s, const float4 *map, int m, float inv_cell, unsigned long long *hkeys, int *hvals,
-                       unsigned long long *ckeys, unsigned long long *cmask, int hcap) {
+                       unsigned long long *ckeys, unsigned long long *cmask, unsigned long long *skeys,
+                       unsigned long long *smask, int hcap) {
     int g = (hcap + 255) / 256;
     if (g > 148 * 8) g = 148 * 8;
-    hash_clear_kernel<<<g, 256, 0, s>>>(hkeys, ckeys, cmask, hcap);
+    hash_clear_kernel<<<g, 256, 0, s>>>(hkeys, ckeys, cmask, skeys, smask, hcap);
     if (m > 0) {
         int gi = (m + 255) / 256;
         if (gi > 148 * 8) gi = 148 * 8;
-        hash_insert_kernel<<<gi, 256, 0, s>>>(map, m, inv_cell, hkeys, hvals, ckeys, cmask, hcap - 1);
+        hash_insert_kernel<<<gi, 256, 0, s>>>(map, m, inv_cell, hkeys, hvals, ckeys, cmask, skeys, smask, hcap - 1);
     }
 }
 
@@ -384,16 +501,19 @@ void launch_associate(cudaStream_t s, const AssocParams &p, const float4 *cur_wo
     long long warps = (long long) p.n_refs * p.q;
     if (warps <= 0) return;
     int grid = (int) ((warps + kAssocWarps - 1) / kAssocWarps);
-    associate_knn_kernel<<<grid, kAssocWarps * 32, 0, s>>>(p, cur_world);
+    init_knn_smem();
+    associate_knn_kernel<<<grid, kAssocWarps * 32, kKnnSmem, s>>>(p, cur_world);
     dim3 g2((p.q + 127) / 128, p.n_refs);
     associate_plane_kernel<<<g2, 128, 0, s>>>(p, cur_world, cur_lidar);
 }
 
 void launch_knn5(cudaStream_t s, const float4 *map, const unsigned long long *hkeys, const int *hvals,
-                 const unsigned long long *ckeys, const unsigned long long *cmask, int hmask, int m, const float4 *query, int q, float inv_cell, float cell, int r_max, float max_d2, int32_t *nn_idx,
+                 const unsigned long long *ckeys, const unsigned long long *cmask, const unsigned long long *skeys,
+                 const unsigned long long *smask, int hmask, int m, const float4 *query, int q, float inv_cell, float cell, int r_max, float max_d2, int32_t *nn_idx,
                  float *nn_d2, int32_t *nn_count) {
     if (q <= 0) return;
-    knn5_kernel<<<(q + kAssocWarps - 1) / kAssocWarps, kAssocWarps * 32, 0, s>>>(map, hkeys, hvals, ckeys, cmask, hmask, m, query, q, inv_cell, cell, r_max, max_d2, nn_idx,
+    init_knn_smem();
+    knn5_kernel<<<(q + kAssocWarps - 1) / kAssocWarps, kAssocWarps * 32, kKnnSmem, s>>>(map, hkeys, hvals, ckeys, cmask, skeys, smask, hmask, m, query, q, inv_cell, cell, r_max, max_d2, nn_idx,
                                             nn_d2, nn_count);
 }
 

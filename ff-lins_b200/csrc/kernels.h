@@ -83,7 +83,8 @@ int launch_voxel_downsample(cudaStream_t s, const VoxelWork &w, const float4 *in
 // hkeys/hvals: fine hash (cell -> map index, one slot per point); ckeys/cmask: coarse occupancy hash
 // (4x4x4 fine cells per entry, 64-bit mask). All four arrays have hcap entries.
 void launch_hash_build(cudaStream_t s, const float4 *map, int m, float inv_cell, unsigned long long *hkeys,
-                       int *hvals, unsigned long long *ckeys, unsigned long long *cmask, int hcap);
+                       int *hvals, unsigned long long *ckeys, unsigned long long *cmask, unsigned long long *skeys,
+                       unsigned long long *smask, int hcap);
 
 // ---- K5 association (lidar_map.cc:326-408, pointcloud.cc:61-93, ikd_Tree.cc:897-924) -------------------
 struct FeatureSoA {
@@ -101,6 +102,8 @@ struct AssocRef {
     const int *hvals;
     const unsigned long long *ckeys;
     const unsigned long long *cmask;
+    const unsigned long long *skeys; // super occupancy (4x4x4 coarse blocks per entry)
+    const unsigned long long *smask;
     int hmask;
     int m;
     Pose12 T_ref_world;
@@ -121,7 +124,8 @@ struct AssocParams {
 void launch_associate(cudaStream_t s, const AssocParams &p, const float4 *cur_world, const float4 *cur_lidar);
 // brute-force-free stand-alone 5-NN against a hash (fflins_knn5)
 void launch_knn5(cudaStream_t s, const float4 *map, const unsigned long long *hkeys, const int *hvals,
-                 const unsigned long long *ckeys, const unsigned long long *cmask, int hmask, int m, const float4 *query, int q, float inv_cell, float cell, int r_max, float max_d2,
+                 const unsigned long long *ckeys, const unsigned long long *cmask, const unsigned long long *skeys,
+                 const unsigned long long *smask, int hmask, int m, const float4 *query, int q, float inv_cell, float cell, int r_max, float max_d2,
                  int32_t *nn_idx, float *nn_d2, int32_t *nn_count);
 void launch_plane_estimation(cudaStream_t s, const float4 *pts, int n, double thr, double *unit, double *ninv,
                              double *dist, uint8_t *ok);

@@ -93,6 +93,7 @@ class CpuSession:
                                               td, flags=self.flags, threads=self.threads))
                 return out
             t0 = time.perf_counter()
+            ev = None
             for _ in range(self.n_eval[0]):
                 ev = evaluate()
             self._tick("factor_eval", t0)
