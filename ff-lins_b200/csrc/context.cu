@@ -41,8 +41,7 @@ struct Frame {
     bool hash_pending = false; // map still being built on the map stream: the hash is inserted at first use
     int pending_slot = -1; // >= 0: counts of the last frame_process still sit in pinned slot (asynchronous mode)
     // keyframe hash (K4)
-    unsigned long long *hkeys = nullptr, *ckeys = nullptr, *cmask = nullptr, *skeys = nullptr, *smask = nullptr;
-    int *hvals                = nullptr;
+    MapIndex index; // fine / coarse / super hash tables (hcap slots each)
     int hcap                  = 0;
     // features stored on this (ref) frame, indexed by the cur frame's points
     FeatureSoA feat;
@@ -327,12 +326,9 @@ int ensure_cloud(fflins_ctx *ctx, Cloud &c, int n, bool keep = false) {
 
 void free_frame(fflins_ctx *ctx, Frame *f) {
     for (auto &c : f->c) ctx->pool.release(c.d);
-    ctx->pool.release(f->hkeys);
-    ctx->pool.release(f->hvals);
-    ctx->pool.release(f->ckeys);
-    ctx->pool.release(f->cmask);
-    ctx->pool.release(f->skeys);
-    ctx->pool.release(f->smask);
+    ctx->pool.release(f->index.fine);
+    ctx->pool.release(f->index.coarse);
+    ctx->pool.release(f->index.super);
     ctx->pool.release(f->feat.type);
     ctx->pool.release(f->feat.covered);
     ctx->pool.release(f->feat.outlier);
@@ -640,23 +636,18 @@ int build_hash(fflins_ctx *ctx, Frame *f) {
     const Cloud &m = f->c[FFLINS_CLOUD_MAP];
     int hcap       = next_pow2(2 * std::max(m.n, 1));
     if (hcap > f->hcap) {
-        ctx->pool.release(f->hkeys);
-        ctx->pool.release(f->hvals);
-        ctx->pool.release(f->ckeys);
-        ctx->pool.release(f->cmask);
-        ctx->pool.release(f->skeys);
-        ctx->pool.release(f->smask);
-        f->hkeys = (unsigned long long *) ctx->pool.alloc((size_t) hcap * 8);
-        f->hvals = (int *) ctx->pool.alloc((size_t) hcap * 4);
-        f->ckeys = (unsigned long long *) ctx->pool.alloc((size_t) hcap * 8);
-        f->cmask = (unsigned long long *) ctx->pool.alloc((size_t) hcap * 8);
-        f->skeys = (unsigned long long *) ctx->pool.alloc((size_t) hcap * 8);
-        f->smask = (unsigned long long *) ctx->pool.alloc((size_t) hcap * 8);
-        if (!f->hkeys || !f->hvals || !f->ckeys || !f->cmask || !f->skeys || !f->smask) return fail(ctx, FFLINS_E_NOMEM, "device allocation failed");
+        ctx->pool.release(f->index.fine);
+        ctx->pool.release(f->index.coarse);
+        ctx->pool.release(f->index.super);
+        f->index.fine   = (FineSlot *) ctx->pool.alloc((size_t) hcap * sizeof(FineSlot));
+        f->index.coarse = (MaskSlot *) ctx->pool.alloc((size_t) hcap * sizeof(MaskSlot));
+        f->index.super  = (MaskSlot *) ctx->pool.alloc((size_t) hcap * sizeof(MaskSlot));
+        if (!f->index.fine || !f->index.coarse || !f->index.super) return fail(ctx, FFLINS_E_NOMEM, "device allocation failed");
     }
-    f->hcap = hcap;
+    f->hcap        = hcap;
+    f->index.hmask = hcap - 1;
     ProfScope ps(ctx->prof(), "hash_build", ctx->stream);
-    launch_hash_build(ctx->stream, m.d, m.n, 1.0f / search_cell(ctx), f->hkeys, f->hvals, f->ckeys, f->cmask, f->skeys, f->smask, hcap);
+    launch_hash_build(ctx->stream, m.d, m.n, 1.0f / search_cell(ctx), f->index);
     ctx->launches += (m.n > 0) ? 2 : 1;
     return FFLINS_OK;
 }
@@ -709,16 +700,10 @@ int run_associate(fflins_ctx *ctx, const std::vector<Frame *> &refs, Frame *cur,
             r->hash_pending = false;
         }
         if ((rc = ensure_features(ctx, r, q))) return rc;
-        if (!r->hkeys && r->c[FFLINS_CLOUD_MAP].n > 0) return fail(ctx, FFLINS_E_INVALID, "reference frame has no map index (fflins_keyframe_add not called)");
+        if (!r->index.fine && r->c[FFLINS_CLOUD_MAP].n > 0) return fail(ctx, FFLINS_E_INVALID, "reference frame has no map index (fflins_keyframe_add not called)");
         AssocRef &a   = P.ref[i];
         a.map         = r->c[FFLINS_CLOUD_MAP].d;
-        a.hkeys       = r->hkeys;
-        a.hvals       = r->hvals;
-        a.ckeys       = r->ckeys;
-        a.cmask       = r->cmask;
-        a.skeys       = r->skeys;
-        a.smask       = r->smask;
-        a.hmask       = r->hcap - 1;
+        a.index       = r->index;
         a.m           = r->c[FFLINS_CLOUD_MAP].n;
         a.T_ref_world = ref_world(r->pose);
         a.feat        = r->feat;
@@ -1339,37 +1324,33 @@ int fflins_knn5(fflins_ctx *ctx, const float *map_xyzi, int32_t m, const float *
     int hcap       = next_pow2(2 * std::max(m, 1));
     float4 *d_map  = (float4 *) ctx->pool.alloc((size_t) std::max(m, 1) * 16);
     float4 *d_q    = (float4 *) ctx->pool.alloc((size_t) q * 16);
-    unsigned long long *hk = (unsigned long long *) ctx->pool.alloc((size_t) hcap * 8);
-    unsigned long long *ck = (unsigned long long *) ctx->pool.alloc((size_t) hcap * 8);
-    unsigned long long *cm = (unsigned long long *) ctx->pool.alloc((size_t) hcap * 8);
-    unsigned long long *sk = (unsigned long long *) ctx->pool.alloc((size_t) hcap * 8);
-    unsigned long long *sm = (unsigned long long *) ctx->pool.alloc((size_t) hcap * 8);
-    int *hv        = (int *) ctx->pool.alloc((size_t) hcap * 4);
+    MapIndex X;
+    X.fine   = (FineSlot *) ctx->pool.alloc((size_t) hcap * sizeof(FineSlot));
+    X.coarse = (MaskSlot *) ctx->pool.alloc((size_t) hcap * sizeof(MaskSlot));
+    X.super  = (MaskSlot *) ctx->pool.alloc((size_t) hcap * sizeof(MaskSlot));
+    X.hmask  = hcap - 1;
     int32_t *d_idx = (int32_t *) ctx->pool.alloc((size_t) q * 20);
     float *d_d2    = (float *) ctx->pool.alloc((size_t) q * 20);
     int32_t *d_cnt = (int32_t *) ctx->pool.alloc((size_t) q * 4);
     auto cleanup = [&]() {
         ctx->pool.release(d_map);
         ctx->pool.release(d_q);
-        ctx->pool.release(hk);
-        ctx->pool.release(ck);
-        ctx->pool.release(cm);
-        ctx->pool.release(sk);
-        ctx->pool.release(sm);
-        ctx->pool.release(hv);
+        ctx->pool.release(X.fine);
+        ctx->pool.release(X.coarse);
+        ctx->pool.release(X.super);
         ctx->pool.release(d_idx);
         ctx->pool.release(d_d2);
         ctx->pool.release(d_cnt);
     };
-    if (!d_map || !d_q || !hk || !ck || !cm || !sk || !sm || !hv || !d_idx || !d_d2 || !d_cnt) {
+    if (!d_map || !d_q || !X.fine || !X.coarse || !X.super || !d_idx || !d_d2 || !d_cnt) {
         cleanup();
         return fail(ctx, FFLINS_E_NOMEM, "device allocation failed");
     }
     if (m > 0) cudaMemcpyAsync(d_map, map_xyzi, (size_t) m * 16, cudaMemcpyHostToDevice, s);
     cudaMemcpyAsync(d_q, query_xyzi, (size_t) q * 16, cudaMemcpyHostToDevice, s);
     float cell = search_cell(ctx);
-    launch_hash_build(s, d_map, m, 1.0f / cell, hk, hv, ck, cm, sk, sm, hcap);
-    launch_knn5(s, d_map, hk, hv, ck, cm, sk, sm, hcap - 1, m, d_q, q, 1.0f / cell, cell, (int) std::ceil(max_dist / cell) + 1,
+    launch_hash_build(s, d_map, m, 1.0f / cell, X);
+    launch_knn5(s, X, m, d_q, q, 1.0f / cell, cell, (int) std::ceil(max_dist / cell) + 1,
                 (float) (max_dist * max_dist), d_idx, d_d2, d_cnt);
     ctx->launches += 3;
     cudaMemcpyAsync(nn_idx, d_idx, (size_t) q * 20, cudaMemcpyDeviceToHost, s);
@@ -1570,7 +1551,7 @@ int fflins_associate_pair(fflins_ctx *ctx, uint64_t ref_id, uint64_t cur_id, int
     Frame *ref = find_frame(ctx, ref_id), *cur = find_frame(ctx, cur_id);
     if (!ref || !cur) return fail(ctx, FFLINS_E_NOTFOUND, "unknown frame");
     int rc;
-    if (!ref->hkeys || ref->hcap < next_pow2(2 * std::max(ref->c[FFLINS_CLOUD_MAP].n, 1)))
+    if (!ref->index.fine || ref->hcap < next_pow2(2 * std::max(ref->c[FFLINS_CLOUD_MAP].n, 1)))
         if ((rc = build_hash(ctx, ref))) return rc;
     int32_t nf[kMaxRefs] = {0}, nc[kMaxRefs] = {0};
     std::vector<Frame *> refs{ref};

@@ -47,62 +47,52 @@ __device__ __forceinline__ unsigned hash_cell(u64 k) {
     return (unsigned) k;
 }
 
-// ckeys/cmask: coarse occupancy hash. One entry per 4x4x4 block of fine cells; the 64-bit mask says
-// which of the 64 fine cells hold at least one map point.
-// skeys/smask: the same one level up — one entry per 4x4x4 block of COARSE blocks (16^3 cells), the mask
-// says which coarse blocks are occupied. Lets the wide search stages enumerate occupied blocks only.
-__global__ void hash_clear_kernel(u64 *__restrict__ hkeys, u64 *__restrict__ ckeys, u64 *__restrict__ cmask,
-                                  u64 *__restrict__ skeys, u64 *__restrict__ smask, int hcap) {
+__global__ void hash_clear_kernel(MapIndex X) {
+    const int hcap = X.hmask + 1;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hcap; i += gridDim.x * blockDim.x) {
-        hkeys[i] = kEmpty;
-        ckeys[i] = kEmpty;
-        cmask[i] = 0ull;
-        skeys[i] = kEmpty;
-        smask[i] = 0ull;
+        X.fine[i].key    = kEmpty;
+        X.coarse[i].key  = kEmpty;
+        X.coarse[i].mask = 0ull;
+        X.super[i].key   = kEmpty;
+        X.super[i].mask  = 0ull;
     }
 }
 
-// One slot per map point; points sharing a cell occupy consecutive probe positions with equal keys.
-__global__ void hash_insert_kernel(const float4 *__restrict__ map, int m, float inv_cell, u64 *__restrict__ hkeys,
-                                   int *__restrict__ hvals, u64 *__restrict__ ckeys, u64 *__restrict__ cmask,
-                                   u64 *__restrict__ skeys, u64 *__restrict__ smask, int hmask) {
+__device__ __forceinline__ void mask_insert(MaskSlot *__restrict__ tab, int hmask, u64 key, int bit) {
+    unsigned h = hash_cell(key) & hmask;
+    while (true) {
+        u64 old = atomicCAS(&tab[h].key, kEmpty, key);
+        if (old == kEmpty || old == key) {
+            atomicOr(&tab[h].mask, 1ull << bit);
+            return;
+        }
+        h = (h + 1) & hmask;
+    }
+}
+
+// One fine slot per map point; points sharing a cell occupy consecutive probe positions with equal keys.
+__global__ void hash_insert_kernel(const float4 *__restrict__ map, int m, float inv_cell, MapIndex X) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
         float4 p = __ldg(map + i);
         int ix = (int) floorf(p.x * inv_cell), iy = (int) floorf(p.y * inv_cell), iz = (int) floorf(p.z * inv_cell);
         u64 key    = pack_cell(ix, iy, iz);
-        unsigned h = hash_cell(key) & hmask;
+        unsigned h = hash_cell(key) & X.hmask;
         while (true) {
-            u64 old = atomicCAS(hkeys + h, kEmpty, key);
+            u64 old = atomicCAS(&X.fine[h].key, kEmpty, key);
             if (old == kEmpty) {
-                hvals[h] = i;
+                X.fine[h].x   = p.x;
+                X.fine[h].y   = p.y;
+                X.fine[h].z   = p.z;
+                X.fine[h].idx = i;
                 break;
             }
-            h = (h + 1) & hmask;
+            h = (h + 1) & X.hmask;
         }
-        // coarse occupancy: insert-or-find the 4x4x4 block, set the bit of this fine cell
-        u64 ck  = pack_cell(ix >> 2, iy >> 2, iz >> 2);
-        int sub = (ix & 3) | ((iy & 3) << 2) | ((iz & 3) << 4);
-        h       = hash_cell(ck) & hmask;
-        while (true) {
-            u64 old = atomicCAS(ckeys + h, kEmpty, ck);
-            if (old == kEmpty || old == ck) {
-                atomicOr(cmask + h, 1ull << sub);
-                break;
-            }
-            h = (h + 1) & hmask;
-        }
+        // coarse occupancy: the 4x4x4 block of cells, bit of this cell
+        mask_insert(X.coarse, X.hmask, pack_cell(ix >> 2, iy >> 2, iz >> 2), (ix & 3) | ((iy & 3) << 2) | ((iz & 3) << 4));
         // super occupancy: the 4x4x4 block of coarse blocks, bit of this coarse block
-        u64 sk   = pack_cell(ix >> 4, iy >> 4, iz >> 4);
-        int csub = ((ix >> 2) & 3) | (((iy >> 2) & 3) << 2) | (((iz >> 2) & 3) << 4);
-        h        = hash_cell(sk) & hmask;
-        while (true) {
-            u64 old = atomicCAS(skeys + h, kEmpty, sk);
-            if (old == kEmpty || old == sk) {
-                atomicOr(smask + h, 1ull << csub);
-                break;
-            }
-            h = (h + 1) & hmask;
-        }
+        mask_insert(X.super, X.hmask, pack_cell(ix >> 4, iy >> 4, iz >> 4),
+                    ((ix >> 2) & 3) | (((iy >> 2) & 3) << 2) | (((iz >> 2) & 3) << 4));
     }
 }
 
@@ -116,33 +106,32 @@ __device__ __forceinline__ void ins5(u64 &a0, u64 &a1, u64 &a2, u64 &a3, u64 &a4
     }
 }
 
-struct HashView {
-    const float4 *map;
-    const u64 *hkeys;
-    const int *hvals;
-    const u64 *ckeys;
-    const u64 *cmask;
-    const u64 *skeys;
-    const u64 *smask;
-    int hmask;
-};
+typedef MapIndex HashView;
 
-// probe one fine cell, push every map point stored under it
+// Probe one fine cell and push every map point stored under it. A slot is two independent 16-byte loads
+// (key | x y, z idx | pad), so a hit needs ONE memory round trip; the next probe slot is requested before the
+// current one is examined.
 __device__ __forceinline__ void probe_cell(const HashView &H, int fx, int fy, int fz, float qx, float qy, float qz,
                                            float max_d2, u64 &a0, u64 &a1, u64 &a2, u64 &a3, u64 &a4) {
-    u64 key    = pack_cell(fx, fy, fz);
-    unsigned h = hash_cell(key) & H.hmask;
+    const u64 key = pack_cell(fx, fy, fz);
+    unsigned h    = hash_cell(key) & H.hmask;
+    const ulonglong2 *tab = reinterpret_cast<const ulonglong2 *>(H.fine);
+    ulonglong2 s0a = __ldg(tab + 2 * h), s0b = __ldg(tab + 2 * h + 1);
     while (true) {
-        u64 k = __ldg(H.hkeys + h);
-        if (k == kEmpty) break;
-        if (k == key) {
-            int idx  = __ldg(H.hvals + h);
-            float4 b = __ldg(H.map + idx);
-            float ex = qx - b.x, ey = qy - b.y, ez = qz - b.z;
+        const unsigned hn = (h + 1) & H.hmask;
+        ulonglong2 s1a = __ldg(tab + 2 * hn), s1b = __ldg(tab + 2 * hn + 1); // speculative next slot
+        if (s0a.x == kEmpty) break;
+        if (s0a.x == key) {
+            float bx = __uint_as_float((unsigned) (s0a.y & 0xffffffffull)), by = __uint_as_float((unsigned) (s0a.y >> 32));
+            float bz = __uint_as_float((unsigned) (s0b.x & 0xffffffffull));
+            unsigned idx = (unsigned) (s0b.x >> 32);
+            float ex = qx - bx, ey = qy - by, ez = qz - bz;
             float d2 = (ex * ex + ey * ey) + ez * ez; // ikd_Tree.cc:1427-1431 (no FMA: -fmad=false)
-            if (d2 <= max_d2) ins5(a0, a1, a2, a3, a4, ((u64) __float_as_uint(d2) << 32) | (unsigned) idx);
+            if (d2 <= max_d2) ins5(a0, a1, a2, a3, a4, ((u64) __float_as_uint(d2) << 32) | idx);
         }
-        h = (h + 1) & H.hmask;
+        s0a = s1a;
+        s0b = s1b;
+        h   = hn;
     }
 }
 
@@ -178,8 +167,9 @@ __device__ __forceinline__ u64 cube_mask(int ax, int ay, int az, int r) {
 }
 
 constexpr int kAssocWarps = 4;            // warps per CTA
-constexpr int kQueueCap   = 32 * 64;      // occupied fine cells of 32 coarse blocks
-constexpr int kCQueueCap  = 32 * 64;      // occupied coarse blocks of 32 super blocks
+constexpr int kLookupLanes = 16;           // lanes that fetch an occupancy mask per round (bounds the queues)
+constexpr int kQueueCap   = kLookupLanes * 64; // occupied fine cells of 16 coarse blocks
+constexpr int kCQueueCap  = kLookupLanes * 64; // occupied coarse blocks of 16 super blocks
 
 // Warp-cooperative exact 5-NN on the two-level hash. best[] is warp-uniform on return (kInf = not found).
 //
@@ -190,12 +180,13 @@ constexpr int kCQueueCap  = 32 * 64;      // occupied coarse blocks of 32 super 
 // per lane — so the probes of a round are in flight together and the load is balanced no matter how
 // the points are distributed over the blocks. After a stage every unvisited map point is farther than
 // hi*cell, so the search stops as soon as d5 < (hi*cell - 1 mm)^2: the result is the exact 5-NN.
-__device__ __forceinline__ u64 lookup_mask(const u64 *__restrict__ keys, const u64 *__restrict__ masks, int hmask, u64 key) {
+__device__ __forceinline__ u64 lookup_mask(const MaskSlot *__restrict__ tab, int hmask, u64 key) {
     unsigned h = hash_cell(key) & hmask;
+    const ulonglong2 *t = reinterpret_cast<const ulonglong2 *>(tab);
     while (true) {
-        u64 k = __ldg(keys + h);
-        if (k == kEmpty) return 0ull;
-        if (k == key) return __ldg(masks + h);
+        ulonglong2 s = __ldg(t + h); // key and mask in one 16-byte load
+        if (s.x == kEmpty) return 0ull;
+        if (s.x == key) return s.y;
         h = (h + 1) & hmask;
     }
 }
@@ -226,7 +217,7 @@ __device__ __forceinline__ void warp_knn5(const HashView &H, float qx, float qy,
         u64 keep = 0ull;
         if (have) {
             u64 want = cube_mask(ax, ay, az, hi) & ~cube_mask(ax, ay, az, lo); // pure bit arithmetic
-            if (want) keep = lookup_mask(H.ckeys, H.cmask, H.hmask, pack_cell((ax + cx) >> 2, (ay + cy) >> 2, (az + cz) >> 2)) & want;
+            if (want) keep = lookup_mask(H.coarse, H.hmask, pack_cell((ax + cx) >> 2, (ay + cy) >> 2, (az + cz) >> 2)) & want;
         }
         const int cnt = __popcll(keep);
         int incl      = cnt;
@@ -263,13 +254,13 @@ __device__ __forceinline__ void warp_knn5(const HashView &H, float qx, float qy,
             const int nx = ((cx + hi) >> 2) - lox + 1, ny = ((cy + hi) >> 2) - loy + 1, nz = ((cz + hi) >> 2) - loz + 1;
             const int total = nx * ny * nz;
 #pragma unroll 1
-            for (int t0 = 0; t0 < total; t0 += 32) {
+            for (int t0 = 0; t0 < total; t0 += kLookupLanes) {
                 const int t = t0 + lane;
                 int bz  = t / (nx * ny);
                 int rem = t - bz * (nx * ny);
                 int by  = rem / nx;
                 int bx  = rem - by * nx;
-                round(t < total, (bx + lox) * 4 - cx, (by + loy) * 4 - cy, (bz + loz) * 4 - cz);
+                round(lane < kLookupLanes && t < total, (bx + lox) * 4 - cx, (by + loy) * 4 - cy, (bz + loz) * 4 - cz);
             }
         } else {
             // wide stages: the super masks list the occupied coarse blocks, empty space costs one probe per
@@ -279,11 +270,11 @@ __device__ __forceinline__ void warp_knn5(const HashView &H, float qx, float qy,
             const int nx = ((cx + hi) >> 4) - lox + 1, ny = ((cy + hi) >> 4) - loy + 1, nz = ((cz + hi) >> 4) - loz + 1;
             const int total = nx * ny * nz;
 #pragma unroll 1
-            for (int t0 = 0; t0 < total; t0 += 32) {
+            for (int t0 = 0; t0 < total; t0 += kLookupLanes) {
                 const int t = t0 + lane;
                 u64 keep    = 0ull;
                 int sx = 0, sy = 0, sz = 0; // offset of the super block's first cell from the query cell
-                if (t < total) {
+                if (lane < kLookupLanes && t < total) {
                     int bz  = t / (nx * ny);
                     int rem = t - bz * (nx * ny);
                     int by  = rem / nx;
@@ -294,7 +285,7 @@ __device__ __forceinline__ void warp_knn5(const HashView &H, float qx, float qy,
                     int mn, mx;
                     block_range(sx, sy, sz, 16, mn, mx);
                     if (mx > lo && mn <= hi) {
-                        u64 m = lookup_mask(H.skeys, H.smask, H.hmask, pack_cell(bx + lox, by + loy, bz + loz));
+                        u64 m = lookup_mask(H.super, H.hmask, pack_cell(bx + lox, by + loy, bz + loz));
                         while (m) { // keep the occupied coarse blocks that intersect the stage
                             int sub = __ffsll((long long) m) - 1;
                             m &= m - 1;
@@ -311,7 +302,7 @@ __device__ __forceinline__ void warp_knn5(const HashView &H, float qx, float qy,
                     int v = __shfl_up_sync(0xffffffffu, incl, o);
                     if (lane >= o) incl += v;
                 }
-                const int Tc = __shfl_sync(0xffffffffu, incl, 31); // coarse blocks of these 32 super blocks (<= 2048)
+                const int Tc = __shfl_sync(0xffffffffu, incl, 31); // coarse blocks of these 16 super blocks (<= 1024)
                 if (Tc == 0) continue;
                 int off = incl - cnt;
                 while (keep) {
@@ -322,10 +313,11 @@ __device__ __forceinline__ void warp_knn5(const HashView &H, float qx, float qy,
                 }
                 __syncwarp();
 #pragma unroll 1
-                for (int k0 = 0; k0 < Tc; k0 += 32) {
+                for (int k0 = 0; k0 < Tc; k0 += kLookupLanes) {
                     const int k = k0 + lane;
-                    unsigned e  = k < Tc ? cqueue[k] : 0u;
-                    round(k < Tc, (int) (e & 1023u) - 512, (int) ((e >> 10) & 1023u) - 512, (int) (e >> 20) - 512);
+                    const bool have = lane < kLookupLanes && k < Tc;
+                    unsigned e      = have ? cqueue[k] : 0u;
+                    round(have, (int) (e & 1023u) - 512, (int) ((e >> 10) & 1023u) - 512, (int) (e >> 20) - 512);
                 }
                 __syncwarp();
             }
@@ -357,7 +349,7 @@ associate_knn_kernel(const __grid_constant__ AssocParams P, const float4 *__rest
     float4 rp   = project_rn(ref.T_ref_world.R, ref.T_ref_world.t, __ldg(cur_world + k));
     u64 best[5] = {kInf, kInf, kInf, kInf, kInf};
     if (ref.m > 0) {
-        HashView H{ref.map, ref.hkeys, ref.hvals, ref.ckeys, ref.cmask, ref.skeys, ref.smask, ref.hmask};
+        const HashView &H = ref.index;
         warp_knn5(H, rp.x, rp.y, rp.z, P.inv_cell, P.cell, P.r_max, P.max_d2, my_queue, my_cqueue, best);
     }
     if (lane < 5) {
@@ -420,10 +412,7 @@ associate_plane_kernel(const __grid_constant__ AssocParams P, const float4 *__re
 }
 
 __global__ void __launch_bounds__(kAssocWarps * 32)
-knn5_kernel(const float4 *__restrict__ map, const u64 *__restrict__ hkeys, const int *__restrict__ hvals,
-            const u64 *__restrict__ ckeys, const u64 *__restrict__ cmask, const u64 *__restrict__ skeys,
-            const u64 *__restrict__ smask, int hmask, int m,
-            const float4 *__restrict__ query, int q, float inv_cell, float cell, int r_max, float max_d2,
+knn5_kernel(MapIndex H, int m, const float4 *__restrict__ query, int q, float inv_cell, float cell, int r_max, float max_d2,
             int32_t *__restrict__ nn_idx, float *__restrict__ nn_d2, int32_t *__restrict__ nn_count) {
     extern __shared__ unsigned smem_q[];
     unsigned *my_queue  = smem_q + (threadIdx.x >> 5) * (kQueueCap + kCQueueCap);
@@ -434,7 +423,6 @@ knn5_kernel(const float4 *__restrict__ map, const u64 *__restrict__ hkeys, const
     float4 qp   = __ldg(query + gwarp);
     u64 best[5] = {kInf, kInf, kInf, kInf, kInf};
     if (m > 0) {
-        HashView H{map, hkeys, hvals, ckeys, cmask, skeys, smask, hmask};
         warp_knn5(H, qp.x, qp.y, qp.z, inv_cell, cell, r_max, max_d2, my_queue, my_cqueue, best);
     }
     int found = 0;
@@ -484,16 +472,15 @@ void init_knn_smem() {
 
 } // namespace
 
-void launch_hash_build(cudaStream_t s, const float4 *map, int m, float inv_cell, unsigned long long *hkeys, int *hvals,
-                       unsigned long long *ckeys, unsigned long long *cmask, unsigned long long *skeys,
-                       unsigned long long *smask, int hcap) {
+void launch_hash_build(cudaStream_t s, const float4 *map, int m, float inv_cell, MapIndex index) {
+    const int hcap = index.hmask + 1;
     int g = (hcap + 255) / 256;
     if (g > 148 * 8) g = 148 * 8;
-    hash_clear_kernel<<<g, 256, 0, s>>>(hkeys, ckeys, cmask, skeys, smask, hcap);
+    hash_clear_kernel<<<g, 256, 0, s>>>(index);
     if (m > 0) {
         int gi = (m + 255) / 256;
         if (gi > 148 * 8) gi = 148 * 8;
-        hash_insert_kernel<<<gi, 256, 0, s>>>(map, m, inv_cell, hkeys, hvals, ckeys, cmask, skeys, smask, hcap - 1);
+        hash_insert_kernel<<<gi, 256, 0, s>>>(map, m, inv_cell, index);
     }
 }
 
@@ -507,14 +494,12 @@ void launch_associate(cudaStream_t s, const AssocParams &p, const float4 *cur_wo
     associate_plane_kernel<<<g2, 128, 0, s>>>(p, cur_world, cur_lidar);
 }
 
-void launch_knn5(cudaStream_t s, const float4 *map, const unsigned long long *hkeys, const int *hvals,
-                 const unsigned long long *ckeys, const unsigned long long *cmask, const unsigned long long *skeys,
-                 const unsigned long long *smask, int hmask, int m, const float4 *query, int q, float inv_cell, float cell, int r_max, float max_d2, int32_t *nn_idx,
-                 float *nn_d2, int32_t *nn_count) {
+void launch_knn5(cudaStream_t s, MapIndex index, int m, const float4 *query, int q, float inv_cell, float cell, int r_max,
+                 float max_d2, int32_t *nn_idx, float *nn_d2, int32_t *nn_count) {
     if (q <= 0) return;
     init_knn_smem();
-    knn5_kernel<<<(q + kAssocWarps - 1) / kAssocWarps, kAssocWarps * 32, kKnnSmem, s>>>(map, hkeys, hvals, ckeys, cmask, skeys, smask, hmask, m, query, q, inv_cell, cell, r_max, max_d2, nn_idx,
-                                            nn_d2, nn_count);
+    knn5_kernel<<<(q + kAssocWarps - 1) / kAssocWarps, kAssocWarps * 32, kKnnSmem, s>>>(index, m, query, q, inv_cell, cell, r_max,
+                                                                                        max_d2, nn_idx, nn_d2, nn_count);
 }
 
 void launch_plane_estimation(cudaStream_t s, const float4 *pts, int n, double thr, double *unit, double *ninv,

@@ -80,11 +80,28 @@ int launch_voxel_downsample(cudaStream_t s, const VoxelWork &w, const float4 *in
                             const VoxelTail *tail = nullptr);
 
 // ---- K4 keyframe hash insert (replaces ikd_Tree::build, lidar_map.cc:100-118) -------------------------
-// hkeys/hvals: fine hash (cell -> map index, one slot per point); ckeys/cmask: coarse occupancy hash
-// (4x4x4 fine cells per entry, 64-bit mask). All four arrays have hcap entries.
-void launch_hash_build(cudaStream_t s, const float4 *map, int m, float inv_cell, unsigned long long *hkeys,
-                       int *hvals, unsigned long long *ckeys, unsigned long long *cmask, unsigned long long *skeys,
-                       unsigned long long *smask, int hcap);
+// Two-level (plus one) open-addressing index of a keyframe map, all tables with hmask + 1 slots:
+//   fine   : one 32-byte slot per map point {packed cell key, x, y, z, map index} - a probe that hits brings the
+//            point along in the same memory round trip (points sharing a cell sit in consecutive probe slots);
+//   coarse : {packed 4x4x4-cell block key, 64-bit occupancy mask of its cells};
+//   super  : {packed 4x4x4-coarse-block key, 64-bit occupancy mask of its coarse blocks}.
+struct alignas(32) FineSlot {
+    unsigned long long key;
+    float x, y, z;
+    int idx;
+    unsigned long long pad;
+};
+struct alignas(16) MaskSlot {
+    unsigned long long key;
+    unsigned long long mask;
+};
+struct MapIndex {
+    FineSlot *fine   = nullptr;
+    MaskSlot *coarse = nullptr;
+    MaskSlot *super  = nullptr;
+    int hmask        = 0;
+};
+void launch_hash_build(cudaStream_t s, const float4 *map, int m, float inv_cell, MapIndex index);
 
 // ---- K5 association (lidar_map.cc:326-408, pointcloud.cc:61-93, ikd_Tree.cc:897-924) -------------------
 struct FeatureSoA {
@@ -98,13 +115,7 @@ struct FeatureSoA {
 };
 struct AssocRef {
     const float4 *map;
-    const unsigned long long *hkeys;
-    const int *hvals;
-    const unsigned long long *ckeys;
-    const unsigned long long *cmask;
-    const unsigned long long *skeys; // super occupancy (4x4x4 coarse blocks per entry)
-    const unsigned long long *smask;
-    int hmask;
+    MapIndex index;
     int m;
     Pose12 T_ref_world;
     FeatureSoA feat;
@@ -123,10 +134,8 @@ struct AssocParams {
 };
 void launch_associate(cudaStream_t s, const AssocParams &p, const float4 *cur_world, const float4 *cur_lidar);
 // brute-force-free stand-alone 5-NN against a hash (fflins_knn5)
-void launch_knn5(cudaStream_t s, const float4 *map, const unsigned long long *hkeys, const int *hvals,
-                 const unsigned long long *ckeys, const unsigned long long *cmask, const unsigned long long *skeys,
-                 const unsigned long long *smask, int hmask, int m, const float4 *query, int q, float inv_cell, float cell, int r_max, float max_d2,
-                 int32_t *nn_idx, float *nn_d2, int32_t *nn_count);
+void launch_knn5(cudaStream_t s, MapIndex index, int m, const float4 *query, int q, float inv_cell, float cell, int r_max,
+                 float max_d2, int32_t *nn_idx, float *nn_d2, int32_t *nn_count);
 void launch_plane_estimation(cudaStream_t s, const float4 *pts, int n, double thr, double *unit, double *ninv,
                              double *dist, uint8_t *ok);
 
