@@ -109,10 +109,8 @@ struct fflins_ctx : public Profiler {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t stage_copied[3] = {nullptr, nullptr, nullptr}, stage_consumed[3] = {nullptr, nullptr, nullptr};
     int stage_next = 0, stage_cur = -1;
-    double *d_ins = nullptr; // t[w] p[3w] q[4w]
     int ins_cap = 0;
     double *d_tab = nullptr;
-    Pose12 *d_frame_pose = nullptr; // [2]
     int *d_counters = nullptr;      // [64]
     VoxelWork vox;
     void *vox_base = nullptr;
@@ -386,12 +384,10 @@ int stage_publish(fflins_ctx *ctx) {
 
 int ensure_ins(fflins_ctx *ctx, int w) {
     if (w <= ctx->ins_cap) return FFLINS_OK;
-    ctx->pool.release(ctx->d_ins);
     ctx->pool.release(ctx->d_tab);
     int cap    = std::max(w, 2048);
-    ctx->d_ins = (double *) ctx->pool.alloc((size_t) cap * 8 * sizeof(double));
-    ctx->d_tab = (double *) ctx->pool.alloc((size_t) cap * kRowSize * sizeof(double));
-    if (!ctx->d_ins || !ctx->d_tab) return fail(ctx, FFLINS_E_NOMEM, "device allocation failed");
+    ctx->d_tab = (double *) ctx->pool.alloc((size_t) cap * kRowSize * sizeof(double)); // interval rows (K1 prologue)
+    if (!ctx->d_tab) return fail(ctx, FFLINS_E_NOMEM, "device allocation failed");
     ctx->ins_cap = cap;
     return FFLINS_OK;
 }
@@ -836,13 +832,12 @@ int fflins_create(const fflins_config *cfg, int device, fflins_ctx **out) {
         delete ctx;
         return FFLINS_E_CUDA;
     }
-    ctx->d_frame_pose = (Pose12 *) ctx->pool.alloc(2 * sizeof(Pose12));
     ctx->d_counters   = (int *) ctx->pool.alloc(64 * sizeof(int));
     ctx->d_red        = (double *) ctx->pool.alloc((size_t) kMaxRefs * kRedSize * sizeof(double));
     ctx->d_outliers   = (int *) ctx->pool.alloc(kMaxRefs * sizeof(int));
     ctx->d_map_count  = (int *) ctx->pool.alloc(64);
     ctx->d_assoc_counts = (int *) ctx->pool.alloc(kMaxRefs * 2 * sizeof(int));
-    if (!ctx->d_frame_pose || !ctx->d_counters || !ctx->d_red || !ctx->d_outliers || !ctx->d_map_count || !ctx->d_assoc_counts) {
+    if (!ctx->d_counters || !ctx->d_red || !ctx->d_outliers || !ctx->d_map_count || !ctx->d_assoc_counts) {
         fflins_destroy(ctx);
         return FFLINS_E_NOMEM;
     }

@@ -136,17 +136,6 @@ project_kernel(Pose12 T, const float4 *__restrict__ src, float4 *__restrict__ ds
         dst[k] = project_rn(T.R, T.t, src[k]);
 }
 
-__global__ void __launch_bounds__(256)
-project_dev_kernel(const Pose12 *__restrict__ Tp, const float4 *__restrict__ src, float4 *__restrict__ dst, int n,
-                   const int *__restrict__ n_dev) {
-    __shared__ Pose12 T;
-    if (threadIdx.x < 12) reinterpret_cast<double *>(&T)[threadIdx.x] = reinterpret_cast<const double *>(Tp)[threadIdx.x];
-    __syncthreads();
-    if (n_dev) n = min(n, *n_dev);
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
-        dst[k] = project_rn(T.R, T.t, src[k]);
-}
-
 __global__ void __launch_bounds__(256) project_batch_kernel(const __grid_constant__ ProjectBatch B) {
     const int c = blockIdx.y;
     const int n = B.n[c];
@@ -199,11 +188,6 @@ void launch_project_batch(cudaStream_t s, const ProjectBatch &b) {
     if (b.count <= 0 || nmax <= 0) return;
     dim3 grid(grid_for(nmax, 256), b.count);
     project_batch_kernel<<<grid, 256, 0, s>>>(b);
-}
-
-void launch_project_dev(cudaStream_t s, const Pose12 *T_dev, const float4 *src, float4 *dst, int n, const int *n_dev) {
-    if (n <= 0) return;
-    project_dev_kernel<<<grid_for(n, 256), 256, 0, s>>>(T_dev, src, dst, n, n_dev);
 }
 
 } // namespace fflins

@@ -51,7 +51,6 @@ struct ProjectBatch {
     Pose12 T[kMaxRefs];
 };
 void launch_project_batch(cudaStream_t s, const ProjectBatch &b);
-void launch_project_dev(cudaStream_t s, const Pose12 *T_dev, const float4 *src, float4 *dst, int n, const int *n_dev);
 
 // ---- K2 voxel downsample (pcl::VoxelGrid) --------------------------------------
 struct VoxelWork {
