@@ -707,6 +707,11 @@ int run_associate(fflins_ctx *ctx, const std::vector<Frame *> &refs, Frame *cur,
         r->feat_q     = q;
     }
     CK(cudaMemsetAsync(ctx->d_assoc_counts, 0, kMaxRefs * 2 * sizeof(int), s));
+    long long *dbg = nullptr;
+    if (getenv("FFLINS_DEBUG_KNN")) {
+        dbg = (long long *) ctx->pool.alloc((size_t) P.n_refs * q * 8 + 8);
+        P.dbg_cycles = dbg;
+    }
     {
         ProfScope ps(ctx->prof(), "associate", s);
         launch_associate(s, P, cur->c[FFLINS_CLOUD_WORLD].d, cur->c[FFLINS_CLOUD_LIDAR].d);
@@ -716,6 +721,20 @@ int run_associate(fflins_ctx *ctx, const std::vector<Frame *> &refs, Frame *cur,
     if (!h) return fail(ctx, FFLINS_E_NOMEM, "pinned allocation failed");
     CK(cudaMemcpyAsync(h, ctx->d_assoc_counts, kMaxRefs * 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    if (dbg) {
+        std::vector<long long> cyc((size_t) P.n_refs * q);
+        cudaMemcpy(cyc.data(), dbg, cyc.size() * 8, cudaMemcpyDeviceToHost);
+        ctx->pool.release(dbg);
+        for (int r = 0; r < P.n_refs; r++) {
+            std::vector<long long> v(cyc.begin() + (size_t) r * q, cyc.begin() + (size_t) (r + 1) * q);
+            std::sort(v.begin(), v.end());
+            long long sum = 0;
+            for (auto x : v) sum += x;
+            if (!v.empty())
+                std::fprintf(stderr, "knn ref %d: cycles/warp min %lld p50 %lld p90 %lld p99 %lld max %lld mean %lld\n", r, v.front(),
+                             v[v.size() / 2], v[v.size() * 9 / 10], v[v.size() * 99 / 100], v.back(), sum / (long long) v.size());
+        }
+    }
     for (size_t i = 0; i < refs.size(); i++) {
         int c[2];
         std::memcpy(c, h + 8 * i, 8);

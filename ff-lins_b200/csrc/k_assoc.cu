@@ -96,14 +96,16 @@ __global__ void hash_insert_kernel(const float4 *__restrict__ map, int m, float 
     }
 }
 
-__device__ __forceinline__ void ins5(u64 &a0, u64 &a1, u64 &a2, u64 &a3, u64 &a4, u64 v) {
+__device__ __forceinline__ bool ins5(u64 &a0, u64 &a1, u64 &a2, u64 &a3, u64 &a4, u64 v) {
     if (v < a4) {
         a4 = v;
         if (a4 < a3) { u64 t = a3; a3 = a4; a4 = t; }
         if (a3 < a2) { u64 t = a2; a2 = a3; a3 = t; }
         if (a2 < a1) { u64 t = a1; a1 = a2; a2 = t; }
         if (a1 < a0) { u64 t = a0; a0 = a1; a1 = t; }
+        return true;
     }
+    return false;
 }
 
 typedef MapIndex HashView;
@@ -112,7 +114,7 @@ typedef MapIndex HashView;
 // (key | x y, z idx | pad), so a hit needs ONE memory round trip; the next probe slot is requested before the
 // current one is examined.
 __device__ __forceinline__ void probe_cell(const HashView &H, int fx, int fy, int fz, float qx, float qy, float qz,
-                                           float max_d2, u64 &a0, u64 &a1, u64 &a2, u64 &a3, u64 &a4) {
+                                           float max_d2, u64 &a0, u64 &a1, u64 &a2, u64 &a3, u64 &a4, bool &dirty) {
     const u64 key = pack_cell(fx, fy, fz);
     unsigned h    = hash_cell(key) & H.hmask;
     const ulonglong2 *tab = reinterpret_cast<const ulonglong2 *>(H.fine);
@@ -127,7 +129,7 @@ __device__ __forceinline__ void probe_cell(const HashView &H, int fx, int fy, in
             unsigned idx = (unsigned) (s0b.x >> 32);
             float ex = qx - bx, ey = qy - by, ez = qz - bz;
             float d2 = (ex * ex + ey * ey) + ez * ez; // ikd_Tree.cc:1427-1431 (no FMA: -fmad=false)
-            if (d2 <= max_d2) ins5(a0, a1, a2, a3, a4, ((u64) __float_as_uint(d2) << 32) | idx);
+            if (d2 <= max_d2) dirty |= ins5(a0, a1, a2, a3, a4, ((u64) __float_as_uint(d2) << 32) | idx);
         }
         s0a = s1a;
         s0b = s1b;
@@ -203,22 +205,85 @@ __device__ __forceinline__ void block_range(int ax, int ay, int az, int size, in
 
 constexpr int kSparseFrom = 8; // stages reaching this far enumerate occupied coarse blocks through the super masks
 
+// squared lower bound (in cells^2) of the distance from the query (anywhere inside its own cell) to a cell at
+// per-axis offsets whose absolute values are at least gx, gy, gz cells
+__device__ __forceinline__ float cells_lb2(int gx, int gy, int gz) {
+    float x = (float) max(gx - 1, 0), y = (float) max(gy - 1, 0), z = (float) max(gz - 1, 0);
+    return x * x + y * y + z * z;
+}
+
 __device__ __forceinline__ void warp_knn5(const HashView &H, float qx, float qy, float qz, float inv_cell, float cell,
                                           int r_max, float max_d2, unsigned *__restrict__ queue,
                                           unsigned *__restrict__ cqueue, u64 best[5]) {
     const int lane = threadIdx.x & 31;
     const int cx = (int) floorf(qx * inv_cell), cy = (int) floorf(qy * inv_cell), cz = (int) floorf(qz * inv_cell);
     u64 a0 = kInf, a1 = kInf, a2 = kInf, a3 = kInf, a4 = kInf;
+    bool dirty = false;                                  // this lane inserted since the last warp merge
+    // pruning bound in cells^2: a cell (block) whose lower-bound distance exceeds the cut-off, or the current 5th
+    // distance once five neighbours are known, cannot contribute (strict, with a 0.2 % guard for fp32 rounding)
+    const float cell2 = cell * cell;
+    float prune_c2    = max_d2 / cell2 * 1.002f;
+
+    // first probe of the (<= 27) coarse masks of the near phase: issued now, consumed after the fast-exit test
+    bool near_have = false;
+    int nax = 0, nay = 0, naz = 0;
+    u64 near_key = 0ull;
+    ulonglong2 near_first = make_ulonglong2(kEmpty, 0ull);
+    if (r_max >= 4) {
+        const int lox = (cx - 4) >> 2, loy = (cy - 4) >> 2, loz = (cz - 4) >> 2;
+        const int nx = ((cx + 4) >> 2) - lox + 1, ny = ((cy + 4) >> 2) - loy + 1, nz = ((cz + 4) >> 2) - loz + 1;
+        if (lane < nx * ny * nz) {
+            int bz  = lane / (nx * ny);
+            int rem = lane - bz * (nx * ny);
+            int by  = rem / nx;
+            int bx  = rem - by * nx;
+            nax = (bx + lox) * 4 - cx;
+            nay = (by + loy) * 4 - cy;
+            naz = (bz + loz) * 4 - cz;
+            near_have  = true;
+            near_key   = pack_cell(bx + lox, by + loy, bz + loz);
+            near_first = __ldg(reinterpret_cast<const ulonglong2 *>(H.coarse) + (hash_cell(near_key) & H.hmask));
+        }
+    }
+
+    // ---- fast exit: no occupied coarse block anywhere within r_max of the query (half of all (ref, query) pairs
+    // of a turning sensor): one round of super-mask fetches instead of four empty stages
+    {
+        const int lox = (cx - r_max) >> 4, loy = (cy - r_max) >> 4, loz = (cz - r_max) >> 4;
+        const int nx = ((cx + r_max) >> 4) - lox + 1, ny = ((cy + r_max) >> 4) - loy + 1, nz = ((cz + r_max) >> 4) - loz + 1;
+        const int total = nx * ny * nz;
+        bool any = false;
+#pragma unroll 1
+        for (int t0 = 0; t0 < total && !any; t0 += 32) {
+            const int t = t0 + lane;
+            bool mine   = false;
+            if (t < total) {
+                int bz  = t / (nx * ny);
+                int rem = t - bz * (nx * ny);
+                int by  = rem / nx;
+                int bx  = rem - by * nx;
+                int sx = (bx + lox) * 16 - cx, sy = (by + loy) * 16 - cy, sz = (bz + loz) * 16 - cz;
+                u64 m = lookup_mask(H.super, H.hmask, pack_cell(bx + lox, by + loy, bz + loz));
+                while (m && !mine) {
+                    int sub = __ffsll((long long) m) - 1;
+                    m &= m - 1;
+                    int cmn, cmx;
+                    block_range(sx + 4 * (sub & 3), sy + 4 * ((sub >> 2) & 3), sz + 4 * (sub >> 4), 4, cmn, cmx);
+                    mine = cmn <= r_max;
+                }
+            }
+            any = __any_sync(0xffffffffu, mine);
+        }
+        if (!any) return;
+    }
+
     int lo = -1, hi = 2; // stage (lo, hi]; the first stage includes the query's own cell (ch = 0)
 
-    // One round: every lane may bring one coarse block (first-cell offset ax, ay, az from the query cell; have =
-    // false for idle lanes). Cells of the block inside the stage go to the queue, the queue is drained 32 at a time.
-    auto round = [&](bool have, int ax, int ay, int az) {
-        u64 keep = 0ull;
-        if (have) {
-            u64 want = cube_mask(ax, ay, az, hi) & ~cube_mask(ax, ay, az, lo); // pure bit arithmetic
-            if (want) keep = lookup_mask(H.coarse, H.hmask, pack_cell((ax + cx) >> 2, (ay + cy) >> 2, (az + cz) >> 2)) & want;
-        }
+    // One round: up to kLookupLanes lanes bring one coarse block each (first-cell offset ax, ay, az from the query
+    // cell). Cells of the block inside the stage (and inside the pruning bound) go to the queue, the queue is
+    // drained 32 at a time.
+    // queue the kept cells of every lane's block and probe them 32 at a time
+    auto drain = [&](u64 keep, int ax, int ay, int az) {
         const int cnt = __popcll(keep);
         int incl      = cnt;
 #pragma unroll
@@ -240,10 +305,66 @@ __device__ __forceinline__ void warp_knn5(const HashView &H, float qx, float qy,
         for (int k = lane; k < T; k += 32) {
             unsigned e = queue[k];
             int dx = (int) (e & 1023u) - 512, dy = (int) ((e >> 10) & 1023u) - 512, dz = (int) (e >> 20) - 512;
-            probe_cell(H, cx + dx, cy + dy, cz + dz, qx, qy, qz, max_d2, a0, a1, a2, a3, a4);
+            probe_cell(H, cx + dx, cy + dy, cz + dz, qx, qy, qz, max_d2, a0, a1, a2, a3, a4, dirty);
         }
         __syncwarp();
     };
+    // drop the cells of a block mask whose lower-bound distance exceeds the pruning bound
+    auto prune_cells = [&](u64 keep, int ax, int ay, int az) {
+        u64 m = keep;
+        while (m) {
+            int sub = __ffsll((long long) m) - 1;
+            m &= m - 1;
+            if (cells_lb2(abs(ax + (sub & 3)), abs(ay + ((sub >> 2) & 3)), abs(az + (sub >> 4))) > prune_c2) keep &= ~(1ull << sub);
+        }
+        return keep;
+    };
+    // after a stage: merge if anything was inserted, test the stop rule, tighten the pruning bound
+    auto stage_done = [&]() {
+        if (__any_sync(0xffffffffu, dirty)) { // the shuffle merge is skipped when the stage inserted nothing
+            warp_merge5(a0, a1, a2, a3, a4, best);
+            dirty = false;
+        }
+        if (best[4] != kInf) {
+            float d5    = __uint_as_float((unsigned) (best[4] >> 32));
+            float bound = (float) hi * cell - 1e-3f;
+            if (bound > 0.f && d5 < bound * bound) return true;
+            prune_c2 = fminf(prune_c2, d5 / cell2 * 1.002f);
+        }
+        return false;
+    };
+
+    auto round = [&](bool have, int ax, int ay, int az) {
+        u64 keep = 0ull;
+        if (have) {
+            int gx = max(0, max(ax, -(ax + 3))), gy = max(0, max(ay, -(ay + 3))), gz = max(0, max(az, -(az + 3)));
+            if (cells_lb2(gx, gy, gz) <= prune_c2) {
+                u64 want = cube_mask(ax, ay, az, hi) & ~cube_mask(ax, ay, az, lo); // pure bit arithmetic
+                if (want) keep = lookup_mask(H.coarse, H.hmask, pack_cell((ax + cx) >> 2, (ay + cy) >> 2, (az + cz) >> 2)) & want;
+                if (hi >= 4) keep = prune_cells(keep, ax, ay, az); // per-cell pruning pays once the shell is wide
+            }
+        }
+        drain(keep, ax, ay, az);
+    };
+
+    // ---- near phase: stages (-1,2] and (2,4] share ONE fetch of the (<= 27) coarse masks around the query; the
+    // first probe of each mask was issued before the fast-exit test above, so both round trips overlap
+    if (r_max >= 4) {
+        u64 m27 = 0ull;
+        if (near_have) {
+            if (near_first.x == near_key) m27 = near_first.y;
+            else if (near_first.x != kEmpty) m27 = lookup_mask(H.coarse, H.hmask, near_key);
+        }
+        hi = 2;
+        drain(m27 & cube_mask(nax, nay, naz, 2), nax, nay, naz);
+        if (stage_done()) return;
+        lo = 2;
+        hi = 4;
+        drain(prune_cells(m27 & cube_mask(nax, nay, naz, 4) & ~cube_mask(nax, nay, naz, 2), nax, nay, naz), nax, nay, naz);
+        if (stage_done()) return;
+        lo = 4;
+        hi = 8;
+    }
 
 #pragma unroll 1
     while (lo < r_max) {
@@ -265,7 +386,7 @@ __device__ __forceinline__ void warp_knn5(const HashView &H, float qx, float qy,
         } else {
             // wide stages: the super masks list the occupied coarse blocks, empty space costs one probe per
             // 16^3 cells. Pass 1: lanes fetch super masks and queue the occupied coarse blocks that intersect
-            // the stage. Pass 2: one coarse block per lane and round.
+            // the stage and the pruning bound. Pass 2: one coarse block per lane and round.
             const int lox = (cx - hi) >> 4, loy = (cy - hi) >> 4, loz = (cz - hi) >> 4;
             const int nx = ((cx + hi) >> 4) - lox + 1, ny = ((cy + hi) >> 4) - loy + 1, nz = ((cz + hi) >> 4) - loz + 1;
             const int total = nx * ny * nz;
@@ -322,12 +443,7 @@ __device__ __forceinline__ void warp_knn5(const HashView &H, float qx, float qy,
                 __syncwarp();
             }
         }
-        warp_merge5(a0, a1, a2, a3, a4, best);
-        if (best[4] != kInf) {
-            float d5    = __uint_as_float((unsigned) (best[4] >> 32));
-            float bound = (float) hi * cell - 1e-3f;
-            if (bound > 0.f && d5 < bound * bound) return;
-        }
+        if (stage_done()) return;
         lo = hi;
         hi *= 2;
     }
@@ -345,6 +461,7 @@ associate_knn_kernel(const __grid_constant__ AssocParams P, const float4 *__rest
     const int ri = gwarp / P.q;
     const int k  = gwarp - ri * P.q;
     const AssocRef &ref = P.ref[ri];
+    const long long dbg_t0 = P.dbg_cycles ? clock64() : 0;
     // world -> ref lidar frame (lidar_map.cc:343-345,355-357): fp64 math, fp32 store
     float4 rp   = project_rn(ref.T_ref_world.R, ref.T_ref_world.t, __ldg(cur_world + k));
     u64 best[5] = {kInf, kInf, kInf, kInf, kInf};
@@ -360,6 +477,7 @@ associate_knn_kernel(const __grid_constant__ AssocParams P, const float4 *__rest
         ref.feat.nn_idx[5 * k + lane] = have ? (int) (unsigned) (b & 0xffffffffu) : -1;
         ref.feat.nn_d2[5 * k + lane]  = have ? __uint_as_float((unsigned) (b >> 32)) : 0.f;
     }
+    if (P.dbg_cycles && lane == 0) P.dbg_cycles[gwarp] = clock64() - dbg_t0;
 }
 
 // K5b: one THREAD per (ref, query): plane fit + validity tests + feature record (lidar_map.cc:371-395).

@@ -129,6 +129,7 @@ struct AssocParams {
     float max_d2;          // (max_search_square_distance)^2, ikd_Tree.cc:902
     float plane_d2_gate;   // max_search_square_distance, lidar_map.cc:374
     double plane_thr, sigma, scalar_thr, sigma_gate;
+    long long *dbg_cycles; // debug: per-(ref, query) warp cycles (nullptr = off)
     AssocRef ref[kMaxRefs];
 };
 void launch_associate(cudaStream_t s, const AssocParams &p, const float4 *cur_world, const float4 *cur_lidar);
