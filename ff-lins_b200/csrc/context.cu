@@ -141,6 +141,10 @@ struct fflins_ctx : public Profiler {
     // pinned host scratch
     unsigned char *h_pin = nullptr;
     size_t h_pin_cap = 0;
+    // pinned completion flags released by the kernels of the synchronous solver-facing calls
+    // (window_eval): the host polls them instead of synchronising the stream
+    unsigned long long *h_signal = nullptr; // [kMaxRefs] window_eval flags | chi2 flag | chi2 counts
+    unsigned long long signal_seq = 0;
     // asynchronous frames: per-frame count slots (pinned, written by the last kernel of the frame chain)
     int *h_slots = nullptr;       // kSlots x 2 ints
     int next_slot = 0;
@@ -429,6 +433,26 @@ unsigned char *pin(fflins_ctx *ctx, size_t bytes) {
         ctx->h_pin_cap = cap;
     }
     return ctx->h_pin;
+}
+
+// Waits until the kernel(s) on `s` have released flags[0..n) = seq (pinned host memory, see factor_kernel).
+// Polling costs ~1 us after the device's store lands; a stream synchronisation costs 5-10 us. The stream is
+// queried every few thousand polls so that a failed launch or a sticky device error ends the wait.
+cudaError_t wait_signal(const unsigned long long *flags, int n, unsigned long long seq, cudaStream_t s) {
+    for (int i = 0; i < n; i++) {
+        unsigned spins = 0;
+        while (__atomic_load_n(flags + i, __ATOMIC_ACQUIRE) != seq) {
+            if ((++spins & 0xfffu) == 0) {
+                cudaError_t e = cudaStreamQuery(s);
+                if (e == cudaSuccess) break;                 // stream drained: the stores are visible
+                if (e != cudaErrorNotReady) return e;
+            }
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
+    }
+    return cudaSuccess;
 }
 
 void fill_info(Frame *f, fflins_frame_info *out) {
@@ -843,9 +867,13 @@ int fflins_create(const fflins_config *cfg, int device, fflins_ctx **out) {
         float v = (float) atof(e);
         if (v >= 0.5f && v <= 8.f) ctx->cell_scale = v;
     }
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->map_stream, cudaStreamNonBlocking) != cudaSuccess ||
+    // the solver-facing calls (association, factor evaluation) are latency-critical and run on the main stream;
+    // the keyframe-map rebuild on the map stream is throughput work that must not delay their CTAs
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&ctx->copy_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&ctx->map_stream, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_main_done, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_map_done, cudaEventDisableTiming) != cudaSuccess) {
         delete ctx;
@@ -853,7 +881,7 @@ int fflins_create(const fflins_config *cfg, int device, fflins_ctx **out) {
     }
     ctx->d_counters   = (int *) ctx->pool.alloc(64 * sizeof(int));
     ctx->d_red        = (double *) ctx->pool.alloc((size_t) kMaxRefs * kRedSize * sizeof(double));
-    ctx->d_outliers   = (int *) ctx->pool.alloc(kMaxRefs * sizeof(int));
+    ctx->d_outliers   = (int *) ctx->pool.alloc((kMaxRefs + 1) * sizeof(int));
     ctx->d_map_count  = (int *) ctx->pool.alloc(64);
     ctx->d_assoc_counts = (int *) ctx->pool.alloc(kMaxRefs * 2 * sizeof(int));
     if (!ctx->d_counters || !ctx->d_red || !ctx->d_outliers || !ctx->d_map_count || !ctx->d_assoc_counts) {
@@ -868,11 +896,14 @@ int fflins_create(const fflins_config *cfg, int device, fflins_ctx **out) {
         return FFLINS_E_NOMEM;
     }
     if (cudaMallocHost((void **) &ctx->h_slots, kSlots * 2 * sizeof(int)) != cudaSuccess ||
+        cudaMallocHost((void **) &ctx->h_signal, (2 * kMaxRefs + 16) * sizeof(unsigned long long)) != cudaSuccess ||
         cudaMallocHost((void **) &ctx->h_map_count, 64) != cudaSuccess) {
         ctx->h_slots = nullptr;
         fflins_destroy(ctx);
         return FFLINS_E_NOMEM;
     }
+    std::memset(ctx->h_signal, 0, (2 * kMaxRefs + 16) * sizeof(unsigned long long));
+    cudaMemsetAsync(ctx->d_outliers, 0, (kMaxRefs + 1) * sizeof(int), ctx->stream);
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
         fflins_destroy(ctx);
         return FFLINS_E_CUDA;
@@ -926,6 +957,7 @@ void fflins_destroy(fflins_ctx *ctx) {
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     if (ctx->h_slots) cudaFreeHost(ctx->h_slots);
     if (ctx->h_map_count) cudaFreeHost(ctx->h_map_count);
+    if (ctx->h_signal) cudaFreeHost(ctx->h_signal);
     if (ctx->ev_main_done) cudaEventDestroy(ctx->ev_main_done);
     if (ctx->ev_map_done) cudaEventDestroy(ctx->ev_map_done);
     if (ctx->map_stream) cudaStreamDestroy(ctx->map_stream);
@@ -1763,11 +1795,17 @@ int fflins_window_eval(fflins_ctx *ctx, int32_t n_pairs, const uint64_t *ref_ids
         // the reduced blocks are stored by the kernel straight into pinned host memory (zero-copy):
         // no device-to-host memcpy between the launch and the synchronisation
         ProfScope ps(ctx->prof(), "factor_eval", s);
-        launch_factor_eval(s, P, (const float *) cur->c[FFLINS_CLOUD_LIDAR].d, 1, nullptr, nullptr, nullptr, (double *) h);
+        launch_factor_eval(s, P, (const float *) cur->c[FFLINS_CLOUD_LIDAR].d, 1, nullptr, nullptr, nullptr, (double *) h,
+                           ctx->h_signal, ++ctx->signal_seq);
         ctx->launches++;
     }
-    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    static const bool no_poll = getenv("FFLINS_NO_POLL") != nullptr;
+    if (ctx->prof_on || no_poll) CK(cudaStreamSynchronize(s));   // the profiler's closing event needs the stream drained
+    else CK(wait_signal(ctx->h_signal, n_pairs, ctx->signal_seq, s));
     const double *red = (const double *) h;
+    // the lines were just written by the device: get all the misses in flight before the dependent reads
+    for (size_t o = 0; o < (size_t) n_pairs * kRedSize * 8; o += 64) __builtin_prefetch(h + o, 0, 0);
     for (int i = 0; i < n_pairs; i++)
         unpack_red(red + (size_t) i * kRedSize, H ? H + 361 * i : nullptr, b ? b + 19 * i : nullptr,
                    cost ? cost + 2 * i : nullptr, n_res ? n_res + i : nullptr);
@@ -1784,18 +1822,26 @@ int fflins_window_chi2(fflins_ctx *ctx, int32_t n_pairs, const uint64_t *ref_ids
     FactorParams P{};
     int rc;
     if ((rc = fill_factor_pairs(ctx, P, n_pairs, ref_ids, pose_refs, cur, pose_cur, ext, td, 0))) return rc;
+    if (P.q == 0) {
+        if (n_outliers) std::memset(n_outliers, 0, n_pairs * sizeof(int));
+        return FFLINS_OK;
+    }
     cudaStream_t s = ctx->stream;
-    CK(cudaMemsetAsync(ctx->d_outliers, 0, kMaxRefs * sizeof(int), s));
-    if (P.q > 0) {
+    // counts and completion flag come back through pinned memory (the last CTA publishes them): one launch, no
+    // memset, no copy, no stream synchronisation
+    int *h_counts = (int *) (ctx->h_signal + kMaxRefs + 8);
+    unsigned long long *flag = ctx->h_signal + kMaxRefs;
+    {
         ProfScope ps(ctx->prof(), "chi2", s);
-        launch_chi2(s, P, (const float *) cur->c[FFLINS_CLOUD_LIDAR].d, 1, threshold, ctx->d_outliers);
+        launch_chi2(s, P, (const float *) cur->c[FFLINS_CLOUD_LIDAR].d, 1, threshold, ctx->d_outliers, h_counts, flag,
+                    ++ctx->signal_seq);
         ctx->launches++;
     }
-    unsigned char *h = pin(ctx, 256);
-    if (!h) return fail(ctx, FFLINS_E_NOMEM, "pinned allocation failed");
-    CK(cudaMemcpyAsync(h, ctx->d_outliers, n_pairs * sizeof(int), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    if (n_outliers) std::memcpy(n_outliers, h, n_pairs * sizeof(int));
+    CK(cudaGetLastError());
+    static const bool no_poll = getenv("FFLINS_NO_POLL") != nullptr;
+    if (ctx->prof_on || no_poll) CK(cudaStreamSynchronize(s));
+    else CK(wait_signal(flag, 1, ctx->signal_seq, s));
+    if (n_outliers) std::memcpy(n_outliers, h_counts, n_pairs * sizeof(int));
     return FFLINS_OK;
 }
 

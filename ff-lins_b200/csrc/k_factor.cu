@@ -11,11 +11,9 @@
 // that depends only on the (ref, cur) pair — three rotation matrices, the first-order time-delay
 // motion terms, the products A = Rbl^T Rt0^T, C = A Rt1, E = C Rbl — is computed once per CTA into
 // shared memory; a thread then needs ~250 fp64 operations per residual instead of the ~1000 of the
-// per-residual formulation. The reduction is a 256-row "syrk" out of shared memory: thread e owns
-// one of the 190 upper-triangle entries (or one of the 19 gradient entries / 3 scalars) and
-// accumulates it over the CTA's residuals IN ROW ORDER, CTA partials are then summed in CTA order
-// by the last CTA of the pair — a fixed summation order, so results are run-to-run deterministic.
-// No tensor cores: a 19-wide rank-1 update is not a dense contraction worth a tcgen05 tile.
+// per-residual formulation. The reduction is a 256-row SYRK out of shared memory on the FP64 tensor
+// pipe (mma.sync.m8n8k4.f64 — tcgen05 has no fp64 kind), warp partials and CTA partials are summed in a
+// fixed order, so results are run-to-run deterministic.
 #include "math_factor.cuh"
 
 #include <cooperative_groups.h>
@@ -25,43 +23,44 @@ namespace fflins {
 
 namespace {
 
-constexpr int kRowStride = 24; // 19 J + r + rho0 + valid + 2 pad: 192-byte rows, 16-byte aligned groups of 2
+constexpr int kCols      = 24;                 // 19 J | r | rho0 | valid | 1 | 0
+constexpr int kColStride = kFactorBlock + 4;   // column-major tile, +4 doubles: conflict-free fragment loads
+constexpr int kWarps     = kFactorBlock / 32;
+
+// D (8x8, fp64) += A (8x4, row) * B (4x8, col) on the FP64 tensor pipe.
+__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c[0]), "+d"(c[1])
+                 : "d"(a), "d"(b));
+}
 
 // Grid: (C, n_pairs) with the C CTAs of a pair forming ONE thread-block cluster (C = 1, 2, 4 or 8).
-// CTA c handles residual tiles c, c + C, ... Reduction = a register-tiled SYRK out of shared memory:
-// with v = [J(19) | r], G = sum v v^T is split into 5 x 5 blocks of 4 x 4; thread (slice s, block T) keeps
-// the 16 entries of one upper block in registers and walks the 16 rows s, s+16, ... of the tile with four
-// 16-byte shared-memory loads per row (0.25 loads per FMA instead of 2). The 16 slice partials are summed
-// in slice order, the CTAs then exchange their 212 sums through distributed shared memory and rank 0 adds
-// them in rank order: no global round trip, no atomics, a fixed summation order (bit-deterministic).
+// CTA c handles residual tiles c, c + C, ... Reduction = a SYRK on the FP64 tensor pipe: the tile's rows
+// v = [J(19) | r | rho0 | valid | 1 | 0] are stored column-major in shared memory, G = V^T V (24 x 24) is
+// split into 3 x 3 blocks of 8 x 8 and warp w accumulates the 6 upper blocks over its 32 rows with
+// mma.sync.m8n8k4.f64: the A fragment of column group g (lane l holds V[k0 + l%4][8g + l/4]) is also the B
+// fragment of the same group, so one k-step is 3 shared-memory loads and 6 DMMAs per lane (the scalar
+// version needed 4 x 16-byte loads per 16 FMAs and was shared-memory-bandwidth bound). sum rho and the
+// residual count come out of the same product as G[20][22] and G[21][22] (column 22 is all ones).
+// The 8 warp partials are summed in warp order, the CTAs then exchange their 212 sums through distributed
+// shared memory and rank 0 adds them in rank order: no global round trip, no atomics, a fixed summation
+// order (run-to-run deterministic).
 __global__ void __launch_bounds__(kFactorBlock)
 factor_kernel(const __grid_constant__ FactorParams P, const float *__restrict__ points, int stride4,
               double *__restrict__ r_out, double *__restrict__ J_out, uint8_t *__restrict__ valid_out,
-              double *__restrict__ out_red) {
+              double *__restrict__ out_red, unsigned long long *__restrict__ signal, unsigned long long seq) {
     extern __shared__ __align__(16) double smem[];
-    double (*rows)[kRowStride] = reinterpret_cast<double (*)[kRowStride]>(smem);          // [256][24]
-    double *s_red              = smem + kFactorBlock * kRowStride;                         // [kRedSize]
+    double *cols  = smem;                          // [kCols][kColStride]
+    double *s_red = smem + kCols * kColStride;     // [kRedSize]
     cg::cluster_group cluster = cg::this_cluster();
     const int pair       = blockIdx.y;
     const FactorPair &pr = P.pair[pair];
     const PairConst &pc  = pr.pc;
     const int tid        = threadIdx.x;
-    const int slice = tid >> 4, T = tid & 15;     // 16 row slices x 16 blocks (15 upper 4x4 blocks of G + 1 scalar block)
-    int bi = 0, bj = 0;                           // block coordinates (bi <= bj) of upper block T
-    {
-        int t = T;
+    const int warp = tid >> 5, lane = tid & 31;
+    double acc[6][2];                              // blocks (0,0) (0,1) (0,2) (1,1) (1,2) (2,2)
 #pragma unroll
-        for (int i = 0; i < 5; i++) {
-            int len = 5 - i;
-            if (t >= 0 && t < len) { bi = i; bj = i + t; t = -1; }
-            else if (t >= len) t -= len;
-        }
-    }
-    double acc[4][4];
-#pragma unroll
-    for (int a = 0; a < 4; a++)
-#pragma unroll
-        for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
+    for (int a = 0; a < 6; a++) acc[a][0] = acc[a][1] = 0.0;
 
     for (int tile = blockIdx.x; tile * kFactorBlock < P.q; tile += gridDim.x) {
         const int k = tile * kFactorBlock + threadIdx.x;
@@ -100,92 +99,103 @@ factor_kernel(const __grid_constant__ FactorParams P, const float *__restrict__ 
         }
         if (out_red == nullptr) continue;
 #pragma unroll
-        for (int i = 0; i < 19; i++) rows[threadIdx.x][i] = J[i];
-        rows[threadIdx.x][19] = r;
-        rows[threadIdx.x][20] = rho0;
-        rows[threadIdx.x][21] = valid ? 1.0 : 0.0;
-        rows[threadIdx.x][22] = 0.0;
-        rows[threadIdx.x][23] = 0.0;
-        __syncthreads();
-        if (T < 15) {
-#pragma unroll 4
-            for (int kk = 0; kk < 16; kk++) {
-                const double2 *row = reinterpret_cast<const double2 *>(rows[slice + 16 * kk]);
-                double2 a01 = row[2 * bi], a23 = row[2 * bi + 1], b01 = row[2 * bj], b23 = row[2 * bj + 1];
-                const double av[4] = {a01.x, a01.y, a23.x, a23.y}, bv[4] = {b01.x, b01.y, b23.x, b23.y};
+        for (int i = 0; i < 19; i++) cols[i * kColStride + tid] = J[i];
+        cols[19 * kColStride + tid] = r;
+        cols[20 * kColStride + tid] = rho0;
+        cols[21 * kColStride + tid] = valid ? 1.0 : 0.0;
+        cols[22 * kColStride + tid] = 1.0;
+        cols[23 * kColStride + tid] = 0.0;
+        __syncwarp(); // warp w consumes exactly the 32 rows its own lanes produced
+        {
+            const double *base = cols + (lane >> 2) * kColStride + 32 * warp + (lane & 3);
 #pragma unroll
-                for (int a = 0; a < 4; a++)
-#pragma unroll
-                    for (int b = 0; b < 4; b++) acc[a][b] += av[a] * bv[b];
-            }
-        } else { // scalar block: sum rho (entry 0) and the residual count (entry 1)
-#pragma unroll 4
-            for (int kk = 0; kk < 16; kk++) {
-                acc[0][0] += rows[slice + 16 * kk][20];
-                acc[0][1] += rows[slice + 16 * kk][21];
+            for (int ks = 0; ks < 8; ks++) {
+                const double f0 = base[4 * ks], f1 = base[8 * kColStride + 4 * ks], f2 = base[16 * kColStride + 4 * ks];
+                dmma884(acc[0], f0, f0);
+                dmma884(acc[1], f0, f1);
+                dmma884(acc[2], f0, f2);
+                dmma884(acc[3], f1, f1);
+                dmma884(acc[4], f1, f2);
+                dmma884(acc[5], f2, f2);
             }
         }
-        __syncthreads();
+        __syncwarp();
     }
     if (out_red == nullptr) return;
-    // slice partials -> shared memory (the row buffer is free now): part[slice][T][16]
-    double *part = smem;
-#pragma unroll
-    for (int a = 0; a < 4; a++)
-#pragma unroll
-        for (int b = 0; b < 4; b++) part[(slice * 16 + T) * 16 + 4 * a + b] = acc[a][b];
+    // warp partials -> shared memory (each warp's rows are its own, but other warps' regions are overwritten:
+    // wait for everyone): part[warp][block][row 0..7][col 0..7]
     __syncthreads();
+    double *part = smem;
     {
-        // thread (T, q) sums entry q of block T over the 16 slices in slice order and files it under its
-        // place in the 212-vector [190 upper-triangle H | 19 b | sum rho | sum r'^2 | count]
-        const int Tq = tid >> 4, q = tid & 15;
+        const int row = lane >> 2, col = 2 * (lane & 3);
+#pragma unroll
+        for (int a = 0; a < 6; a++)
+            *reinterpret_cast<double2 *>(part + ((warp * 6 + a) * 8 + row) * 8 + col) = make_double2(acc[a][0], acc[a][1]);
+    }
+    __syncthreads();
+    // thread e (and e + 256 < 384) sums entry e = (block, row, col) over the warps in warp order and files it
+    // under its place in the 212-vector [190 upper-triangle H | 19 b | sum rho | sum r'^2 | count]
+    for (int e0 = tid; e0 < 6 * 64; e0 += kFactorBlock) {
         double sum = 0.0;
 #pragma unroll
-        for (int s2 = 0; s2 < 16; s2++) sum += part[(s2 * 16 + Tq) * 16 + q];
-        int ti = 0, tj = 0;
-        {
-            int t = Tq;
-#pragma unroll
-            for (int i = 0; i < 5; i++) {
-                int len = 5 - i;
-                if (t >= 0 && t < len) { ti = i; tj = i + t; t = -1; }
-                else if (t >= len) t -= len;
-            }
-        }
+        for (int w = 0; w < kWarps; w++) sum += part[w * 6 * 64 + e0];
+        const int blk = e0 >> 6, gi = blk < 3 ? 0 : (blk < 5 ? 1 : 2), gj = blk < 3 ? blk : (blk < 5 ? blk - 2 : 2);
+        const int ra = 8 * gi + ((e0 >> 3) & 7), cb = 8 * gj + (e0 & 7);
         int e = -1;
         double sign = 1.0;
-        if (Tq < 15) {
-            const int ra = 4 * ti + (q >> 2), cb = 4 * tj + (q & 3);
-            if (ra < 19 && cb < 19) {
-                if (ra <= cb) e = ra * 19 - (ra * (ra - 1)) / 2 + (cb - ra);          // upper triangle of H
-            } else if (ra < 19 && cb == 19) {
-                e    = 190 + ra;                                                     // b = -J^T r
-                sign = -1.0;
-            } else if (ra == 19 && cb == 19) {
-                e = 210;                                                             // sum r'^2
-            }
-        } else if (q == 0) {
-            e = 209;                                                                 // sum rho
-        } else if (q == 1) {
-            e = 211;                                                                 // count
+        if (ra < 19 && cb < 19) {
+            if (ra <= cb) e = ra * 19 - (ra * (ra - 1)) / 2 + (cb - ra);          // upper triangle of H
+        } else if (ra < 19 && cb == 19) {
+            e    = 190 + ra;                                                     // b = -J^T r
+            sign = -1.0;
+        } else if (ra == 19 && cb == 19) {
+            e = 210;                                                             // sum r'^2
+        } else if (ra == 20 && cb == 22) {
+            e = 209;                                                             // sum rho
+        } else if (ra == 21 && cb == 22) {
+            e = 211;                                                             // count
         }
-        __syncthreads(); // everyone has read `part` before s_red (which lies behind the row buffer) is written
-        if (e >= 0) s_red[e] = sign * sum;
+        if (e >= 0) s_red[e] = sign * sum;   // s_red lies behind the tile buffer, `part` stays intact
     }
     cluster.sync();
-    if (cluster.block_rank() == 0 && tid < kRedSize) {
-        double total = 0.0;
-        for (unsigned rk = 0; rk < cluster.num_blocks(); rk++) total += cluster.map_shared_rank(s_red, rk)[tid];
-        out_red[(size_t) pair * kRedSize + tid] = total;
+    constexpr int kPer = (kRedSize + kFactorBlock - 1) / kFactorBlock;
+    double total[kPer];
+    if (cluster.block_rank() == 0) {
+#pragma unroll
+        for (int j = 0; j < kPer; j++) {
+            const int e = tid + j * kFactorBlock;
+            double v[8];
+#pragma unroll
+            for (unsigned rk = 0; rk < 8; rk++)   // independent remote loads in flight together, summed in rank order
+                v[rk] = (e < kRedSize && rk < cluster.num_blocks()) ? cluster.map_shared_rank(s_red, rk)[e] : 0.0;
+            total[j] = 0.0;
+#pragma unroll
+            for (unsigned rk = 0; rk < 8; rk++) total[j] += v[rk];
+        }
     }
-    cluster.sync(); // keep every CTA's shared memory alive until rank 0 has read it
+    cluster.sync(); // every CTA's shared memory stays alive until rank 0 has read it; the others are done now
+    if (cluster.block_rank() != 0) return;
+#pragma unroll
+    for (int j = 0; j < kPer; j++) {
+        const int e = tid + j * kFactorBlock;
+        if (e < kRedSize) out_red[(size_t) pair * kRedSize + e] = total[j];
+    }
+    if (signal) {
+        // out_red is host memory: publish "pair done" behind the data so that the host can poll for it instead of
+        // paying a stream synchronisation (the release at system scope orders the CTA's stores before the flag)
+        __syncthreads();
+        if (tid == 0) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(signal + pair), "l"(seq) : "memory");
+    }
 }
 
-constexpr size_t kFactorSmem = (size_t) (kFactorBlock * kRowStride + kRedSize + 4) * sizeof(double);
+constexpr size_t kFactorSmem = (size_t) (kCols * kColStride + kRedSize + 4) * sizeof(double);
 
+// K7. counters: [kMaxRefs] per-pair outlier counts + [1] finished-CTA ticket, all zero on entry and zero again
+// on exit (the last CTA publishes the counts to pinned host memory, releases the flag and clears them).
 __global__ void __launch_bounds__(256)
 chi2_kernel(const __grid_constant__ FactorParams P, const float *__restrict__ points, int stride4, double threshold,
-            int *__restrict__ n_outliers) {
+            int *__restrict__ counters, int *__restrict__ host_counts, unsigned long long *__restrict__ signal,
+            unsigned long long seq) {
     const int pair       = blockIdx.y;
     const FactorPair &pr = P.pair[pair];
     const PairConst &pc  = pr.pc;
@@ -203,7 +213,22 @@ chi2_kernel(const __grid_constant__ FactorParams P, const float *__restrict__ po
         }
     }
     int c = __syncthreads_count(out ? 1 : 0);
-    if (threadIdx.x == 0 && c) atomicAdd(n_outliers + pair, c);
+    __shared__ bool last;
+    if (threadIdx.x == 0) {
+        if (c) atomicAdd(counters + pair, c);
+        __threadfence();
+        last = atomicAdd(counters + kMaxRefs, 1) == (int) (gridDim.x * gridDim.y) - 1;
+    }
+    __syncthreads();
+    if (!last) return;
+    if (threadIdx.x < P.n_pairs) {
+        host_counts[threadIdx.x] = atomicExch(counters + threadIdx.x, 0);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        counters[kMaxRefs] = 0;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(signal), "l"(seq) : "memory");
+    }
 }
 
 bool g_factor_init[64] = {false};
@@ -220,7 +245,7 @@ void init_factor() {
 } // namespace
 
 void launch_factor_eval(cudaStream_t s, FactorParams &p, const float *points, int stride4, double *r, double *J,
-                        uint8_t *valid, double *out_red) {
+                        uint8_t *valid, double *out_red, unsigned long long *signal, unsigned long long seq) {
     if (p.n_pairs <= 0 || p.q <= 0) return;
     init_factor();
     for (int i = 0; i < p.n_pairs; i++) make_pair_const(p, p.pair[i], p.pair[i].pc);
@@ -239,14 +264,15 @@ void launch_factor_eval(cudaStream_t s, FactorParams &p, const float *points, in
     attr[0].val.clusterDim.z = 1;
     cfg.attrs    = attr;
     cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, factor_kernel, p, points, stride4, r, J, valid, out_red);
+    cudaLaunchKernelEx(&cfg, factor_kernel, p, points, stride4, r, J, valid, out_red, signal, seq);
 }
 
-void launch_chi2(cudaStream_t s, FactorParams &p, const float *points, int stride4, double threshold, int *n_outliers) {
+void launch_chi2(cudaStream_t s, FactorParams &p, const float *points, int stride4, double threshold, int *counters,
+                 int *host_counts, unsigned long long *signal, unsigned long long seq) {
     if (p.n_pairs <= 0 || p.q <= 0) return;
     for (int i = 0; i < p.n_pairs; i++) make_pair_const(p, p.pair[i], p.pair[i].pc);
     dim3 grid((p.q + 255) / 256, p.n_pairs);
-    chi2_kernel<<<grid, 256, 0, s>>>(p, points, stride4, threshold, n_outliers);
+    chi2_kernel<<<grid, 256, 0, s>>>(p, points, stride4, threshold, counters, host_counts, signal, seq);
 }
 
 } // namespace fflins

@@ -164,14 +164,20 @@ struct FactorParams {
     double sigma, huber_delta;
     FactorPair pair[kMaxRefs];
 };
-constexpr int kFactorBlock = 256;
+constexpr int kFactorBlock = 128;
 constexpr int kRedSize     = 212; // 190 upper-tri H + 19 b + cost0 + cost1 + count
 // points: xyz of cur-frame points as float4 (stride4=1) or packed float3 (stride4=0).
 // r/J/valid (optional) are per (pair, feature): r[pair*q+k], J[22*(pair*q+k)].
 // out_red: n_pairs * kRedSize doubles (nullptr: no reduction). The params are completed in place
-// (PairConst per pair) before the launch.
+// (PairConst per pair) before the launch. signal (optional, host-mapped like a pinned out_red): signal[pair] = seq
+// is released at system scope once the pair's kRedSize sums are stored, so the host may poll instead of
+// synchronising the stream.
 void launch_factor_eval(cudaStream_t s, FactorParams &p, const float *points, int stride4, double *r, double *J,
-                        uint8_t *valid, double *out_red);
-void launch_chi2(cudaStream_t s, FactorParams &p, const float *points, int stride4, double threshold, int *n_outliers);
+                        uint8_t *valid, double *out_red, unsigned long long *signal = nullptr,
+                        unsigned long long seq = 0);
+// counters: kMaxRefs + 1 device ints, zero before the first launch (the kernel leaves them zero); the per-pair
+// outlier counts land in host_counts (pinned) and *signal = seq is released behind them.
+void launch_chi2(cudaStream_t s, FactorParams &p, const float *points, int stride4, double threshold, int *counters,
+                 int *host_counts, unsigned long long *signal, unsigned long long seq);
 
 } // namespace fflins
