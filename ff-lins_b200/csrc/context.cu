@@ -143,7 +143,7 @@ struct fflins_ctx : public Profiler {
     size_t h_pin_cap = 0;
     // pinned completion flags released by the kernels of the synchronous solver-facing calls
     // (window_eval): the host polls them instead of synchronising the stream
-    unsigned long long *h_signal = nullptr; // [kMaxRefs] window_eval flags | chi2 flag | chi2 counts
+    unsigned long long *h_signal = nullptr; // [kMaxRefs] window_eval flags | chi2 flag, associate flag | [8..] chi2 counts | [16..] associate counts
     unsigned long long signal_seq = 0;
     // asynchronous frames: per-frame count slots (pinned, written by the last kernel of the frame chain)
     int *h_slots = nullptr;       // kSlots x 2 ints
@@ -730,21 +730,30 @@ int run_associate(fflins_ctx *ctx, const std::vector<Frame *> &refs, Frame *cur,
         a.counts      = ctx->d_assoc_counts + 2 * i;
         r->feat_q     = q;
     }
-    CK(cudaMemsetAsync(ctx->d_assoc_counts, 0, kMaxRefs * 2 * sizeof(int), s));
     long long *dbg = nullptr;
     if (getenv("FFLINS_DEBUG_KNN")) {
         dbg = (long long *) ctx->pool.alloc((size_t) P.n_refs * q * 8 + 8);
         P.dbg_cycles = dbg;
     }
+    // counts and completion flag come back through pinned memory (published by the last CTA of the plane kernel)
+    unsigned long long *flag = ctx->h_signal + kMaxRefs + 1;
+    int *h = (int *) (ctx->h_signal + kMaxRefs + 16);
+    P.ticket      = ctx->d_assoc_counts + 2 * kMaxRefs;
+    P.host_counts = h;
+    P.signal      = flag;
+    P.seq         = ++ctx->signal_seq;
+    const bool launched = q > 0 && !refs.empty();
     {
         ProfScope ps(ctx->prof(), "associate", s);
         launch_associate(s, P, cur->c[FFLINS_CLOUD_WORLD].d, cur->c[FFLINS_CLOUD_LIDAR].d);
-        if (q > 0 && !refs.empty()) ctx->launches += 2;
+        if (launched) ctx->launches += 2;
     }
-    unsigned char *h = pin(ctx, 1024);
-    if (!h) return fail(ctx, FFLINS_E_NOMEM, "pinned allocation failed");
-    CK(cudaMemcpyAsync(h, ctx->d_assoc_counts, kMaxRefs * 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    if (launched) {
+        static const bool no_poll = getenv("FFLINS_NO_POLL") != nullptr;
+        if (ctx->prof_on || no_poll || dbg) CK(cudaStreamSynchronize(s));
+        else CK(wait_signal(flag, 1, P.seq, s));
+    }
     if (dbg) {
         std::vector<long long> cyc((size_t) P.n_refs * q);
         cudaMemcpy(cyc.data(), dbg, cyc.size() * 8, cudaMemcpyDeviceToHost);
@@ -760,11 +769,8 @@ int run_associate(fflins_ctx *ctx, const std::vector<Frame *> &refs, Frame *cur,
         }
     }
     for (size_t i = 0; i < refs.size(); i++) {
-        int c[2];
-        std::memcpy(c, h + 8 * i, 8);
-        if (q == 0) c[0] = c[1] = 0;
-        nf[i] = c[0];
-        nc[i] = c[1];
+        nf[i] = launched ? h[2 * i] : 0;
+        nc[i] = launched ? h[2 * i + 1] : 0;
     }
     return FFLINS_OK;
 }
@@ -883,7 +889,7 @@ int fflins_create(const fflins_config *cfg, int device, fflins_ctx **out) {
     ctx->d_red        = (double *) ctx->pool.alloc((size_t) kMaxRefs * kRedSize * sizeof(double));
     ctx->d_outliers   = (int *) ctx->pool.alloc((kMaxRefs + 1) * sizeof(int));
     ctx->d_map_count  = (int *) ctx->pool.alloc(64);
-    ctx->d_assoc_counts = (int *) ctx->pool.alloc(kMaxRefs * 2 * sizeof(int));
+    ctx->d_assoc_counts = (int *) ctx->pool.alloc((kMaxRefs * 2 + 1) * sizeof(int));
     if (!ctx->d_counters || !ctx->d_red || !ctx->d_outliers || !ctx->d_map_count || !ctx->d_assoc_counts) {
         fflins_destroy(ctx);
         return FFLINS_E_NOMEM;
@@ -896,14 +902,15 @@ int fflins_create(const fflins_config *cfg, int device, fflins_ctx **out) {
         return FFLINS_E_NOMEM;
     }
     if (cudaMallocHost((void **) &ctx->h_slots, kSlots * 2 * sizeof(int)) != cudaSuccess ||
-        cudaMallocHost((void **) &ctx->h_signal, (2 * kMaxRefs + 16) * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMallocHost((void **) &ctx->h_signal, (3 * kMaxRefs + 16) * sizeof(unsigned long long)) != cudaSuccess ||
         cudaMallocHost((void **) &ctx->h_map_count, 64) != cudaSuccess) {
         ctx->h_slots = nullptr;
         fflins_destroy(ctx);
         return FFLINS_E_NOMEM;
     }
-    std::memset(ctx->h_signal, 0, (2 * kMaxRefs + 16) * sizeof(unsigned long long));
+    std::memset(ctx->h_signal, 0, (3 * kMaxRefs + 16) * sizeof(unsigned long long));
     cudaMemsetAsync(ctx->d_outliers, 0, (kMaxRefs + 1) * sizeof(int), ctx->stream);
+    cudaMemsetAsync(ctx->d_assoc_counts, 0, (kMaxRefs * 2 + 1) * sizeof(int), ctx->stream);
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
         fflins_destroy(ctx);
         return FFLINS_E_CUDA;

@@ -523,9 +523,20 @@ associate_plane_kernel(const __grid_constant__ AssocParams P, const float4 *__re
     }
     int nf = __syncthreads_count(type == 0);
     int nc = __syncthreads_count(covered != 0);
+    __shared__ bool last;
     if (threadIdx.x == 0) {
         if (nf) atomicAdd(ref.counts + 0, nf);
         if (nc) atomicAdd(ref.counts + 1, nc);
+        __threadfence();
+        last = atomicAdd(P.ticket, 1) == (int) (gridDim.x * gridDim.y) - 1;
+    }
+    __syncthreads();
+    if (!last) return;
+    if (threadIdx.x < 2 * P.n_refs) P.host_counts[threadIdx.x] = atomicExch(P.ref[threadIdx.x >> 1].counts + (threadIdx.x & 1), 0);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *P.ticket = 0;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(P.signal), "l"(P.seq) : "memory");
     }
 }
 

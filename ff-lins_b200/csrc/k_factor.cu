@@ -45,8 +45,9 @@ __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
 // The 8 warp partials are summed in warp order, the CTAs then exchange their 212 sums through distributed
 // shared memory and rank 0 adds them in rank order: no global round trip, no atomics, a fixed summation
 // order (run-to-run deterministic).
+template <int NP>
 __global__ void __launch_bounds__(kFactorBlock)
-factor_kernel(const __grid_constant__ FactorParams P, const float *__restrict__ points, int stride4,
+factor_kernel(const __grid_constant__ FactorDev<NP> P, const float *__restrict__ points, int stride4,
               double *__restrict__ r_out, double *__restrict__ J_out, uint8_t *__restrict__ valid_out,
               double *__restrict__ out_red, unsigned long long *__restrict__ signal, unsigned long long seq) {
     extern __shared__ __align__(16) double smem[];
@@ -54,9 +55,8 @@ factor_kernel(const __grid_constant__ FactorParams P, const float *__restrict__ 
     double *s_red = smem + kCols * kColStride;     // [kRedSize]
     cg::cluster_group cluster = cg::this_cluster();
     const int pair       = blockIdx.y;
-    const FactorPair &pr = P.pair[pair];
-    const PairConst &pc  = pr.pc;
-    const int tid        = threadIdx.x;
+    const FactorDevPair &pr = P.pair[pair];
+    const int tid           = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     double acc[6][2];                              // blocks (0,0) (0,1) (0,2) (1,1) (1,2) (2,2)
 #pragma unroll
@@ -74,7 +74,7 @@ factor_kernel(const __grid_constant__ FactorParams P, const float *__restrict__ 
             V3 p = v3((double) pp[0], (double) pp[1], (double) pp[2]);
             V3 n = v3(pr.normal[3 * k], pr.normal[3 * k + 1], pr.normal[3 * k + 2]);
             double s = 1.0 / (pr.std ? pr.std[k] : P.sigma); // sqrt_info (lidar_factor.cc:38)
-            r = eval_residual<true>(pc, p, n, pr.d[k], s, J);
+            r = eval_residual<true>(P.cc, pr.rc, p, n, pr.d[k], s, J);
             if (P.flags & 2u) { J[0] = J[1] = J[2] = J[3] = J[4] = J[5] = 0.0; }
             if (P.flags & 4u) { J[6] = J[7] = J[8] = J[9] = J[10] = J[11] = 0.0; }
             if (P.flags & 8u) { J[12] = J[13] = J[14] = J[15] = J[16] = J[17] = 0.0; }
@@ -192,13 +192,13 @@ constexpr size_t kFactorSmem = (size_t) (kCols * kColStride + kRedSize + 4) * si
 
 // K7. counters: [kMaxRefs] per-pair outlier counts + [1] finished-CTA ticket, all zero on entry and zero again
 // on exit (the last CTA publishes the counts to pinned host memory, releases the flag and clears them).
+template <int NP>
 __global__ void __launch_bounds__(256)
-chi2_kernel(const __grid_constant__ FactorParams P, const float *__restrict__ points, int stride4, double threshold,
+chi2_kernel(const __grid_constant__ FactorDev<NP> P, const float *__restrict__ points, int stride4, double threshold,
             int *__restrict__ counters, int *__restrict__ host_counts, unsigned long long *__restrict__ signal,
             unsigned long long seq) {
     const int pair       = blockIdx.y;
-    const FactorPair &pr = P.pair[pair];
-    const PairConst &pc  = pr.pc;
+    const FactorDevPair &pr = P.pair[pair];
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     bool out    = false;
     if (k < P.q && pr.type[k] == 0 && pr.outlier[k] == 0) {
@@ -206,7 +206,7 @@ chi2_kernel(const __grid_constant__ FactorParams P, const float *__restrict__ po
         V3 p = v3((double) pp[0], (double) pp[1], (double) pp[2]);
         V3 n = v3(pr.normal[3 * k], pr.normal[3 * k + 1], pr.normal[3 * k + 2]);
         double s = 1.0 / (pr.std ? pr.std[k] : P.sigma);
-        double r = eval_residual<false>(pc, p, n, pr.d[k], s, nullptr);
+        double r = eval_residual<false>(P.cc, pr.rc, p, n, pr.d[k], s, nullptr);
         if (r * r > threshold) {       // optimizer.cc:536-541
             pr.outlier[k] = 1;
             out = true;
@@ -231,24 +231,40 @@ chi2_kernel(const __grid_constant__ FactorParams P, const float *__restrict__ po
     }
 }
 
-bool g_factor_init[64] = {false};
+// host FactorParams -> the compact by-value kernel parameter block
+template <int NP> void to_dev(const FactorParams &p, FactorDev<NP> &d) {
+    d.n_pairs     = p.n_pairs;
+    d.q           = p.q;
+    d.flags       = p.flags;
+    d.sigma       = p.sigma;
+    d.huber_delta = p.huber_delta;
+    for (int i = 0; i < p.n_pairs; i++) {
+        PairConst pc;
+        make_pair_const(p, p.pair[i], pc);
+        if (i == 0) d.cc = pc.cur;
+        FactorDevPair &o = d.pair[i];
+        o.type    = p.pair[i].type;
+        o.outlier = p.pair[i].outlier;
+        o.normal  = p.pair[i].normal;
+        o.d       = p.pair[i].d;
+        o.std     = p.pair[i].std;
+        o.rc      = pc.ref;
+    }
+}
 
-void init_factor() {
+template <int NP>
+void factor_launch(cudaStream_t s, const FactorParams &p, const float *points, int stride4, double *r, double *J,
+                   uint8_t *valid, double *out_red, unsigned long long *signal, unsigned long long seq) {
+    static bool init[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
     dev &= 63;
-    if (g_factor_init[dev]) return;
-    cudaFuncSetAttribute(factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kFactorSmem);
-    g_factor_init[dev] = true;
-}
-
-} // namespace
-
-void launch_factor_eval(cudaStream_t s, FactorParams &p, const float *points, int stride4, double *r, double *J,
-                        uint8_t *valid, double *out_red, unsigned long long *signal, unsigned long long seq) {
-    if (p.n_pairs <= 0 || p.q <= 0) return;
-    init_factor();
-    for (int i = 0; i < p.n_pairs; i++) make_pair_const(p, p.pair[i], p.pair[i].pc);
+    if (!init[dev]) {
+        cudaFuncSetAttribute(factor_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kFactorSmem);
+        init[dev] = true;
+    }
+    FactorDev<NP> d;
+    to_dev(p, d);
     int tiles = (p.q + kFactorBlock - 1) / kFactorBlock;
     int C     = 1;
     while (C < tiles && C < 8) C <<= 1; // cluster of 1, 2, 4 or 8 CTAs per pair
@@ -264,15 +280,36 @@ void launch_factor_eval(cudaStream_t s, FactorParams &p, const float *points, in
     attr[0].val.clusterDim.z = 1;
     cfg.attrs    = attr;
     cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, factor_kernel, p, points, stride4, r, J, valid, out_red, signal, seq);
+    cudaLaunchKernelEx(&cfg, factor_kernel<NP>, d, points, stride4, r, J, valid, out_red, signal, seq);
 }
 
-void launch_chi2(cudaStream_t s, FactorParams &p, const float *points, int stride4, double threshold, int *counters,
+template <int NP>
+void chi2_launch(cudaStream_t s, const FactorParams &p, const float *points, int stride4, double threshold, int *counters,
+                 int *host_counts, unsigned long long *signal, unsigned long long seq) {
+    FactorDev<NP> d;
+    to_dev(p, d);
+    dim3 grid((p.q + 255) / 256, p.n_pairs);
+    chi2_kernel<NP><<<grid, 256, 0, s>>>(d, points, stride4, threshold, counters, host_counts, signal, seq);
+}
+
+} // namespace
+
+void launch_factor_eval(cudaStream_t s, const FactorParams &p, const float *points, int stride4, double *r, double *J,
+                        uint8_t *valid, double *out_red, unsigned long long *signal, unsigned long long seq) {
+    if (p.n_pairs <= 0 || p.q <= 0) return;
+    if (p.n_pairs <= 4) factor_launch<4>(s, p, points, stride4, r, J, valid, out_red, signal, seq);
+    else if (p.n_pairs <= 8) factor_launch<8>(s, p, points, stride4, r, J, valid, out_red, signal, seq);
+    else if (p.n_pairs <= 12) factor_launch<12>(s, p, points, stride4, r, J, valid, out_red, signal, seq);
+    else factor_launch<16>(s, p, points, stride4, r, J, valid, out_red, signal, seq);
+}
+
+void launch_chi2(cudaStream_t s, const FactorParams &p, const float *points, int stride4, double threshold, int *counters,
                  int *host_counts, unsigned long long *signal, unsigned long long seq) {
     if (p.n_pairs <= 0 || p.q <= 0) return;
-    for (int i = 0; i < p.n_pairs; i++) make_pair_const(p, p.pair[i], p.pair[i].pc);
-    dim3 grid((p.q + 255) / 256, p.n_pairs);
-    chi2_kernel<<<grid, 256, 0, s>>>(p, points, stride4, threshold, counters, host_counts, signal, seq);
+    if (p.n_pairs <= 4) chi2_launch<4>(s, p, points, stride4, threshold, counters, host_counts, signal, seq);
+    else if (p.n_pairs <= 8) chi2_launch<8>(s, p, points, stride4, threshold, counters, host_counts, signal, seq);
+    else if (p.n_pairs <= 12) chi2_launch<12>(s, p, points, stride4, threshold, counters, host_counts, signal, seq);
+    else chi2_launch<16>(s, p, points, stride4, threshold, counters, host_counts, signal, seq);
 }
 
 } // namespace fflins

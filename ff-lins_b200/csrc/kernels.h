@@ -130,6 +130,12 @@ struct AssocParams {
     float plane_d2_gate;   // max_search_square_distance, lidar_map.cc:374
     double plane_thr, sigma, scalar_thr, sigma_gate;
     long long *dbg_cycles; // debug: per-(ref, query) warp cycles (nullptr = off)
+    // completion: the last CTA of the plane kernel copies the per-ref counts (AssocRef::counts, zero on entry, zero
+    // again on exit) to host_counts[2 * ref + {0, 1}] (pinned) and releases *signal = seq behind them
+    int *ticket;           // device int, zero on entry / exit
+    int *host_counts;
+    unsigned long long *signal;
+    unsigned long long seq;
     AssocRef ref[kMaxRefs];
 };
 void launch_associate(cudaStream_t s, const AssocParams &p, const float4 *cur_world, const float4 *cur_lidar);
@@ -141,9 +147,17 @@ void launch_plane_estimation(cudaStream_t s, const float4 *pts, int n, double th
 
 // ---- K6 / K7 factors (lidar_factor.cc:41-118, residual_block_info.cc:49-77, marginalization_info.cc:181-210)
 // everything of LidarFactor::Evaluate that depends only on the (ref, cur) pair (math_factor.cuh)
+struct CurConst {           // ... and only on the current frame / extrinsic (shared by every pair of a launch)
+    M3 R1, B1, Rt1, Rbl;
+    V3 tt1, tbl, w1;
+};
+struct RefConst {           // ... and on the reference frame too
+    M3 R0, B0, Rt0, D, E;
+    V3 tt0, w0, dv;
+};
 struct PairConst {
-    M3 R0, B0, Rt0, R1, B1, Rt1, Rbl, D, E;
-    V3 tt0, tt1, tbl, w0, w1, dv;
+    CurConst cur;
+    RefConst ref;
 };
 struct FactorPair {
     const int8_t *type;     // nullptr => every residual valid (stateless batch)
@@ -153,7 +167,6 @@ struct FactorPair {
     const double *std;      // nullptr => sigma below
     double pose_ref[7];
     double v0[3], w0[3], td0;
-    PairConst pc;           // filled on the host by the launchers (make_pair_const)
 };
 struct FactorParams {
     int n_pairs;
@@ -164,20 +177,38 @@ struct FactorParams {
     double sigma, huber_delta;
     FactorPair pair[kMaxRefs];
 };
+// What the kernels receive (__grid_constant__): the host-evaluated constants and the feature arrays, NP pair slots
+// (4, 8, 12 or 16 — kernel parameters are copied per launch, so the block is kept as small as the window allows).
+struct FactorDevPair {
+    const int8_t *type;
+    uint8_t *outlier;
+    const double *normal;
+    const double *d;
+    const double *std;
+    RefConst rc;
+};
+template <int NP> struct FactorDev {
+    int n_pairs;
+    int q;
+    uint32_t flags;
+    double sigma, huber_delta;
+    CurConst cc;
+    FactorDevPair pair[NP];
+};
 constexpr int kFactorBlock = 128;
 constexpr int kRedSize     = 212; // 190 upper-tri H + 19 b + cost0 + cost1 + count
 // points: xyz of cur-frame points as float4 (stride4=1) or packed float3 (stride4=0).
 // r/J/valid (optional) are per (pair, feature): r[pair*q+k], J[22*(pair*q+k)].
-// out_red: n_pairs * kRedSize doubles (nullptr: no reduction). The params are completed in place
-// (PairConst per pair) before the launch. signal (optional, host-mapped like a pinned out_red): signal[pair] = seq
+// out_red: n_pairs * kRedSize doubles (nullptr: no reduction). The pair constants are evaluated on the host
+// (make_pair_const) and passed by value. signal (optional, host-mapped like a pinned out_red): signal[pair] = seq
 // is released at system scope once the pair's kRedSize sums are stored, so the host may poll instead of
 // synchronising the stream.
-void launch_factor_eval(cudaStream_t s, FactorParams &p, const float *points, int stride4, double *r, double *J,
+void launch_factor_eval(cudaStream_t s, const FactorParams &p, const float *points, int stride4, double *r, double *J,
                         uint8_t *valid, double *out_red, unsigned long long *signal = nullptr,
                         unsigned long long seq = 0);
 // counters: kMaxRefs + 1 device ints, zero before the first launch (the kernel leaves them zero); the per-pair
 // outlier counts land in host_counts (pinned) and *signal = seq is released behind them.
-void launch_chi2(cudaStream_t s, FactorParams &p, const float *points, int stride4, double threshold, int *counters,
+void launch_chi2(cudaStream_t s, const FactorParams &p, const float *points, int stride4, double threshold, int *counters,
                  int *host_counts, unsigned long long *signal, unsigned long long seq);
 
 } // namespace fflins

@@ -10,15 +10,17 @@ namespace fflins {
 
 __host__ __device__ __forceinline__ M3 skew_plus_I(V3 v) { return M3{{1.0, -v.z, v.y, v.z, 1.0, -v.x, -v.y, v.x, 1.0}}; }
 
-__host__ __device__ inline void make_pair_const(const FactorParams &P, const FactorPair &pr, PairConst &c) {
+__host__ __device__ inline void make_pair_const(const FactorParams &P, const FactorPair &pr, PairConst &pc) {
+    CurConst &k = pc.cur;
+    RefConst &c = pc.ref;
     V3 t0  = v3(pr.pose_ref[0], pr.pose_ref[1], pr.pose_ref[2]);
     Q4 q0  = Q4{pr.pose_ref[3], pr.pose_ref[4], pr.pose_ref[5], pr.pose_ref[6]};
     V3 t1  = v3(P.pose_cur[0], P.pose_cur[1], P.pose_cur[2]);
     Q4 q1  = Q4{P.pose_cur[3], P.pose_cur[4], P.pose_cur[5], P.pose_cur[6]};
-    c.tbl  = v3(P.ext[0], P.ext[1], P.ext[2]);
+    k.tbl  = v3(P.ext[0], P.ext[1], P.ext[2]);
     Q4 qbl = Q4{P.ext[3], P.ext[4], P.ext[5], P.ext[6]};
     c.w0   = v3(pr.w0[0], pr.w0[1], pr.w0[2]);
-    c.w1   = v3(P.w1[0], P.w1[1], P.w1[2]);
+    k.w1   = v3(P.w1[0], P.w1[1], P.w1[2]);
     V3 v0  = v3(pr.v0[0], pr.v0[1], pr.v0[2]);
     V3 v1  = v3(P.v1[0], P.v1[1], P.v1[2]);
     c.dv   = v1 - v0;
@@ -27,42 +29,42 @@ __host__ __device__ inline void make_pair_const(const FactorParams &P, const Fac
     c.B0  = skew_plus_I(c.w0 * dt0);   // I + [w0 dt0]x   (lidar_factor.cc:59)
     c.Rt0 = mul(c.R0, c.B0);
     c.tt0 = t0 + v0 * dt0;
-    c.R1  = quat_to_R(q1);
-    c.B1  = skew_plus_I(c.w1 * dt1);
-    c.Rt1 = mul(c.R1, c.B1);
-    c.tt1 = t1 + v1 * dt1;
-    c.Rbl = quat_to_R(qbl);
-    M3 A  = mul(transpose(c.Rbl), transpose(c.Rt0));
-    M3 C  = mul(A, c.Rt1);             // `common` (lidar_factor.cc:102)
-    M3 Rblt = transpose(c.Rbl);
+    k.R1  = quat_to_R(q1);
+    k.B1  = skew_plus_I(k.w1 * dt1);
+    k.Rt1 = mul(k.R1, k.B1);
+    k.tt1 = t1 + v1 * dt1;
+    k.Rbl = quat_to_R(qbl);
+    M3 A  = mul(transpose(k.Rbl), transpose(c.Rt0));
+    M3 C  = mul(A, k.Rt1);             // `common` (lidar_factor.cc:102)
+    M3 Rblt = transpose(k.Rbl);
 #pragma unroll
     for (int i = 0; i < 9; i++) c.D.m[i] = C.m[i] - Rblt.m[i];
-    c.E = mul(C, c.Rbl);
+    c.E = mul(C, k.Rbl);
 }
 
 // r and the 19 tangent-space Jacobian entries [ref t, ref th, cur t, cur th, ext t, ext th, td].
 template <bool JAC>
-__host__ __device__ __forceinline__ double eval_residual(const PairConst &c, V3 p, V3 n, double d, double s, double *J) {
-    V3 pb1 = mul(c.Rbl, p) + c.tbl;
-    V3 pw  = mul(c.Rt1, pb1) + c.tt1;
+__host__ __device__ __forceinline__ double eval_residual(const CurConst &k, const RefConst &c, V3 p, V3 n, double d, double s, double *J) {
+    V3 pb1 = mul(k.Rbl, p) + k.tbl;
+    V3 pw  = mul(k.Rt1, pb1) + k.tt1;
     V3 u   = pw - c.tt0;
     V3 pb0 = mulT(c.Rt0, u);
-    V3 pl0 = mulT(c.Rbl, pb0 - c.tbl);
+    V3 pl0 = mulT(k.Rbl, pb0 - k.tbl);
     double r = s * (dot(n, pl0) + d);
     if (JAC) {
         V3 sn = n * s;
-        V3 sc = mul(c.Rbl, sn);           // (s n^T Rbl^T)^T
+        V3 sc = mul(k.Rbl, sn);           // (s n^T Rbl^T)^T
         V3 g0 = mul(c.Rt0, sc);           // (sc^T Rt0^T)^T
         V3 w  = mulT(c.R0, u);            // R0^T (pw - tt0)
         V3 a  = mul(c.B0, sc);
         V3 jr = cross(a, w);              // sc^T B0^T [w]x
-        V3 h  = mulT(c.R1, g0);
-        V3 m  = mul(c.B1, pb1);
+        V3 h  = mulT(k.R1, g0);
+        V3 m  = mul(k.B1, pb1);
         V3 jc = cross(m, h);              // -g0^T R1 [B1 pb1]x
         V3 je = mulT(c.D, sn);            // s n^T (C - Rbl^T)
         V3 kk = mulT(c.E, sn);
         V3 jf = cross(sn, pl0) - cross(kk, p); // s n^T ([pl0]x - C Rbl [p]x)
-        V3 z  = mul(c.R1, cross(c.w1, pb1)) + c.dv;
+        V3 z  = mul(k.R1, cross(k.w1, pb1)) + c.dv;
         double jt = dot(sc, cross(w, c.w0) + mulT(c.Rt0, z));
         J[0] = -g0.x; J[1] = -g0.y; J[2] = -g0.z;
         J[3] = jr.x;  J[4] = jr.y;  J[5] = jr.z;

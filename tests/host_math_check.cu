@@ -59,7 +59,7 @@ int main() {
         PairConst pc;
         make_pair_const(P, P.pair[0], pc);
         double J[19];
-        double r = eval_residual<true>(pc, v3(pf[0], pf[1], pf[2]), v3(n[0], n[1], n[2]), d, 1.0 / sigma, J);
+        double r = eval_residual<true>(pc.cur, pc.ref, v3(pf[0], pf[1], pf[2]), v3(n[0], n[1], n[2]), d, 1.0 / sigma, J);
         const double *par[4] = {P.pair[0].pose_ref, P.pose_cur, P.ext, &P.td};
         double ro, J0[7], J1[7], J2[7], J3[1];
         double *jac[4] = {J0, J1, J2, J3};
