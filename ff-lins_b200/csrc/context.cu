@@ -39,6 +39,7 @@ struct Frame {
     int n_raw = 0, n_fallback = 0;
     bool is_key = false;
     bool hash_pending = false; // map still being built on the map stream: the hash is inserted at first use
+    bool hash_early   = false; // ... unless the map job itself inserted it (table sized from the previous map)
     int pending_slot = -1; // >= 0: counts of the last frame_process still sit in pinned slot (asynchronous mode)
     // keyframe hash (K4)
     MapIndex index; // fine / coarse / super hash tables (hcap slots each)
@@ -120,6 +121,7 @@ struct fflins_ctx : public Profiler {
     VoxelWork vox_map;
     void *vox_map_base = nullptr;
     int *d_map_count = nullptr, *h_map_count = nullptr;
+    int last_map_n = 0; // size of the last keyframe map built on the map stream (sizes the next early index)
     cudaEvent_t ev_main_done = nullptr, ev_map_done = nullptr;
     bool map_job_active = false;
     uint64_t map_job_key = 0;
@@ -303,7 +305,15 @@ int resolve_map(fflins_ctx *ctx) {
     }
     CK(cudaEventSynchronize(ctx->ev_map_done));
     ctx->map_job_active = false;
-    if (Frame *key = find_frame(ctx, ctx->map_job_key)) key->c[FFLINS_CLOUD_MAP].n = ctx->h_map_count[0];
+    if (Frame *key = find_frame(ctx, ctx->map_job_key)) {
+        const int nm = ctx->h_map_count[0];
+        key->c[FFLINS_CLOUD_MAP].n = nm;
+        ctx->last_map_n            = nm;
+        if (key->hash_early) { // the map job built the index too: valid unless the size guess was too small
+            key->hash_early   = false;
+            key->hash_pending = (long long) nm * 10 > (long long) key->hcap * 7;
+        }
+    }
     for (Frame *f : ctx->deferred_frames) free_frame(ctx, f);
     ctx->deferred_frames.clear();
     for (void *b : ctx->deferred_blocks) ctx->pool.release(b);
@@ -714,10 +724,12 @@ int run_associate(fflins_ctx *ctx, const std::vector<Frame *> &refs, Frame *cur,
     int rc;
     for (size_t i = 0; i < refs.size(); i++) {
         Frame *r = refs[i];
-        if (r->hash_pending) { // map built on the map stream: insert its hash now (first use as a reference)
+        if (r->hash_pending || r->hash_early) { // map built on the map stream
             if (ctx->map_job_active && ctx->map_job_key == r->id && (rc = resolve_map(ctx))) return rc;
-            if ((rc = build_hash(ctx, r))) return rc;
-            r->hash_pending = false;
+            if (r->hash_pending) { // no index yet (or its size guess failed): insert it now, at first use as a reference
+                if ((rc = build_hash(ctx, r))) return rc;
+                r->hash_pending = false;
+            }
         }
         if ((rc = ensure_features(ctx, r, q))) return rc;
         if (!r->index.fine && r->c[FFLINS_CLOUD_MAP].n > 0) return fail(ctx, FFLINS_E_INVALID, "reference frame has no map index (fflins_keyframe_add not called)");
@@ -1476,11 +1488,33 @@ int fflins_keyframe_merge(fflins_ctx *ctx, uint64_t key_id, const uint64_t *nonk
         batches.push_back(B);
     }
     full.n = total;
+    // the keyframe's search index is inserted by the map job as well (off the association's critical path): its
+    // tables are sized from the previous keyframe map, the real count is checked when the job is adopted
+    bool early = false;
+    MapIndex early_index{};
+    if (!out && ctx->last_map_n > 0) {
+        int hcap = next_pow2(2 * ctx->last_map_n);
+        if (hcap > key->hcap) {
+            if (key->index.fine) ctx->deferred_blocks.push_back(key->index.fine);
+            if (key->index.coarse) ctx->deferred_blocks.push_back(key->index.coarse);
+            if (key->index.super) ctx->deferred_blocks.push_back(key->index.super);
+            key->index.fine   = (FineSlot *) ctx->pool.alloc((size_t) hcap * sizeof(FineSlot));
+            key->index.coarse = (MaskSlot *) ctx->pool.alloc((size_t) hcap * sizeof(MaskSlot));
+            key->index.super  = (MaskSlot *) ctx->pool.alloc((size_t) hcap * sizeof(MaskSlot));
+            if (!key->index.fine || !key->index.coarse || !key->index.super) return fail(ctx, FFLINS_E_NOMEM, "device allocation failed");
+            key->hcap = hcap;
+        }
+        key->index.hmask = key->hcap - 1;
+        early            = true;
+        early_index      = key->index;
+    }
+    key->hash_early = early;
     // everything below only issues CUDA work on the map stream with the arguments prepared above
     const float4 *in_ptr = full.d;
     float4 *out_ptr      = map.d;
     const bool profiling = ctx->prof_on;
-    auto issue = [ctx, ms, batches, in_ptr, out_ptr, total, profiling]() {
+    const float inv_cell = 1.0f / search_cell(ctx);
+    auto issue = [ctx, ms, batches, in_ptr, out_ptr, total, profiling, early, early_index, inv_cell]() {
         int64_t nl = 0;
         for (const ProjectBatch &B : batches) {
             ProfScope ps(profiling ? ctx : nullptr, "merge_project", ms);
@@ -1490,6 +1524,11 @@ int fflins_keyframe_merge(fflins_ctx *ctx, uint64_t key_id, const uint64_t *nonk
         launch_voxel_downsample(ms, ctx->vox_map, in_ptr, total, (float) ctx->cfg.downsample_size, out_ptr, ctx->d_map_count,
                                 nullptr, &nl, profiling ? ctx : nullptr, "voxel_map");
         cudaMemcpyAsync(ctx->h_map_count, ctx->d_map_count, sizeof(int), cudaMemcpyDeviceToHost, ms);
+        if (early) {
+            ProfScope ps(profiling ? ctx : nullptr, "hash_build", ms);
+            launch_hash_build(ms, out_ptr, total, inv_cell, early_index, ctx->d_map_count);
+            nl += 2;
+        }
         cudaEventRecord(ctx->ev_map_done, ms);
         ctx->launches += nl;
     };
@@ -1518,7 +1557,9 @@ int fflins_keyframe_add(fflins_ctx *ctx, uint64_t key_id) {
     REQUIRE((int) ctx->keyframes.size() < kMaxRefs, "keyframe window is full");
     int rc;
     if (ctx->map_job_active && ctx->map_job_key == key_id) {
-        f->hash_pending = true; // its map is still being built: the hash insert happens at first use as a ref
+        // its map is still being built: the map job inserts the index itself (hash_early) or it happens at first
+        // use as a reference
+        f->hash_pending = !f->hash_early;
     } else if ((rc = build_hash(ctx, f))) {
         return rc;
     }

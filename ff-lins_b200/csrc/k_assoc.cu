@@ -71,7 +71,14 @@ __device__ __forceinline__ void mask_insert(MaskSlot *__restrict__ tab, int hmas
 }
 
 // One fine slot per map point; points sharing a cell occupy consecutive probe positions with equal keys.
-__global__ void hash_insert_kernel(const float4 *__restrict__ map, int m, float inv_cell, MapIndex X) {
+// m_dev (optional): the point count still sits in device memory (map built on the same stream just before); a
+// table that would be loaded above 0.7 is left empty — the host applies the same test and rebuilds it.
+__global__ void hash_insert_kernel(const float4 *__restrict__ map, int m, const int *__restrict__ m_dev, float inv_cell,
+                                   MapIndex X) {
+    if (m_dev) {
+        m = *m_dev;
+        if ((long long) m * 10 > (long long) (X.hmask + 1) * 7) return;
+    }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
         float4 p = __ldg(map + i);
         int ix = (int) floorf(p.x * inv_cell), iy = (int) floorf(p.y * inv_cell), iz = (int) floorf(p.z * inv_cell);
@@ -601,7 +608,7 @@ void init_knn_smem() {
 
 } // namespace
 
-void launch_hash_build(cudaStream_t s, const float4 *map, int m, float inv_cell, MapIndex index) {
+void launch_hash_build(cudaStream_t s, const float4 *map, int m, float inv_cell, MapIndex index, const int *m_dev) {
     const int hcap = index.hmask + 1;
     int g = (hcap + 255) / 256;
     if (g > 148 * 8) g = 148 * 8;
@@ -609,7 +616,7 @@ void launch_hash_build(cudaStream_t s, const float4 *map, int m, float inv_cell,
     if (m > 0) {
         int gi = (m + 255) / 256;
         if (gi > 148 * 8) gi = 148 * 8;
-        hash_insert_kernel<<<gi, 256, 0, s>>>(map, m, inv_cell, index);
+        hash_insert_kernel<<<gi, 256, 0, s>>>(map, m, m_dev, inv_cell, index);
     }
 }
 

@@ -100,7 +100,9 @@ struct MapIndex {
     MaskSlot *super  = nullptr;
     int hmask        = 0;
 };
-void launch_hash_build(cudaStream_t s, const float4 *map, int m, float inv_cell, MapIndex index);
+// m_dev != nullptr: the count is read from device memory (m is then only an upper bound used to size the grid)
+void launch_hash_build(cudaStream_t s, const float4 *map, int m, float inv_cell, MapIndex index,
+                       const int *m_dev = nullptr);
 
 // ---- K5 association (lidar_map.cc:326-408, pointcloud.cc:61-93, ikd_Tree.cc:897-924) -------------------
 struct FeatureSoA {
