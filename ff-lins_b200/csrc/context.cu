@@ -400,7 +400,7 @@ int ensure_ins(fflins_ctx *ctx, int w) {
     if (w <= ctx->ins_cap) return FFLINS_OK;
     ctx->pool.release(ctx->d_tab);
     int cap    = std::max(w, 2048);
-    ctx->d_tab = (double *) ctx->pool.alloc((size_t) cap * kRowSize * sizeof(double)); // interval rows (K1 prologue)
+    ctx->d_tab = (double *) ctx->pool.alloc((size_t) cap * (kRowSize + 1) * sizeof(double)); // interval rows (K1 prologue) + time stamps
     if (!ctx->d_tab) return fail(ctx, FFLINS_E_NOMEM, "device allocation failed");
     ctx->ins_cap = cap;
     return FFLINS_OK;
@@ -527,7 +527,7 @@ int pack_window(fflins_ctx *ctx, const double *ins_t, const double *ins_p, const
                 int *slot_out) {
     const size_t need = (size_t) w * 64;
     if (need > ctx->h_win_slot) {
-        CK(cudaStreamSynchronize(ctx->copy_stream));
+        CK(cudaStreamSynchronize(ctx->stream)); // ins_prep kernels read the ring in place
         if (ctx->h_win) cudaFreeHost(ctx->h_win);
         ctx->h_win_slot = std::max<size_t>(need, 4096 * 64);
         if (cudaMallocHost((void **) &ctx->h_win, ctx->h_win_slot * kWinRing) != cudaSuccess) {
@@ -556,28 +556,25 @@ struct StagedFrame {
     const float4 *d_xyzi = nullptr;
     const double *d_time = nullptr;
     const void *d_aos    = nullptr;
-    const double *d_win  = nullptr;
+    const double *d_win  = nullptr; // pinned ring slot holding the packed INS window (read zero-copy by ins_prep)
+    int wslot            = -1;
 };
 int stage_frame(fflins_ctx *ctx, const float *xyzi, const double *time, const void *aos, int n, const double *ins_t,
                 const double *ins_p, const double *ins_q, int w, StagedFrame *out) {
     int rc;
-    const size_t win_bytes = ((size_t) w * 64 + 255) & ~(size_t) 255;
-    size_t pts_bytes       = aos ? (size_t) n * 32 : (xyzi ? (size_t) n * 24 : 0);
-    pts_bytes              = (pts_bytes + 255) & ~(size_t) 255;
-    char *stage;
-    if ((rc = stage_acquire(ctx, win_bytes + pts_bytes + 256, &stage))) return rc;
     double *hp;
-    int wslot;
-    if ((rc = pack_window(ctx, ins_t, ins_p, ins_q, w, &hp, &wslot))) return rc;
+    if ((rc = pack_window(ctx, ins_t, ins_p, ins_q, w, &hp, &out->wslot))) return rc;
+    out->d_win = hp;
+    if (!aos && !xyzi) return FFLINS_OK; // device-resident points: nothing to copy, no copy-stream traffic at all
+    size_t pts_bytes = aos ? (size_t) n * 32 : (size_t) n * 24;
+    pts_bytes        = (pts_bytes + 255) & ~(size_t) 255;
+    char *pts;
+    if ((rc = stage_acquire(ctx, pts_bytes + 256, &pts))) return rc;
     cudaStream_t cs = ctx->copy_stream;
-    CK(cudaMemcpyAsync(stage, hp, (size_t) w * 64, cudaMemcpyHostToDevice, cs));
-    CK(cudaEventRecord(ctx->win_ev[wslot], cs));
-    out->d_win = (const double *) stage;
-    char *pts  = stage + win_bytes;
     if (aos) {
         if (n > 0) CK(cudaMemcpyAsync(pts, aos, (size_t) n * 32, cudaMemcpyHostToDevice, cs));
         out->d_aos = pts;
-    } else if (xyzi) {
+    } else {
         if (n > 0) {
             CK(cudaMemcpyAsync(pts, xyzi, (size_t) n * 16, cudaMemcpyHostToDevice, cs));
             CK(cudaMemcpyAsync(pts + (size_t) n * 16, time, (size_t) n * 8, cudaMemcpyHostToDevice, cs));
@@ -587,12 +584,8 @@ int stage_frame(fflins_ctx *ctx, const float *xyzi, const double *time, const vo
     }
     return stage_publish(ctx);
 }
-
-// ins_* are HOST pointers (the window is small and produced by the CPU-side INS mechanisation); the
-// point buffers are device pointers. The frame pose at `stamp` (lidar_map.cc:223) is evaluated on the
-// host — one pose, the same fp64 chain as MISC::getPoseFromInsWindow — and handed to the kernels by value.
 int process_core(fflins_ctx *ctx, uint64_t id, const float4 *d_xyzi, const double *d_time, const void *d_aos, int n,
-                 const double *d_win, const double *ins_t, const double *ins_p, const double *ins_q, int w,
+                 const double *d_win, int wslot, const double *ins_t, const double *ins_p, const double *ins_q, int w,
                  const fflins_pose *pose_b_l, double stamp, double td, fflins_frame_info *out) {
     cudaStream_t s = ctx->stream;
     Frame *f       = get_frame(ctx, id);
@@ -609,14 +602,16 @@ int process_core(fflins_ctx *ctx, uint64_t id, const float4 *d_xyzi, const doubl
     std::memcpy(f->pose.R, frame.R, sizeof(frame.R));
     std::memcpy(f->pose.t, frame.t, sizeof(frame.t));
     const double *d_ins_t = d_win, *d_ins_p = d_win + w, *d_ins_q = d_win + 4 * (size_t) w;
+    double *d_t = ctx->d_tab + (size_t) ctx->ins_cap * kRowSize; // device copy of the window's time stamps
     {
         ProfScope ps(ctx->prof(), "ins_prep", s);
-        launch_ins_prep(s, d_ins_t, d_ins_p, d_ins_q, w, ext, frame, ctx->d_tab, ctx->d_counters);
+        launch_ins_prep(s, d_ins_t, d_ins_p, d_ins_q, w, ext, frame, ctx->d_tab, d_t, ctx->d_counters);
         ctx->launches++;
     }
+    if (wslot >= 0) CK(cudaEventRecord(ctx->win_ev[wslot], s)); // the pinned window slot may be repacked after this
     {
         ProfScope ps(ctx->prof(), "undistort", s);
-        launch_undistort(s, d_xyzi, d_time, d_aos, n, d_ins_t, w, ctx->d_tab, td, F, f->c[FFLINS_CLOUD_MAP_FULL].d,
+        launch_undistort(s, d_xyzi, d_time, d_aos, n, d_t, w, ctx->d_tab, td, F, f->c[FFLINS_CLOUD_MAP_FULL].d,
                          f->c[FFLINS_CLOUD_LIDAR_FULL].d, ctx->d_counters);
         if (n > 0) ctx->launches++;
     }
@@ -1029,7 +1024,7 @@ int fflins_frame_process(fflins_ctx *ctx, uint64_t frame_id, const float *xyzi, 
     if ((rc = check_window(ctx, ins_t, w))) return rc;
     StagedFrame sf;
     if ((rc = stage_frame(ctx, xyzi, time, nullptr, n, ins_t, ins_p, ins_q, w, &sf))) return rc;
-    return process_core(ctx, frame_id, sf.d_xyzi, sf.d_time, nullptr, n, sf.d_win, ins_t, ins_p, ins_q, w, pose_b_l, stamp, td,
+    return process_core(ctx, frame_id, sf.d_xyzi, sf.d_time, nullptr, n, sf.d_win, sf.wslot, ins_t, ins_p, ins_q, w, pose_b_l, stamp, td,
                         out);
 }
 
@@ -1042,7 +1037,7 @@ int fflins_frame_process_aos(fflins_ctx *ctx, uint64_t frame_id, const void *poi
     if ((rc = check_window(ctx, ins_t, w))) return rc;
     StagedFrame sf;
     if ((rc = stage_frame(ctx, nullptr, nullptr, points32, n, ins_t, ins_p, ins_q, w, &sf))) return rc;
-    return process_core(ctx, frame_id, nullptr, nullptr, sf.d_aos, n, sf.d_win, ins_t, ins_p, ins_q, w, pose_b_l, stamp, td, out);
+    return process_core(ctx, frame_id, nullptr, nullptr, sf.d_aos, n, sf.d_win, sf.wslot, ins_t, ins_p, ins_q, w, pose_b_l, stamp, td, out);
 }
 
 int fflins_frame_process_dev(fflins_ctx *ctx, uint64_t frame_id, const float *d_xyzi, const double *d_time, int32_t n,
@@ -1054,7 +1049,7 @@ int fflins_frame_process_dev(fflins_ctx *ctx, uint64_t frame_id, const float *d_
     if ((rc = check_window(ctx, ins_t, w))) return rc;
     StagedFrame sf;
     if ((rc = stage_frame(ctx, nullptr, nullptr, nullptr, n, ins_t, ins_p, ins_q, w, &sf))) return rc;
-    return process_core(ctx, frame_id, (const float4 *) d_xyzi, d_time, nullptr, n, sf.d_win, ins_t, ins_p, ins_q, w, pose_b_l,
+    return process_core(ctx, frame_id, (const float4 *) d_xyzi, d_time, nullptr, n, sf.d_win, sf.wslot, ins_t, ins_p, ins_q, w, pose_b_l,
                         stamp, td, out);
 }
 

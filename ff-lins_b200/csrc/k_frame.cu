@@ -23,12 +23,16 @@ namespace {
 
 // One thread per window entry: row i is the closed-form relative pose of interval [i-1, i]; row 0 the
 // out-of-window fallback. The quaternion log (atan2 + divisions) happens here, once per interval.
+// The window is read straight out of the caller's pinned staging slot (zero-copy over PCIe: 64 bytes per entry,
+// no memcpy / event / cross-stream wait in front of the kernel); the time stamps the undistortion kernel needs
+// for its interval lookup are copied to device memory on the way.
 __global__ void ins_prep_kernel(const double *__restrict__ ins_t, const double *__restrict__ ins_p,
                                 const double *__restrict__ ins_q, int w, Pose12 ext, Pose12 frame,
-                                double *__restrict__ rows, int *__restrict__ counters) {
+                                double *__restrict__ rows, double *__restrict__ t_copy, int *__restrict__ counters) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < 4) counters[i] = 0; // per-frame counters (fallbacks, voxel count): saves a memset in the stream
     if (i >= w) return;
+    if (t_copy) t_copy[i] = ins_t[i];
     double row[kRowSize];
     interval_row(ins_t, ins_p, ins_q, w, i, ext, frame, row);
 #pragma unroll
@@ -154,8 +158,8 @@ inline int grid_for(int n, int block, int per_sm = 8) {
 } // namespace
 
 void launch_ins_prep(cudaStream_t s, const double *ins_t, const double *ins_p, const double *ins_q, int w, Pose12 ext,
-                     Pose12 frame_pose, double *rows, int *counters) {
-    ins_prep_kernel<<<(w + 63) / 64, 64, 0, s>>>(ins_t, ins_p, ins_q, w, ext, frame_pose, rows, counters);
+                     Pose12 frame_pose, double *rows, double *t_copy, int *counters) {
+    ins_prep_kernel<<<(w + 63) / 64, 64, 0, s>>>(ins_t, ins_p, ins_q, w, ext, frame_pose, rows, t_copy, counters);
 }
 
 void launch_undistort(cudaStream_t s, const float4 *xyzi, const double *time, const void *aos, int n,

@@ -26,8 +26,9 @@ struct ProfScope {
 // ---- K1 undistort (lidar_map.cc:223-256, misc.cc:27-105, pointcloud.cc:30-59) -------------------
 // rows: kRowSize (42) doubles per window entry, the closed-form relative pose of IMU interval
 // [i-1, i] w.r.t. the frame pose (math_undistort.cuh); row 0 = out-of-window fallback (misc.cc:76-79).
+// ins_t/p/q may be pinned host memory (read zero-copy); t_copy (optional, device, w doubles) receives ins_t.
 void launch_ins_prep(cudaStream_t s, const double *ins_t, const double *ins_p, const double *ins_q, int w,
-                     Pose12 ext, Pose12 frame_pose, double *rows, int *counters /* [4], zeroed here */);
+                     Pose12 ext, Pose12 frame_pose, double *rows, double *t_copy, int *counters /* [4], zeroed here */);
 // aos != nullptr: raw 32-byte PointXYZIT records; else xyzi + time arrays.
 void launch_undistort(cudaStream_t s, const float4 *xyzi, const double *time, const void *aos, int n,
                       const double *ins_t, int w, const double *rows, double td, int filter_num, float4 *out_full,
