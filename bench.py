@@ -273,6 +273,12 @@ def run_ours(args, rank, world, local_rank):
             "chi2": 53 * n_refs * q,
             "reproject": 32 * q,
         }
+        # asynchronous frames share launches (up to 8 per batch): scale the per-launch bytes of the frame stages
+        frames_prof = prof_steps * FRAMES_PER_KEY
+        for g, key in (("undistort", "undistort"), ("voxel_frame", "voxel_frame.one_cta")):
+            cnt = prof.get(key, (0.0, 0))[1]
+            if cnt:
+                alg[g] = int(alg[g] * frames_prof / cnt)
         groups = {}
         for name, (ms, cnt) in prof.items():
             g = name.split(".")[0]

@@ -89,6 +89,19 @@ struct ProfRec {
     cudaEvent_t a, b;
 };
 
+constexpr int kWinRing   = 2 * kFrameBatch;  // pinned INS-window slots
+constexpr int kStageRing = kFrameBatch;      // device staging slots for host-resident points
+constexpr int kGuardRing = 8;
+constexpr unsigned long long kQueued = ~0ull;
+constexpr int kItemScratch = 32;             // ints per batch item: [0..3] counters, [16..31] voxel meta
+
+struct QueuedFrame {
+    Frame *f;
+    FrameItem item;      // scratch pointers are filled in at flush time
+    int wslot;           // pinned window slot
+    int stage_slot;      // device staging slot (-1: device-resident points)
+};
+
 } // namespace
 
 struct fflins_ctx : public Profiler {
@@ -108,10 +121,19 @@ struct fflins_ctx : public Profiler {
     void *d_stage = nullptr;      // kStageRing x stage_cap bytes
     size_t stage_cap = 0;
     cudaStream_t copy_stream = nullptr;
-    cudaEvent_t stage_copied[3] = {nullptr, nullptr, nullptr}, stage_consumed[3] = {nullptr, nullptr, nullptr};
-    int stage_next = 0, stage_cur = -1;
+    int stage_next = 0;
+    cudaEvent_t ev_copied = nullptr;  // copy stream: every host-to-device copy of the queued frames is done
+    // Frame queue: asynchronous fflins_frame_process* calls only stage their inputs; the per-frame kernel chain
+    // is launched for all queued frames at once (flush_frames) by the first call that needs a result.
+    std::vector<QueuedFrame> fq;
+    // batch guards: batch_ev[seq % kGuardRing] is recorded once batch `seq` has consumed its inputs; the pinned
+    // window slots and device staging slots remember the batch that reads them (kQueued = not launched yet)
+    cudaEvent_t batch_ev[kGuardRing] = {};
+    unsigned long long batch_seq = 0;
+    unsigned long long win_guard[kWinRing] = {}, stage_guard[kStageRing] = {};
+    int *d_fscratch = nullptr;        // per batch item: 4 counters + M_SIZE voxel meta ints
     int ins_cap = 0;
-    double *d_tab = nullptr;
+    double *d_tab = nullptr;          // kFrameBatch x ins_cap x (kRowSize + 1) doubles
     int *d_counters = nullptr;      // [64]
     VoxelWork vox;
     void *vox_base = nullptr;
@@ -155,7 +177,6 @@ struct fflins_ctx : public Profiler {
     unsigned char *h_win = nullptr;
     size_t h_win_slot = 0;
     int win_next = 0;
-    cudaEvent_t win_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
     // profiler
     bool prof_on = false;
@@ -219,7 +240,6 @@ struct fflins_ctx : public Profiler {
 namespace {
 
 constexpr int kSlots = 64;
-constexpr int kWinRing = 8;
 
 #define CK(call)                                                                                         \
     do {                                                                                                 \
@@ -276,7 +296,13 @@ Frame *get_frame(fflins_ctx *ctx, uint64_t id) {
 }
 
 // Read back the counts of every frame processed asynchronously (one synchronisation for all of them).
+int flush_frames(fflins_ctx *ctx);
+
 int resolve_pending(fflins_ctx *ctx) {
+    {
+        int rc = flush_frames(ctx);
+        if (rc) return rc;
+    }
     if (ctx->pending.empty()) return FFLINS_OK;
     CK(cudaStreamSynchronize(ctx->stream));
     for (uint64_t id : ctx->pending) {
@@ -352,10 +378,12 @@ void free_frame(fflins_ctx *ctx, Frame *f) {
     delete f;
 }
 
-constexpr int kStageRing = 3;
+int flush_frames(fflins_ctx *ctx);
 
 int ensure_stage(fflins_ctx *ctx, size_t bytes) {
     if (bytes <= ctx->stage_cap) return FFLINS_OK;
+    int rc;
+    if ((rc = flush_frames(ctx))) return rc;
     if (ctx->d_stage) {
         CK(cudaStreamSynchronize(ctx->copy_stream));
         CK(cudaStreamSynchronize(ctx->stream));
@@ -368,39 +396,33 @@ int ensure_stage(fflins_ctx *ctx, size_t bytes) {
         return fail(ctx, FFLINS_E_NOMEM, "device allocation failed");
     }
     ctx->stage_cap = cap;
+    for (auto &g : ctx->stage_guard) g = 0;
     return FFLINS_OK;
 }
 
-// Next slot of the staging ring: the copy stream first waits until the kernels that read the slot's
-// previous content are done. Returns the device pointer; finish with stage_publish().
-int stage_acquire(fflins_ctx *ctx, size_t bytes, char **ptr) {
+// Next slot of the device staging ring: the copy stream first waits until the batch that read the slot's previous
+// content has consumed it (a slot still waiting in the frame queue forces the queue out first).
+int stage_acquire(fflins_ctx *ctx, size_t bytes, char **ptr, int *slot) {
     int rc;
     if ((rc = ensure_stage(ctx, bytes))) return rc;
-    const int k     = ctx->stage_next;
+    const int k = ctx->stage_next;
+    if (ctx->stage_guard[k] == kQueued && (rc = flush_frames(ctx))) return rc;
     ctx->stage_next = (k + 1) % kStageRing;
-    ctx->stage_cur  = k;
-    if (!ctx->stage_copied[k]) {
-        CK(cudaEventCreateWithFlags(&ctx->stage_copied[k], cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&ctx->stage_consumed[k], cudaEventDisableTiming));
-    } else {
-        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->stage_consumed[k], 0));
-    }
-    *ptr = (char *) ctx->d_stage + (size_t) k * ctx->stage_cap;
-    return FFLINS_OK;
-}
-// the compute stream may read the slot once the copies are done
-int stage_publish(fflins_ctx *ctx) {
-    const int k = ctx->stage_cur;
-    CK(cudaEventRecord(ctx->stage_copied[k], ctx->copy_stream));
-    CK(cudaStreamWaitEvent(ctx->stream, ctx->stage_copied[k], 0));
+    if (ctx->stage_guard[k]) CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->batch_ev[ctx->stage_guard[k] % kGuardRing], 0));
+    ctx->stage_guard[k] = kQueued;
+    *ptr  = (char *) ctx->d_stage + (size_t) k * ctx->stage_cap;
+    *slot = k;
     return FFLINS_OK;
 }
 
 int ensure_ins(fflins_ctx *ctx, int w) {
     if (w <= ctx->ins_cap) return FFLINS_OK;
+    int rc;
+    if ((rc = flush_frames(ctx))) return rc;
     ctx->pool.release(ctx->d_tab);
     int cap    = std::max(w, 2048);
-    ctx->d_tab = (double *) ctx->pool.alloc((size_t) cap * (kRowSize + 1) * sizeof(double)); // interval rows (K1 prologue) + time stamps
+    // interval rows (K1 prologue) + time stamps, one set per batch item
+    ctx->d_tab = (double *) ctx->pool.alloc((size_t) kFrameBatch * cap * (kRowSize + 1) * sizeof(double));
     if (!ctx->d_tab) return fail(ctx, FFLINS_E_NOMEM, "device allocation failed");
     ctx->ins_cap = cap;
     return FFLINS_OK;
@@ -479,55 +501,21 @@ void fill_info(Frame *f, fflins_frame_info *out) {
 
 // Shared tail of the two lidarFrameProcessing overloads: voxel filter of the decimated cloud,
 // world projection, result read-back (one synchronisation per frame).
-int frame_tail(fflins_ctx *ctx, Frame *f, int n, int ndec, fflins_frame_info *out) {
-    cudaStream_t s = ctx->stream;
-    int rc;
-    if ((rc = ensure_voxel(ctx, ndec))) return rc;
-    int *d_ndown = ctx->d_counters + 1;
-    // the last kernel of the chain stores the two counts straight into a pinned host slot
-    if ((int) ctx->pending.size() >= kSlots - 1 && (rc = resolve_pending(ctx))) return rc;
-    const int slot = ctx->next_slot;
-    ctx->next_slot = (ctx->next_slot + 1) % kSlots;
-    int *h         = ctx->h_slots + 2 * slot;
-    VoxelTail tail{to12(f->pose), f->c[FFLINS_CLOUD_WORLD].d, h, ctx->d_counters};
-    int64_t nl = 0;
-    int fused  = launch_voxel_downsample(s, ctx->vox, f->c[FFLINS_CLOUD_LIDAR_FULL].d, ndec, (float) ctx->cfg.downsample_size,
-                                         f->c[FFLINS_CLOUD_LIDAR].d, d_ndown, nullptr, &nl, ctx->prof(), "voxel_frame", &tail);
-    ctx->launches += nl;
-    if (fused <= 0) { // large decimated cloud (or empty frame): separate projection kernel
-        ProfScope ps(ctx->prof(), "project_world", s);
-        launch_project(s, to12(f->pose), f->c[FFLINS_CLOUD_LIDAR].d, f->c[FFLINS_CLOUD_WORLD].d, ndec, d_ndown, h,
-                       ctx->d_counters);
-        ctx->launches++;
-    }
-    f->n_raw                        = n;
-    f->n_fallback                   = 0;
-    f->c[FFLINS_CLOUD_MAP_FULL].n   = n;
-    f->c[FFLINS_CLOUD_LIDAR_FULL].n = ndec;
-    f->c[FFLINS_CLOUD_LIDAR].n      = 0;
-    f->c[FFLINS_CLOUD_WORLD].n      = 0;
-    f->c[FFLINS_CLOUD_MAP].n        = 0;
-    f->pending_slot                 = slot;
-    ctx->pending.push_back(f->id);
-    if (!out) return FFLINS_OK; // asynchronous mode: counts are read back by the next call that needs them
-    if ((rc = resolve_pending(ctx))) return rc;
-    fill_info(f, out);
-    return FFLINS_OK;
-}
-
 int check_window(fflins_ctx *ctx, const double *ins_t, int w) {
     REQUIRE(w >= 2 && w <= 65536, "INS window must hold 2..65536 entries");
     for (int i = 1; i < w; i++) REQUIRE(ins_t[i] > ins_t[i - 1], "INS window times must be strictly increasing");
     return FFLINS_OK;
 }
 
-// t | p | q packed into a pinned staging slot (64 B per entry). The slots form a ring guarded by events so
-// that packing window k+1 never overwrites a copy that is still queued on the copy stream.
+// t | p | q packed into a pinned slot (64 B per entry) that the prologue kernel reads in place. The slots form a
+// ring: a slot is repacked only after the batch that read it has run.
 int pack_window(fflins_ctx *ctx, const double *ins_t, const double *ins_p, const double *ins_q, int w, double **hp_out,
                 int *slot_out) {
     const size_t need = (size_t) w * 64;
+    int rc;
     if (need > ctx->h_win_slot) {
-        CK(cudaStreamSynchronize(ctx->stream)); // ins_prep kernels read the ring in place
+        if ((rc = flush_frames(ctx))) return rc;
+        CK(cudaStreamSynchronize(ctx->stream)); // prologue kernels read the ring in place
         if (ctx->h_win) cudaFreeHost(ctx->h_win);
         ctx->h_win_slot = std::max<size_t>(need, 4096 * 64);
         if (cudaMallocHost((void **) &ctx->h_win, ctx->h_win_slot * kWinRing) != cudaSuccess) {
@@ -535,11 +523,13 @@ int pack_window(fflins_ctx *ctx, const double *ins_t, const double *ins_p, const
             ctx->h_win_slot = 0;
             return fail(ctx, FFLINS_E_NOMEM, "pinned allocation failed");
         }
+        for (auto &g : ctx->win_guard) g = 0;
     }
-    const int k   = ctx->win_next;
+    const int k = ctx->win_next;
+    if (ctx->win_guard[k] == kQueued && (rc = flush_frames(ctx))) return rc;
     ctx->win_next = (k + 1) % kWinRing;
-    if (!ctx->win_ev[k]) CK(cudaEventCreateWithFlags(&ctx->win_ev[k], cudaEventDisableTiming));
-    else CK(cudaEventSynchronize(ctx->win_ev[k]));
+    if (ctx->win_guard[k]) CK(cudaEventSynchronize(ctx->batch_ev[ctx->win_guard[k] % kGuardRing]));
+    ctx->win_guard[k] = kQueued;
     double *hp = (double *) (ctx->h_win + (size_t) k * ctx->h_win_slot);
     std::memcpy(hp, ins_t, (size_t) w * 8);
     std::memcpy(hp + w, ins_p, (size_t) w * 24);
@@ -549,78 +539,172 @@ int pack_window(fflins_ctx *ctx, const double *ins_t, const double *ins_p, const
     return FFLINS_OK;
 }
 
-// Stage one frame's inputs in the next slot of the device ring: the INS window always, the points when they
-// are host-resident (xyzi + time, or 32-byte AoS records). EVERY host-to-device copy goes to the copy stream,
-// so the copies of frame k+1 never queue behind kernels of frame k.
-struct StagedFrame {
-    const float4 *d_xyzi = nullptr;
-    const double *d_time = nullptr;
-    const void *d_aos    = nullptr;
-    const double *d_win  = nullptr; // pinned ring slot holding the packed INS window (read zero-copy by ins_prep)
-    int wslot            = -1;
-};
-int stage_frame(fflins_ctx *ctx, const float *xyzi, const double *time, const void *aos, int n, const double *ins_t,
-                const double *ins_p, const double *ins_q, int w, StagedFrame *out) {
-    int rc;
-    double *hp;
-    if ((rc = pack_window(ctx, ins_t, ins_p, ins_q, w, &hp, &out->wslot))) return rc;
-    out->d_win = hp;
-    if (!aos && !xyzi) return FFLINS_OK; // device-resident points: nothing to copy, no copy-stream traffic at all
-    size_t pts_bytes = aos ? (size_t) n * 32 : (size_t) n * 24;
-    pts_bytes        = (pts_bytes + 255) & ~(size_t) 255;
-    char *pts;
-    if ((rc = stage_acquire(ctx, pts_bytes + 256, &pts))) return rc;
-    cudaStream_t cs = ctx->copy_stream;
-    if (aos) {
-        if (n > 0) CK(cudaMemcpyAsync(pts, aos, (size_t) n * 32, cudaMemcpyHostToDevice, cs));
-        out->d_aos = pts;
-    } else {
-        if (n > 0) {
-            CK(cudaMemcpyAsync(pts, xyzi, (size_t) n * 16, cudaMemcpyHostToDevice, cs));
-            CK(cudaMemcpyAsync(pts + (size_t) n * 16, time, (size_t) n * 8, cudaMemcpyHostToDevice, cs));
-        }
-        out->d_xyzi = (const float4 *) pts;
-        out->d_time = (const double *) (pts + (size_t) n * 16);
-    }
-    return stage_publish(ctx);
+// A new batch id; its event is recorded on the compute stream by the caller once the inputs are consumed.
+unsigned long long next_batch(fflins_ctx *ctx) {
+    const unsigned long long seq = ++ctx->batch_seq;
+    if (!ctx->batch_ev[seq % kGuardRing]) cudaEventCreateWithFlags(&ctx->batch_ev[seq % kGuardRing], cudaEventDisableTiming);
+    return seq;
 }
-int process_core(fflins_ctx *ctx, uint64_t id, const float4 *d_xyzi, const double *d_time, const void *d_aos, int n,
-                 const double *d_win, int wslot, const double *ins_t, const double *ins_p, const double *ins_q, int w,
-                 const fflins_pose *pose_b_l, double stamp, double td, fflins_frame_info *out) {
-    cudaStream_t s = ctx->stream;
-    Frame *f       = get_frame(ctx, id);
-    const int F    = ctx->cfg.point_filter_num;
-    const int ndec = (n + F - 1) / F;
+
+// Bookkeeping shared by every frame entry point: clouds sized, counts pending in a pinned slot.
+int frame_begin(fflins_ctx *ctx, Frame *f, int n, int ndec, int **report) {
     int rc;
     if ((rc = ensure_cloud(ctx, f->c[FFLINS_CLOUD_MAP_FULL], n))) return rc;
     if ((rc = ensure_cloud(ctx, f->c[FFLINS_CLOUD_LIDAR_FULL], ndec))) return rc;
     if ((rc = ensure_cloud(ctx, f->c[FFLINS_CLOUD_LIDAR], ndec))) return rc;
     if ((rc = ensure_cloud(ctx, f->c[FFLINS_CLOUD_WORLD], ndec))) return rc;
-    if ((rc = ensure_ins(ctx, w))) return rc;
-    Pose12 ext = to12(*pose_b_l), frame;
-    pose_from_window(ins_t, ins_p, ins_q, w, ext, stamp, frame);
-    std::memcpy(f->pose.R, frame.R, sizeof(frame.R));
-    std::memcpy(f->pose.t, frame.t, sizeof(frame.t));
-    const double *d_ins_t = d_win, *d_ins_p = d_win + w, *d_ins_q = d_win + 4 * (size_t) w;
-    double *d_t = ctx->d_tab + (size_t) ctx->ins_cap * kRowSize; // device copy of the window's time stamps
-    {
-        ProfScope ps(ctx->prof(), "ins_prep", s);
-        launch_ins_prep(s, d_ins_t, d_ins_p, d_ins_q, w, ext, frame, ctx->d_tab, d_t, ctx->d_counters);
+    if ((int) ctx->pending.size() >= kSlots - 1 && (rc = resolve_pending(ctx))) return rc;
+    const int slot = ctx->next_slot;
+    ctx->next_slot = (ctx->next_slot + 1) % kSlots;
+    *report        = ctx->h_slots + 2 * slot;
+    f->n_raw                        = n;
+    f->n_fallback                   = 0;
+    f->c[FFLINS_CLOUD_MAP_FULL].n   = n;
+    f->c[FFLINS_CLOUD_LIDAR_FULL].n = ndec;
+    f->c[FFLINS_CLOUD_LIDAR].n      = 0;
+    f->c[FFLINS_CLOUD_WORLD].n      = 0;
+    f->c[FFLINS_CLOUD_MAP].n        = 0;
+    f->pending_slot                 = slot;
+    ctx->pending.push_back(f->id);
+    return FFLINS_OK;
+}
+
+// Voxel filter + world projection + count report of the batch: one CTA per frame, or the multi-kernel filter
+// for a decimated cloud too large for a single CTA.
+int frame_voxel_tail(fflins_ctx *ctx, const FrameBatch &B) {
+    cudaStream_t s = ctx->stream;
+    bool any_small = false;
+    for (int i = 0; i < B.count; i++) any_small |= B.it[i].ndec <= kVoxSmallCap;
+    if (any_small) {
+        ProfScope ps(ctx->prof(), "voxel_frame.one_cta", s);
+        launch_frame_voxel(s, B);
         ctx->launches++;
     }
-    if (wslot >= 0) CK(cudaEventRecord(ctx->win_ev[wslot], s)); // the pinned window slot may be repacked after this
+    for (int i = 0; i < B.count; i++) {
+        const FrameItem &it = B.it[i];
+        if (it.ndec <= kVoxSmallCap) continue;
+        int rc;
+        if ((rc = ensure_voxel(ctx, it.ndec))) return rc;
+        int64_t nl = 0;
+        launch_voxel_downsample(s, ctx->vox, it.out_dec, it.ndec, (float) ctx->cfg.downsample_size, it.down, it.d_nout, nullptr,
+                                &nl, ctx->prof(), "voxel_frame");
+        ctx->launches += nl;
+        ProfScope ps(ctx->prof(), "project_world", s);
+        launch_project(s, it.frame, it.down, it.world, it.ndec, it.d_nout, it.report, it.counters);
+        ctx->launches++;
+    }
+    return FFLINS_OK;
+}
+
+// Per-item scratch of batch slot i.
+void item_scratch(fflins_ctx *ctx, int i, FrameItem &it) {
+    it.rows     = ctx->d_tab + (size_t) i * ctx->ins_cap * (kRowSize + 1);
+    it.t_dev    = it.rows + (size_t) ctx->ins_cap * kRowSize;
+    it.counters = ctx->d_fscratch + i * kItemScratch;
+    it.d_nout   = it.counters + 1;
+    it.meta     = it.counters + 16;
+}
+
+// Launch the kernel chain of every queued frame: prologue, undistortion, voxel tail — three launches per batch.
+int flush_frames(fflins_ctx *ctx) {
+    if (ctx->fq.empty()) return FFLINS_OK;
+    cudaStream_t s = ctx->stream;
+    FrameBatch B{};
+    B.count     = (int) ctx->fq.size();
+    bool staged = false;
+    for (int i = 0; i < B.count; i++) {
+        B.it[i] = ctx->fq[i].item;
+        item_scratch(ctx, i, B.it[i]);
+        staged |= ctx->fq[i].stage_slot >= 0;
+    }
+    if (staged) { // the points of these frames were copied on the copy stream
+        CK(cudaEventRecord(ctx->ev_copied, ctx->copy_stream));
+        CK(cudaStreamWaitEvent(s, ctx->ev_copied, 0));
+    }
+    {
+        ProfScope ps(ctx->prof(), "ins_prep", s);
+        launch_frame_prologue(s, B);
+        ctx->launches++;
+    }
     {
         ProfScope ps(ctx->prof(), "undistort", s);
-        launch_undistort(s, d_xyzi, d_time, d_aos, n, d_t, w, ctx->d_tab, td, F, f->c[FFLINS_CLOUD_MAP_FULL].d,
-                         f->c[FFLINS_CLOUD_LIDAR_FULL].d, ctx->d_counters);
-        if (n > 0) ctx->launches++;
+        launch_frame_undistort(s, B);
+        ctx->launches++;
     }
-    if (ctx->stage_cur >= 0) { // the raw input of this frame has been consumed: its staging slot may be refilled
-        CK(cudaEventRecord(ctx->stage_consumed[ctx->stage_cur], s));
-        ctx->stage_cur = -1;
+    const unsigned long long seq = next_batch(ctx);
+    CK(cudaEventRecord(ctx->batch_ev[seq % kGuardRing], s)); // window slots and staging slots may be refilled after this
+    for (const QueuedFrame &q : ctx->fq) {
+        ctx->win_guard[q.wslot] = seq;
+        if (q.stage_slot >= 0) ctx->stage_guard[q.stage_slot] = seq;
     }
+    ctx->fq.clear();
+    int rc = frame_voxel_tail(ctx, B);
+    CK(cudaGetLastError());
+    return rc;
+}
+
+// Common body of fflins_frame_process / _aos / _dev: stage the inputs, queue the frame, and (synchronous
+// call, or a full queue) launch.
+int enqueue_frame(fflins_ctx *ctx, uint64_t id, const float *xyzi, const double *time, const void *aos, bool on_device,
+                  int n, const double *ins_t, const double *ins_p, const double *ins_q, int w, const fflins_pose *pose_b_l,
+                  double stamp, double td, fflins_frame_info *out) {
+    int rc;
+    if ((rc = check_window(ctx, ins_t, w))) return rc;
+    Frame *f = get_frame(ctx, id);
+    // one input kind per batch; a frame is queued at most once
+    bool must_flush = (int) ctx->fq.size() >= kFrameBatch;
+    for (const QueuedFrame &q : ctx->fq) must_flush |= q.f == f || (q.item.aos != nullptr) != (aos != nullptr);
+    if (must_flush && (rc = flush_frames(ctx))) return rc;
+    if ((rc = ensure_ins(ctx, w))) return rc;
+    const int F    = ctx->cfg.point_filter_num;
+    const int ndec = (n + F - 1) / F;
+    QueuedFrame q{};
+    q.f          = f;
+    q.stage_slot = -1;
+    FrameItem &it = q.item;
+    double *hp;
+    if ((rc = pack_window(ctx, ins_t, ins_p, ins_q, w, &hp, &q.wslot))) return rc;
+    it.win = hp;
+    it.w   = w;
+    if (on_device || n == 0) {
+        it.xyzi = (const float4 *) xyzi;
+        it.time = time;
+        it.aos  = aos;
+    } else { // host-resident points: every host-to-device copy goes to the copy stream
+        size_t bytes = aos ? (size_t) n * 32 : (size_t) n * 24;
+        char *pts;
+        if ((rc = stage_acquire(ctx, bytes + 256, &pts, &q.stage_slot))) return rc;
+        cudaStream_t cs = ctx->copy_stream;
+        if (aos) {
+            CK(cudaMemcpyAsync(pts, aos, (size_t) n * 32, cudaMemcpyHostToDevice, cs));
+            it.aos = pts;
+        } else {
+            CK(cudaMemcpyAsync(pts, xyzi, (size_t) n * 16, cudaMemcpyHostToDevice, cs));
+            CK(cudaMemcpyAsync(pts + (size_t) n * 16, time, (size_t) n * 8, cudaMemcpyHostToDevice, cs));
+            it.xyzi = (const float4 *) pts;
+            it.time = (const double *) (pts + (size_t) n * 16);
+        }
+    }
+    it.ext = to12(*pose_b_l);
+    pose_from_window(ins_t, ins_p, ins_q, w, it.ext, stamp, it.frame);
+    std::memcpy(f->pose.R, it.frame.R, sizeof(it.frame.R));
+    std::memcpy(f->pose.t, it.frame.t, sizeof(it.frame.t));
     f->td = td;
-    return frame_tail(ctx, f, n, ndec, out);
+    if ((rc = frame_begin(ctx, f, n, ndec, &it.report))) return rc;
+    it.n          = n;
+    it.td         = td;
+    it.filter_num = F;
+    it.out_full   = f->c[FFLINS_CLOUD_MAP_FULL].d;
+    it.out_dec    = f->c[FFLINS_CLOUD_LIDAR_FULL].d;
+    it.ndec       = ndec;
+    it.inv_leaf   = 1.0f / (float) ctx->cfg.downsample_size;
+    it.down       = f->c[FFLINS_CLOUD_LIDAR].d;
+    it.world      = f->c[FFLINS_CLOUD_WORLD].d;
+    ctx->fq.push_back(q);
+    if (!out) return FFLINS_OK; // asynchronous: launched together with the next frames, read back on demand
+    if ((rc = resolve_pending(ctx))) return rc;
+    fill_info(f, out);
+    return FFLINS_OK;
 }
 
 int next_pow2(int v) {
@@ -888,16 +972,18 @@ int fflins_create(const fflins_config *cfg, int device, fflins_ctx **out) {
         cudaStreamCreateWithPriority(&ctx->copy_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaStreamCreateWithPriority(&ctx->map_stream, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_main_done, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_map_done, cudaEventDisableTiming) != cudaSuccess) {
         delete ctx;
         return FFLINS_E_CUDA;
     }
     ctx->d_counters   = (int *) ctx->pool.alloc(64 * sizeof(int));
+    ctx->d_fscratch   = (int *) ctx->pool.alloc(kFrameBatch * kItemScratch * sizeof(int));
     ctx->d_red        = (double *) ctx->pool.alloc((size_t) kMaxRefs * kRedSize * sizeof(double));
     ctx->d_outliers   = (int *) ctx->pool.alloc((kMaxRefs + 1) * sizeof(int));
     ctx->d_map_count  = (int *) ctx->pool.alloc(64);
     ctx->d_assoc_counts = (int *) ctx->pool.alloc((kMaxRefs * 2 + 1) * sizeof(int));
-    if (!ctx->d_counters || !ctx->d_red || !ctx->d_outliers || !ctx->d_map_count || !ctx->d_assoc_counts) {
+    if (!ctx->d_counters || !ctx->d_fscratch || !ctx->d_red || !ctx->d_outliers || !ctx->d_map_count || !ctx->d_assoc_counts) {
         fflins_destroy(ctx);
         return FFLINS_E_NOMEM;
     }
@@ -976,8 +1062,9 @@ void fflins_destroy(fflins_ctx *ctx) {
     if (ctx->ev_map_done) cudaEventDestroy(ctx->ev_map_done);
     if (ctx->map_stream) cudaStreamDestroy(ctx->map_stream);
     if (ctx->h_win) cudaFreeHost(ctx->h_win);
-    for (auto e : ctx->win_ev)
+    for (auto e : ctx->batch_ev)
         if (e) cudaEventDestroy(e);
+    if (ctx->ev_copied) cudaEventDestroy(ctx->ev_copied);
     for (auto &r : ctx->prof_open) {
         cudaEventDestroy(r.a);
         cudaEventDestroy(r.b);
@@ -985,10 +1072,6 @@ void fflins_destroy(fflins_ctx *ctx) {
     for (auto e : ctx->ev_free) cudaEventDestroy(e);
     if (ctx->timer_a) cudaEventDestroy(ctx->timer_a);
     if (ctx->timer_b) cudaEventDestroy(ctx->timer_b);
-    for (int k = 0; k < 3; k++) {
-        if (ctx->stage_copied[k]) cudaEventDestroy(ctx->stage_copied[k]);
-        if (ctx->stage_consumed[k]) cudaEventDestroy(ctx->stage_consumed[k]);
-    }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -1001,6 +1084,10 @@ int fflins_synchronize(fflins_ctx *ctx) {
     {
         int rcm = resolve_map(ctx);
         if (rcm) return rcm;
+    }
+    {
+        int rcf = flush_frames(ctx);
+        if (rcf) return rcf;
     }
     CK(cudaStreamSynchronize(ctx->stream));
     return resolve_pending(ctx);
@@ -1020,12 +1107,7 @@ int fflins_frame_process(fflins_ctx *ctx, uint64_t frame_id, const float *xyzi, 
                          const fflins_pose *pose_b_l, double stamp, double td, fflins_frame_info *out) {
     if (!ctx) return FFLINS_E_INVALID;
     REQUIRE(n >= 0 && (n == 0 || (xyzi && time)) && ins_t && ins_p && ins_q && pose_b_l, "null argument");
-    int rc;
-    if ((rc = check_window(ctx, ins_t, w))) return rc;
-    StagedFrame sf;
-    if ((rc = stage_frame(ctx, xyzi, time, nullptr, n, ins_t, ins_p, ins_q, w, &sf))) return rc;
-    return process_core(ctx, frame_id, sf.d_xyzi, sf.d_time, nullptr, n, sf.d_win, sf.wslot, ins_t, ins_p, ins_q, w, pose_b_l, stamp, td,
-                        out);
+    return enqueue_frame(ctx, frame_id, xyzi, time, nullptr, false, n, ins_t, ins_p, ins_q, w, pose_b_l, stamp, td, out);
 }
 
 int fflins_frame_process_aos(fflins_ctx *ctx, uint64_t frame_id, const void *points32, int32_t n, const double *ins_t,
@@ -1033,11 +1115,7 @@ int fflins_frame_process_aos(fflins_ctx *ctx, uint64_t frame_id, const void *poi
                              double stamp, double td, fflins_frame_info *out) {
     if (!ctx) return FFLINS_E_INVALID;
     REQUIRE(n >= 0 && (n == 0 || points32) && ins_t && ins_p && ins_q && pose_b_l, "null argument");
-    int rc;
-    if ((rc = check_window(ctx, ins_t, w))) return rc;
-    StagedFrame sf;
-    if ((rc = stage_frame(ctx, nullptr, nullptr, points32, n, ins_t, ins_p, ins_q, w, &sf))) return rc;
-    return process_core(ctx, frame_id, nullptr, nullptr, sf.d_aos, n, sf.d_win, sf.wslot, ins_t, ins_p, ins_q, w, pose_b_l, stamp, td, out);
+    return enqueue_frame(ctx, frame_id, nullptr, nullptr, points32, false, n, ins_t, ins_p, ins_q, w, pose_b_l, stamp, td, out);
 }
 
 int fflins_frame_process_dev(fflins_ctx *ctx, uint64_t frame_id, const float *d_xyzi, const double *d_time, int32_t n,
@@ -1045,29 +1123,24 @@ int fflins_frame_process_dev(fflins_ctx *ctx, uint64_t frame_id, const float *d_
                              const fflins_pose *pose_b_l, double stamp, double td, fflins_frame_info *out) {
     if (!ctx) return FFLINS_E_INVALID;
     REQUIRE(n >= 0 && (n == 0 || (d_xyzi && d_time)) && ins_t && ins_p && ins_q && pose_b_l, "null argument");
-    int rc;
-    if ((rc = check_window(ctx, ins_t, w))) return rc;
-    StagedFrame sf;
-    if ((rc = stage_frame(ctx, nullptr, nullptr, nullptr, n, ins_t, ins_p, ins_q, w, &sf))) return rc;
-    return process_core(ctx, frame_id, (const float4 *) d_xyzi, d_time, nullptr, n, sf.d_win, sf.wslot, ins_t, ins_p, ins_q, w, pose_b_l,
-                        stamp, td, out);
+    return enqueue_frame(ctx, frame_id, d_xyzi, d_time, nullptr, true, n, ins_t, ins_p, ins_q, w, pose_b_l, stamp, td, out);
 }
 
 int fflins_frame_process_static(fflins_ctx *ctx, uint64_t frame_id, const float *xyzi, int32_t n, const double state_p[3],
                                 const double state_q[4], const fflins_pose *pose_b_l, fflins_frame_info *out) {
     if (!ctx) return FFLINS_E_INVALID;
     REQUIRE(n >= 0 && (n == 0 || xyzi) && state_p && state_q && pose_b_l, "null argument");
+    int rc;
+    if ((rc = flush_frames(ctx))) return rc;
     cudaStream_t s = ctx->stream;
     Frame *f       = get_frame(ctx, frame_id);
     const int F    = ctx->cfg.point_filter_num;
     const int ndec = (n + F - 1) / F;
-    int rc;
-    if ((rc = ensure_cloud(ctx, f->c[FFLINS_CLOUD_MAP_FULL], n))) return rc;
-    if ((rc = ensure_cloud(ctx, f->c[FFLINS_CLOUD_LIDAR_FULL], ndec))) return rc;
-    if ((rc = ensure_cloud(ctx, f->c[FFLINS_CLOUD_LIDAR], ndec))) return rc;
-    if ((rc = ensure_cloud(ctx, f->c[FFLINS_CLOUD_WORLD], ndec))) return rc;
-    char *stage;
-    if ((rc = stage_acquire(ctx, (size_t) std::max(n, 1) * 16, &stage))) return rc;
+    FrameBatch B{};
+    B.count       = 1;
+    FrameItem &it = B.it[0];
+    if ((rc = ensure_ins(ctx, 2))) return rc;
+    item_scratch(ctx, 0, it);
     // MISC::stateToPoseWithExtrinsic (misc.cc:99-105), host fp64
     {
         Q4 q{state_q[0], state_q[1], state_q[2], state_q[3]};
@@ -1078,20 +1151,36 @@ int fflins_frame_process_static(fflins_ctx *ctx, uint64_t frame_id, const float 
             for (int j = 0; j < 3; j++)
                 f->pose.R[3 * i + j] = (R.m[3 * i] * pose_b_l->R[j] + R.m[3 * i + 1] * pose_b_l->R[3 + j]) + R.m[3 * i + 2] * pose_b_l->R[6 + j];
     }
-    CK(cudaMemsetAsync(ctx->d_counters, 0, 4 * sizeof(int), s));
+    if ((rc = frame_begin(ctx, f, n, ndec, &it.report))) return rc;
+    it.frame    = to12(f->pose);
+    it.out_dec  = f->c[FFLINS_CLOUD_LIDAR_FULL].d;
+    it.ndec     = ndec;
+    it.inv_leaf = 1.0f / (float) ctx->cfg.downsample_size;
+    it.down     = f->c[FFLINS_CLOUD_LIDAR].d;
+    it.world    = f->c[FFLINS_CLOUD_WORLD].d;
+    CK(cudaMemsetAsync(it.counters, 0, 4 * sizeof(int), s));
     if (n > 0) {
+        char *stage;
+        int slot;
+        if ((rc = stage_acquire(ctx, (size_t) n * 16, &stage, &slot))) return rc;
         CK(cudaMemcpyAsync(stage, xyzi, (size_t) n * 16, cudaMemcpyHostToDevice, ctx->copy_stream));
-        if ((rc = stage_publish(ctx))) return rc;
-        ProfScope ps(ctx->prof(), "copy_decimate", s);
-        launch_copy_decimate(s, (const float4 *) stage, n, F, f->c[FFLINS_CLOUD_MAP_FULL].d,
-                             f->c[FFLINS_CLOUD_LIDAR_FULL].d);
-        ctx->launches++;
+        CK(cudaEventRecord(ctx->ev_copied, ctx->copy_stream));
+        CK(cudaStreamWaitEvent(s, ctx->ev_copied, 0));
+        {
+            ProfScope ps(ctx->prof(), "copy_decimate", s);
+            launch_copy_decimate(s, (const float4 *) stage, n, F, f->c[FFLINS_CLOUD_MAP_FULL].d,
+                                 f->c[FFLINS_CLOUD_LIDAR_FULL].d);
+            ctx->launches++;
+        }
+        const unsigned long long seq = next_batch(ctx);
+        CK(cudaEventRecord(ctx->batch_ev[seq % kGuardRing], s));
+        ctx->stage_guard[slot] = seq;
     }
-    if (ctx->stage_cur >= 0) {
-        CK(cudaEventRecord(ctx->stage_consumed[ctx->stage_cur], s));
-        ctx->stage_cur = -1;
-    }
-    return frame_tail(ctx, f, n, ndec, out);
+    if ((rc = frame_voxel_tail(ctx, B))) return rc;
+    if (!out) return FFLINS_OK;
+    if ((rc = resolve_pending(ctx))) return rc;
+    fill_info(f, out);
+    return FFLINS_OK;
 }
 
 int fflins_frame_info_get(fflins_ctx *ctx, uint64_t frame_id, fflins_frame_info *out) {
@@ -1183,6 +1272,10 @@ int fflins_frame_set_motion(fflins_ctx *ctx, uint64_t frame_id, const double v[3
 
 int fflins_frame_release(fflins_ctx *ctx, uint64_t frame_id) {
     if (!ctx) return FFLINS_E_INVALID;
+    {
+        int rcf = flush_frames(ctx); // a queued frame must be launched before its buffers go back to the pool
+        if (rcf) return rcf;
+    }
     auto it = ctx->frames.find(frame_id);
     if (it == ctx->frames.end()) return fail(ctx, FFLINS_E_NOTFOUND, "unknown frame");
     for (auto k : ctx->keyframes)
@@ -1426,7 +1519,8 @@ int fflins_keyframe_merge(fflins_ctx *ctx, uint64_t key_id, const uint64_t *nonk
     if (!ctx) return FFLINS_E_INVALID;
     REQUIRE(n >= 0 && (n == 0 || nonkey_ids), "bad argument");
     int rc;
-    if ((rc = resolve_map(ctx))) return rc; // one map job in flight at a time
+    if ((rc = flush_frames(ctx))) return rc; // the frames being merged may still be queued
+    if ((rc = resolve_map(ctx))) return rc;  // one map job in flight at a time
     Frame *key = find_frame(ctx, key_id);
     if (!key) return fail(ctx, FFLINS_E_NOTFOUND, "unknown keyframe");
     cudaStream_t ms = ctx->map_stream;
@@ -1566,6 +1660,8 @@ int fflins_keyframe_add(fflins_ctx *ctx, uint64_t key_id) {
 static int remove_key(fflins_ctx *ctx, bool oldest, uint64_t *removed_id) {
     REQUIRE(!ctx->keyframes.empty(), "no keyframe in the window");
     {
+        int rcf = flush_frames(ctx);
+        if (rcf) return rcf;
         uint64_t victim = oldest ? ctx->keyframes.front() : ctx->keyframes.back();
         if (ctx->map_job_active && ctx->map_job_key == victim) {
             int rcm = resolve_map(ctx);
@@ -1936,6 +2032,10 @@ int fflins_timer_start(fflins_ctx *ctx) {
 
 int fflins_timer_stop(fflins_ctx *ctx, double *ms) {
     if (!ctx || !ms || !ctx->timer_a) return FFLINS_E_INVALID;
+    {
+        int rcf = flush_frames(ctx); // queued frames belong to the timed region
+        if (rcf) return rcf;
+    }
     CK(cudaEventRecord(ctx->timer_b, ctx->stream));
     CK(cudaEventSynchronize(ctx->timer_b));
     float f = 0;

@@ -26,17 +26,18 @@ namespace {
 // The window is read straight out of the caller's pinned staging slot (zero-copy over PCIe: 64 bytes per entry,
 // no memcpy / event / cross-stream wait in front of the kernel); the time stamps the undistortion kernel needs
 // for its interval lookup are copied to device memory on the way.
-__global__ void ins_prep_kernel(const double *__restrict__ ins_t, const double *__restrict__ ins_p,
-                                const double *__restrict__ ins_q, int w, Pose12 ext, Pose12 frame,
-                                double *__restrict__ rows, double *__restrict__ t_copy, int *__restrict__ counters) {
+__global__ void ins_prep_kernel(const __grid_constant__ FrameBatch B) {
+    const FrameItem &it = B.it[blockIdx.y];
+    const int w = it.w;
+    const double *__restrict__ ins_t = it.win, *__restrict__ ins_p = it.win + w, *__restrict__ ins_q = it.win + 4 * (size_t) w;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < 4) counters[i] = 0; // per-frame counters (fallbacks, voxel count): saves a memset in the stream
+    if (i < 4) it.counters[i] = 0; // per-frame counters (fallbacks, voxel count): saves a memset in the stream
     if (i >= w) return;
-    if (t_copy) t_copy[i] = ins_t[i];
+    it.t_dev[i] = ins_t[i];
     double row[kRowSize];
-    interval_row(ins_t, ins_p, ins_q, w, i, ext, frame, row);
+    interval_row(ins_t, ins_p, ins_q, w, i, it.ext, it.frame, row);
 #pragma unroll
-    for (int k = 0; k < kRowSize; k++) rows[(size_t) i * kRowSize + k] = row[k];
+    for (int k = 0; k < kRowSize; k++) it.rows[(size_t) i * kRowSize + k] = row[k];
 }
 
 struct RawAoS {   // PointXYZIT, ff_lins/lidar/lidar.h:30-38 (32 bytes)
@@ -50,11 +51,19 @@ struct RawAoS {   // PointXYZIT, ff_lins/lidar/lidar.h:30-38 (32 bytes)
 // the 44-double row is fetched once (warp-broadcast out of L1) and applied to both points as it arrives.
 // The first version issued 42 8-byte row loads per point and was bound by load-instruction issue, not HBM.
 template <bool AOS>
-__global__ void __launch_bounds__(256, 3)
-undistort_kernel(const float4 *__restrict__ xyzi, const double *__restrict__ time, const RawAoS *__restrict__ aos,
-                 int n, const double *__restrict__ ins_t, int w, const double *__restrict__ rows, double td,
-                 int filter_num, float4 *__restrict__ out_full, float4 *__restrict__ out_dec,
-                 int *__restrict__ n_fallback) {
+__global__ void __launch_bounds__(256, 3) undistort_kernel(const __grid_constant__ FrameBatch B) {
+    const FrameItem &it = B.it[blockIdx.y];
+    const float4 *__restrict__ xyzi = it.xyzi;
+    const double *__restrict__ time = it.time;
+    const RawAoS *__restrict__ aos  = static_cast<const RawAoS *>(it.aos);
+    const int n = it.n, w = it.w, filter_num = it.filter_num;
+    const double *__restrict__ ins_t = it.t_dev;
+    const double *__restrict__ rows  = it.rows;
+    const double td = it.td;
+    float4 *__restrict__ out_full = it.out_full;
+    float4 *__restrict__ out_dec  = it.out_dec;
+    int *__restrict__ n_fallback  = it.counters;
+    if (n <= 0) return;
     const double t_front = ins_t[0], t_back = ins_t[w - 1];
     const double inv_dt  = (double) (w - 1) / (t_back - t_front);
     const int pairs      = (n + 1) >> 1;
@@ -157,22 +166,20 @@ inline int grid_for(int n, int block, int per_sm = 8) {
 
 } // namespace
 
-void launch_ins_prep(cudaStream_t s, const double *ins_t, const double *ins_p, const double *ins_q, int w, Pose12 ext,
-                     Pose12 frame_pose, double *rows, double *t_copy, int *counters) {
-    ins_prep_kernel<<<(w + 63) / 64, 64, 0, s>>>(ins_t, ins_p, ins_q, w, ext, frame_pose, rows, t_copy, counters);
+void launch_frame_prologue(cudaStream_t s, const FrameBatch &b) {
+    int wmax = 0;
+    for (int i = 0; i < b.count; i++) wmax = b.it[i].w > wmax ? b.it[i].w : wmax;
+    if (b.count <= 0 || wmax <= 0) return;
+    ins_prep_kernel<<<dim3((wmax + 63) / 64, b.count), 64, 0, s>>>(b);
 }
 
-void launch_undistort(cudaStream_t s, const float4 *xyzi, const double *time, const void *aos, int n,
-                      const double *ins_t, int w, const double *rows, double td, int filter_num, float4 *out_full,
-                      float4 *out_dec, int *n_fallback) {
-    if (n <= 0) return;
-    int grid = grid_for((n + 1) / 2, 256, 8);
-    if (aos)
-        undistort_kernel<true><<<grid, 256, 0, s>>>(nullptr, nullptr, static_cast<const RawAoS *>(aos), n, ins_t, w, rows,
-                                                    td, filter_num, out_full, out_dec, n_fallback);
-    else
-        undistort_kernel<false><<<grid, 256, 0, s>>>(xyzi, time, nullptr, n, ins_t, w, rows, td, filter_num, out_full,
-                                                     out_dec, n_fallback);
+void launch_frame_undistort(cudaStream_t s, const FrameBatch &b) {
+    int nmax = 0;
+    for (int i = 0; i < b.count; i++) nmax = b.it[i].n > nmax ? b.it[i].n : nmax;
+    if (b.count <= 0 || nmax <= 0) return;
+    dim3 grid(grid_for((nmax + 1) / 2, 256, 8), b.count);
+    if (b.it[0].aos) undistort_kernel<true><<<grid, 256, 0, s>>>(b);
+    else undistort_kernel<false><<<grid, 256, 0, s>>>(b);
 }
 
 void launch_copy_decimate(cudaStream_t s, const float4 *xyzi, int n, int filter_num, float4 *out_full, float4 *out_dec) {

@@ -420,7 +420,7 @@ seg_centroid_kernel(const float4 *__restrict__ in, const uint32_t *__restrict__ 
 // shared memory -> heads -> ordered centroid. Replaces 18 launch-latency-bound launches for the per-frame
 // filter of ~2-3 k decimated points. (A first version sorted 64-bit composites with a bitonic network:
 // 66 barrier rounds, ~3,000 instructions per warp, issue-bound on its one SM; the radix passes need ~1/4.)
-constexpr int SMALL_CAP     = 4096;
+constexpr int SMALL_CAP     = kVoxSmallCap;
 constexpr int SMALL_THREADS = 1024;
 constexpr int SMALL_ROUNDS  = SMALL_CAP / SMALL_THREADS; // 32-item rounds per warp
 
@@ -436,9 +436,9 @@ struct SmallSmem {
     int total;
 };
 
-__global__ void __launch_bounds__(SMALL_THREADS)
-vox_small_kernel(const float4 *__restrict__ in, int n, float inv, int *__restrict__ meta, float4 *__restrict__ out,
-                 int *__restrict__ d_nout, int32_t *__restrict__ keys_out, bool has_tail, const __grid_constant__ VoxelTail tail) {
+__device__ __forceinline__ void
+vox_small_body(const float4 *__restrict__ in, int n, float inv, int *__restrict__ meta, float4 *__restrict__ out,
+               int *__restrict__ d_nout, int32_t *__restrict__ keys_out, bool has_tail, const VoxelTail &tail) {
     extern __shared__ __align__(16) unsigned char small_raw[];
     SmallSmem &S = *reinterpret_cast<SmallSmem *>(small_raw);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -628,7 +628,45 @@ vox_small_kernel(const float4 *__restrict__ in, int n, float inv, int *__restric
     }
 }
 
+__global__ void __launch_bounds__(SMALL_THREADS)
+vox_small_kernel(const float4 *__restrict__ in, int n, float inv, int *__restrict__ meta, float4 *__restrict__ out,
+                 int *__restrict__ d_nout, int32_t *__restrict__ keys_out, bool has_tail, const __grid_constant__ VoxelTail tail) {
+    vox_small_body(in, n, inv, meta, out, d_nout, keys_out, has_tail, tail);
+}
+
+// one CTA per queued frame: decimated cloud -> voxel centroids -> world projection -> pinned count report
+__global__ void __launch_bounds__(SMALL_THREADS) vox_frame_kernel(const __grid_constant__ FrameBatch B) {
+    const FrameItem &it = B.it[blockIdx.x];
+    if (it.ndec > SMALL_CAP) return; // multi-kernel path, launched by the host for this frame
+    if (it.ndec <= 0) {
+        if (threadIdx.x == 0) {
+            *it.d_nout   = 0;
+            it.report[0] = it.counters[0];
+            it.report[1] = 0;
+        }
+        return;
+    }
+    VoxelTail tail;
+    tail.T        = it.frame;
+    tail.world    = it.world;
+    tail.report   = it.report;
+    tail.counters = it.counters;
+    vox_small_body(it.out_dec, it.ndec, it.inv_leaf, it.meta, it.down, it.d_nout, nullptr, true, tail);
+}
+
 } // namespace
+
+void launch_frame_voxel(cudaStream_t s, const FrameBatch &b) {
+    if (b.count <= 0) return;
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev & 63]) {
+        cudaFuncSetAttribute(vox_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(SmallSmem));
+        attr_set[dev & 63] = true;
+    }
+    vox_frame_kernel<<<b.count, SMALL_THREADS, sizeof(SmallSmem), s>>>(b);
+}
 
 size_t voxel_work_bytes(int cap, size_t *off) {
     auto al = [](size_t x) { return (x + 255) & ~(size_t) 255; };

@@ -23,16 +23,47 @@ struct ProfScope {
     }
 };
 
-// ---- K1 undistort (lidar_map.cc:223-256, misc.cc:27-105, pointcloud.cc:30-59) -------------------
-// rows: kRowSize (42) doubles per window entry, the closed-form relative pose of IMU interval
-// [i-1, i] w.r.t. the frame pose (math_undistort.cuh); row 0 = out-of-window fallback (misc.cc:76-79).
-// ins_t/p/q may be pinned host memory (read zero-copy); t_copy (optional, device, w doubles) receives ins_t.
-void launch_ins_prep(cudaStream_t s, const double *ins_t, const double *ins_p, const double *ins_q, int w,
-                     Pose12 ext, Pose12 frame_pose, double *rows, double *t_copy, int *counters /* [4], zeroed here */);
-// aos != nullptr: raw 32-byte PointXYZIT records; else xyzi + time arrays.
-void launch_undistort(cudaStream_t s, const float4 *xyzi, const double *time, const void *aos, int n,
-                      const double *ins_t, int w, const double *rows, double td, int filter_num, float4 *out_full,
-                      float4 *out_dec, int *n_fallback);
+// ---- K1 undistort (lidar_map.cc:223-256, misc.cc:27-105, pointcloud.cc:30-59) + per-frame K2/K3 -----
+// The per-frame chain (interval rows -> undistortion + decimation -> single-CTA voxel filter + world
+// projection) is launched for up to kFrameBatch queued frames at once: blockIdx.y (blockIdx.x for the voxel
+// filter) selects the frame. A lone 150k-point frame keeps ~1/10 of the GPU busy for ~40 us of dependent
+// launches; frames queued by asynchronous fflins_frame_process* calls share those three launches.
+// rows: kRowSize doubles per window entry, the closed-form relative pose of IMU interval [i-1, i] w.r.t. the
+// frame pose (math_undistort.cuh); row 0 = out-of-window fallback (misc.cc:76-79).
+constexpr int kFrameBatch  = 8;
+constexpr int kVoxSmallCap = 4096; // largest decimated cloud the single-CTA voxel filter takes
+struct FrameItem {
+    // prologue: the packed window [t(w) | p(3w) | q(4w)] may be pinned host memory (read zero-copy)
+    const double *win;
+    int w;
+    Pose12 ext, frame;
+    double *rows;        // [w][kRowSize]
+    double *t_dev;       // [w] device copy of the time stamps for the interval lookup
+    int *counters;       // [4] zeroed by the prologue; [0] = out-of-window fallbacks
+    // undistortion: aos != nullptr: raw 32-byte PointXYZIT records; else xyzi + time arrays
+    const float4 *xyzi;
+    const double *time;
+    const void *aos;
+    int n;
+    double td;
+    int filter_num;
+    float4 *out_full, *out_dec;
+    // voxel filter of the decimated cloud + world projection + count report (pinned, 2 ints)
+    int ndec;
+    float inv_leaf;
+    float4 *down, *world;
+    int *report;
+    int *meta;           // [M_SIZE] scratch
+    int *d_nout;
+};
+struct FrameBatch {
+    int count;
+    FrameItem it[kFrameBatch];
+};
+void launch_frame_prologue(cudaStream_t s, const FrameBatch &b);
+void launch_frame_undistort(cudaStream_t s, const FrameBatch &b); // every item of one input kind (aos or not)
+// items with ndec > kVoxSmallCap are skipped (the caller runs the multi-kernel filter for them)
+void launch_frame_voxel(cudaStream_t s, const FrameBatch &b);
 // static overload (lidar_map.cc:275-324): copy + decimate
 void launch_copy_decimate(cudaStream_t s, const float4 *xyzi, int n, int filter_num, float4 *out_full,
                           float4 *out_dec);

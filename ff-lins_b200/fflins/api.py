@@ -162,6 +162,28 @@ class Context:
                                                  C.c_double(stamp), C.c_double(td), C.byref(info) if sync else None))
         return info
 
+    # Argument tuples converted once per frame ("prepared" calls): what a C++ caller pays per call. The tuple keeps
+    # the arrays alive; asynchronous mode only (out = NULL).
+    @staticmethod
+    def prepare_frame_dev(d_xyzi, d_time, n, ins_t, ins_p, ins_q, pose_bl, stamp, td):
+        keep = (ins_t, ins_p, ins_q, pose_bl)
+        return (C.c_void_p(d_xyzi), C.c_void_p(d_time), n, _p(ins_t), _p(ins_p), _p(ins_q), len(ins_t), C.byref(pose_bl),
+                C.c_double(stamp), C.c_double(td), None), keep
+
+    def frame_process_dev_prepared(self, fid, prep):
+        self._ck(self.L.fflins_frame_process_dev(self.h, C.c_uint64(fid), *prep[0]))
+
+    @staticmethod
+    def prepare_frame(xyzi, time, ins_t, ins_p, ins_q, pose_bl, stamp, td):
+        xyzi, time = _c(xyzi, np.float32), _c(time, np.float64)
+        ins_t, ins_p, ins_q = _c(ins_t, np.float64), _c(ins_p, np.float64), _c(ins_q, np.float64)
+        keep = (xyzi, time, ins_t, ins_p, ins_q, pose_bl)
+        return (_p(xyzi), _p(time), len(time), _p(ins_t), _p(ins_p), _p(ins_q), len(ins_t), C.byref(pose_bl),
+                C.c_double(stamp), C.c_double(td), None), keep
+
+    def frame_process_prepared(self, fid, prep):
+        self._ck(self.L.fflins_frame_process(self.h, C.c_uint64(fid), *prep[0]))
+
     def frame_process_static(self, fid, xyzi, p, q, R_bl, t_bl):
         xyzi = _c(xyzi, np.float32)
         info = FrameInfo()
@@ -291,10 +313,12 @@ class Context:
         return rid.value
 
     def keyframe_ids(self):
-        n = C.c_int32()
-        ids = np.zeros(16, np.uint64)
-        self._ck(self.L.fflins_keyframe_ids(self.h, _p(ids), 16, C.byref(n)))
-        return [int(x) for x in ids[:n.value]]
+        buf = self.__dict__.get("_ids_buf")
+        if buf is None:
+            buf = self.__dict__["_ids_buf"] = ((C.c_uint64 * 16)(), C.c_int32())
+        ids, n = buf
+        self._ck(self.L.fflins_keyframe_ids(self.h, ids, 16, C.byref(n)))
+        return ids[:n.value]
 
     # ---- association --------------------------------------------------------------------------------
     def associate(self):
@@ -383,6 +407,13 @@ class Context:
             out[k + "_p"] = _p(out[k])
         prep = dict(n=n, ids=ids, refs=refs, cur=cur, ext=ex, ids_p=_p(ids), refs_p=_p(refs), cur_p=_p(cur), ext_p=_p(ex))
         return prep, out
+
+    def window_chi2_prepared(self, prep, td, threshold=3.841):
+        """prep from prepare_window; returns the per-pair outlier counts."""
+        cnt = np.zeros(max(prep["n"], 1), np.int32)
+        self._ck(self.L.fflins_window_chi2(self.h, prep["n"], prep["ids_p"], prep["refs_p"], prep["cur_p"], prep["ext_p"],
+                                           C.c_double(td), C.c_double(threshold), _p(cnt)))
+        return cnt[:prep["n"]]
 
     def window_chi2(self, ref_ids, pose_refs, pose_cur, ext, td, threshold=3.841):
         ids = np.array(list(ref_ids), np.uint64)

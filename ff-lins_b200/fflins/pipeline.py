@@ -59,17 +59,32 @@ class Session:
     def process_frame(self, fr):
         fid = self.next_id
         self.next_id += 1
+        if not self.sync_frames:   # asynchronous: the ctypes argument tuple is built once per frame dict
+            prep = fr.get("_prep_host")
+            if prep is None:
+                prep = fr["_prep_host"] = api.Context.prepare_frame(fr["xyzi"], fr["time"], fr["ins_t"], fr["ins_p"],
+                                                                    fr["ins_q"], self.pose_bl, fr["stamp"], fr["td"])
+            self.ctx.frame_process_prepared(fid, prep)
+            return fid, None
         info = self.ctx.frame_process(fid, fr["xyzi"], fr["time"], fr["ins_t"], fr["ins_p"], fr["ins_q"],
-                                      self.pose_bl, None, fr["stamp"], fr["td"], sync=self.sync_frames)
+                                      self.pose_bl, None, fr["stamp"], fr["td"], sync=True)
         return fid, info
 
     def process_frame_dev(self, fr_dev):
         """fr_dev: raw device pointers of the point data (resident in HBM) + host INS window + scalars."""
         fid = self.next_id
         self.next_id += 1
+        if not self.sync_frames:
+            prep = fr_dev.get("_prep_dev")
+            if prep is None:
+                prep = fr_dev["_prep_dev"] = api.Context.prepare_frame_dev(
+                    fr_dev["xyzi"], fr_dev["time"], fr_dev["n"], fr_dev["ins_t"], fr_dev["ins_p"], fr_dev["ins_q"],
+                    self.pose_bl, fr_dev["stamp"], fr_dev["td"])
+            self.ctx.frame_process_dev_prepared(fid, prep)
+            return fid, None
         info = self.ctx.frame_process_dev(fid, fr_dev["xyzi"], fr_dev["time"], fr_dev["n"], fr_dev["ins_t"],
                                           fr_dev["ins_p"], fr_dev["ins_q"], self.pose_bl, fr_dev["stamp"],
-                                          fr_dev["td"], sync=self.sync_frames)
+                                          fr_dev["td"], sync=True)
         return fid, info
 
     def after_frame(self, fid, fr, force_key=None):
@@ -99,7 +114,7 @@ class Session:
             # first solve: n_eval[0] LM iterations' worth of evaluations
             for _ in range(self.n_eval[0]):
                 ctx.window_eval_prepared(prep, fr["td"], self.flags, out)
-            self.last["chi2"] = ctx.window_chi2(refs, pose_refs, pose_cur, self.ext7, fr["td"])
+            self.last["chi2"] = ctx.window_chi2_prepared(prep, fr["td"])
             for _ in range(self.n_eval[1]):
                 ctx.window_eval_prepared(prep, fr["td"], self.flags, out)
             self.last["eval"] = out
