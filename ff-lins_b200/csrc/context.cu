@@ -41,6 +41,7 @@ struct Frame {
     bool hash_pending = false; // map still being built on the map stream: the hash is inserted at first use
     bool hash_early   = false; // ... unless the map job itself inserted it (table sized from the previous map)
     int pending_slot = -1; // >= 0: counts of the last frame_process still sit in pinned slot (asynchronous mode)
+    bool bg = false;       // its kernel chain runs on the copy stream behind its own host-to-device copy (see flush_frames)
     // keyframe hash (K4)
     MapIndex index; // fine / coarse / super hash tables (hcap slots each)
     int hcap                  = 0;
@@ -100,6 +101,11 @@ struct QueuedFrame {
     FrameItem item;      // scratch pointers are filled in at flush time
     int wslot;           // pinned window slot
     int stage_slot;      // device staging slot (-1: device-resident points)
+    // pinned host points: the copies are issued at flush time (newest frame first); n_copy = 0: nothing deferred
+    int n_copy;
+    const void *h_src[2];
+    char *d_dst[2];
+    size_t bytes[2];
 };
 
 } // namespace
@@ -122,7 +128,10 @@ struct fflins_ctx : public Profiler {
     size_t stage_cap = 0;
     cudaStream_t copy_stream = nullptr;
     int stage_next = 0;
-    cudaEvent_t ev_copied = nullptr;  // copy stream: every host-to-device copy of the queued frames is done
+    cudaEvent_t ev_copied = nullptr;  // copy stream: the host-to-device copies the compute stream waits for are done
+    cudaEvent_t ev_bg_done = nullptr; // copy stream: the background part of the last split batch is done
+    bool bg_active = false;           // ... and nobody has waited for it yet
+    unsigned long long last_main_seq = 0;
     // Frame queue: asynchronous fflins_frame_process* calls only stage their inputs; the per-frame kernel chain
     // is launched for all queued frames at once (flush_frames) by the first call that needs a result.
     std::vector<QueuedFrame> fq;
@@ -298,26 +307,44 @@ Frame *get_frame(fflins_ctx *ctx, uint64_t id) {
 // Read back the counts of every frame processed asynchronously (one synchronisation for all of them).
 int flush_frames(fflins_ctx *ctx);
 
-int resolve_pending(fflins_ctx *ctx) {
+// The compute stream joins the background part of a split batch (flush_frames): later work on it may touch those frames.
+int join_bg(fflins_ctx *ctx) {
+    if (!ctx->bg_active) return FFLINS_OK;
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_bg_done, 0));
+    ctx->bg_active = false;
+    for (auto &kv : ctx->frames) kv.second->bg = false;
+    for (Frame *f : ctx->deferred_frames) f->bg = false;
+    return FFLINS_OK;
+}
+
+// Read back the counts of every frame processed asynchronously (one synchronisation for all of them).
+// all = false: only the frames whose chain ran on the compute stream — the background frames of a split batch stay
+// pending, so that the caller (association, factor evaluation of the newest keyframe) does not wait for their copies.
+int resolve_pending(fflins_ctx *ctx, bool all = true) {
     {
         int rc = flush_frames(ctx);
         if (rc) return rc;
+        if (all && (rc = join_bg(ctx))) return rc;
     }
     if (ctx->pending.empty()) return FFLINS_OK;
     CK(cudaStreamSynchronize(ctx->stream));
+    std::vector<uint64_t> keep;
     for (uint64_t id : ctx->pending) {
         Frame *f = find_frame(ctx, id);
         if (!f || f->pending_slot < 0) continue;
+        if (f->bg) {
+            keep.push_back(id);
+            continue;
+        }
         const int *cnt                 = ctx->h_slots + 2 * f->pending_slot;
         f->n_fallback                  = cnt[0];
         f->c[FFLINS_CLOUD_LIDAR].n     = cnt[1];
         f->c[FFLINS_CLOUD_WORLD].n     = cnt[1];
         f->pending_slot                = -1;
     }
-    ctx->pending.clear();
+    ctx->pending.swap(keep);
     return FFLINS_OK;
 }
-
 void free_frame(fflins_ctx *ctx, Frame *f);
 
 // Wait for the keyframe-map job on the map stream (if any), adopt its voxel count and free what had to
@@ -408,6 +435,7 @@ int stage_acquire(fflins_ctx *ctx, size_t bytes, char **ptr, int *slot) {
     const int k = ctx->stage_next;
     if (ctx->stage_guard[k] == kQueued && (rc = flush_frames(ctx))) return rc;
     ctx->stage_next = (k + 1) % kStageRing;
+    // (copies are FIFO on the copy stream, so waiting here also covers a copy that is issued later, at flush time)
     if (ctx->stage_guard[k]) CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->batch_ev[ctx->stage_guard[k] % kGuardRing], 0));
     ctx->stage_guard[k] = kQueued;
     *ptr  = (char *) ctx->d_stage + (size_t) k * ctx->stage_cap;
@@ -571,8 +599,7 @@ int frame_begin(fflins_ctx *ctx, Frame *f, int n, int ndec, int **report) {
 
 // Voxel filter + world projection + count report of the batch: one CTA per frame, or the multi-kernel filter
 // for a decimated cloud too large for a single CTA.
-int frame_voxel_tail(fflins_ctx *ctx, const FrameBatch &B) {
-    cudaStream_t s = ctx->stream;
+int frame_voxel_tail(fflins_ctx *ctx, cudaStream_t s, const FrameBatch &B) {
     bool any_small = false;
     for (int i = 0; i < B.count; i++) any_small |= B.it[i].ndec <= kVoxSmallCap;
     if (any_small) {
@@ -605,22 +632,9 @@ void item_scratch(fflins_ctx *ctx, int i, FrameItem &it) {
     it.meta     = it.counters + 16;
 }
 
-// Launch the kernel chain of every queued frame: prologue, undistortion, voxel tail — three launches per batch.
-int flush_frames(fflins_ctx *ctx) {
-    if (ctx->fq.empty()) return FFLINS_OK;
-    cudaStream_t s = ctx->stream;
-    FrameBatch B{};
-    B.count     = (int) ctx->fq.size();
-    bool staged = false;
-    for (int i = 0; i < B.count; i++) {
-        B.it[i] = ctx->fq[i].item;
-        item_scratch(ctx, i, B.it[i]);
-        staged |= ctx->fq[i].stage_slot >= 0;
-    }
-    if (staged) { // the points of these frames were copied on the copy stream
-        CK(cudaEventRecord(ctx->ev_copied, ctx->copy_stream));
-        CK(cudaStreamWaitEvent(s, ctx->ev_copied, 0));
-    }
+// Prologue, undistortion and voxel tail of one batch on stream s; *seq_out = the batch id whose event guards the
+// batch's window and staging slots.
+int launch_chain(fflins_ctx *ctx, cudaStream_t s, const FrameBatch &B, unsigned long long *seq_out) {
     {
         ProfScope ps(ctx->prof(), "ins_prep", s);
         launch_frame_prologue(s, B);
@@ -633,14 +647,93 @@ int flush_frames(fflins_ctx *ctx) {
     }
     const unsigned long long seq = next_batch(ctx);
     CK(cudaEventRecord(ctx->batch_ev[seq % kGuardRing], s)); // window slots and staging slots may be refilled after this
-    for (const QueuedFrame &q : ctx->fq) {
-        ctx->win_guard[q.wslot] = seq;
-        if (q.stage_slot >= 0) ctx->stage_guard[q.stage_slot] = seq;
+    *seq_out = seq;
+    return FFLINS_OK;
+}
+
+int issue_copies(fflins_ctx *ctx, const QueuedFrame &q) {
+    for (int c = 0; c < q.n_copy; c++)
+        CK(cudaMemcpyAsync(q.d_dst[c], q.h_src[c], q.bytes[c], cudaMemcpyHostToDevice, ctx->copy_stream));
+    return FFLINS_OK;
+}
+
+// Launch the kernel chain of every queued frame: prologue, undistortion, voxel tail — three launches per batch.
+//
+// Batches whose points come from pinned host memory are SPLIT: the newest frame (the one the caller is about to use:
+// association and factor evaluation only ever need the current keyframe) is copied first and processed on the compute
+// stream; the older frames of the batch — which only feed the keyframe-map merge — are copied behind it and processed
+// on the copy stream, so that their PCIe time overlaps the solver instead of preceding it.
+int flush_frames(fflins_ctx *ctx) {
+    if (ctx->fq.empty()) return FFLINS_OK;
+    cudaStream_t s = ctx->stream, cs = ctx->copy_stream;
+    const int count = (int) ctx->fq.size();
+    const int L     = count - 1;
+    int rc;
+    if ((rc = join_bg(ctx))) return rc; // scratch slots and stream order: one background part at a time
+    const bool split = count >= 2 && ctx->fq[L].n_copy > 0 && !ctx->prof_on;
+    bool staged = false;
+    for (const QueuedFrame &q : ctx->fq) staged |= q.stage_slot >= 0;
+    FrameBatch B{};
+    if (!split) {
+        B.count = count;
+        for (int i = 0; i < count; i++) {
+            B.it[i] = ctx->fq[i].item;
+            item_scratch(ctx, i, B.it[i]);
+            if ((rc = issue_copies(ctx, ctx->fq[i]))) return rc;
+        }
+        if (staged) { // the points of these frames travel on the copy stream
+            CK(cudaEventRecord(ctx->ev_copied, cs));
+            CK(cudaStreamWaitEvent(s, ctx->ev_copied, 0));
+        }
+        unsigned long long seq;
+        if ((rc = launch_chain(ctx, s, B, &seq))) return rc;
+        for (const QueuedFrame &q : ctx->fq) {
+            ctx->win_guard[q.wslot] = seq;
+            if (q.stage_slot >= 0) ctx->stage_guard[q.stage_slot] = seq;
+        }
+        ctx->last_main_seq = seq;
+        ctx->fq.clear();
+        rc = frame_voxel_tail(ctx, s, B);
+        CK(cudaGetLastError());
+        return rc;
+    }
+    // newest frame: its copy goes first, the compute stream runs its chain
+    const QueuedFrame &ql = ctx->fq[L];
+    if ((rc = issue_copies(ctx, ql))) return rc;
+    CK(cudaEventRecord(ctx->ev_copied, cs));
+    CK(cudaStreamWaitEvent(s, ctx->ev_copied, 0));
+    B.count = 1;
+    B.it[0] = ql.item;
+    item_scratch(ctx, L, B.it[0]);
+    unsigned long long seq;
+    if ((rc = launch_chain(ctx, s, B, &seq))) return rc;
+    ctx->win_guard[ql.wslot]       = seq;
+    ctx->stage_guard[ql.stage_slot] = seq;
+    if ((rc = frame_voxel_tail(ctx, s, B))) return rc;
+    // the rest: copies and kernels in FIFO order on the copy stream (their scratch slots 0..L-1 were last used by
+    // the previous batch on the compute stream)
+    if (ctx->last_main_seq) CK(cudaStreamWaitEvent(cs, ctx->batch_ev[ctx->last_main_seq % kGuardRing], 0));
+    ctx->last_main_seq = seq;
+    FrameBatch G{};
+    G.count = L;
+    for (int i = 0; i < L; i++) {
+        G.it[i] = ctx->fq[i].item;
+        item_scratch(ctx, i, G.it[i]);
+        if ((rc = issue_copies(ctx, ctx->fq[i]))) return rc;
+        ctx->fq[i].f->bg = true;
+    }
+    unsigned long long seq_bg;
+    if ((rc = launch_chain(ctx, cs, G, &seq_bg))) return rc;
+    for (int i = 0; i < L; i++) {
+        ctx->win_guard[ctx->fq[i].wslot] = seq_bg;
+        if (ctx->fq[i].stage_slot >= 0) ctx->stage_guard[ctx->fq[i].stage_slot] = seq_bg;
     }
     ctx->fq.clear();
-    int rc = frame_voxel_tail(ctx, B);
+    if ((rc = frame_voxel_tail(ctx, cs, G))) return rc;
+    CK(cudaEventRecord(ctx->ev_bg_done, cs));
+    ctx->bg_active = true;
     CK(cudaGetLastError());
-    return rc;
+    return FFLINS_OK;
 }
 
 // Common body of fflins_frame_process / _aos / _dev: stage the inputs, queue the frame, and (synchronous
@@ -674,15 +767,35 @@ int enqueue_frame(fflins_ctx *ctx, uint64_t id, const float *xyzi, const double 
         size_t bytes = aos ? (size_t) n * 32 : (size_t) n * 24;
         char *pts;
         if ((rc = stage_acquire(ctx, bytes + 256, &pts, &q.stage_slot))) return rc;
-        cudaStream_t cs = ctx->copy_stream;
         if (aos) {
-            CK(cudaMemcpyAsync(pts, aos, (size_t) n * 32, cudaMemcpyHostToDevice, cs));
-            it.aos = pts;
+            q.n_copy   = 1;
+            q.h_src[0] = aos;
+            q.d_dst[0] = pts;
+            q.bytes[0] = (size_t) n * 32;
+            it.aos     = pts;
         } else {
-            CK(cudaMemcpyAsync(pts, xyzi, (size_t) n * 16, cudaMemcpyHostToDevice, cs));
-            CK(cudaMemcpyAsync(pts + (size_t) n * 16, time, (size_t) n * 8, cudaMemcpyHostToDevice, cs));
-            it.xyzi = (const float4 *) pts;
-            it.time = (const double *) (pts + (size_t) n * 16);
+            q.n_copy   = 2;
+            q.h_src[0] = xyzi;
+            q.d_dst[0] = pts;
+            q.bytes[0] = (size_t) n * 16;
+            q.h_src[1] = time;
+            q.d_dst[1] = pts + (size_t) n * 16;
+            q.bytes[1] = (size_t) n * 8;
+            it.xyzi    = (const float4 *) pts;
+            it.time    = (const double *) (pts + (size_t) n * 16);
+        }
+        // Pinned (page-locked / registered) buffers are copied when the batch is launched, newest frame first: an
+        // asynchronous copy from pinned memory already obliges the caller to keep the buffer until the frame's results
+        // are consumed. Pageable buffers are copied now (the runtime stages them before cudaMemcpyAsync returns).
+        bool pinned = !out;
+        for (int c = 0; c < q.n_copy && pinned; c++) {
+            cudaPointerAttributes at{};
+            pinned = cudaPointerGetAttributes(&at, q.h_src[c]) == cudaSuccess && at.type == cudaMemoryTypeHost;
+        }
+        cudaGetLastError();
+        if (!pinned) {
+            if ((rc = issue_copies(ctx, q))) return rc;
+            q.n_copy = 0;
         }
     }
     it.ext = to12(*pose_b_l);
@@ -792,8 +905,11 @@ Pose12 ref_world(const fflins_pose &pose) {
 int run_associate(fflins_ctx *ctx, const std::vector<Frame *> &refs, Frame *cur, int32_t *nf, int32_t *nc) {
     cudaStream_t s = ctx->stream;
     {
-        int rcp = resolve_pending(ctx);
+        int rcp = flush_frames(ctx);
         if (rcp) return rcp;
+        bool need_bg = cur->bg; // only the frames involved have to be complete
+        for (Frame *r : refs) need_bg |= r->bg;
+        if ((rcp = resolve_pending(ctx, need_bg))) return rcp;
     }
     const int q    = cur->c[FFLINS_CLOUD_LIDAR].n;
     AssocParams P{};
@@ -889,8 +1005,9 @@ int fill_factor_pairs(fflins_ctx *ctx, FactorParams &P, int n_pairs, const uint6
                       Frame *cur, const double *pose_cur, const double *ext, double td, uint32_t flags) {
     REQUIRE(n_pairs >= 0 && n_pairs <= kMaxRefs, "too many pairs");
     {
-        int rcp = resolve_pending(ctx);
+        int rcp = flush_frames(ctx);
         if (rcp) return rcp;
+        if ((rcp = resolve_pending(ctx, cur->bg))) return rcp;
     }
     P.n_pairs = n_pairs;
     P.q       = cur->c[FFLINS_CLOUD_LIDAR].n;
@@ -973,6 +1090,7 @@ int fflins_create(const fflins_config *cfg, int device, fflins_ctx **out) {
         cudaStreamCreateWithPriority(&ctx->map_stream, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_main_done, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_bg_done, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_map_done, cudaEventDisableTiming) != cudaSuccess) {
         delete ctx;
         return FFLINS_E_CUDA;
@@ -1065,6 +1183,7 @@ void fflins_destroy(fflins_ctx *ctx) {
     for (auto e : ctx->batch_ev)
         if (e) cudaEventDestroy(e);
     if (ctx->ev_copied) cudaEventDestroy(ctx->ev_copied);
+    if (ctx->ev_bg_done) cudaEventDestroy(ctx->ev_bg_done);
     for (auto &r : ctx->prof_open) {
         cudaEventDestroy(r.a);
         cudaEventDestroy(r.b);
@@ -1176,7 +1295,7 @@ int fflins_frame_process_static(fflins_ctx *ctx, uint64_t frame_id, const float 
         CK(cudaEventRecord(ctx->batch_ev[seq % kGuardRing], s));
         ctx->stage_guard[slot] = seq;
     }
-    if ((rc = frame_voxel_tail(ctx, B))) return rc;
+    if ((rc = frame_voxel_tail(ctx, s, B))) return rc;
     if (!out) return FFLINS_OK;
     if ((rc = resolve_pending(ctx))) return rc;
     fill_info(f, out);
@@ -1536,6 +1655,7 @@ int fflins_keyframe_merge(fflins_ctx *ctx, uint64_t key_id, const uint64_t *nonk
     // frames being merged) is done
     CK(cudaEventRecord(ctx->ev_main_done, ctx->stream));
     CK(cudaStreamWaitEvent(ms, ctx->ev_main_done, 0));
+    if (ctx->bg_active) CK(cudaStreamWaitEvent(ms, ctx->ev_bg_done, 0)); // ... and the background part of the batch
     // grow the keyframe's full cloud to K*N on the map stream; blocks the job may still read are freed later
     Cloud &full = key->c[FFLINS_CLOUD_MAP_FULL];
     if (total > full.cap) {

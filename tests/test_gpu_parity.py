@@ -662,6 +662,24 @@ def test_async_frames_match_sync(robot):
         assert (info.n_down, info.n_dec, info.n_fallback) == (sync_infos[i].n_down, sync_infos[i].n_dec, 0)
         for which in (api.CLOUD_LIDAR_FULL, api.CLOUD_LIDAR, api.CLOUD_WORLD, api.CLOUD_MAP_FULL):
             assert bits_equal(c.download(200 + i, which), c.download(100 + i, which))
+    # the same out of page-locked memory: copies deferred to the launch, batch split over two streams
+    pinned = []
+    for i, fr in enumerate(frames[:4]):
+        x, t = np.ascontiguousarray(fr["xyzi"], np.float32).copy(), np.ascontiguousarray(fr["time"], np.float64).copy()
+        api.host_register(x)
+        api.host_register(t)
+        pinned.append((x, t))
+        c.frame_process(400 + i, x, t, fr["ins_t"], fr["ins_p"], fr["ins_q"], robot.R_bl, robot.t_bl, fr["stamp"], fr["td"],
+                        sync=False)
+    for i in (3, 0, 1, 2):
+        info = c.frame_info(400 + i)
+        assert (info.n_down, info.n_dec, info.n_fallback) == (sync_infos[i].n_down, sync_infos[i].n_dec, 0)
+        for which in (api.CLOUD_LIDAR_FULL, api.CLOUD_LIDAR, api.CLOUD_WORLD, api.CLOUD_MAP_FULL):
+            assert bits_equal(c.download(400 + i, which), c.download(100 + i, which))
+    c.synchronize()
+    for x, t in pinned:
+        api.host_unregister(x)
+        api.host_unregister(t)
     # merge straight after asynchronous frames (the keyframe path of the benchmark)
     for i, fr in enumerate(frames[:3]):
         c.frame_process(300 + i, fr["xyzi"], fr["time"], fr["ins_t"], fr["ins_p"], fr["ins_q"], robot.R_bl, robot.t_bl,
@@ -680,22 +698,41 @@ def test_async_keyframe_pipeline_matches_sync(robot):
     from fflins.pipeline import Session
     frames = [robot.frame(i) for i in range(15)]
     res = []
-    for sync in (True, False):
+    # "pinned": asynchronous frames out of page-locked host memory — the batch is split, the newest frame goes first
+    # on the compute stream and the older ones follow on the copy stream behind their own copies
+    for mode in ("sync", "async", "pinned"):
         c = api.Context(api.default_config(point_filter_num=robot.filter_num, window_size=3))
-        sess = Session(c, robot, frames_per_key=3, n_eval=(1, 1), sync_frames=sync)
-        for fr in frames:
+        sess = Session(c, robot, frames_per_key=3, n_eval=(1, 1), sync_frames=(mode == "sync"))
+        use = frames
+        if mode == "pinned":
+            use = [dict(fr) for fr in frames]
+            for fr in use:
+                fr["xyzi"] = np.ascontiguousarray(fr["xyzi"], np.float32).copy()
+                fr["time"] = np.ascontiguousarray(fr["time"], np.float64).copy()
+                api.host_register(fr["xyzi"])
+                api.host_register(fr["time"])
+        for fr in use:
             fid, _ = sess.process_frame(fr)
             sess.after_frame(fid, fr)
         ids = c.keyframe_ids()
         maps = [c.download(k, api.CLOUD_MAP) for k in ids]
         feats = [c.features(k) for k in ids[:-1]]
-        res.append((ids, maps, feats, sess.last["eval"]["H"].copy(), [c.frame_info(k).n_map for k in ids]))
+        downs = [c.download(k, api.CLOUD_WORLD) for k in ids]
+        res.append((list(ids), maps, feats, sess.last["eval"]["H"].copy(), [c.frame_info(k).n_map for k in ids], downs))
         c.close()
-    (ids_a, maps_a, feats_a, H_a, nm_a), (ids_b, maps_b, feats_b, H_b, nm_b) = res
-    assert ids_a == ids_b and nm_a == nm_b and all(n > 0 for n in nm_a)
-    for ma, mb in zip(maps_a, maps_b):
-        assert bits_equal(ma, mb)
-    for fa, fb in zip(feats_a, feats_b):
-        for k in ("type", "nn_idx", "nn_d2", "normal", "d", "outlier"):
-            assert bits_equal(fa[k], fb[k])
-    assert bits_equal(H_a, H_b)
+        if mode == "pinned":
+            for fr in use:
+                api.host_unregister(fr["xyzi"])
+                api.host_unregister(fr["time"])
+    ids_a, maps_a, feats_a, H_a, nm_a, downs_a = res[0]
+    assert all(n > 0 for n in nm_a)
+    for ids_b, maps_b, feats_b, H_b, nm_b, downs_b in res[1:]:
+        assert ids_a == ids_b and nm_a == nm_b
+        for ma, mb in zip(maps_a, maps_b):
+            assert bits_equal(ma, mb)
+        for da, db in zip(downs_a, downs_b):
+            assert bits_equal(da, db)
+        for fa, fb in zip(feats_a, feats_b):
+            for k in ("type", "nn_idx", "nn_d2", "normal", "d", "outlier"):
+                assert bits_equal(fa[k], fb[k])
+        assert bits_equal(H_a, H_b)
