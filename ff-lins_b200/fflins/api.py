@@ -114,6 +114,7 @@ class Context:
         if rc != 0:
             raise FflinsError(rc, "fflins_create failed (no CUDA device?)" if rc == -6 else "fflins_create failed")
         self.h = h
+        self._window_eval = self.L.fflins_window_eval   # bound once: the solver loop calls it 15 times per keyframe
 
     def close(self):
         if getattr(self, "h", None):
@@ -391,9 +392,15 @@ class Context:
 
     def window_eval_prepared(self, prep, td, flags, out):
         """Same call with the argument arrays converted once (`prepare_window`): what a C++ caller pays."""
-        self._ck(self.L.fflins_window_eval(self.h, prep["n"], prep["ids_p"], prep["refs_p"], prep["cur_p"], prep["ext_p"],
-                                           C.c_double(td), C.c_uint32(flags), out["H_p"], out["b_p"], out["cost_p"],
-                                           out["n_res_p"]))
+        key = (td, flags)
+        args = prep.get("_eval_args")
+        if args is None or prep.get("_eval_key") != key:
+            args = (self.h, prep["n"], prep["ids_p"], prep["refs_p"], prep["cur_p"], prep["ext_p"], C.c_double(td),
+                    C.c_uint32(flags), out["H_p"], out["b_p"], out["cost_p"], out["n_res_p"])
+            prep["_eval_args"], prep["_eval_key"] = args, key
+        rc = self._window_eval(*args)
+        if rc != 0:
+            self._ck(rc)
         return out
 
     @staticmethod

@@ -116,11 +116,16 @@ int         fflins_host_register(void *ptr, uint64_t bytes);
 int         fflins_host_unregister(void *ptr);
 
 /* ---- per frame: LidarMap::lidarFrameProcessing (lidar_map.cc:213-273) ------------------ */
-/* `out` may be NULL = ASYNCHRONOUS mode: the call only enqueues the frame's work on the context's stream
- * and returns; the counts are read back by the next call that needs them (fflins_frame_info_get,
- * fflins_keyframe_merge, fflins_associate, downloads, fflins_synchronize, ...). The frame pose is always
- * available at once (fflins_frame_get_pose): it is evaluated on the host. In asynchronous mode page-locked
- * input buffers must stay untouched until such a call returns (pageable buffers are staged by CUDA).
+/* `out` may be NULL = ASYNCHRONOUS mode: the call only QUEUES the frame (INS window packed, frame pose
+ * evaluated on the host, buffers sized) and returns. Up to 8 queued frames share one launch of each kernel of
+ * the per-frame chain; they are launched, and their counts read back, by the next call that needs a result
+ * (fflins_frame_info_get, fflins_keyframe_merge, fflins_associate, downloads, fflins_synchronize, ...).
+ * The frame pose is always available at once (fflins_frame_get_pose). Buffer lifetime in asynchronous mode:
+ * page-locked (fflins_host_register / cudaMallocHost) point buffers and device point buffers (_dev) must stay
+ * untouched until fflins_synchronize, fflins_frame_info_get or a download of THAT frame returns — their
+ * copies are issued when the batch is launched, newest frame first, and the older frames of the batch are
+ * processed on the copy stream behind their own copies so that association and factor evaluation of the newest
+ * frame never wait for them; pageable buffers are copied before the call returns.
  * SoA input. ins_* is the INS window (deque<pair<IMU,IntegrationState>>): strictly
  * increasing times, positions, quaternions; 2 <= w <= 65536 (misc.cc:27-62). stamp is
  * frame->stamp() (= end time + td, ff_lins.cc:352-353), td is frame->timeDelay(). */
