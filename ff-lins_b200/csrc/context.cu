@@ -659,10 +659,11 @@ int issue_copies(fflins_ctx *ctx, const QueuedFrame &q) {
 
 // Launch the kernel chain of every queued frame: prologue, undistortion, voxel tail — three launches per batch.
 //
-// Batches whose points come from pinned host memory are SPLIT: the newest frame (the one the caller is about to use:
-// association and factor evaluation only ever need the current keyframe) is copied first and processed on the compute
-// stream; the older frames of the batch — which only feed the keyframe-map merge — are copied behind it and processed
-// on the copy stream, so that their PCIe time overlaps the solver instead of preceding it.
+// Batches of two or more frames are SPLIT: the newest frame (the one the caller is about to use: association and
+// factor evaluation only ever need the current keyframe) is copied first and processed on the compute stream; the
+// older frames of the batch — which only feed the keyframe-map merge — are copied behind it (pinned host buffers: their
+// copies are issued here, newest first) and processed on the copy stream, so that their PCIe and kernel time overlaps
+// the solver instead of preceding it.
 int flush_frames(fflins_ctx *ctx) {
     if (ctx->fq.empty()) return FFLINS_OK;
     cudaStream_t s = ctx->stream, cs = ctx->copy_stream;
@@ -670,7 +671,7 @@ int flush_frames(fflins_ctx *ctx) {
     const int L     = count - 1;
     int rc;
     if ((rc = join_bg(ctx))) return rc; // scratch slots and stream order: one background part at a time
-    const bool split = count >= 2 && ctx->fq[L].n_copy > 0 && !ctx->prof_on;
+    const bool split = count >= 2 && !ctx->prof_on;
     bool staged = false;
     for (const QueuedFrame &q : ctx->fq) staged |= q.stage_slot >= 0;
     FrameBatch B{};
@@ -700,15 +701,17 @@ int flush_frames(fflins_ctx *ctx) {
     // newest frame: its copy goes first, the compute stream runs its chain
     const QueuedFrame &ql = ctx->fq[L];
     if ((rc = issue_copies(ctx, ql))) return rc;
-    CK(cudaEventRecord(ctx->ev_copied, cs));
-    CK(cudaStreamWaitEvent(s, ctx->ev_copied, 0));
+    if (ql.stage_slot >= 0) {
+        CK(cudaEventRecord(ctx->ev_copied, cs));
+        CK(cudaStreamWaitEvent(s, ctx->ev_copied, 0));
+    }
     B.count = 1;
     B.it[0] = ql.item;
     item_scratch(ctx, L, B.it[0]);
     unsigned long long seq;
     if ((rc = launch_chain(ctx, s, B, &seq))) return rc;
-    ctx->win_guard[ql.wslot]       = seq;
-    ctx->stage_guard[ql.stage_slot] = seq;
+    ctx->win_guard[ql.wslot] = seq;
+    if (ql.stage_slot >= 0) ctx->stage_guard[ql.stage_slot] = seq;
     if ((rc = frame_voxel_tail(ctx, s, B))) return rc;
     // the rest: copies and kernels in FIFO order on the copy stream (their scratch slots 0..L-1 were last used by
     // the previous batch on the compute stream)

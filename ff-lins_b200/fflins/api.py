@@ -221,8 +221,9 @@ class Context:
         return pose.numpy()
 
     def set_motion(self, fid, v, omega, td):
-        v, omega = _c(v, np.float64), _c(omega, np.float64)
-        self._ck(self.L.fflins_frame_set_motion(self.h, C.c_uint64(fid), _p(v), _p(omega), C.c_double(td)))
+        d3 = C.c_double * 3
+        self._ck(self.L.fflins_frame_set_motion(self.h, C.c_uint64(fid), d3(v[0], v[1], v[2]),
+                                                d3(omega[0], omega[1], omega[2]), C.c_double(td)))
 
     def release(self, fid):
         self._ck(self.L.fflins_frame_release(self.h, C.c_uint64(fid)))
@@ -233,14 +234,14 @@ class Context:
 
     def reproject_window(self, ids, poses):
         """poses: ctypes array (Pose * n) or list of (R, t)."""
-        ids = np.array(list(ids), np.uint64)
         n = len(ids)
+        ids = (C.c_uint64 * n)(*ids)
         if not isinstance(poses, C.Array):
             arr = (Pose * n)()
             for i, (R, t) in enumerate(poses):
                 arr[i] = Pose.make(R, t)
             poses = arr
-        self._ck(self.L.fflins_reproject_window(self.h, n, _p(ids), poses))
+        self._ck(self.L.fflins_reproject_window(self.h, n, ids, poses))
 
     def get_pose_struct(self, fid):
         pose = Pose()
