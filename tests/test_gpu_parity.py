@@ -416,6 +416,49 @@ def _window_params(seq, keys, rng):
     return pose_refs, pose_cur, seq.ext7(), cur["fr"]["td"] + 0.003
 
 
+def test_marginalization_prior_from_device_blocks(window, oracle):
+    """Next row 2: the LiDAR share of the marginalization prior. The (oldest, current) 19 x 19
+    block of fflins_window_eval goes through the host Schur complement / linearisation
+    (marginalization_info.cc:93-131); the same with the oracle's block must give the same prior."""
+    from fflins import marginalization as M
+    c, seq, keys = window
+    c.associate()
+    rng = np.random.default_rng(77)
+    pose_refs, pose_cur, ext, td = _window_params(seq, keys, rng)
+    cur = keys[-1]
+    refs = [k["id"] for k in keys[:-1]]
+    out = c.window_eval(refs, pose_refs, pose_cur, ext, td, 1)
+    f = c.features(refs[0])
+    valid = ((f["type"] == 0) & (f["outlier"] == 0)).astype(np.uint8)
+    motion_cur = np.concatenate([cur["fr"]["v"], cur["fr"]["omega"], [cur["fr"]["td"]]])
+    motion = np.concatenate([keys[0]["fr"]["v"], keys[0]["fr"]["omega"], [keys[0]["fr"]["td"]], motion_cur])
+    q = len(valid)
+    _, _, Ho, bo, _ = oracle.factor_batch(cur["down"][:, :3], f["normal"], f["d"], np.full(q, 0.1), valid, motion, pose_refs[0],
+                                          pose_cur, ext, td, flags=1)
+    Hg, bg = out["H"][0], out["b"][0]
+    # A lone relative factor leaves NO information on the remaining states once its reference pose is eliminated
+    # (J_ref_t = -J_cur_t): in the estimator the oldest keyframe also carries the previous prior / its IMU factor.
+    # Stand in for that share with a Gaussian prior on the reference pose (sigma 1 cm / 0.2 deg).
+    W = np.zeros((19, 19))
+    W[:6, :6] = np.diag([1e4] * 3 + [8.2e4] * 3)
+
+    def marginal(H, b):
+        H0, b0 = M.assemble([H + W], [b], [0], 1)
+        return M.schur(H0, b0, 6)
+    Hp_g, bp_g = marginal(Hg, bg)
+    Hp_o, bp_o = marginal(Ho, bo)
+    scale = np.abs(Hg).max()
+    assert np.abs(Hp_g).max() > 1e-3 * scale, "the marginal must carry information"
+    assert np.abs(Hp_g - Hp_o).max() <= 1e-9 * scale and np.abs(bp_g - bp_o).max() <= 1e-9 * max(np.abs(bg).max(), 1.0)
+    J0, e0 = M.linearize(Hp_g, bp_g)
+    # directions the eigenvalue cut (EPS = 1e-8) keeps reproduce the marginal normal equations
+    assert np.abs(J0.T @ J0 - Hp_g).max() <= 1e-9 * scale + 1e-7
+    dx = rng.normal(size=13) * 1e-2
+    e = M.prior_residual(J0, e0, dx)
+    quad = dx @ Hp_g @ dx - 2 * bp_g @ dx
+    assert abs((e @ e - e0 @ e0) - quad) <= 1e-6 * max(1.0, abs(quad))
+
+
 @pytest.mark.parametrize("flags", [0, 1, 1 | 8 | 16])
 def test_factor_reduce_parity(window, oracle, flags):
     """K6: per-pair H = sum J^T J, b = -sum J^T r, cost vs. the oracle's sequential sums."""
