@@ -225,7 +225,10 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(args.prefill or PREFILL_KEYS):
         step("dev")
     warm = max(args.warmup, 3)
+    t_settle = time.perf_counter()
     for _ in range(warm):
+        step("dev")
+    while time.perf_counter() - t_settle < 0.5:   # untimed: let clocks, caches and the allocator pool settle
         step("dev")
     sampler = ClockSampler(local_rank)
     sampler.start()

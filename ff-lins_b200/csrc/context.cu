@@ -367,6 +367,14 @@ int resolve_map(fflins_ctx *ctx) {
             key->hash_pending = (long long) nm * 10 > (long long) key->hcap * 7;
         }
     }
+    {
+        bool any_bg = false; // (a frame released while an unrelated job was running may still be busy on the copy stream)
+        for (Frame *f : ctx->deferred_frames) any_bg |= f->bg;
+        if (any_bg) {
+            int rcj = join_bg(ctx);
+            if (rcj) return rcj;
+        }
+    }
     for (Frame *f : ctx->deferred_frames) free_frame(ctx, f);
     ctx->deferred_frames.clear();
     for (void *b : ctx->deferred_blocks) ctx->pool.release(b);
@@ -751,6 +759,7 @@ int enqueue_frame(fflins_ctx *ctx, uint64_t id, const float *xyzi, const double 
     bool must_flush = (int) ctx->fq.size() >= kFrameBatch;
     for (const QueuedFrame &q : ctx->fq) must_flush |= q.f == f || (q.item.aos != nullptr) != (aos != nullptr);
     if (must_flush && (rc = flush_frames(ctx))) return rc;
+    if (f->bg && (rc = join_bg(ctx))) return rc; // re-processing a frame whose previous chain is still on the copy stream
     if ((rc = ensure_ins(ctx, w))) return rc;
     const int F    = ctx->cfg.point_filter_num;
     const int ndec = (n + F - 1) / F;
@@ -1413,6 +1422,11 @@ int fflins_frame_release(fflins_ctx *ctx, uint64_t frame_id) {
             ctx->deferred_frames.push_back(it->second);
         }
     } else {
+        // its chain may still be running on the copy stream: order the compute stream (where the blocks are reused) behind it
+        if (it->second->bg) {
+            int rcj = join_bg(ctx);
+            if (rcj) return rcj;
+        }
         free_frame(ctx, it->second);
     }
     ctx->frames.erase(it);
@@ -1799,6 +1813,10 @@ static int remove_key(fflins_ctx *ctx, bool oldest, uint64_t *removed_id) {
     if (removed_id) *removed_id = id;
     auto it = ctx->frames.find(id);
     if (it != ctx->frames.end()) {
+        if (it->second->bg) {
+            int rcj = join_bg(ctx);
+            if (rcj) return rcj;
+        }
         free_frame(ctx, it->second);
         ctx->frames.erase(it);
     }
