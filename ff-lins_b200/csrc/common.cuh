@@ -98,13 +98,14 @@ __device__ __forceinline__ float4 project_rn(const double *__restrict__ R, const
 __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int lane_mask) {
     return __shfl_xor_sync(0xffffffffu, v, lane_mask);
 }
+// lexicographic minimum of a 64-bit key over the warp with two hardware reductions (redux.sync): the high words
+// first, then the low words of the lanes that hold the minimal high word
 __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        unsigned long long u = shfl_xor_u64(v, o);
-        v = u < v ? u : v;
-    }
-    return v;
+    const unsigned hi = (unsigned) (v >> 32);
+    const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned lo = hi == mh ? (unsigned) v : 0xffffffffu;
+    const unsigned ml = __reduce_min_sync(0xffffffffu, lo);
+    return ((unsigned long long) mh << 32) | ml;
 }
 #endif
 

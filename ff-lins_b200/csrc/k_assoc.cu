@@ -51,6 +51,7 @@ __global__ void hash_clear_kernel(MapIndex X) {
     const int hcap = X.hmask + 1;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hcap; i += gridDim.x * blockDim.x) {
         X.fine[i].key    = kEmpty;
+        if (i == 0) X.fine[0].pad = 0ull; // "some cell holds more than one point" flag, see hash_insert_kernel
         X.coarse[i].key  = kEmpty;
         X.coarse[i].mask = 0ull;
         X.super[i].key   = kEmpty;
@@ -70,7 +71,7 @@ __device__ __forceinline__ void mask_insert(MaskSlot *__restrict__ tab, int hmas
     }
 }
 
-// One fine slot per map point; points sharing a cell occupy consecutive probe positions with equal keys.
+// One fine slot per map point; points sharing a cell lie in the same probe run (not necessarily adjacent).
 // m_dev (optional): the point count still sits in device memory (map built on the same stream just before); a
 // table that would be loaded above 0.7 is left empty — the host applies the same test and rebuilds it.
 __global__ void hash_insert_kernel(const float4 *__restrict__ map, int m, const int *__restrict__ m_dev, float inv_cell,
@@ -93,6 +94,9 @@ __global__ void hash_insert_kernel(const float4 *__restrict__ map, int m, const 
                 X.fine[h].idx = i;
                 break;
             }
+            // A second point in the same cell: searches must then walk to the end of the probe run. With the search
+            // cell equal to the voxel leaf (the default) a keyframe map never has one, and a probe stops at its hit.
+            if (old == key) X.fine[0].pad = 1ull;
             h = (h + 1) & X.hmask;
         }
         // coarse occupancy: the 4x4x4 block of cells, bit of this cell
@@ -120,7 +124,7 @@ typedef MapIndex HashView;
 // Probe one fine cell and push every map point stored under it. A slot is two independent 16-byte loads
 // (key | x y, z idx | pad), so a hit needs ONE memory round trip; the next probe slot is requested before the
 // current one is examined.
-__device__ __forceinline__ void probe_cell(const HashView &H, int fx, int fy, int fz, float qx, float qy, float qz,
+__device__ __forceinline__ void probe_cell(const HashView &H, bool multi, int fx, int fy, int fz, float qx, float qy, float qz,
                                            float max_d2, u64 &a0, u64 &a1, u64 &a2, u64 &a3, u64 &a4, bool &dirty) {
     const u64 key = pack_cell(fx, fy, fz);
     unsigned h    = hash_cell(key) & H.hmask;
@@ -137,6 +141,7 @@ __device__ __forceinline__ void probe_cell(const HashView &H, int fx, int fy, in
             float ex = qx - bx, ey = qy - by, ez = qz - bz;
             float d2 = (ex * ex + ey * ey) + ez * ez; // ikd_Tree.cc:1427-1431 (no FMA: -fmad=false)
             if (d2 <= max_d2) dirty |= ins5(a0, a1, a2, a3, a4, ((u64) __float_as_uint(d2) << 32) | idx);
+            if (!multi) break; // one point per cell: the hit ends the probe (otherwise walk to the end of the run)
         }
         s0a = s1a;
         s0b = s1b;
@@ -161,9 +166,8 @@ __device__ __forceinline__ unsigned axis_bits4(int a, int r) {
     for (int i = 0; i < 4; i++) b |= (abs(a + i) <= r ? 1u : 0u) << i;
     return b;
 }
-__device__ __forceinline__ u64 cube_mask(int ax, int ay, int az, int r) {
-    if (r < 0) return 0ull;
-    unsigned nx = axis_bits4(ax, r), ny = axis_bits4(ay, r), nz = axis_bits4(az, r);
+// outer product of three 4-bit axis masks: bit (x | y<<2 | z<<4) = nx[x] & ny[y] & nz[z]
+__device__ __forceinline__ u64 outer3(unsigned nx, unsigned ny, unsigned nz) {
     u64 X = (u64) nx * 0x1111111111111111ull;
     unsigned y16 = 0;
 #pragma unroll
@@ -173,6 +177,37 @@ __device__ __forceinline__ u64 cube_mask(int ax, int ay, int az, int r) {
 #pragma unroll
     for (int z = 0; z < 4; z++) Z |= ((nz >> z) & 1u) ? (0xFFFFull << (16 * z)) : 0ull;
     return X & Y & Z;
+}
+__device__ __forceinline__ u64 cube_mask(int ax, int ay, int az, int r) {
+    if (r < 0) return 0ull;
+    return outer3(axis_bits4(ax, r), axis_bits4(ay, r), axis_bits4(az, r));
+}
+// The same for the 4x4x4 COARSE blocks (4 cells wide each) of a super block whose first cell sits at offset s from
+// the query cell: bit i of the axis mask = the nearest (farthest) cell of sub-block i is within r cells on that axis.
+// A block's Chebyshev range [mn, mx] is the per-axis maximum, so "mn <= r" and "mx <= r" are both outer products.
+__device__ __forceinline__ unsigned axis_blocks_near(int s, int r) {
+    unsigned b = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int a = s + 4 * i;
+        b |= (max(a, -(a + 3)) <= r ? 1u : 0u) << i;
+    }
+    return b;
+}
+__device__ __forceinline__ unsigned axis_blocks_far(int s, int r) {
+    unsigned b = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int a = s + 4 * i;
+        b |= (max(abs(a), abs(a + 3)) <= r ? 1u : 0u) << i;
+    }
+    return b;
+}
+// coarse blocks of a super block that intersect the Chebyshev shell (lo, hi]: mn <= hi and mx > lo
+__device__ __forceinline__ u64 shell_blocks(int sx, int sy, int sz, int lo, int hi) {
+    u64 in = outer3(axis_blocks_near(sx, hi), axis_blocks_near(sy, hi), axis_blocks_near(sz, hi));
+    if (lo >= 0) in &= ~outer3(axis_blocks_far(sx, lo), axis_blocks_far(sy, lo), axis_blocks_far(sz, lo));
+    return in;
 }
 
 constexpr int kAssocWarps = 4;            // warps per CTA
@@ -219,12 +254,24 @@ __device__ __forceinline__ float cells_lb2(int gx, int gy, int gz) {
     return x * x + y * y + z * z;
 }
 
+// t -> (bx, by, bz) of an nx x ny x nz box without integer division: (t + 0.5) / d is never within 0.5 / d of an
+// integer, so the truncated fp32 product is exact for the few hundred boxes a stage can have
+__device__ __forceinline__ void split3(int t, int nx, int ny, int &bx, int &by, int &bz) {
+    const int nxy      = nx * ny;
+    const float inv_xy = __fdividef(1.0f, (float) nxy), inv_x = __fdividef(1.0f, (float) nx); // approximate: margin 0.5 / d
+    bz      = (int) (((float) t + 0.5f) * inv_xy);
+    int rem = t - bz * nxy;
+    by      = (int) (((float) rem + 0.5f) * inv_x);
+    bx      = rem - by * nx;
+}
+
 __device__ __forceinline__ void warp_knn5(const HashView &H, float qx, float qy, float qz, float inv_cell, float cell,
                                           int r_max, float max_d2, unsigned *__restrict__ queue,
                                           unsigned *__restrict__ cqueue, u64 best[5]) {
     const int lane = threadIdx.x & 31;
     const int cx = (int) floorf(qx * inv_cell), cy = (int) floorf(qy * inv_cell), cz = (int) floorf(qz * inv_cell);
     u64 a0 = kInf, a1 = kInf, a2 = kInf, a3 = kInf, a4 = kInf;
+    const bool multi = __ldg(&H.fine[0].pad) != 0ull;
     bool dirty = false;                                  // this lane inserted since the last warp merge
     // pruning bound in cells^2: a cell (block) whose lower-bound distance exceeds the cut-off, or the current 5th
     // distance once five neighbours are known, cannot contribute (strict, with a 0.2 % guard for fp32 rounding)
@@ -240,10 +287,8 @@ __device__ __forceinline__ void warp_knn5(const HashView &H, float qx, float qy,
         const int lox = (cx - 4) >> 2, loy = (cy - 4) >> 2, loz = (cz - 4) >> 2;
         const int nx = ((cx + 4) >> 2) - lox + 1, ny = ((cy + 4) >> 2) - loy + 1, nz = ((cz + 4) >> 2) - loz + 1;
         if (lane < nx * ny * nz) {
-            int bz  = lane / (nx * ny);
-            int rem = lane - bz * (nx * ny);
-            int by  = rem / nx;
-            int bx  = rem - by * nx;
+            int bx, by, bz;
+            split3(lane, nx, ny, bx, by, bz);
             nax = (bx + lox) * 4 - cx;
             nay = (by + loy) * 4 - cy;
             naz = (bz + loz) * 4 - cz;
@@ -265,19 +310,11 @@ __device__ __forceinline__ void warp_knn5(const HashView &H, float qx, float qy,
             const int t = t0 + lane;
             bool mine   = false;
             if (t < total) {
-                int bz  = t / (nx * ny);
-                int rem = t - bz * (nx * ny);
-                int by  = rem / nx;
-                int bx  = rem - by * nx;
+                int bx, by, bz;
+                split3(t, nx, ny, bx, by, bz);
                 int sx = (bx + lox) * 16 - cx, sy = (by + loy) * 16 - cy, sz = (bz + loz) * 16 - cz;
                 u64 m = lookup_mask(H.super, H.hmask, pack_cell(bx + lox, by + loy, bz + loz));
-                while (m && !mine) {
-                    int sub = __ffsll((long long) m) - 1;
-                    m &= m - 1;
-                    int cmn, cmx;
-                    block_range(sx + 4 * (sub & 3), sy + 4 * ((sub >> 2) & 3), sz + 4 * (sub >> 4), 4, cmn, cmx);
-                    mine = cmn <= r_max;
-                }
+                mine  = (m & shell_blocks(sx, sy, sz, -1, r_max)) != 0ull;
             }
             any = __any_sync(0xffffffffu, mine);
         }
@@ -301,18 +338,27 @@ __device__ __forceinline__ void warp_knn5(const HashView &H, float qx, float qy,
         const int T = __shfl_sync(0xffffffffu, incl, 31);
         if (T == 0) return;
         int off = incl - cnt;
-        while (keep) {
-            int sub = __ffsll((long long) keep) - 1;
-            keep &= keep - 1;
-            int dx = ax + (sub & 3), dy = ay + ((sub >> 2) & 3), dz = az + (sub >> 4);
-            queue[off++] = (unsigned) (dx + 512) | ((unsigned) (dy + 512) << 10) | ((unsigned) (dz + 512) << 20);
+        {
+            // cell (dx, dy, dz) = block offset + (sub & 3, (sub >> 2) & 3, sub >> 4), 10 bits per axis (biased by 512):
+            // the three 2-bit fields of `sub` are spread to the three 10-bit fields and added to the block's code
+            const unsigned base = (unsigned) (ax + 512) | ((unsigned) (ay + 512) << 10) | ((unsigned) (az + 512) << 20);
+            unsigned half = (unsigned) keep;
+#pragma unroll
+            for (int hh = 0; hh < 2; hh++) {
+                while (half) {
+                    const unsigned sub = (unsigned) (__ffs((int) half) - 1 + 32 * hh);
+                    half &= half - 1;
+                    queue[off++] = base + ((sub & 3u) | ((sub & 12u) << 8) | ((sub & 48u) << 16));
+                }
+                half = (unsigned) (keep >> 32);
+            }
         }
         __syncwarp();
 #pragma unroll 1
         for (int k = lane; k < T; k += 32) {
             unsigned e = queue[k];
             int dx = (int) (e & 1023u) - 512, dy = (int) ((e >> 10) & 1023u) - 512, dz = (int) (e >> 20) - 512;
-            probe_cell(H, cx + dx, cy + dy, cz + dz, qx, qy, qz, max_d2, a0, a1, a2, a3, a4, dirty);
+            probe_cell(H, multi, cx + dx, cy + dy, cz + dz, qx, qy, qz, max_d2, a0, a1, a2, a3, a4, dirty);
         }
         __syncwarp();
     };
@@ -384,10 +430,8 @@ __device__ __forceinline__ void warp_knn5(const HashView &H, float qx, float qy,
 #pragma unroll 1
             for (int t0 = 0; t0 < total; t0 += kLookupLanes) {
                 const int t = t0 + lane;
-                int bz  = t / (nx * ny);
-                int rem = t - bz * (nx * ny);
-                int by  = rem / nx;
-                int bx  = rem - by * nx;
+                int bx, by, bz;
+                split3(t, nx, ny, bx, by, bz);
                 round(lane < kLookupLanes && t < total, (bx + lox) * 4 - cx, (by + loy) * 4 - cy, (bz + loz) * 4 - cz);
             }
         } else {
@@ -403,24 +447,16 @@ __device__ __forceinline__ void warp_knn5(const HashView &H, float qx, float qy,
                 u64 keep    = 0ull;
                 int sx = 0, sy = 0, sz = 0; // offset of the super block's first cell from the query cell
                 if (lane < kLookupLanes && t < total) {
-                    int bz  = t / (nx * ny);
-                    int rem = t - bz * (nx * ny);
-                    int by  = rem / nx;
-                    int bx  = rem - by * nx;
+                    int bx, by, bz;
+                    split3(t, nx, ny, bx, by, bz);
                     sx = (bx + lox) * 16 - cx;
                     sy = (by + loy) * 16 - cy;
                     sz = (bz + loz) * 16 - cz;
                     int mn, mx;
                     block_range(sx, sy, sz, 16, mn, mx);
                     if (mx > lo && mn <= hi) {
-                        u64 m = lookup_mask(H.super, H.hmask, pack_cell(bx + lox, by + loy, bz + loz));
-                        while (m) { // keep the occupied coarse blocks that intersect the stage
-                            int sub = __ffsll((long long) m) - 1;
-                            m &= m - 1;
-                            int cmn, cmx;
-                            block_range(sx + 4 * (sub & 3), sy + 4 * ((sub >> 2) & 3), sz + 4 * (sub >> 4), 4, cmn, cmx);
-                            if (cmx > lo && cmn <= hi) keep |= 1ull << sub;
-                        }
+                        // the occupied coarse blocks that intersect the stage: pure bit arithmetic
+                        keep = lookup_mask(H.super, H.hmask, pack_cell(bx + lox, by + loy, bz + loz)) & shell_blocks(sx, sy, sz, lo, hi);
                     }
                 }
                 const int cnt = __popcll(keep);
@@ -463,10 +499,9 @@ associate_knn_kernel(const __grid_constant__ AssocParams P, const float4 *__rest
     unsigned *my_queue  = smem_q + (threadIdx.x >> 5) * (kQueueCap + kCQueueCap);
     unsigned *my_cqueue = my_queue + kQueueCap;
     const int lane  = threadIdx.x & 31;
-    const int gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (gwarp >= P.n_refs * P.q) return;
-    const int ri = gwarp / P.q;
-    const int k  = gwarp - ri * P.q;
+    const int ri = blockIdx.y;                                    // grid: (ceil(q / warps per CTA), refs)
+    const int k  = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (k >= P.q) return;
     const AssocRef &ref = P.ref[ri];
     const long long dbg_t0 = P.dbg_cycles ? clock64() : 0;
     // world -> ref lidar frame (lidar_map.cc:343-345,355-357): fp64 math, fp32 store
@@ -484,7 +519,7 @@ associate_knn_kernel(const __grid_constant__ AssocParams P, const float4 *__rest
         ref.feat.nn_idx[5 * k + lane] = have ? (int) (unsigned) (b & 0xffffffffu) : -1;
         ref.feat.nn_d2[5 * k + lane]  = have ? __uint_as_float((unsigned) (b >> 32)) : 0.f;
     }
-    if (P.dbg_cycles && lane == 0) P.dbg_cycles[gwarp] = clock64() - dbg_t0;
+    if (P.dbg_cycles && lane == 0) P.dbg_cycles[ri * P.q + k] = clock64() - dbg_t0;
 }
 
 // K5b: one THREAD per (ref, query): plane fit + validity tests + feature record (lidar_map.cc:371-395).
@@ -623,7 +658,7 @@ void launch_hash_build(cudaStream_t s, const float4 *map, int m, float inv_cell,
 void launch_associate(cudaStream_t s, const AssocParams &p, const float4 *cur_world, const float4 *cur_lidar) {
     long long warps = (long long) p.n_refs * p.q;
     if (warps <= 0) return;
-    int grid = (int) ((warps + kAssocWarps - 1) / kAssocWarps);
+    dim3 grid((p.q + kAssocWarps - 1) / kAssocWarps, p.n_refs);
     init_knn_smem();
     associate_knn_kernel<<<grid, kAssocWarps * 32, kKnnSmem, s>>>(p, cur_world);
     dim3 g2((p.q + 127) / 128, p.n_refs);
