@@ -228,7 +228,7 @@ def run_ours(args, rank, world, local_rank):
     t_settle = time.perf_counter()
     for _ in range(warm):
         step("dev")
-    while time.perf_counter() - t_settle < 0.5:   # untimed: let clocks, caches and the allocator pool settle
+    while time.perf_counter() - t_settle < args.settle:   # untimed: let clocks, caches and the allocator pool settle
         step("dev")
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -494,6 +494,7 @@ def main():
     ap.add_argument("--no-batched", action="store_true", help="skip the batched per-kernel roofline pass")
     ap.add_argument("--frames", type=int, default=None, help="distinct synthetic frames to cycle over (default: one lap)")
     ap.add_argument("--prefill", type=int, default=None, help="untimed keyframes that fill the window (default 11)")
+    ap.add_argument("--settle", type=float, default=0.5, help="seconds of untimed steps before the timed region (0 for profiler runs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
