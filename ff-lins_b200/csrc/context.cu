@@ -819,6 +819,11 @@ int enqueue_frame(fflins_ctx *ctx, uint64_t id, const float *xyzi, const double 
     it.n          = n;
     it.td         = td;
     it.filter_num = F;
+    // k / F by multiply-high: exact for k < 2^32 / F (ceil(2^32 / F) * F - 2^32 < F)
+    it.dec_magic  = (F > 1 && (unsigned long long) n * (unsigned long long) F < (1ull << 32)) ? (unsigned) (((1ull << 32) + F - 1) / F) : 0u;
+    it.t_front    = ins_t[0];
+    it.t_back     = ins_t[w - 1];
+    it.inv_dt     = (double) (w - 1) / (ins_t[w - 1] - ins_t[0]);
     it.out_full   = f->c[FFLINS_CLOUD_MAP_FULL].d;
     it.out_dec    = f->c[FFLINS_CLOUD_LIDAR_FULL].d;
     it.ndec       = ndec;

@@ -64,8 +64,8 @@ __global__ void __launch_bounds__(256, 3) undistort_kernel(const __grid_constant
     float4 *__restrict__ out_dec  = it.out_dec;
     int *__restrict__ n_fallback  = it.counters;
     if (n <= 0) return;
-    const double t_front = ins_t[0], t_back = ins_t[w - 1];
-    const double inv_dt  = (double) (w - 1) / (t_back - t_front);
+    const double t_front = it.t_front, t_back = it.t_back, inv_dt = it.inv_dt;
+    const unsigned magic = it.dec_magic;
     const int pairs      = (n + 1) >> 1;
     for (int pr = blockIdx.x * blockDim.x + threadIdx.x; pr < pairs; pr += gridDim.x * blockDim.x) {
         const int k0 = 2 * pr;
@@ -116,14 +116,20 @@ __global__ void __launch_bounds__(256, 3) undistort_kernel(const __grid_constant
             for (int j = 0; j < 2; j++)
                 row_apply(rows + (size_t) idx[j] * kRowSize, tt[j], (double) p[j].x, (double) p[j].y, (double) p[j].z, o[j]);
         }
+        // index decimation (lidar_map.cc:249-256): one multiply-high per pair instead of two divisions per point
+        int q0 = magic ? (int) __umulhi((unsigned) k0, magic) : k0 / filter_num;
+        int r0 = k0 - q0 * filter_num;
 #pragma unroll
         for (int j = 0; j < 2; j++) {
             const int k = k0 + j;
             if (k >= n) break;
             float4 r    = make_float4((float) o[j][0], (float) o[j][1], (float) o[j][2], p[j].w);
             out_full[k] = r;
-            // index decimation (lidar_map.cc:249-256)
-            if (out_dec != nullptr && (k % filter_num) == 0) out_dec[k / filter_num] = r;
+            if (out_dec != nullptr && r0 == 0) out_dec[q0] = r;
+            if (++r0 == filter_num) { // the next point starts the next decimation group
+                r0 = 0;
+                q0++;
+            }
         }
     }
 }

@@ -47,6 +47,8 @@ struct FrameItem {
     int n;
     double td;
     int filter_num;
+    unsigned dec_magic;  // ceil(2^32 / filter_num): k / filter_num = umulhi(k, dec_magic), exact while n * filter_num < 2^32 (0: divide)
+    double t_front, t_back, inv_dt; // window span and (w - 1) / span, evaluated once on the host
     float4 *out_full, *out_dec;
     // voxel filter of the decimated cloud + world projection + count report (pinned, 2 ints)
     int ndec;
