@@ -240,7 +240,13 @@ def run_ours(args, rank, world, local_rank):
         trace.clear()
     for _ in range(warm):
         step("host")
+    if trace is not None:
+        trace.clear()
     e2e_dev_ms, e2e_wall_ms, _ = timed("host", args.steps)
+    if trace is not None and rank == 0:
+        for k, (t, c) in sorted(trace.items(), key=lambda kv: -kv[1][0]):
+            print(f"trace[e2e] {k:24s} calls={c:6d} total={t * 1e3:9.2f} ms avg={t / c * 1e6:8.1f} us", file=sys.stderr)
+        trace.clear()
 
     frames_total = aggregate_frames(args.steps, world)
     value = frames_total / (dev_ms / 1e3)
