@@ -75,7 +75,6 @@ void launch_copy_decimate(cudaStream_t s, const float4 *xyzi, int n, int filter_
 // there, so the caller needs no device-to-host copy after the frame chain.
 void launch_project(cudaStream_t s, Pose12 T, const float4 *src, float4 *dst, int n, const int *n_dev,
                     int *report = nullptr, const int *counters = nullptr);
-// same with the pose read from device memory (the frame pose produced by launch_ins_prep)
 // up to kMaxRefs clouds in one launch (blockIdx.y selects the cloud)
 struct ProjectBatch {
     int count;
