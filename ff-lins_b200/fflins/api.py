@@ -144,14 +144,14 @@ class Context:
                                              C.c_double(td), C.byref(info) if sync else None))
         return info
 
-    def frame_process_aos(self, fid, rec, ins_t, ins_p, ins_q, R_bl, t_bl, stamp, td):
+    def frame_process_aos(self, fid, rec, ins_t, ins_p, ins_q, R_bl, t_bl, stamp, td, sync=True):
         assert rec.dtype.itemsize == 32
         ins_t, ins_p, ins_q = _c(ins_t, np.float64), _c(ins_p, np.float64), _c(ins_q, np.float64)
-        info = FrameInfo()
+        info = FrameInfo() if sync else None
         pose = Pose.make(R_bl, t_bl)
         self._ck(self.L.fflins_frame_process_aos(self.h, C.c_uint64(fid), _p(rec), len(rec), _p(ins_t), _p(ins_p),
                                                  _p(ins_q), len(ins_t), C.byref(pose), C.c_double(stamp),
-                                                 C.c_double(td), C.byref(info)))
+                                                 C.c_double(td), C.byref(info) if sync else None))
         return info
 
     def frame_process_dev(self, fid, d_xyzi, d_time, n, ins_t, ins_p, ins_q, pose_bl, stamp, td, sync=True):

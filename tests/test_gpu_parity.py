@@ -734,6 +734,55 @@ def test_async_frames_match_sync(robot):
     c.close()
 
 
+def test_frame_queue_edge_cases(robot):
+    """The asynchronous frame queue: more frames than one batch holds, input kinds alternating inside the queue
+    (SoA / 32-byte AoS records), an empty frame, and a decimated cloud too large for the one-CTA voxel filter in the
+    same batch as small ones — every cloud and count bit-identical to the synchronous calls."""
+    from fflins import api, synth
+    frames = [robot.frame(i) for i in range(11)]
+    clouds = (api.CLOUD_LIDAR_FULL, api.CLOUD_LIDAR, api.CLOUD_WORLD, api.CLOUD_MAP_FULL)
+
+    def run(c, fid, fr, kind, sync):
+        if kind == "aos":
+            return c.frame_process_aos(fid, synth.pack_aos(fr["xyzi"], fr["time"]), fr["ins_t"], fr["ins_p"], fr["ins_q"],
+                                       robot.R_bl, robot.t_bl, fr["stamp"], fr["td"], sync=sync)
+        x, t = fr["xyzi"], fr["time"]
+        if kind == "empty":
+            x, t = x[:0], t[:0]
+        return c.frame_process(fid, x, t, fr["ins_t"], fr["ins_p"], fr["ins_q"], robot.R_bl, robot.t_bl, fr["stamp"], fr["td"],
+                               sync=sync)
+
+    # 1. eleven frames in flight (batch = 8), kinds alternating, one empty
+    kinds = ["soa", "soa", "aos", "soa", "empty", "aos", "aos", "soa", "soa", "soa", "aos"]
+    c = api.Context(api.default_config(point_filter_num=robot.filter_num))
+    ref = [run(c, 100 + i, fr, k, True) for i, (fr, k) in enumerate(zip(frames, kinds))]
+    for i, (fr, k) in enumerate(zip(frames, kinds)):
+        assert run(c, 200 + i, fr, k, False) is None
+    for i in reversed(range(len(frames))):
+        info = c.frame_info(200 + i)
+        assert (info.n_raw, info.n_dec, info.n_down, info.n_fallback) == (ref[i].n_raw, ref[i].n_dec, ref[i].n_down, ref[i].n_fallback)
+        for which in clouds:
+            assert bits_equal(c.download(200 + i, which), c.download(100 + i, which))
+    assert ref[4].n_raw == 0 and ref[4].n_down == 0
+    c.close()
+    # 2. filter_num = 1: the decimated cloud (> 4096 points) takes the multi-kernel voxel filter inside a batch
+    c = api.Context(api.default_config(point_filter_num=1))
+    big = [frames[0], frames[1], frames[2]]
+    small = dict(frames[3])
+    small["xyzi"], small["time"] = small["xyzi"][:3000], small["time"][:3000]
+    seqs = [big[0], small, big[1], small, big[2]]
+    assert len(big[0]["xyzi"]) > 4096
+    ref = [run(c, 100 + i, fr, "soa", True) for i, fr in enumerate(seqs)]
+    for i, fr in enumerate(seqs):
+        run(c, 200 + i, fr, "soa", False)
+    for i in range(len(seqs)):
+        info = c.frame_info(200 + i)
+        assert (info.n_dec, info.n_down) == (ref[i].n_dec, ref[i].n_down) and info.n_down > 0
+        for which in clouds:
+            assert bits_equal(c.download(200 + i, which), c.download(100 + i, which))
+    c.close()
+
+
 def test_async_keyframe_pipeline_matches_sync(robot):
     """The benchmark's asynchronous call sequence (frames and keyframe merge with out = NULL, map built on
     the map stream and adopted at first use) produces bit-identical maps, features and H blocks."""
