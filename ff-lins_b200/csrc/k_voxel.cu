@@ -166,23 +166,20 @@ rs_hist_kernel(const uint32_t *__restrict__ k0, const uint32_t *__restrict__ k1,
 // totals are scanned through shared memory and the offsets written back in one pass.
 constexpr int SCAN_ITEMS = 16;                       // 32-value rounds per warp and super-chunk
 constexpr int SCAN_SUPER = 32 * 32 * SCAN_ITEMS;     // 16384 entries per super-chunk
-__global__ void __launch_bounds__(1024)
-rs_scan_kernel(int *__restrict__ meta, int pass, uint32_t *__restrict__ block_hist, int total) {
-    const bool active = pass * 8 < meta[M_NBITS];
-    if (threadIdx.x == 0) meta[M_PARITY + pass + 1] = meta[M_PARITY + pass] ^ (active ? 1 : 0);
-    if (!active) return;
+// exclusive scan of block_hist[lo, hi) in place by one 1024-thread CTA, starting from `carry0`
+__device__ __forceinline__ void scan_range(uint32_t *__restrict__ block_hist, int lo, int hi, uint32_t carry0) {
     __shared__ uint32_t warp_sums[32];
     __shared__ uint32_t s_carry;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_carry = 0;
+    if (threadIdx.x == 0) s_carry = carry0;
     __syncthreads();
-    for (int sbase = 0; sbase < total; sbase += SCAN_SUPER) {
+    for (int sbase = lo; sbase < hi; sbase += SCAN_SUPER) {
         const int wbase = sbase + wid * (32 * SCAN_ITEMS);
         uint32_t v[SCAN_ITEMS];
 #pragma unroll
         for (int r = 0; r < SCAN_ITEMS; r++) {
             int i = wbase + r * 32 + lane;
-            v[r]  = (i < total) ? block_hist[i] : 0u;
+            v[r]  = (i < hi) ? block_hist[i] : 0u;
         }
         uint32_t run = 0; // running total of this warp's earlier rounds
 #pragma unroll
@@ -213,13 +210,78 @@ rs_scan_kernel(int *__restrict__ meta, int pass, uint32_t *__restrict__ block_hi
 #pragma unroll
         for (int r = 0; r < SCAN_ITEMS; r++) {
             int i = wbase + r * 32 + lane;
-            if (i < total) block_hist[i] = base + v[r];
+            if (i < hi) block_hist[i] = base + v[r];
         }
         __syncthreads();
         // carry for the next super-chunk: offset of the last warp + its total
         if (threadIdx.x == 1023) s_carry = base + run;
         __syncthreads();
     }
+}
+
+__global__ void __launch_bounds__(1024)
+rs_scan_kernel(int *__restrict__ meta, int pass, uint32_t *__restrict__ block_hist, int total) {
+    const bool active = pass * 8 < meta[M_NBITS];
+    if (threadIdx.x == 0) meta[M_PARITY + pass + 1] = meta[M_PARITY + pass] ^ (active ? 1 : 0);
+    if (!active) return;
+    scan_range(block_hist, 0, total, 0u);
+}
+
+// Large inputs (more than ~1 M points): the histogram table no longer fits one CTA's patience. Three launches:
+// per-chunk sums, a scan of the (<= 1024) chunk sums, and the chunk scans seeded with them.
+__global__ void __launch_bounds__(1024)
+rs_scan_reduce_kernel(const int *__restrict__ meta, int pass, const uint32_t *__restrict__ block_hist, int total, int chunk,
+                      uint32_t *__restrict__ partial) {
+    if (pass * 8 >= meta[M_NBITS]) return;
+    const int lo = blockIdx.x * chunk, hi = min(total, lo + chunk);
+    uint32_t sum = 0;
+    for (int i = lo + threadIdx.x; i < hi; i += 1024) sum += block_hist[i];
+    __shared__ uint32_t ws[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint32_t v = ws[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) partial[blockIdx.x] = v;
+    }
+}
+__global__ void __launch_bounds__(1024)
+rs_scan_partials_kernel(int *__restrict__ meta, int pass, uint32_t *__restrict__ partial, int g) {
+    const bool active = pass * 8 < meta[M_NBITS];
+    if (threadIdx.x == 0) meta[M_PARITY + pass + 1] = meta[M_PARITY + pass] ^ (active ? 1 : 0);
+    if (!active) return;
+    __shared__ uint32_t ws[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t v = threadIdx.x < g ? partial[threadIdx.x] : 0u;
+    uint32_t incl    = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+    }
+    if (lane == 31) ws[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t w = ws[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t u = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += u;
+        }
+        ws[lane] = wi - w;
+    }
+    __syncthreads();
+    if (threadIdx.x < g) partial[threadIdx.x] = ws[wid] + incl - v;
+}
+__global__ void __launch_bounds__(1024)
+rs_scan_apply_kernel(const int *__restrict__ meta, int pass, uint32_t *__restrict__ block_hist, int total, int chunk,
+                     const uint32_t *__restrict__ partial) {
+    if (pass * 8 >= meta[M_NBITS]) return;
+    const int lo = blockIdx.x * chunk;
+    scan_range(block_hist, lo, min(total, lo + chunk), partial[blockIdx.x]);
 }
 
 __global__ void __launch_bounds__(RS_THREADS)
@@ -677,7 +739,7 @@ size_t voxel_work_bytes(int cap, size_t *off) {
     off[1] = o; o += al((size_t) cap * 4);
     off[2] = o; o += al((size_t) cap * 4);
     off[3] = o; o += al((size_t) cap * 4);
-    off[4] = o; o += al(256 * nb * 4);
+    off[4] = o; o += al(256 * nb * 4 + 4096); // + 1024 chunk sums of the multi-CTA scan
     off[5] = o; o += al(nb2 * 4);
     off[6] = o; o += al(M_SIZE * 4);
     off[7] = o; o += al(((size_t) cap + 1) * 4);
@@ -726,7 +788,18 @@ int launch_voxel_downsample(cudaStream_t s, const VoxelWork &w, const float4 *in
         ProfScope ps(prof, nm("radix_sort"), s);
         for (int pass = 0; pass < 4; pass++) {
             rs_hist_kernel<<<nb, RS_THREADS, 0, s>>>(w.keys[0], w.keys[1], w.meta, pass, n, w.block_hist, nb);
-            rs_scan_kernel<<<1, 1024, 0, s>>>(w.meta, pass, w.block_hist, 256 * nb);
+            const int total = 256 * nb;
+            if (total <= 8 * SCAN_SUPER) {
+                rs_scan_kernel<<<1, 1024, 0, s>>>(w.meta, pass, w.block_hist, total);
+            } else {
+                int g     = std::min(296, (total + SCAN_SUPER - 1) / SCAN_SUPER);
+                int chunk = ((total + g - 1) / g + SCAN_SUPER - 1) / SCAN_SUPER * SCAN_SUPER;
+                g         = (total + chunk - 1) / chunk;
+                uint32_t *partial = w.block_hist + (size_t) 256 * ((size_t) (w.cap + RS_TILE - 1) / RS_TILE + 1);
+                rs_scan_reduce_kernel<<<g, 1024, 0, s>>>(w.meta, pass, w.block_hist, total, chunk, partial);
+                rs_scan_partials_kernel<<<1, 1024, 0, s>>>(w.meta, pass, partial, g);
+                rs_scan_apply_kernel<<<g, 1024, 0, s>>>(w.meta, pass, w.block_hist, total, chunk, partial);
+            }
             rs_scatter_kernel<<<nb, RS_THREADS, 0, s>>>(w.keys[0], w.keys[1], w.idx[0], w.idx[1], w.meta, pass, n,
                                                         w.block_hist, nb);
         }
@@ -740,7 +813,7 @@ int launch_voxel_downsample(cudaStream_t s, const VoxelWork &w, const float4 *in
         if (gc > 148 * 8) gc = 148 * 8;
         seg_centroid_kernel<<<gc, CEN_THREADS, 0, s>>>(in, w.idx[0], w.idx[1], w.meta, n, w.seg_start, out);
     }
-    if (launches) *launches += 3 + 12 + 3;
+    if (launches) *launches += 3 + (256 * nb <= 8 * SCAN_SUPER ? 12 : 20) + 3;
     return 0;
 }
 

@@ -147,6 +147,16 @@ def test_voxel_bit_exact(ctx, oracle, n):
     assert bits_equal(out, ref), "centroids must be bit-exact (ascending key, index-ordered fp32 sums)"
 
 
+def test_voxel_large_input_multi_cta_scan(ctx, oracle):
+    """Above ~1 M points the radix passes scan their histogram table with the three-launch multi-CTA scan."""
+    rng = np.random.default_rng(4242)
+    pts = random_scene_cloud(rng, 2_500_000, extent=120.0)
+    out, keys = ctx.voxel_downsample(pts, 0.5, want_keys=True)
+    ref, rkeys, _ = oracle.voxel_filter(pts, 0.5, want_keys=True)
+    assert bits_equal(keys, rkeys) and len(out) == len(ref) > 100000
+    assert bits_equal(out, ref)
+
+
 def test_voxel_other_leaf_and_dense_voxels(ctx, oracle):
     rng = np.random.default_rng(77)
     pts = random_scene_cloud(rng, 60000, extent=2.0)   # thousands of points per voxel
