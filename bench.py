@@ -9,7 +9,8 @@ A STEP is one keyframe interval of the synthetic AT128 sequence (153,600 points/
   them, re-projection of every keyframe, removal of the oldest keyframe.
 frames/s = 5 * steps / time.  `value` runs with every input resident in HBM
 (fflins_frame_process_dev); `e2e` runs the same steps through the host-buffer C-ABI
-(fflins_frame_process: pinned host -> device copies and result read-backs inside the timed region).
+(fflins_frame_process_aos on the reference's raw 32-byte PointXYZIT records: pinned host -> device copies and
+result read-backs inside the timed region).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config at128]
 Multi-GPU = N independent replicas (one sequence per GPU, no data-path collective; weak scaling).
@@ -158,7 +159,7 @@ def make_sequence(name, n_frames=None):
 def run_ours(args, rank, world, local_rank):
     import torch
     import fflins
-    from fflins import api
+    from fflins import api, synth
     from fflins.pipeline import Session
 
     # synthesise the frames first: the worker pool forks, which must happen before CUDA / NCCL start
@@ -179,8 +180,12 @@ def run_ours(args, rank, world, local_rank):
     for fr in frames:
         h = {k: torch.from_numpy(np.ascontiguousarray(fr[k])).pin_memory() for k in ("xyzi", "time", "ins_t", "ins_p", "ins_q")}
         d = {k: h[k].cuda() for k in ("xyzi", "time")}
-        host.append({**{k: v.numpy() for k, v in h.items()}, "stamp": fr["stamp"], "td": fr["td"], "v": fr["v"],
-                     "omega": fr["omega"], "_keep": h})
+        # e2e input = what the reference hands to lidarFrameProcessing: raw 32-byte PointXYZIT records, page-locked
+        rec = synth.pack_aos(fr["xyzi"], fr["time"])
+        rec_pin = torch.from_numpy(rec.view(np.uint8)).pin_memory()
+        host.append({"aos": rec_pin.numpy().view(rec.dtype), "ins_t": h["ins_t"].numpy(), "ins_p": h["ins_p"].numpy(),
+                     "ins_q": h["ins_q"].numpy(), "stamp": fr["stamp"], "td": fr["td"], "v": fr["v"],
+                     "omega": fr["omega"], "_keep": (h, rec_pin)})
         dev.append({"xyzi": d["xyzi"].data_ptr(), "time": d["time"].data_ptr(), "ins_t": h["ins_t"].numpy(),
                     "ins_p": h["ins_p"].numpy(), "ins_q": h["ins_q"].numpy(), "n": n, "w": w,
                     "stamp": fr["stamp"], "td": fr["td"], "_keep": (d, h)})
@@ -318,7 +323,7 @@ def run_ours(args, rank, world, local_rank):
     # D2H per step: 5 frame infos (2 ints + pose), merge count, assoc counts, 15 evals x refs x 212 doubles, chi2 counts
     n_refs = cfg.window_size
     d2h = FRAMES_PER_KEY * 8 + 4 + 8 * n_refs + sum(N_EVAL) * n_refs * 212 * 8 + 4 * n_refs
-    h2d = FRAMES_PER_KEY * (n * 24 + w * 64)
+    h2d = FRAMES_PER_KEY * (n * 32 + w * 64)   # raw 32-byte records + the packed INS window (read zero-copy)
 
     last_m = None
     if rank == 0:

@@ -185,6 +185,18 @@ class Context:
     def frame_process_prepared(self, fid, prep):
         self._ck(self.L.fflins_frame_process(self.h, C.c_uint64(fid), *prep[0]))
 
+    @staticmethod
+    def prepare_frame_aos(rec, ins_t, ins_p, ins_q, pose_bl, stamp, td):
+        """rec: the reference's raw 32-byte PointXYZIT records (what LidarMap::lidarFrameProcessing receives)."""
+        assert rec.dtype.itemsize == 32 and rec.flags["C_CONTIGUOUS"]
+        ins_t, ins_p, ins_q = _c(ins_t, np.float64), _c(ins_p, np.float64), _c(ins_q, np.float64)
+        keep = (rec, ins_t, ins_p, ins_q, pose_bl)
+        return (_p(rec), len(rec), _p(ins_t), _p(ins_p), _p(ins_q), len(ins_t), C.byref(pose_bl), C.c_double(stamp),
+                C.c_double(td), None), keep
+
+    def frame_process_aos_prepared(self, fid, prep):
+        self._ck(self.L.fflins_frame_process_aos(self.h, C.c_uint64(fid), *prep[0]))
+
     def frame_process_static(self, fid, xyzi, p, q, R_bl, t_bl):
         xyzi = _c(xyzi, np.float32)
         info = FrameInfo()

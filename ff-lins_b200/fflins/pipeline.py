@@ -59,6 +59,13 @@ class Session:
     def process_frame(self, fr):
         fid = self.next_id
         self.next_id += 1
+        if not self.sync_frames and "aos" in fr:   # the reference-facing input: raw 32-byte PointXYZIT records
+            prep = fr.get("_prep_aos")
+            if prep is None:
+                prep = fr["_prep_aos"] = api.Context.prepare_frame_aos(fr["aos"], fr["ins_t"], fr["ins_p"], fr["ins_q"],
+                                                                       self.pose_bl, fr["stamp"], fr["td"])
+            self.ctx.frame_process_aos_prepared(fid, prep)
+            return fid, None
         if not self.sync_frames:   # asynchronous: the ctypes argument tuple is built once per frame dict
             prep = fr.get("_prep_host")
             if prep is None:
