@@ -101,11 +101,21 @@ __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v,
 // lexicographic minimum of a 64-bit key over the warp with two hardware reductions (redux.sync): the high words
 // first, then the low words of the lanes that hold the minimal high word
 __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ < 800
+    // (only reached by tests/host_math_check.cu, which compiles this header for nvcc's default architecture)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long u = shfl_xor_u64(v, o);
+        v = u < v ? u : v;
+    }
+    return v;
+#else
     const unsigned hi = (unsigned) (v >> 32);
     const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
     const unsigned lo = hi == mh ? (unsigned) v : 0xffffffffu;
     const unsigned ml = __reduce_min_sync(0xffffffffu, lo);
     return ((unsigned long long) mh << 32) | ml;
+#endif
 }
 #endif
 
