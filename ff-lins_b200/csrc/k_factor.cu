@@ -238,17 +238,15 @@ template <int NP> void to_dev(const FactorParams &p, FactorDev<NP> &d) {
     d.flags       = p.flags;
     d.sigma       = p.sigma;
     d.huber_delta = p.huber_delta;
+    make_cur_const(p, d.cc);
     for (int i = 0; i < p.n_pairs; i++) {
-        PairConst pc;
-        make_pair_const(p, p.pair[i], pc);
-        if (i == 0) d.cc = pc.cur;
         FactorDevPair &o = d.pair[i];
         o.type    = p.pair[i].type;
         o.outlier = p.pair[i].outlier;
         o.normal  = p.pair[i].normal;
         o.d       = p.pair[i].d;
         o.std     = p.pair[i].std;
-        o.rc      = pc.ref;
+        make_ref_const(p, p.pair[i], d.cc, o.rc);
     }
 }
 

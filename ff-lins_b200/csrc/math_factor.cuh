@@ -10,36 +10,46 @@ namespace fflins {
 
 __host__ __device__ __forceinline__ M3 skew_plus_I(V3 v) { return M3{{1.0, -v.z, v.y, v.z, 1.0, -v.x, -v.y, v.x, 1.0}}; }
 
-__host__ __device__ inline void make_pair_const(const FactorParams &P, const FactorPair &pr, PairConst &pc) {
-    CurConst &k = pc.cur;
-    RefConst &c = pc.ref;
-    V3 t0  = v3(pr.pose_ref[0], pr.pose_ref[1], pr.pose_ref[2]);
-    Q4 q0  = Q4{pr.pose_ref[3], pr.pose_ref[4], pr.pose_ref[5], pr.pose_ref[6]};
+// the part that depends only on the current frame, the extrinsic and td: once per launch
+__host__ __device__ inline void make_cur_const(const FactorParams &P, CurConst &k) {
     V3 t1  = v3(P.pose_cur[0], P.pose_cur[1], P.pose_cur[2]);
     Q4 q1  = Q4{P.pose_cur[3], P.pose_cur[4], P.pose_cur[5], P.pose_cur[6]};
     k.tbl  = v3(P.ext[0], P.ext[1], P.ext[2]);
     Q4 qbl = Q4{P.ext[3], P.ext[4], P.ext[5], P.ext[6]};
-    c.w0   = v3(pr.w0[0], pr.w0[1], pr.w0[2]);
     k.w1   = v3(P.w1[0], P.w1[1], P.w1[2]);
-    V3 v0  = v3(pr.v0[0], pr.v0[1], pr.v0[2]);
     V3 v1  = v3(P.v1[0], P.v1[1], P.v1[2]);
-    c.dv   = v1 - v0;
-    double dt0 = P.td - pr.td0, dt1 = P.td - P.td1;
-    c.R0  = quat_to_R(q0);
-    c.B0  = skew_plus_I(c.w0 * dt0);   // I + [w0 dt0]x   (lidar_factor.cc:59)
-    c.Rt0 = mul(c.R0, c.B0);
-    c.tt0 = t0 + v0 * dt0;
+    double dt1 = P.td - P.td1;
     k.R1  = quat_to_R(q1);
     k.B1  = skew_plus_I(k.w1 * dt1);
     k.Rt1 = mul(k.R1, k.B1);
     k.tt1 = t1 + v1 * dt1;
     k.Rbl = quat_to_R(qbl);
+}
+
+// the per-reference part (needs the current-frame part)
+__host__ __device__ inline void make_ref_const(const FactorParams &P, const FactorPair &pr, const CurConst &k, RefConst &c) {
+    V3 t0  = v3(pr.pose_ref[0], pr.pose_ref[1], pr.pose_ref[2]);
+    Q4 q0  = Q4{pr.pose_ref[3], pr.pose_ref[4], pr.pose_ref[5], pr.pose_ref[6]};
+    c.w0   = v3(pr.w0[0], pr.w0[1], pr.w0[2]);
+    V3 v0  = v3(pr.v0[0], pr.v0[1], pr.v0[2]);
+    V3 v1  = v3(P.v1[0], P.v1[1], P.v1[2]);
+    c.dv   = v1 - v0;
+    double dt0 = P.td - pr.td0;
+    c.R0  = quat_to_R(q0);
+    c.B0  = skew_plus_I(c.w0 * dt0);   // I + [w0 dt0]x   (lidar_factor.cc:59)
+    c.Rt0 = mul(c.R0, c.B0);
+    c.tt0 = t0 + v0 * dt0;
     M3 A  = mul(transpose(k.Rbl), transpose(c.Rt0));
     M3 C  = mul(A, k.Rt1);             // `common` (lidar_factor.cc:102)
     M3 Rblt = transpose(k.Rbl);
 #pragma unroll
     for (int i = 0; i < 9; i++) c.D.m[i] = C.m[i] - Rblt.m[i];
     c.E = mul(C, k.Rbl);
+}
+
+__host__ __device__ inline void make_pair_const(const FactorParams &P, const FactorPair &pr, PairConst &pc) {
+    make_cur_const(P, pc.cur);
+    make_ref_const(P, pr, pc.cur, pc.ref);
 }
 
 // r and the 19 tangent-space Jacobian entries [ref t, ref th, cur t, cur th, ext t, ext th, td].
