@@ -4,6 +4,9 @@ Bit-exact stages are fed the ORACLE's output of the previous stage, so a 1-ulp d
 upstream transcendental cannot leak into a bit-exact claim. Tolerances (BASELINE.json north_star):
 voxel keys / output sets / kNN index sets bit-exact; fp64 residuals, Jacobians, H, b <= 1e-9
 relative per block; fp32 undistortion output within 1 ulp."""
+import os
+import sys
+
 import numpy as np
 import pytest
 
@@ -742,6 +745,43 @@ def test_async_frames_match_sync(robot):
     assert a.n_map == b.n_map and a.n_down == sync_infos[2].n_down
     assert bits_equal(c.download(302, api.CLOUD_MAP), c.download(102, api.CLOUD_MAP))
     c.close()
+
+
+_ALT_SCRIPT = r"""
+import sys, os, hashlib
+sys.path.insert(0, os.path.join(sys.argv[1], "ff-lins_b200"))
+import numpy as np
+from fflins import api, synth
+from fflins.pipeline import Session
+seq = synth.Sequence("robot")
+c = api.Context(api.default_config(point_filter_num=seq.filter_num, window_size=3))
+sess = Session(c, seq, frames_per_key=3, n_eval=(1, 1), sync_frames=False)
+for i in range(12):
+    fr = seq.frame(i)
+    fid, _ = sess.process_frame(fr)
+    sess.after_frame(fid, fr)
+h = hashlib.sha256()
+for k in c.keyframe_ids():
+    h.update(c.download(k, api.CLOUD_MAP).tobytes())
+h.update(sess.last["eval"]["H"].tobytes())
+print("DIGEST", h.hexdigest())
+"""
+
+
+def test_alternative_host_paths_same_bits(tmp_path):
+    """FFLINS_NO_POLL (stream synchronisation instead of polled completion flags) and FFLINS_NO_HELPER_THREAD (map job
+    issued by the calling thread) are debugging switches: same maps, same H blocks."""
+    import subprocess
+    script = tmp_path / "alt.py"
+    script.write_text(_ALT_SCRIPT)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    digests = []
+    for extra in ({}, {"FFLINS_NO_POLL": "1"}, {"FFLINS_NO_HELPER_THREAD": "1"}):
+        env = dict(os.environ, **extra)
+        out = subprocess.run([sys.executable, str(script), root], env=env, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        digests.append([l for l in out.stdout.splitlines() if l.startswith("DIGEST")][0])
+    assert digests[0] == digests[1] == digests[2]
 
 
 def test_frame_queue_edge_cases(robot):
