@@ -51,7 +51,7 @@ struct RawAoS {   // PointXYZIT, ff_lins/lidar/lidar.h:30-38 (32 bytes)
 // the 44-double row is fetched once (warp-broadcast out of L1) and applied to both points as it arrives.
 // The first version issued 42 8-byte row loads per point and was bound by load-instruction issue, not HBM.
 template <bool AOS>
-__global__ void __launch_bounds__(256, 3) undistort_kernel(const __grid_constant__ FrameBatch B) {
+__global__ void __launch_bounds__(256, 4) undistort_kernel(const __grid_constant__ FrameBatch B) {
     const FrameItem &it = B.it[blockIdx.y];
     const float4 *__restrict__ xyzi = it.xyzi;
     const double *__restrict__ time = it.time;
