@@ -51,7 +51,7 @@ struct RawAoS {   // PointXYZIT, ff_lins/lidar/lidar.h:30-38 (32 bytes)
 // the 44-double row is fetched once (warp-broadcast out of L1) and applied to both points as it arrives.
 // The first version issued 42 8-byte row loads per point and was bound by load-instruction issue, not HBM.
 template <bool AOS>
-__global__ void __launch_bounds__(256, 4) undistort_kernel(const __grid_constant__ FrameBatch B) {
+__global__ void __launch_bounds__(128, 8) undistort_kernel(const __grid_constant__ FrameBatch B) {
     const FrameItem &it = B.it[blockIdx.y];
     const float4 *__restrict__ xyzi = it.xyzi;
     const double *__restrict__ time = it.time;
@@ -183,9 +183,11 @@ void launch_frame_undistort(cudaStream_t s, const FrameBatch &b) {
     int nmax = 0;
     for (int i = 0; i < b.count; i++) nmax = b.it[i].n > nmax ? b.it[i].n : nmax;
     if (b.count <= 0 || nmax <= 0) return;
-    dim3 grid(grid_for((nmax + 1) / 2, 256, 8), b.count);
-    if (b.it[0].aos) undistort_kernel<true><<<grid, 256, 0, s>>>(b);
-    else undistort_kernel<false><<<grid, 256, 0, s>>>(b);
+    // eight 128-thread CTAs are resident per SM (64 registers): the grid is capped at exactly one resident wave and the
+    // threads stride over the pairs (measured at 4 M points: 3.06 TB/s, against 2.83-2.98 TB/s with 2-16 waves)
+    dim3 grid(grid_for((nmax + 1) / 2, 128, 8), b.count);
+    if (b.it[0].aos) undistort_kernel<true><<<grid, 128, 0, s>>>(b);
+    else undistort_kernel<false><<<grid, 128, 0, s>>>(b);
 }
 
 void launch_copy_decimate(cudaStream_t s, const float4 *xyzi, int n, int filter_num, float4 *out_full, float4 *out_dec) {
