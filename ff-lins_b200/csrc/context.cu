@@ -41,6 +41,8 @@ struct Frame {
     bool hash_pending = false; // map still being built on the map stream: the hash is inserted at first use
     bool hash_early   = false; // ... unless the map job itself inserted it (table sized from the previous map)
     int pending_slot = -1; // >= 0: counts of the last frame_process still sit in pinned slot (asynchronous mode)
+    const int *d_ndown = nullptr;        // device copy of the voxel count of its last chain (batch scratch) ...
+    unsigned long long d_ndown_gen = 0;  // ... valid while no later launch has reused the scratch (ctx->scratch_gen)
     bool bg = false;       // its kernel chain runs on the copy stream behind its own host-to-device copy (see flush_frames)
     // keyframe hash (K4)
     MapIndex index; // fine / coarse / super hash tables (hcap slots each)
@@ -132,6 +134,7 @@ struct fflins_ctx : public Profiler {
     cudaEvent_t ev_bg_done = nullptr; // copy stream: the background part of the last split batch is done
     bool bg_active = false;           // ... and nobody has waited for it yet
     unsigned long long last_main_seq = 0;
+    unsigned long long scratch_gen = 0; // bumped whenever the per-item batch scratch is handed out again
     // Frame queue: asynchronous fflins_frame_process* calls only stage their inputs; the per-frame kernel chain
     // is launched for all queued frames at once (flush_frames) by the first call that needs a result.
     std::vector<QueuedFrame> fq;
@@ -327,6 +330,14 @@ int resolve_pending(fflins_ctx *ctx, bool all = true) {
         if (all && (rc = join_bg(ctx))) return rc;
     }
     if (ctx->pending.empty()) return FFLINS_OK;
+    if (!all) { // nothing to adopt while only background frames are pending: no synchronisation either
+        bool any = false;
+        for (uint64_t id : ctx->pending) {
+            Frame *f = find_frame(ctx, id);
+            any |= f && f->pending_slot >= 0 && !f->bg;
+        }
+        if (!any) return FFLINS_OK;
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     std::vector<uint64_t> keep;
     for (uint64_t id : ctx->pending) {
@@ -679,6 +690,7 @@ int flush_frames(fflins_ctx *ctx) {
     const int L     = count - 1;
     int rc;
     if ((rc = join_bg(ctx))) return rc; // scratch slots and stream order: one background part at a time
+    ctx->scratch_gen++;
     const bool split = count >= 2 && !ctx->prof_on;
     bool staged = false;
     for (const QueuedFrame &q : ctx->fq) staged |= q.stage_slot >= 0;
@@ -696,9 +708,12 @@ int flush_frames(fflins_ctx *ctx) {
         }
         unsigned long long seq;
         if ((rc = launch_chain(ctx, s, B, &seq))) return rc;
-        for (const QueuedFrame &q : ctx->fq) {
+        for (int i = 0; i < count; i++) {
+            const QueuedFrame &q = ctx->fq[i];
             ctx->win_guard[q.wslot] = seq;
             if (q.stage_slot >= 0) ctx->stage_guard[q.stage_slot] = seq;
+            q.f->d_ndown       = B.it[i].d_nout;
+            q.f->d_ndown_gen = ctx->scratch_gen;
         }
         ctx->last_main_seq = seq;
         ctx->fq.clear();
@@ -720,6 +735,8 @@ int flush_frames(fflins_ctx *ctx) {
     if ((rc = launch_chain(ctx, s, B, &seq))) return rc;
     ctx->win_guard[ql.wslot] = seq;
     if (ql.stage_slot >= 0) ctx->stage_guard[ql.stage_slot] = seq;
+    ql.f->d_ndown       = B.it[0].d_nout;
+    ql.f->d_ndown_gen = ctx->scratch_gen;
     if ((rc = frame_voxel_tail(ctx, s, B))) return rc;
     // the rest: copies and kernels in FIFO order on the copy stream (their scratch slots 0..L-1 were last used by
     // the previous batch on the compute stream)
@@ -921,18 +938,26 @@ Pose12 ref_world(const fflins_pose &pose) {
 
 int run_associate(fflins_ctx *ctx, const std::vector<Frame *> &refs, Frame *cur, int32_t *nf, int32_t *nc) {
     cudaStream_t s = ctx->stream;
+    bool need_bg = false, late_q = false;
     {
         int rcp = flush_frames(ctx);
         if (rcp) return rcp;
-        bool need_bg = cur->bg; // only the frames involved have to be complete
+        need_bg = cur->bg; // only the frames involved have to be complete
         for (Frame *r : refs) need_bg |= r->bg;
-        if ((rcp = resolve_pending(ctx, need_bg))) return rcp;
+        // The current frame's chain has just been launched on this stream and its voxel count is still on the device:
+        // launch the search for the upper bound (the decimated size) and let the kernels read the count, instead of
+        // synchronising the stream in the middle of the association's critical path. Counts are adopted afterwards.
+        static const bool no_poll = getenv("FFLINS_NO_POLL") != nullptr;
+        late_q = !need_bg && cur->pending_slot >= 0 && cur->d_ndown && cur->d_ndown_gen == ctx->scratch_gen &&
+                 cur->c[FFLINS_CLOUD_LIDAR_FULL].n > 0 && !ctx->prof_on && !no_poll && !getenv("FFLINS_DEBUG_KNN");
+        if (!late_q && (rcp = resolve_pending(ctx, need_bg))) return rcp;
     }
-    const int q    = cur->c[FFLINS_CLOUD_LIDAR].n;
+    const int q    = late_q ? cur->c[FFLINS_CLOUD_LIDAR_FULL].n : cur->c[FFLINS_CLOUD_LIDAR].n;
     AssocParams P{};
     fill_assoc_common(ctx, P);
     P.n_refs = (int) refs.size();
     P.q      = q;
+    P.q_dev  = late_q ? cur->d_ndown : nullptr;
     int rc;
     for (size_t i = 0; i < refs.size(); i++) {
         Frame *r = refs[i];
@@ -995,6 +1020,26 @@ int run_associate(fflins_ctx *ctx, const std::vector<Frame *> &refs, Frame *cur,
     for (size_t i = 0; i < refs.size(); i++) {
         nf[i] = launched ? h[2 * i] : 0;
         nc[i] = launched ? h[2 * i + 1] : 0;
+    }
+    if (late_q) {
+        // the completion flag was released behind the whole chain: the pinned count slots are final, adopt them
+        // without a stream synchronisation
+        std::vector<uint64_t> keep;
+        for (uint64_t id : ctx->pending) {
+            Frame *f = find_frame(ctx, id);
+            if (!f || f->pending_slot < 0) continue;
+            if (f->bg) {
+                keep.push_back(id);
+                continue;
+            }
+            const int *cnt             = ctx->h_slots + 2 * f->pending_slot;
+            f->n_fallback              = cnt[0];
+            f->c[FFLINS_CLOUD_LIDAR].n = cnt[1];
+            f->c[FFLINS_CLOUD_WORLD].n = cnt[1];
+            f->pending_slot            = -1;
+        }
+        ctx->pending.swap(keep);
+        for (Frame *r : refs) r->feat_q = cur->c[FFLINS_CLOUD_LIDAR].n;
     }
     return FFLINS_OK;
 }
@@ -1276,6 +1321,7 @@ int fflins_frame_process_static(fflins_ctx *ctx, uint64_t frame_id, const float 
     B.count       = 1;
     FrameItem &it = B.it[0];
     if ((rc = ensure_ins(ctx, 2))) return rc;
+    ctx->scratch_gen++;
     item_scratch(ctx, 0, it);
     // MISC::stateToPoseWithExtrinsic (misc.cc:99-105), host fp64
     {

@@ -501,7 +501,7 @@ associate_knn_kernel(const __grid_constant__ AssocParams P, const float4 *__rest
     const int lane  = threadIdx.x & 31;
     const int ri = blockIdx.y;                                    // grid: (ceil(q / warps per CTA), refs)
     const int k  = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (k >= P.q) return;
+    if (k >= (P.q_dev ? min(*P.q_dev, P.q) : P.q)) return;
     const AssocRef &ref = P.ref[ri];
     const long long dbg_t0 = P.dbg_cycles ? clock64() : 0;
     // world -> ref lidar frame (lidar_map.cc:343-345,355-357): fp64 math, fp32 store
@@ -532,7 +532,7 @@ associate_plane_kernel(const __grid_constant__ AssocParams P, const float4 *__re
     const AssocRef &ref = P.ref[ri];
     int8_t type     = -1;
     uint8_t covered = 0;
-    if (k < P.q) {
+    if (k < (P.q_dev ? min(*P.q_dev, P.q) : P.q)) {
         float4 rp = project_rn(ref.T_ref_world.R, ref.T_ref_world.t, __ldg(cur_world + k));
         int idx[5];
 #pragma unroll

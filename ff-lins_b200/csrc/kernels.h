@@ -165,6 +165,7 @@ struct AssocParams {
     float plane_d2_gate;   // max_search_square_distance, lidar_map.cc:374
     double plane_thr, sigma, scalar_thr, sigma_gate;
     long long *dbg_cycles; // debug: per-(ref, query) warp cycles (nullptr = off)
+    const int *q_dev;      // optional: the query count still sits in device memory (q is then an upper bound)
     // completion: the last CTA of the plane kernel copies the per-ref counts (AssocRef::counts, zero on entry, zero
     // again on exit) to host_counts[2 * ref + {0, 1}] (pinned) and releases *signal = seq behind them
     int *ticket;           // device int, zero on entry / exit
