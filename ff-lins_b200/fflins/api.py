@@ -417,14 +417,16 @@ class Context:
         return out
 
     @staticmethod
-    def prepare_window(ref_ids, pose_refs, pose_cur, ext):
+    def prepare_window(ref_ids, pose_refs, pose_cur, ext, out=None):
+        """out: a result dict of an earlier call with the same number of pairs may be reused (overwritten in place)."""
         ids = np.array(list(ref_ids), np.uint64)
         n = len(ids)
         refs = _c(pose_refs, np.float64).reshape(n, 7)
         cur, ex = _pose7(pose_cur), _pose7(ext)
-        out = dict(H=np.zeros((n, 19, 19)), b=np.zeros((n, 19)), cost=np.zeros((n, 2)), n_res=np.zeros(n, np.int32))
-        for k in ("H", "b", "cost", "n_res"):
-            out[k + "_p"] = _p(out[k])
+        if out is None or len(out["n_res"]) != n:
+            out = dict(H=np.zeros((n, 19, 19)), b=np.zeros((n, 19)), cost=np.zeros((n, 2)), n_res=np.zeros(n, np.int32))
+            for k in ("H", "b", "cost", "n_res"):
+                out[k + "_p"] = _p(out[k])
         prep = dict(n=n, ids=ids, refs=refs, cur=cur, ext=ex, ids_p=_p(ids), refs_p=_p(refs), cur_p=_p(cur), ext_p=_p(ex))
         return prep, out
 

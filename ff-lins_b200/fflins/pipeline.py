@@ -117,7 +117,7 @@ class Session:
             # solver state: IMU pose blocks of the keyframes (precomputed per frame when available)
             pose_refs = np.stack([self.key_pose7[r] for r in refs])
             pose_cur = self.key_pose7[fid]
-            prep, out = api.Context.prepare_window(refs, pose_refs, pose_cur, self.ext7)
+            prep, out = api.Context.prepare_window(refs, pose_refs, pose_cur, self.ext7, out=self.last.get("eval"))
             # first solve: n_eval[0] LM iterations' worth of evaluations
             for _ in range(self.n_eval[0]):
                 ctx.window_eval_prepared(prep, fr["td"], self.flags, out)
