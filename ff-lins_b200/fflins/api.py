@@ -93,7 +93,7 @@ def default_config(**kw):
 
 
 def _p(a):
-    return None if a is None else a.ctypes.data_as(C.c_void_p)
+    return None if a is None else C.c_void_p(a.ctypes.data)
 
 
 def _c(a, dt):
@@ -307,10 +307,10 @@ class Context:
     # ---- keyframes -------------------------------------------------------------------------------
     def keyframe_merge(self, key_id, nonkey_ids, sync=True):
         """sync=False: out = NULL, the map is built on the map stream and adopted at first use."""
-        ids = np.array(list(nonkey_ids), np.uint64)
+        n = len(nonkey_ids)
+        ids = (C.c_uint64 * n)(*nonkey_ids) if n else None
         info = FrameInfo() if sync else None
-        self._ck(self.L.fflins_keyframe_merge(self.h, C.c_uint64(key_id), _p(ids) if len(ids) else None, len(ids),
-                                              C.byref(info) if sync else None))
+        self._ck(self.L.fflins_keyframe_merge(self.h, C.c_uint64(key_id), ids, n, C.byref(info) if sync else None))
         return info
 
     def keyframe_add(self, key_id):

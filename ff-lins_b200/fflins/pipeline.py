@@ -115,7 +115,7 @@ class Session:
             self.last["assoc"] = ctx.associate()
             refs = ids[:-1]
             # solver state: IMU pose blocks of the keyframes (precomputed per frame when available)
-            pose_refs = np.stack([self.key_pose7[r] for r in refs])
+            pose_refs = np.array([self.key_pose7[r] for r in refs])
             pose_cur = self.key_pose7[fid]
             prep, out = api.Context.prepare_window(refs, pose_refs, pose_cur, self.ext7, out=self.last.get("eval"))
             # first solve: n_eval[0] LM iterations' worth of evaluations
