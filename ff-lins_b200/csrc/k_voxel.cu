@@ -486,12 +486,15 @@ constexpr int SMALL_CAP     = kVoxSmallCap;
 constexpr int SMALL_THREADS = 1024;
 constexpr int SMALL_ROUNDS  = SMALL_CAP / SMALL_THREADS; // 32-item rounds per warp
 
+constexpr int SMALL_DIGIT = 9;                 // 18-bit keys (every per-frame cloud) sort in two passes
+constexpr int SMALL_BINS  = 1 << SMALL_DIGIT;
 struct SmallSmem {
     float4 pts[SMALL_CAP];
     uint32_t key[2][SMALL_CAP];
     uint16_t idx[2][SMALL_CAP];
-    uint16_t warp_hist[32][256];
-    uint32_t digit_base[256];
+    uint16_t warp_hist[32][SMALL_BINS];
+    uint16_t half_tot[2][SMALL_BINS]; // digit totals of warps 0-15 and 16-31
+    uint32_t digit_base[SMALL_BINS];
     float mn[3][32], mx[3][32];
     int bbox[6];
     int ws[32];
@@ -570,8 +573,8 @@ vox_small_body(const float4 *__restrict__ in, int n, float inv, int *__restrict_
     const int rounds  = C / 32;
     const unsigned lt = (1u << lane) - 1u;
     int cur = 0;
-    for (int shift = 0; shift < g.nbits; shift += 8) {
-        for (int i = tid; i < 32 * 256; i += SMALL_THREADS) (&S.warp_hist[0][0])[i] = 0;
+    for (int shift = 0; shift < g.nbits; shift += SMALL_DIGIT) {
+        for (int i = tid; i < 32 * SMALL_BINS; i += SMALL_THREADS) (&S.warp_hist[0][0])[i] = 0;
         __syncthreads();
         uint32_t key[SMALL_ROUNDS];
         uint16_t val[SMALL_ROUNDS], rank[SMALL_ROUNDS];
@@ -582,8 +585,8 @@ vox_small_body(const float4 *__restrict__ in, int n, float inv, int *__restrict_
                 const bool valid = i < n;
                 key[r]           = valid ? S.key[cur][i] : 0xffffffffu;
                 val[r]           = valid ? S.idx[cur][i] : (uint16_t) 0;
-                const uint32_t d = (key[r] >> shift) & 255u;
-                const unsigned m = __match_any_sync(0xffffffffu, valid ? d : 256u + lane);
+                const uint32_t d = (key[r] >> shift) & (SMALL_BINS - 1);
+                const unsigned m = __match_any_sync(0xffffffffu, valid ? d : SMALL_BINS + lane);
                 const uint16_t prev = S.warp_hist[wid][d];
                 __syncwarp();
                 const unsigned rk = __popc(m & lt);
@@ -593,16 +596,24 @@ vox_small_body(const float4 *__restrict__ in, int n, float inv, int *__restrict_
             }
         }
         __syncthreads();
-        // per digit: exclusive prefix over the 32 warps, digit totals
-        uint32_t tot = 0;
-        if (tid < 256) {
+        // per digit: exclusive prefix over the warps — thread (digit, half) walks 16 warps, the two halves run side by
+        // side and the second half's offset (the first half's total) is added when the items are scattered
+        {
+            const int d = tid & (SMALL_BINS - 1), half = tid >> SMALL_DIGIT;
+            uint32_t tot = 0;
 #pragma unroll 8
-            for (int w = 0; w < 32; w++) {
-                uint16_t c           = S.warp_hist[w][tid];
-                S.warp_hist[w][tid]  = (uint16_t) tot;
+            for (int w = 16 * half; w < 16 * half + 16; w++) {
+                uint16_t c        = S.warp_hist[w][d];
+                S.warp_hist[w][d] = (uint16_t) tot;
                 tot += c;
             }
-            // exclusive scan of the 256 digit totals (8 warps)
+            S.half_tot[half][d] = (uint16_t) tot;
+        }
+        __syncthreads();
+        uint32_t tot = 0;
+        if (tid < SMALL_BINS) {
+            tot = (uint32_t) S.half_tot[0][tid] + (uint32_t) S.half_tot[1][tid];
+            // exclusive scan of the digit totals (16 warps)
             uint32_t incl = tot;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -613,7 +624,7 @@ vox_small_body(const float4 *__restrict__ in, int n, float inv, int *__restrict_
             tot = incl - tot; // exclusive within the warp
         }
         __syncthreads();
-        if (tid < 256) {
+        if (tid < SMALL_BINS) {
             uint32_t base = 0;
             for (int w = 0; w < wid; w++) base += (uint32_t) S.ws[w];
             S.digit_base[tid] = base + tot;
@@ -624,8 +635,8 @@ vox_small_body(const float4 *__restrict__ in, int n, float inv, int *__restrict_
             if (r < rounds) {
                 const int i = wid * C + r * 32 + lane;
                 if (i < n) {
-                    const uint32_t d   = (key[r] >> shift) & 255u;
-                    const uint32_t dst = S.digit_base[d] + S.warp_hist[wid][d] + rank[r];
+                    const uint32_t d   = (key[r] >> shift) & (SMALL_BINS - 1);
+                    const uint32_t dst = S.digit_base[d] + S.warp_hist[wid][d] + (wid >= 16 ? (uint32_t) S.half_tot[0][d] : 0u) + rank[r];
                     S.key[cur ^ 1][dst] = key[r];
                     S.idx[cur ^ 1][dst] = val[r];
                 }
