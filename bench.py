@@ -44,6 +44,27 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def bind_to_gpu_cpus(index):
+    """Pin this replica (its fusion, helper and sampler threads, and the first touch of its pinned buffers) to the CPUs
+    NVML reports as local to GPU `index`: N replicas on a two-socket host otherwise share cores and cross the socket
+    link with every launch, poll and copy. Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = ((os.cpu_count() or 64) + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * i + b for i, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if len(cpus) >= 4:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
+
+
 class ClockSampler:
     """SM clocks and throttle reasons sampled DURING the timed region, through NVML in a background thread
     (an nvidia-smi child process takes ~100 ms to start and its driver queries perturb a 50 ms timed region;
@@ -165,6 +186,7 @@ def run_ours(args, rank, world, local_rank):
     # synthesise the frames first: the worker pool forks, which must happen before CUDA / NCCL start
     seq, frames = make_sequence(args.config, args.frames)
     torch.cuda.set_device(local_rank)
+    cpus_bound = bind_to_gpu_cpus(local_rank) if world > 1 else 0
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -350,6 +372,7 @@ def run_ours(args, rank, world, local_rank):
                        "points_per_frame": n, "frames_per_step": FRAMES_PER_KEY, "window": cfg.window_size,
                        "ins_window": w, "factor_evals_per_keyframe": sum(N_EVAL) + 1,
                        "replicas": world, "parallelism": f"{world} independent session(s), no collective",
+                       "cpus_bound_per_replica": cpus_bound,
                        "call_mode": "frames and keyframe merge enqueued asynchronously (out = NULL); association, the 15 "
                                     "factor evaluations and the chi2 cull return their results synchronously",
                        "l2": f"inputs cycle over {P} distinct frames ({input_bytes / 1e6:.0f} MB) > 126 MB L2"},
