@@ -947,9 +947,9 @@ int run_associate(fflins_ctx *ctx, const std::vector<Frame *> &refs, Frame *cur,
         // The current frame's chain has just been launched on this stream and its voxel count is still on the device:
         // launch the search for the upper bound (the decimated size) and let the kernels read the count, instead of
         // synchronising the stream in the middle of the association's critical path. Counts are adopted afterwards.
-        static const bool no_poll = getenv("FFLINS_NO_POLL") != nullptr;
+        static const bool no_poll = getenv("FFLINS_NO_POLL") != nullptr, debug_knn = getenv("FFLINS_DEBUG_KNN") != nullptr;
         late_q = !need_bg && cur->pending_slot >= 0 && cur->d_ndown && cur->d_ndown_gen == ctx->scratch_gen &&
-                 cur->c[FFLINS_CLOUD_LIDAR_FULL].n > 0 && !ctx->prof_on && !no_poll && !getenv("FFLINS_DEBUG_KNN");
+                 cur->c[FFLINS_CLOUD_LIDAR_FULL].n > 0 && !ctx->prof_on && !no_poll && !debug_knn;
         if (!late_q && (rcp = resolve_pending(ctx, need_bg))) return rcp;
     }
     const int q    = late_q ? cur->c[FFLINS_CLOUD_LIDAR_FULL].n : cur->c[FFLINS_CLOUD_LIDAR].n;
@@ -980,7 +980,8 @@ int run_associate(fflins_ctx *ctx, const std::vector<Frame *> &refs, Frame *cur,
         r->feat_q     = q;
     }
     long long *dbg = nullptr;
-    if (getenv("FFLINS_DEBUG_KNN")) {
+    static const bool debug_knn_stats = getenv("FFLINS_DEBUG_KNN") != nullptr;
+    if (debug_knn_stats) {
         dbg = (long long *) ctx->pool.alloc((size_t) P.n_refs * q * 8 + 8);
         P.dbg_cycles = dbg;
     }
