@@ -186,7 +186,8 @@ int fflins_knn5(fflins_ctx *ctx, const float *map_xyzi, int32_t m, const float *
  * call that needs them (the next fflins_associate, a download, fflins_frame_info_get, ...). */
 int fflins_keyframe_merge(fflins_ctx *ctx, uint64_t key_id, const uint64_t *nonkey_ids, int32_t n,
                           fflins_frame_info *out);
-/* LidarMap::addNewKeyFrame (lidar_map.cc:100-126): device hash insert of the map cloud. */
+/* LidarMap::addNewKeyFrame (lidar_map.cc:100-126): the keyframe joins the window; its map gets the device search index
+ * that replaces the ikd-Tree (inserted here, or already by the asynchronous map job of fflins_keyframe_merge). */
 int fflins_keyframe_add(fflins_ctx *ctx, uint64_t key_id);
 int fflins_keyframe_remove_oldest(fflins_ctx *ctx, uint64_t *removed_id); /* lidar_map.cc:128-173 */
 int fflins_keyframe_remove_newest(fflins_ctx *ctx, uint64_t *removed_id); /* lidar_map.cc:175-188 */
@@ -194,7 +195,8 @@ int fflins_keyframe_count(fflins_ctx *ctx, int32_t *n);
 int fflins_keyframe_ids(fflins_ctx *ctx, uint64_t *ids, int32_t cap, int32_t *n);
 
 /* ---- association: LidarMap::updateLidarFeaturesInMap / findFeaturesInMap ---------------- */
-/* cur = newest keyframe, refs = all older keyframes (lidar_map.cc:428-459). */
+/* cur = newest keyframe, refs = all older keyframes (lidar_map.cc:428-459). Always synchronous: the counts are
+ * returned when the features of every (ref, cur) pair are complete in device memory. */
 int fflins_associate(fflins_ctx *ctx, fflins_assoc_stats *out);
 /* One (ref, cur) pair (lidar_map.cc:326-408). */
 int fflins_associate_pair(fflins_ctx *ctx, uint64_t ref_id, uint64_t cur_id, int32_t *num_features,
