@@ -132,6 +132,8 @@ struct fflins_ctx : public Profiler {
     int stage_next = 0;
     cudaEvent_t ev_copied = nullptr;  // copy stream: the host-to-device copies the compute stream waits for are done
     cudaEvent_t ev_bg_done = nullptr; // copy stream: the background part of the last split batch is done
+    cudaEvent_t ev_flush = nullptr;   // compute stream: everything queued before a split batch was flushed
+    cudaEvent_t ev_join_a = nullptr, ev_join_b = nullptr; // timer: map / copy stream joins
     bool bg_active = false;           // ... and nobody has waited for it yet
     unsigned long long last_main_seq = 0;
     unsigned long long scratch_gen = 0; // bumped whenever the per-item batch scratch is handed out again
@@ -171,15 +173,19 @@ struct fflins_ctx : public Profiler {
     bool map_quit   = false;
     std::vector<void *> deferred_blocks;
     // factor scratch
+    FactorRuntime *frt = nullptr;   // K6 / K7 runtime: setup ring, partial sums, resident evaluation kernel
     double *d_red = nullptr;
-    int *d_outliers = nullptr;
     int *d_assoc_counts = nullptr; // [kMaxRefs][2]: PLANE / covered counts of one association launch
+    // The resident evaluation kernel is not ordered on the compute stream: it may only be used while nothing the
+    // evaluation reads (features, outlier flags, the current keyframe's cloud) is still being produced on a stream.
+    // Set by the calls that WAIT for such work (association, launched evaluations), cleared by the calls that queue it.
+    bool eval_inputs_settled = false;
     // pinned host scratch
     unsigned char *h_pin = nullptr;
     size_t h_pin_cap = 0;
     // pinned completion flags released by the kernels of the synchronous solver-facing calls
     // (window_eval): the host polls them instead of synchronising the stream
-    unsigned long long *h_signal = nullptr; // [kMaxRefs] window_eval flags | chi2 flag, associate flag | [8..] chi2 counts | [16..] associate counts
+    unsigned long long *h_signal = nullptr; // [kMaxRefs] window_eval flags | -, associate flag | [8..] chi2 counts | [16..] associate counts | [48..] chi2 flags
     unsigned long long signal_seq = 0;
     // asynchronous frames: per-frame count slots (pinned, written by the last kernel of the frame chain)
     int *h_slots = nullptr;       // kSlots x 2 ints
@@ -604,6 +610,7 @@ int frame_begin(fflins_ctx *ctx, Frame *f, int n, int ndec, int **report) {
     const int slot = ctx->next_slot;
     ctx->next_slot = (ctx->next_slot + 1) % kSlots;
     *report        = ctx->h_slots + 2 * slot;
+    (*report)[0] = (*report)[1] = -1; // never adopt the slot's previous user's counts
     f->n_raw                        = n;
     f->n_fallback                   = 0;
     f->c[FFLINS_CLOUD_MAP_FULL].n   = n;
@@ -692,6 +699,7 @@ int flush_frames(fflins_ctx *ctx) {
     if ((rc = join_bg(ctx))) return rc; // scratch slots and stream order: one background part at a time
     ctx->scratch_gen++;
     const bool split = count >= 2 && !ctx->prof_on;
+    if (split) CK(cudaEventRecord(ctx->ev_flush, s));
     bool staged = false;
     for (const QueuedFrame &q : ctx->fq) staged |= q.stage_slot >= 0;
     FrameBatch B{};
@@ -740,7 +748,9 @@ int flush_frames(fflins_ctx *ctx) {
     if ((rc = frame_voxel_tail(ctx, s, B))) return rc;
     // the rest: copies and kernels in FIFO order on the copy stream (their scratch slots 0..L-1 were last used by
     // the previous batch on the compute stream)
-    if (ctx->last_main_seq) CK(cudaStreamWaitEvent(cs, ctx->batch_ev[ctx->last_main_seq % kGuardRing], 0));
+    // pool blocks handed to these frames may have been released by earlier compute-stream work (re-projection, voxel
+    // tail, ...): the copy stream starts behind everything the compute stream had queued when the batch was flushed
+    CK(cudaStreamWaitEvent(cs, ctx->ev_flush, 0));
     ctx->last_main_seq = seq;
     FrameBatch G{};
     G.count = L;
@@ -771,6 +781,7 @@ int enqueue_frame(fflins_ctx *ctx, uint64_t id, const float *xyzi, const double 
                   double stamp, double td, fflins_frame_info *out) {
     int rc;
     if ((rc = check_window(ctx, ins_t, w))) return rc;
+    ctx->eval_inputs_settled = false;
     Frame *f = get_frame(ctx, id);
     // one input kind per batch; a frame is queued at most once
     bool must_flush = (int) ctx->fq.size() >= kFrameBatch;
@@ -888,6 +899,11 @@ int ensure_features(fflins_ctx *ctx, Frame *f, int q) {
 
 float search_cell(const fflins_ctx *ctx) { return (float) ctx->cfg.downsample_size * ctx->cell_scale; }
 
+// The kNN queue entries pack cell / block offsets into 10-bit fields biased by 512 (k_assoc.cu): offsets reach
+// -(r_max + 15), so the search radius in cells is bounded.
+constexpr int kMaxSearchCells = 511 - 16;
+int search_r_max(double max_dist, float cell) { return (int) std::ceil(max_dist / cell) + 1; }
+
 int build_hash(fflins_ctx *ctx, Frame *f) {
     const Cloud &m = f->c[FFLINS_CLOUD_MAP];
     int hcap       = next_pow2(2 * std::max(m.n, 1));
@@ -913,7 +929,7 @@ void fill_assoc_common(const fflins_ctx *ctx, AssocParams &P) {
     P.inv_cell      = 1.0f / cell;
     P.cell          = cell;
     double max_dist = ctx->cfg.max_search_square_distance; // passed as max_dist and squared (ikd_Tree.cc:902)
-    P.r_max         = (int) std::ceil(max_dist / cell) + 1;
+    P.r_max         = search_r_max(max_dist, cell);
     P.max_d2        = (float) (max_dist * max_dist);
     P.plane_d2_gate = (float) ctx->cfg.max_search_square_distance;
     P.plane_thr     = ctx->cfg.plane_estimation_threshold;
@@ -939,6 +955,7 @@ Pose12 ref_world(const fflins_pose &pose) {
 int run_associate(fflins_ctx *ctx, const std::vector<Frame *> &refs, Frame *cur, int32_t *nf, int32_t *nc) {
     cudaStream_t s = ctx->stream;
     bool need_bg = false, late_q = false;
+    ctx->eval_inputs_settled = false; // features are about to be rewritten on the stream
     {
         int rcp = flush_frames(ctx);
         if (rcp) return rcp;
@@ -948,7 +965,8 @@ int run_associate(fflins_ctx *ctx, const std::vector<Frame *> &refs, Frame *cur,
         // launch the search for the upper bound (the decimated size) and let the kernels read the count, instead of
         // synchronising the stream in the middle of the association's critical path. Counts are adopted afterwards.
         static const bool no_poll = getenv("FFLINS_NO_POLL") != nullptr, debug_knn = getenv("FFLINS_DEBUG_KNN") != nullptr;
-        late_q = !need_bg && cur->pending_slot >= 0 && cur->d_ndown && cur->d_ndown_gen == ctx->scratch_gen &&
+        // (no reference = no kernel to wait for: the counts are then adopted the ordinary way, behind a synchronisation)
+        late_q = !refs.empty() && !need_bg && cur->pending_slot >= 0 && cur->d_ndown && cur->d_ndown_gen == ctx->scratch_gen &&
                  cur->c[FFLINS_CLOUD_LIDAR_FULL].n > 0 && !ctx->prof_on && !no_poll && !debug_knn;
         if (!late_q && (rcp = resolve_pending(ctx, need_bg))) return rcp;
     }
@@ -1003,6 +1021,7 @@ int run_associate(fflins_ctx *ctx, const std::vector<Frame *> &refs, Frame *cur,
         static const bool no_poll = getenv("FFLINS_NO_POLL") != nullptr;
         if (ctx->prof_on || no_poll || dbg) CK(cudaStreamSynchronize(s));
         else CK(wait_signal(flag, 1, P.seq, s));
+        ctx->eval_inputs_settled = true; // the flag is released behind the whole chain: frame chain, search, plane fit
     }
     if (dbg) {
         std::vector<long long> cyc((size_t) P.n_refs * q);
@@ -1144,6 +1163,10 @@ int fflins_create(const fflins_config *cfg, int device, fflins_ctx **out) {
         float v = (float) atof(e);
         if (v >= 0.5f && v <= 8.f) ctx->cell_scale = v;
     }
+    if (!(cfg->max_search_square_distance > 0) || search_r_max(cfg->max_search_square_distance, search_cell(ctx)) > kMaxSearchCells) {
+        delete ctx; // leaf too small for the search radius: the packed queue fields of the kNN would wrap
+        return FFLINS_E_INVALID;
+    }
     // the solver-facing calls (association, factor evaluation) are latency-critical and run on the main stream;
     // the keyframe-map rebuild on the map stream is throughput work that must not delay their CTAs
     int prio_lo = 0, prio_hi = 0;
@@ -1154,6 +1177,9 @@ int fflins_create(const fflins_config *cfg, int device, fflins_ctx **out) {
         cudaEventCreateWithFlags(&ctx->ev_main_done, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_bg_done, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_flush, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_join_a, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_join_b, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_map_done, cudaEventDisableTiming) != cudaSuccess) {
         delete ctx;
         return FFLINS_E_CUDA;
@@ -1161,10 +1187,9 @@ int fflins_create(const fflins_config *cfg, int device, fflins_ctx **out) {
     ctx->d_counters   = (int *) ctx->pool.alloc(64 * sizeof(int));
     ctx->d_fscratch   = (int *) ctx->pool.alloc(kFrameBatch * kItemScratch * sizeof(int));
     ctx->d_red        = (double *) ctx->pool.alloc((size_t) kMaxRefs * kRedSize * sizeof(double));
-    ctx->d_outliers   = (int *) ctx->pool.alloc((kMaxRefs + 1) * sizeof(int));
     ctx->d_map_count  = (int *) ctx->pool.alloc(64);
     ctx->d_assoc_counts = (int *) ctx->pool.alloc((kMaxRefs * 2 + 1) * sizeof(int));
-    if (!ctx->d_counters || !ctx->d_fscratch || !ctx->d_red || !ctx->d_outliers || !ctx->d_map_count || !ctx->d_assoc_counts) {
+    if (!ctx->d_counters || !ctx->d_fscratch || !ctx->d_red || !ctx->d_map_count || !ctx->d_assoc_counts) {
         fflins_destroy(ctx);
         return FFLINS_E_NOMEM;
     }
@@ -1176,14 +1201,18 @@ int fflins_create(const fflins_config *cfg, int device, fflins_ctx **out) {
         return FFLINS_E_NOMEM;
     }
     if (cudaMallocHost((void **) &ctx->h_slots, kSlots * 2 * sizeof(int)) != cudaSuccess ||
-        cudaMallocHost((void **) &ctx->h_signal, (3 * kMaxRefs + 16) * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMallocHost((void **) &ctx->h_signal, (5 * kMaxRefs + 16) * sizeof(unsigned long long)) != cudaSuccess ||
         cudaMallocHost((void **) &ctx->h_map_count, 64) != cudaSuccess) {
         ctx->h_slots = nullptr;
         fflins_destroy(ctx);
         return FFLINS_E_NOMEM;
     }
-    std::memset(ctx->h_signal, 0, (3 * kMaxRefs + 16) * sizeof(unsigned long long));
-    cudaMemsetAsync(ctx->d_outliers, 0, (kMaxRefs + 1) * sizeof(int), ctx->stream);
+    std::memset(ctx->h_signal, 0, (5 * kMaxRefs + 16) * sizeof(unsigned long long));
+    ctx->frt = factor_runtime_create(device);
+    if (!ctx->frt) {
+        fflins_destroy(ctx);
+        return FFLINS_E_NOMEM;
+    }
     cudaMemsetAsync(ctx->d_assoc_counts, 0, (kMaxRefs * 2 + 1) * sizeof(int), ctx->stream);
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
         fflins_destroy(ctx);
@@ -1224,6 +1253,8 @@ void fflins_destroy(fflins_ctx *ctx) {
         }
         ctx->map_worker.join();
     }
+    factor_runtime_destroy(ctx->frt); // retires the resident evaluation kernel first
+    ctx->frt = nullptr;
     if (ctx->map_stream) cudaStreamSynchronize(ctx->map_stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
@@ -1247,6 +1278,9 @@ void fflins_destroy(fflins_ctx *ctx) {
         if (e) cudaEventDestroy(e);
     if (ctx->ev_copied) cudaEventDestroy(ctx->ev_copied);
     if (ctx->ev_bg_done) cudaEventDestroy(ctx->ev_bg_done);
+    if (ctx->ev_flush) cudaEventDestroy(ctx->ev_flush);
+    if (ctx->ev_join_a) cudaEventDestroy(ctx->ev_join_a);
+    if (ctx->ev_join_b) cudaEventDestroy(ctx->ev_join_b);
     for (auto &r : ctx->prof_open) {
         cudaEventDestroy(r.a);
         cudaEventDestroy(r.b);
@@ -1314,6 +1348,7 @@ int fflins_frame_process_static(fflins_ctx *ctx, uint64_t frame_id, const float 
     REQUIRE(n >= 0 && (n == 0 || xyzi) && state_p && state_q && pose_b_l, "null argument");
     int rc;
     if ((rc = flush_frames(ctx))) return rc;
+    ctx->eval_inputs_settled = false;
     cudaStream_t s = ctx->stream;
     Frame *f       = get_frame(ctx, frame_id);
     const int F    = ctx->cfg.point_filter_num;
@@ -1661,6 +1696,7 @@ int fflins_knn5(fflins_ctx *ctx, const float *map_xyzi, int32_t m, const float *
     REQUIRE(m >= 0 && q >= 0 && (m == 0 || map_xyzi) && (q == 0 || (query_xyzi && nn_idx && nn_d2 && nn_count)) && max_dist > 0,
             "bad argument");
     if (q == 0) return FFLINS_OK;
+    REQUIRE(search_r_max(max_dist, search_cell(ctx)) <= kMaxSearchCells, "max_dist too large for the search cell (more than 495 cells)");
     cudaStream_t s = ctx->stream;
     int hcap       = next_pow2(2 * std::max(m, 1));
     float4 *d_map  = (float4 *) ctx->pool.alloc((size_t) std::max(m, 1) * 16);
@@ -2042,8 +2078,15 @@ int fflins_factor_eval_batch(fflins_ctx *ctx, int32_t n, const float *point, con
     P.pair[0].normal = d_n;
     P.pair[0].d      = d_d;
     P.pair[0].std    = d_std;
-    launch_factor_eval(s, P, d_p, 0, r ? d_r : nullptr, J ? d_J : nullptr, nullptr, nullptr);
-    ctx->launches++;
+    {
+        int64_t nl = 0;
+        int rcl    = launch_factor_eval(ctx->frt, s, P, d_p, 0, r ? d_r : nullptr, J ? d_J : nullptr, nullptr, nullptr, nullptr, 0, false, &nl);
+        ctx->launches += nl;
+        if (rcl < 0) {
+            ctx->pool.release(d);
+            return fail(ctx, FFLINS_E_CUDA, cudaGetErrorString((cudaError_t) -rcl));
+        }
+    }
     if (r) cudaMemcpyAsync(r, d_r, (size_t) n * 8, cudaMemcpyDeviceToHost, s);
     if (J) cudaMemcpyAsync(J, d_J, (size_t) n * 176, cudaMemcpyDeviceToHost, s);
     cudaError_t e = cudaStreamSynchronize(s);
@@ -2084,9 +2127,14 @@ int fflins_factor_eval(fflins_ctx *ctx, uint64_t ref_id, uint64_t cur_id, const 
     }
     {
         ProfScope ps(ctx->prof(), "factor_eval", s);
-        launch_factor_eval(s, P, (const float *) cur->c[FFLINS_CLOUD_LIDAR].d, 1, r ? d_r : nullptr, J ? d_J : nullptr,
-                           valid ? d_valid : nullptr, ctx->d_red);
-        ctx->launches++;
+        int64_t nl = 0;
+        int rcl    = launch_factor_eval(ctx->frt, s, P, (const float *) cur->c[FFLINS_CLOUD_LIDAR].d, 1, r ? d_r : nullptr,
+                                        J ? d_J : nullptr, valid ? d_valid : nullptr, ctx->d_red, nullptr, 0, false, &nl);
+        ctx->launches += nl;
+        if (rcl < 0) {
+            ctx->pool.release(d);
+            return fail(ctx, FFLINS_E_CUDA, cudaGetErrorString((cudaError_t) -rcl));
+        }
     }
     unsigned char *h = pin(ctx, kRedSize * 8);
     if (!h) {
@@ -2123,18 +2171,24 @@ int fflins_window_eval(fflins_ctx *ctx, int32_t n_pairs, const uint64_t *ref_ids
     cudaStream_t s = ctx->stream;
     unsigned char *h = pin(ctx, (size_t) n_pairs * kRedSize * 8);
     if (!h) return fail(ctx, FFLINS_E_NOMEM, "pinned allocation failed");
-    {
-        // the reduced blocks are stored by the kernel straight into pinned host memory (zero-copy):
-        // no device-to-host memcpy between the launch and the synchronisation
-        ProfScope ps(ctx->prof(), "factor_eval", s);
-        launch_factor_eval(s, P, (const float *) cur->c[FFLINS_CLOUD_LIDAR].d, 1, nullptr, nullptr, nullptr, (double *) h,
-                           ctx->h_signal, ++ctx->signal_seq);
-        ctx->launches++;
-    }
-    CK(cudaGetLastError());
     static const bool no_poll = getenv("FFLINS_NO_POLL") != nullptr;
-    if (ctx->prof_on || no_poll) CK(cudaStreamSynchronize(s));   // the profiler's closing event needs the stream drained
-    else CK(wait_signal(ctx->h_signal, n_pairs, ctx->signal_seq, s));
+    int how;
+    {
+        // the reduced blocks are stored by the kernel straight into pinned host memory (zero-copy): no device-to-host
+        // memcpy between the evaluation and its results. Normally the evaluation is POSTED to the resident kernel (no
+        // launch at all); the launched kernel is the cold path and the one the per-stage profiler times.
+        ProfScope ps(ctx->prof(), "factor_eval", s);
+        int64_t nl = 0;
+        how = launch_factor_eval(ctx->frt, s, P, (const float *) cur->c[FFLINS_CLOUD_LIDAR].d, 1, nullptr, nullptr, nullptr, (double *) h,
+                                 ctx->h_signal, ++ctx->signal_seq, ctx->eval_inputs_settled && !ctx->prof_on && !no_poll, &nl);
+        ctx->launches += nl;
+    }
+    if (how < 0) return fail(ctx, FFLINS_E_CUDA, std::string("factor evaluation: ") + cudaGetErrorString((cudaError_t) -how));
+    if (how == 1) {
+        if (ctx->prof_on || no_poll) CK(cudaStreamSynchronize(s));   // the profiler's closing event needs the stream drained
+        else CK(wait_signal(ctx->h_signal, n_pairs, ctx->signal_seq, s));
+        ctx->eval_inputs_settled = true; // the compute stream has drained up to here
+    }
     const double *red = (const double *) h;
     // the lines were just written by the device: get all the misses in flight before the dependent reads
     for (size_t o = 0; o < (size_t) n_pairs * kRedSize * 8; o += 64) __builtin_prefetch(h + o, 0, 0);
@@ -2162,17 +2216,22 @@ int fflins_window_chi2(fflins_ctx *ctx, int32_t n_pairs, const uint64_t *ref_ids
     // counts and completion flag come back through pinned memory (the last CTA publishes them): one launch, no
     // memset, no copy, no stream synchronisation
     int *h_counts = (int *) (ctx->h_signal + kMaxRefs + 8);
-    unsigned long long *flag = ctx->h_signal + kMaxRefs;
+    unsigned long long *flags = ctx->h_signal + 3 * kMaxRefs;
+    static const bool no_poll = getenv("FFLINS_NO_POLL") != nullptr;
+    int how;
     {
         ProfScope ps(ctx->prof(), "chi2", s);
-        launch_chi2(s, P, (const float *) cur->c[FFLINS_CLOUD_LIDAR].d, 1, threshold, ctx->d_outliers, h_counts, flag,
-                    ++ctx->signal_seq);
-        ctx->launches++;
+        int64_t nl = 0;
+        how = launch_chi2(ctx->frt, s, P, (const float *) cur->c[FFLINS_CLOUD_LIDAR].d, 1, threshold, h_counts, flags, ++ctx->signal_seq,
+                          ctx->eval_inputs_settled && !ctx->prof_on && !no_poll, &nl);
+        ctx->launches += nl;
     }
-    CK(cudaGetLastError());
-    static const bool no_poll = getenv("FFLINS_NO_POLL") != nullptr;
-    if (ctx->prof_on || no_poll) CK(cudaStreamSynchronize(s));
-    else CK(wait_signal(flag, 1, ctx->signal_seq, s));
+    if (how < 0) return fail(ctx, FFLINS_E_CUDA, std::string("chi2 cull: ") + cudaGetErrorString((cudaError_t) -how));
+    if (how == 1) {
+        if (ctx->prof_on || no_poll) CK(cudaStreamSynchronize(s));
+        else CK(wait_signal(flags, n_pairs, ctx->signal_seq, s));
+        ctx->eval_inputs_settled = true;
+    }
     if (n_outliers) std::memcpy(n_outliers, h_counts, n_pairs * sizeof(int));
     return FFLINS_OK;
 }
@@ -2229,6 +2288,16 @@ int fflins_timer_stop(fflins_ctx *ctx, double *ms) {
         int rcf = flush_frames(ctx); // queued frames belong to the timed region
         if (rcf) return rcf;
     }
+    // the stop event is recorded behind EVERYTHING the context has in flight: the keyframe-map job on the map stream
+    // (issued by the helper thread) and the background frames / copies on the copy stream are joined first
+    if (ctx->map_job_active) {
+        std::unique_lock<std::mutex> lk(ctx->map_mu);
+        ctx->map_cv.wait(lk, [ctx] { return ctx->map_issued; });
+    }
+    CK(cudaEventRecord(ctx->ev_join_a, ctx->map_stream));
+    CK(cudaEventRecord(ctx->ev_join_b, ctx->copy_stream));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join_a, 0));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join_b, 0));
     CK(cudaEventRecord(ctx->timer_b, ctx->stream));
     CK(cudaEventSynchronize(ctx->timer_b));
     float f = 0;
@@ -2238,5 +2307,24 @@ int fflins_timer_stop(fflins_ctx *ctx, double *ms) {
 }
 
 int64_t fflins_launch_count(const fflins_ctx *ctx) { return ctx ? ctx->launches.load() : 0; }
+
+int fflins_eval_stats_get(const fflins_ctx *ctx, fflins_eval_stats *out) {
+    if (!ctx || !out) return FFLINS_E_INVALID;
+    FactorStats st{};
+    factor_runtime_stats(ctx->frt, &st);
+    out->resident_launches  = st.resident_launches;
+    out->resident_evals     = st.resident_evals;
+    out->launched_evals     = st.launched_evals;
+    out->resident_fallbacks = st.resident_fallbacks;
+    return FFLINS_OK;
+}
+
+int fflins_measure_fp64(fflins_ctx *ctx, double *tflops) {
+    if (!ctx || !tflops) return FFLINS_E_INVALID;
+    CK(cudaStreamSynchronize(ctx->stream));
+    *tflops = measure_fp64_tflops(ctx->stream);
+    CK(cudaGetLastError());
+    return FFLINS_OK;
+}
 
 } // extern "C"

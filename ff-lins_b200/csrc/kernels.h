@@ -213,38 +213,71 @@ struct FactorParams {
     double sigma, huber_delta;
     FactorPair pair[kMaxRefs];
 };
-// What the kernels receive (__grid_constant__): the host-evaluated constants and the feature arrays, NP pair slots
-// (4, 8, 12 or 16 — kernel parameters are copied per launch, so the block is kept as small as the window allows).
-struct FactorDevPair {
-    const int8_t *type;
-    uint8_t *outlier;
+// What the kernels receive. The data of an evaluation is split by how often it changes:
+//   FactorSetup  once per keyframe (feature arrays, frozen per-frame motion): lives in device memory, uploaded when it
+//                changes (setup generation);
+//   FactorMsg    once per evaluation (what a solver iteration changes: pose blocks, extrinsic, td, flags): ~1 KB of
+//                64-bit words, passed by value to a launched kernel or through the pinned mailbox of the RESIDENT kernel.
+// Everything of LidarFactor::Evaluate that depends only on the (ref, cur) pair (CurConst / RefConst) is evaluated on
+// the device by the first threads of each CTA (pair_const_to_smem).
+struct FactorSetupPair {
+    const int8_t *type;     // nullptr => every residual valid (stateless batch)
+    uint8_t *outlier;       // read by K6, written by K7
     const double *normal;
     const double *d;
-    const double *std;
-    RefConst rc;
+    const double *std;      // nullptr => sigma
+    double v0[3], w0[3], td0;
 };
-template <int NP> struct FactorDev {
-    int n_pairs;
-    int q;
-    uint32_t flags;
+struct FactorSetup {
+    const float *points;    // cur-frame points: float4 (stride4 = 1) or packed float3
+    int stride4;
+    int q;                  // features per pair
+    double v1[3], w1[3], td1;
     double sigma, huber_delta;
-    CurConst cc;
-    FactorDevPair pair[NP];
+    FactorSetupPair pair[kMaxRefs];
+};
+enum { kCmdEval = 1, kCmdChi2 = 2, kCmdQuit = 3 };
+// word 0: cmd | flags << 32     word 1: n_pairs | setup generation << 32     word 2: td     word 3: chi2 threshold
+// word 4: completion value (signal[pair] = seq)   5: out_red   6: host_counts   7: signal (pinned host addresses)
+// 8..14 pose_cur   15..21 ext   22 + 7 i .. pose_ref[i]
+constexpr int kMsgHead  = 22;
+constexpr int kMsgWords = kMsgHead + 7 * kMaxRefs;
+struct FactorMsg {
+    unsigned long long w[kMsgWords];
 };
 constexpr int kFactorBlock = 128;
+constexpr int kFactorRanks = 8;   // CTAs per pair (each takes every 8th 128-residual tile)
 constexpr int kRedSize     = 212; // 190 upper-tri H + 19 b + cost0 + cost1 + count
+
+// Per-context state of K6 / K7: setup ring, cross-CTA partial sums, and the resident evaluation kernel with its
+// pinned mailbox. Created / destroyed by the context (k_factor.cu).
+struct FactorRuntime;
+FactorRuntime *factor_runtime_create(int device);
+void factor_runtime_destroy(FactorRuntime *rt);
+struct FactorStats {
+    long long resident_launches, resident_evals, launched_evals, resident_fallbacks;
+};
+void factor_runtime_stats(const FactorRuntime *rt, FactorStats *out);
+// Stop the resident kernel (if it is running) and wait for it: called before anything that synchronises the device.
+void factor_runtime_quiesce(FactorRuntime *rt);
+
 // points: xyz of cur-frame points as float4 (stride4=1) or packed float3 (stride4=0).
-// r/J/valid (optional) are per (pair, feature): r[pair*q+k], J[22*(pair*q+k)].
-// out_red: n_pairs * kRedSize doubles (nullptr: no reduction). The pair constants are evaluated on the host
-// (make_pair_const) and passed by value. signal (optional, host-mapped like a pinned out_red): signal[pair] = seq
-// is released at system scope once the pair's kRedSize sums are stored, so the host may poll instead of
-// synchronising the stream.
-void launch_factor_eval(cudaStream_t s, const FactorParams &p, const float *points, int stride4, double *r, double *J,
-                        uint8_t *valid, double *out_red, unsigned long long *signal = nullptr,
-                        unsigned long long seq = 0);
-// counters: kMaxRefs + 1 device ints, zero before the first launch (the kernel leaves them zero); the per-pair
-// outlier counts land in host_counts (pinned) and *signal = seq is released behind them.
-void launch_chi2(cudaStream_t s, const FactorParams &p, const float *points, int stride4, double threshold, int *counters,
-                 int *host_counts, unsigned long long *signal, unsigned long long seq);
+// r/J/valid (optional, device) are per (pair, feature): r[pair*q+k], J[22*(pair*q+k)].
+// out_red: n_pairs * kRedSize doubles (nullptr: no reduction), device or pinned host memory. signal (optional, pinned):
+// signal[pair] = seq is released at system scope once the pair's kRedSize sums are stored, so the host may poll instead
+// of synchronising the stream.
+// resident = true (needs pinned out_red + signal, no per-feature outputs): the evaluation is posted to the resident
+// kernel's mailbox instead of being launched (the kernel is started on demand and retires by itself when idle); the call
+// returns after the results have ARRIVED (it polls the flags itself). Returns 0 = done, 1 = launched on `s` (the caller
+// waits for signal / the stream), < 0 = error (cudaError_t negated).
+int launch_factor_eval(FactorRuntime *rt, cudaStream_t s, const FactorParams &p, const float *points, int stride4, double *r,
+                       double *J, uint8_t *valid, double *out_red, unsigned long long *signal, unsigned long long seq,
+                       bool resident, int64_t *launches);
+// K7: outlier flags are set in p.pair[i].outlier; per-pair counts land in host_counts (pinned) and signal[pair] = seq is
+// released behind each of them. Same return convention as launch_factor_eval.
+int launch_chi2(FactorRuntime *rt, cudaStream_t s, const FactorParams &p, const float *points, int stride4, double threshold,
+                int *host_counts, unsigned long long *signal, unsigned long long seq, bool resident, int64_t *launches);
+// fp64 FMA throughput of the device (the roofline of K6): TFLOP/s of a register-resident DFMA loop on every SM.
+double measure_fp64_tflops(cudaStream_t s);
 
 } // namespace fflins

@@ -10,15 +10,16 @@ namespace fflins {
 
 __host__ __device__ __forceinline__ M3 skew_plus_I(V3 v) { return M3{{1.0, -v.z, v.y, v.z, 1.0, -v.x, -v.y, v.x, 1.0}}; }
 
-// the part that depends only on the current frame, the extrinsic and td: once per launch
-__host__ __device__ inline void make_cur_const(const FactorParams &P, CurConst &k) {
-    V3 t1  = v3(P.pose_cur[0], P.pose_cur[1], P.pose_cur[2]);
-    Q4 q1  = Q4{P.pose_cur[3], P.pose_cur[4], P.pose_cur[5], P.pose_cur[6]};
-    k.tbl  = v3(P.ext[0], P.ext[1], P.ext[2]);
-    Q4 qbl = Q4{P.ext[3], P.ext[4], P.ext[5], P.ext[6]};
-    k.w1   = v3(P.w1[0], P.w1[1], P.w1[2]);
-    V3 v1  = v3(P.v1[0], P.v1[1], P.v1[2]);
-    double dt1 = P.td - P.td1;
+// the part that depends only on the current frame, the extrinsic and td: once per evaluation
+__host__ __device__ inline void make_cur_const_raw(const double *pose_cur, const double *ext, double td, const double *v1p,
+                                                   const double *w1p, double td1, CurConst &k) {
+    V3 t1  = v3(pose_cur[0], pose_cur[1], pose_cur[2]);
+    Q4 q1  = Q4{pose_cur[3], pose_cur[4], pose_cur[5], pose_cur[6]};
+    k.tbl  = v3(ext[0], ext[1], ext[2]);
+    Q4 qbl = Q4{ext[3], ext[4], ext[5], ext[6]};
+    k.w1   = v3(w1p[0], w1p[1], w1p[2]);
+    V3 v1  = v3(v1p[0], v1p[1], v1p[2]);
+    double dt1 = td - td1;
     k.R1  = quat_to_R(q1);
     k.B1  = skew_plus_I(k.w1 * dt1);
     k.Rt1 = mul(k.R1, k.B1);
@@ -26,25 +27,37 @@ __host__ __device__ inline void make_cur_const(const FactorParams &P, CurConst &
     k.Rbl = quat_to_R(qbl);
 }
 
-// the per-reference part (needs the current-frame part)
-__host__ __device__ inline void make_ref_const(const FactorParams &P, const FactorPair &pr, const CurConst &k, RefConst &c) {
-    V3 t0  = v3(pr.pose_ref[0], pr.pose_ref[1], pr.pose_ref[2]);
-    Q4 q0  = Q4{pr.pose_ref[3], pr.pose_ref[4], pr.pose_ref[5], pr.pose_ref[6]};
-    c.w0   = v3(pr.w0[0], pr.w0[1], pr.w0[2]);
-    V3 v0  = v3(pr.v0[0], pr.v0[1], pr.v0[2]);
-    V3 v1  = v3(P.v1[0], P.v1[1], P.v1[2]);
+// the per-reference part, first half: independent of the current frame
+__host__ __device__ inline void make_ref_const_a(const double *pose_ref, const double *v0p, const double *w0p, double td0,
+                                                 double td, const double *v1p, RefConst &c) {
+    V3 t0  = v3(pose_ref[0], pose_ref[1], pose_ref[2]);
+    Q4 q0  = Q4{pose_ref[3], pose_ref[4], pose_ref[5], pose_ref[6]};
+    c.w0   = v3(w0p[0], w0p[1], w0p[2]);
+    V3 v0  = v3(v0p[0], v0p[1], v0p[2]);
+    V3 v1  = v3(v1p[0], v1p[1], v1p[2]);
     c.dv   = v1 - v0;
-    double dt0 = P.td - pr.td0;
+    double dt0 = td - td0;
     c.R0  = quat_to_R(q0);
     c.B0  = skew_plus_I(c.w0 * dt0);   // I + [w0 dt0]x   (lidar_factor.cc:59)
     c.Rt0 = mul(c.R0, c.B0);
     c.tt0 = t0 + v0 * dt0;
+}
+// ... second half: the products with the current-frame part
+__host__ __device__ inline void make_ref_const_b(const CurConst &k, RefConst &c) {
     M3 A  = mul(transpose(k.Rbl), transpose(c.Rt0));
     M3 C  = mul(A, k.Rt1);             // `common` (lidar_factor.cc:102)
     M3 Rblt = transpose(k.Rbl);
 #pragma unroll
     for (int i = 0; i < 9; i++) c.D.m[i] = C.m[i] - Rblt.m[i];
     c.E = mul(C, k.Rbl);
+}
+
+__host__ __device__ inline void make_cur_const(const FactorParams &P, CurConst &k) {
+    make_cur_const_raw(P.pose_cur, P.ext, P.td, P.v1, P.w1, P.td1, k);
+}
+__host__ __device__ inline void make_ref_const(const FactorParams &P, const FactorPair &pr, const CurConst &k, RefConst &c) {
+    make_ref_const_a(pr.pose_ref, pr.v0, pr.w0, pr.td0, P.td, P.v1, c);
+    make_ref_const_b(k, c);
 }
 
 __host__ __device__ inline void make_pair_const(const FactorParams &P, const FactorPair &pr, PairConst &pc) {

@@ -25,6 +25,7 @@ EXPORTS = [
     "fflins_features_download", "fflins_features_set_outlier", "fflins_factor_eval_batch", "fflins_factor_eval",
     "fflins_window_eval", "fflins_window_chi2", "fflins_profile_enable", "fflins_profile_reset", "fflins_profile_get",
     "fflins_launch_count", "fflins_timer_start", "fflins_timer_stop", "fflins_reproject_window",
+    "fflins_eval_stats_get", "fflins_measure_fp64",
 ]
 
 
@@ -60,6 +61,11 @@ class FrameInfo(C.Structure):
 class AssocStats(C.Structure):
     _fields_ = [("n_refs", C.c_int32), ("n_queries", C.c_int32), ("num_features", C.c_int32 * 16),
                 ("num_covered", C.c_int32 * 16), ("ref_ids", C.c_uint64 * 16)]
+
+
+class EvalStats(C.Structure):
+    _fields_ = [("resident_launches", C.c_int64), ("resident_evals", C.c_int64), ("launched_evals", C.c_int64),
+                ("resident_fallbacks", C.c_int64)]
 
 
 class FflinsError(RuntimeError):
@@ -479,6 +485,16 @@ class Context:
 
     def launch_count(self):
         return int(self.L.fflins_launch_count(self.h))
+
+    def eval_stats(self):
+        st = EvalStats()
+        self._ck(self.L.fflins_eval_stats_get(self.h, C.byref(st)))
+        return {k: int(getattr(st, k)) for k, _ in EvalStats._fields_}
+
+    def measure_fp64(self):
+        v = C.c_double()
+        self._ck(self.L.fflins_measure_fp64(self.h, C.byref(v)))
+        return v.value
 
 
 def host_register(arr):

@@ -125,6 +125,7 @@ class Session:
             for _ in range(self.n_eval[1]):
                 ctx.window_eval_prepared(prep, fr["td"], self.flags, out)
             self.last["eval"] = out
+            self.last["eval_prep"] = (prep, out, fr["td"])
             # updateParametersFromOptimizer: re-project every keyframe (optimizer.cc:203-218)
             poses = (api.Pose * len(ids))(*[self.key_pose[k] for k in ids])
             ctx.reproject_window(ids, poses)

@@ -27,6 +27,12 @@ CONFIGS = {
                      q_b_l=(0.0, 0.0, 0.0, 1.0), t_b_l=(-0.05, 0.0, 0.055), pattern="spin64", index=2),
     "at128": dict(n=153600, filter_num=80, imu_hz=200, radius=10.0, period=125, td=0.0,
                   q_b_l=(1.0, 0.0, 0.0, 0.0), t_b_l=(0.0, 0.0, 0.0), pattern="at128", index=3),
+    # BASELINE.json config 4 read as the "dense-map association stress case": the same AT128 scan in a street-sized
+    # scene (400 x 400 x 40 m, building-sized boxes, ~20 m/s): surfaces 50-200 m away put only a few points into each
+    # 0.5 m voxel, so a 5-frame keyframe map holds ~1.2 x 10^5 centroids instead of ~1.5 x 10^4 (Q ~ 1.4 k)
+    "dense": dict(n=153600, filter_num=80, imu_hz=200, radius=50.0, period=160, td=0.0,
+                  q_b_l=(1.0, 0.0, 0.0, 0.0), t_b_l=(0.0, 0.0, 0.0), pattern="at128", index=4,
+                  scene=dict(half=200.0, height=40.0, boxes=90, size_lo=(8.0, 8.0, 6.0), size_hi=(40.0, 40.0, 30.0), clear=6.0)),
 }
 
 
@@ -57,21 +63,23 @@ def R_to_quat_xyzw(R):
 class Scene:
     """Room (inside-out box) plus solid boxes; all axis-aligned."""
 
-    def __init__(self, rng, ring_radius):
-        self.room_lo = np.array([-30.0, -30.0, 0.0])
-        self.room_hi = np.array([30.0, 30.0, 10.0])
+    def __init__(self, rng, ring_radius, half=30.0, height=10.0, boxes=14, size_lo=(1.5, 1.5, 1.0), size_hi=(6.0, 6.0, 6.0),
+                 clear=2.5):
+        n_boxes = boxes
+        self.room_lo = np.array([-half, -half, 0.0])
+        self.room_hi = np.array([half, half, height])
         boxes = []
         tries = 0
-        while len(boxes) < 14 and tries < 1000:
+        while len(boxes) < n_boxes and tries < 1000:
             tries += 1
-            c = rng.uniform([-26, -26, 0], [26, 26, 0])
-            s = rng.uniform([1.5, 1.5, 1.0], [6.0, 6.0, 6.0])
+            c = rng.uniform([-(half - 4), -(half - 4), 0], [half - 4, half - 4, 0])
+            s = rng.uniform(list(size_lo), list(size_hi))
             lo = np.array([c[0] - s[0] / 2, c[1] - s[1] / 2, 0.0])
             hi = np.array([c[0] + s[0] / 2, c[1] + s[1] / 2, s[2]])
-            # keep the driving ring clear by 2 m
+            # keep the driving ring clear
             corners = np.array([[lo[0], lo[1]], [lo[0], hi[1]], [hi[0], lo[1]], [hi[0], hi[1]], c[:2]])
             r = np.linalg.norm(corners, axis=1)
-            near = np.abs(r - ring_radius).min() < 2.5 or (r.min() < ring_radius < r.max())
+            near = np.abs(r - ring_radius).min() < clear or (r.min() < ring_radius < r.max())
             if not near:
                 boxes.append((lo, hi))
         self.boxes = boxes
@@ -111,7 +119,7 @@ class Sequence:
         self.speed = self.omega_z * self.radius
         self.R_bl = quat_xyzw_to_R(cfg["q_b_l"])
         self.t_bl = np.array(cfg["t_b_l"], np.float64)
-        self.scene = Scene(np.random.default_rng(self.seed), self.radius)
+        self.scene = Scene(np.random.default_rng(self.seed), self.radius, **cfg.get("scene", {}))
         self._dirs_cache = {}
 
     # ---- analytic trajectory of the IMU body frame ------------------------------------

@@ -245,6 +245,18 @@ int fflins_timer_start(fflins_ctx *ctx);
 int fflins_timer_stop(fflins_ctx *ctx, double *ms);
 /* Total kernels launched by this context so far. */
 int64_t fflins_launch_count(const fflins_ctx *ctx);
+/* How fflins_window_eval / fflins_window_chi2 were served: by a message to the RESIDENT evaluation kernel (no launch;
+ * the kernel is started on demand, polls a pinned mailbox and retires after FFLINS_RESIDENT_IDLE_US, default 1000) or
+ * by an ordinary kernel launch (first use, profiling, FFLINS_NO_RESIDENT=1, or the resident kernel just retired). */
+typedef struct fflins_eval_stats {
+    int64_t resident_launches;  /* times the resident kernel was (re)started              */
+    int64_t resident_evals;     /* evaluations / chi2 passes served through the mailbox   */
+    int64_t launched_evals;     /* ... served by a kernel launch                          */
+    int64_t resident_fallbacks; /* posted, but the kernel had retired: launched instead   */
+} fflins_eval_stats;
+int fflins_eval_stats_get(const fflins_ctx *ctx, fflins_eval_stats *out);
+/* fp64 FMA throughput of the device in TFLOP/s (register-resident DFMA loop on every SM): the roofline of K6. */
+int fflins_measure_fp64(fflins_ctx *ctx, double *tflops);
 
 #ifdef __cplusplus
 }

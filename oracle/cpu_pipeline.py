@@ -1,7 +1,10 @@
 """The reference's per-frame / per-keyframe LiDAR call sequence executed by the CPU oracle
 (OpenMP at the reference's tbb::parallel_for sites). TEST INFRASTRUCTURE / CPU BASELINE ONLY:
 used by tests/ for end-to-end comparisons and by bench.py's cpu_baseline and --impl reference
-legs. Mirrors ff-lins_b200/fflins/pipeline.py call for call."""
+legs. Mirrors ff-lins_b200/fflins/pipeline.py call for call, with the reference's own life cycle: the search tree
+of a keyframe map is built ONCE when the keyframe is added (lidar_map.cc:100-118) and reused by every later
+association; all (ref, query) pairs of an association run in one parallel loop (lidar_map.cc:436-444, 349-398);
+one solver iteration's factor work is one C call."""
 import time
 
 import numpy as np
@@ -11,9 +14,10 @@ from . import pyoracle as O
 
 class CpuSession:
     def __init__(self, seq, threads=None, frames_per_key=5, window=10, n_eval=(5, 10), knn_mode=1, leaf=0.5,
-                 sigma=0.1, flags=1):
+                 sigma=0.1, flags=1, oracle=None):
+        self.O = oracle or O     # (bench.py passes a second build of the same oracle for its -march=native figure)
         self.seq = seq
-        self.threads = threads or O.max_threads()
+        self.threads = threads or self.O.max_threads()
         self.K = frames_per_key
         self.window = window
         self.n_eval = n_eval
@@ -31,6 +35,7 @@ class CpuSession:
         self.t[name] = self.t.get(name, 0.0) + (time.perf_counter() - t0)
 
     def process_frame(self, fr):
+        O = self.O
         s = self.seq
         t0 = time.perf_counter()
         und, R, t, fb = O.undistort(fr["xyzi"], fr["time"], fr["ins_t"], fr["ins_p"], fr["ins_q"], s.R_bl, s.t_bl,
@@ -46,6 +51,7 @@ class CpuSession:
         return dict(und=und, dec=dec, down=down, world=world, R=R, t=t, fr=fr, fallback=fb)
 
     def after_frame(self, f, force_key=None):
+        O = self.O
         is_key = force_key if force_key is not None else (len(self.nonkeys) + 1 >= self.K)
         if not is_key:
             self.nonkeys.append(f)
@@ -61,62 +67,66 @@ class CpuSession:
         f["map"] = O.voxel_filter(f["map_full"], self.leaf)
         self._tick("voxel_map", t0)
         self.nonkeys = []
+        t0 = time.perf_counter()
+        f["tree"] = O.MapTree(f["map"])   # KD_TREE::build once per keyframe (addNewKeyFrame, lidar_map.cc:100-118)
+        self._tick("tree_build", t0)
         self.keys.append(f)
         if len(self.keys) >= 2:
             cur = self.keys[-1]
             refs = self.keys[:-1]
+            n = len(refs)
             t0 = time.perf_counter()
-            feats = []
-            for ref in refs:   # kd-tree build + search per ref (lidar_map.cc:100-118, 436-444)
-                feats.append(O.associate(ref["R"], ref["t"], cur["world"], cur["down"], ref["map"], sigma=self.sigma,
-                                         knn_mode=self.knn_mode, threads=self.threads))
+            # updateLidarFeaturesInMap (lidar_map.cc:428-459): all refs x all queries in one parallel loop
+            aw = O.associate_window([r["tree"] for r in refs], [r["R"] for r in refs], [r["t"] for r in refs],
+                                    cur["world"], cur["down"], sigma=self.sigma, threads=self.threads)
             self._tick("associate", t0)
-            for ref, ft in zip(refs, feats):
+            feats = []
+            for i, ref in enumerate(refs):
+                ft = {k: aw[k][i] for k in ("type", "covered", "nn_idx", "nn_d2", "normal", "d")}
+                ft["num_features"], ft["num_covered"] = int(aw["num_features"][i]), int(aw["num_covered"][i])
                 ref["feat"] = ft
-                ref["outlier"] = np.zeros(len(cur["down"]), np.uint8)
+                feats.append(ft)
             s = self.seq
-            pose_refs = [s.imu_pose7(r["fr"]["stamp"]) for r in refs]
-            pose_cur = s.imu_pose7(cur["fr"]["stamp"])
+            pose_refs = np.ascontiguousarray(np.stack([s.imu_pose7(r["fr"]["stamp"]) for r in refs]))
+            pose_cur = np.ascontiguousarray(s.imu_pose7(cur["fr"]["stamp"]))
             td = cur["fr"]["td"]
             mc = np.concatenate([cur["fr"]["v"], cur["fr"]["omega"], [cur["fr"]["td"]]])
-            q = len(cur["down"])
-            std = np.full(q, self.sigma)
+            motions = np.ascontiguousarray(np.stack([np.concatenate([r["fr"]["v"], r["fr"]["omega"], [r["fr"]["td"]], mc])
+                                                     for r in refs]))
             pts = np.ascontiguousarray(cur["down"][:, :3])
+            outlier = np.zeros(aw["type"].shape, np.uint8)
+            is_plane = np.ascontiguousarray((aw["type"] == 0).astype(np.uint8))
+            ext7 = np.ascontiguousarray(self.ext7, dtype=np.float64)
+            bufs = None
 
             def evaluate():
-                out = []
-                for ref, pr in zip(refs, pose_refs):
-                    ft = ref["feat"]
-                    valid = ((ft["type"] == 0) & (ref["outlier"] == 0)).astype(np.uint8)
-                    motion = np.concatenate([ref["fr"]["v"], ref["fr"]["omega"], [ref["fr"]["td"]], mc])
-                    out.append(O.factor_batch(pts, ft["normal"], ft["d"], std, valid, motion, pr, pose_cur, self.ext7,
-                                              td, flags=self.flags, threads=self.threads))
-                return out
+                # one solver iteration: every valid residual of every pair, one C call (optimizer.cc:437-490 + the solve)
+                valid = is_plane & (outlier == 0)
+                return O.window_eval(pts, aw["normal"], aw["d"], self.sigma, valid, motions, pose_refs, pose_cur, ext7, td,
+                                     flags=self.flags, threads=self.threads, out=bufs)
             t0 = time.perf_counter()
             ev = None
             for _ in range(self.n_eval[0]):
-                ev = evaluate()
+                ev = bufs = evaluate()
             self._tick("factor_eval", t0)
             t0 = time.perf_counter()
-            n_out = []
-            for ref, pr in zip(refs, pose_refs):
-                ft = ref["feat"]
-                valid = ((ft["type"] == 0) & (ref["outlier"] == 0)).astype(np.uint8)
-                motion = np.concatenate([ref["fr"]["v"], ref["fr"]["omega"], [ref["fr"]["td"]], mc])
-                mask, c = O.chi2(pts, ft["normal"], ft["d"], std, valid, motion, pr, pose_cur, self.ext7, td,
-                                 threads=self.threads)
-                ref["outlier"] |= mask
-                n_out.append(c)
+            n_out = O.window_chi2(pts, aw["normal"], aw["d"], self.sigma, is_plane, motions, pose_refs, pose_cur, ext7, td,
+                                  outlier, threads=self.threads)
             self._tick("chi2", t0)
             t0 = time.perf_counter()
             for _ in range(self.n_eval[1]):
-                ev = evaluate()
+                ev = bufs = evaluate()
             self._tick("factor_eval", t0)
+            for i, ref in enumerate(refs):
+                ref["outlier"] = outlier[i]
             t0 = time.perf_counter()
             for k in self.keys:
                 k["world"] = O.project(k["R"], k["t"], k["down"], threads=self.threads)
             self._tick("reproject", t0)
-            self.last = dict(eval=ev, chi2=n_out, feats=feats)
+            # per-pair tuples (r, J, H, b, cost) as the per-ref oracle call returns them (tests index [i][2] = H)
+            self.last = dict(eval=[(None, None, ev[0][i], ev[1][i], ev[2][i]) for i in range(n)], chi2=list(n_out),
+                             feats=feats)
         if len(self.keys) > self.window:
-            self.keys.pop(0)
+            old = self.keys.pop(0)
+            old["tree"].close()
         return True

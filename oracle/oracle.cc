@@ -796,75 +796,128 @@ int orc_plane_estimation(const float *pts, double threshold, double *unit_normal
     return plane_estimation(pts, threshold, unit_normal, norm_inverse, distance) ? 1 : 0;
 }
 
+/* One query of LidarMap::findFeaturesInMap (lidar/lidar_map.cc:349-398). tree == nullptr: brute force. */
+static inline void associate_query(const Pose &T, const KdTree *tree, const float *map_xyzi, int m, const float *world_k,
+                                   const float *lidar_k, double max_sq, double plane_thr, double sigma, double scalar_thr,
+                                   double sigma_gate, int8_t *type, uint8_t *covered, int32_t *nn_idx, float *nn_d2,
+                                   double *normal, double *dd) {
+    float ref[4];
+    project_point(T, world_k, ref);
+    int32_t idx[5] = {-1, -1, -1, -1, -1};
+    float d2[5]    = {0, 0, 0, 0, 0};
+    int found;
+    if (tree) {
+        KdTree::Top5 top;
+        if (m > 0) tree->search_rec(0, ref, (float) (max_sq * max_sq), top);
+        found = top.n;
+        for (int j = 0; j < found; j++) {
+            idx[j] = top.idx[j];
+            d2[j]  = top.d2[j];
+        }
+    } else {
+        found = knn5_brute(map_xyzi, m, ref, max_sq, idx, d2);
+    }
+    double unit[3] = {0, 0, 0}, ninv = 0;
+    int8_t ftype = -1;
+    uint8_t cov  = 0;
+    if (found == 5) {
+        cov = 1;
+        if ((double) d2[4] < max_sq) {
+            float pts[20];
+            for (int j = 0; j < 5; j++) std::memcpy(pts + 4 * j, map_xyzi + 4 * idx[j], 16);
+            double dist[5];
+            if (plane_estimation(pts, plane_thr, unit, &ninv, dist)) {
+                double dis = std::fabs(
+                    ((unit[0] * (double) ref[0] + unit[1] * (double) ref[1]) + unit[2] * (double) ref[2]) + ninv);
+                const float *l = lidar_k;
+                float nrm      = std::sqrt((l[0] * l[0] + l[1] * l[1]) + l[2] * l[2]);
+                double scalar  = dis / (double) std::sqrt(nrm); /* fp32 sqrt of fp32 norm (:384) */
+                if (scalar < scalar_thr && dis < sigma_gate * sigma) ftype = 0;
+            }
+        }
+    }
+    *type    = ftype;
+    *covered = cov;
+    for (int j = 0; j < 5; j++) {
+        nn_idx[j] = j < found ? idx[j] : -1;
+        nn_d2[j]  = j < found ? d2[j] : 0.f;
+    }
+    normal[0] = unit[0];
+    normal[1] = unit[1];
+    normal[2] = unit[2];
+    *dd       = ninv;
+}
+
+static inline Pose world_to_ref(const double *ref_R, const double *ref_t) {
+    Pose T;
+    T.R = tr(ldm(ref_R));
+    M3 negR = T.R;
+    for (int i = 0; i < 9; i++) negR.m[i] = -negR.m[i];
+    T.t = mv(negR, ld3(ref_t));
+    return T;
+}
+
 /* LidarMap::findFeaturesInMap (lidar/lidar_map.cc:326-408). ref_R/ref_t is the REF frame's
  * pose (lidar->world); the world->ref transform is formed as at :343-345. */
 void orc_associate(const double *ref_R, const double *ref_t, const float *cur_world, const float *cur_lidar, int q,
                    const float *map_xyzi, int m, double max_sq, double plane_thr, double sigma, double scalar_thr,
                    double sigma_gate, int knn_mode, int threads, int8_t *type, uint8_t *covered, int32_t *nn_idx,
                    float *nn_d2, double *normal, double *dd, int32_t *num_features, int32_t *num_covered) {
-    Pose T;
-    T.R = tr(ldm(ref_R));
-    {
-        M3 negR = T.R;
-        for (int i = 0; i < 9; i++) negR.m[i] = -negR.m[i];
-        T.t = mv(negR, ld3(ref_t));
-    }
+    const Pose T = world_to_ref(ref_R, ref_t);
     KdTree tree;
     if (knn_mode == 1) tree.build(map_xyzi, m);
     int nf = 0, nc = 0;
     (void) threads;
 #pragma omp parallel for num_threads(threads > 0 ? threads : 1) reduction(+ : nf, nc) schedule(dynamic, 64)
     for (int k = 0; k < q; k++) {
-        float ref[4];
-        project_point(T, cur_world + 4 * k, ref);
-        int32_t idx[5] = {-1, -1, -1, -1, -1};
-        float d2[5]    = {0, 0, 0, 0, 0};
-        int found;
-        if (knn_mode == 1) {
-            KdTree::Top5 top;
-            if (m > 0) tree.search_rec(0, ref, (float) (max_sq * max_sq), top);
-            found = top.n;
-            for (int j = 0; j < found; j++) {
-                idx[j] = top.idx[j];
-                d2[j]  = top.d2[j];
-            }
-        } else {
-            found = knn5_brute(map_xyzi, m, ref, max_sq, idx, d2);
-        }
-        double unit[3] = {0, 0, 0}, ninv = 0;
-        int8_t ftype = -1;
-        uint8_t cov  = 0;
-        if (found == 5) {
-            cov = 1;
-            if ((double) d2[4] < max_sq) {
-                float pts[20];
-                for (int j = 0; j < 5; j++) std::memcpy(pts + 4 * j, map_xyzi + 4 * idx[j], 16);
-                double dist[5];
-                if (plane_estimation(pts, plane_thr, unit, &ninv, dist)) {
-                    double dis = std::fabs(
-                        ((unit[0] * (double) ref[0] + unit[1] * (double) ref[1]) + unit[2] * (double) ref[2]) + ninv);
-                    const float *l = cur_lidar + 4 * k;
-                    float nrm      = std::sqrt((l[0] * l[0] + l[1] * l[1]) + l[2] * l[2]);
-                    double scalar  = dis / (double) std::sqrt(nrm); /* fp32 sqrt of fp32 norm (:384) */
-                    if (scalar < scalar_thr && dis < sigma_gate * sigma) ftype = 0;
-                }
-            }
-        }
-        type[k]    = ftype;
-        covered[k] = cov;
-        for (int j = 0; j < 5; j++) {
-            nn_idx[5 * k + j] = j < found ? idx[j] : -1;
-            nn_d2[5 * k + j]  = j < found ? d2[j] : 0.f;
-        }
-        normal[3 * k]     = unit[0];
-        normal[3 * k + 1] = unit[1];
-        normal[3 * k + 2] = unit[2];
-        dd[k]             = ninv;
-        nf += (ftype == 0);
-        nc += cov;
+        associate_query(T, knn_mode == 1 ? &tree : nullptr, map_xyzi, m, cur_world + 4 * k, cur_lidar + 4 * k, max_sq, plane_thr,
+                        sigma, scalar_thr, sigma_gate, type + k, covered + k, nn_idx + 5 * k, nn_d2 + 5 * k, normal + 3 * k, dd + k);
+        nf += (type[k] == 0);
+        nc += covered[k];
     }
     *num_features = nf;
     *num_covered  = nc;
+}
+
+/* ---- the reference's keyframe life cycle for the CPU BASELINE: the tree of a keyframe map is built ONCE when the
+ * keyframe is added (LidarMap::addNewKeyFrame, lidar_map.cc:100-118) and searched by every later association. The map
+ * array must outlive the handle. */
+void *orc_tree_build(const float *map_xyzi, int m) {
+    KdTree *t = new KdTree();
+    t->build(map_xyzi, m);
+    return t;
+}
+void orc_tree_free(void *tree) { delete static_cast<KdTree *>(tree); }
+
+/* LidarMap::updateLidarFeaturesInMap (lidar_map.cc:428-459): every reference keyframe against the current one, the
+ * reference's nested tbb::parallel_for (refs :436-444, queries :349-398) restated as one OpenMP loop over all
+ * (ref, query) pairs. Per-ref inputs are arrays of pointers; outputs are [n_refs][q] row-major. */
+void orc_associate_window(int n_refs, void *const *trees, const float *const *maps, const int *m, const double *ref_R,
+                          const double *ref_t, const float *cur_world, const float *cur_lidar, int q, double max_sq,
+                          double plane_thr, double sigma, double scalar_thr, double sigma_gate, int threads, int8_t *type,
+                          uint8_t *covered, int32_t *nn_idx, float *nn_d2, double *normal, double *dd, int32_t *num_features,
+                          int32_t *num_covered) {
+    std::vector<Pose> T(n_refs);
+    for (int r = 0; r < n_refs; r++) T[r] = world_to_ref(ref_R + 9 * r, ref_t + 3 * r);
+    (void) threads;
+    const long total = (long) n_refs * q;
+#pragma omp parallel for num_threads(threads > 0 ? threads : 1) schedule(dynamic, 64)
+    for (long e = 0; e < total; e++) {
+        const int r = (int) (e / q), k = (int) (e % q);
+        const size_t o = (size_t) r * q + k;
+        associate_query(T[r], static_cast<const KdTree *>(trees[r]), maps[r], m[r], cur_world + 4 * k, cur_lidar + 4 * k, max_sq,
+                        plane_thr, sigma, scalar_thr, sigma_gate, type + o, covered + o, nn_idx + 5 * o, nn_d2 + 5 * o,
+                        normal + 3 * o, dd + o);
+    }
+    for (int r = 0; r < n_refs; r++) {
+        int nf = 0, nc = 0;
+        for (int k = 0; k < q; k++) {
+            nf += type[(size_t) r * q + k] == 0;
+            nc += covered[(size_t) r * q + k];
+        }
+        num_features[r] = nf;
+        num_covered[r]  = nc;
+    }
 }
 
 int orc_lidar_factor_evaluate(const float *point_xyz, const double *n, double d, double std, const double *motion,
@@ -954,6 +1007,110 @@ int orc_chi2(int n, const float *point_xyz, const double *normal, const double *
         }
     }
     return count;
+}
+
+
+/* One solver iteration's worth of LiDAR factor work for the CPU BASELINE, in one call: every valid residual of every
+ * (ref, cur) pair evaluated in parallel (Ceres evaluates residual blocks on its thread pool, optimizer.cc:103) and
+ * reduced the way MarginalizationInfo::constructEquation does it (marginalization_info.cc:133-179): the factors are
+ * split into `threads` chunks, each chunk accumulates its own H0 / b0 (constructSingleEquation :181-210), the chunks
+ * are summed serially (:174-177). Inputs per pair are [n_pairs][q] row-major (normal [n_pairs][q][3]); motions
+ * [n_pairs][14]; pose_refs [n_pairs][7]. Outputs H [n_pairs][361], b [n_pairs][19], cost [n_pairs][2]. */
+void orc_window_eval(int n_pairs, int q, const float *point_xyz, const double *normal, const double *d, double std,
+                     const uint8_t *valid, const double *motions, const double *pose_refs, const double *pose_cur,
+                     const double *ext, double td, uint32_t flags, double huber_delta, double *H, double *b, double *cost,
+                     int threads) {
+    const int T = threads > 0 ? threads : 1;
+    const long total = (long) n_pairs * q;
+    struct Acc {
+        double H[19 * 19], b[19], c0, c1;
+    };
+    std::vector<Acc> acc((size_t) T * n_pairs);
+    std::memset(acc.data(), 0, acc.size() * sizeof(Acc));
+#pragma omp parallel num_threads(T)
+    {
+        int tid = 0;
+#ifdef _OPENMP
+        tid = omp_get_thread_num();
+#endif
+        /* contiguous chunk of the factor list per thread, as constructEquation hands them out */
+        const long lo = total * tid / T, hi = total * (tid + 1) / T;
+        for (long e = lo; e < hi; e++) {
+            const int p = (int) (e / q), k = (int) (e % q);
+            if (valid && !valid[e]) continue;
+            const double *par[4] = {pose_refs + 7 * p, pose_cur, ext, &td};
+            FactorConst f        = make_const(point_xyz + 3 * k, normal + 3 * e, d[e], std, motions + 14 * p);
+            double Jk[22], r;
+            double *jac[4] = {Jk, Jk + 7, Jk + 14, Jk + 21};
+            lidar_factor(f, par, &r, jac);
+            if (flags & 2u)
+                for (int i = 0; i < 7; i++) Jk[i] = 0;
+            if (flags & 4u)
+                for (int i = 0; i < 7; i++) Jk[7 + i] = 0;
+            if (flags & 8u)
+                for (int i = 0; i < 7; i++) Jk[14 + i] = 0;
+            if (flags & 16u) Jk[21] = 0;
+            double rho0 = (flags & 1u) ? huber_correct(huber_delta, &r, Jk) : r * r;
+            Acc &a = acc[(size_t) tid * n_pairs + p];
+            double jl[19];
+            for (int i = 0; i < 19; i++) jl[i] = Jk[LOCAL_OF_J[i]];
+            for (int i = 0; i < 19; i++) {
+                for (int c = i; c < 19; c++) a.H[19 * i + c] += jl[i] * jl[c];
+                a.b[i] -= jl[i] * r;
+            }
+            a.c0 += rho0;
+            a.c1 += r * r;
+        }
+    }
+    for (int p = 0; p < n_pairs; p++) {
+        Acc s;
+        std::memset(&s, 0, sizeof(s));
+        for (int t = 0; t < T; t++) {
+            const Acc &a = acc[(size_t) t * n_pairs + p];
+            for (int i = 0; i < 361; i++) s.H[i] += a.H[i];
+            for (int i = 0; i < 19; i++) s.b[i] += a.b[i];
+            s.c0 += a.c0;
+            s.c1 += a.c1;
+        }
+        for (int i = 0; i < 19; i++)
+            for (int c = i + 1; c < 19; c++) s.H[19 * c + i] = s.H[19 * i + c];
+        if (H) std::memcpy(H + 361 * (size_t) p, s.H, sizeof(s.H));
+        if (b) std::memcpy(b + 19 * (size_t) p, s.b, sizeof(s.b));
+        if (cost) {
+            cost[2 * p]     = 0.5 * s.c0;
+            cost[2 * p + 1] = s.c1;
+        }
+    }
+}
+
+/* Optimizer::lidarOutlierCullingByChi2 over the whole window in one call (optimizer.cc:515-548: one tbb loop over all
+ * residual blocks). outlier [n_pairs][q] is OR-ed in place; counts [n_pairs]. */
+void orc_window_chi2(int n_pairs, int q, const float *point_xyz, const double *normal, const double *d, double std,
+                     const uint8_t *valid, const double *motions, const double *pose_refs, const double *pose_cur,
+                     const double *ext, double td, double threshold, uint8_t *outlier, int32_t *counts, int threads) {
+    const long total = (long) n_pairs * q;
+    (void) threads;
+#pragma omp parallel for num_threads(threads > 0 ? threads : 1) schedule(static)
+    for (long e = 0; e < total; e++) {
+        const int p = (int) (e / q), k = (int) (e % q);
+        if ((valid && !valid[e]) || outlier[e]) continue;
+        const double *par[4] = {pose_refs + 7 * p, pose_cur, ext, &td};
+        FactorConst f        = make_const(point_xyz + 3 * k, normal + 3 * e, d[e], std, motions + 14 * p);
+        double res;
+        lidar_factor(f, par, &res, nullptr);
+        if (res * res > threshold) outlier[e] = 2; /* newly culled */
+    }
+    for (int p = 0; p < n_pairs; p++) {
+        int c = 0;
+        for (int k = 0; k < q; k++) {
+            uint8_t &o = outlier[(size_t) p * q + k];
+            if (o == 2) {
+                o = 1;
+                c++;
+            }
+        }
+        counts[p] = c;
+    }
 }
 
 } /* extern "C" */

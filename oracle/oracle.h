@@ -59,6 +59,22 @@ void orc_factor_batch(int n, const float *point_xyz, const double *normal, const
 int  orc_chi2(int n, const float *point_xyz, const double *normal, const double *d, const double *std,
               const uint8_t *valid, const double *motion, const double *pose_ref, const double *pose_cur,
               const double *ext, double td, double threshold, uint8_t *outlier, int threads);
+/* ---- CPU-baseline forms of the per-keyframe work (bench.py's reference arm): same arithmetic, the reference's own
+ * life cycle and parallel structure. */
+void *orc_tree_build(const float *map_xyzi, int m);     /* once per keyframe (lidar_map.cc:100-118) */
+void orc_tree_free(void *tree);
+void orc_associate_window(int n_refs, void *const *trees, const float *const *maps, const int *m, const double *ref_R,
+                          const double *ref_t, const float *cur_world, const float *cur_lidar, int q, double max_sq,
+                          double plane_thr, double sigma, double scalar_thr, double sigma_gate, int threads, int8_t *type,
+                          uint8_t *covered, int32_t *nn_idx, float *nn_d2, double *normal, double *d, int32_t *num_features,
+                          int32_t *num_covered);
+void orc_window_eval(int n_pairs, int q, const float *point_xyz, const double *normal, const double *d, double std,
+                     const uint8_t *valid, const double *motions, const double *pose_refs, const double *pose_cur,
+                     const double *ext, double td, uint32_t flags, double huber_delta, double *H, double *b, double *cost,
+                     int threads);
+void orc_window_chi2(int n_pairs, int q, const float *point_xyz, const double *normal, const double *d, double std,
+                     const uint8_t *valid, const double *motions, const double *pose_refs, const double *pose_cur,
+                     const double *ext, double td, double threshold, uint8_t *outlier, int32_t *counts, int threads);
 int  orc_max_threads(void);
 
 #ifdef __cplusplus

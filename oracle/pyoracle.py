@@ -26,7 +26,8 @@ def build():
 def lib():
     global _LIB
     if _LIB is None:
-        path = os.path.join(HERE, "liboracle.so")
+        # FFLINS_ORACLE_LIB: an alternative build of the same source (bench.py's labelled -march=native figure)
+        path = os.environ.get("FFLINS_ORACLE_LIB") or os.path.join(HERE, "liboracle.so")
         if not os.path.exists(path):
             build()
         L = C.CDLL(path)
@@ -55,6 +56,21 @@ def lib():
         L.orc_factor_batch.restype = None
         L.orc_chi2.argtypes = [C.c_int, f32p, f64p, f64p, f64p, C.c_void_p, f64p, f64p, f64p, f64p, C.c_double,
                                C.c_double, u8p, C.c_int]
+        pp = C.POINTER(C.c_void_p)
+        L.orc_tree_build.argtypes = [f32p, C.c_int]
+        L.orc_tree_build.restype = C.c_void_p
+        L.orc_tree_free.argtypes = [C.c_void_p]
+        L.orc_tree_free.restype = None
+        L.orc_associate_window.argtypes = [C.c_int, pp, pp, i32p, f64p, f64p, f32p, f32p, C.c_int, C.c_double, C.c_double,
+                                           C.c_double, C.c_double, C.c_double, C.c_int, i8p, u8p, i32p, f32p, f64p, f64p,
+                                           i32p, i32p]
+        L.orc_associate_window.restype = None
+        L.orc_window_eval.argtypes = [C.c_int, C.c_int, f32p, f64p, f64p, C.c_double, u8p, f64p, f64p, f64p, f64p,
+                                      C.c_double, C.c_uint32, C.c_double, f64p, f64p, f64p, C.c_int]
+        L.orc_window_eval.restype = None
+        L.orc_window_chi2.argtypes = [C.c_int, C.c_int, f32p, f64p, f64p, C.c_double, u8p, f64p, f64p, f64p, f64p,
+                                      C.c_double, C.c_double, u8p, i32p, C.c_int]
+        L.orc_window_chi2.restype = None
         _LIB = L
     return _LIB
 
@@ -229,6 +245,76 @@ def chi2(point_xyz, normal, d, std, valid, motion, pose_ref, pose_cur, ext, td, 
                        None if v is None else v.ctypes.data, _c(motion, np.float64), _c(pose_ref, np.float64),
                        _c(pose_cur, np.float64), _c(ext, np.float64), float(td), float(threshold), out, threads)
     return out, c
+
+
+# ---- CPU-baseline forms: the reference's keyframe life cycle (tree built once per keyframe) and window-level calls ----
+class MapTree:
+    """Exact static kd-tree over one keyframe map, built once (LidarMap::addNewKeyFrame, lidar_map.cc:100-118)."""
+
+    def __init__(self, map_xyzi):
+        self.map = _c(map_xyzi, np.float32).reshape(-1, 4)
+        if len(self.map) == 0:
+            self.map = np.zeros((1, 4), np.float32)
+            self.m = 0
+        else:
+            self.m = len(self.map)
+        self.h = lib().orc_tree_build(self.map, self.m)
+
+    def close(self):
+        if self.h:
+            lib().orc_tree_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def associate_window(trees, ref_R, ref_t, cur_world, cur_lidar, max_sq=5.0, plane_thr=0.1, sigma=0.1, scalar_thr=0.1,
+                     sigma_gate=4.5, threads=1):
+    """updateLidarFeaturesInMap: every ref (MapTree) against the current keyframe in one parallel loop."""
+    n = len(trees)
+    cur_world = _c(cur_world, np.float32)
+    cur_lidar = _c(cur_lidar, np.float32)
+    q = len(cur_world)
+    out = dict(type=np.zeros((n, q), np.int8), covered=np.zeros((n, q), np.uint8), nn_idx=np.zeros((n, q, 5), np.int32),
+               nn_d2=np.zeros((n, q, 5), np.float32), normal=np.zeros((n, q, 3)), d=np.zeros((n, q)),
+               num_features=np.zeros(n, np.int32), num_covered=np.zeros(n, np.int32))
+    hs = (C.c_void_p * n)(*[t.h for t in trees])
+    ms = (C.c_void_p * n)(*[t.map.ctypes.data for t in trees])
+    m = np.array([t.m for t in trees], np.int32)
+    R = _c(np.stack([np.asarray(r).reshape(9) for r in ref_R]), np.float64).reshape(-1)
+    T = _c(np.stack([np.asarray(t).reshape(3) for t in ref_t]), np.float64).reshape(-1)
+    lib().orc_associate_window(n, hs, ms, m, R, T, cur_world.reshape(-1), cur_lidar.reshape(-1), q, max_sq, plane_thr, sigma,
+                               scalar_thr, sigma_gate, threads, out["type"].reshape(-1), out["covered"].reshape(-1),
+                               out["nn_idx"].reshape(-1), out["nn_d2"].reshape(-1), out["normal"].reshape(-1),
+                               out["d"].reshape(-1), out["num_features"], out["num_covered"])
+    return out
+
+
+def window_eval(point_xyz, normal, d, std, valid, motions, pose_refs, pose_cur, ext, td, flags=0, huber_delta=1.0, threads=1,
+                out=None):
+    """All pairs of the window in one call; inputs [n, q(, 3)]; returns H [n,19,19], b [n,19], cost [n,2]."""
+    n, q = d.shape
+    if out is None:
+        out = (np.zeros((n, 19, 19)), np.zeros((n, 19)), np.zeros((n, 2)))
+    H, b, cost = out
+    lib().orc_window_eval(n, q, point_xyz, normal.reshape(-1), d.reshape(-1), float(std), valid.reshape(-1),
+                          motions.reshape(-1), pose_refs.reshape(-1), pose_cur, ext, float(td), int(flags),
+                          float(huber_delta), H.reshape(-1), b.reshape(-1), cost.reshape(-1), threads)
+    return H, b, cost
+
+
+def window_chi2(point_xyz, normal, d, std, valid, motions, pose_refs, pose_cur, ext, td, outlier, threshold=3.841, threads=1):
+    """outlier [n, q] uint8 is updated in place; returns the per-pair counts of newly culled residuals."""
+    n, q = d.shape
+    counts = np.zeros(n, np.int32)
+    lib().orc_window_chi2(n, q, point_xyz, normal.reshape(-1), d.reshape(-1), float(std), valid.reshape(-1),
+                          motions.reshape(-1), pose_refs.reshape(-1), pose_cur, ext, float(td), float(threshold),
+                          outlier.reshape(-1), counts, threads)
+    return counts
 
 
 # ---- the reference's own ikd-Tree (compiled from /root/reference, oracle/Makefile `ref`) ----

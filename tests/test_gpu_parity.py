@@ -11,6 +11,7 @@ import numpy as np
 import pytest
 
 from util import bits_equal, block_rel, rand_pose, random_scene_cloud, ulp_diff
+from util import build_window as _build_window, window_params as _window_params
 
 pytestmark = pytest.mark.gpu
 
@@ -268,51 +269,6 @@ def test_knn5_ties_broken_by_index(ctx, oracle):
 
 
 # ---------------------------------------------------------------- M1 merge + A3/A4 association
-def _build_window(ctx, oracle, seq, n_keys, frames_per_key, first_id=1000):
-    """Drive GPU and oracle side by side over the same frames; the GPU side is fed the ORACLE's
-    undistorted clouds (staged parity)."""
-    from fflins import api
-    leaf = 0.5
-    F = seq.filter_num
-    keys = []
-    fid = first_id
-    fi = 0
-    for k in range(n_keys):
-        group = []
-        for j in range(frames_per_key):
-            fr = seq.frame(fi)
-            fi += 1
-            und, R, t, _ = oracle.undistort(fr["xyzi"], fr["time"], fr["ins_t"], fr["ins_p"], fr["ins_q"], seq.R_bl,
-                                            seq.t_bl, fr["stamp"], fr["td"], threads=8)
-            dec = oracle.decimate(und, F)
-            down = oracle.voxel_filter(dec, leaf)
-            world = oracle.project(R, t, down)
-            ctx.upload(fid, api.CLOUD_MAP_FULL, und)
-            ctx.upload(fid, api.CLOUD_LIDAR_FULL, dec)
-            ctx.upload(fid, api.CLOUD_LIDAR, down)
-            ctx.upload(fid, api.CLOUD_WORLD, world)
-            ctx.set_pose(fid, R, t)
-            group.append(dict(id=fid, und=und, down=down, world=world, R=R, t=t, fr=fr))
-            fid += 1
-        key = group[-1]
-        # oracle merge (lidar_map.cc:190-211)
-        clouds = [key["und"]]
-        for g in group[:-1]:
-            Rr, tr = oracle.relative_pose(key["R"], key["t"], g["R"], g["t"])
-            clouds.append(oracle.project(Rr, tr, g["und"]))
-        full = np.concatenate(clouds)
-        key["map_full"] = full
-        key["map"] = oracle.voxel_filter(full, leaf)
-        info = ctx.keyframe_merge(key["id"], [g["id"] for g in group[:-1]])
-        assert info.n_map == len(key["map"])
-        for g in group[:-1]:
-            ctx.release(g["id"])
-        ctx.keyframe_add(key["id"])
-        ctx.set_motion(key["id"], key["fr"]["v"], key["fr"]["omega"], key["fr"]["td"])
-        keys.append(key)
-    return keys
-
-
 @pytest.fixture(scope="module", params=["robot", "ouster64", "lili"])
 def window(request):
     """A small sliding window per sensor config: robot (identity extrinsic), ouster64 (65 k points, 400 Hz
@@ -420,13 +376,6 @@ def test_factor_kat_coincident_poses(ctx):
     assert abs(r[0]) < 1e-12
     assert np.allclose(J[0, 0:3], -J[0, 7:10], atol=0, rtol=0)
     assert np.allclose(J[0, 7:10], [0, 0, 10.0], atol=1e-12)
-
-
-def _window_params(seq, keys, rng):
-    cur = keys[-1]
-    pose_refs = np.stack([seq.imu_pose7(k["fr"]["stamp"], rng, 0.01, 0.002) for k in keys[:-1]])
-    pose_cur = seq.imu_pose7(cur["fr"]["stamp"], rng, 0.01, 0.002)
-    return pose_refs, pose_cur, seq.ext7(), cur["fr"]["td"] + 0.003
 
 
 def test_marginalization_prior_from_device_blocks(window, oracle):

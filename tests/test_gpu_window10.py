@@ -1,0 +1,302 @@
+"""Parity on the configuration bench.py times: the AT128-shaped sequence with a FULL sliding window
+(11 keyframes x 5 frames -> 10 reference keyframes), plus a 15-keyframe window (14 references, the
+largest the context accepts), compared with the oracle for EVERY (ref, query) pair.
+
+  association   idx / d2 / type / normal bit-exact              lidar_map.cc:326-459
+  factors       H, b, cost <= 1e-9 per block                    lidar_factor.cc:41-118, marginalization_info.cc:181-210
+  chi2 cull     outlier mask identical                          optimizer.cc:515-548
+and each factor / chi2 result once through the RESIDENT evaluation kernel (mailbox) and once through
+the launched kernel (the profiler forces it), which must agree bit for bit.
+Also: removeNewestLidarFrame, LidarFeature::setOutlier round trip, the single-keyframe association
+after an asynchronous frame, the kNN radius bound, and the unstaged
+end-to-end flip counts on at128 / ouster64."""
+import time
+
+import numpy as np
+import pytest
+
+from util import bits_equal, block_rel, build_window, window_params
+
+pytestmark = pytest.mark.gpu
+
+
+def _make_window(name, n_keys, frames_per_key, window_size=10):
+    from fflins import api, synth
+    from oracle import pyoracle
+    seq = synth.Sequence(name)
+    c = api.Context(api.default_config(point_filter_num=seq.filter_num, window_size=window_size))
+    keys = build_window(c, pyoracle, seq, n_keys=n_keys, frames_per_key=frames_per_key)
+    return c, seq, keys
+
+
+@pytest.fixture(scope="module")
+def window10():
+    """The benched configuration: at128, 11 keyframes of 5 frames (10 references)."""
+    c, seq, keys = _make_window("at128", 11, 5)
+    yield c, seq, keys
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def window15():
+    """14 references (robot frames: the pair count is what is being exercised)."""
+    c, seq, keys = _make_window("robot", 15, 2, window_size=15)
+    yield c, seq, keys
+    c.close()
+
+
+def _motion(key):
+    return np.concatenate([key["fr"]["v"], key["fr"]["omega"], [key["fr"]["td"]]])
+
+
+def _check_association(c, oracle, keys):
+    st = c.associate()
+    cur = keys[-1]
+    assert st.n_refs == len(keys) - 1 and st.n_queries == len(cur["down"])
+    planes = 0
+    for i, ref in enumerate(keys[:-1]):
+        o = oracle.associate(ref["R"], ref["t"], cur["world"], cur["down"], ref["map"], threads=8)
+        g = c.features(ref["id"])
+        assert np.array_equal(g["nn_idx"], o["nn_idx"]), f"ref {i}: kNN index 5-tuples must be bit-exact"
+        assert bits_equal(g["nn_d2"], o["nn_d2"])
+        assert np.array_equal(g["covered"], o["covered"]) and np.array_equal(g["type"], o["type"])
+        assert bits_equal(g["normal"], o["normal"]) and bits_equal(g["d"], o["d"])
+        assert st.num_features[i] == o["num_features"] and st.num_covered[i] == o["num_covered"]
+        planes += o["num_features"]
+    return st, planes
+
+
+def _eval_both_paths(c, refs, pose_refs, pose_cur, ext, td, flags):
+    """window_eval through the resident kernel and through a launch; returns (resident, launched)."""
+    s0 = c.eval_stats()
+    a = c.window_eval(refs, pose_refs, pose_cur, ext, td, flags)
+    s1 = c.eval_stats()
+    c.profile_enable(True)      # the per-stage profiler needs stream-ordered kernels: forces the launched path
+    b = c.window_eval(refs, pose_refs, pose_cur, ext, td, flags)
+    c.profile_enable(False)
+    s2 = c.eval_stats()
+    assert s2["launched_evals"] == s1["launched_evals"] + 1
+    resident = s1["resident_evals"] == s0["resident_evals"] + 1
+    return a, b, resident
+
+
+def _check_factors(c, oracle, seq, keys, flags, seed):
+    rng = np.random.default_rng(seed)
+    pose_refs, pose_cur, ext, td = window_params(seq, keys, rng)
+    cur = keys[-1]
+    refs = [k["id"] for k in keys[:-1]]
+    a, b, resident = _eval_both_paths(c, refs, pose_refs, pose_cur, ext, td, flags)
+    for k in ("H", "b", "cost", "n_res"):
+        assert bits_equal(a[k], b[k]), f"resident and launched evaluation differ in {k}"
+    q = len(cur["down"])
+    total = 0
+    for i, ref in enumerate(keys[:-1]):
+        f = c.features(ref["id"])
+        valid = ((f["type"] == 0) & (f["outlier"] == 0)).astype(np.uint8)
+        motion = np.concatenate([_motion(ref), _motion(cur)])
+        _, _, Ho, bo, co = oracle.factor_batch(cur["down"][:, :3], f["normal"], f["d"], np.full(q, 0.1), valid, motion,
+                                               pose_refs[i], pose_cur, ext, td, flags=flags)
+        assert a["n_res"][i] == valid.sum()
+        total += int(valid.sum())
+        if valid.sum() == 0:
+            assert not a["H"][i].any()
+            continue
+        assert block_rel(a["H"][i], Ho) <= 1e-9 and block_rel(a["b"][i], bo) <= 1e-9
+        assert block_rel(a["cost"][i], co) <= 1e-9
+        assert np.array_equal(a["H"][i], a["H"][i].T)
+    return total, resident
+
+
+def _check_chi2(c, oracle, seq, keys, seed):
+    rng = np.random.default_rng(seed)
+    pose_refs, pose_cur, ext, td = window_params(seq, keys, rng)
+    cur = keys[-1]
+    refs = [k["id"] for k in keys[:-1]]
+    q = len(cur["down"])
+    before = [c.features(r) for r in refs]
+    want = []
+    for i, ref in enumerate(keys[:-1]):
+        f = before[i]
+        valid = ((f["type"] == 0) & (f["outlier"] == 0)).astype(np.uint8)
+        motion = np.concatenate([_motion(ref), _motion(cur)])
+        want.append(oracle.chi2(cur["down"][:, :3], f["normal"], f["d"], np.full(q, 0.1), valid, motion, pose_refs[i],
+                                pose_cur, ext, td, 3.841))
+    s0 = c.eval_stats()
+    cnt = c.window_chi2(refs, pose_refs, pose_cur, ext, td, 3.841)          # resident (after a settled association)
+    s1 = c.eval_stats()
+    for i, r in enumerate(refs):
+        mask, n = want[i]
+        assert np.array_equal(c.features(r)["outlier"], mask | before[i]["outlier"]) and cnt[i] == n
+    # LidarFeature::setOutlier round trip: restore the flags, cull again through the launched kernel
+    for i, r in enumerate(refs):
+        c.set_outlier(r, before[i]["outlier"])
+        assert np.array_equal(c.features(r)["outlier"], before[i]["outlier"])
+    c.profile_enable(True)
+    cnt2 = c.window_chi2(refs, pose_refs, pose_cur, ext, td, 3.841)
+    c.profile_enable(False)
+    assert np.array_equal(cnt, cnt2)
+    for i, r in enumerate(refs):
+        assert np.array_equal(c.features(r)["outlier"], want[i][0] | before[i]["outlier"])
+    assert c.eval_stats()["launched_evals"] == s1["launched_evals"] + 1
+    return int(np.sum(cnt)), s1["resident_evals"] == s0["resident_evals"] + 1
+
+
+# ------------------------------------------------------------------------------------------------ at128, 10 refs
+def test_window10_association_every_pair(window10, oracle):
+    c, seq, keys = window10
+    st, planes = _check_association(c, oracle, keys)
+    assert st.n_refs == 10
+    print(f"at128 window10: Q={st.n_queries} M={[len(k['map']) for k in keys]} plane features={planes}")
+    assert planes > 1000
+
+
+@pytest.mark.parametrize("flags", [1, 0, 1 | 8 | 16])
+def test_window10_factor_blocks(window10, oracle, flags):
+    c, seq, keys = window10
+    c.associate()
+    total, resident = _check_factors(c, oracle, seq, keys, flags, 60 + flags)
+    assert total > 1000
+    assert resident, "after a settled association the evaluation must be served by the resident kernel"
+
+
+def test_window10_chi2(window10, oracle):
+    c, seq, keys = window10
+    c.associate()
+    n_out, resident = _check_chi2(c, oracle, seq, keys, 71)
+    assert resident
+    print(f"at128 window10: chi2 culled {n_out}")
+
+
+def test_window10_resident_retires_and_restarts(window10):
+    """The resident kernel retires after its idle period (1 ms) and is restarted by the next evaluation; results
+    are unchanged and no evaluation is lost across the boundary."""
+    c, seq, keys = window10
+    c.associate()
+    rng = np.random.default_rng(5)
+    pose_refs, pose_cur, ext, td = window_params(seq, keys, rng)
+    refs = [k["id"] for k in keys[:-1]]
+    first = c.window_eval(refs, pose_refs, pose_cur, ext, td, 1)
+    first = {k: v.copy() for k, v in first.items()}
+    s0 = c.eval_stats()
+    for _ in range(3):
+        time.sleep(0.02)
+        again = c.window_eval(refs, pose_refs, pose_cur, ext, td, 1)
+        assert bits_equal(again["H"], first["H"]) and bits_equal(again["b"], first["b"])
+    for _ in range(50):      # back to back: served without a restart
+        again = c.window_eval(refs, pose_refs, pose_cur, ext, td, 1)
+    assert bits_equal(again["H"], first["H"])
+    s1 = c.eval_stats()
+    assert s1["resident_launches"] >= s0["resident_launches"] + 2
+    assert s1["resident_evals"] + s1["launched_evals"] == s0["resident_evals"] + s0["launched_evals"] + 53
+    assert s1["resident_evals"] >= s0["resident_evals"] + 50
+
+
+def test_window10_remove_newest(window10, oracle):
+    """removeNewestLidarFrame (lidar_map.cc:175-188): the newest keyframe leaves the window, the previous one becomes
+    the current frame of the next association."""
+    from fflins import api
+    c, seq, keys = window10
+    ids = c.keyframe_ids()
+    assert ids == [k["id"] for k in keys]
+    rid = c.keyframe_remove_newest()
+    assert rid == keys[-1]["id"] and c.keyframe_ids() == ids[:-1]
+    with pytest.raises(api.FflinsError):
+        c.frame_info(rid)
+    st, planes = _check_association(c, oracle, keys[:-1])
+    assert st.n_refs == 9 and planes > 500
+    total, _ = _check_factors(c, oracle, seq, keys[:-1], 1, 81)
+    assert total > 500
+
+
+# ------------------------------------------------------------------------------------------------ 14 refs
+def test_window15_all_pairs(window15, oracle):
+    c, seq, keys = window15
+    st, planes = _check_association(c, oracle, keys)
+    assert st.n_refs == 14 and planes > 200
+    for flags in (1, 1 | 2, 1 | 4 | 16):
+        total, resident = _check_factors(c, oracle, seq, keys, flags, 90 + flags)
+        assert total > 200 and resident
+    _check_chi2(c, oracle, seq, keys, 93)
+
+
+# ------------------------------------------------------------------------------------------------ ADVICE r1
+def test_associate_single_keyframe_after_async_frame(oracle):
+    """A lone keyframe (no reference yet) right after an asynchronous frame: the association launches nothing, so the
+    frame's counts must be adopted behind a real synchronisation, never from a stale pinned slot."""
+    from fflins import api, synth
+    seq = synth.Sequence("robot")
+    c = api.Context(api.default_config(point_filter_num=seq.filter_num))
+    # occupy every pinned count slot once with a different (larger) frame, so stale values exist
+    big = synth.Sequence("lili")
+    for i in range(70):
+        fr = big.frame(i % 2)
+        c.frame_process(5000 + i, fr["xyzi"], fr["time"], fr["ins_t"], fr["ins_p"], fr["ins_q"], big.R_bl, big.t_bl,
+                        fr["stamp"], fr["td"])
+        c.release(5000 + i)
+    fr = seq.frame(0)
+    want = c.frame_process(1, fr["xyzi"], fr["time"], fr["ins_t"], fr["ins_p"], fr["ins_q"], seq.R_bl, seq.t_bl,
+                           fr["stamp"], fr["td"])
+    c.release(1)
+    c.frame_process(2, fr["xyzi"], fr["time"], fr["ins_t"], fr["ins_p"], fr["ins_q"], seq.R_bl, seq.t_bl, fr["stamp"],
+                    fr["td"], sync=False)
+    c.keyframe_merge(2, [], sync=False)
+    c.keyframe_add(2)
+    st = c.associate()
+    assert st.n_refs == 0
+    info = c.frame_info(2)
+    assert info.n_down == want.n_down and info.n_fallback == want.n_fallback
+    assert st.n_queries == want.n_down
+    c.close()
+
+
+def test_knn_search_radius_bound(ctx):
+    """The packed queue fields of the kNN hold offsets up to 495 cells: a leaf too small for the search radius is
+    rejected instead of silently wrapping."""
+    from fflins import api
+    with pytest.raises(api.FflinsError) as e:
+        api.Context(api.default_config(downsample_size=0.005))
+    assert e.value.code == -1
+    ok = api.Context(api.default_config(downsample_size=0.02))   # 5 m / 2 cm = 251 cells: accepted
+    ok.close()
+    mp = np.zeros((10, 4), np.float32)
+    with pytest.raises(api.FflinsError):
+        ctx.knn5(mp, mp, max_dist=400.0)
+
+
+# ------------------------------------------------------------------------------------------------ unstaged flips
+@pytest.mark.parametrize("name,frames_per_key", [("at128", 5), ("ouster64", 5)])
+def test_end_to_end_flip_counts(oracle, name, frames_per_key):
+    """Whole call sequence with NO staging (raw frames into both pipelines) over 25 frames: undistortion is allowed
+    1 ulp of fp32 difference, which may flip a voxel assignment or a validity test now and then. Reports and bounds
+    the discrete flips and the drift of the normal equations."""
+    from fflins import api, synth
+    from fflins.pipeline import Session
+    from oracle.cpu_pipeline import CpuSession
+    seq = synth.Sequence(name)
+    c = api.Context(api.default_config(point_filter_num=seq.filter_num))
+    gs = Session(c, seq, frames_per_key=frames_per_key, n_eval=(1, 1))
+    cs = CpuSession(seq, threads=8, frames_per_key=frames_per_key, n_eval=(1, 1), knn_mode=1)
+    flips_q = 0
+    for i in range(25):
+        fr = seq.frame(i)
+        fid, info = gs.process_frame(fr)
+        f = cs.process_frame(fr)
+        flips_q += abs(info.n_down - len(f["down"]))
+        gs.after_frame(fid, fr)
+        cs.after_frame(f)
+    ids = c.keyframe_ids()
+    assert len(ids) == len(cs.keys) == 25 // frames_per_key
+    flips_type = flips_idx = feats = 0
+    for i, (r, ck) in enumerate(zip(ids[:-1], cs.keys[:-1])):
+        g = c.features(r)
+        assert c.frame_info(r).n_map == len(ck["map"]) or abs(c.frame_info(r).n_map - len(ck["map"])) <= 2
+        if len(g["type"]) == len(ck["feat"]["type"]):
+            flips_type += int(np.sum(g["type"] != ck["feat"]["type"]))
+            flips_idx += int(np.sum(np.any(g["nn_idx"] != ck["feat"]["nn_idx"], axis=1)))
+            feats += len(g["type"])
+        Hg, Ho = gs.last["eval"]["H"][i], cs.last["eval"][i][2]
+        assert block_rel(Hg, Ho) < 1e-3, "end-to-end H drift"
+    print(f"{name}: unstaged flips over 25 frames: voxel-count {flips_q}, feature-type {flips_type}, "
+          f"kNN 5-tuple {flips_idx} of {feats} (ref, query) pairs")
+    assert flips_q <= 3 and flips_type <= max(5, feats // 500) and flips_idx <= max(10, feats // 200)
+    c.close()

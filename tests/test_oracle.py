@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from util import bits_equal, block_rel
+from util import bits_equal, block_rel, rand_pose, random_scene_cloud
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -288,3 +288,48 @@ def test_frame_golden(oracle):
     assert bits_equal(down, g["down"]) and bits_equal(keys, g["keys"])
     assert bits_equal(oracle.project(R, t, down), g["world"])
     assert np.abs(und[:, :3] - g["xyzi"][:, :3]).max() > 1e-3, "the fixture must carry real motion distortion"
+
+
+# ---------------------------------------------------------------- CPU-baseline forms (bench.py's reference arm)
+def test_window_forms_match_per_ref_calls(oracle):
+    """orc_associate_window / orc_window_eval / orc_window_chi2 (kd-tree built once per keyframe, all pairs per call,
+    chunked reduction as marginalization_info.cc:133-179) give what the per-ref oracle calls give."""
+    rng = np.random.default_rng(3)
+    q, n = 700, 3
+    maps = [random_scene_cloud(rng, 6000 + 500 * i, 12.0) for i in range(n)]
+    poses = [rand_pose(rng, 0.5) for _ in range(n)]
+    lidar = random_scene_cloud(rng, q, 10.0)
+    world = lidar.copy()
+    trees = [oracle.MapTree(m) for m in maps]
+    aw = oracle.associate_window(trees, [p[0] for p in poses], [p[1] for p in poses], world, lidar, threads=4)
+    for i in range(n):
+        o = oracle.associate(poses[i][0], poses[i][1], world, lidar, maps[i], knn_mode=0)
+        assert np.array_equal(aw["nn_idx"][i], o["nn_idx"]) and np.array_equal(aw["type"][i], o["type"])
+        assert aw["normal"][i].tobytes() == o["normal"].tobytes() and aw["d"][i].tobytes() == o["d"].tobytes()
+        assert aw["num_features"][i] == o["num_features"] and aw["num_covered"][i] == o["num_covered"]
+    assert aw["num_features"].sum() > 50
+
+    def p7():
+        qq = rng.normal(size=4)
+        return np.concatenate([rng.uniform(-1, 1, 3), qq / np.linalg.norm(qq)])
+    pose_refs = np.stack([p7() for _ in range(n)])
+    pose_cur, ext, td = p7(), np.array([0.01, 0, 0.02, 0, 0, 0, 1.0]), 0.004
+    motions = rng.normal(0, 0.3, (n, 14))
+    motions[:, 6] = motions[:, 13] = 0.001
+    pts = np.ascontiguousarray(lidar[:, :3])
+    valid = np.ascontiguousarray((aw["type"] == 0).astype(np.uint8))
+    H, b, cost = oracle.window_eval(pts, aw["normal"], aw["d"], 0.1, valid, motions, pose_refs, pose_cur, ext, td, flags=1,
+                                    threads=4)
+    outlier = np.zeros((n, q), np.uint8)
+    cnt = oracle.window_chi2(pts, aw["normal"], aw["d"], 0.1, valid, motions, pose_refs, pose_cur, ext, td, outlier,
+                             threshold=3.841, threads=4)
+    for i in range(n):
+        _, _, Ho, bo, co = oracle.factor_batch(pts, aw["normal"][i], aw["d"][i], np.full(q, 0.1), valid[i], motions[i],
+                                               pose_refs[i], pose_cur, ext, td, flags=1)
+        assert np.abs(H[i] - Ho).max() <= 1e-12 * np.abs(Ho).max() and np.abs(b[i] - bo).max() <= 1e-12 * np.abs(bo).max()
+        assert np.abs(cost[i] - co).max() <= 1e-12 * np.abs(co).max()
+        mask, c = oracle.chi2(pts, aw["normal"][i], aw["d"][i], np.full(q, 0.1), valid[i], motions[i], pose_refs[i],
+                              pose_cur, ext, td, 3.841)
+        assert np.array_equal(mask, outlier[i]) and c == cnt[i]
+    for t in trees:
+        t.close()
