@@ -295,8 +295,12 @@ def run_ours(args, rank, world, local_rank):
     e2e_dev_ms, e2e_wall_ms, _, e2e_rep_ms = timed("host", args.steps, repeats)
     # round trip of one solver-facing evaluation as the host sees it (wall clock around the C-ABI call)
     rt_us = None
-    if "eval_prep" in sess.last:
-        prep, out_buf, td_ = sess.last["eval_prep"]
+    ids_now = ctx.keyframe_ids()
+    if len(ids_now) >= 2 and "eval_prep" in sess.last:
+        td_ = sess.last["eval_prep"][2]
+        refs_now = ids_now[:-1]   # (the oldest keyframe of the last association has left the window)
+        prep, out_buf = api.Context.prepare_window(refs_now, np.array([sess.key_pose7[r] for r in refs_now]),
+                                                   sess.key_pose7[ids_now[-1]], sess.ext7)
         for _ in range(20):
             ctx.window_eval_prepared(prep, td_, sess.flags, out_buf)
         t0 = time.perf_counter()

@@ -1085,7 +1085,7 @@ void unpack_red(const double *red, double *H, double *b, double *cost, int32_t *
 
 int fill_factor_pairs(fflins_ctx *ctx, FactorParams &P, int n_pairs, const uint64_t *ref_ids, const double *pose_refs,
                       Frame *cur, const double *pose_cur, const double *ext, double td, uint32_t flags) {
-    REQUIRE(n_pairs >= 0 && n_pairs <= kMaxRefs, "too many pairs");
+    REQUIRE(n_pairs >= 0 && n_pairs <= kMaxPairs, "too many pairs (a window holds at most 15 reference keyframes)");
     {
         int rcp = flush_frames(ctx);
         if (rcp) return rcp;
@@ -2080,7 +2080,7 @@ int fflins_factor_eval_batch(fflins_ctx *ctx, int32_t n, const float *point, con
     P.pair[0].std    = d_std;
     {
         int64_t nl = 0;
-        int rcl    = launch_factor_eval(ctx->frt, s, P, d_p, 0, r ? d_r : nullptr, J ? d_J : nullptr, nullptr, nullptr, nullptr, 0, false, &nl);
+        int rcl    = launch_factor_eval(ctx->frt, s, P, d_p, 0, r ? d_r : nullptr, J ? d_J : nullptr, nullptr, false, nullptr, false, nullptr, &nl);
         ctx->launches += nl;
         if (rcl < 0) {
             ctx->pool.release(d);
@@ -2129,7 +2129,7 @@ int fflins_factor_eval(fflins_ctx *ctx, uint64_t ref_id, uint64_t cur_id, const 
         ProfScope ps(ctx->prof(), "factor_eval", s);
         int64_t nl = 0;
         int rcl    = launch_factor_eval(ctx->frt, s, P, (const float *) cur->c[FFLINS_CLOUD_LIDAR].d, 1, r ? d_r : nullptr,
-                                        J ? d_J : nullptr, valid ? d_valid : nullptr, ctx->d_red, nullptr, 0, false, &nl);
+                                        J ? d_J : nullptr, valid ? d_valid : nullptr, true, ctx->d_red, false, nullptr, &nl);
         ctx->launches += nl;
         if (rcl < 0) {
             ctx->pool.release(d);
@@ -2169,9 +2169,12 @@ int fflins_window_eval(fflins_ctx *ctx, int32_t n_pairs, const uint64_t *ref_ids
         return FFLINS_OK;
     }
     cudaStream_t s = ctx->stream;
-    unsigned char *h = pin(ctx, (size_t) n_pairs * kRedSize * 8);
-    if (!h) return fail(ctx, FFLINS_E_NOMEM, "pinned allocation failed");
     static const bool no_poll = getenv("FFLINS_NO_POLL") != nullptr;
+    FactorResults res{};
+    res.H     = H;
+    res.b     = b;
+    res.cost  = cost;
+    res.n_res = n_res;
     int how;
     {
         // the reduced blocks are stored by the kernel straight into pinned host memory (zero-copy): no device-to-host
@@ -2179,19 +2182,20 @@ int fflins_window_eval(fflins_ctx *ctx, int32_t n_pairs, const uint64_t *ref_ids
         // launch at all); the launched kernel is the cold path and the one the per-stage profiler times.
         ProfScope ps(ctx->prof(), "factor_eval", s);
         int64_t nl = 0;
-        how = launch_factor_eval(ctx->frt, s, P, (const float *) cur->c[FFLINS_CLOUD_LIDAR].d, 1, nullptr, nullptr, nullptr, (double *) h,
-                                 ctx->h_signal, ++ctx->signal_seq, ctx->eval_inputs_settled && !ctx->prof_on && !no_poll, &nl);
+        how = launch_factor_eval(ctx->frt, s, P, (const float *) cur->c[FFLINS_CLOUD_LIDAR].d, 1, nullptr, nullptr, nullptr, true,
+                                 nullptr, ctx->eval_inputs_settled && !ctx->prof_on && !no_poll, &res, &nl);
         ctx->launches += nl;
     }
     if (how < 0) return fail(ctx, FFLINS_E_CUDA, std::string("factor evaluation: ") + cudaGetErrorString((cudaError_t) -how));
     if (how == 1) {
         if (ctx->prof_on || no_poll) CK(cudaStreamSynchronize(s));   // the profiler's closing event needs the stream drained
-        else CK(wait_signal(ctx->h_signal, n_pairs, ctx->signal_seq, s));
+        else CK(wait_signal(res.signal, n_pairs, res.seq, s));
         ctx->eval_inputs_settled = true; // the compute stream has drained up to here
     }
-    const double *red = (const double *) h;
+    if (res.unpacked) return FFLINS_OK;   // the resident path has already filed its result units under H / b / cost / n_res
+    const double *red = res.red;
     // the lines were just written by the device: get all the misses in flight before the dependent reads
-    for (size_t o = 0; o < (size_t) n_pairs * kRedSize * 8; o += 64) __builtin_prefetch(h + o, 0, 0);
+    for (size_t o = 0; o < (size_t) n_pairs * kRedSize * 8; o += 64) __builtin_prefetch((const char *) red + o, 0, 0);
     for (int i = 0; i < n_pairs; i++)
         unpack_red(red + (size_t) i * kRedSize, H ? H + 361 * i : nullptr, b ? b + 19 * i : nullptr,
                    cost ? cost + 2 * i : nullptr, n_res ? n_res + i : nullptr);
@@ -2213,26 +2217,25 @@ int fflins_window_chi2(fflins_ctx *ctx, int32_t n_pairs, const uint64_t *ref_ids
         return FFLINS_OK;
     }
     cudaStream_t s = ctx->stream;
-    // counts and completion flag come back through pinned memory (the last CTA publishes them): one launch, no
-    // memset, no copy, no stream synchronisation
-    int *h_counts = (int *) (ctx->h_signal + kMaxRefs + 8);
-    unsigned long long *flags = ctx->h_signal + 3 * kMaxRefs;
+    // counts and completion flags come back through pinned memory (the last CTA of each pair publishes them): no memset,
+    // no copy, no stream synchronisation — and normally no launch either (resident kernel)
     static const bool no_poll = getenv("FFLINS_NO_POLL") != nullptr;
+    FactorResults res{};
     int how;
     {
         ProfScope ps(ctx->prof(), "chi2", s);
         int64_t nl = 0;
-        how = launch_chi2(ctx->frt, s, P, (const float *) cur->c[FFLINS_CLOUD_LIDAR].d, 1, threshold, h_counts, flags, ++ctx->signal_seq,
-                          ctx->eval_inputs_settled && !ctx->prof_on && !no_poll, &nl);
+        how = launch_chi2(ctx->frt, s, P, (const float *) cur->c[FFLINS_CLOUD_LIDAR].d, 1, threshold,
+                          ctx->eval_inputs_settled && !ctx->prof_on && !no_poll, &res, &nl);
         ctx->launches += nl;
     }
     if (how < 0) return fail(ctx, FFLINS_E_CUDA, std::string("chi2 cull: ") + cudaGetErrorString((cudaError_t) -how));
     if (how == 1) {
         if (ctx->prof_on || no_poll) CK(cudaStreamSynchronize(s));
-        else CK(wait_signal(flags, n_pairs, ctx->signal_seq, s));
+        else CK(wait_signal(res.signal, n_pairs, res.seq, s));
         ctx->eval_inputs_settled = true;
     }
-    if (n_outliers) std::memcpy(n_outliers, h_counts, n_pairs * sizeof(int));
+    if (n_outliers) std::memcpy(n_outliers, res.counts, n_pairs * sizeof(int));
     return FFLINS_OK;
 }
 

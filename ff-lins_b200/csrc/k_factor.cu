@@ -10,23 +10,27 @@
 // All arithmetic is fp64 (the reference's normal equations are double). B200 design:
 //  * everything that depends only on the (ref, cur) pair — three rotation matrices, the first-order time-delay
 //    motion terms, the products A = Rbl^T Rt0^T, C = A Rt1, E = C Rbl — is computed once per CTA into shared
-//    memory (three threads, two barriers); a thread then needs ~250 fp64 operations per residual instead of the
-//    ~1000 of the per-residual formulation;
+//    memory; a thread then needs ~250 fp64 operations per residual instead of the ~1000 of the per-residual
+//    formulation;
 //  * the reduction is a SYRK out of shared memory on the FP64 tensor pipe (mma.sync.m8n8k4.f64 — tcgen05 has no
-//    fp64 kind); warp partials are summed in warp order, the (up to 8) CTAs of a pair leave their 212 partial sums
-//    in L2 and the last one to arrive (ticket) adds them in rank order: a fixed summation order, run-to-run
-//    deterministic, no cluster barrier on the critical path;
-//  * a solver iterates on these blocks 16 times per keyframe and each iteration used to be one kernel launch whose
-//    launch -> host-visible latency (~20 us) dwarfed the ~4 us of work. The RESIDENT kernel below removes the launch:
-//    one dispatcher CTA polls a pinned host mailbox (16-byte {word, sequence tag} slots, so a message is complete the
-//    moment all its tags match — one PCIe round trip), republishes the message in device memory and 8 x 16 worker CTAs
-//    pick it up from L2, evaluate and store the blocks straight into pinned host memory behind a system-scope
-//    release. The kernel retires by itself after an idle period (default 1 ms), every wait in it is bounded, and
-//    the launched kernel (same worker code, message by value) remains as the cold path and for profiling.
+//    fp64 kind); warp partials are summed in warp order and the (up to 8) CTAs of a pair in rank order: a fixed
+//    summation order, run-to-run deterministic;
+//  * a solver iterates on these blocks 16 times per keyframe, and each iteration used to be one kernel launch whose
+//    launch -> host-visible latency (~20 us) dwarfed the ~4 us of work. The RESIDENT kernel removes the launch and
+//    every fence from that round trip. Measured on this box (tools/pcie_probe.cu): a host store is seen by a polling
+//    warp and answered with a plain posted store in 2.2 us; 10 CTAs polling DISTINCT host lines: 2.7 us; the same
+//    with all CTAs polling the SAME lines: 25 us (sysmem reads of one line serialise); a system-scope release costs a
+//    further ~1.5-2.5 us. Hence: one mailbox region per pair, polled by one warp of the pair's rank-0 CTA; every
+//    hand-off (host -> rank 0, rank 0 -> ranks 1..7 through L2, partial sums back, results to the host) is made of
+//    16-byte {value, sequence tag} slots written with one vector store each — a slot is valid the moment its tag
+//    matches, so no fence, flag, ticket or barrier sits between producer and consumer. The kernel retires by itself
+//    after an idle period (default 1 ms), every wait in it is bounded, and the launched kernel (same evaluation code,
+//    message by value, ticket reduction) remains as the cold path and for profiling.
 #include "math_factor.cuh"
 
 #include <algorithm>
 #include <chrono>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -39,25 +43,25 @@ constexpr int kCols      = 24;                 // 19 J | r | rho0 | valid | 1 | 
 constexpr int kColStride = kFactorBlock + 4;   // column-major tile, +4 doubles: conflict-free fragment loads
 constexpr int kWarps     = kFactorBlock / 32;
 constexpr int kSetupRing = 8;
-constexpr unsigned long long kQuitSeq = ~0ull;
 
 // message words (kernels.h)
-enum { W_CMD = 0, W_NP = 1, W_TD = 2, W_THR = 3, W_SEQ = 4, W_OUT = 5, W_CNT = 6, W_SIG = 7, W_CUR = 8, W_EXT = 15, W_REF = kMsgHead };
-static_assert(kMsgHead == 22, "message layout");
+enum { W_CMD = 0, W_NP = 1, W_TD = 2, W_THR = 3, W_SEQ = 4, W_CUR = 5, W_EXT = 12, W_REF = kMsgHead };
+static_assert(kMsgHead == 19, "message layout");
+// FactorSetup as 64-bit words: the common part, then one block per pair
+constexpr int kSetupCommon = 11, kSetupPair = 12, kSetupLocal = kSetupCommon + kSetupPair;
+static_assert(sizeof(FactorSetupPair) == 8 * kSetupPair && sizeof(FactorSetup) == 8 * (kSetupCommon + kSetupPair * kMaxRefs) &&
+                  offsetof(FactorSetup, pair) == 8 * kSetupCommon,
+              "setup layout");
+// what ONE pair needs of a message: the 19 header words and its own reference pose
+constexpr int kPairMsg   = kMsgHead + 7;       // 26 words
+constexpr int kPairSlots = 32;                 // host mailbox region per pair: one warp, one 16-byte load per lane
+constexpr int kRowSlots  = 64;                 // device hand-off per pair: 26 message words, 23 setup words from slot 32
 
 // D (8x8, fp64) += A (8x4, row) * B (4x8, col) on the FP64 tensor pipe.
 __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c[0]), "+d"(c[1])
                  : "d"(a), "d"(b));
-}
-__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_gpu(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -67,156 +71,183 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+// 16-byte {value, tag} slots: one vector access each (never torn: a slot lies inside one 32-byte sector)
+__device__ __forceinline__ ulonglong2 ld_slot(const ulonglong2 *p) {
+    ulonglong2 v;
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_slot(ulonglong2 *p, unsigned long long w, unsigned long long tag) {
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(w), "l"(tag) : "memory");
+}
+// device-to-device hand-offs only need GPU scope (L2 is the point of coherence)
+__device__ __forceinline__ ulonglong2 ld_slot_gpu(const ulonglong2 *p) {
+    ulonglong2 v;
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_slot_gpu(ulonglong2 *p, unsigned long long w, unsigned long long tag) {
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(w), "l"(tag) : "memory");
+}
+// 32-byte {3 values, tag} units for the bulk hand-offs (partial sums through L2, results to the host): one 256-bit
+// access each (sm_100: LDG/STG.256), one sector, so a unit is valid the moment its tag matches
+struct alignas(32) Unit {
+    unsigned long long w[3];
+    unsigned long long tag;
+};
+constexpr int kRedUnits = (kRedSize + 2) / 3;   // 71
+__device__ __forceinline__ Unit ld_unit(const Unit *p) {
+    Unit u;
+    asm volatile("ld.volatile.global.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(u.w[0]), "=l"(u.w[1]), "=l"(u.w[2]), "=l"(u.tag) : "l"(p) : "memory");
+    return u;
+}
+__device__ __forceinline__ void st_unit(Unit *p, unsigned long long a, unsigned long long b, unsigned long long c, unsigned long long tag) {
+    asm volatile("st.volatile.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(tag) : "memory");
+}
+__device__ __forceinline__ Unit ld_unit_gpu(const Unit *p) {
+    Unit u;
+    asm volatile("ld.relaxed.gpu.global.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(u.w[0]), "=l"(u.w[1]), "=l"(u.w[2]), "=l"(u.tag) : "l"(p) : "memory");
+    return u;
+}
+__device__ __forceinline__ void st_unit_gpu(Unit *p, unsigned long long a, unsigned long long b, unsigned long long c, unsigned long long tag) {
+    asm volatile("st.relaxed.gpu.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(tag) : "memory");
+}
+__device__ __forceinline__ double w2d(unsigned long long w) { return __longlong_as_double((long long) w); }
+__device__ __forceinline__ unsigned long long d2w_dev(double d) { return (unsigned long long) __double_as_longlong(d); }
 
-// The CTA's view of one evaluation: header, pair constants and the pair's feature arrays, in shared memory.
+struct SetupLocal {   // the words of FactorSetup one CTA needs: the common part and its own pair
+    const float *points;
+    int stride4, q;
+    double v1[3], w1[3], td1, sigma, huber;
+    FactorSetupPair sp;
+};
+static_assert(sizeof(SetupLocal) == 8 * kSetupLocal, "setup layout");
+
+// The CTA's view of one evaluation, in shared memory: message words [0, 19) header + [19, 26) own reference pose.
 struct PairShared {
     CurConst cc;
     RefConst rc;
-    FactorSetupPair sp;
-    const float *points;
-    double *out_red;
-    int *host_counts;
-    unsigned long long *signal;
+    SetupLocal su;
+    unsigned long long msg[kPairSlots];
     unsigned long long seq;
-    double td, thr, sigma, huber;
+    double td, thr;
     unsigned cmd, flags;
-    int n_pairs, q, stride4, last, count;
+    int n_pairs, last, count;
 };
 
 struct WorkBuffers {
-    double *partials;            // [kMaxRefs][kFactorRanks][kRedSize]
+    double *partials;            // launched kernel: [kMaxRefs][kFactorRanks][kRedSize]
     int *tickets;                // [kMaxRefs], zero on entry / exit
     int *counts;                 // [kMaxRefs], zero on entry / exit
-    unsigned long long *acks;    // resident kernel only: one increment per CTA per message, once the message is consumed
+    double *out_red;             // [n_pairs][kRedSize]: pinned host (with signal) or device memory; nullptr = no reduction
+    int *host_counts;            // pinned, chi2
+    unsigned long long *signal;  // pinned, [pair] = seq released behind the pair's results (nullptr with a device out_red)
 };
 
 constexpr int kTileDoubles   = kCols * kColStride + kRedSize + 4;
 constexpr size_t kFactorSmem = (size_t) kTileDoubles * sizeof(double) + sizeof(PairShared);
 
-__device__ __forceinline__ double w2d(unsigned long long w) { return __longlong_as_double((long long) w); }
-
-// One evaluation (or chi-square pass) of pair `pair` by CTA `rank` of `ranks`. msg: kMsgWords words (kernel parameter
-// space or global memory); setup: device memory.
-__device__ void factor_work(const unsigned long long *__restrict__ msg, const FactorSetup *__restrict__ setup, int pair,
-                            int rank, int ranks, double *smem, const WorkBuffers &wb, double *__restrict__ r_out,
-                            double *__restrict__ J_out, uint8_t *__restrict__ valid_out) {
-    double *cols   = smem;                          // [kCols][kColStride]
-    double *s_red  = smem + kCols * kColStride;     // [kRedSize]
-    PairShared &sh = *reinterpret_cast<PairShared *>(smem + kTileDoubles);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-    // ---- header + pair constants (lidar_factor.cc:43-69): three threads in parallel, then the dependent products
+// ---- phase A: header + pair constants (lidar_factor.cc:43-69) out of sh.msg / sh.su. Every thread calls it.
+__device__ __forceinline__ void pair_prepare(PairShared &sh) {
+    const int tid = threadIdx.x;
     if (tid == 0) {
-        const unsigned long long w0 = msg[W_CMD], w1 = msg[W_NP];
+        const unsigned long long w0 = sh.msg[W_CMD], w1 = sh.msg[W_NP];
         sh.cmd     = (unsigned) w0;
         sh.flags   = (unsigned) (w0 >> 32);
         sh.n_pairs = (int) (unsigned) w1;
-        sh.td      = w2d(msg[W_TD]);
-        sh.thr     = w2d(msg[W_THR]);
-        sh.seq     = msg[W_SEQ];
-        sh.out_red     = reinterpret_cast<double *>(msg[W_OUT]);
-        sh.host_counts = reinterpret_cast<int *>(msg[W_CNT]);
-        sh.signal      = reinterpret_cast<unsigned long long *>(msg[W_SIG]);
-        sh.count       = 0;
+        sh.td      = w2d(sh.msg[W_TD]);
+        sh.thr     = w2d(sh.msg[W_THR]);
+        sh.seq     = sh.msg[W_SEQ];
+        sh.count   = 0;
         double pc[7], ex[7];
 #pragma unroll
         for (int i = 0; i < 7; i++) {
-            pc[i] = w2d(msg[W_CUR + i]);
-            ex[i] = w2d(msg[W_EXT + i]);
+            pc[i] = w2d(sh.msg[W_CUR + i]);
+            ex[i] = w2d(sh.msg[W_EXT + i]);
         }
-        make_cur_const_raw(pc, ex, sh.td, setup->v1, setup->w1, setup->td1, sh.cc);
+        make_cur_const_raw(pc, ex, sh.td, sh.su.v1, sh.su.w1, sh.su.td1, sh.cc);
     } else if (tid == 32) {
-        sh.sp = setup->pair[pair];
         double pr[7];
 #pragma unroll
-        for (int i = 0; i < 7; i++) pr[i] = w2d(msg[W_REF + 7 * pair + i]);
-        make_ref_const_a(pr, sh.sp.v0, sh.sp.w0, sh.sp.td0, w2d(msg[W_TD]), setup->v1, sh.rc);
-    } else if (tid == 64) {
-        sh.points  = setup->points;
-        sh.stride4 = setup->stride4;
-        sh.q       = setup->q;
-        sh.sigma   = setup->sigma;
-        sh.huber   = setup->huber_delta;
+        for (int i = 0; i < 7; i++) pr[i] = w2d(sh.msg[W_REF + i]);
+        make_ref_const_a(pr, sh.su.sp.v0, sh.su.sp.w0, sh.su.sp.td0, w2d(sh.msg[W_TD]), sh.su.v1, sh.rc);
     }
     __syncthreads();
-    if (tid == 0) {
-        if (wb.acks) atomicAdd(wb.acks, 1ull);       // message and setup are consumed: the dispatcher may move on
-        make_ref_const_b(sh.cc, sh.rc);
-    }
-    if (pair >= sh.n_pairs) return;
-    const int q     = sh.q;
-    const int tiles = (q + kFactorBlock - 1) / kFactorBlock;
-    const int C     = tiles < ranks ? (tiles > 0 ? tiles : 1) : ranks;  // CTAs of this pair that hold work
-    if (rank >= C) return;
+    if (tid == 0) make_ref_const_b(sh.cc, sh.rc);
     __syncthreads();
-    const FactorSetupPair &pr = sh.sp;
-    const float *__restrict__ points = sh.points;
-    const int pstride = sh.stride4 ? 4 : 3;
+}
 
-    if (sh.cmd == kCmdChi2) {
-        // ---- K7 (optimizer.cc:515-548): residual only, r^2 > threshold -> outlier
-        int mine = 0;
-        for (int tile = rank; tile < tiles; tile += C) {
-            const int k = tile * kFactorBlock + tid;
-            bool valid  = k < q;
-            if (valid && pr.type) valid = pr.type[k] == 0 && pr.outlier[k] == 0;
-            if (valid) {
-                const float *pp = points + (size_t) k * pstride;
-                V3 p = v3((double) pp[0], (double) pp[1], (double) pp[2]);
-                V3 n = v3(pr.normal[3 * k], pr.normal[3 * k + 1], pr.normal[3 * k + 2]);
-                double s = 1.0 / (pr.std ? pr.std[k] : sh.sigma);
-                double r = eval_residual<false>(sh.cc, sh.rc, p, n, pr.d[k], s, nullptr);
-                if (r * r > sh.thr) {       // optimizer.cc:536-541
-                    if (pr.outlier) pr.outlier[k] = 1;
-                    mine++;
-                }
-            }
-        }
-        if (mine) atomicAdd(&sh.count, mine);
-        __syncthreads();
-        if (tid == 0) {
-            if (sh.count) atomicAdd(wb.counts + pair, sh.count);
-            __threadfence();
-            const int t = atomicAdd(wb.tickets + pair, 1);
-            if (t == C - 1) {
-                __threadfence();
-                sh.host_counts[pair] = atomicExch(wb.counts + pair, 0);
-                wb.tickets[pair]     = 0;
-                st_release_sys(sh.signal + pair, sh.seq);
-            }
-        }
-        return;
-    }
-
-    // ---- K6: residual + Jacobians, SYRK on the FP64 tensor pipe. The tile's rows v = [J(19) | r | rho0 | valid | 1 | 0]
-    // are stored column-major in shared memory, G = V^T V (24 x 24) is split into 3 x 3 blocks of 8 x 8 and warp w
-    // accumulates the 6 upper blocks over its 32 rows with mma.sync.m8n8k4.f64: the A fragment of column group g (lane l
-    // holds V[k0 + l%4][8g + l/4]) is also the B fragment of the same group, so one k-step is 3 shared-memory loads and 6
-    // DMMAs per lane. sum rho and the residual count come out of the same product as G[20][22] and G[21][22] (column 22
-    // is all ones).
-    double acc[6][2];                              // blocks (0,0) (0,1) (0,2) (1,1) (1,2) (2,2)
-#pragma unroll
-    for (int a = 0; a < 6; a++) acc[a][0] = acc[a][1] = 0.0;
-    const bool reduce    = sh.out_red != nullptr;
-    const unsigned flags = sh.flags;
+// ---- K7 (optimizer.cc:515-548): residual only, r^2 > threshold -> outlier. Returns the CTA's count (in every thread).
+__device__ __forceinline__ int chi2_tiles(PairShared &sh, int rank, int C, int tiles) {
+    const int tid = threadIdx.x, q = sh.su.q;
+    const FactorSetupPair &pr = sh.su.sp;
+    const float *__restrict__ points = sh.su.points;
+    const int pstride = sh.su.stride4 ? 4 : 3;
+    int mine = 0;
     for (int tile = rank; tile < tiles; tile += C) {
         const int k = tile * kFactorBlock + tid;
         bool valid  = k < q;
-        if (valid && pr.type) valid = (pr.type[k] == 0) && (pr.outlier[k] == 0); // optimizer.cc:468
-        double J[19], r = 0.0, rho0 = 0.0;
-#pragma unroll
-        for (int i = 0; i < 19; i++) J[i] = 0.0;
+        if (valid && pr.type) valid = pr.type[k] == 0 && pr.outlier[k] == 0;
         if (valid) {
             const float *pp = points + (size_t) k * pstride;
             V3 p = v3((double) pp[0], (double) pp[1], (double) pp[2]);
             V3 n = v3(pr.normal[3 * k], pr.normal[3 * k + 1], pr.normal[3 * k + 2]);
-            double s = 1.0 / (pr.std ? pr.std[k] : sh.sigma); // sqrt_info (lidar_factor.cc:38)
-            r = eval_residual<true>(sh.cc, sh.rc, p, n, pr.d[k], s, J);
+            double s = 1.0 / (pr.std ? pr.std[k] : sh.su.sigma);
+            double r = eval_residual<false>(sh.cc, sh.rc, p, n, pr.d[k], s, nullptr);
+            if (r * r > sh.thr) {       // optimizer.cc:536-541
+                if (pr.outlier) pr.outlier[k] = 1;
+                mine++;
+            }
+        }
+    }
+    if (mine) atomicAdd(&sh.count, mine);
+    __syncthreads();
+    return sh.count;
+}
+
+// ---- K6: residual + Jacobians of the CTA's tiles, SYRK on the FP64 tensor pipe, warp partials summed in warp order
+// into s_red[212] = [190 upper-triangle H | 19 b | sum rho | sum r'^2 | count]. The tile's rows
+// v = [J(19) | r | rho0 | valid | 1 | 0] are stored column-major in shared memory, G = V^T V (24 x 24) is split into 3 x 3
+// blocks of 8 x 8 and warp w accumulates the 6 upper blocks over its 32 rows with mma.sync.m8n8k4.f64: the A fragment of
+// column group g (lane l holds V[k0 + l%4][8g + l/4]) is also the B fragment of the same group, so one k-step is 3
+// shared-memory loads and 6 DMMAs per lane. sum rho and the residual count come out of the same product as G[20][22] and
+// G[21][22] (column 22 is all ones).
+__device__ __forceinline__ void eval_tiles(PairShared &sh, double *smem, int pair, int rank, int C, int tiles, bool reduce,
+                                           double *__restrict__ r_out, double *__restrict__ J_out, uint8_t *__restrict__ valid_out) {
+    double *cols  = smem;                          // [kCols][kColStride]
+    double *s_red = smem + kCols * kColStride;     // [kRedSize]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q = sh.su.q;
+    const FactorSetupPair &pr = sh.su.sp;
+    const float *__restrict__ points = sh.su.points;
+    const int pstride = sh.su.stride4 ? 4 : 3;
+    const double sigma = sh.su.sigma;
+    double acc[6][2];                              // blocks (0,0) (0,1) (0,2) (1,1) (1,2) (2,2)
+#pragma unroll
+    for (int a = 0; a < 6; a++) acc[a][0] = acc[a][1] = 0.0;
+    const unsigned flags = sh.flags;
+    for (int tile = rank; tile < tiles; tile += C) {
+        const int k  = tile * kFactorBlock + tid;
+        const int kk = k < q ? k : q - 1;
+        // every input of the residual is requested before the first one is looked at: one L2 round trip, not three
+        const int ty = pr.type ? (int) pr.type[kk] : 0, ol = pr.type ? (int) pr.outlier[kk] : 0;
+        const float *pp = points + (size_t) kk * pstride;
+        const float px = pp[0], py = pp[1], pz = pp[2];
+        const double nx = pr.normal[3 * kk], ny = pr.normal[3 * kk + 1], nz = pr.normal[3 * kk + 2], dk = pr.d[kk];
+        const double sd = pr.std ? pr.std[kk] : sigma;
+        const bool valid = k < q && ty == 0 && ol == 0;                           // optimizer.cc:468
+        double J[19], r = 0.0, rho0 = 0.0;
+#pragma unroll
+        for (int i = 0; i < 19; i++) J[i] = 0.0;
+        if (valid) {
+            V3 p = v3((double) px, (double) py, (double) pz);
+            V3 n = v3(nx, ny, nz);
+            double s = 1.0 / sd;                              // sqrt_info (lidar_factor.cc:38)
+            r = eval_residual<true>(sh.cc, sh.rc, p, n, dk, s, J);
             if (flags & 2u) { J[0] = J[1] = J[2] = J[3] = J[4] = J[5] = 0.0; }
             if (flags & 4u) { J[6] = J[7] = J[8] = J[9] = J[10] = J[11] = 0.0; }
             if (flags & 8u) { J[12] = J[13] = J[14] = J[15] = J[16] = J[17] = 0.0; }
             if (flags & 16u) J[18] = 0.0;
-            if (flags & 1u) rho0 = huber_correct(sh.huber, r, J);
+            if (flags & 1u) rho0 = huber_correct(sh.su.huber, r, J);
             else rho0 = r * r;
         }
         if (k < q) {
@@ -271,7 +302,7 @@ __device__ void factor_work(const unsigned long long *__restrict__ msg, const Fa
     }
     __syncthreads();
     // thread e (and e + 128, e + 256 < 384) sums entry e = (block, row, col) over the warps in warp order and files it
-    // under its place in the 212-vector [190 upper-triangle H | 19 b | sum rho | sum r'^2 | count]
+    // under its place in the 212-vector
     for (int e0 = tid; e0 < 6 * 64; e0 += kFactorBlock) {
         double sum = 0.0;
 #pragma unroll
@@ -295,12 +326,56 @@ __device__ void factor_work(const unsigned long long *__restrict__ msg, const Fa
         if (e >= 0) s_red[e] = sign * sum;   // s_red lies behind the tile buffer, `part` stays intact
     }
     __syncthreads();
-    double *out = sh.out_red + (size_t) pair * kRedSize;
+}
+
+__device__ __forceinline__ int ctas_with_work(int tiles, int ranks) { return tiles < ranks ? (tiles > 0 ? tiles : 1) : ranks; }
+
+// ---- launched form: grid (kFactorRanks or fewer, n_pairs), message by value; cross-CTA reduction through L2 partial
+// sums and a ticket (the last CTA to arrive adds them in rank order), completion flag released at system scope.
+__global__ void __launch_bounds__(kFactorBlock)
+factor_kernel(const __grid_constant__ FactorMsg M, const FactorSetup *__restrict__ setup, WorkBuffers wb,
+              double *__restrict__ r_out, double *__restrict__ J_out, uint8_t *__restrict__ valid_out) {
+    extern __shared__ __align__(16) double smem[];
+    PairShared &sh = *reinterpret_cast<PairShared *>(smem + kTileDoubles);
+    double *s_red  = smem + kCols * kColStride;
+    const int tid = threadIdx.x, pair = blockIdx.y, rank = blockIdx.x;
+    if (tid < kPairMsg) sh.msg[tid] = tid < kMsgHead ? M.w[tid] : M.w[kMsgHead + 7 * pair + (tid - kMsgHead)];
+    {
+        const unsigned long long *sw = reinterpret_cast<const unsigned long long *>(setup);
+        unsigned long long *dst      = reinterpret_cast<unsigned long long *>(&sh.su);
+        if (tid >= 32 && tid < 32 + kSetupLocal) {
+            const int i = tid - 32;
+            dst[i]      = sw[i < kSetupCommon ? i : kSetupCommon + kSetupPair * pair + (i - kSetupCommon)];
+        }
+    }
+    __syncthreads();
+    pair_prepare(sh);
+    const int q = sh.su.q, tiles = (q + kFactorBlock - 1) / kFactorBlock, C = ctas_with_work(tiles, gridDim.x);
+    if (rank >= C) return;
+    if (sh.cmd == kCmdChi2) {
+        const int c = chi2_tiles(sh, rank, C, tiles);
+        if (tid == 0) {
+            if (c) atomicAdd(wb.counts + pair, c);
+            __threadfence();
+            const int t = atomicAdd(wb.tickets + pair, 1);
+            if (t == C - 1) {
+                __threadfence();
+                wb.host_counts[pair] = atomicExch(wb.counts + pair, 0);
+                wb.tickets[pair]     = 0;
+                st_release_sys(wb.signal + pair, sh.seq);
+            }
+        }
+        return;
+    }
+    const bool reduce = wb.out_red != nullptr;
+    eval_tiles(sh, smem, pair, rank, C, tiles, reduce, r_out, J_out, valid_out);
+    if (!reduce) return;
+    double *out = wb.out_red + (size_t) pair * kRedSize;
     if (C == 1) {
         for (int e = tid; e < kRedSize; e += kFactorBlock) out[e] = s_red[e];
     } else {
-        // cross-CTA reduction through L2: every CTA leaves its 212 sums, the last one to take a ticket adds them in
-        // rank order (threadfence-reduction pattern; fixed order = deterministic)
+        // every CTA leaves its 212 sums in L2, the last one to take a ticket adds them in rank order
+        // (threadfence-reduction pattern; fixed order = deterministic)
         double *mine = wb.partials + ((size_t) pair * kFactorRanks + rank) * kRedSize;
         for (int e = tid; e < kRedSize; e += kFactorBlock) mine[e] = s_red[e];
         __threadfence();
@@ -324,128 +399,233 @@ __device__ void factor_work(const unsigned long long *__restrict__ msg, const Fa
         }
         if (tid == 0) wb.tickets[pair] = 0;
     }
-    if (sh.signal) {
+    if (wb.signal) {
         // out_red is host memory: publish "pair done" behind the data so that the host can poll for it instead of
         // paying a stream synchronisation (the release at system scope orders the CTA's stores before the flag)
         __syncthreads();
-        if (tid == 0) st_release_sys(sh.signal + pair, sh.seq);
+        if (tid == 0) st_release_sys(wb.signal + pair, sh.seq);
     }
-}
-
-// Launched form: grid (kFactorRanks or fewer, n_pairs), message by value.
-__global__ void __launch_bounds__(kFactorBlock)
-factor_kernel(const __grid_constant__ FactorMsg M, const FactorSetup *__restrict__ setup, WorkBuffers wb,
-              double *__restrict__ r_out, double *__restrict__ J_out, uint8_t *__restrict__ valid_out) {
-    extern __shared__ __align__(16) double smem[];
-    factor_work(M.w, setup, blockIdx.y, blockIdx.x, gridDim.x, smem, wb, r_out, J_out, valid_out);
 }
 
 // ---- resident form ------------------------------------------------------------------------------------------------
+// Grid (kFactorRanks, rows): row p serves pair p. Tags are message sequence numbers (never 0).
+//   host mailbox   h_mail [rows][kPairSlots]            {word, tag}   host -> rank 0 of the row (PCIe reads by one warp)
+//   setup ring     h_setup[kSetupRing]                                 fetched by rank 0 when the generation changes
+//   device row     d_row  [rows][kRowSlots]             {word, tag}   rank 0 -> ranks 1..7 (message + setup, through L2)
+//   partial sums   d_part [rows][kFactorRanks][kRedUnits] {3 values, tag} ranks 1..7 -> rank 0
+//   results        h_res  [rows][kRedUnits]               {3 values, tag} rank 0 -> host (posted PCIe writes)
+//   h_exit [rows]  = launch id, written by rank 0 of a row when it retires
+constexpr unsigned kCmdRetire = 0xffffffffu;
 struct ResidentArgs {
-    const ulonglong2 *h_slots;          // pinned mailbox: kMsgWords x {word, tag}
-    const FactorSetup *h_setup;         // pinned ring [kSetupRing]
-    unsigned long long *h_state;        // pinned: [0] last sequence number dispatched, [1] launch id (written at exit)
-    FactorMsg *d_msg;
-    FactorSetup *d_setup;
-    unsigned long long *d_seq;          // dispatch counter (kQuitSeq = retire)
+    const ulonglong2 *h_mail;
+    const FactorSetup *h_setup;
+    unsigned long long *h_exit;
+    Unit *h_res;
+    ulonglong2 *d_row;
+    Unit *d_part;
     unsigned long long start_seq, launch_id, idle_ns;
-    WorkBuffers wb;
+    int rows;
+    long long *timeline;   // diagnostics (FFLINS_RES_TIMELINE=1): pinned, clock64 stamps of row 0 / rank 0
 };
-
-__device__ void resident_dispatch(const ResidentArgs &A, double *smem) {
-    unsigned long long *s_msg = reinterpret_cast<unsigned long long *>(smem);
-    __shared__ int s_flag;
-    const int tid = threadIdx.x;
-    unsigned long long expect = A.start_seq + 1, acks_expected = 0, cached_gen = ~0ull;
-    const unsigned long long n_workers = (unsigned long long) kFactorRanks * kMaxRefs;
-    unsigned long long t_last = globaltimer_ns();
-    while (true) {
-        // one PCIe round trip per poll: every thread fetches its own {word, tag} slots; the message is complete when
-        // all tags carry the expected sequence number (the host stores word before tag, 16-byte slots never tear)
-        bool ok = true;
-        for (int slot = tid; slot < kMsgWords; slot += kFactorBlock) {
-            unsigned long long w, t;
-            asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w), "=l"(t) : "l"(A.h_slots + slot) : "memory");
-            ok &= t == expect;
-            s_msg[slot] = w;
-        }
-        if (!__syncthreads_and(ok)) {
-            if (tid == 0) s_flag = globaltimer_ns() - t_last > A.idle_ns;
-            __syncthreads();
-            if (s_flag) break;
-            continue;
-        }
-        // the workers must be done reading the previous message (long since, normally)
-        if (tid == 0) {
-            int bad = 0;
-            const unsigned long long t0 = globaltimer_ns();
-            while (ld_acquire_gpu(A.wb.acks) < acks_expected)
-                if (globaltimer_ns() - t0 > 4 * A.idle_ns + 1000000ull) {
-                    bad = 1;
-                    break;
-                }
-            s_flag = bad;
-        }
-        __syncthreads();
-        if (s_flag) break;
-        const unsigned cmd           = (unsigned) s_msg[W_CMD];
-        const unsigned long long gen = s_msg[W_NP] >> 32;
-        if (cmd == kCmdQuit) {
-            expect++;   // (acknowledged as dispatched)
-            break;
-        }
-        if (gen != cached_gen) { // new keyframe: fetch the setup from the host ring (one more round trip, once per keyframe)
-            const unsigned long long *src = reinterpret_cast<const unsigned long long *>(A.h_setup + (gen % kSetupRing));
-            unsigned long long *dst       = reinterpret_cast<unsigned long long *>(A.d_setup);
-            for (int i = tid; i < (int) (sizeof(FactorSetup) / 8); i += kFactorBlock) {
-                unsigned long long v;
-                asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(src + i) : "memory");
-                dst[i] = v;
-            }
-            cached_gen = gen;
-        }
-        for (int i = tid; i < kMsgWords; i += kFactorBlock) A.d_msg->w[i] = s_msg[i];
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) st_release_gpu(A.d_seq, expect);
-        acks_expected += n_workers;
-        expect++;
-        t_last = globaltimer_ns();
-    }
-    // retire: tell the workers, then the host (which falls back to a launch for anything not dispatched)
-    if (tid == 0) {
-        st_release_gpu(A.d_seq, kQuitSeq);
-        A.h_state[0] = expect - 1;
-        __threadfence_system();
-        st_release_sys(A.h_state + 1, A.launch_id);
-    }
-}
 
 __global__ void __launch_bounds__(kFactorBlock) resident_kernel(const __grid_constant__ ResidentArgs A) {
     extern __shared__ __align__(16) double smem[];
-    if (blockIdx.y == kMaxRefs) {
-        if (blockIdx.x == 0) resident_dispatch(A, smem);
-        return;
-    }
-    __shared__ unsigned long long s_seq;
-    unsigned long long last = A.start_seq;
+    PairShared &sh = *reinterpret_cast<PairShared *>(smem + kTileDoubles);
+    double *s_red  = smem + kCols * kColStride;
+    __shared__ unsigned long long s_tag;       // tag of the message being served (0: retire)
+    __shared__ unsigned long long s_gen;       // setup generation held in sh.su (rank 0)
+    const int tid = threadIdx.x, pair = blockIdx.y, rank = blockIdx.x;
+    const ulonglong2 *mail = A.h_mail + (size_t) pair * kPairSlots;
+    ulonglong2 *row        = A.d_row + (size_t) pair * kRowSlots;
+    Unit *part             = A.d_part + (size_t) pair * kFactorRanks * kRedUnits;
+    Unit *res              = A.h_res + (size_t) pair * kRedUnits;
+    unsigned long long expect = A.start_seq + 1;
+    if (tid == 0) s_gen = ~0ull;
+    __syncthreads();
+    const bool stamp = A.timeline && pair == 0 && rank == 0 && tid == 0;
+    const bool stamp1 = A.timeline && pair == 0 && rank == 1 && tid == 0;   // a follower rank, for comparison
+    long long tl[4], t1[4];
+    unsigned long long g0 = 0, g1 = 0;
+    const unsigned long long hard_ns = 8 * A.idle_ns + 20000000ull;   // a peer is gone: never spin forever
     while (true) {
-        if (threadIdx.x == 0) {
-            const unsigned long long t0 = globaltimer_ns();
-            unsigned long long s;
-            while ((s = ld_acquire_gpu(A.d_seq)) == last) {
-                if (globaltimer_ns() - t0 > 8 * A.idle_ns + 20000000ull) { // the dispatcher is gone: never spin forever
-                    s = kQuitSeq;
-                    break;
+        // ---- pick up the next message -------------------------------------------------------------------------------
+        if (rank == 0) {
+            if (tid < 32) {
+                // one warp, one 16-byte load per lane and poll: the message is complete when the 26 tags agree
+                const unsigned long long t0 = globaltimer_ns();
+                unsigned long long tag = 0;
+                while (true) {
+                    const ulonglong2 v = ld_slot(mail + tid);
+                    const unsigned long long t = __shfl_sync(0xffffffffu, v.y, 0);
+                    if (__all_sync(0xffffffffu, t >= expect && (tid >= kPairMsg || v.y == t))) {
+                        sh.msg[tid] = v.x;
+                        tag         = t;
+                        break;
+                    }
+                    if (__any_sync(0xffffffffu, globaltimer_ns() - t0 > A.idle_ns)) break;   // idle: retire
+                }
+                if (tid == 0) s_tag = tag;
+            }
+            __syncthreads();
+            if (stamp) {
+                tl[0] = clock64();
+                g0    = globaltimer_ns();
+            }
+            const unsigned long long tag = s_tag;
+            unsigned cmd                 = tag ? (unsigned) sh.msg[W_CMD] : kCmdRetire;
+            if (cmd == kCmdQuit) cmd = kCmdRetire;
+            if (cmd != kCmdRetire) {
+                const unsigned long long gen = sh.msg[W_NP] >> 32;
+                if (gen != s_gen) {   // new keyframe: this pair's part of the setup from the host ring (one more round trip)
+                    const unsigned long long *sw = reinterpret_cast<const unsigned long long *>(A.h_setup + (gen % kSetupRing));
+                    unsigned long long *dst      = reinterpret_cast<unsigned long long *>(&sh.su);
+                    if (tid < kSetupLocal) {
+                        const int src = tid < kSetupCommon ? tid : kSetupCommon + kSetupPair * pair + (tid - kSetupCommon);
+                        unsigned long long v;
+                        asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(sw + src) : "memory");
+                        dst[tid] = v;
+                    }
+                    __syncthreads();
+                    if (tid == 0) s_gen = gen;
                 }
             }
-            s_seq = s;
+            // hand the message (and the setup) to the other ranks of the row: tagged slots through L2, no fence
+            const unsigned long long out_tag = tag ? tag : expect;
+            if (tid < kPairMsg)
+                st_slot_gpu(row + tid, cmd == kCmdRetire && tid == W_CMD ? (unsigned long long) kCmdRetire : sh.msg[tid], out_tag);
+            else if (tid >= 32 && tid < 32 + kSetupLocal)
+                st_slot_gpu(row + tid, reinterpret_cast<const unsigned long long *>(&sh.su)[tid - 32], out_tag);
+            if (cmd == kCmdRetire) {
+                if (tid == 0) {
+                    A.h_exit[pair] = A.launch_id;
+                    __threadfence_system();
+                }
+                return;
+            }
+            expect = tag + 1;
+        } else {
+            // ranks 1..7: the same message out of L2 (26 + 23 slots, one per thread, each spinning on its own slot), then
+            // one agreement check (all slots of one message; a rank without work may have skipped messages)
+            const bool mine = tid < kPairMsg || (tid >= 32 && tid < 32 + kSetupLocal);
+            const unsigned long long t0 = globaltimer_ns();
+            ulonglong2 v = make_ulonglong2(0, 0);
+            while (true) {
+                bool late = false;
+                if (mine) {
+                    unsigned n = 0;
+                    while ((v = ld_slot_gpu(row + tid)).y < expect)
+                        if ((++n & 63u) == 0 && globaltimer_ns() - t0 > hard_ns) {
+                            late = true;
+                            break;
+                        }
+                }
+                if (tid == 0) s_tag = v.y;
+                if (__syncthreads_or(late)) return;                                  // rank 0 is gone: never spin forever
+                if (__syncthreads_and(!mine || v.y == s_tag)) break;
+            }
+            const unsigned long long tag = s_tag;
+            if (stamp1) {
+                t1[0] = clock64();
+                g1    = globaltimer_ns();
+            }
+            if (tid < kPairMsg) sh.msg[tid] = v.x;
+            else if (mine) reinterpret_cast<unsigned long long *>(&sh.su)[tid - 32] = v.x;
+            __syncthreads();
+            if ((unsigned) sh.msg[W_CMD] == kCmdRetire) return;
+            expect = tag + 1;
         }
-        __syncthreads();
-        const unsigned long long s = s_seq;
-        if (s == kQuitSeq) return;
-        factor_work(A.d_msg->w, A.d_setup, blockIdx.y, blockIdx.x, kFactorRanks, smem, A.wb, nullptr, nullptr, nullptr);
-        last = s;
+        // ---- evaluate -----------------------------------------------------------------------------------------------
+        const unsigned long long tag = expect - 1;
+        pair_prepare(sh);
+        if (stamp) tl[1] = clock64();
+        if (stamp1) t1[1] = clock64();
+        const int q = sh.su.q, tiles = (q + kFactorBlock - 1) / kFactorBlock, C = ctas_with_work(tiles, kFactorRanks);
+        if (pair >= sh.n_pairs || rank >= C) {
+            __syncthreads();
+            continue;
+        }
+        if (sh.cmd == kCmdChi2) {
+            const int c = chi2_tiles(sh, rank, C, tiles);
+            if (rank != 0) {
+                if (tid == 0) st_unit_gpu(part + (size_t) rank * kRedUnits, (unsigned long long) c, 0ull, 0ull, tag);
+            } else if (tid == 0) {
+                int total = c;
+                bool ok   = true;
+                const unsigned long long t0 = globaltimer_ns();
+                for (int rk = 1; rk < C && ok; rk++) {
+                    Unit u;
+                    while ((u = ld_unit_gpu(part + (size_t) rk * kRedUnits)).tag != tag)
+                        if (globaltimer_ns() - t0 > hard_ns) {
+                            ok = false;
+                            break;
+                        }
+                    total += (int) u.w[0];
+                }
+                if (ok) st_unit(res, (unsigned long long) (unsigned) total, 0ull, 0ull, tag);
+            }
+            __syncthreads();
+            continue;
+        }
+        eval_tiles(sh, smem, pair, rank, C, tiles, true, nullptr, nullptr, nullptr);
+        if (stamp) tl[2] = clock64();
+        if (stamp1) t1[2] = clock64();
+        if (rank != 0) {
+            if (tid < kRedUnits)
+                st_unit_gpu(part + (size_t) rank * kRedUnits + tid, d2w_dev(s_red[3 * tid]), d2w_dev(s_red[3 * tid + 1]),
+                        3 * tid + 2 < kRedSize ? d2w_dev(s_red[3 * tid + 2]) : 0ull, tag);
+            if (stamp1) {
+                t1[3] = clock64();
+                for (int i = 0; i < 4; i++) A.timeline[8 + i] = t1[i];
+                A.timeline[12] = (long long) g1;
+                A.timeline[13] = (long long) globaltimer_ns();
+            }
+        } else {
+            // gather: thread t < 71 owns unit t = entries 3t .. 3t+2. Every partial unit is awaited individually (its tag says
+            // when it is there); the units a thread still misses are re-read TOGETHER (one L2 round trip per sweep, not one
+            // per unit); summed in rank order; the result unit goes straight into pinned host memory (posted write, no fence).
+            if (tid < kRedUnits) {
+                const unsigned long long t0 = globaltimer_ns();
+                Unit u[kFactorRanks];
+                unsigned pending = 0;
+#pragma unroll
+                for (int rk = 1; rk < kFactorRanks; rk++)
+                    if (rk < C) pending |= 1u << rk;
+                bool ok = true;
+                while (pending) {
+#pragma unroll
+                    for (int rk = 1; rk < kFactorRanks; rk++)
+                        if (pending & (1u << rk)) u[rk] = ld_unit_gpu(part + (size_t) rk * kRedUnits + tid);
+#pragma unroll
+                    for (int rk = 1; rk < kFactorRanks; rk++)
+                        if ((pending & (1u << rk)) && u[rk].tag == tag) pending &= ~(1u << rk);
+                    if (pending && globaltimer_ns() - t0 > hard_ns) {
+                        ok = false;
+                        break;
+                    }
+                }
+                if (ok) {
+                    unsigned long long out[3];
+#pragma unroll
+                    for (int k = 0; k < 3; k++) {
+                        const int e  = 3 * tid + k;
+                        double total = 0.0;  // same order as the launched kernel: 0 + rank 0 + rank 1 + ... (also the sign of zero)
+                        total += e < kRedSize ? s_red[e] : 0.0;
+#pragma unroll
+                        for (int rk = 1; rk < kFactorRanks; rk++)
+                            if (rk < C) total += w2d(u[rk].w[k]);
+                        total += 0.0;
+                        out[k] = d2w_dev(total);
+                    }
+                    st_unit(res + tid, out[0], out[1], out[2], tag);
+                }
+            }
+            if (stamp) {
+                tl[3] = clock64();
+                for (int i = 0; i < 4; i++) A.timeline[i] = tl[i];
+                A.timeline[4] = (long long) g0;
+                A.timeline[5] = (long long) globaltimer_ns();
+            }
+        }
         __syncthreads();
     }
 }
@@ -472,18 +652,27 @@ struct FactorRuntime {
     bool have_cached = false;
     unsigned long long gen = 0;
     WorkBuffers wb{};
+    // pinned result block of the host-facing calls: red [kMaxRefs][kRedSize] | signal [kMaxRefs] | counts [kMaxRefs]
+    double *h_red = nullptr;
+    int *h_counts = nullptr;
+    unsigned long long *h_signal = nullptr;
+    unsigned long long signal_seq = 0;
     // resident kernel
     cudaStream_t res_stream = nullptr;
-    ulonglong2 *h_slots = nullptr;
-    unsigned long long *h_state = nullptr;
-    FactorMsg *d_msg = nullptr;
-    FactorSetup *d_setup_res = nullptr;
-    unsigned long long *d_seq = nullptr;
+    ulonglong2 *h_mail = nullptr, *d_row = nullptr;
+    Unit *h_res = nullptr, *d_part = nullptr;
+    unsigned long long *h_exit = nullptr;
     unsigned long long mseq = 0, launch_id = 0, idle_ns = 1000000ull;
+    int rows = 0;
     bool running = false, enabled = true;
     int strikes = 0;
     unsigned long long evals_this_launch = 0;
     FactorStats st{};
+    // diagnostics (FFLINS_RES_TIMELINE=1): where a resident evaluation's round trip goes
+    bool timeline = false;
+    long long *h_timeline = nullptr;
+    double tl_post = 0, tl_wait = 0, tl_unpack = 0, tl_cyc[3] = {0, 0, 0}, tl_r1[3] = {0, 0, 0}, tl_g[3] = {0, 0, 0};
+    long long tl_n = 0;
 };
 
 void factor_runtime_destroy(FactorRuntime *rt);
@@ -491,24 +680,31 @@ void factor_runtime_destroy(FactorRuntime *rt);
 FactorRuntime *factor_runtime_create(int device) {
     FactorRuntime *rt = new FactorRuntime();
     rt->device        = device;
+    const size_t res_bytes = sizeof(double) * kMaxRefs * kRedSize + sizeof(unsigned long long) * kMaxRefs + sizeof(int) * kMaxRefs;
     bool ok = cudaMallocHost((void **) &rt->h_setup, sizeof(FactorSetup) * kSetupRing) == cudaSuccess &&
               cudaMalloc((void **) &rt->d_setup, sizeof(FactorSetup) * kSetupRing) == cudaSuccess &&
               cudaMalloc((void **) &rt->wb.partials, sizeof(double) * kMaxRefs * kFactorRanks * kRedSize) == cudaSuccess &&
               cudaMalloc((void **) &rt->wb.tickets, sizeof(int) * 2 * kMaxRefs + 16) == cudaSuccess &&
-              cudaMallocHost((void **) &rt->h_slots, sizeof(ulonglong2) * kMsgWords) == cudaSuccess &&
-              cudaMallocHost((void **) &rt->h_state, 64) == cudaSuccess &&
-              cudaMalloc((void **) &rt->d_msg, sizeof(FactorMsg)) == cudaSuccess &&
-              cudaMalloc((void **) &rt->d_setup_res, sizeof(FactorSetup)) == cudaSuccess &&
-              cudaMalloc((void **) &rt->d_seq, 64) == cudaSuccess &&
+              cudaMallocHost((void **) &rt->h_red, res_bytes) == cudaSuccess &&
+              cudaMallocHost((void **) &rt->h_mail, sizeof(ulonglong2) * kMaxRefs * kPairSlots) == cudaSuccess &&
+              cudaMallocHost((void **) &rt->h_res, sizeof(Unit) * kMaxRefs * kRedUnits) == cudaSuccess &&
+              cudaMallocHost((void **) &rt->h_exit, sizeof(unsigned long long) * (kMaxRefs + 16)) == cudaSuccess &&
+              cudaMalloc((void **) &rt->d_row, sizeof(ulonglong2) * kMaxRefs * kRowSlots) == cudaSuccess &&
+              cudaMalloc((void **) &rt->d_part, sizeof(Unit) * kMaxRefs * kFactorRanks * kRedUnits) == cudaSuccess &&
               cudaStreamCreateWithFlags(&rt->res_stream, cudaStreamNonBlocking) == cudaSuccess;
     if (ok) {
-        rt->wb.counts = rt->wb.tickets + kMaxRefs;
-        rt->wb.acks   = nullptr;
+        rt->wb.counts  = rt->wb.tickets + kMaxRefs;
+        rt->h_signal   = reinterpret_cast<unsigned long long *>(rt->h_red + kMaxRefs * kRedSize);
+        rt->h_counts   = reinterpret_cast<int *>(rt->h_signal + kMaxRefs);
+        rt->h_timeline = reinterpret_cast<long long *>(rt->h_exit + kMaxRefs);
+        std::memset(rt->h_red, 0, res_bytes);
+        std::memset(rt->h_mail, 0, sizeof(ulonglong2) * kMaxRefs * kPairSlots);
+        std::memset(rt->h_res, 0, sizeof(Unit) * kMaxRefs * kRedUnits);
+        std::memset(rt->h_exit, 0, sizeof(unsigned long long) * (kMaxRefs + 16));
         ok = cudaMemset(rt->wb.tickets, 0, sizeof(int) * 2 * kMaxRefs + 16) == cudaSuccess &&
-             cudaMemset(rt->d_seq, 0, 64) == cudaSuccess;
-        std::memset(rt->h_slots, 0, sizeof(ulonglong2) * kMsgWords);
-        std::memset(rt->h_state, 0, 64);
-        ok = ok && cudaFuncSetAttribute(factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kFactorSmem) == cudaSuccess &&
+             cudaMemset(rt->d_row, 0, sizeof(ulonglong2) * kMaxRefs * kRowSlots) == cudaSuccess &&
+             cudaMemset(rt->d_part, 0, sizeof(Unit) * kMaxRefs * kFactorRanks * kRedUnits) == cudaSuccess &&
+             cudaFuncSetAttribute(factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kFactorSmem) == cudaSuccess &&
              cudaFuncSetAttribute(resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kFactorSmem) == cudaSuccess;
     }
     if (!ok) {
@@ -521,6 +717,7 @@ FactorRuntime *factor_runtime_create(int device) {
         long v = atol(e);
         if (v >= 10 && v <= 1000000) rt->idle_ns = (unsigned long long) v * 1000ull;
     }
+    rt->timeline = getenv("FFLINS_RES_TIMELINE") != nullptr;
     return rt;
 }
 
@@ -528,48 +725,67 @@ namespace {
 
 using Clock = std::chrono::steady_clock;
 
-void post_message(FactorRuntime *rt, const FactorMsg &m, unsigned long long tag) {
-    // word before tag; x86-64 keeps the two stores in order and a 16-byte slot is fetched by the device in one piece
-    volatile unsigned long long *p = reinterpret_cast<volatile unsigned long long *>(rt->h_slots);
-    for (int i = 0; i < kMsgWords; i++) {
-        p[2 * i] = m.w[i];
-        __atomic_store_n(const_cast<unsigned long long *>(p + 2 * i + 1), tag, __ATOMIC_RELEASE);
+inline void put_slot(ulonglong2 *slot, unsigned long long w, unsigned long long tag) {
+    // word before tag; x86-64 keeps the two stores in order and the device fetches a 16-byte slot in one piece
+    volatile unsigned long long *p = reinterpret_cast<volatile unsigned long long *>(slot);
+    p[0] = w;
+    __atomic_store_n(const_cast<unsigned long long *>(p + 1), tag, __ATOMIC_RELEASE);
+}
+
+// One mailbox region per pair: the 19 header words and the pair's own reference pose.
+void post_message(FactorRuntime *rt, const FactorMsg &m, int n_pairs, unsigned long long tag) {
+    for (int p = 0; p < n_pairs; p++) {
+        ulonglong2 *reg = rt->h_mail + (size_t) p * kPairSlots;
+        for (int i = 0; i < kMsgHead; i++) put_slot(reg + i, m.w[i], tag);
+        for (int i = 0; i < 7; i++) put_slot(reg + kMsgHead + i, m.w[kMsgHead + 7 * p + i], tag);
     }
 }
 
-bool resident_exited(const FactorRuntime *rt) {
-    return __atomic_load_n(rt->h_state + 1, __ATOMIC_ACQUIRE) == rt->launch_id;
+bool resident_exited(const FactorRuntime *rt, int n) {
+    for (int p = 0; p < n; p++)
+        if (__atomic_load_n(rt->h_exit + p, __ATOMIC_ACQUIRE) == rt->launch_id) return true;
+    return false;
 }
 
-cudaError_t resident_start(FactorRuntime *rt) {
+WorkBuffers host_buffers(const FactorRuntime *rt) {
+    WorkBuffers wb  = rt->wb;
+    wb.out_red      = rt->h_red;
+    wb.host_counts  = rt->h_counts;
+    wb.signal       = rt->h_signal;
+    return wb;
+}
+
+cudaError_t resident_start(FactorRuntime *rt, int rows) {
     ResidentArgs A{};
-    A.h_slots   = rt->h_slots;
+    A.h_mail    = rt->h_mail;
     A.h_setup   = rt->h_setup;
-    A.h_state   = rt->h_state;
-    A.d_msg     = rt->d_msg;
-    A.d_setup   = rt->d_setup_res;
-    A.d_seq     = rt->d_seq;
+    A.h_exit    = rt->h_exit;
+    A.h_res     = rt->h_res;
+    A.d_row     = rt->d_row;
+    A.d_part    = rt->d_part;
     A.start_seq = rt->mseq;
     A.launch_id = ++rt->launch_id;
     A.idle_ns   = rt->idle_ns;
-    A.wb        = rt->wb;
-    A.wb.acks   = rt->d_seq + 1;
-    unsigned long long init[2] = {rt->mseq, 0ull};
-    cudaError_t e = cudaMemcpyAsync(rt->d_seq, init, sizeof(init), cudaMemcpyHostToDevice, rt->res_stream);
-    if (e != cudaSuccess) return e;
-    resident_kernel<<<dim3(kFactorRanks, kMaxRefs + 1), kFactorBlock, kFactorSmem, rt->res_stream>>>(A);
-    e = cudaGetLastError();
+    A.rows      = rows;
+    A.timeline  = rt->timeline ? rt->h_timeline : nullptr;
+    // a retired kernel leaves its farewell in the device rows (tagged with the NEXT sequence number): clear them
+    cudaError_t em = cudaMemsetAsync(rt->d_row, 0, sizeof(ulonglong2) * kMaxRefs * kRowSlots, rt->res_stream);
+    if (em != cudaSuccess) return em;
+    resident_kernel<<<dim3(kFactorRanks, rows), kFactorBlock, kFactorSmem, rt->res_stream>>>(A);
+    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     rt->running           = true;
+    rt->rows              = rows;
     rt->evals_this_launch = 0;
     rt->st.resident_launches++;
     return cudaSuccess;
 }
 
-// The resident kernel has retired (or is about to): account for it.
+// Some row of the resident kernel has retired (idle): wait for all of them, account for the launch.
 void resident_reap(FactorRuntime *rt) {
     cudaStreamSynchronize(rt->res_stream);
     rt->running = false;
+    if (rt->timeline) std::fprintf(stderr, "[fflins] resident kernel %llu reaped after %llu calls\n", rt->launch_id, rt->evals_this_launch);
     if (rt->evals_this_launch == 0) {
         if (++rt->strikes >= 3) rt->enabled = false; // e.g. under a profiler that serialises kernels: stop trying
     } else {
@@ -577,13 +793,51 @@ void resident_reap(FactorRuntime *rt) {
     }
 }
 
-// Post `m` to the resident kernel and wait for flags[0..n) = seq. Returns 0 done, 1 not handled (caller launches), < 0 error.
-int resident_call(FactorRuntime *rt, FactorMsg &m, const unsigned long long *flags, int n, unsigned long long seq) {
+// Where entry e of the 212-vector goes in the caller's blocks: H offsets (two, symmetric) for e < 190.
+struct UnpackMap {
+    short a[190], b[190];
+    UnpackMap() {
+        int e = 0;
+        for (int i = 0; i < 19; i++)
+            for (int j = i; j < 19; j++) {
+                a[e] = (short) (19 * i + j);
+                b[e] = (short) (19 * j + i);
+                e++;
+            }
+    }
+};
+inline void unpack_entry(const UnpackMap &M, int e, double v, double *H, double *b, double *cost, int32_t *n_res) {
+    if (e < 190) {
+        if (H) {
+            H[M.a[e]] = v;
+            H[M.b[e]] = v;
+        }
+    } else if (e < 209) {
+        if (b) b[e - 190] = v;
+    } else if (e == 209) {
+        if (cost) cost[0] = 0.5 * v;
+    } else if (e == 210) {
+        if (cost) cost[1] = v;
+    } else if (e == 211) {
+        if (n_res) *n_res = (int32_t) (v + 0.5);
+    }
+}
+
+// A result unit is there when it carries the message's tag.
+inline bool unit_ready(const Unit *u, unsigned long long tag) { return __atomic_load_n(&u->tag, __ATOMIC_ACQUIRE) == tag; }
+
+// Post `m` to the resident kernel, wait for the tagged results of n pairs and copy them into the runtime's plain result
+// block (h_red / h_counts) — what the launched kernel would have written. Returns 0 done, 1 not handled (the caller
+// launches), < 0 error.
+int resident_call(FactorRuntime *rt, FactorMsg &m, int n, bool chi2, FactorResults *res) {
+    static const UnpackMap umap;
+    const bool direct = res && !chi2 && (res->H || res->b || res->cost || res->n_res);
     if (!rt->enabled) return 1;
-    if (rt->running && resident_exited(rt)) resident_reap(rt);
+    if (rt->running && resident_exited(rt, rt->rows)) resident_reap(rt);
+    if (rt->running && rt->rows != n) factor_runtime_quiesce(rt); // the window has grown (or shrunk): one row per pair
     if (!rt->enabled) return 1;
     if (!rt->running) {
-        cudaError_t e = resident_start(rt);
+        cudaError_t e = resident_start(rt, n);
         if (e != cudaSuccess) {
             cudaGetLastError();
             rt->enabled = false;
@@ -591,42 +845,85 @@ int resident_call(FactorRuntime *rt, FactorMsg &m, const unsigned long long *fla
         }
     }
     const unsigned long long tag = ++rt->mseq;
-    post_message(rt, m, tag);
+    Clock::time_point tl0, tl1, tl2;
+    if (rt->timeline) tl0 = Clock::now();
+    post_message(rt, m, n, tag);
+    if (rt->timeline) tl1 = Clock::now();
+    const int per = chi2 ? 1 : kRedUnits;
     unsigned spins = 0;
     Clock::time_point t0;
-    bool timing = false;
-    for (int i = 0; i < n; i++) {
-        while (__atomic_load_n(flags + i, __ATOMIC_ACQUIRE) != seq) {
-            if ((++spins & 0x3ffu) == 0) {
-                if (resident_exited(rt)) {
-                    const unsigned long long done = rt->h_state[0];
-                    if (done >= tag) rt->evals_this_launch++;
-                    resident_reap(rt); // (joins the kernel: every store it made is visible now)
-                    bool all = done >= tag;
-                    for (int j = 0; j < n && all; j++) all = __atomic_load_n(flags + j, __ATOMIC_ACQUIRE) == seq;
-                    if (all) {
-                        rt->st.resident_evals++;
-                        return 0;
+    bool timing = false, first = true;
+    for (int p = 0; p < n; p++) {
+        const Unit *reg = rt->h_res + (size_t) p * kRedUnits;
+        double *dst     = rt->h_red + (size_t) p * kRedSize;
+        for (int e = 0; e < per; e++) {
+            if ((e & 1) == 0) __builtin_prefetch(reg + e + 8, 0, 0);   // the lines were just written by the device
+            while (!unit_ready(reg + e, tag)) {
+                if ((++spins & 0x3ffu) == 0) {
+                    if (resident_exited(rt, rt->rows)) {
+                        resident_reap(rt); // (joins the kernel: every store it made is visible now)
+                        if (unit_ready(reg + e, tag)) continue;
+                        rt->st.resident_fallbacks++;
+                        if (rt->timeline) std::fprintf(stderr, "[fflins] resident call %llu: kernel retired, pair %d unit %d missing -> launch\n", tag, p, e);
+                        return 1;
                     }
-                    rt->st.resident_fallbacks++;
-                    return 1;
+                    if (!timing) {
+                        t0     = Clock::now();
+                        timing = true;
+                    } else if (Clock::now() - t0 > std::chrono::seconds(2)) {
+                        cudaError_t er = cudaStreamQuery(rt->res_stream);
+                        rt->enabled    = false;
+                        return er != cudaSuccess && er != cudaErrorNotReady ? -(int) er : -(int) cudaErrorLaunchTimeout;
+                    }
                 }
-                if (!timing) {
-                    t0     = Clock::now();
-                    timing = true;
-                } else if (Clock::now() - t0 > std::chrono::seconds(2)) {
-                    cudaError_t e = cudaStreamQuery(rt->res_stream);
-                    rt->enabled   = false;
-                    return e != cudaSuccess && e != cudaErrorNotReady ? -(int) e : -(int) cudaErrorLaunchTimeout;
+#if defined(__x86_64__)
+                __builtin_ia32_pause();
+#endif
+            }
+            if (rt->timeline && first) {
+                tl2   = Clock::now();
+                first = false;
+            }
+            const volatile unsigned long long *w = reg[e].w;
+            if (chi2) {
+                rt->h_counts[p] = (int) w[0];
+            } else {
+                const int k = 3 * e, m = kRedSize - k < 3 ? kRedSize - k : 3;
+                unsigned long long tmp[3] = {w[0], w[1], w[2]};
+                if (direct) {
+                    for (int i = 0; i < m; i++) {
+                        double v;
+                        std::memcpy(&v, tmp + i, 8);
+                        unpack_entry(umap, k + i, v, res->H ? res->H + 361 * (size_t) p : nullptr, res->b ? res->b + 19 * (size_t) p : nullptr,
+                                     res->cost ? res->cost + 2 * (size_t) p : nullptr, res->n_res ? res->n_res + p : nullptr);
+                    }
+                } else {
+                    std::memcpy(dst + k, tmp, 8 * m);
                 }
             }
-#if defined(__x86_64__)
-            __builtin_ia32_pause();
-#endif
         }
     }
     rt->evals_this_launch++;
     rt->st.resident_evals++;
+    if (res) res->unpacked = direct;
+    if (rt->timeline) {
+        const auto tl3 = Clock::now();
+        auto us = [](Clock::duration d) { return std::chrono::duration<double, std::micro>(d).count(); };
+        rt->tl_post += us(tl1 - tl0);
+        rt->tl_wait += us(tl2 - tl1);
+        rt->tl_unpack += us(tl3 - tl2);
+        if (!chi2)
+            for (int i = 0; i < 3; i++) {
+                rt->tl_cyc[i] += (double) (rt->h_timeline[i + 1] - rt->h_timeline[i]);
+                rt->tl_r1[i] += (double) (rt->h_timeline[8 + i + 1] - rt->h_timeline[8 + i]);
+            }
+        if (!chi2) {
+            rt->tl_g[0] += (double) (rt->h_timeline[12] - rt->h_timeline[4]);   // rank 1 sees the message after rank 0 (ns)
+            rt->tl_g[1] += (double) (rt->h_timeline[13] - rt->h_timeline[4]);   // rank 1 partials stored, since rank 0 saw the message
+            rt->tl_g[2] += (double) (rt->h_timeline[5] - rt->h_timeline[4]);    // rank 0 results stored
+        }
+        rt->tl_n++;
+    }
     return 0;
 }
 
@@ -671,21 +968,17 @@ unsigned long long d2w(double d) {
     return w;
 }
 
-void fill_msg(const FactorRuntime *rt, const FactorParams &p, unsigned cmd, double thr, unsigned long long seq, double *out_red,
-              int *host_counts, unsigned long long *signal, FactorMsg &m) {
+void fill_msg(const FactorRuntime *rt, const FactorParams &p, unsigned cmd, double thr, unsigned long long seq, FactorMsg &m) {
     m.w[W_CMD] = (unsigned long long) cmd | ((unsigned long long) p.flags << 32);
     m.w[W_NP]  = (unsigned long long) (unsigned) p.n_pairs | (rt->gen << 32);
     m.w[W_TD]  = d2w(p.td);
     m.w[W_THR] = d2w(thr);
     m.w[W_SEQ] = seq;
-    m.w[W_OUT] = (unsigned long long) (uintptr_t) out_red;
-    m.w[W_CNT] = (unsigned long long) (uintptr_t) host_counts;
-    m.w[W_SIG] = (unsigned long long) (uintptr_t) signal;
     for (int i = 0; i < 7; i++) {
         m.w[W_CUR + i] = d2w(p.pose_cur[i]);
         m.w[W_EXT + i] = d2w(p.ext[i]);
     }
-    for (int j = 0; j < kMaxRefs; j++)
+    for (int j = 0; j < kMaxPairs; j++)
         for (int i = 0; i < 7; i++) m.w[W_REF + 7 * j + i] = j < p.n_pairs ? d2w(p.pair[j].pose_ref[i]) : 0ull;
 }
 
@@ -694,15 +987,50 @@ int ranks_for(int q) {
     return tiles < 1 ? 1 : (tiles < kFactorRanks ? tiles : kFactorRanks);
 }
 
+int run(FactorRuntime *rt, cudaStream_t s, const FactorParams &p, const float *points, int stride4, unsigned cmd, double thr,
+        double *r, double *J, uint8_t *valid, bool want_red, double *d_red, bool resident, FactorResults *res, int64_t *launches) {
+    if (p.n_pairs <= 0 || p.q <= 0) return 0;
+    if (p.n_pairs > kMaxPairs) return -(int) cudaErrorInvalidValue;
+    FactorSetup su;
+    fill_setup(p, points, stride4, su);
+    cudaError_t e = push_setup(rt, s, su);
+    if (e != cudaSuccess) return -(int) e;
+    const bool to_host = (cmd == kCmdChi2 || want_red) && !d_red;
+    const unsigned long long seq = to_host ? ++rt->signal_seq : 0;
+    if (res) {
+        res->red      = rt->h_red;
+        res->counts   = rt->h_counts;
+        res->signal   = rt->h_signal;
+        res->seq      = seq;
+        res->unpacked = false;
+    }
+    FactorMsg m;
+    fill_msg(rt, p, cmd, thr, seq, m);
+    if (resident && to_host && !r && !J && !valid) {
+        int rc = resident_call(rt, m, p.n_pairs, cmd == kCmdChi2, res);
+        if (rc <= 0) return rc;
+    }
+    WorkBuffers wb = to_host ? host_buffers(rt) : rt->wb;
+    if (!to_host) {
+        wb.out_red     = (want_red ? d_red : nullptr);
+        wb.host_counts = nullptr;
+        wb.signal      = nullptr;
+    }
+    factor_kernel<<<dim3(ranks_for(p.q), p.n_pairs), kFactorBlock, kFactorSmem, s>>>(m, rt->d_setup + (rt->gen % kSetupRing), wb, r, J, valid);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return -(int) e;
+    rt->st.launched_evals++;
+    if (launches) (*launches)++;
+    return 1;
+}
+
 } // namespace
 
 void factor_runtime_quiesce(FactorRuntime *rt) {
     if (!rt || !rt->running) return;
-    if (!resident_exited(rt)) {
-        FactorMsg m{};
-        m.w[W_CMD] = kCmdQuit;
-        post_message(rt, m, ++rt->mseq);
-    }
+    FactorMsg m{};
+    m.w[W_CMD] = kCmdQuit;
+    post_message(rt, m, rt->rows, ++rt->mseq);   // (rows that have already retired ignore it)
     cudaStreamSynchronize(rt->res_stream);
     rt->running = false;
 }
@@ -710,16 +1038,31 @@ void factor_runtime_quiesce(FactorRuntime *rt) {
 void factor_runtime_destroy(FactorRuntime *rt) {
     if (!rt) return;
     factor_runtime_quiesce(rt);
+    if (rt->timeline && rt->tl_n) {
+        const double n = (double) rt->tl_n;
+        std::fprintf(stderr,
+                     "[fflins] resident timeline over %lld calls (us): post %.2f | posted -> first result slot visible %.2f | "
+                     "remaining slots + unpack %.2f\n"
+                     "[fflins]   row 0, rank 0 (cycles): message seen -> constants ready %.0f | evaluate + SYRK + warp partials %.0f | "
+                     "gather partials + host stores %.0f\n",
+                     rt->tl_n, rt->tl_post / n, rt->tl_wait / n, rt->tl_unpack / n, rt->tl_cyc[0] / n, rt->tl_cyc[1] / n, rt->tl_cyc[2] / n);
+        std::fprintf(stderr,
+                     "[fflins]   row 0, rank 1 (cycles): message seen -> constants ready %.0f | evaluate %.0f | partial stores %.0f;  "
+                     "globaltimer (ns, 1 us ticks): rank 1 sees message %+.0f, rank 1 partials stored %+.0f, rank 0 results stored %+.0f "
+                     "after rank 0 saw the message\n",
+                     rt->tl_r1[0] / n, rt->tl_r1[1] / n, rt->tl_r1[2] / n, rt->tl_g[0] / n, rt->tl_g[1] / n, rt->tl_g[2] / n);
+    }
     if (rt->res_stream) cudaStreamDestroy(rt->res_stream);
     if (rt->h_setup) cudaFreeHost(rt->h_setup);
-    if (rt->h_slots) cudaFreeHost(rt->h_slots);
-    if (rt->h_state) cudaFreeHost(rt->h_state);
+    if (rt->h_mail) cudaFreeHost(rt->h_mail);
+    if (rt->h_res) cudaFreeHost(rt->h_res);
+    if (rt->h_exit) cudaFreeHost(rt->h_exit);
+    if (rt->h_red) cudaFreeHost(rt->h_red);
     cudaFree(rt->d_setup);
     cudaFree(rt->wb.partials);
     cudaFree(rt->wb.tickets);
-    cudaFree(rt->d_msg);
-    cudaFree(rt->d_setup_res);
-    cudaFree(rt->d_seq);
+    cudaFree(rt->d_row);
+    cudaFree(rt->d_part);
     delete rt;
 }
 
@@ -728,48 +1071,14 @@ void factor_runtime_stats(const FactorRuntime *rt, FactorStats *out) {
 }
 
 int launch_factor_eval(FactorRuntime *rt, cudaStream_t s, const FactorParams &p, const float *points, int stride4, double *r,
-                       double *J, uint8_t *valid, double *out_red, unsigned long long *signal, unsigned long long seq,
-                       bool resident, int64_t *launches) {
-    if (p.n_pairs <= 0 || p.q <= 0) return 0;
-    FactorSetup su;
-    fill_setup(p, points, stride4, su);
-    cudaError_t e = push_setup(rt, s, su);
-    if (e != cudaSuccess) return -(int) e;
-    FactorMsg m;
-    fill_msg(rt, p, kCmdEval, 0.0, seq, out_red, nullptr, signal, m);
-    if (resident && signal && out_red && !r && !J && !valid) {
-        int rc = resident_call(rt, m, signal, p.n_pairs, seq);
-        if (rc <= 0) return rc;
-    }
-    factor_kernel<<<dim3(ranks_for(p.q), p.n_pairs), kFactorBlock, kFactorSmem, s>>>(m, rt->d_setup + (rt->gen % kSetupRing), rt->wb, r, J,
-                                                                                      valid);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return -(int) e;
-    rt->st.launched_evals++;
-    if (launches) (*launches)++;
-    return 1;
+                       double *J, uint8_t *valid, bool want_red, double *d_red, bool resident, FactorResults *res,
+                       int64_t *launches) {
+    return run(rt, s, p, points, stride4, kCmdEval, 0.0, r, J, valid, want_red, d_red, resident, res, launches);
 }
 
 int launch_chi2(FactorRuntime *rt, cudaStream_t s, const FactorParams &p, const float *points, int stride4, double threshold,
-                int *host_counts, unsigned long long *signal, unsigned long long seq, bool resident, int64_t *launches) {
-    if (p.n_pairs <= 0 || p.q <= 0) return 0;
-    FactorSetup su;
-    fill_setup(p, points, stride4, su);
-    cudaError_t e = push_setup(rt, s, su);
-    if (e != cudaSuccess) return -(int) e;
-    FactorMsg m;
-    fill_msg(rt, p, kCmdChi2, threshold, seq, nullptr, host_counts, signal, m);
-    if (resident) {
-        int rc = resident_call(rt, m, signal, p.n_pairs, seq);
-        if (rc <= 0) return rc;
-    }
-    factor_kernel<<<dim3(ranks_for(p.q), p.n_pairs), kFactorBlock, kFactorSmem, s>>>(m, rt->d_setup + (rt->gen % kSetupRing), rt->wb,
-                                                                                      nullptr, nullptr, nullptr);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return -(int) e;
-    rt->st.launched_evals++;
-    if (launches) (*launches)++;
-    return 1;
+                bool resident, FactorResults *res, int64_t *launches) {
+    return run(rt, s, p, points, stride4, kCmdChi2, threshold, nullptr, nullptr, nullptr, false, nullptr, resident, res, launches);
 }
 
 double measure_fp64_tflops(cudaStream_t s) {

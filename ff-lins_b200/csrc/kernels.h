@@ -238,10 +238,13 @@ struct FactorSetup {
 };
 enum { kCmdEval = 1, kCmdChi2 = 2, kCmdQuit = 3 };
 // word 0: cmd | flags << 32     word 1: n_pairs | setup generation << 32     word 2: td     word 3: chi2 threshold
-// word 4: completion value (signal[pair] = seq)   5: out_red   6: host_counts   7: signal (pinned host addresses)
-// 8..14 pose_cur   15..21 ext   22 + 7 i .. pose_ref[i]
-constexpr int kMsgHead  = 22;
-constexpr int kMsgWords = kMsgHead + 7 * kMaxRefs;
+// word 4: completion value (signal[pair] = seq)   5..11 pose_cur   12..18 ext   19 + 7 i .. pose_ref[i]
+// A window holds at most kMaxRefs keyframes, i.e. kMaxRefs - 1 references: 19 + 7 * 15 = 124 words, so that the
+// 128 threads of the resident kernel's dispatcher fetch a whole message with ONE 16-byte load each.
+constexpr int kMaxPairs = kMaxRefs - 1;
+constexpr int kMsgHead  = 19;
+constexpr int kMsgWords = kMsgHead + 7 * kMaxPairs;
+static_assert(kMsgWords <= 128, "a message must fit one poll of the dispatcher CTA");
 struct FactorMsg {
     unsigned long long w[kMsgWords];
 };
@@ -263,20 +266,31 @@ void factor_runtime_quiesce(FactorRuntime *rt);
 
 // points: xyz of cur-frame points as float4 (stride4=1) or packed float3 (stride4=0).
 // r/J/valid (optional, device) are per (pair, feature): r[pair*q+k], J[22*(pair*q+k)].
-// out_red: n_pairs * kRedSize doubles (nullptr: no reduction), device or pinned host memory. signal (optional, pinned):
-// signal[pair] = seq is released at system scope once the pair's kRedSize sums are stored, so the host may poll instead
-// of synchronising the stream.
-// resident = true (needs pinned out_red + signal, no per-feature outputs): the evaluation is posted to the resident
-// kernel's mailbox instead of being launched (the kernel is started on demand and retires by itself when idle); the call
-// returns after the results have ARRIVED (it polls the flags itself). Returns 0 = done, 1 = launched on `s` (the caller
-// waits for signal / the stream), < 0 = error (cudaError_t negated).
+// Where the reduced results of the solver-facing calls arrive: pinned host memory owned by the runtime, written by the
+// kernels (zero-copy) with signal[pair] = seq released at system scope behind each pair's data, so the host polls
+// instead of synchronising a stream.
+struct FactorResults {
+    const double *red;                 // [kMaxRefs][kRedSize]
+    const int *counts;                 // [kMaxRefs] chi2
+    const unsigned long long *signal;  // [kMaxRefs]
+    unsigned long long seq;            // value the flags take for THIS call
+    // optional: where the caller wants the blocks (per pair: H 19x19 row-major, b 19, cost 2, n_res). A call served by
+    // the resident kernel unpacks its tagged result units straight into them (unpacked = true) instead of into `red`.
+    double *H, *b, *cost;
+    int32_t *n_res;
+    bool unpacked;
+};
+// want_red: reduce into the runtime's pinned result block (FactorResults) — or, when d_red is given, into device memory
+// (no flags). resident = true (only with want_red and no per-feature outputs): the evaluation is POSTED to the resident
+// kernel's mailbox instead of being launched (the kernel is started on demand and retires by itself when idle) and the
+// call returns after the results have ARRIVED. Returns 0 = done, 1 = launched on `s` (the caller waits for res->signal or
+// the stream), < 0 = error (cudaError_t negated).
 int launch_factor_eval(FactorRuntime *rt, cudaStream_t s, const FactorParams &p, const float *points, int stride4, double *r,
-                       double *J, uint8_t *valid, double *out_red, unsigned long long *signal, unsigned long long seq,
-                       bool resident, int64_t *launches);
-// K7: outlier flags are set in p.pair[i].outlier; per-pair counts land in host_counts (pinned) and signal[pair] = seq is
-// released behind each of them. Same return convention as launch_factor_eval.
+                       double *J, uint8_t *valid, bool want_red, double *d_red, bool resident, FactorResults *res,
+                       int64_t *launches);
+// K7: outlier flags are set in p.pair[i].outlier; per-pair counts land in res->counts. Same return convention.
 int launch_chi2(FactorRuntime *rt, cudaStream_t s, const FactorParams &p, const float *points, int stride4, double threshold,
-                int *host_counts, unsigned long long *signal, unsigned long long seq, bool resident, int64_t *launches);
+                bool resident, FactorResults *res, int64_t *launches);
 // fp64 FMA throughput of the device (the roofline of K6): TFLOP/s of a register-resident DFMA loop on every SM.
 double measure_fp64_tflops(cudaStream_t s);
 
