@@ -239,6 +239,58 @@ class Sequence:
                     ins_t=GPS_T0 + t_ins, ins_p=np.ascontiguousarray(p_ins), ins_q=np.ascontiguousarray(q_ins),
                     v=v, omega=w)
 
+    # ---- raw IMU increments of the analytic trajectory (what the INS mechanization consumes) -----------------------
+    def body_accel(self, t):
+        """Second derivative of body_pose's position (analytic)."""
+        t = np.atleast_1d(np.asarray(t, np.float64))
+        a, w = self.omega_z * t, self.omega_z
+        return np.stack([-self.radius * w * w * np.cos(a), -self.radius * w * w * np.sin(a),
+                         -0.05 * 9 * w * w * np.sin(3 * a)], -1)
+
+    def body_rate(self, t, h=1e-5):
+        """Body-frame angular rate: vee(log(R(t-h)^T R(t+h))) / 2h."""
+        t = np.atleast_1d(np.asarray(t, np.float64))
+        _, R0 = self.body_pose(t - h)
+        _, R1 = self.body_pose(t + h)
+        dR = np.einsum("nji,njk->nik", R0, R1)
+        v = np.stack([dR[:, 2, 1] - dR[:, 1, 2], dR[:, 0, 2] - dR[:, 2, 0], dR[:, 1, 0] - dR[:, 0, 1]], -1) / 2
+        s = np.linalg.norm(v, axis=1, keepdims=True)
+        ang = np.arcsin(np.clip(s, 0, 1))
+        return v * np.where(s > 1e-12, ang / np.maximum(s, 1e-300), 1.0) / (2 * h)
+
+    def imu_samples(self, k0, k1, gravity=-9.80, bg=(0, 0, 0), ba=(0, 0, 0), rng=None, arw=0.0, vrw=0.0):
+        """IMU epochs k0..k1 (inclusive) at the IMU rate, absolute times GPS_T0 + k dt: (time, dt, dtheta[3], dvel[3]) with
+        dtheta = integral of the body rate and dvel = integral of the specific force over (t - dt, t] (4-point Gauss-
+        Legendre), plus optional constant biases and white noise (angle / velocity random walk, per sqrt(s))."""
+        dt = 1.0 / self.imu_hz
+        ks = np.arange(k0, k1 + 1)
+        t1 = ks * dt
+        gx = np.array([-0.8611363115940526, -0.3399810435848563, 0.3399810435848563, 0.8611363115940526])
+        gw = np.array([0.3478548451374538, 0.6521451548625461, 0.6521451548625461, 0.3478548451374538])
+        g = np.array([0.0, 0.0, gravity])
+        dth = np.zeros((len(ks), 3))
+        dv = np.zeros((len(ks), 3))
+        for x, w in zip(gx, gw):
+            tau = t1 - dt / 2 + x * dt / 2
+            _, R = self.body_pose(tau)
+            f = np.einsum("nji,nj->ni", R, self.body_accel(tau) - g)
+            dv += w * dt / 2 * f
+            dth += w * dt / 2 * self.body_rate(tau)
+        dth += np.asarray(bg) * dt
+        dv += np.asarray(ba) * dt
+        if rng is not None:
+            dth += rng.normal(0, arw * np.sqrt(dt), dth.shape)
+            dv += rng.normal(0, vrw * np.sqrt(dt), dv.shape)
+        return GPS_T0 + t1, np.full(len(ks), dt), dth, dv
+
+    def body_state(self, t):
+        """(p, q xyzw, v) of the body at relative time t (truth)."""
+        p, R = self.body_pose(np.array([t]))
+        h = 1e-5
+        p1, _ = self.body_pose(np.array([t + h]))
+        p0, _ = self.body_pose(np.array([t - h]))
+        return p[0], R_to_quat_xyzw(R[0]), (p1[0] - p0[0]) / (2 * h)
+
     def imu_pose7(self, stamp, rng=None, sigma_p=0.0, sigma_r=0.0):
         """IMU pose block [t, q xyzw] at absolute time `stamp`, optionally perturbed."""
         p, R = self.body_pose(np.array([stamp - GPS_T0]))
