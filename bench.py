@@ -411,6 +411,9 @@ def run_ours(args, rank, world, local_rank):
         ctx = None
         batched = batched_roofline(seq, frames, local_rank)
 
+    shim = None
+    if rank == 0 and world == 1 and not args.no_shim:
+        shim = shim_figure(seq, frames, min(args.steps, 200), max(args.warmup, PREFILL_KEYS + 2))
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline(args.config, frames, seq, steps=5)
@@ -442,6 +445,7 @@ def run_ours(args, rank, world, local_rank):
             "roofline": roof,
             "stages": stages,
             "roofline_batched": batched,
+            "shim": shim,
             "cpu_baseline": cpu,
             "workload_sizes": {"Q": sess.last["assoc"].n_queries if "assoc" in sess.last else None,
                                "M": last_m},
@@ -454,6 +458,48 @@ def run_ours(args, rank, world, local_rank):
 
 
 # ------------------------------------------------------------------------------------------------
+def write_shim_frames(path, seq, frames, n_frames):
+    """frames.bin for tools/shim_bench: header, then per frame its scalars, INS window and raw 32-byte records."""
+    from fflins import synth
+    with open(path, "wb") as f:
+        np.array([0x46464c53, n_frames, seq.n, seq.W, seq.filter_num, FRAMES_PER_KEY], np.int32).tofile(f)
+        np.asarray(seq.R_bl, np.float64).reshape(-1).tofile(f)
+        np.asarray(seq.t_bl, np.float64).tofile(f)
+        np.asarray(seq.ext7(), np.float64).tofile(f)
+        for fr in frames[:n_frames]:
+            sc = np.zeros(19)
+            sc[0], sc[1] = fr["stamp"], fr["td"]
+            sc[2:5], sc[5:8], sc[8:15] = fr["v"], fr["omega"], fr["pose7"]
+            sc[15], sc[16] = fr["start"], fr["end"]
+            sc.tofile(f)
+            for k in ("ins_t", "ins_p", "ins_q"):
+                np.ascontiguousarray(fr[k], np.float64).tofile(f)
+            synth.pack_aos(fr["xyzi"], fr["time"]).tofile(f)
+
+
+def shim_figure(seq, frames, steps, warmup):
+    """The drop-in figure: the reference's call sequence through the C++ shim (tools/shim_bench.cc), pageable buffers."""
+    exe = os.path.join(ROOT, "tools", "shim_bench")
+    if not os.path.exists(exe):
+        return {"unavailable": "tools/shim_bench not built (python -c 'import __graft_entry__ as g; g.build()')"}
+    import tempfile
+    n_frames = min(len(frames), 5 * FRAMES_PER_KEY * 5)
+    out = {}
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "frames.bin")
+        write_shim_frames(path, seq, frames, n_frames)
+        for mode in ("queued", "sync"):
+            try:
+                txt = subprocess.check_output([exe, path, str(steps), str(warmup)] + (["sync"] if mode == "sync" else []),
+                                              text=True, timeout=300)
+                out[mode] = json.loads(txt.strip().splitlines()[-1])
+            except Exception as e:   # noqa: BLE001
+                out[mode] = {"error": str(e)[:200]}
+    out["note"] = ("lidar::LidarMap / LidarWindowEvaluator from ff-lins_b200/shim/lidar_shim.h in the reference's call order "
+                   "(ff_lins.cc:236-283,349-367), pageable PointCloudCustom buffers, wall clock, host->device copies included")
+    return out
+
+
 def batched_roofline(seq, frames, device, batch=26):
     """Per-kernel HBM roofline on launches large enough to be bandwidth-bound: `batch`
     AT128 frames concatenated into one 4 M-point launch (what `batch` sessions sharing a GPU would
@@ -621,6 +667,7 @@ def main():
     ap.add_argument("--repeats", type=int, default=0, help="timed repetitions of --steps steps (default: enough for 0.25 s)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-batched", action="store_true", help="skip the batched per-kernel roofline pass")
+    ap.add_argument("--no-shim", action="store_true", help="skip the drop-in (C++ shim) figure")
     ap.add_argument("--frames", type=int, default=None, help="distinct synthetic frames to cycle over (default: one lap)")
     ap.add_argument("--prefill", type=int, default=None, help="untimed keyframes that fill the window (default 11)")
     ap.add_argument("--settle", type=float, default=0.5, help="seconds of untimed steps before the timed region (0 for profiler runs)")

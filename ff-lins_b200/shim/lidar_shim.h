@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <deque>
 #include <fstream>
+#include <mutex>
 #include <sstream>
 #include <stdexcept>
 #include <string>
@@ -27,6 +28,13 @@ namespace fflins_shim {
 inline fflins_ctx *&default_ctx() {
     static fflins_ctx *c = nullptr;
     return c;
+}
+
+// Ceres evaluates residual blocks from several threads (optimizer.cc:103, num_threads = 8); calls on one context are
+// serialised (include/fflins.h), so every adapter takes this lock around its C-ABI call.
+inline std::mutex &ctx_mutex() {
+    static std::mutex m;
+    return m;
 }
 
 inline fflins_pose toAbi(const Pose &p) {
@@ -231,6 +239,19 @@ public:
     }
     void adoptPose(const fflins_pose &p) { pose_ = fflins_shim::fromAbi(p); }
     fflins_ctx *context() const { return ctx_; }
+    // the raw cloud's storage is page-locked once, so that the frame can be QUEUED (out = NULL) and its copy run at PCIe
+    // rate behind the caller's back; unlocked again when the frame goes away
+    bool pinRaw() {
+        if (!raw_pinned_ && raw_pointcloud_ && !raw_pointcloud_->points.empty())
+            raw_pinned_ = fflins_host_register(raw_pointcloud_->points.data(), raw_pointcloud_->points.size() * sizeof(PointTypeCustom)) == FFLINS_OK;
+        return raw_pinned_;
+    }
+    ~LidarFrame() {
+        if (raw_pinned_) {
+            if (ctx_) fflins_synchronize(ctx_);   // a queued copy may still read the buffer
+            fflins_host_unregister(raw_pointcloud_->points.data());
+        }
+    }
 
 private:
     void pushMotion() {
@@ -270,6 +291,7 @@ private:
     double point_std_ = 0.1;
     bool is_in_map_{false};
     bool is_keyframe_{false};
+    bool raw_pinned_{false};
     ulong_t id_;
     fflins_ctx *ctx_ = nullptr;
 };
@@ -364,9 +386,15 @@ public:
         fflins_frame_info info;
         auto raw = frame->rawPointCloud();
         frame->bind(ctx_, cfg_.point_to_plane_std);
+        // Asynchronous by default: the frame is only QUEUED (out = NULL) — its raw records are page-locked in place, the
+        // copy and the kernel chain are issued with the next frames of the keyframe interval, and the counts are read back
+        // by whatever needs them first (an accessor, mergeNonKeyframes, updateLidarFeaturesInMap). The frame pose, which
+        // is all LINS needs at once (keyframeSelection), is evaluated on the host inside the call.
+        const bool async = async_frames_ && frame->pinRaw();
         int rc = fflins_frame_process_aos(ctx_, frame->id(), raw->points.data(), (int32_t) raw->size(), ins_t_.data(),
                                           ins_p_.data(), ins_q_.data(), (int32_t) w, &ext, frame->stamp(),
-                                          frame->timeDelay(), &info);
+                                          frame->timeDelay(), async ? nullptr : &info);
+        if (rc == FFLINS_OK && async) rc = fflins_frame_get_pose(ctx_, frame->id(), &info.pose);
         if (rc != FFLINS_OK) {
             std::fprintf(stderr, "[fflins] lidarFrameProcessing: %s\n", fflins_last_error(ctx_));
             return false;
@@ -375,6 +403,8 @@ public:
         frame->invalidate(true, false);
         return true;
     }
+    // false: every lidarFrameProcessing call returns with the frame complete (pageable staged copy, one synchronisation)
+    void setAsyncFrames(bool on) { async_frames_ = on; }
     // static overload, lidar_map.cc:275-324
     bool lidarFrameProcessing(const IntegrationState &state, const Pose &pose_b_l, LidarFrame::Ptr frame) {
         auto raw = frame->rawPointCloud();
@@ -432,10 +462,11 @@ public:
         std::vector<uint64_t> ids;
         for (auto &f : nonkeyframes) ids.push_back(f->id());
         fflins_frame_info info;
-        fflins_shim::check(ctx_, fflins_keyframe_merge(ctx_, keyframe->id(), ids.data(), (int32_t) ids.size(), &info), "mergeNonKeyframes");
+        fflins_shim::check(ctx_, fflins_keyframe_merge(ctx_, keyframe->id(), ids.data(), (int32_t) ids.size(), async_frames_ ? nullptr : &info),
+                           "mergeNonKeyframes");
         keyframe->invalidate(true, false);
         for (auto &f : nonkeyframes) {
-            f->pointCloudMapFull(); // keep a host copy alive if a caller still wants it
+            if (keep_nonkey_clouds_) f->pointCloudMapFull(); // keep a host copy alive if a caller still wants it (viewer)
             fflins_frame_release(ctx_, f->id());
             f->bind(nullptr, cfg_.point_to_plane_std);
         }
@@ -448,7 +479,7 @@ public:
     // lidar_map.cc:128-173 / 175-188
     void removeOldestLidarFrame() {
         marginalized_frame_ = keyframes_.front();
-        marginalized_frame_->pointCloudMapFull();
+        if (keep_nonkey_clouds_) marginalized_frame_->pointCloudMapFull();
         keyframes_.pop_front();
         uint64_t id;
         fflins_keyframe_remove_oldest(ctx_, &id);
@@ -476,6 +507,7 @@ public:
     // ---- additions that make the batched device path reachable from the reference's call sites ----
     fflins_ctx *context() { return ctx_; }
     // Optimizer::updateParametersFromOptimizer (optimizer.cc:203-218): one launch for the whole window
+    void setKeepReleasedClouds(bool on) { keep_nonkey_clouds_ = on; }
     void reprojectWorld(const std::vector<Pose> &poses) {
         std::vector<uint64_t> ids;
         std::vector<fflins_pose> ps;
@@ -502,6 +534,8 @@ private:
     LidarFrame::Ptr marginalized_frame_;
     std::vector<double> ins_t_, ins_p_, ins_q_;
     std::vector<double> statistic_parameters_;
+    bool async_frames_ = true;
+    bool keep_nonkey_clouds_ = false;   // the reference keeps them for the viewer / PCD dump only (lidar_map.cc:140-170)
     double stat_average_features_ = 0, stat_keyframe_interval_ = 0, stat_keyframe_translation_ = 0, stat_keyframe_rotation_ = 0;
     int stat_newest_features_ = 0;
 };
@@ -555,6 +589,7 @@ public:
     // parameters = {pose_ref[7], pose_cur[7], extrinsic[7], td[1]}; jacobians / jacobians[i] may be null
     bool Evaluate(const double *const *parameters, double *residuals, double **jacobians) const override {
         double J[22];
+        std::lock_guard<std::mutex> lk(fflins_shim::ctx_mutex());
         int rc = fflins_factor_eval_batch(ctx_, 1, point_, normal_, &norm_inverse_, &std_, motion_, parameters[0], parameters[1],
                                           parameters[2], parameters[3][0], 0, residuals, jacobians ? J : nullptr);
         if (rc != FFLINS_OK) return false;
@@ -592,16 +627,190 @@ public:
         out.b.assign(19 * n, 0);
         out.cost.assign(2 * n, 0);
         out.n_res.assign(n, 0);
+        std::lock_guard<std::mutex> lk(fflins_shim::ctx_mutex());
         return fflins_window_eval(ctx_, (int32_t) n, ref_ids.data(), pose_refs.data(), pose_cur, ext, td, flags, out.H.data(),
                                   out.b.data(), out.cost.data(), out.n_res.data()) == FFLINS_OK;
     }
     bool chi2(const std::vector<uint64_t> &ref_ids, const std::vector<double> &pose_refs, const double pose_cur[7],
               const double ext[7], double td, double threshold, std::vector<int32_t> &n_outliers) {
         n_outliers.assign(ref_ids.size(), 0);
+        std::lock_guard<std::mutex> lk(fflins_shim::ctx_mutex());
         return fflins_window_chi2(ctx_, (int32_t) ref_ids.size(), ref_ids.data(), pose_refs.data(), pose_cur, ext, td, threshold,
                                   n_outliers.data()) == FFLINS_OK;
     }
 
 private:
     fflins_ctx *ctx_;
+};
+
+// ---- Ceres-shaped adapters for one (ref, cur) pair --------------------------------------------------
+// Both keep LidarFactor's parameter-block signature {pose_ref[7], pose_cur[7], extrinsic[7], td[1]} and are added with
+// loss = nullptr: HuberLoss(1.0) is applied per residual inside the kernel, exactly as ResidualBlockInfo::Evaluate does
+// (residual_block_info.cc:49-77) — Ceres itself would apply a loss per residual BLOCK, which is not what the reference's
+// one-block-per-point construction means.
+#if defined(FFLINS_SHIM_USE_CERES)
+typedef ceres::CostFunction LidarPairFactorBase;
+#else
+namespace fflins_shim {
+class LidarPairFactorBase {   // the slice of ceres::CostFunction a dynamically sized factor uses
+public:
+    virtual ~LidarPairFactorBase() {}
+    virtual bool Evaluate(const double *const *parameters, double *residuals, double **jacobians) const = 0;
+    int num_residuals() const { return num_residuals_; }
+    const std::vector<int32_t> &parameter_block_sizes() const { return sizes_; }
+
+protected:
+    void set_num_residuals(int n) { num_residuals_ = n; }
+    std::vector<int32_t> *mutable_parameter_block_sizes() { return &sizes_; }
+
+private:
+    int num_residuals_ = 0;
+    std::vector<int32_t> sizes_;
+};
+} // namespace fflins_shim
+typedef fflins_shim::LidarPairFactorBase LidarPairFactorBase;
+#endif
+
+// (i) batched factor: num_residuals = P (the pair's valid residuals, fixed at construction: PLANE and not outlier,
+// optimizer.cc:468), one kernel launch per Evaluate for all of them.
+class LidarBatchedFactor : public LidarPairFactorBase {
+public:
+    LidarBatchedFactor(fflins_ctx *ctx, uint64_t ref_id, uint64_t cur_id, uint32_t flags = FFLINS_HUBER)
+        : ctx_(ctx), ref_(ref_id), cur_(cur_id), flags_(flags) {
+        int32_t q = 0;
+        fflins_shim::check(ctx_, fflins_features_download(ctx_, ref_, 0, &q, 0, 0, 0, 0, 0, 0, 0, 0), "features size");
+        std::vector<int8_t> type(q);
+        std::vector<uint8_t> outlier(q);
+        if (q > 0)
+            fflins_shim::check(ctx_, fflins_features_download(ctx_, ref_, q, &q, type.data(), nullptr, outlier.data(), nullptr, nullptr,
+                                                              nullptr, nullptr, nullptr), "features");
+        for (int k = 0; k < q; k++)
+            if (type[k] == FFLINS_FEATURE_PLANE && !outlier[k]) rows_.push_back(k);
+        q_ = q;
+        set_num_residuals((int) rows_.size());
+        *mutable_parameter_block_sizes() = {7, 7, 7, 1};
+    }
+    bool Evaluate(const double *const *parameters, double *residuals, double **jacobians) const override {
+        std::vector<double> r(q_), J(jacobians ? (size_t) 22 * q_ : 0);
+        std::vector<uint8_t> valid(q_);
+        int32_t n_res = 0;
+        {
+            std::lock_guard<std::mutex> lk(fflins_shim::ctx_mutex());
+            if (fflins_factor_eval(ctx_, ref_, cur_, parameters[0], parameters[1], parameters[2], parameters[3][0], flags_, q_, &n_res,
+                                   valid.data(), r.data(), jacobians ? J.data() : nullptr, nullptr, nullptr, nullptr) != FFLINS_OK)
+                return false;
+        }
+        const int P = (int) rows_.size();
+        const int off[4] = {0, 7, 14, 21}, len[4] = {7, 7, 7, 1};
+        for (int i = 0; i < P; i++) {
+            const int k  = rows_[i];
+            residuals[i] = valid[k] ? r[k] : 0.0;   // a residual culled after construction contributes nothing
+            if (!jacobians) continue;
+            for (int b = 0; b < 4; b++)
+                if (jacobians[b])
+                    for (int c = 0; c < len[b]; c++) jacobians[b][(size_t) i * len[b] + c] = valid[k] ? J[(size_t) 22 * k + off[b] + c] : 0.0;
+        }
+        return true;
+    }
+
+private:
+    fflins_ctx *ctx_;
+    uint64_t ref_, cur_;
+    uint32_t flags_;
+    int32_t q_ = 0;
+    std::vector<int> rows_;
+};
+
+// (ii) square-root-compressed factor: the kernel returns the pair's robustified H = sum J^T J (19 x 19), b = -sum J^T r and
+// c = sum r^2; with H = V S V^T the factor hands Ceres J' = S^{1/2} V^T (19 rows) and r' = -S^{-1/2} V^T b, plus one
+// Jacobian-free residual sqrt(c - |r'|^2): cost, gradient and Gauss-Newton Hessian are those of the P original residuals
+// (the algebra of MarginalizationInfo::linearization, marginalization_info.cc:93-107). 20 residuals instead of P.
+class LidarSqrtFactor : public LidarPairFactorBase {
+public:
+    LidarSqrtFactor(fflins_ctx *ctx, uint64_t ref_id, uint64_t cur_id, uint32_t flags = FFLINS_HUBER)
+        : ctx_(ctx), ref_(ref_id), cur_(cur_id), flags_(flags) {
+        set_num_residuals(20);
+        *mutable_parameter_block_sizes() = {7, 7, 7, 1};
+    }
+    bool Evaluate(const double *const *parameters, double *residuals, double **jacobians) const override {
+        double H[361], b[19], cost[2];
+        int32_t n_res = 0;
+        {
+            std::lock_guard<std::mutex> lk(fflins_shim::ctx_mutex());
+            if (fflins_factor_eval(ctx_, ref_, cur_, parameters[0], parameters[1], parameters[2], parameters[3][0], flags_, 0, &n_res,
+                                   nullptr, nullptr, nullptr, H, b, cost) != FFLINS_OK)
+                return false;
+        }
+        double w[19], V[361];
+        symEig19(H, w, V);
+        double wmax = 0;
+        for (int k = 0; k < 19; k++) wmax = std::fmax(wmax, w[k]);
+        double rr = 0;
+        for (int k = 0; k < 19; k++) {
+            const bool live = w[k] > 1e-12 * wmax && w[k] > 0;
+            const double sq = live ? std::sqrt(w[k]) : 0.0;
+            double vb = 0;
+            for (int j = 0; j < 19; j++) vb += V[19 * j + k] * b[j];
+            residuals[k] = live ? -vb / sq : 0.0;
+            rr += residuals[k] * residuals[k];
+            if (jacobians) {   // tangent column j of the 19-vector -> block / column of the 7,7,7,1 layout (column 6 = 0)
+                for (int j = 0; j < 19; j++) {
+                    const int blk = j < 18 ? j / 6 : 3, col = j < 18 ? j % 6 : 0, len = blk < 3 ? 7 : 1;
+                    if (jacobians[blk]) jacobians[blk][(size_t) k * len + col] = sq * V[19 * j + k];
+                }
+                for (int blk = 0; blk < 3; blk++)
+                    if (jacobians[blk]) jacobians[blk][(size_t) k * 7 + 6] = 0.0;
+            }
+        }
+        residuals[19] = std::sqrt(std::fmax(cost[1] - rr, 0.0));
+        if (jacobians)
+            for (int blk = 0; blk < 4; blk++)
+                if (jacobians[blk])
+                    for (int c = 0; c < (blk < 3 ? 7 : 1); c++) jacobians[blk][(size_t) 19 * (blk < 3 ? 7 : 1) + c] = 0.0;
+        return true;
+    }
+
+private:
+    // cyclic Jacobi: H = V diag(w) V^T (row-major 19 x 19)
+    static void symEig19(const double *Hin, double *w, double *V) {
+        const int n = 19;
+        double A[361];
+        std::memcpy(A, Hin, sizeof(A));
+        for (int i = 0; i < n * n; i++) V[i] = (i % (n + 1) == 0) ? 1.0 : 0.0;
+        for (int sweep = 0; sweep < 60; sweep++) {
+            double off = 0, diag = 0;
+            for (int i = 0; i < n; i++) {
+                diag += A[n * i + i] * A[n * i + i];
+                for (int j = i + 1; j < n; j++) off += A[n * i + j] * A[n * i + j];
+            }
+            if (off <= 1e-32 * (diag + 1e-300)) break;
+            for (int p = 0; p < n; p++)
+                for (int q = p + 1; q < n; q++) {
+                    const double apq = A[n * p + q];
+                    if (std::fabs(apq) < 1e-300) continue;
+                    const double theta = (A[n * q + q] - A[n * p + p]) / (2 * apq);
+                    const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1));
+                    const double c = 1 / std::sqrt(t * t + 1), s = t * c;
+                    for (int k = 0; k < n; k++) {
+                        const double akp = A[n * k + p], akq = A[n * k + q];
+                        A[n * k + p] = c * akp - s * akq;
+                        A[n * k + q] = s * akp + c * akq;
+                    }
+                    for (int k = 0; k < n; k++) {
+                        const double apk = A[n * p + k], aqk = A[n * q + k];
+                        A[n * p + k] = c * apk - s * aqk;
+                        A[n * q + k] = s * apk + c * aqk;
+                    }
+                    for (int k = 0; k < n; k++) {
+                        const double vkp = V[n * k + p], vkq = V[n * k + q];
+                        V[n * k + p] = c * vkp - s * vkq;
+                        V[n * k + q] = s * vkp + c * vkq;
+                    }
+                }
+        }
+        for (int i = 0; i < n; i++) w[i] = A[n * i + i];
+    }
+    fflins_ctx *ctx_;
+    uint64_t ref_, cur_;
+    uint32_t flags_;
 };

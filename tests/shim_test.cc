@@ -108,7 +108,72 @@ int main() {
     }
     LidarWindowEvaluator::Blocks blk;
     if (!ev.evaluate(ids, poses, pose_cur, extp, td, FFLINS_HUBER, blk)) return 6;
-    std::printf("SHIM_OK keyframes=%d planes=%d residuals=%d factor_max_abs_err=%.3e H00=%.6e\n", n_keys, planes, blk.n_res[0], worst,
-                blk.H[0]);
-    return (planes > 20 && worst < 1e-9 && blk.n_res[0] > 0) ? 0 : 7;
+    // ---- the two Ceres-shaped pair adapters against the per-residual sum -----------------------------
+    // reference: every valid residual through LidarFactor::Evaluate, Huber corrector per residual on the host
+    // (residual_block_info.cc:49-77, here the oracle's restatement), summed into cost / gradient / J^T J over the 19 tangent
+    // columns [ref 6 | cur 6 | ext 6 | td]
+    double Hs[361] = {0}, gs[19] = {0}, cs = 0;
+    int P = 0;
+    for (size_t k = 0; k < feats.size(); k++) {
+        if (feats[k]->featureType() != lidar::LidarFeature::FEATURE_PLANE || feats[k]->isOutlier()) continue;
+        const auto &pt = cur->pointCloudLidar()->points[k];
+        LidarFactor factor(pt, feats[k]->unitNormalVector(), feats[k]->normInverse(), feats[k]->pointStd(), ref->velocity(),
+                           ref->angularVelocity(), ref->timeDelay(), cur->velocity(), cur->angularVelocity(), cur->timeDelay());
+        double r, J[22];
+        double *jac[4] = {J, J + 7, J + 14, J + 21};
+        if (!factor.Evaluate(par, &r, jac)) return 8;
+        orc_huber_correct(1.0, &r, J);
+        double jl[19];
+        for (int a = 0; a < 18; a++) jl[a] = J[7 * (a / 6) + a % 6];
+        jl[18] = J[21];
+        for (int a = 0; a < 19; a++) {
+            gs[a] += jl[a] * r;
+            for (int c = 0; c < 19; c++) Hs[19 * a + c] += jl[a] * jl[c];
+        }
+        cs += r * r;
+        P++;
+    }
+    auto sums = [](const LidarPairFactorBase &f, const double *const *par, double *H, double *g, double *c) -> bool {
+        const int m = f.num_residuals();
+        std::vector<double> r(m), J0(7 * m), J1(7 * m), J2(7 * m), J3(m);
+        double *jac[4] = {J0.data(), J1.data(), J2.data(), J3.data()};
+        if (!f.Evaluate(par, r.data(), jac)) return false;
+        std::fill(H, H + 361, 0.0);
+        std::fill(g, g + 19, 0.0);
+        *c = 0;
+        for (int i = 0; i < m; i++) {
+            double jl[19];
+            for (int a = 0; a < 6; a++) {
+                jl[a]      = J0[7 * i + a];
+                jl[6 + a]  = J1[7 * i + a];
+                jl[12 + a] = J2[7 * i + a];
+            }
+            jl[18] = J3[i];
+            if (J0[7 * i + 6] != 0 || J1[7 * i + 6] != 0 || J2[7 * i + 6] != 0) return false;   // column 6 must be zero
+            for (int a = 0; a < 19; a++) {
+                g[a] += jl[a] * r[i];
+                for (int cc = 0; cc < 19; cc++) H[19 * a + cc] += jl[a] * jl[cc];
+            }
+            *c += r[i] * r[i];
+        }
+        return true;
+    };
+    auto rel = [](const double *a, const double *b, int n) {
+        double num = 0, den = 0;
+        for (int i = 0; i < n; i++) {
+            num = std::fmax(num, std::fabs(a[i] - b[i]));
+            den = std::fmax(den, std::fabs(b[i]));
+        }
+        return den > 0 ? num / den : num;
+    };
+    double Hb[361], gb[19], cb, Hq[361], gq[19], cq;
+    LidarBatchedFactor batched(map.context(), ref->id(), cur->id());
+    LidarSqrtFactor sqrtf(map.context(), ref->id(), cur->id());
+    if (batched.num_residuals() != P || sqrtf.num_residuals() != 20) return 9;
+    if (!sums(batched, par, Hb, gb, &cb) || !sums(sqrtf, par, Hq, gq, &cq)) return 10;
+    const double eb = std::fmax(std::fmax(rel(Hb, Hs, 361), rel(gb, gs, 19)), std::fabs(cb - cs) / cs);
+    const double eq = std::fmax(std::fmax(rel(Hq, Hs, 361), rel(gq, gs, 19)), std::fabs(cq - cs) / cs);
+    std::printf("SHIM_OK keyframes=%d planes=%d residuals=%d factor_max_abs_err=%.3e H00=%.6e adapters: P=%d batched_rel=%.2e sqrt_rel=%.2e\n",
+                n_keys, planes, blk.n_res[0], worst, blk.H[0], P, eb, eq);
+    return (planes > 20 && worst < 1e-9 && blk.n_res[0] > 0 && P > 20 && eb < 1e-9 && eq < 1e-9) ? 0 : 7;
 }

@@ -107,3 +107,17 @@ def test_shim_runs_on_gpu(tmp_path):
                            "-Wl,-rpath," + os.path.join(ROOT, "oracle")])
     out = subprocess.check_output([str(exe)], text=True)
     assert "SHIM_OK" in out, out
+
+
+def test_host_library_exports_every_declared_symbol():
+    """libfflins_host.so (INS mechanization, preintegration, window solver, converters) exports what include/fflins_host.h
+    declares; it has no CUDA dependency."""
+    from fflins import host
+    src = open(os.path.join(ROOT, "include", "fflins_host.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = sorted(set(re.findall(r"\b(fflins_[a-z0-9_]+)\s*\(", src)) - {"fflins_lidar_eval_fn", "fflins_lidar_chi2_fn"})
+    lib = host.load()
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert len(names) >= 35 and not missing, missing
+    needed = subprocess.check_output(["ldd", host.LIB_PATH], text=True)
+    assert "cuda" not in needed.lower()
