@@ -110,6 +110,82 @@ struct QueuedFrame {
     size_t bytes[2];
 };
 
+// Pageable caller buffers: cudaMemcpyAsync stages them through the driver's bounce buffer on the calling thread at
+// 6-8 GB/s (0.6 ms for a 4.9 MB AT128 frame — the whole cost of the drop-in path, which cannot ask the caller for pinned
+// memory). The context copies them into its own page-locked ring with a few helper threads instead and hands the DMA
+// engine a pinned source.
+struct CopyPool {
+    static constexpr int kWorkers = 3;
+    std::thread th[kWorkers];
+    std::mutex mu;
+    std::condition_variable cv, done_cv;
+    const char *src = nullptr;
+    char *dst = nullptr;
+    size_t bytes = 0;
+    unsigned long long job = 0;
+    int pending = 0;
+    bool quit = false, started = false;
+
+    static void slice(int part, int parts, size_t bytes, size_t *lo, size_t *hi) {
+        const size_t chunk = ((bytes + parts - 1) / parts + 4095) & ~(size_t) 4095;
+        *lo = std::min(bytes, chunk * part);
+        *hi = std::min(bytes, chunk * (part + 1));
+    }
+    void start() {
+        if (started) return;
+        started = true;
+        for (int w = 0; w < kWorkers; w++)
+            th[w] = std::thread([this, w] {
+                unsigned long long seen = 0;
+                std::unique_lock<std::mutex> lk(mu);
+                while (true) {
+                    cv.wait(lk, [&] { return quit || job != seen; });
+                    if (quit) return;
+                    seen = job;
+                    size_t lo, hi;
+                    slice(w + 1, kWorkers + 1, bytes, &lo, &hi);
+                    const char *s = src;
+                    char *d       = dst;
+                    lk.unlock();
+                    if (hi > lo) std::memcpy(d + lo, s + lo, hi - lo);
+                    lk.lock();
+                    if (--pending == 0) done_cv.notify_one();
+                }
+            });
+    }
+    void copy(void *d, const void *s, size_t n) {
+        if (n < (1u << 20) || !started) {   // small: not worth a wake-up
+            std::memcpy(d, s, n);
+            return;
+        }
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            src     = (const char *) s;
+            dst     = (char *) d;
+            bytes   = n;
+            pending = kWorkers;
+            job++;
+        }
+        cv.notify_all();
+        size_t lo, hi;
+        slice(0, kWorkers + 1, n, &lo, &hi);
+        std::memcpy((char *) d + lo, (const char *) s + lo, hi - lo);
+        std::unique_lock<std::mutex> lk(mu);
+        done_cv.wait(lk, [&] { return pending == 0; });
+    }
+    void stop() {
+        if (!started) return;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            quit = true;
+        }
+        cv.notify_all();
+        for (auto &t : th)
+            if (t.joinable()) t.join();
+        started = false;
+    }
+};
+
 } // namespace
 
 struct fflins_ctx : public Profiler {
@@ -137,6 +213,12 @@ struct fflins_ctx : public Profiler {
     bool bg_active = false;           // ... and nobody has waited for it yet
     unsigned long long last_main_seq = 0;
     unsigned long long scratch_gen = 0; // bumped whenever the per-item batch scratch is handed out again
+    // page-locked bounce ring for pageable caller buffers (filled by CopyPool, drained by the copy stream)
+    CopyPool copy_pool;
+    unsigned char *h_bounce = nullptr;
+    size_t bounce_cap = 0;
+    int bounce_next = 0;
+    cudaEvent_t bounce_ev[kStageRing] = {};
     // Frame queue: asynchronous fflins_frame_process* calls only stage their inputs; the per-frame kernel chain
     // is launched for all queued frames at once (flush_frames) by the first call that needs a result.
     std::vector<QueuedFrame> fq;
@@ -834,7 +916,39 @@ int enqueue_frame(fflins_ctx *ctx, uint64_t id, const float *xyzi, const double 
         }
         cudaGetLastError();
         if (!pinned) {
-            if ((rc = issue_copies(ctx, q))) return rc;
+            // pageable source: into the page-locked bounce ring with the copy pool (the caller's buffer is free again when
+            // the call returns), then an ordinary pinned copy
+            size_t total = 0;
+            for (int c = 0; c < q.n_copy; c++) total += (q.bytes[c] + 255) & ~(size_t) 255;
+            static const bool no_bounce = getenv("FFLINS_NO_BOUNCE") != nullptr;
+            if (!no_bounce && total >= (1u << 20)) {
+                if (total > ctx->bounce_cap) {
+                    CK(cudaStreamSynchronize(ctx->copy_stream));
+                    if (ctx->h_bounce) cudaFreeHost(ctx->h_bounce);
+                    ctx->bounce_cap = Pool::round(total);
+                    if (cudaMallocHost((void **) &ctx->h_bounce, ctx->bounce_cap * kStageRing) != cudaSuccess) {
+                        ctx->h_bounce   = nullptr;
+                        ctx->bounce_cap = 0;
+                        return fail(ctx, FFLINS_E_NOMEM, "pinned allocation failed");
+                    }
+                    ctx->copy_pool.start();
+                }
+                const int k = ctx->bounce_next;
+                ctx->bounce_next = (k + 1) % kStageRing;
+                if (!ctx->bounce_ev[k]) CK(cudaEventCreateWithFlags(&ctx->bounce_ev[k], cudaEventDisableTiming));
+                else CK(cudaEventSynchronize(ctx->bounce_ev[k]));   // the slot's previous copy has left it
+                unsigned char *slot = ctx->h_bounce + (size_t) k * ctx->bounce_cap;
+                size_t off = 0;
+                for (int c = 0; c < q.n_copy; c++) {
+                    ctx->copy_pool.copy(slot + off, q.h_src[c], q.bytes[c]);
+                    q.h_src[c] = slot + off;
+                    off += (q.bytes[c] + 255) & ~(size_t) 255;
+                }
+                if ((rc = issue_copies(ctx, q))) return rc;
+                CK(cudaEventRecord(ctx->bounce_ev[k], ctx->copy_stream));
+            } else if ((rc = issue_copies(ctx, q))) {
+                return rc;
+            }
             q.n_copy = 0;
         }
     }
@@ -1253,6 +1367,7 @@ void fflins_destroy(fflins_ctx *ctx) {
         }
         ctx->map_worker.join();
     }
+    ctx->copy_pool.stop();
     factor_runtime_destroy(ctx->frt); // retires the resident evaluation kernel first
     ctx->frt = nullptr;
     if (ctx->map_stream) cudaStreamSynchronize(ctx->map_stream);
@@ -1267,6 +1382,9 @@ void fflins_destroy(fflins_ctx *ctx) {
     ctx->frames.clear();
     ctx->pool.destroy();
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+    if (ctx->h_bounce) cudaFreeHost(ctx->h_bounce);
+    for (auto e : ctx->bounce_ev)
+        if (e) cudaEventDestroy(e);
     if (ctx->h_slots) cudaFreeHost(ctx->h_slots);
     if (ctx->h_map_count) cudaFreeHost(ctx->h_map_count);
     if (ctx->h_signal) cudaFreeHost(ctx->h_signal);
@@ -1316,6 +1434,19 @@ int fflins_host_register(void *ptr, uint64_t bytes) {
 int fflins_host_unregister(void *ptr) {
     if (!ptr) return FFLINS_E_INVALID;
     return cudaHostUnregister(ptr) == cudaSuccess ? FFLINS_OK : FFLINS_E_CUDA;
+}
+
+int fflins_host_buffer_done(fflins_ctx *ctx, const void *ptr) {
+    if (!ctx) return FFLINS_E_INVALID;
+    bool queued = false;
+    for (const QueuedFrame &q : ctx->fq)
+        for (int c = 0; c < q.n_copy; c++) queued |= q.h_src[c] == ptr;
+    if (queued) {
+        int rc = flush_frames(ctx);   // its copy has not even been issued yet
+        if (rc) return rc;
+    }
+    CK(cudaStreamSynchronize(ctx->copy_stream));   // every host-to-device copy of point data runs on the copy stream
+    return FFLINS_OK;
 }
 
 int fflins_frame_process(fflins_ctx *ctx, uint64_t frame_id, const float *xyzi, const double *time, int32_t n,

@@ -25,7 +25,7 @@ EXPORTS = [
     "fflins_features_download", "fflins_features_set_outlier", "fflins_factor_eval_batch", "fflins_factor_eval",
     "fflins_window_eval", "fflins_window_chi2", "fflins_profile_enable", "fflins_profile_reset", "fflins_profile_get",
     "fflins_launch_count", "fflins_timer_start", "fflins_timer_stop", "fflins_reproject_window",
-    "fflins_eval_stats_get", "fflins_measure_fp64",
+    "fflins_eval_stats_get", "fflins_measure_fp64", "fflins_host_buffer_done",
 ]
 
 

@@ -228,9 +228,14 @@ public:
     void setNumCovered(int num_covered) { num_covered_ = num_covered; }
 
     // ---- binding to the device session (used by LidarMap) ----
-    void bind(fflins_ctx *ctx, double point_std) {
+    // `alive` is the owning LidarMap's life token: a frame may outlive its map (LINS keeps frames in its own containers)
+    void bind(fflins_ctx *ctx, double point_std, std::shared_ptr<bool> alive = nullptr) {
         ctx_       = ctx;
         point_std_ = point_std;
+        if (ctx) {   // (un-binding keeps the session the raw buffer was queued on: the destructor still has to wait for its copy)
+            sess_  = ctx;
+            alive_ = std::move(alive);
+        }
     }
     void invalidate(bool clouds, bool features) {
         if (clouds)
@@ -248,7 +253,7 @@ public:
     }
     ~LidarFrame() {
         if (raw_pinned_) {
-            if (ctx_) fflins_synchronize(ctx_);   // a queued copy may still read the buffer
+            if (sess_ && alive_ && *alive_) fflins_host_buffer_done(sess_, raw_pointcloud_->points.data());   // a queued copy may still read it
             fflins_host_unregister(raw_pointcloud_->points.data());
         }
     }
@@ -293,7 +298,8 @@ private:
     bool is_keyframe_{false};
     bool raw_pinned_{false};
     ulong_t id_;
-    fflins_ctx *ctx_ = nullptr;
+    fflins_ctx *ctx_ = nullptr, *sess_ = nullptr;
+    std::shared_ptr<bool> alive_;
 };
 
 class PointCloudCommon {
@@ -361,6 +367,7 @@ public:
         if (!fflins_shim::default_ctx()) fflins_shim::default_ctx() = ctx_;
     }
     ~LidarMap() {
+        *alive_ = false;   // frames that outlive the map must not touch the session any more
         if (fflins_shim::default_ctx() == ctx_) fflins_shim::default_ctx() = nullptr;
         fflins_destroy(ctx_);
     }
@@ -385,12 +392,14 @@ public:
         fflins_pose ext = fflins_shim::toAbi(pose_b_l);
         fflins_frame_info info;
         auto raw = frame->rawPointCloud();
-        frame->bind(ctx_, cfg_.point_to_plane_std);
-        // Asynchronous by default: the frame is only QUEUED (out = NULL) — its raw records are page-locked in place, the
-        // copy and the kernel chain are issued with the next frames of the keyframe interval, and the counts are read back
-        // by whatever needs them first (an accessor, mergeNonKeyframes, updateLidarFeaturesInMap). The frame pose, which
-        // is all LINS needs at once (keyframeSelection), is evaluated on the host inside the call.
-        const bool async = async_frames_ && frame->pinRaw();
+        frame->bind(ctx_, cfg_.point_to_plane_std, alive_);
+        // Asynchronous by default: the frame is only QUEUED (out = NULL). The raw records are pageable (a std::vector): the
+        // library copies them into its page-locked ring before the call returns (so the cloud may be freed at once), the
+        // kernel chain is issued with the next frames of the keyframe interval, and the counts are read back by whatever
+        // needs them first (an accessor, mergeNonKeyframes, updateLidarFeaturesInMap). The frame pose, which is all LINS
+        // needs at once (keyframeSelection), is evaluated on the host inside the call. (Page-locking every frame's vector
+        // in place — LidarFrame::pinRaw — was measured at ~3 ms per frame for cudaHostRegister + Unregister: not used.)
+        const bool async = async_frames_;
         int rc = fflins_frame_process_aos(ctx_, frame->id(), raw->points.data(), (int32_t) raw->size(), ins_t_.data(),
                                           ins_p_.data(), ins_q_.data(), (int32_t) w, &ext, frame->stamp(),
                                           frame->timeDelay(), async ? nullptr : &info);
@@ -418,7 +427,7 @@ public:
         double q[4]     = {state.q.x(), state.q.y(), state.q.z(), state.q.w()};
         fflins_pose ext = fflins_shim::toAbi(pose_b_l);
         fflins_frame_info info;
-        frame->bind(ctx_, cfg_.point_to_plane_std);
+        frame->bind(ctx_, cfg_.point_to_plane_std, alive_);
         int rc = fflins_frame_process_static(ctx_, frame->id(), xyzi.data(), (int32_t) raw->size(), state.p.data(), q, &ext, &info);
         if (rc != FFLINS_OK) return false;
         frame->adoptPose(info.pose);
@@ -465,10 +474,13 @@ public:
         fflins_shim::check(ctx_, fflins_keyframe_merge(ctx_, keyframe->id(), ids.data(), (int32_t) ids.size(), async_frames_ ? nullptr : &info),
                            "mergeNonKeyframes");
         keyframe->invalidate(true, false);
+        // frames retired at the previous keyframe go now: their queued copies are long done, so un-pinning them costs nothing
+        retired_.clear();
         for (auto &f : nonkeyframes) {
             if (keep_nonkey_clouds_) f->pointCloudMapFull(); // keep a host copy alive if a caller still wants it (viewer)
             fflins_frame_release(ctx_, f->id());
             f->bind(nullptr, cfg_.point_to_plane_std);
+            retired_.push_back(f);
         }
     }
     // lidar_map.cc:100-126
@@ -530,7 +542,9 @@ public:
 private:
     fflins_config cfg_;
     fflins_ctx *ctx_ = nullptr;
+    std::shared_ptr<bool> alive_ = std::make_shared<bool>(true);
     std::deque<LidarFrame::Ptr> keyframes_;
+    std::vector<LidarFrame::Ptr> retired_;
     LidarFrame::Ptr marginalized_frame_;
     std::vector<double> ins_t_, ins_p_, ins_q_;
     std::vector<double> statistic_parameters_;
@@ -747,7 +761,9 @@ public:
         for (int k = 0; k < 19; k++) wmax = std::fmax(wmax, w[k]);
         double rr = 0;
         for (int k = 0; k < 19; k++) {
-            const bool live = w[k] > 1e-12 * wmax && w[k] > 0;
+            // keep every direction whose Jacobian is above ~1e-10 of the largest (a weakly observed block such as td must keep
+            // its gradient); true null directions (ref t = -cur t) sit at ~1e-16 of the largest eigenvalue
+            const bool live = w[k] > 1e-20 * wmax && w[k] > 0;
             const double sq = live ? std::sqrt(w[k]) : 0.0;
             double vb = 0;
             for (int j = 0; j < 19; j++) vb += V[19 * j + k] * b[j];

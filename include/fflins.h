@@ -114,6 +114,9 @@ int         fflins_synchronize(fflins_ctx *ctx);
 /* Page-lock a caller buffer so the H2D/D2H copies inside the calls run at PCIe rate. */
 int         fflins_host_register(void *ptr, uint64_t bytes);
 int         fflins_host_unregister(void *ptr);
+/* Returns once no queued or in-flight host-to-device copy of this context still reads the caller's point buffer `ptr`
+ * (asynchronous frames): after it the buffer may be freed, overwritten or un-registered. Cheap when the copy is long done. */
+int         fflins_host_buffer_done(fflins_ctx *ctx, const void *ptr);
 
 /* ---- per frame: LidarMap::lidarFrameProcessing (lidar_map.cc:213-273) ------------------ */
 /* `out` may be NULL = ASYNCHRONOUS mode: the call only QUEUES the frame (INS window packed, frame pose

@@ -173,6 +173,8 @@ int main() {
     if (!sums(batched, par, Hb, gb, &cb) || !sums(sqrtf, par, Hq, gq, &cq)) return 10;
     const double eb = std::fmax(std::fmax(rel(Hb, Hs, 361), rel(gb, gs, 19)), std::fabs(cb - cs) / cs);
     const double eq = std::fmax(std::fmax(rel(Hq, Hs, 361), rel(gq, gs, 19)), std::fabs(cq - cs) / cs);
+    std::printf("sqrt factor: H rel %.3e  g rel %.3e  cost rel %.3e | batched: H %.3e g %.3e cost %.3e\n", rel(Hq, Hs, 361), rel(gq, gs, 19),
+                std::fabs(cq - cs) / cs, rel(Hb, Hs, 361), rel(gb, gs, 19), std::fabs(cb - cs) / cs);
     std::printf("SHIM_OK keyframes=%d planes=%d residuals=%d factor_max_abs_err=%.3e H00=%.6e adapters: P=%d batched_rel=%.2e sqrt_rel=%.2e\n",
                 n_keys, planes, blk.n_res[0], worst, blk.H[0], P, eb, eq);
     return (planes > 20 && worst < 1e-9 && blk.n_res[0] > 0 && P > 20 && eb < 1e-9 && eq < 1e-9) ? 0 : 7;

@@ -137,7 +137,7 @@ int main(int argc, char **argv) {
     fflins_eval_stats_get(map.context(), &es);
     std::printf("{\"shim_frames_per_s\": %.2f, \"ms_per_step\": %.4f, \"steps\": %d, \"frames_per_step\": %d, \"points_per_frame\": %d, "
                 "\"mode\": \"%s\", \"keyframes\": %zu, \"resident_evals\": %lld, \"launched_evals\": %lld, \"mean_plane_features\": %.0f}\n",
-                per_key * steps / sec, sec * 1e3 / steps, steps, per_key, n_points, sync ? "synchronous frames (pageable staged copies)" : "queued frames (raw records page-locked in place)",
+                per_key * steps / sec, sec * 1e3 / steps, steps, per_key, n_points, sync ? "synchronous frames" : "queued frames",
                 map.keyframes().size(), (long long) es.resident_evals, (long long) es.launched_evals,
                 (double) features / std::max(1, steps + warmup));
     return 0;
