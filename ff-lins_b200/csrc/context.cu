@@ -584,6 +584,7 @@ int ensure_voxel_work(fflins_ctx *ctx, VoxelWork &vw, void *&base, int n) {
     vw.meta        = (int *) (b + off[6]);
     vw.seg_start   = (uint32_t *) (b + off[7]);
     vw.cap         = cap;
+    vw.fresh       = true;
     return FFLINS_OK;
 }
 int ensure_voxel(fflins_ctx *ctx, int n) { return ensure_voxel_work(ctx, ctx->vox, ctx->vox_base, n); }
@@ -1966,9 +1967,11 @@ int fflins_keyframe_merge(fflins_ctx *ctx, uint64_t key_id, const uint64_t *nonk
             launch_project_batch(ms, B);
             nl++;
         }
-        launch_voxel_downsample(ms, ctx->vox_map, in_ptr, total, (float) ctx->cfg.downsample_size, out_ptr, ctx->d_map_count,
-                                nullptr, &nl, profiling ? ctx : nullptr, "voxel_map");
-        cudaMemcpyAsync(ctx->h_map_count, ctx->d_map_count, sizeof(int), cudaMemcpyDeviceToHost, ms);
+        // the cooperative filter stores the voxel count straight into the pinned word (rc 2); other paths copy it
+        const int vrc = launch_voxel_downsample(ms, ctx->vox_map, in_ptr, total, (float) ctx->cfg.downsample_size, out_ptr,
+                                                ctx->d_map_count, nullptr, &nl, profiling ? ctx : nullptr, "voxel_map", nullptr,
+                                                ctx->h_map_count);
+        if (vrc != 2) cudaMemcpyAsync(ctx->h_map_count, ctx->d_map_count, sizeof(int), cudaMemcpyDeviceToHost, ms);
         if (early) {
             ProfScope ps(profiling ? ctx : nullptr, "hash_build", ms);
             launch_hash_build(ms, out_ptr, total, inv_cell, early_index, ctx->d_map_count);

@@ -15,8 +15,10 @@
 // from the bounding box, the host never synchronises inside the chain).
 #include "kernels.h"
 
+#include <algorithm>
 #include <cfloat>
 #include <cstdio>
+#include <cstdlib>
 
 namespace fflins {
 
@@ -477,6 +479,540 @@ seg_centroid_kernel(const float4 *__restrict__ in, const uint32_t *__restrict__ 
     }
 }
 
+// ---- large clouds: the whole filter in ONE cooperative launch -------------------------------------------
+// The multi-kernel chain above costs 18 launches (3 per digit pass plus a single-CTA scan each) for a keyframe map of
+// 768 k points that the GPU streams in a few microseconds, i.e. it is bound by launch gaps and by the serial scans.
+// vox_coop_kernel runs the same algorithm as a persistent grid of one 512-thread CTA per SM (half the register file,
+// 20 KB of shared memory: the solver-facing kernels of the compute stream still fit next to it) with grid barriers
+// between the phases:   bbox | keys + digit histogram | (rank + scatter | digit histogram)* | head count | centroids.
+//   * CTA c owns the contiguous chunk [c S, (c+1) S) of the (current order of the) items in every phase, so a stable
+//     pass only needs, per digit, the counts of the chunks before it: a [G][bins] table that every CTA sums for itself
+//     after the barrier (no separate scan kernel, no look-back chain: with <= 148 chunks the table is 300 KB);
+//   * digits are 9 bits wide where that saves a pass (18-bit keys of a 60 m scene: two passes instead of three);
+//   * (key, index) travel as one 8-byte item: one scattered store per point and pass;
+//   * the ordered centroid walks the sorted items contiguously: each warp owns a slice, finds the voxel heads from the
+//     keys (no segment table), gathers 64 points per round with the next round's gathers and the indices of the round
+//     after that already in flight, and lets four lanes run the x / y / z / intensity chains in ascending original index.
+// Bit-exactness is unchanged: stable LSD order, sequential fp32 sums, IEEE division.
+constexpr int COOP_THREADS = 512;
+constexpr int COOP_WARPS   = COOP_THREADS / 32;
+constexpr int COOP_ROUNDS  = 8;                           // 32-item rounds per warp and sub-tile (held in registers)
+constexpr int COOP_TILE    = COOP_THREADS * COOP_ROUNDS;  // 4096 items per sub-tile
+constexpr int COOP_BINS    = 512;
+constexpr int COOP_MAXG    = 256;                         // chunks (CTAs) the work tables are sized for
+constexpr int COOP_CEN     = 64;                          // points per centroid round and warp
+constexpr int COOP_STAMPS  = 20;
+
+struct CoopSmem {
+    union {
+        uint16_t warp_hist[COOP_WARPS][COOP_BINS];        // rank + scatter
+        float4 stage[COOP_WARPS][COOP_CEN];               // centroid
+    };
+    uint32_t hist[COOP_BINS];
+    uint32_t offset[COOP_BINS];
+    uint32_t tot[COOP_BINS];
+    float mn[3][COOP_WARPS], mx[3][COOP_WARPS];
+    int bbox[6];
+    int ws[32];
+    int cta_base, cta_total;
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned target) {
+    // every CTA of the (co-resident, cooperative) grid arrives once per barrier; the counter only grows during a launch
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+        } while ((int) (v - target) < 0);
+    }
+    __syncthreads();
+}
+
+struct CoopArgs {
+    const float4 *in;
+    int n;
+    float inv;
+    int *meta;
+    uint2 *kv[2];         // (key, original index) items, ping-pong
+    void *table;          // [G][COOP_BINS] chunk digit counts: uint16_t while a chunk holds < 65536 items, else uint32_t
+    uint32_t *heads;      // [G] chunk head counts, [COOP_MAXG + G][6] chunk bounding boxes behind them
+    unsigned *bar;        // [0] grid barrier counter, [1] exit counter: both zero between launches (the last CTA to leave resets them)
+    float4 *out;
+    int *d_nout;
+    int32_t *keys_out;
+    int *report;          // optional pinned host int: voxel count (zero-copy read-back)
+    unsigned long long *stamps; // optional: globaltimer at the phase boundaries (CTA 0; [COOP_STAMPS - 1]: last CTA to leave)
+};
+
+__device__ __forceinline__ unsigned long long coop_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void coop_exit(const CoopArgs &a) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(a.bar + 1, 1u);
+        if (t == gridDim.x - 1) { // everybody is behind the last barrier
+            a.bar[0] = 0;
+            a.bar[1] = 0;
+            if (a.stamps) a.stamps[COOP_STAMPS - 1] = coop_now();
+        }
+    }
+}
+__device__ __forceinline__ void coop_stamp(const CoopArgs &a, int k) {
+    if (a.stamps && blockIdx.x == 0 && threadIdx.x == 0) a.stamps[k] = coop_now();
+}
+
+template <typename TabT>
+__global__ void __launch_bounds__(COOP_THREADS, 2) vox_coop_kernel(const __grid_constant__ CoopArgs a) {
+    __shared__ CoopSmem S;
+    TabT *table = static_cast<TabT *>(a.table);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int G = gridDim.x, c = blockIdx.x, n = a.n;
+    const int chunk = (((n + G - 1) / G) + 127) & ~127;    // multiple of 128: unrolled warp rounds stay aligned
+    const int lo = min(n, c * chunk), hi = min(n, lo + chunk);
+    unsigned bar_target = 0;
+    int *bbox_tab = (int *) (a.heads + COOP_MAXG);
+    coop_stamp(a, 0);
+    // ---- phase 0: bounding box of the chunk -> table, barrier, every CTA folds the G boxes -------------------------
+    {
+        float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+        for (int base = lo + wid * 128; base < hi; base += COOP_THREADS * 4) {
+            float4 p[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = base + u * 32 + lane;
+                p[u] = i < hi ? __ldg(a.in + i) : make_float4(FLT_MAX, FLT_MAX, FLT_MAX, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (base + u * 32 + lane < hi) {
+                    mn[0] = fminf(mn[0], p[u].x); mx[0] = fmaxf(mx[0], p[u].x);
+                    mn[1] = fminf(mn[1], p[u].y); mx[1] = fmaxf(mx[1], p[u].y);
+                    mn[2] = fminf(mn[2], p[u].z); mx[2] = fmaxf(mx[2], p[u].z);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
+                mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+            }
+            if (lane == 0) { S.mn[k][wid] = mn[k]; S.mx[k][wid] = mx[k]; }
+        }
+        __syncthreads();
+        if (wid == 0) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                float v = lane < COOP_WARPS ? S.mn[k][lane] : FLT_MAX, u = lane < COOP_WARPS ? S.mx[k][lane] : -FLT_MAX;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+                    u = fmaxf(u, __shfl_xor_sync(0xffffffffu, u, o));
+                }
+                if (lane == 0) { bbox_tab[6 * c + k] = f2ord(v); bbox_tab[6 * c + 3 + k] = f2ord(u); }
+            }
+        }
+        bar_target += G;
+        grid_barrier(a.bar, bar_target);
+        if (wid == 0) {
+            int v[6];
+#pragma unroll
+            for (int k = 0; k < 6; k++) v[k] = k < 3 ? f2ord(FLT_MAX) : f2ord(-FLT_MAX);
+            for (int g = lane; g < G; g += 32) {
+#pragma unroll
+                for (int k = 0; k < 6; k++) {
+                    int b = __ldcg(bbox_tab + 6 * g + k);
+                    v[k]  = k < 3 ? min(v[k], b) : max(v[k], b);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                v[k] = k < 3 ? __reduce_min_sync(0xffffffffu, v[k]) : __reduce_max_sync(0xffffffffu, v[k]);
+                if (lane == 0) S.bbox[k] = v[k];
+            }
+        }
+        __syncthreads();
+    }
+    const Grid3 g = make_grid(S.bbox, a.inv);
+    if (c == 0 && tid == 0) {
+        a.meta[M_OVERFLOW] = g.overflow ? 1 : 0;
+        a.meta[M_NBITS]    = g.nbits;
+#pragma unroll
+        for (int k = 0; k < 6; k++) a.meta[M_BBOX + k] = S.bbox[k];
+    }
+    coop_stamp(a, 1);
+    if (g.overflow) { // PCL: "leaf size too small": the input cloud is returned unchanged
+        for (int i = lo + tid; i < hi; i += COOP_THREADS) {
+            a.out[i] = a.in[i];
+            if (a.keys_out) a.keys_out[i] = 0;
+        }
+        if (c == 0 && tid == 0) {
+            *a.d_nout      = n;
+            a.meta[M_NOUT] = n;
+            if (a.report) *a.report = n;
+        }
+        coop_exit(a);
+        return;
+    }
+    const int passes = g.nbits <= 9 ? 1 : g.nbits <= 18 ? 2 : g.nbits <= 27 ? 3 : 4;
+    const int dbits  = (g.nbits + passes - 1) / passes;
+    const int bins   = 1 << dbits;
+    const unsigned dmask = (unsigned) bins - 1u;
+    const unsigned lt    = (1u << lane) - 1u;
+    // ---- phase 1: keys + histogram of digit 0 -------------------------------------------------------------------------
+    S.hist[tid] = 0;
+    __syncthreads();
+    for (int base = lo + wid * 128; base < hi; base += COOP_THREADS * 4) {
+        float4 p[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = base + u * 32 + lane;
+            p[u] = i < hi ? __ldg(a.in + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = base + u * 32 + lane;
+            if (base + u * 32 < hi) { // warp-uniform
+                unsigned d = bins + lane; // invalid lanes: distinct values, never counted
+                if (i < hi) {
+                    int i0k = (int) (floorf(__fmul_rn(p[u].x, a.inv)) - (float) g.min_b[0]);
+                    int i1k = (int) (floorf(__fmul_rn(p[u].y, a.inv)) - (float) g.min_b[1]);
+                    int i2k = (int) (floorf(__fmul_rn(p[u].z, a.inv)) - (float) g.min_b[2]);
+                    int key = i0k + i1k * g.mul1 + i2k * g.mul2;
+                    a.kv[0][i] = make_uint2((uint32_t) key, (uint32_t) i);
+                    if (a.keys_out) a.keys_out[i] = key;
+                    d = (uint32_t) key & dmask;
+                }
+                const unsigned m = __match_any_sync(0xffffffffu, d);
+                if (i < hi && (m & lt) == 0) atomicAdd(&S.hist[d], (uint32_t) __popc(m));
+            }
+        }
+    }
+    __syncthreads();
+    if (tid < bins) table[(size_t) c * COOP_BINS + tid] = (TabT) S.hist[tid];
+    bar_target += G;
+    grid_barrier(a.bar, bar_target);
+    coop_stamp(a, 2);
+    // ---- digit passes ---------------------------------------------------------------------------------------------------
+    int cur = 0;
+    for (int pass = 0; pass < passes; pass++) {
+        const int shift  = pass * dbits;
+        const uint2 *kin = a.kv[cur];
+        uint2 *kout      = a.kv[cur ^ 1];
+        // (a) where this chunk's items of every digit start: digit base + counts of the chunks before this one.
+        //     Thread (q, r): E consecutive digits (one 16-byte load per table row), rows r, r + R, ...
+        {
+            constexpr int E = 16 / (int) sizeof(TabT), QN = COOP_BINS / E, R = COOP_THREADS / QN;
+            const int q = tid % QN, r = tid / QN;
+            uint32_t all[E], before[E];
+#pragma unroll
+            for (int k = 0; k < E; k++) all[k] = before[k] = 0;
+            S.tot[tid]    = 0;
+            S.offset[tid] = 0;
+            __syncthreads();
+            if (E * q < bins) {
+#pragma unroll 4
+                for (int gg = r; gg < G; gg += R) {
+                    const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(table + (size_t) gg * COOP_BINS) + q);
+                    const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int k = 0; k < E; k++) {
+                        const uint32_t x = sizeof(TabT) == 2 ? ((w4[k >> 1] >> ((k & 1) * 16)) & 0xffffu) : w4[k & 3];
+                        all[k] += x;
+                        before[k] += gg < c ? x : 0u;
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < E; k++) {
+                    if (all[k]) atomicAdd(&S.tot[E * q + k], all[k]);
+                    if (before[k]) atomicAdd(&S.offset[E * q + k], before[k]);
+                }
+            }
+            __syncthreads();
+            // exclusive scan of the digit totals over the 512 bins (16 warps)
+            const uint32_t tot = S.tot[tid];
+            uint32_t incl      = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += u;
+            }
+            if (lane == 31) S.ws[wid] = (int) incl;
+            __syncthreads();
+            uint32_t base = 0;
+            for (int w = 0; w < wid; w++) base += (uint32_t) S.ws[w];
+            S.offset[tid] += base + incl - tot;
+            __syncthreads();
+        }
+        coop_stamp(a, 3 + 3 * pass);
+        // (b) stable rank + scatter of the chunk, one sub-tile of COOP_TILE items at a time
+        for (int t0 = lo; t0 < hi; t0 += COOP_TILE) {
+            const int tn     = min(COOP_TILE, hi - t0);
+            const int C      = ((tn + COOP_THREADS - 1) / COOP_THREADS) * 32; // items per warp (contiguous)
+            const int rounds = C / 32;
+            {
+                uint4 z = make_uint4(0, 0, 0, 0);
+                uint4 *wh = reinterpret_cast<uint4 *>(&S.warp_hist[0][0]);
+#pragma unroll
+                for (int i = 0; i < COOP_WARPS * COOP_BINS * 2 / 16 / COOP_THREADS; i++) wh[i * COOP_THREADS + tid] = z;
+            }
+            __syncthreads();
+            uint2 it[COOP_ROUNDS];
+            uint16_t rank[COOP_ROUNDS];
+#pragma unroll
+            for (int r = 0; r < COOP_ROUNDS; r++) {
+                if (r < rounds) {
+                    const int j = wid * C + r * 32 + lane;
+                    it[r]       = j < tn ? __ldcg(kin + t0 + j) : make_uint2(0xffffffffu, 0u);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < COOP_ROUNDS; r++) {
+                if (r < rounds) {
+                    const int j      = wid * C + r * 32 + lane;
+                    const bool valid = j < tn;
+                    const uint32_t d = (it[r].x >> shift) & dmask;
+                    const unsigned m = __match_any_sync(0xffffffffu, valid ? d : COOP_BINS + lane);
+                    const uint16_t prev = S.warp_hist[wid][d];
+                    __syncwarp();
+                    const unsigned rk = __popc(m & lt);
+                    if (valid && rk == 0) S.warp_hist[wid][d] = (uint16_t) (prev + __popc(m));
+                    __syncwarp();
+                    rank[r] = (uint16_t) (prev + rk);
+                }
+            }
+            __syncthreads();
+            {   // per digit: exclusive prefix over the warps
+                uint32_t tot = 0;
+#pragma unroll
+                for (int w = 0; w < COOP_WARPS; w++) {
+                    uint16_t cnt        = S.warp_hist[w][tid];
+                    S.warp_hist[w][tid] = (uint16_t) tot;
+                    tot += cnt;
+                }
+                S.tot[tid] = tot;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < COOP_ROUNDS; r++) {
+                if (r < rounds) {
+                    const int j = wid * C + r * 32 + lane;
+                    if (j < tn) {
+                        const uint32_t d = (it[r].x >> shift) & dmask;
+                        kout[S.offset[d] + S.warp_hist[wid][d] + rank[r]] = it[r];
+                    }
+                }
+            }
+            __syncthreads();
+            S.offset[tid] += S.tot[tid];
+            __syncthreads();
+        }
+        cur ^= 1;
+        bar_target += G;
+        grid_barrier(a.bar, bar_target);
+        coop_stamp(a, 4 + 3 * pass);
+        if (pass + 1 < passes) {
+            // (c) histogram of the next digit over this chunk of the new order
+            const int nshift = (pass + 1) * dbits;
+            const uint2 *kk  = a.kv[cur];
+            S.hist[tid] = 0;
+            __syncthreads();
+            for (int base = lo + wid * 128; base < hi; base += COOP_THREADS * 4) {
+                uint32_t key[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int i = base + u * 32 + lane;
+                    key[u] = i < hi ? __ldcg(&kk[i].x) : 0u;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int i = base + u * 32 + lane;
+                    if (base + u * 32 < hi) {
+                        const unsigned d = i < hi ? ((key[u] >> nshift) & dmask) : (unsigned) (bins + lane);
+                        const unsigned m = __match_any_sync(0xffffffffu, d);
+                        if (i < hi && (m & lt) == 0) atomicAdd(&S.hist[d], (uint32_t) __popc(m));
+                    }
+                }
+            }
+            __syncthreads();
+            if (tid < bins) table[(size_t) c * COOP_BINS + tid] = (TabT) S.hist[tid];
+            bar_target += G;
+            grid_barrier(a.bar, bar_target);
+            coop_stamp(a, 5 + 3 * pass);
+        }
+    }
+    // ---- heads: every warp owns a slice of the sorted items ---------------------------------------------------------------
+    const uint2 *skv = a.kv[cur];
+    const int W     = G * COOP_WARPS;
+    const int slice = (((n + W - 1) / W) + 31) & ~31;
+    const int gw    = c * COOP_WARPS + wid;
+    const int s_lo  = (int) min((long long) n, (long long) gw * slice), s_hi = min(n, s_lo + slice);
+    int heads = 0;
+    {
+        uint32_t carry = s_lo > 0 && s_lo < s_hi ? __ldcg(&skv[s_lo - 1].x) : 0u; // key in front of the slice
+        for (int base = s_lo; base < s_hi; base += 128) {
+            uint32_t key[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = base + u * 32 + lane;
+                key[u] = i < s_hi ? __ldcg(&skv[i].x) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = base + u * 32 + lane;
+                uint32_t kp = __shfl_up_sync(0xffffffffu, key[u], 1);
+                if (lane == 0) kp = carry;
+                const bool h = i < s_hi && (i == 0 || key[u] != kp);
+                heads += __popc(__ballot_sync(0xffffffffu, h));
+                carry = __shfl_sync(0xffffffffu, key[u], 31);
+            }
+        }
+    }
+    if (lane == 0) S.ws[wid] = heads;
+    __syncthreads();
+    if (wid == 0) {
+        int w = lane < COOP_WARPS ? S.ws[lane] : 0, wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int v = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += v;
+        }
+        S.ws[lane] = wi - w;
+        if (lane == 31) a.heads[c] = (uint32_t) wi;
+    }
+    bar_target += G;
+    grid_barrier(a.bar, bar_target);
+    coop_stamp(a, 15);
+    if (wid == 0) {
+        int before = 0, all = 0;
+        for (int gg = lane; gg < G; gg += 32) {
+            int v = (int) __ldcg(a.heads + gg);
+            all += v;
+            before += gg < c ? v : 0;
+        }
+        before = __reduce_add_sync(0xffffffffu, before);
+        all    = __reduce_add_sync(0xffffffffu, all);
+        if (lane == 0) { S.cta_base = before; S.cta_total = all; }
+    }
+    __syncthreads();
+    if (c == 0 && tid == 0) {
+        *a.d_nout      = S.cta_total;
+        a.meta[M_NOUT] = S.cta_total;
+        if (a.report) *a.report = S.cta_total;
+    }
+    // ---- ordered centroids: the warp walks from the first head of its slice to the first head behind it ------------------
+    if (heads > 0) {
+        int slot    = S.cta_base + S.ws[wid];
+        float sum   = 0.f;
+        int count   = 0;
+        bool open   = false, done = false;
+        float *outf = reinterpret_cast<float *>(a.out);
+        const float *st = reinterpret_cast<const float *>(&S.stage[wid][0]) + (lane & 3);
+        auto load_items = [&](int i0, uint2 &x0, uint2 &x1) {
+            x0 = (i0 + lane < n) ? __ldcg(skv + i0 + lane) : make_uint2(0u, 0u);
+            x1 = (i0 + 32 + lane < n) ? __ldcg(skv + i0 + 32 + lane) : make_uint2(0u, 0u);
+        };
+        auto gather = [&](int i0, const uint2 &x0, const uint2 &x1, float4 &p0, float4 &p1) {
+            p0 = (i0 + lane < n) ? __ldg(a.in + x0.y) : make_float4(0.f, 0.f, 0.f, 0.f);
+            p1 = (i0 + 32 + lane < n) ? __ldg(a.in + x1.y) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        int i0 = s_lo;
+        uint2 a0, a1, b0, b1;
+        float4 p0, p1;
+        load_items(i0, a0, a1);
+        load_items(i0 + COOP_CEN, b0, b1);
+        uint32_t kprev_last = (i0 > 0) ? __ldcg(&skv[i0 - 1].x) : 0u;
+        gather(i0, a0, a1, p0, p1);
+        while (!done && i0 < n) {
+            const int cnt = min(COOP_CEN, n - i0);
+            // next round's gathers and the items of the round after that: in flight during this round's accumulation
+            float4 q0, q1;
+            uint2 c0, c1;
+            gather(i0 + COOP_CEN, b0, b1, q0, q1);
+            load_items(i0 + 2 * COOP_CEN, c0, c1);
+            uint32_t kp0 = __shfl_up_sync(0xffffffffu, a0.x, 1), kp1 = __shfl_up_sync(0xffffffffu, a1.x, 1);
+            const uint32_t k0_last = __shfl_sync(0xffffffffu, a0.x, 31);
+            if (lane == 0) { kp0 = kprev_last; kp1 = k0_last; }
+            const bool h0 = lane < cnt && (i0 + lane == 0 || a0.x != kp0);
+            const bool h1 = 32 + lane < cnt && a1.x != kp1;
+            const unsigned hm0 = __ballot_sync(0xffffffffu, h0), hm1 = __ballot_sync(0xffffffffu, h1);
+            kprev_last = __shfl_sync(0xffffffffu, a1.x, 31);
+            S.stage[wid][lane]      = p0;
+            S.stage[wid][32 + lane] = p1;
+            __syncwarp();
+            // Heads of this round as a bit mask. `mine`: heads inside the slice; the first head behind the slice ends the
+            // walk. The voxel carried in from earlier rounds and the one left open at the end of the round are summed by
+            // the whole warp (lane & 3 = channel, adds back to back); the voxels that begin AND end inside the round are
+            // summed concurrently, one lane each (what keeps one-point-per-voxel regions from serialising the warp).
+            const unsigned long long hm = (unsigned long long) hm0 | ((unsigned long long) hm1 << 32);
+            const int limit = max(0, min(cnt, s_hi - i0));
+            const unsigned long long inmask = limit >= 64 ? ~0ull : ((1ull << limit) - 1ull);
+            const unsigned long long mine = hm & inmask, foreign = hm & ~inmask;
+            const int E = foreign ? __ffsll((long long) foreign) - 1 : cnt;   // items [0, E) belong to this warp's voxels
+            auto add_range = [&](int j0, int j1) {
+                int j = j0;
+                for (; j + 8 <= j1; j += 8) {
+                    float v[8];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) v[k] = st[4 * (j + k)];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) sum += v[k];
+                }
+                for (; j < j1; j++) sum += st[4 * j];
+                count += j1 - j0;
+            };
+            if (open) add_range(0, mine ? __ffsll((long long) mine) - 1 : E);
+            if (mine) {
+                if (open) {
+                    if (lane < 4) outf[4 * (size_t) slot + lane] = sum / (float) count;
+                    slot++;
+                }
+                const int last = 63 - __clzll((long long) mine);
+                const unsigned long long mid = mine & ~(1ull << last);
+                if (mid) {
+#pragma unroll
+                    for (int half = 0; half < 2; half++) {
+                        const int pos = 32 * half + lane;
+                        if ((mid >> pos) & 1ull) {
+                            const int nxt = pos + __ffsll((long long) (hm >> (pos + 1))); // a later head exists (at most `last`)
+                            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                            for (int j = pos; j < nxt; j++) {
+                                const float4 v = S.stage[wid][j];
+                                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                            }
+                            const float fc = (float) (nxt - pos);
+                            a.out[slot + __popcll(mid & ((1ull << pos) - 1ull))] = make_float4(acc.x / fc, acc.y / fc, acc.z / fc, acc.w / fc);
+                        }
+                    }
+                    slot += __popcll(mid);
+                }
+                open  = true;
+                sum   = 0.f;
+                count = 0;
+                add_range(last, E);
+            }
+            if (foreign) {
+                if (open && lane < 4) outf[4 * (size_t) slot + lane] = sum / (float) count;
+                open = false;
+                done = true;
+            }
+            __syncwarp();
+            i0 += COOP_CEN;
+            a0 = b0; a1 = b1; b0 = c0; b1 = c1; p0 = q0; p1 = q1;
+        }
+        if (open && lane < 4) outf[4 * (size_t) slot + lane] = sum / (float) count;
+    }
+    coop_stamp(a, 16);
+    coop_exit(a);
+}
+
 // ---- small clouds (n <= SMALL_CAP): the whole filter in ONE CTA ---------------------------------------
 // bbox -> keys -> stable LSD radix sort (8-bit digits, only the passes the key width needs) entirely in
 // shared memory -> heads -> ordered centroid. Replaces 18 launch-latency-bound launches for the per-frame
@@ -750,8 +1286,8 @@ size_t voxel_work_bytes(int cap, size_t *off) {
     off[1] = o; o += al((size_t) cap * 4);
     off[2] = o; o += al((size_t) cap * 4);
     off[3] = o; o += al((size_t) cap * 4);
-    off[4] = o; o += al(256 * nb * 4 + 4096); // + 1024 chunk sums of the multi-CTA scan
-    off[5] = o; o += al(nb2 * 4);
+    off[4] = o; o += al(std::max<size_t>(256 * nb * 4 + 4096, (size_t) COOP_MAXG * COOP_BINS * 4)); // + 1024 chunk sums of the multi-CTA scan; or the cooperative kernel's [G][bins] table
+    off[5] = o; o += al(std::max<size_t>(nb2 * 4, (size_t) COOP_MAXG * 7 * 4)); // chunk head counts + chunk bounding boxes
     off[6] = o; o += al(M_SIZE * 4);
     off[7] = o; o += al(((size_t) cap + 1) * 4);
     return o;
@@ -759,7 +1295,7 @@ size_t voxel_work_bytes(int cap, size_t *off) {
 
 int launch_voxel_downsample(cudaStream_t s, const VoxelWork &w, const float4 *in, int n, float leaf, float4 *out,
                             int *d_nout, int32_t *keys_out, int64_t *launches, Profiler *prof, const char *tag,
-                            const VoxelTail *tail) {
+                            const VoxelTail *tail, int *report) {
     if (n <= 0) {
         cudaMemsetAsync(d_nout, 0, sizeof(int), s);
         return 0;
@@ -785,6 +1321,58 @@ int launch_voxel_downsample(cudaStream_t s, const VoxelWork &w, const float4 *in
                                                                      tail ? *tail : none);
         if (launches) *launches += 1;
         return tail ? 1 : 0;
+    }
+    if (w.fresh) { // barrier counters of a new work buffer
+        cudaMemsetAsync(w.meta, 0, 256, s);
+        w.fresh = false;
+    }
+    static const bool chain_only = getenv("FFLINS_VOXEL_CHAIN") != nullptr;
+    static const bool coop_stamps = getenv("FFLINS_VOXEL_STAMPS") != nullptr;
+    if (!chain_only) {
+        static int sm_count[64] = {0};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!sm_count[dev & 63]) {
+            int coop = 0, sms = 0;
+            cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            sm_count[dev & 63] = coop ? std::min(sms, COOP_MAXG) : -1;
+        }
+        if (sm_count[dev & 63] > 0 && w.keys[1] == w.keys[0] + w.cap && w.idx[1] == w.idx[0] + w.cap) {
+            CoopArgs a{};
+            a.in = in; a.n = n; a.inv = inv; a.meta = w.meta;
+            // keys[0] | keys[1] and idx[0] | idx[1] are adjacent (the capacity is a power of two): two arrays of 8-byte items
+            a.kv[0] = reinterpret_cast<uint2 *>(w.keys[0]); a.kv[1] = reinterpret_cast<uint2 *>(w.idx[0]);
+            a.table = w.block_hist; a.heads = w.block_heads;
+            a.bar = (unsigned *) (w.meta + 14);
+            a.out = out; a.d_nout = d_nout; a.keys_out = keys_out; a.report = report;
+            a.stamps = coop_stamps ? (unsigned long long *) (w.meta + 16) : nullptr;
+            int G = std::min(sm_count[dev & 63], (n + 2047) / 2048);
+            void *args[] = {(void *) &a};
+            const bool narrow = (n + G - 1) / G + 128 < 65536; // chunk digit counts fit 16 bits
+            ProfScope ps(prof, nm("coop"), s);
+            cudaError_t e = cudaLaunchCooperativeKernel(narrow ? (const void *) vox_coop_kernel<uint16_t> : (const void *) vox_coop_kernel<uint32_t>,
+                                                        dim3(G), dim3(COOP_THREADS), args, 0, s);
+            if (e == cudaSuccess) {
+                if (launches) *launches += 1;
+                if (coop_stamps) { // debug: phase durations of this launch (synchronises the stream)
+                    unsigned long long t[COOP_STAMPS] = {0};
+                    cudaStreamSynchronize(s);
+                    cudaMemcpy(t, w.meta + 16, sizeof(t), cudaMemcpyDeviceToHost);
+                    fprintf(stderr, "vox_coop n=%d G=%d ns:", n, G);
+                    unsigned long long prev = t[0];
+                    for (int k = 1; k < COOP_STAMPS - 1; k++)
+                        if (t[k] >= prev && t[k] != 0) {
+                            fprintf(stderr, " [%d]+%llu", k, t[k] - prev);
+                            prev = t[k];
+                        }
+                    fprintf(stderr, " cta0 %llu all %llu\n", prev - t[0], t[COOP_STAMPS - 1] - t[0]);
+                    cudaMemsetAsync(w.meta + 16, 0, sizeof(t), s);
+                }
+                return report ? 2 : 0;
+            }
+            cudaGetLastError(); // fall back to the multi-kernel chain
+        }
     }
     int g = (n + 255) / 256;
     if (g > 148 * 8) g = 148 * 8;

@@ -94,13 +94,15 @@ struct VoxelWork {
     uint32_t *seg_start  = nullptr; // cap + 1
     int      *meta      = nullptr;  // see k_voxel.cu
     int       cap       = 0;        // points capacity
+    mutable bool fresh  = true;     // meta (barrier counters of the cooperative kernel) not yet zeroed
 };
 size_t voxel_work_bytes(int cap, size_t *offsets /*8*/);
 // out must hold n points; *d_nout (device int) receives the voxel count, d_flag receives 1 on the
 // PCL "leaf too small" overflow (output = input). keys_out optional (n).
 // Optional fused tail (single-CTA path only, n <= 4096): world[i] = T * out[i] and report[0..1] =
 // {counters[0], voxel count} stored to pinned host memory. Returns 1 when the tail was fused, 0 when the
-// caller still has to project, < 0 on error.
+// caller still has to project, 2 when the voxel count was stored to `report` (optional pinned host int; large-cloud
+// cooperative kernel only), < 0 on error.
 struct VoxelTail {
     Pose12 T;
     float4 *world;
@@ -109,7 +111,7 @@ struct VoxelTail {
 };
 int launch_voxel_downsample(cudaStream_t s, const VoxelWork &w, const float4 *in, int n, float leaf, float4 *out,
                             int *d_nout, int32_t *keys_out, int64_t *launches, Profiler *prof, const char *tag,
-                            const VoxelTail *tail = nullptr);
+                            const VoxelTail *tail = nullptr, int *report = nullptr);
 
 // ---- K4 keyframe hash insert (replaces ikd_Tree::build, lidar_map.cc:100-118) -------------------------
 // Two-level (plus one) open-addressing index of a keyframe map, all tables with hmask + 1 slots:
