@@ -40,6 +40,27 @@ __global__ void ins_prep_kernel(const __grid_constant__ FrameBatch B) {
     for (int k = 0; k < kRowSize; k++) it.rows[(size_t) i * kRowSize + k] = row[k];
 }
 
+struct alignas(32) F8 {
+    float4 a, b;
+};
+__device__ __forceinline__ F8 ld256_stream(const void *p) {
+    F8 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ double2 ld128_stream_f64(const double *p) {
+    double2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st256(void *p, const F8 &v) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v.a.x), "f"(v.a.y), "f"(v.a.z), "f"(v.a.w),
+                 "f"(v.b.x), "f"(v.b.y), "f"(v.b.z), "f"(v.b.w)
+                 : "memory");
+}
+
 struct RawAoS {   // PointXYZIT, ff_lins/lidar/lidar.h:30-38 (32 bytes)
     float4 xyz_pad;
     float intensity;
@@ -66,25 +87,47 @@ __global__ void __launch_bounds__(128, 8) undistort_kernel(const __grid_constant
     if (n <= 0) return;
     const double t_front = it.t_front, t_back = it.t_back, inv_dt = it.inv_dt;
     const unsigned magic = it.dec_magic;
+    // 32-byte accesses need 32-byte aligned arrays (device pools and page-locked buffers are; a caller's odd pointer is not)
+    const bool wide = ((reinterpret_cast<uintptr_t>(out_full) | (AOS ? reinterpret_cast<uintptr_t>(aos) : (reinterpret_cast<uintptr_t>(xyzi) | (reinterpret_cast<uintptr_t>(time) << 1)))) & 31u) == 0;
     const int pairs      = (n + 1) >> 1;
     for (int pr = blockIdx.x * blockDim.x + threadIdx.x; pr < pairs; pr += gridDim.x * blockDim.x) {
         const int k0 = 2 * pr;
         float4 p[2];
         double tt[2];
         int idx[2];
+        if (wide && k0 + 1 < n) {
+            // one 256-bit request per 32-byte sector (streaming, no L1 allocation): the two points of the pair, or one raw record
+            if (AOS) {
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    const F8 r = ld256_stream(aos + k0 + j);
+                    p[j]       = make_float4(r.a.x, r.a.y, r.a.z, r.b.x);
+                    tt[j]      = __hiloint2double(__float_as_int(r.b.w), __float_as_int(r.b.z)) + td;
+                }
+            } else {
+                const F8 r      = ld256_stream(xyzi + k0);
+                const double2 t = ld128_stream_f64(time + k0);
+                p[0] = r.a; p[1] = r.b;
+                tt[0] = t.x + td; tt[1] = t.y + td;                   // lidar_map.cc:237
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const int k = min(k0 + j, n - 1);
+                if (AOS) {
+                    const float4 *rec = reinterpret_cast<const float4 *>(aos + k);
+                    float4 a          = __ldg(rec);
+                    float4 b          = __ldg(rec + 1);
+                    p[j]              = make_float4(a.x, a.y, a.z, b.x);
+                    tt[j]             = __hiloint2double(__float_as_int(b.w), __float_as_int(b.z)) + td;
+                } else {
+                    p[j]  = __ldg(xyzi + k);
+                    tt[j] = __ldg(time + k) + td;
+                }
+            }
+        }
 #pragma unroll
         for (int j = 0; j < 2; j++) {
-            const int k = min(k0 + j, n - 1);
-            if (AOS) {
-                const float4 *rec = reinterpret_cast<const float4 *>(aos + k);
-                float4 a          = __ldg(rec);
-                float4 b          = __ldg(rec + 1);
-                p[j]              = make_float4(a.x, a.y, a.z, b.x);
-                tt[j]             = __hiloint2double(__float_as_int(b.w), __float_as_int(b.z)) + td;
-            } else {
-                p[j]  = __ldg(xyzi + k);
-                tt[j] = __ldg(time + k) + td;                         // lidar_map.cc:237
-            }
             idx[j] = window_index(ins_t, w, tt[j], t_front, t_back, inv_dt);
             if (idx[j] == 0 && k0 + j < n) atomicAdd(n_fallback, 1);
         }
@@ -119,16 +162,25 @@ __global__ void __launch_bounds__(128, 8) undistort_kernel(const __grid_constant
         // index decimation (lidar_map.cc:249-256): one multiply-high per pair instead of two divisions per point
         int q0 = magic ? (int) __umulhi((unsigned) k0, magic) : k0 / filter_num;
         int r0 = k0 - q0 * filter_num;
+        float4 r[2];
 #pragma unroll
-        for (int j = 0; j < 2; j++) {
-            const int k = k0 + j;
-            if (k >= n) break;
-            float4 r    = make_float4((float) o[j][0], (float) o[j][1], (float) o[j][2], p[j].w);
-            out_full[k] = r;
-            if (out_dec != nullptr && r0 == 0) out_dec[q0] = r;
-            if (++r0 == filter_num) { // the next point starts the next decimation group
-                r0 = 0;
-                q0++;
+        for (int j = 0; j < 2; j++) r[j] = make_float4((float) o[j][0], (float) o[j][1], (float) o[j][2], p[j].w);
+        if (wide && k0 + 1 < n) {
+            F8 v;
+            v.a = r[0]; v.b = r[1];
+            st256(out_full + k0, v);                                   // the pair fills its 32-byte sector in one store
+        } else {
+            out_full[k0] = r[0];
+            if (k0 + 1 < n) out_full[k0 + 1] = r[1];
+        }
+        if (out_dec != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                if (k0 + j < n && r0 == 0) out_dec[q0] = r[j];
+                if (++r0 == filter_num) { // the next point starts the next decimation group
+                    r0 = 0;
+                    q0++;
+                }
             }
         }
     }
