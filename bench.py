@@ -16,6 +16,7 @@ result read-backs inside the timed region).
 Multi-GPU = N independent replicas (one sequence per GPU, no data-path collective; weak scaling).
 """
 import argparse
+import ctypes
 import json
 import math
 import os
@@ -187,6 +188,78 @@ def make_sequence(name, n_frames=None):
 
 
 # ------------------------------------------------------------------------------------------------
+class NativeSession:
+    """tools/session_driver.cc through ctypes: the same call sequence as fflins.pipeline.Session, as a native loop over the
+    C-ABI (the reference's caller is C++; ~40 ctypes calls per keyframe measured the interpreter as much as the library)."""
+
+    class Frame(ctypes.Structure):
+        _fields_ = [("pts", ctypes.c_void_p), ("time", ctypes.c_void_p), ("ins_t", ctypes.c_void_p), ("ins_p", ctypes.c_void_p),
+                    ("ins_q", ctypes.c_void_p), ("n", ctypes.c_int32), ("w", ctypes.c_int32), ("stamp", ctypes.c_double),
+                    ("td", ctypes.c_double), ("v", ctypes.c_double * 3), ("omega", ctypes.c_double * 3),
+                    ("pose7", ctypes.c_double * 7)]
+
+    def __init__(self, ctx, seq, frames_per_key, n_eval, flags):
+        from fflins import api
+        path = os.path.join(ROOT, "tools", "libfflins_driver.so")
+        if not os.path.exists(path):
+            raise RuntimeError("tools/libfflins_driver.so is missing: run __graft_entry__.build()")
+        L = self.L = ctypes.CDLL(path)
+        L.drv_create.restype = ctypes.c_void_p
+        L.drv_create.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                 ctypes.c_uint32, ctypes.c_int, ctypes.c_double]
+        L.drv_run.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+        L.drv_destroy.argtypes = [ctypes.c_void_p]
+        L.drv_error.restype = ctypes.c_char_p
+        L.drv_error.argtypes = [ctypes.c_void_p]
+        L.drv_last_assoc.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.drv_last_nres.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.drv_eval_roundtrip_us.restype = ctypes.c_double
+        L.drv_eval_roundtrip_us.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+        self._pose = api.Pose.make(seq.R_bl, seq.t_bl)
+        self._ext = np.ascontiguousarray(seq.ext7(), np.float64)
+        self.h = L.drv_create(ctx.h, ctypes.addressof(self._pose), self._ext.ctypes.data, frames_per_key, n_eval[0], n_eval[1],
+                              flags, ctx.cfg.window_size, 3.841)
+        self._tables = {}
+
+    def table(self, mode, items):
+        """items: dicts with pts / time (addresses), ins arrays, n, w, stamp, td, v, omega, pose7."""
+        arr = (self.Frame * len(items))()
+        for a, it in zip(arr, items):
+            a.pts, a.time = it["pts"], it.get("time", 0) or 0
+            a.ins_t, a.ins_p, a.ins_q = it["ins_t"].ctypes.data, it["ins_p"].ctypes.data, it["ins_q"].ctypes.data
+            a.n, a.w, a.stamp, a.td = it["n"], it["w"], it["stamp"], it["td"]
+            a.v[:] = list(np.asarray(it["v"], np.float64))
+            a.omega[:] = list(np.asarray(it["omega"], np.float64))
+            a.pose7[:] = list(np.asarray(it["pose7"], np.float64))
+        self._tables[mode] = (arr, len(items), items)
+
+    def run(self, mode, steps):
+        arr, n, _ = self._tables[mode]
+        rc = self.L.drv_run(self.h, 0 if mode == "dev" else 1, arr, n, steps)
+        if rc != 0:
+            raise RuntimeError("session driver: " + self.L.drv_error(self.h).decode())
+
+    def last_assoc(self):
+        a, b = ctypes.c_int32(), ctypes.c_int32()
+        if self.L.drv_last_assoc(self.h, ctypes.byref(a), ctypes.byref(b)) != 0:
+            return None
+        return a.value, b.value
+
+    def last_nres(self):
+        out = (ctypes.c_int32 * 16)()
+        k = self.L.drv_last_nres(self.h, out)
+        return int(sum(out[i] for i in range(min(k, 16))))
+
+    def eval_roundtrip_us(self):
+        v = self.L.drv_eval_roundtrip_us(self.h, 20, 200)
+        return v if v >= 0 else None
+
+    def close(self):
+        if self.h:
+            self.L.drv_destroy(self.h)
+            self.h = None
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import fflins
@@ -225,11 +298,24 @@ def run_ours(args, rank, world, local_rank):
     input_bytes = P * (n * 24 + w * 64)
 
     trace = {} if os.environ.get("FFLINS_TRACE") else None
-    sess = Session(ctx, seq, FRAMES_PER_KEY, N_EVAL, trace=trace, sync_frames=False)
+    native = args.driver == "native" and trace is None
     state = {"frame": 0}
+    if native:
+        sess = None
+        nsess = NativeSession(ctx, seq, FRAMES_PER_KEY, N_EVAL, api.HUBER)
+        common = [{"ins_t": d_["ins_t"], "ins_p": d_["ins_p"], "ins_q": d_["ins_q"], "n": n, "w": w, "stamp": fr["stamp"],
+                   "td": fr["td"], "v": fr["v"], "omega": fr["omega"], "pose7": fr["pose7"]} for d_, fr in zip(dev, frames)]
+        nsess.table("dev", [dict(c_, pts=d_["xyzi"], time=d_["time"]) for c_, d_ in zip(common, dev)])
+        nsess.table("host", [dict(c_, pts=h_["aos"].ctypes.data, time=0) for c_, h_ in zip(common, host)])
+    else:
+        nsess = None
+        sess = Session(ctx, seq, FRAMES_PER_KEY, N_EVAL, trace=trace, sync_frames=False)
 
-    def step(mode):
-        for _ in range(FRAMES_PER_KEY):
+    def step(mode, count=1):
+        if native:
+            nsess.run(mode, count)
+            return
+        for _ in range(count * FRAMES_PER_KEY):
             i = state["frame"] % P
             state["frame"] += 1
             if mode == "dev":
@@ -249,8 +335,7 @@ def run_ours(args, rank, world, local_rank):
         l0 = ctx.launch_count()
         t0 = time.perf_counter()
         ctx.timer_start()
-        for _ in range(steps):
-            step(mode)
+        step(mode, steps)
         dev_ms = ctx.timer_stop()          # CUDA events; the stop event joins the map and copy streams too
         wall_ms = (time.perf_counter() - t0) * 1e3
         launches = ctx.launch_count() - l0
@@ -292,11 +377,17 @@ def run_ours(args, rank, world, local_rank):
         step("host")
     if trace is not None:
         trace.clear()
+    if native and os.environ.get("DRV_TRACE"):
+        print("--- device-resident steps", file=sys.stderr)
+        nsess.L.drv_trace_dump(1)
     e2e_dev_ms, e2e_wall_ms, _, e2e_rep_ms = timed("host", args.steps, repeats)
+    if native and os.environ.get("DRV_TRACE"):
+        print("--- host-buffer steps", file=sys.stderr)
+        nsess.L.drv_trace_dump(1)
     # round trip of one solver-facing evaluation as the host sees it (wall clock around the C-ABI call)
-    rt_us = None
+    rt_us = nsess.eval_roundtrip_us() if native else None
     ids_now = ctx.keyframe_ids()
-    if len(ids_now) >= 2 and "eval_prep" in sess.last:
+    if not native and len(ids_now) >= 2 and "eval_prep" in sess.last:
         td_ = sess.last["eval_prep"][2]
         refs_now = ids_now[:-1]   # (the oldest keyframe of the last association has left the window)
         prep, out_buf = api.Context.prepare_window(refs_now, np.array([sess.key_pose7[r] for r in refs_now]),
@@ -326,11 +417,11 @@ def run_ours(args, rank, world, local_rank):
             step("dev")
         prof = ctx.profile_get()
         ctx.profile_enable(False)
-        assoc = sess.last.get("assoc")
+        la = nsess.last_assoc() if native else ((sess.last["assoc"].n_refs, sess.last["assoc"].n_queries) if "assoc" in sess.last else None)
         kids = ctx.keyframe_ids()
         m_map = ctx.frame_info(kids[-1]).n_map if kids else 0
-        q = assoc.n_queries if assoc else 0
-        n_refs = assoc.n_refs if assoc else 0
+        q = la[1] if la else 0
+        n_refs = la[0] if la else 0
         n_map_in = FRAMES_PER_KEY * n
         ndec = (n + seq.filter_num - 1) // seq.filter_num
         # algorithmic bytes per launch group
@@ -374,7 +465,7 @@ def run_ours(args, rank, world, local_rank):
         except Exception:
             pass
         fp64_peak = ctx.measure_fp64()
-        n_valid = int(np.sum(sess.last["eval"]["n_res"])) if "eval" in sess.last else 0
+        n_valid = nsess.last_nres() if native else (int(np.sum(sess.last["eval"]["n_res"])) if "eval" in sess.last else 0)
         # K6/K7 are fp64 work (~1,000 fp64 flop per residual, reference formulation), everything else moves bytes
         if top in ("factor_eval", "chi2"):
             flop = (1000 if top == "factor_eval" else 150) * n_valid
@@ -401,10 +492,14 @@ def run_ours(args, rank, world, local_rank):
     d2h = FRAMES_PER_KEY * 8 + 4 + 8 * n_refs + sum(N_EVAL) * n_refs * 212 * 8 + 4 * n_refs
     h2d = FRAMES_PER_KEY * (n * 32 + w * 64)   # raw 32-byte records + the packed INS window (read zero-copy)
 
-    last_m = None
+    last_m, q_last = None, None
     if rank == 0:
         kids = ctx.keyframe_ids()
         last_m = ctx.frame_info(kids[-1]).n_map if kids else None
+        la = nsess.last_assoc() if native else ((sess.last["assoc"].n_refs, sess.last["assoc"].n_queries) if "assoc" in sess.last else None)
+        q_last = la[1] if la else None
+    if nsess is not None:
+        nsess.close()
     batched = None
     if rank == 0 and not args.no_batched:
         ctx.close()
@@ -429,6 +524,8 @@ def run_ours(args, rank, world, local_rank):
                      "cpus_bound_per_replica": cpus_bound,
                      "call_mode": "frames and keyframe merge enqueued asynchronously (out = NULL); association, the 15 "
                                   "factor evaluations and the chi2 cull return their results synchronously",
+                     "caller": ("native loop over the C-ABI (tools/session_driver.cc: the call sequence of fflins/pipeline.py, as the "
+                                "reference's C++ fusion thread would issue it)") if native else "fflins/pipeline.py through ctypes",
                      "l2": f"inputs cycle over {P} distinct frames ({input_bytes / 1e6:.0f} MB) > 126 MB L2",
                      "timing": f"{repeats} repetitions of exactly {args.steps} steps each, CUDA events (stop event joins the "
                                f"map and copy streams), max over ranks; the median repetition is reported",
@@ -447,8 +544,7 @@ def run_ours(args, rank, world, local_rank):
             "roofline_batched": batched,
             "shim": shim,
             "cpu_baseline": cpu,
-            "workload_sizes": {"Q": sess.last["assoc"].n_queries if "assoc" in sess.last else None,
-                               "M": last_m},
+            "workload_sizes": {"Q": q_last, "M": last_m},
         }
         print(json.dumps(out))
     if ctx is not None:
@@ -561,6 +657,51 @@ def batched_roofline(seq, frames, device, batch=26):
     res["peak_gbs"] = peak
     res["peak_source"] = peak_src
     res["batch"] = batch
+    # association at the same scale: three keyframe groups of `batch` tiled sessions (two reference maps of ~batch x M
+    # points, ~batch x Q queries), all (ref, query) pairs of the newest keyframe in one fflins_associate call
+    try:
+        ctx.profile_enable(False)
+        groups_n = 3
+        for g in range(groups_n):
+            ids = []
+            for k in range(FRAMES_PER_KEY):
+                fr = frames[(FRAMES_PER_KEY * g + k) % len(frames)]
+                if FRAMES_PER_KEY * g + k < len(big):
+                    _, xyzi, time_ = big[FRAMES_PER_KEY * g + k]
+                else:
+                    tiled = (fr["xyzi"][None, :, :] + shift).reshape(-1, 4).astype(np.float32)
+                    xyzi = torch.from_numpy(np.ascontiguousarray(tiled)).cuda()
+                    time_ = torch.from_numpy(np.tile(fr["time"], batch)).cuda()
+                    big.append((fr, xyzi, time_))
+                fid = 100000 + 100 * g + k
+                ctx.frame_process_dev(fid, xyzi.data_ptr(), time_.data_ptr(), n, fr["ins_t"], fr["ins_p"], fr["ins_q"], pose_bl,
+                                      fr["stamp"], fr["td"])
+                ids.append(fid)
+            ctx.keyframe_merge(ids[-1], ids[:-1])
+            for i in ids[:-1]:
+                ctx.release(i)
+            ctx.keyframe_add(ids[-1])
+            ctx.set_motion(ids[-1], fr["v"], fr["omega"], fr["td"])
+        st = ctx.associate()                     # cold: builds what is still pending
+        ctx.profile_enable(True)
+        ctx.profile_reset()
+        reps_a = 3
+        for _ in range(reps_a):
+            st = ctx.associate()
+        pa = ctx.profile_get()
+        ms_a = pa.get("associate", (0.0, 0))[0] / reps_a
+        pairs = int(st.n_refs) * int(st.n_queries)
+        bytes_a = 152 * pairs
+        res["associate"] = {"refs": int(st.n_refs), "queries": int(st.n_queries), "ref_query_pairs": pairs,
+                            "map_points": [int(ctx.frame_info(i).n_map) for i in ctx.keyframe_ids()[:-1]],
+                            "alg_bytes_per_launch": bytes_a, "ms_per_launch": round(ms_a, 4),
+                            "achieved_gbs": round(bytes_a / (ms_a * 1e-3) / 1e9, 1) if ms_a > 0 else 0.0,
+                            "frac_of_measured_peak": round(bytes_a / (ms_a * 1e-3) / 1e9 / peak, 4) if ms_a > 0 else 0.0,
+                            "pairs_per_us": round(pairs / (ms_a * 1e3), 1) if ms_a > 0 else 0.0,
+                            "note": "integer-issue bound (cell / block / mask bookkeeping), the maps stay L2-resident: the HBM fraction "
+                                    "is reported because the contract asks for it, the rate that matters is (ref, query) pairs per us"}
+    except Exception as e:   # the association figure must not take the other figures down with it
+        res["associate"] = {"error": repr(e)}
     ctx.close()
     return res
 
@@ -665,6 +806,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="at128", choices=["robot", "lili", "ouster64", "at128", "dense"])
     ap.add_argument("--repeats", type=int, default=0, help="timed repetitions of --steps steps (default: enough for 0.25 s)")
+    ap.add_argument("--driver", default="native", choices=["native", "python"],
+                    help="who issues the C-ABI calls of the timed loop: tools/session_driver.cc (default) or fflins/pipeline.py")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-batched", action="store_true", help="skip the batched per-kernel roofline pass")
     ap.add_argument("--no-shim", action="store_true", help="skip the drop-in (C++ shim) figure")

@@ -205,12 +205,18 @@ struct fflins_ctx : public Profiler {
     void *d_stage = nullptr;      // kStageRing x stage_cap bytes
     size_t stage_cap = 0;
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t bg_stream = nullptr;   // kernels of the background frames of a split batch (the copy stream only copies)
     int stage_next = 0;
     cudaEvent_t ev_copied = nullptr;  // copy stream: the host-to-device copies the compute stream waits for are done
-    cudaEvent_t ev_bg_done = nullptr; // copy stream: the background part of the last split batch is done
+    cudaEvent_t ev_bg_done = nullptr; // background stream: the background part of the last split batch is done
+    cudaEvent_t ev_bg_copied = nullptr; // copy stream: the copies of that part have arrived
+    cudaEvent_t ev_join_c = nullptr;
+    cudaEvent_t ev_tl[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // FFLINS_COPY_TIMELINE=1 (debug)
+    bool tl_armed = false;
     cudaEvent_t ev_flush = nullptr;   // compute stream: everything queued before a split batch was flushed
     cudaEvent_t ev_join_a = nullptr, ev_join_b = nullptr; // timer: map / copy stream joins
     bool bg_active = false;           // ... and nobody has waited for it yet
+    bool bg_staged = false;           // ... and it contains host-to-device copies of point data
     unsigned long long last_main_seq = 0;
     unsigned long long scratch_gen = 0; // bumped whenever the per-item batch scratch is handed out again
     // page-locked bounce ring for pageable caller buffers (filled by CopyPool, drained by the copy stream)
@@ -520,6 +526,7 @@ int ensure_stage(fflins_ctx *ctx, size_t bytes) {
     if ((rc = flush_frames(ctx))) return rc;
     if (ctx->d_stage) {
         CK(cudaStreamSynchronize(ctx->copy_stream));
+        CK(cudaStreamSynchronize(ctx->bg_stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
     ctx->pool.release(ctx->d_stage);
@@ -557,7 +564,7 @@ int ensure_ins(fflins_ctx *ctx, int w) {
     ctx->pool.release(ctx->d_tab);
     int cap    = std::max(w, 2048);
     // interval rows (K1 prologue) + time stamps, one set per batch item
-    ctx->d_tab = (double *) ctx->pool.alloc((size_t) kFrameBatch * cap * (kRowSize + 1) * sizeof(double));
+    ctx->d_tab = (double *) ctx->pool.alloc((size_t) kFrameBatch * cap * (kRowSize + 1 + 8) * sizeof(double));
     if (!ctx->d_tab) return fail(ctx, FFLINS_E_NOMEM, "device allocation failed");
     ctx->ins_cap = cap;
     return FFLINS_OK;
@@ -734,7 +741,7 @@ int frame_voxel_tail(fflins_ctx *ctx, cudaStream_t s, const FrameBatch &B) {
 
 // Per-item scratch of batch slot i.
 void item_scratch(fflins_ctx *ctx, int i, FrameItem &it) {
-    it.rows     = ctx->d_tab + (size_t) i * ctx->ins_cap * (kRowSize + 1);
+    it.rows     = ctx->d_tab + (size_t) i * ctx->ins_cap * (kRowSize + 1 + 8);
     it.t_dev    = it.rows + (size_t) ctx->ins_cap * kRowSize;
     it.counters = ctx->d_fscratch + i * kItemScratch;
     it.d_nout   = it.counters + 1;
@@ -766,6 +773,23 @@ int issue_copies(fflins_ctx *ctx, const QueuedFrame &q) {
     return FFLINS_OK;
 }
 
+bool staged_any(const fflins_ctx *ctx) {
+    for (const QueuedFrame &q : ctx->fq)
+        if (q.stage_slot >= 0) return true;
+    return false;
+}
+
+// Frames whose points cross PCIe on the copy stream take their INS window along (64 bytes per entry, in front of the points):
+// the prologue's zero-copy read of the pinned window costs ~8 us on an idle link, but 100+ us while the background copies
+// of the batch saturate it (measured: newest frame copied -> its chain done 150-170 us instead of ~45 us).
+int stage_window(fflins_ctx *ctx, const QueuedFrame &q, FrameItem &it) {
+    if (q.stage_slot < 0 || it.w <= 0) return FFLINS_OK;
+    double *dst = it.t_dev + ctx->ins_cap;   // behind the item's time stamps (item_scratch)
+    CK(cudaMemcpyAsync(dst, it.win, (size_t) it.w * 64, cudaMemcpyHostToDevice, ctx->copy_stream));
+    it.win = dst;
+    return FFLINS_OK;
+}
+
 // Launch the kernel chain of every queued frame: prologue, undistortion, voxel tail — three launches per batch.
 //
 // Batches of two or more frames are SPLIT: the newest frame (the one the caller is about to use: association and
@@ -779,8 +803,15 @@ int flush_frames(fflins_ctx *ctx) {
     const int count = (int) ctx->fq.size();
     const int L     = count - 1;
     int rc;
+    const bool had_bg = ctx->bg_active;
     if ((rc = join_bg(ctx))) return rc; // scratch slots and stream order: one background part at a time
     ctx->scratch_gen++;
+    // the staged windows land in the per-item scratch (stage_window): the copy stream must not overwrite a slot whose
+    // previous prologue may still be reading it (compute stream: slot of the newest frame; background stream: the others)
+    if (staged_any(ctx)) {
+        if (ctx->last_main_seq) CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->batch_ev[ctx->last_main_seq % kGuardRing], 0));
+        if (had_bg && !(count >= 2 && !ctx->prof_on)) CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_bg_done, 0));
+    }
     const bool split = count >= 2 && !ctx->prof_on;
     if (split) CK(cudaEventRecord(ctx->ev_flush, s));
     bool staged = false;
@@ -791,6 +822,7 @@ int flush_frames(fflins_ctx *ctx) {
         for (int i = 0; i < count; i++) {
             B.it[i] = ctx->fq[i].item;
             item_scratch(ctx, i, B.it[i]);
+            if ((rc = stage_window(ctx, ctx->fq[i], B.it[i]))) return rc;
             if ((rc = issue_copies(ctx, ctx->fq[i]))) return rc;
         }
         if (staged) { // the points of these frames travel on the copy stream
@@ -813,15 +845,35 @@ int flush_frames(fflins_ctx *ctx) {
         return rc;
     }
     // newest frame: its copy goes first, the compute stream runs its chain
+    static const bool copy_tl = getenv("FFLINS_COPY_TIMELINE") != nullptr;
+    if (copy_tl) {
+        if (!ctx->ev_tl[0])
+            for (auto &e : ctx->ev_tl) CK(cudaEventCreate(&e));
+        if (ctx->tl_armed) { // the previous batch: where its copies and kernels sat in time (synchronises: debug only)
+            CK(cudaEventSynchronize(ctx->ev_tl[4]));
+            CK(cudaEventSynchronize(ctx->ev_tl[5]));
+            float a = 0, b = 0, c2 = 0, d = 0, e = 0;
+            cudaEventElapsedTime(&a, ctx->ev_tl[0], ctx->ev_tl[1]);
+            cudaEventElapsedTime(&b, ctx->ev_tl[1], ctx->ev_tl[2]);
+            cudaEventElapsedTime(&c2, ctx->ev_tl[2], ctx->ev_tl[3]);
+            cudaEventElapsedTime(&d, ctx->ev_tl[3], ctx->ev_tl[4]);
+            cudaEventElapsedTime(&e, ctx->ev_tl[1], ctx->ev_tl[5]);
+            fprintf(stderr, "[fflins] copy timeline (us): wait+newest copy %.1f | %d background copies %.1f | -> bg kernels start %.1f | bg kernels %.1f | newest copied -> its chain done %.1f\n",
+                    a * 1e3, L, b * 1e3, c2 * 1e3, d * 1e3, e * 1e3);
+        }
+        CK(cudaEventRecord(ctx->ev_tl[0], cs));
+    }
     const QueuedFrame &ql = ctx->fq[L];
+    B.count = 1;
+    B.it[0] = ql.item;
+    item_scratch(ctx, L, B.it[0]);
+    if ((rc = stage_window(ctx, ql, B.it[0]))) return rc;
     if ((rc = issue_copies(ctx, ql))) return rc;
+    if (copy_tl) CK(cudaEventRecord(ctx->ev_tl[1], cs));
     if (ql.stage_slot >= 0) {
         CK(cudaEventRecord(ctx->ev_copied, cs));
         CK(cudaStreamWaitEvent(s, ctx->ev_copied, 0));
     }
-    B.count = 1;
-    B.it[0] = ql.item;
-    item_scratch(ctx, L, B.it[0]);
     unsigned long long seq;
     if ((rc = launch_chain(ctx, s, B, &seq))) return rc;
     ctx->win_guard[ql.wslot] = seq;
@@ -829,30 +881,46 @@ int flush_frames(fflins_ctx *ctx) {
     ql.f->d_ndown       = B.it[0].d_nout;
     ql.f->d_ndown_gen = ctx->scratch_gen;
     if ((rc = frame_voxel_tail(ctx, s, B))) return rc;
-    // the rest: copies and kernels in FIFO order on the copy stream (their scratch slots 0..L-1 were last used by
-    // the previous batch on the compute stream)
-    // pool blocks handed to these frames may have been released by earlier compute-stream work (re-projection, voxel
-    // tail, ...): the copy stream starts behind everything the compute stream had queued when the batch was flushed
-    CK(cudaStreamWaitEvent(cs, ctx->ev_flush, 0));
+    if (copy_tl) CK(cudaEventRecord(ctx->ev_tl[5], s));
+    // the rest: their copies in FIFO order on the copy stream, their kernels on the background stream behind the last of
+    // those copies. The copy stream ONLY copies: were the kernels queued on it as well, the newest frame of the NEXT batch
+    // could not start crossing PCIe until they had run (measured: ~65 us of idle DMA per keyframe on the association's
+    // critical path). Scratch slots 0..L-1 were last used by the previous background part (same stream).
+    // Pool blocks handed to these frames may have been released by earlier compute-stream work (re-projection, voxel
+    // tail, ...): the kernels start behind everything the compute stream had queued when the batch was flushed.
+    cudaStream_t bs = ctx->bg_stream;
+    CK(cudaStreamWaitEvent(bs, ctx->ev_flush, 0));
+    if (had_bg && staged) CK(cudaStreamWaitEvent(cs, ctx->ev_bg_done, 0)); // (see above: scratch slots 0..L-1 of the previous part)
     ctx->last_main_seq = seq;
     FrameBatch G{};
     G.count = L;
     for (int i = 0; i < L; i++) {
         G.it[i] = ctx->fq[i].item;
         item_scratch(ctx, i, G.it[i]);
+        if ((rc = stage_window(ctx, ctx->fq[i], G.it[i]))) return rc;
         if ((rc = issue_copies(ctx, ctx->fq[i]))) return rc;
         ctx->fq[i].f->bg = true;
     }
+    // (pageable sources were copied at call time, also on the copy stream: the event covers them too)
+    CK(cudaEventRecord(ctx->ev_bg_copied, cs));
+    if (copy_tl) CK(cudaEventRecord(ctx->ev_tl[2], cs));
+    CK(cudaStreamWaitEvent(bs, ctx->ev_bg_copied, 0));
+    if (copy_tl) CK(cudaEventRecord(ctx->ev_tl[3], bs));
     unsigned long long seq_bg;
-    if ((rc = launch_chain(ctx, cs, G, &seq_bg))) return rc;
+    if ((rc = launch_chain(ctx, bs, G, &seq_bg))) return rc;
     for (int i = 0; i < L; i++) {
         ctx->win_guard[ctx->fq[i].wslot] = seq_bg;
         if (ctx->fq[i].stage_slot >= 0) ctx->stage_guard[ctx->fq[i].stage_slot] = seq_bg;
     }
     ctx->fq.clear();
-    if ((rc = frame_voxel_tail(ctx, cs, G))) return rc;
-    CK(cudaEventRecord(ctx->ev_bg_done, cs));
+    if ((rc = frame_voxel_tail(ctx, bs, G))) return rc;
+    CK(cudaEventRecord(ctx->ev_bg_done, bs));
+    if (copy_tl) {
+        CK(cudaEventRecord(ctx->ev_tl[4], bs));
+        ctx->tl_armed = true;
+    }
     ctx->bg_active = true;
+    ctx->bg_staged = staged;
     CK(cudaGetLastError());
     return FFLINS_OK;
 }
@@ -1208,7 +1276,10 @@ int fill_factor_pairs(fflins_ctx *ctx, FactorParams &P, int n_pairs, const uint6
     }
     P.n_pairs = n_pairs;
     P.q       = cur->c[FFLINS_CLOUD_LIDAR].n;
-    P.flags   = flags;
+    // copies of the batch's background frames may still be crossing PCIe: the resident kernel polls with one warp only
+    static const int force_quiet = getenv("FFLINS_QUIET") ? atoi(getenv("FFLINS_QUIET")) : -1;   // experiments: 0 never, 1 always
+    const bool quiet = force_quiet >= 0 ? force_quiet != 0 : (ctx->bg_active && ctx->bg_staged);
+    P.flags   = (flags & ~kFlagQuietNext) | (quiet ? kFlagQuietNext : 0u);
     std::memcpy(P.pose_cur, pose_cur, 7 * sizeof(double));
     std::memcpy(P.ext, ext, 7 * sizeof(double));
     P.td = td;
@@ -1288,10 +1359,13 @@ int fflins_create(const fflins_config *cfg, int device, fflins_ctx **out) {
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     if (cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaStreamCreateWithPriority(&ctx->copy_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&ctx->bg_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaStreamCreateWithPriority(&ctx->map_stream, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_main_done, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_bg_done, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_bg_copied, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_join_c, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_flush, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_join_a, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_join_b, cudaEventDisableTiming) != cudaSuccess ||
@@ -1373,6 +1447,7 @@ void fflins_destroy(fflins_ctx *ctx) {
     ctx->frt = nullptr;
     if (ctx->map_stream) cudaStreamSynchronize(ctx->map_stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    if (ctx->bg_stream) cudaStreamSynchronize(ctx->bg_stream);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (Frame *f : ctx->deferred_frames) delete f;
     ctx->deferred_frames.clear();
@@ -1397,6 +1472,8 @@ void fflins_destroy(fflins_ctx *ctx) {
         if (e) cudaEventDestroy(e);
     if (ctx->ev_copied) cudaEventDestroy(ctx->ev_copied);
     if (ctx->ev_bg_done) cudaEventDestroy(ctx->ev_bg_done);
+    if (ctx->ev_bg_copied) cudaEventDestroy(ctx->ev_bg_copied);
+    if (ctx->ev_join_c) cudaEventDestroy(ctx->ev_join_c);
     if (ctx->ev_flush) cudaEventDestroy(ctx->ev_flush);
     if (ctx->ev_join_a) cudaEventDestroy(ctx->ev_join_a);
     if (ctx->ev_join_b) cudaEventDestroy(ctx->ev_join_b);
@@ -1408,6 +1485,7 @@ void fflins_destroy(fflins_ctx *ctx) {
     if (ctx->timer_a) cudaEventDestroy(ctx->timer_a);
     if (ctx->timer_b) cudaEventDestroy(ctx->timer_b);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->bg_stream) cudaStreamDestroy(ctx->bg_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -2194,7 +2272,7 @@ int fflins_factor_eval_batch(fflins_ctx *ctx, int32_t n, const float *point, con
     FactorParams P{};
     P.n_pairs = 1;
     P.q       = n;
-    P.flags   = flags;
+    P.flags   = flags & ~kFlagQuietNext;
     std::memcpy(P.pose_cur, pose_cur, 56);
     std::memcpy(P.ext, ext, 56);
     P.td = td;
@@ -2433,8 +2511,10 @@ int fflins_timer_stop(fflins_ctx *ctx, double *ms) {
     }
     CK(cudaEventRecord(ctx->ev_join_a, ctx->map_stream));
     CK(cudaEventRecord(ctx->ev_join_b, ctx->copy_stream));
+    CK(cudaEventRecord(ctx->ev_join_c, ctx->bg_stream));
     CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join_a, 0));
     CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join_b, 0));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join_c, 0));
     CK(cudaEventRecord(ctx->timer_b, ctx->stream));
     CK(cudaEventSynchronize(ctx->timer_b));
     float f = 0;

@@ -153,7 +153,7 @@ __device__ __forceinline__ void pair_prepare(PairShared &sh) {
     if (tid == 0) {
         const unsigned long long w0 = sh.msg[W_CMD], w1 = sh.msg[W_NP];
         sh.cmd     = (unsigned) w0;
-        sh.flags   = (unsigned) (w0 >> 32);
+        sh.flags   = (unsigned) (w0 >> 32) & ~kFlagQuietNext;
         sh.n_pairs = (int) (unsigned) w1;
         sh.td      = w2d(sh.msg[W_TD]);
         sh.thr     = w2d(sh.msg[W_THR]);
@@ -440,6 +440,8 @@ __global__ void __launch_bounds__(kFactorBlock) resident_kernel(const __grid_con
     Unit *part             = A.d_part + (size_t) pair * kFactorRanks * kRedUnits;
     Unit *res              = A.h_res + (size_t) pair * kRedUnits;
     unsigned long long expect = A.start_seq + 1;
+    unsigned long long *go    = reinterpret_cast<unsigned long long *>(A.d_row + (size_t) kMaxPairs * kRowSlots);   // the spare row
+    bool quiet                = false;
     if (tid == 0) s_gen = ~0ull;
     __syncthreads();
     const bool stamp = A.timeline && pair == 0 && rank == 0 && tid == 0;
@@ -454,7 +456,23 @@ __global__ void __launch_bounds__(kFactorBlock) resident_kernel(const __grid_con
                 // one warp, one 16-byte load per lane and poll: the message is complete when the 26 tags agree
                 const unsigned long long t0 = globaltimer_ns();
                 unsigned long long tag = 0;
-                while (true) {
+                bool idle = false;
+                if (quiet && pair != 0) {
+                    // QUIET mode (asked for by the previous message: host-to-device copies are in flight). Ten warps polling
+                    // host memory cut the DMA rate from 53 to 32 GB/s (tools/h2d_probe.cu: PCIe read requests, not bytes);
+                    // one warp does not. Only row 0 polls the host; the other rows wait in L2 for its "go" and then read
+                    // their own region, which the host wrote BEFORE row 0's.
+                    while (true) {
+                        unsigned long long g;
+                        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(g) : "l"(go) : "memory");
+                        if (g >= expect) break;
+                        if (globaltimer_ns() - t0 > A.idle_ns) {
+                            idle = true;
+                            break;
+                        }
+                    }
+                }
+                while (!idle) {
                     const ulonglong2 v = ld_slot(mail + tid);
                     const unsigned long long t = __shfl_sync(0xffffffffu, v.y, 0);
                     if (__all_sync(0xffffffffu, t >= expect && (tid >= kPairMsg || v.y == t))) {
@@ -462,9 +480,12 @@ __global__ void __launch_bounds__(kFactorBlock) resident_kernel(const __grid_con
                         tag         = t;
                         break;
                     }
-                    if (__any_sync(0xffffffffu, globaltimer_ns() - t0 > A.idle_ns)) break;   // idle: retire
+                    if (__any_sync(0xffffffffu, globaltimer_ns() - t0 > A.idle_ns + (quiet && pair != 0 ? 2000000ull : 0ull))) break;   // idle: retire
                 }
-                if (tid == 0) s_tag = tag;
+                if (tid == 0) {
+                    s_tag = tag;
+                    if (pair == 0 && tag) asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(go), "l"(tag) : "memory");
+                }
             }
             __syncthreads();
             if (stamp) {
@@ -474,6 +495,7 @@ __global__ void __launch_bounds__(kFactorBlock) resident_kernel(const __grid_con
             const unsigned long long tag = s_tag;
             unsigned cmd                 = tag ? (unsigned) sh.msg[W_CMD] : kCmdRetire;
             if (cmd == kCmdQuit) cmd = kCmdRetire;
+            quiet = tag && (sh.msg[W_CMD] >> 63);   // how to wait for the NEXT message
             if (cmd != kCmdRetire) {
                 const unsigned long long gen = sh.msg[W_NP] >> 32;
                 if (gen != s_gen) {   // new keyframe: this pair's part of the setup from the host ring (one more round trip)
@@ -734,7 +756,7 @@ inline void put_slot(ulonglong2 *slot, unsigned long long w, unsigned long long 
 
 // One mailbox region per pair: the 19 header words and the pair's own reference pose.
 void post_message(FactorRuntime *rt, const FactorMsg &m, int n_pairs, unsigned long long tag) {
-    for (int p = 0; p < n_pairs; p++) {
+    for (int p = n_pairs - 1; p >= 0; p--) {   // row 0's region LAST: in quiet mode the other rows read theirs once it has arrived
         ulonglong2 *reg = rt->h_mail + (size_t) p * kPairSlots;
         for (int i = 0; i < kMsgHead; i++) put_slot(reg + i, m.w[i], tag);
         for (int i = 0; i < 7; i++) put_slot(reg + kMsgHead + i, m.w[kMsgHead + 7 * p + i], tag);

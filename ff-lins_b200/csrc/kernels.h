@@ -239,6 +239,9 @@ struct FactorSetup {
     FactorSetupPair pair[kMaxRefs];
 };
 enum { kCmdEval = 1, kCmdChi2 = 2, kCmdQuit = 3 };
+// internal flag bit (never an API flag): while host-to-device copies are in flight only ONE warp of the resident kernel polls
+// host memory for the next message (k_factor.cu, quiet mode)
+constexpr uint32_t kFlagQuietNext = 1u << 31;
 // word 0: cmd | flags << 32     word 1: n_pairs | setup generation << 32     word 2: td     word 3: chi2 threshold
 // word 4: completion value (signal[pair] = seq)   5..11 pose_cur   12..18 ext   19 + 7 i .. pose_ref[i]
 // A window holds at most kMaxRefs keyframes, i.e. kMaxRefs - 1 references: 19 + 7 * 15 = 124 words, so that the

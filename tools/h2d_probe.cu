@@ -1,0 +1,70 @@
+// h2d_probe.cu — does a resident kernel that polls pinned host memory slow the host-to-device DMA down?
+// Times 5 x 4.9 MB page-locked copies (one keyframe interval of raw AT128 records) back to back on a copy stream
+//   (a) alone, (b) while P warps poll DISTINCT pinned 512-byte regions (one 16-byte load per lane, like the resident
+//   evaluation kernel's per-pair mailboxes), (c) polling one 16-byte slot per warp, (d) polling with a pause between polls.
+// Build: nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o tools/h2d_probe tools/h2d_probe.cu
+#include <cuda_runtime.h>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { std::fprintf(stderr, "%s: %s\n", #x, cudaGetErrorString(e)); std::exit(1); } } while (0)
+
+__global__ void poller(const ulonglong2 *mail, volatile int *stop, int lanes, int pause_ns, unsigned long long *polls) {
+    const int lane = threadIdx.x & 31;
+    const ulonglong2 *mine = mail + (size_t) blockIdx.x * 32;
+    unsigned long long n = 0, acc = 0;
+    while (!*stop) {
+        if (lane < lanes) {
+            ulonglong2 v;
+            asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(mine + lane) : "memory");
+            acc += v.x + v.y;
+        }
+        n++;
+        if (pause_ns) __nanosleep(pause_ns);
+    }
+    if (threadIdx.x == 0) polls[blockIdx.x] = n + (acc & 1);
+}
+
+int main() {
+    const size_t bytes = 153600 * 32;
+    const int copies = 5, reps = 40;
+    char *h, *d;
+    CK(cudaMallocHost(&h, bytes * copies));
+    CK(cudaMalloc(&d, bytes * copies));
+    ulonglong2 *mail;
+    int *stop;
+    unsigned long long *polls;
+    CK(cudaMallocHost(&mail, 64 * 32 * 16));
+    CK(cudaMallocHost(&stop, 64));
+    CK(cudaMallocManaged(&polls, 64 * 8));
+    cudaStream_t cs, ks;
+    CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ks, cudaStreamNonBlocking));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    struct Cfg { int warps, lanes, pause; const char *name; };
+    const Cfg cfgs[] = {{0, 0, 0, "alone"}, {10, 32, 0, "10 warps x 512 B, back to back"}, {10, 1, 0, "10 warps x 16 B, back to back"},
+                        {10, 32, 1000, "10 warps x 512 B, 1 us pause"}, {10, 32, 4000, "10 warps x 512 B, 4 us pause"},
+                        {1, 32, 0, "1 warp x 512 B, back to back"}, {15, 32, 0, "15 warps x 512 B, back to back"}};
+    for (const Cfg &c : cfgs) {
+        *stop = 0;
+        if (c.warps) poller<<<c.warps, 32, 0, ks>>>(mail, stop, c.lanes, c.pause, polls);
+        float best = 1e9f, sum = 0;
+        for (int r = 0; r < reps; r++) {
+            CK(cudaEventRecord(e0, cs));
+            for (int k = 0; k < copies; k++) CK(cudaMemcpyAsync(d + k * bytes, h + k * bytes, bytes, cudaMemcpyHostToDevice, cs));
+            CK(cudaEventRecord(e1, cs));
+            CK(cudaEventSynchronize(e1));
+            float ms;
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            best = ms < best ? ms : best;
+            sum += ms;
+        }
+        *stop = 1;
+        CK(cudaStreamSynchronize(ks));
+        std::printf("%-36s 5 x 4.9 MB: best %.1f us (%.1f GB/s), mean %.1f us (%.1f GB/s)%s\n", c.name, best * 1e3, bytes * copies / best / 1e6,
+                    sum / reps * 1e3, bytes * copies / (sum / reps) / 1e6, "");
+    }
+    return 0;
+}
