@@ -121,3 +121,17 @@ def test_host_library_exports_every_declared_symbol():
     assert len(names) >= 35 and not missing, missing
     needed = subprocess.check_output(["ldd", host.LIB_PATH], text=True)
     assert "cuda" not in needed.lower()
+
+
+def test_native_session_driver_builds_and_exports():
+    """tools/session_driver.cc — the native caller bench.py hands its timed loop to — links against the C-ABI only."""
+    so = os.path.join(ROOT, "tools", "libfflins_driver.so")
+    if not os.path.exists(so):
+        subprocess.check_call([GXX, "-std=c++17", "-O2", "-shared", "-fPIC", "-o", so, os.path.join(ROOT, "tools", "session_driver.cc"),
+                               "-L", os.path.join(ROOT, "ff-lins_b200"), "-lfflins_b200", "-Wl,-rpath,$ORIGIN/../ff-lins_b200"])
+    lib = C.CDLL(so)
+    for name in ("drv_create", "drv_run", "drv_destroy", "drv_error", "drv_last_assoc", "drv_last_nres", "drv_last_blocks",
+                 "drv_eval_roundtrip_us", "drv_trace_dump"):
+        assert hasattr(lib, name), name
+    src = open(os.path.join(ROOT, "tools", "session_driver.cc")).read()
+    assert "cuda" not in src.lower() and "oracle" not in src.lower()

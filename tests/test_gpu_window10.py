@@ -300,3 +300,65 @@ def test_end_to_end_flip_counts(oracle, name, frames_per_key):
           f"kNN 5-tuple {flips_idx} of {feats} (ref, query) pairs")
     assert flips_q <= 3 and flips_type <= max(5, feats // 500) and flips_idx <= max(10, feats // 200)
     c.close()
+
+
+# ------------------------------------------------------------------------------------------------ native caller of bench.py
+def test_native_session_driver_issues_the_same_calls():
+    """tools/session_driver.cc (what bench.py times) against fflins/pipeline.py (the readable statement of the call sequence):
+    the same frames through two contexts must leave bit-identical evaluation blocks and association counts."""
+    import ctypes
+    import bench
+    import fflins
+    from fflins import api, synth
+    from fflins.pipeline import Session
+    seq = synth.Sequence("robot", n_points=8000)
+    frames = [seq.frame(i) for i in range(12)]
+    for fr in frames:
+        fr["pose7"] = seq.imu_pose7(fr["stamp"])
+    K, steps = 3, 4
+    # Python session, synchronous frames on host buffers
+    c1 = fflins.Context(fflins.default_config(point_filter_num=seq.filter_num, window_size=3))
+    s1 = Session(c1, seq, K, (2, 1), sync_frames=False)
+    for i in range(K * steps):
+        fid, _ = s1.process_frame(frames[i])
+        s1.after_frame(fid, frames[i])
+    want = {k: np.array(s1.last["eval"][k], copy=True) for k in ("H", "b", "cost", "n_res")}
+    a1 = s1.last["assoc"]
+    # native driver, device-resident inputs
+    import torch
+    c2 = fflins.Context(fflins.default_config(point_filter_num=seq.filter_num, window_size=3))
+    ns = bench.NativeSession(c2, seq, K, (2, 1), api.HUBER)
+    keep, items = [], []
+    for fr in frames:
+        x = torch.from_numpy(np.ascontiguousarray(fr["xyzi"])).cuda()
+        t = torch.from_numpy(np.ascontiguousarray(fr["time"])).cuda()
+        ins = [np.ascontiguousarray(fr[k], np.float64) for k in ("ins_t", "ins_p", "ins_q")]
+        keep.append((x, t, ins))
+        items.append({"pts": x.data_ptr(), "time": t.data_ptr(), "ins_t": ins[0], "ins_p": ins[1], "ins_q": ins[2], "n": len(fr["xyzi"]),
+                      "w": len(ins[0]), "stamp": fr["stamp"], "td": fr["td"], "v": fr["v"], "omega": fr["omega"], "pose7": fr["pose7"]})
+    torch.cuda.synchronize()
+    ns.table("dev", items)
+    ns.run("dev", steps)
+    assert ns.last_assoc() == (a1.n_refs, a1.n_queries)
+    n = a1.n_refs
+    H, b, cost = np.zeros((16, 361)), np.zeros((16, 19)), np.zeros((16, 2))
+    ns.L.drv_last_blocks.argtypes = [ctypes.c_void_p] * 4
+    assert ns.L.drv_last_blocks(ns.h, H.ctypes.data, b.ctypes.data, cost.ctypes.data) == n
+    assert bits_equal(H[:n].reshape(want["H"][:n].shape), want["H"][:n]) and bits_equal(b[:n].reshape(want["b"][:n].shape), want["b"][:n])
+    assert ns.last_nres() == int(np.sum(want["n_res"][:n])) and ns.last_nres() > 100
+    ns.close()
+    c1.close()
+    c2.close()
+
+
+def test_voxel_chain_fallback_still_bit_exact():
+    """The multi-kernel voxel chain (FFLINS_VOXEL_CHAIN=1: the fallback behind the cooperative filter) against the oracle."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, FFLINS_VOXEL_CHAIN="1")
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "vox_bench.py"), "robot", "1"], env=env, capture_output=True, text=True,
+                         timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "bit_exact_vs_oracle=True" in out.stdout and "voxel.radix_sort" in out.stdout

@@ -52,6 +52,7 @@ typedef struct drv_session {
     bool have_assoc;
     int32_t chi2_outliers[16];
     double last_td;
+    int last_pairs;                        // pairs of the last window evaluation (the oldest keyframe may have left since)
     std::vector<double> H, b, cost;
     int32_t n_res[16];
     char err[256];
@@ -73,6 +74,7 @@ drv_session *drv_create(fflins_ctx *ctx, const fflins_pose *pose_bl, const doubl
     s->cursor  = 0;
     s->have_assoc = false;
     s->last_td = 0.0;
+    s->last_pairs = 0;
     s->H.resize(361 * 16);
     s->b.resize(19 * 16);
     s->cost.resize(2 * 16);
@@ -152,6 +154,7 @@ static int keyframe_work(drv_session *s, uint64_t fid, const drv_frame &fr) {
         for (int it = 0; it < s->n1; it++)
             DRV_CK(fflins_window_eval(s->ctx, n, ids, pose_refs, pose_cur, s->ext7, fr.td, s->flags, s->H.data(), s->b.data(), s->cost.data(), s->n_res));
         s->last_td = fr.td;
+        s->last_pairs = n;
         // updateParametersFromOptimizer: re-project every keyframe of the window (optimizer.cc:203-218)
         uint64_t all[16];
         fflins_pose poses[16];
@@ -205,9 +208,17 @@ int drv_last_assoc(const drv_session *s, int32_t *n_refs, int32_t *n_queries) {
 }
 // residual counts of the last window evaluation, one per (ref, cur) pair; returns the pair count
 int drv_last_nres(const drv_session *s, int32_t *out16) {
-    const int n = s->keys.size() >= 2 ? (int) s->keys.size() - 1 : 0;
+    const int n = s->last_pairs;
     for (int i = 0; i < n && i < 16; i++) out16[i] = s->n_res[i];
-    return s->have_assoc ? n : 0;
+    return n;
+}
+// blocks of the last window evaluation (H 361, b 19, cost 2 per pair); returns the pair count
+int drv_last_blocks(const drv_session *s, double *H, double *b, double *cost) {
+    const int n = s->last_pairs;
+    std::memcpy(H, s->H.data(), sizeof(double) * 361 * n);
+    std::memcpy(b, s->b.data(), sizeof(double) * 19 * n);
+    std::memcpy(cost, s->cost.data(), sizeof(double) * 2 * n);
+    return n;
 }
 int drv_keys(const drv_session *s, uint64_t *ids, int cap) {
     int n = 0;
