@@ -46,20 +46,47 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def bind_to_gpu_cpus(index):
-    """Pin this replica (its fusion, helper and sampler threads, and the first touch of its pinned buffers) to the CPUs
-    NVML reports as local to GPU `index`: N replicas on a two-socket host otherwise share cores and cross the socket
-    link with every launch, poll and copy. Best effort."""
+def _physical_cores(cpus):
+    """cpus grouped by physical core (hyper-thread siblings together), cores in ascending order of their first cpu."""
+    cores = {}
+    for c in cpus:
+        key = c
+        try:
+            sib = open(f"/sys/devices/system/cpu/cpu{c}/topology/thread_siblings_list").read().strip()
+            key = sib
+        except OSError:
+            pass
+        cores.setdefault(key, []).append(c)
+    return sorted(cores.values(), key=lambda g: min(g))
+
+
+def bind_to_gpu_cpus(index, world=1):
+    """Pin this replica (its fusion, helper and sampler threads, and the first touch of its pinned buffers) to CPUs local to
+    GPU `index` (NVML): N replicas on a two-socket host otherwise share cores and cross the socket link with every launch,
+    poll and copy. Replicas whose GPUs report the SAME local set (a single-socket host: all of them) split that set's physical
+    cores evenly, so that one replica's spin-polling fusion thread never shares a core with another replica's. Best effort."""
     try:
         import pynvml
         pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(index)
         words = ((os.cpu_count() or 64) + 63) // 64
-        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
-        cpus = [64 * i + b for i, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1]
         allowed = os.sched_getaffinity(0)
-        cpus = [c for c in cpus if c in allowed]
-        if len(cpus) >= 4:
+
+        def local(i):
+            mask = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(i), words)
+            return tuple(c for c in (64 * k + b for k, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1) if c in allowed)
+
+        mine = local(index)
+        if len(mine) < 4:
+            return 0
+        peers = [i for i in range(world) if i == index or local(i) == mine]
+        cpus = list(mine)
+        if len(peers) > 1:
+            cores = _physical_cores(cpus)
+            k = peers.index(index)
+            per = len(cores) // len(peers)
+            if per >= 1:
+                cpus = [c for g in cores[k * per:(k + 1) * per] for c in g]
+        if len(cpus) >= 2:
             os.sched_setaffinity(0, cpus)
             return len(cpus)
     except Exception:
@@ -269,7 +296,7 @@ def run_ours(args, rank, world, local_rank):
     # synthesise the frames first: the worker pool forks, which must happen before CUDA / NCCL start
     seq, frames = make_sequence(args.config, args.frames)
     torch.cuda.set_device(local_rank)
-    cpus_bound = bind_to_gpu_cpus(local_rank) if world > 1 else 0
+    cpus_bound = bind_to_gpu_cpus(local_rank, world) if world > 1 else 0
     dist = None
     if world > 1:
         import torch.distributed as dist

@@ -1,3 +1,4 @@
+#include <atomic>
 // k_assoc.cu — K4 keyframe-map hash insert and K5 frame-to-frame association:
 // exact 5-NN on a device-resident voxel hash + 5-point plane fit + validity tests.
 //
@@ -631,7 +632,7 @@ __global__ void plane_estimation_kernel(const float4 *__restrict__ pts, int n, d
 constexpr size_t kKnnSmem = (size_t) kAssocWarps * (kQueueCap + kCQueueCap) * sizeof(unsigned);
 
 void init_knn_smem() {
-    static bool done[64] = {false};
+    static std::atomic<bool> done[64]; // (zero-initialised; the attribute call is idempotent)
     int dev = 0;
     cudaGetDevice(&dev);
     dev &= 63;

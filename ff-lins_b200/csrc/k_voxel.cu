@@ -15,6 +15,8 @@
 // from the bounding box, the host never synchronises inside the chain).
 #include "kernels.h"
 
+#include <atomic>
+
 #include <algorithm>
 #include <cfloat>
 #include <cstdio>
@@ -1267,7 +1269,7 @@ __global__ void __launch_bounds__(SMALL_THREADS) vox_frame_kernel(const __grid_c
 
 void launch_frame_voxel(cudaStream_t s, const FrameBatch &b) {
     if (b.count <= 0) return;
-    static bool attr_set[64] = {false};
+    static std::atomic<bool> attr_set[64]; // (zero-initialised; contexts on different threads may race here: the call is idempotent)
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr_set[dev & 63]) {
@@ -1308,7 +1310,7 @@ int launch_voxel_downsample(cudaStream_t s, const VoxelWork &w, const float4 *in
         return name;
     };
     if (n <= SMALL_CAP) {
-        static bool attr_set[64] = {false};
+        static std::atomic<bool> attr_set[64]; // (zero-initialised; contexts on different threads may race here: the call is idempotent)
         int dev = 0;
         cudaGetDevice(&dev);
         if (!attr_set[dev & 63]) {
@@ -1329,7 +1331,7 @@ int launch_voxel_downsample(cudaStream_t s, const VoxelWork &w, const float4 *in
     static const bool chain_only = getenv("FFLINS_VOXEL_CHAIN") != nullptr;
     static const bool coop_stamps = getenv("FFLINS_VOXEL_STAMPS") != nullptr;
     if (!chain_only) {
-        static int sm_count[64] = {0};
+        static std::atomic<int> sm_count[64];
         int dev = 0;
         cudaGetDevice(&dev);
         if (!sm_count[dev & 63]) {
@@ -1338,7 +1340,8 @@ int launch_voxel_downsample(cudaStream_t s, const VoxelWork &w, const float4 *in
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
             sm_count[dev & 63] = coop ? std::min(sms, COOP_MAXG) : -1;
         }
-        if (sm_count[dev & 63] > 0 && w.keys[1] == w.keys[0] + w.cap && w.idx[1] == w.idx[0] + w.cap) {
+        const int sm_n = sm_count[dev & 63].load();
+        if (sm_n > 0 && w.keys[1] == w.keys[0] + w.cap && w.idx[1] == w.idx[0] + w.cap) {
             CoopArgs a{};
             a.in = in; a.n = n; a.inv = inv; a.meta = w.meta;
             // keys[0] | keys[1] and idx[0] | idx[1] are adjacent (the capacity is a power of two): two arrays of 8-byte items
@@ -1347,7 +1350,7 @@ int launch_voxel_downsample(cudaStream_t s, const VoxelWork &w, const float4 *in
             a.bar = (unsigned *) (w.meta + 14);
             a.out = out; a.d_nout = d_nout; a.keys_out = keys_out; a.report = report;
             a.stamps = coop_stamps ? (unsigned long long *) (w.meta + 16) : nullptr;
-            int G = std::min(sm_count[dev & 63], (n + 2047) / 2048);
+            int G = std::min(sm_n, (n + 2047) / 2048);
             void *args[] = {(void *) &a};
             const bool narrow = (n + G - 1) / G + 128 < 65536; // chunk digit counts fit 16 bits
             ProfScope ps(prof, nm("coop"), s);
