@@ -96,6 +96,7 @@ struct alignas(32) Unit {
     unsigned long long tag;
 };
 constexpr int kRedUnits = (kRedSize + 2) / 3;   // 71
+constexpr int kPrefetchUnits = 32;              // host read-out of the result units: prefetch distance (32-byte units)
 __device__ __forceinline__ Unit ld_unit(const Unit *p) {
     Unit u;
     asm volatile("ld.volatile.global.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(u.w[0]), "=l"(u.w[1]), "=l"(u.w[2]), "=l"(u.tag) : "l"(p) : "memory");
@@ -693,6 +694,7 @@ struct FactorRuntime {
     // diagnostics (FFLINS_RES_TIMELINE=1): where a resident evaluation's round trip goes
     bool timeline = false;
     long long *h_timeline = nullptr;
+    double tl_spins_late = 0;   // polls that found a unit missing AFTER the first unit of the call had arrived
     double tl_post = 0, tl_wait = 0, tl_unpack = 0, tl_cyc[3] = {0, 0, 0}, tl_r1[3] = {0, 0, 0}, tl_g[3] = {0, 0, 0};
     long long tl_n = 0;
 };
@@ -872,15 +874,19 @@ int resident_call(FactorRuntime *rt, FactorMsg &m, int n, bool chi2, FactorResul
     post_message(rt, m, n, tag);
     if (rt->timeline) tl1 = Clock::now();
     const int per = chi2 ? 1 : kRedUnits;
-    unsigned spins = 0;
+    unsigned spins = 0, late_spins = 0;
     Clock::time_point t0;
     bool timing = false, first = true;
     for (int p = 0; p < n; p++) {
         const Unit *reg = rt->h_res + (size_t) p * kRedUnits;
         double *dst     = rt->h_red + (size_t) p * kRedSize;
         for (int e = 0; e < per; e++) {
-            if ((e & 1) == 0) __builtin_prefetch(reg + e + 8, 0, 0);   // the lines were just written by the device
+            // The lines were just written by the device: every one of them is a cache miss for the host. A short prefetch
+            // distance kept ~4 of the 355 lines of a 10-pair result in flight and the read-out took 5.8 us; 16 lines ahead
+            // (the regions of consecutive pairs are contiguous, so the stream runs on into the next pair) hides most of it.
+            if ((e & 1) == 0) __builtin_prefetch(reg + e + kPrefetchUnits, 0, 3);
             while (!unit_ready(reg + e, tag)) {
+                if (!first) late_spins++;
                 if ((++spins & 0x3ffu) == 0) {
                     if (resident_exited(rt, rt->rows)) {
                         resident_reap(rt); // (joins the kernel: every store it made is visible now)
@@ -934,6 +940,7 @@ int resident_call(FactorRuntime *rt, FactorMsg &m, int n, bool chi2, FactorResul
         rt->tl_post += us(tl1 - tl0);
         rt->tl_wait += us(tl2 - tl1);
         rt->tl_unpack += us(tl3 - tl2);
+        rt->tl_spins_late += late_spins;
         if (!chi2)
             for (int i = 0; i < 3; i++) {
                 rt->tl_cyc[i] += (double) (rt->h_timeline[i + 1] - rt->h_timeline[i]);
@@ -1064,10 +1071,10 @@ void factor_runtime_destroy(FactorRuntime *rt) {
         const double n = (double) rt->tl_n;
         std::fprintf(stderr,
                      "[fflins] resident timeline over %lld calls (us): post %.2f | posted -> first result slot visible %.2f | "
-                     "remaining slots + unpack %.2f\n"
+                     "remaining slots + unpack %.2f (polls that still had to wait in that part: %.1f per call)\n"
                      "[fflins]   row 0, rank 0 (cycles): message seen -> constants ready %.0f | evaluate + SYRK + warp partials %.0f | "
                      "gather partials + host stores %.0f\n",
-                     rt->tl_n, rt->tl_post / n, rt->tl_wait / n, rt->tl_unpack / n, rt->tl_cyc[0] / n, rt->tl_cyc[1] / n, rt->tl_cyc[2] / n);
+                     rt->tl_n, rt->tl_post / n, rt->tl_wait / n, rt->tl_unpack / n, rt->tl_spins_late / n, rt->tl_cyc[0] / n, rt->tl_cyc[1] / n, rt->tl_cyc[2] / n);
         std::fprintf(stderr,
                      "[fflins]   row 0, rank 1 (cycles): message seen -> constants ready %.0f | evaluate %.0f | partial stores %.0f;  "
                      "globaltimer (ns, 1 us ticks): rank 1 sees message %+.0f, rank 1 partials stored %+.0f, rank 0 results stored %+.0f "
