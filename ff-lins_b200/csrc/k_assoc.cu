@@ -211,7 +211,8 @@ __device__ __forceinline__ u64 shell_blocks(int sx, int sy, int sz, int lo, int 
     return in;
 }
 
-constexpr int kAssocWarps = 4;            // warps per CTA
+constexpr int kAssocWarps = 1;            // warps per CTA: one. A CTA keeps its slot until its SLOWEST warp is done and search times vary 20x
+                                          // between queries: with 4 warps per CTA only 16 of the 28 possible warps per SM were active on average
 constexpr int kLookupLanes = 16;           // lanes that fetch an occupancy mask per round (bounds the queues)
 constexpr int kQueueCap   = kLookupLanes * 64; // occupied fine cells of 16 coarse blocks
 constexpr int kCQueueCap  = kLookupLanes * 64; // occupied coarse blocks of 16 super blocks
