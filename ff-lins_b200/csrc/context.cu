@@ -1377,7 +1377,7 @@ int fflins_create(const fflins_config *cfg, int device, fflins_ctx **out) {
     ctx->d_fscratch   = (int *) ctx->pool.alloc(kFrameBatch * kItemScratch * sizeof(int));
     ctx->d_red        = (double *) ctx->pool.alloc((size_t) kMaxRefs * kRedSize * sizeof(double));
     ctx->d_map_count  = (int *) ctx->pool.alloc(64);
-    ctx->d_assoc_counts = (int *) ctx->pool.alloc((kMaxRefs * 2 + 1) * sizeof(int));
+    ctx->d_assoc_counts = (int *) ctx->pool.alloc((kMaxRefs * 2 + 2) * sizeof(int));   // counts, ticket, task counter
     if (!ctx->d_counters || !ctx->d_fscratch || !ctx->d_red || !ctx->d_map_count || !ctx->d_assoc_counts) {
         fflins_destroy(ctx);
         return FFLINS_E_NOMEM;
@@ -1402,7 +1402,7 @@ int fflins_create(const fflins_config *cfg, int device, fflins_ctx **out) {
         fflins_destroy(ctx);
         return FFLINS_E_NOMEM;
     }
-    cudaMemsetAsync(ctx->d_assoc_counts, 0, (kMaxRefs * 2 + 1) * sizeof(int), ctx->stream);
+    cudaMemsetAsync(ctx->d_assoc_counts, 0, (kMaxRefs * 2 + 2) * sizeof(int), ctx->stream);
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
         fflins_destroy(ctx);
         return FFLINS_E_CUDA;

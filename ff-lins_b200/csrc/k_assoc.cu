@@ -1,3 +1,4 @@
+#include <algorithm>
 #include <atomic>
 // k_assoc.cu — K4 keyframe-map hash insert and K5 frame-to-frame association:
 // exact 5-NN on a device-resident voxel hash + 5-point plane fit + validity tests.
@@ -495,33 +496,47 @@ __device__ __forceinline__ void warp_knn5(const HashView &H, float qx, float qy,
 }
 
 // K5a: one warp per (ref, query): exact 5-NN only. Writes nn_idx / nn_d2 (ascending, -1 padded).
+// Persistent grid of one-warp CTAs: every warp draws (ref, query) tasks from a counter until none is left. Search times
+// vary 20x between queries (fast exits against old references, wide searches at the rim of a map); the newest references,
+// which overlap the current frame most and cost 3x as much per query, are handed out FIRST so that the long searches
+// start at once and the short ones fill the tail. (With a (query, ref) grid the block scheduler walked the references
+// oldest first: SMs were active for 52 k of the kernel's 94 k cycles.)
 __global__ void __launch_bounds__(kAssocWarps * 32)
 associate_knn_kernel(const __grid_constant__ AssocParams P, const float4 *__restrict__ cur_world) {
     extern __shared__ unsigned smem_q[]; // per warp: fine-cell queue, then coarse-block queue
     unsigned *my_queue  = smem_q + (threadIdx.x >> 5) * (kQueueCap + kCQueueCap);
     unsigned *my_cqueue = my_queue + kQueueCap;
     const int lane  = threadIdx.x & 31;
-    const int ri = blockIdx.y;                                    // grid: (ceil(q / warps per CTA), refs)
-    const int k  = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (k >= (P.q_dev ? min(*P.q_dev, P.q) : P.q)) return;
-    const AssocRef &ref = P.ref[ri];
-    const long long dbg_t0 = P.dbg_cycles ? clock64() : 0;
-    // world -> ref lidar frame (lidar_map.cc:343-345,355-357): fp64 math, fp32 store
-    float4 rp   = project_rn(ref.T_ref_world.R, ref.T_ref_world.t, __ldg(cur_world + k));
-    u64 best[5] = {kInf, kInf, kInf, kInf, kInf};
-    if (ref.m > 0) {
-        const HashView &H = ref.index;
-        warp_knn5(H, rp.x, rp.y, rp.z, P.inv_cell, P.cell, P.r_max, P.max_d2, my_queue, my_cqueue, best);
-    }
-    if (lane < 5) {
-        u64 b = best[0];
+    const int q     = P.q_dev ? min(*P.q_dev, P.q) : P.q;
+    const int total = q * P.n_refs;
+    int *counter    = P.ticket + 1;              // zero on entry; reset by the plane kernel's last CTA
+    while (true) {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(counter, 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= total) break;
+        const int ri = P.n_refs - 1 - t / q;     // newest reference first
+        const int k  = t - (t / q) * q;
+        const AssocRef &ref = P.ref[ri];
+        const long long dbg_t0 = P.dbg_cycles ? clock64() : 0;
+        // world -> ref lidar frame (lidar_map.cc:343-345,355-357): fp64 math, fp32 store
+        float4 rp   = project_rn(ref.T_ref_world.R, ref.T_ref_world.t, __ldg(cur_world + k));
+        u64 best[5] = {kInf, kInf, kInf, kInf, kInf};
+        if (ref.m > 0) {
+            const HashView &H = ref.index;
+            warp_knn5(H, rp.x, rp.y, rp.z, P.inv_cell, P.cell, P.r_max, P.max_d2, my_queue, my_cqueue, best);
+        }
+        if (lane < 5) {
+            u64 b = best[0];
 #pragma unroll
-        for (int j = 1; j < 5; j++) b = (lane == j) ? best[j] : b;
-        bool have = b != kInf;
-        ref.feat.nn_idx[5 * k + lane] = have ? (int) (unsigned) (b & 0xffffffffu) : -1;
-        ref.feat.nn_d2[5 * k + lane]  = have ? __uint_as_float((unsigned) (b >> 32)) : 0.f;
+            for (int j = 1; j < 5; j++) b = (lane == j) ? best[j] : b;
+            bool have = b != kInf;
+            ref.feat.nn_idx[5 * k + lane] = have ? (int) (unsigned) (b & 0xffffffffu) : -1;
+            ref.feat.nn_d2[5 * k + lane]  = have ? __uint_as_float((unsigned) (b >> 32)) : 0.f;
+        }
+        if (P.dbg_cycles && lane == 0) P.dbg_cycles[ri * P.q + k] = clock64() - dbg_t0;
+        __syncwarp();
     }
-    if (P.dbg_cycles && lane == 0) P.dbg_cycles[ri * P.q + k] = clock64() - dbg_t0;
 }
 
 // K5b: one THREAD per (ref, query): plane fit + validity tests + feature record (lidar_map.cc:371-395).
@@ -579,7 +594,8 @@ associate_plane_kernel(const __grid_constant__ AssocParams P, const float4 *__re
     if (threadIdx.x < 2 * P.n_refs) P.host_counts[threadIdx.x] = atomicExch(P.ref[threadIdx.x >> 1].counts + (threadIdx.x & 1), 0);
     __syncthreads();
     if (threadIdx.x == 0) {
-        *P.ticket = 0;
+        P.ticket[0] = 0;
+        P.ticket[1] = 0;   // task counter of the search kernel
         asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(P.signal), "l"(P.seq) : "memory");
     }
 }
@@ -660,8 +676,18 @@ void launch_hash_build(cudaStream_t s, const float4 *map, int m, float inv_cell,
 void launch_associate(cudaStream_t s, const AssocParams &p, const float4 *cur_world, const float4 *cur_lidar) {
     long long warps = (long long) p.n_refs * p.q;
     if (warps <= 0) return;
-    dim3 grid((p.q + kAssocWarps - 1) / kAssocWarps, p.n_refs);
     init_knn_smem();
+    // one resident wave of one-warp CTAs (8 KB of queues each: 28 per SM), fed from a task counter
+    static std::atomic<int> sms[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!sms[dev & 63]) {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        sms[dev & 63] = n > 0 ? n : 148;
+    }
+    const long long wave = (long long) sms[dev & 63].load() * 28 * kAssocWarps;
+    const int grid = (int) std::min<long long>((warps + kAssocWarps - 1) / kAssocWarps, wave / kAssocWarps);
     associate_knn_kernel<<<grid, kAssocWarps * 32, kKnnSmem, s>>>(p, cur_world);
     dim3 g2((p.q + 127) / 128, p.n_refs);
     associate_plane_kernel<<<g2, 128, 0, s>>>(p, cur_world, cur_lidar);

@@ -170,7 +170,7 @@ struct AssocParams {
     const int *q_dev;      // optional: the query count still sits in device memory (q is then an upper bound)
     // completion: the last CTA of the plane kernel copies the per-ref counts (AssocRef::counts, zero on entry, zero
     // again on exit) to host_counts[2 * ref + {0, 1}] (pinned) and releases *signal = seq behind them
-    int *ticket;           // device int, zero on entry / exit
+    int *ticket;           // two device ints, zero on entry / exit: [0] completion ticket of the plane kernel, [1] task counter of the search
     int *host_counts;
     unsigned long long *signal;
     unsigned long long seq;
