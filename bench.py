@@ -519,10 +519,11 @@ def run_ours(args, rank, world, local_rank):
     d2h = FRAMES_PER_KEY * 8 + 4 + 8 * n_refs + sum(N_EVAL) * n_refs * 212 * 8 + 4 * n_refs
     h2d = FRAMES_PER_KEY * (n * 32 + w * 64)   # raw 32-byte records + the packed INS window (read zero-copy)
 
-    last_m, q_last = None, None
+    last_m, q_last, m_window = None, None, []
     if rank == 0:
         kids = ctx.keyframe_ids()
         last_m = ctx.frame_info(kids[-1]).n_map if kids else None
+        m_window = [int(ctx.frame_info(k).n_map) for k in kids]
         la = nsess.last_assoc() if native else ((sess.last["assoc"].n_refs, sess.last["assoc"].n_queries) if "assoc" in sess.last else None)
         q_last = la[1] if la else None
     if nsess is not None:
@@ -571,7 +572,7 @@ def run_ours(args, rank, world, local_rank):
             "roofline_batched": batched,
             "shim": shim,
             "cpu_baseline": cpu,
-            "workload_sizes": {"Q": q_last, "M": last_m},
+            "workload_sizes": {"Q": q_last, "M": last_m, "M_window": m_window},
         }
         print(json.dumps(out))
     if ctx is not None:
