@@ -525,9 +525,12 @@ __device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned target) {
     if (threadIdx.x == 0) {
         __threadfence();
         atomicAdd(bar, 1u);
-        unsigned v;
+        unsigned v, polls = 0;
         do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+            // every wait is bounded: a peer that never arrives (a faulted launch left the counters behind) must end in an
+            // error the host sees, not in a hung device (~2^27 L2 polls: seconds, a barrier takes microseconds)
+            if (++polls > (1u << 27)) asm volatile("trap;");
         } while ((int) (v - target) < 0);
     }
     __syncthreads();
