@@ -362,3 +362,52 @@ def test_voxel_chain_fallback_still_bit_exact():
                          timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "bit_exact_vs_oracle=True" in out.stdout and "voxel.radix_sort" in out.stdout
+
+
+_QUIET_SCRIPT = r'''
+import os, sys
+import numpy as np
+root = sys.argv[1]
+sys.path.insert(0, os.path.join(root, "ff-lins_b200")); sys.path.insert(0, root); sys.path.insert(0, os.path.join(root, "tests"))
+from fflins import api, synth
+from oracle import pyoracle
+from util import bits_equal, build_window, window_params
+seq = synth.Sequence("robot")
+c = api.Context(api.default_config(point_filter_num=seq.filter_num, window_size=10))
+keys = build_window(c, pyoracle, seq, n_keys=6, frames_per_key=2)
+c.associate()
+refs = [k["id"] for k in keys[:-1]]
+rng = np.random.default_rng(3)
+n_res = 0
+for it in range(40):
+    pose_refs, pose_cur, ext, td = window_params(seq, keys, rng)
+    s0 = c.eval_stats()
+    a = c.window_eval(refs, pose_refs, pose_cur, ext, td, 1)
+    a = {k: np.array(a[k], copy=True) for k in ("H", "b", "cost", "n_res")}
+    s1 = c.eval_stats()
+    assert s1["resident_evals"] == s0["resident_evals"] + 1 or it == 0, (it, s0, s1)
+    c.profile_enable(True)                      # profiling forces the launched kernel
+    b = c.window_eval(refs, pose_refs, pose_cur, ext, td, 1)
+    c.profile_enable(False)
+    for k in ("H", "b", "cost", "n_res"):
+        assert bits_equal(a[k], np.array(b[k])), (it, k)
+    n_res += int(a["n_res"].sum())
+assert n_res > 1000
+print("QUIET_OK", c.eval_stats())
+c.close()
+'''
+
+
+def test_resident_quiet_mode_matches_launched(tmp_path):
+    """Quiet waiting of the resident kernel (only row 0 polls the host, the other rows wait in L2 for its go: what the
+    library switches to while host-to-device copies are in flight), forced for every message with FFLINS_QUIET=1: 40
+    evaluations of a 5-reference window, each bit-identical to the launched kernel."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "quiet.py"
+    script.write_text(_QUIET_SCRIPT)
+    out = subprocess.run([sys.executable, str(script), root], env=dict(os.environ, FFLINS_QUIET="1"), capture_output=True, text=True,
+                         timeout=900)
+    assert out.returncode == 0 and "QUIET_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
