@@ -501,7 +501,7 @@ constexpr int COOP_WARPS   = COOP_THREADS / 32;
 constexpr int COOP_ROUNDS  = 8;                           // 32-item rounds per warp and sub-tile (held in registers)
 constexpr int COOP_TILE    = COOP_THREADS * COOP_ROUNDS;  // 4096 items per sub-tile
 constexpr int COOP_BINS    = 512;
-constexpr int COOP_MAXG    = 256;                         // chunks (CTAs) the work tables are sized for
+constexpr int COOP_MAXG    = 320;                         // chunks (CTAs) the work tables are sized for (two per SM on 148 SMs)
 constexpr int COOP_CEN     = 64;                          // points per centroid round and warp
 constexpr int COOP_STAMPS  = 20;
 
@@ -1341,7 +1341,7 @@ int launch_voxel_downsample(cudaStream_t s, const VoxelWork &w, const float4 *in
             int coop = 0, sms = 0;
             cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            sm_count[dev & 63] = coop ? std::min(sms, COOP_MAXG) : -1;
+            sm_count[dev & 63] = coop ? sms : -1;
         }
         const int sm_n = sm_count[dev & 63].load();
         if (sm_n > 0 && w.keys[1] == w.keys[0] + w.cap && w.idx[1] == w.idx[0] + w.cap) {
@@ -1353,9 +1353,13 @@ int launch_voxel_downsample(cudaStream_t s, const VoxelWork &w, const float4 *in
             a.bar = (unsigned *) (w.meta + 14);
             a.out = out; a.d_nout = d_nout; a.keys_out = keys_out; a.report = report;
             a.stamps = coop_stamps ? (unsigned long long *) (w.meta + 16) : nullptr;
-            int G = std::min(sm_n, (n + 2047) / 2048);
+            // one CTA per SM leaves half of every SM to the solver-facing kernels (a keyframe map); a launch that is large enough
+            // to be bandwidth-bound takes both halves: twice the warps to hide the latency of its streaming phases
+            const int per_sm = n >= (4 << 20) ? 2 : 1;
+            int G = std::min(std::min(sm_n * per_sm, COOP_MAXG), (n + 2047) / 2048);
             void *args[] = {(void *) &a};
-            const bool narrow = (n + G - 1) / G + 128 < 65536; // chunk digit counts fit 16 bits
+            static const bool force_wide = getenv("FFLINS_VOXEL_WIDE") != nullptr;   // tests: the uint32 instantiation at any size
+            const bool narrow = !force_wide && (n + G - 1) / G + 128 < 65536; // chunk digit counts fit 16 bits
             ProfScope ps(prof, nm("coop"), s);
             cudaError_t e = cudaLaunchCooperativeKernel(narrow ? (const void *) vox_coop_kernel<uint16_t> : (const void *) vox_coop_kernel<uint32_t>,
                                                         dim3(G), dim3(COOP_THREADS), args, 0, s);

@@ -161,6 +161,40 @@ def test_voxel_large_input_multi_cta_scan(ctx, oracle):
     assert bits_equal(out, ref)
 
 
+def test_voxel_cooperative_filter_ten_million_points(oracle):
+    """The cooperative filter at a bandwidth-bound size: two CTAs per SM, four 8-bit passes over keys wider than 27 bits,
+    several sub-tiles per chunk. Overflow of the cooperative path (n > 4,096): the input comes back unchanged."""
+    from conftest import new_ctx
+    rng = np.random.default_rng(991)
+    n = 10_200_000
+    pts = np.empty((n, 4), np.float32)
+    pts[:, 0] = rng.uniform(-700, 700, n)
+    pts[:, 1] = rng.uniform(-700, 700, n)
+    pts[:, 2] = rng.uniform(-20, 20, n) * (rng.uniform(0, 1, n) < 0.5)   # half of the points on a ground sheet: dense voxels
+    pts[:, 3] = rng.uniform(0, 255, n)
+    c = new_ctx()
+    try:
+        out, keys = c.voxel_downsample(pts, 0.5, want_keys=True)
+        ref, rkeys, _ = oracle.voxel_filter(pts, 0.5, want_keys=True)
+        assert int(rkeys.max()).bit_length() > 27
+        assert bits_equal(keys, rkeys) and len(out) == len(ref) > 1_000_000
+        assert bits_equal(out, ref)
+        big = (pts[:50_000] * np.float32(100.0)).astype(np.float32)
+        assert bits_equal(c.voxel_downsample(big, 0.01), big)
+    finally:
+        c.close()
+
+
+def test_voxel_cooperative_filter_wide_count_table():
+    """Above 65,535 points per chunk the digit counts of the cooperative filter no longer fit 16 bits: the uint32
+    instantiation (otherwise only reached by the 20 M-point batched roofline launch), forced here at every size."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "vox_bench.py"), "robot", "1"], env=dict(os.environ, FFLINS_VOXEL_WIDE="1"),
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "bit_exact_vs_oracle=True" in out.stdout and "voxel.coop" in out.stdout, out.stdout + out.stderr
+
+
 def test_voxel_other_leaf_and_dense_voxels(ctx, oracle):
     rng = np.random.default_rng(77)
     pts = random_scene_cloud(rng, 60000, extent=2.0)   # thousands of points per voxel
