@@ -884,8 +884,8 @@ int flush_frames(fflins_ctx *ctx) {
     if (copy_tl) CK(cudaEventRecord(ctx->ev_tl[5], s));
     // the rest: their copies in FIFO order on the copy stream, their kernels on the background stream behind the last of
     // those copies. The copy stream ONLY copies: were the kernels queued on it as well, the newest frame of the NEXT batch
-    // could not start crossing PCIe until they had run (measured: ~65 us of idle DMA per keyframe on the association's
-    // critical path). Scratch slots 0..L-1 were last used by the previous background part (same stream).
+    // could not start crossing PCIe until they had run (~60 us of kernels per batch in front of that copy). Scratch slots
+    // 0..L-1 were last used by the previous background part (same stream).
     // Pool blocks handed to these frames may have been released by earlier compute-stream work (re-projection, voxel
     // tail, ...): the kernels start behind everything the compute stream had queued when the batch was flushed.
     cudaStream_t bs = ctx->bg_stream;
