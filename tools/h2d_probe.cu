@@ -25,6 +25,60 @@ __global__ void poller(const ulonglong2 *mail, volatile int *stop, int lanes, in
     if (threadIdx.x == 0) polls[blockIdx.x] = n + (acc & 1);
 }
 
+// A message pushed by a small host-to-device copy on its own stream, picked up by a kernel that polls DEVICE memory and
+// answers with a posted store into pinned host memory: round trip on an idle link and while big copies saturate it —
+// against the same round trip with the kernel polling the pinned host word itself.
+__global__ void echo_kernel(const volatile unsigned long long *msg, volatile unsigned long long *ack, volatile int *stop) {
+    unsigned long long last = 0;
+    while (!*stop) {
+        const unsigned long long v = *msg;
+        if (v != last) {
+            last = v;
+            *ack = v;
+        }
+    }
+}
+
+static void message_probe(char *h, char *d, size_t bytes, cudaStream_t cs) {
+    unsigned long long *h_msg, *h_ack, *d_msg;
+    int *stop;
+    CK(cudaMallocHost(&h_msg, 4096));
+    CK(cudaMallocHost(&h_ack, 64));
+    CK(cudaMallocHost(&stop, 64));
+    CK(cudaMalloc(&d_msg, 4096));
+    CK(cudaMemset(d_msg, 0, 4096));
+    cudaStream_t ms, ks;
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CK(cudaStreamCreateWithPriority(&ms, cudaStreamNonBlocking, hi));
+    CK(cudaStreamCreateWithFlags(&ks, cudaStreamNonBlocking));
+    for (int via_copy = 0; via_copy < 2; via_copy++)
+        for (int load = 0; load < 2; load++) {
+            *stop  = 0;
+            *h_ack = 0;
+            *h_msg = 0;
+            echo_kernel<<<1, 1, 0, ks>>>(via_copy ? d_msg : h_msg, h_ack, stop);
+            if (load)
+                for (int k = 0; k < 60; k++) CK(cudaMemcpyAsync(d + (k % 5) * bytes, h + (k % 5) * bytes, bytes, cudaMemcpyHostToDevice, cs));
+            double sum = 0, worst = 0;
+            const int reps = 200;
+            for (int r = 1; r <= reps; r++) {
+                const auto t0 = std::chrono::steady_clock::now();
+                *h_msg = (unsigned long long) r;
+                if (via_copy) CK(cudaMemcpyAsync(d_msg, h_msg, 1024, cudaMemcpyHostToDevice, ms));
+                while (*(volatile unsigned long long *) h_ack != (unsigned long long) r) {}
+                const double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+                sum += us;
+                worst = us > worst ? us : worst;
+            }
+            *stop = 1;
+            CK(cudaStreamSynchronize(ks));
+            CK(cudaStreamSynchronize(cs));
+            std::printf("message round trip, %-28s %-22s mean %.2f us, worst %.2f us\n", via_copy ? "1 KB copy + device poll:" : "kernel polls pinned host:",
+                        load ? "link saturated by DMA" : "idle link", sum / reps, worst);
+        }
+}
+
 int main() {
     const size_t bytes = 153600 * 32;
     const int copies = 5, reps = 40;
@@ -66,5 +120,6 @@ int main() {
         std::printf("%-36s 5 x 4.9 MB: best %.1f us (%.1f GB/s), mean %.1f us (%.1f GB/s)%s\n", c.name, best * 1e3, bytes * copies / best / 1e6,
                     sum / reps * 1e3, bytes * copies / (sum / reps) / 1e6, "");
     }
+    message_probe(h, d, bytes, cs);
     return 0;
 }
