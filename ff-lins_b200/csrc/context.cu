@@ -250,7 +250,7 @@ struct fflins_ctx : public Profiler {
     bool map_job_active = false;
     uint64_t map_job_key = 0;
     std::vector<Frame *> deferred_frames; // released while the map job may still read them
-    // The ~20 launches of a map job are issued by a helper thread (the reference, too, hands its per-keyframe
+    // The launches of a map job (3 since the cooperative voxel filter, ~20 before) are issued by a helper thread (the reference, too, hands its per-keyframe
     // tree work to a tbb::task_group, lidar_map.cc:121-125,137), so the fusion thread goes straight on to the
     // association. The helper only issues CUDA calls with arguments prepared by the caller.
     std::thread map_worker;

@@ -1,7 +1,9 @@
 // k_voxel.cu — K2 voxel-grid downsample: bbox -> voxel key -> stable LSD radix sort -> segmented
-// centroid, bit-exact with pcl::VoxelGrid<PointXYZI>::applyFilter as FF-LINS uses it
+// centroid, restating pcl::VoxelGrid<PointXYZI>::applyFilter as FF-LINS uses it
 // (call sites ff_lins/lidar/lidar_map.cc:71,209-210,260-261,311-312; arithmetic restated in
-// SURVEY.md Appendix A.1).
+// SURVEY.md Appendix A.1). Voxel keys and output sets are exact; the centroids are bit-exact with the
+// oracle's STABLE-ORDER model of PCL (fp32 sums in ascending original index): PCL itself sorts with an
+// unstable sort, so its intra-voxel summation order is implementation-defined.
 //
 // Bit-exactness rules:
 //   - keys: int(floorf(x * inv_leaf) - float(min_b)) with a separately rounded fp32 multiply;
