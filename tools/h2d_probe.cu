@@ -121,5 +121,39 @@ int main() {
                     sum / reps * 1e3, bytes * copies / (sum / reps) / 1e6, "");
     }
     message_probe(h, d, bytes, cs);
+    // the decimated points of one frame (every 80th 32-byte record, fetched as the 64-byte pair it belongs to) as a strided
+    // copy on a second stream: completion time on an idle link and while big copies saturate the first stream
+    {
+        cudaStream_t s2;
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CK(cudaStreamCreateWithPriority(&s2, cudaStreamNonBlocking, hi));
+        char *d2;
+        CK(cudaMalloc(&d2, 1920 * 64));
+        cudaEvent_t a, b;
+        CK(cudaEventCreate(&a));
+        CK(cudaEventCreate(&b));
+        for (int load = 0; load < 2; load++) {
+            double sum = 0, worst = 0, wall = 0;
+            const int reps = 40;
+            for (int r = 0; r < reps; r++) {
+                if (load)
+                    for (int k = 0; k < 5; k++) CK(cudaMemcpyAsync(d + k * bytes, h + k * bytes, bytes, cudaMemcpyHostToDevice, cs));
+                const auto t0 = std::chrono::steady_clock::now();
+                CK(cudaEventRecord(a, s2));
+                CK(cudaMemcpy2DAsync(d2, 64, h + 4 * bytes, 80 * 32, 64, 1920, cudaMemcpyHostToDevice, s2));
+                CK(cudaEventRecord(b, s2));
+                CK(cudaEventSynchronize(b));
+                wall += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+                float ms;
+                CK(cudaEventElapsedTime(&ms, a, b));
+                sum += ms * 1e3;
+                worst = ms * 1e3 > worst ? ms * 1e3 : worst;
+                CK(cudaStreamSynchronize(cs));
+            }
+            std::printf("strided copy of 1920 x 64 B (pitch 2560 B) on a second stream, %-22s device %.1f us (worst %.1f), host wall %.1f us\n",
+                        load ? "link saturated by DMA:" : "idle link:", sum / reps, worst, wall / reps);
+        }
+    }
     return 0;
 }
