@@ -503,8 +503,17 @@ def run_ours(args, rank, world, local_rank):
                     "alg_flop_per_launch": flop, "residuals_per_launch": n_valid,
                     "avg_launch_ms": stages[top]["ms_per_call"],
                     "note": "dominant stage by summed CUDA-event time of the LAUNCHED kernel (the profiling pass cannot time the "
-                            "resident kernel); ~10 k residuals per evaluation keep the FP64 pipe busy for ~1 us, the rest is "
-                            "launch / completion latency (DESIGN.md §3 K6)"}
+                            "resident kernel, which serves the timed region: see `resident`); a few thousand residuals per "
+                            "evaluation keep the FP64 pipe busy for ~1 us, the rest is launch / completion latency (DESIGN.md §3 K6)"}
+            if rt_us:
+                # what the timed region actually runs: no launch, the host-measured round trip of one evaluation (an upper
+                # bound of the kernel's share: it contains both PCIe crossings and the host's read-out of the results)
+                ach_r = flop / (rt_us * 1e-6) / 1e12
+                roof["resident"] = {"roundtrip_ms": round(rt_us * 1e-3, 5), "achieved": round(ach_r, 4),
+                                    "frac": round(ach_r / fp64_peak, 5) if fp64_peak else None,
+                                    "timing": "wall clock around fflins_window_eval, 200 calls (no CUDA event can bracket a message "
+                                              "to a resident kernel)"}
+                stages[top]["resident_roundtrip_ms"] = round(rt_us * 1e-3, 5)
         else:
             roof = {"kernel": top, "bound": "hbm", "achieved": stages[top]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                     "frac": round(stages[top]["achieved_gbs"] / peak, 5), "traffic": traffic, "traffic_source": traffic_src,
