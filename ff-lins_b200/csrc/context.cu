@@ -217,6 +217,7 @@ struct fflins_ctx : public Profiler {
     cudaEvent_t ev_join_a = nullptr, ev_join_b = nullptr; // timer: map / copy stream joins
     bool bg_active = false;           // ... and nobody has waited for it yet
     bool bg_staged = false;           // ... and it contains host-to-device copies of point data
+    bool copy_owes_bg_wait = false;   // a background part ran since the copy stream last waited for one (stage_window slots)
     unsigned long long last_main_seq = 0;
     unsigned long long scratch_gen = 0; // bumped whenever the per-item batch scratch is handed out again
     // page-locked bounce ring for pageable caller buffers (filled by CopyPool, drained by the copy stream)
@@ -803,14 +804,17 @@ int flush_frames(fflins_ctx *ctx) {
     const int count = (int) ctx->fq.size();
     const int L     = count - 1;
     int rc;
-    const bool had_bg = ctx->bg_active;
     if ((rc = join_bg(ctx))) return rc; // scratch slots and stream order: one background part at a time
     ctx->scratch_gen++;
     // the staged windows land in the per-item scratch (stage_window): the copy stream must not overwrite a slot whose
     // previous prologue may still be reading it (compute stream: slot of the newest frame; background stream: the others)
     if (staged_any(ctx)) {
         if (ctx->last_main_seq) CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->batch_ev[ctx->last_main_seq % kGuardRing], 0));
-        if (had_bg && !(count >= 2 && !ctx->prof_on)) CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_bg_done, 0));
+        // (not `had_bg`: join_bg may have been called since — it orders the COMPUTE stream behind that part, not this one)
+        if (ctx->copy_owes_bg_wait && !(count >= 2 && !ctx->prof_on)) {
+            CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_bg_done, 0));
+            ctx->copy_owes_bg_wait = false;
+        }
     }
     const bool split = count >= 2 && !ctx->prof_on;
     if (split) CK(cudaEventRecord(ctx->ev_flush, s));
@@ -890,7 +894,10 @@ int flush_frames(fflins_ctx *ctx) {
     // tail, ...): the kernels start behind everything the compute stream had queued when the batch was flushed.
     cudaStream_t bs = ctx->bg_stream;
     CK(cudaStreamWaitEvent(bs, ctx->ev_flush, 0));
-    if (had_bg && staged) CK(cudaStreamWaitEvent(cs, ctx->ev_bg_done, 0)); // (see above: scratch slots 0..L-1 of the previous part)
+    if (ctx->copy_owes_bg_wait && staged) { // (see above: scratch slots 0..L-1 of the previous part)
+        CK(cudaStreamWaitEvent(cs, ctx->ev_bg_done, 0));
+        ctx->copy_owes_bg_wait = false;
+    }
     ctx->last_main_seq = seq;
     FrameBatch G{};
     G.count = L;
@@ -921,6 +928,7 @@ int flush_frames(fflins_ctx *ctx) {
     }
     ctx->bg_active = true;
     ctx->bg_staged = staged;
+    ctx->copy_owes_bg_wait = true;
     CK(cudaGetLastError());
     return FFLINS_OK;
 }
