@@ -230,8 +230,10 @@ class NativeSession:
         path = os.path.join(ROOT, "tools", "libfflins_driver.so")
         if not os.path.exists(path):   # normally built by __graft_entry__.build(); a plain g++ link against the C-ABI
             gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-            subprocess.check_call([gxx, "-std=c++17", "-O2", "-shared", "-fPIC", "-o", path, os.path.join(ROOT, "tools", "session_driver.cc"),
+            tmp = f"{path}.{os.getpid()}.tmp"   # (several replicas may get here at once: build aside, rename atomically)
+            subprocess.check_call([gxx, "-std=c++17", "-O2", "-shared", "-fPIC", "-o", tmp, os.path.join(ROOT, "tools", "session_driver.cc"),
                                    "-L", os.path.join(ROOT, "ff-lins_b200"), "-lfflins_b200", "-Wl,-rpath,$ORIGIN/../ff-lins_b200"])
+            os.replace(tmp, path)
         L = self.L = ctypes.CDLL(path)
         L.drv_create.restype = ctypes.c_void_p
         L.drv_create.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
