@@ -43,7 +43,7 @@ struct Frame {
     int pending_slot = -1; // >= 0: counts of the last frame_process still sit in pinned slot (asynchronous mode)
     const int *d_ndown = nullptr;        // device copy of the voxel count of its last chain (batch scratch) ...
     unsigned long long d_ndown_gen = 0;  // ... valid while no later launch has reused the scratch (ctx->scratch_gen)
-    bool bg = false;       // its kernel chain runs on the copy stream behind its own host-to-device copy (see flush_frames)
+    bool bg = false;       // its kernel chain runs on the background stream behind its own host-to-device copy (see flush_frames)
     // keyframe hash (K4)
     MapIndex index; // fine / coarse / super hash tables (hcap slots each)
     int hcap                  = 0;
@@ -474,7 +474,7 @@ int resolve_map(fflins_ctx *ctx) {
         }
     }
     {
-        bool any_bg = false; // (a frame released while an unrelated job was running may still be busy on the copy stream)
+        bool any_bg = false; // (a frame released while an unrelated job was running may still be busy on the background stream)
         for (Frame *f : ctx->deferred_frames) any_bg |= f->bg;
         if (any_bg) {
             int rcj = join_bg(ctx);
@@ -796,7 +796,7 @@ int stage_window(fflins_ctx *ctx, const QueuedFrame &q, FrameItem &it) {
 // Batches of two or more frames are SPLIT: the newest frame (the one the caller is about to use: association and
 // factor evaluation only ever need the current keyframe) is copied first and processed on the compute stream; the
 // older frames of the batch — which only feed the keyframe-map merge — are copied behind it (pinned host buffers: their
-// copies are issued here, newest first) and processed on the copy stream, so that their PCIe and kernel time overlaps
+// copies are issued here, newest first) and processed on the background stream, so that their PCIe and kernel time overlaps
 // the solver instead of preceding it.
 int flush_frames(fflins_ctx *ctx) {
     if (ctx->fq.empty()) return FFLINS_OK;
@@ -946,7 +946,7 @@ int enqueue_frame(fflins_ctx *ctx, uint64_t id, const float *xyzi, const double 
     bool must_flush = (int) ctx->fq.size() >= kFrameBatch;
     for (const QueuedFrame &q : ctx->fq) must_flush |= q.f == f || (q.item.aos != nullptr) != (aos != nullptr);
     if (must_flush && (rc = flush_frames(ctx))) return rc;
-    if (f->bg && (rc = join_bg(ctx))) return rc; // re-processing a frame whose previous chain is still on the copy stream
+    if (f->bg && (rc = join_bg(ctx))) return rc; // re-processing a frame whose previous chain is still on the background stream
     if ((rc = ensure_ins(ctx, w))) return rc;
     const int F    = ctx->cfg.point_filter_num;
     const int ndec = (n + F - 1) / F;

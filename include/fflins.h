@@ -127,7 +127,7 @@ int         fflins_host_buffer_done(fflins_ctx *ctx, const void *ptr);
  * page-locked (fflins_host_register / cudaMallocHost) point buffers and device point buffers (_dev) must stay
  * untouched until fflins_synchronize, fflins_frame_info_get or a download of THAT frame returns — their
  * copies are issued when the batch is launched, newest frame first, and the older frames of the batch are
- * processed on the copy stream behind their own copies so that association and factor evaluation of the newest
+ * processed on a background stream behind their own copies so that association and factor evaluation of the newest
  * frame never wait for them; pageable buffers are copied before the call returns.
  * SoA input. ins_* is the INS window (deque<pair<IMU,IntegrationState>>): strictly
  * increasing times, positions, quaternions; 2 <= w <= 65536 (misc.cc:27-62). stamp is
