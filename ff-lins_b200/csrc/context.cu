@@ -6,6 +6,7 @@
 #include "kernels.h"
 #include "math_undistort.cuh"
 
+#include <chrono>
 #include <algorithm>
 #include <atomic>
 #include <condition_variable>
@@ -217,6 +218,7 @@ struct fflins_ctx : public Profiler {
     cudaEvent_t ev_join_a = nullptr, ev_join_b = nullptr; // timer: map / copy stream joins
     bool bg_active = false;           // ... and nobody has waited for it yet
     bool bg_staged = false;           // ... and it contains host-to-device copies of point data
+    int merge_reserve = 1;            // frames per keyframe seen so far: every frame's full cloud is allocated with room for them
     bool copy_owes_bg_wait = false;   // a background part ran since the copy stream last waited for one (stage_window slots)
     unsigned long long last_main_seq = 0;
     unsigned long long scratch_gen = 0; // bumped whenever the per-item batch scratch is handed out again
@@ -488,9 +490,10 @@ int resolve_map(fflins_ctx *ctx) {
     return FFLINS_OK;
 }
 
-int ensure_cloud(fflins_ctx *ctx, Cloud &c, int n, bool keep = false) {
+// reserve (>= n): capacity to allocate when the cloud has to grow anyway
+int ensure_cloud(fflins_ctx *ctx, Cloud &c, int n, bool keep = false, long long reserve = 0) {
     if (n <= c.cap) return FFLINS_OK;
-    size_t want = Pool::round((size_t) std::max(n, 256) * sizeof(float4));
+    size_t want = Pool::round((size_t) std::max<long long>(std::max(n, 256), std::min<long long>(reserve, 1ll << 27)) * sizeof(float4));
     float4 *p   = (float4 *) ctx->pool.alloc(want);
     if (!p) return fail(ctx, FFLINS_E_NOMEM, "device allocation failed");
     if (keep && c.d && c.n > 0)
@@ -693,7 +696,9 @@ unsigned long long next_batch(fflins_ctx *ctx) {
 // Bookkeeping shared by every frame entry point: clouds sized, counts pending in a pinned slot.
 int frame_begin(fflins_ctx *ctx, Frame *f, int n, int ndec, int **report) {
     int rc;
-    if ((rc = ensure_cloud(ctx, f->c[FFLINS_CLOUD_MAP_FULL], n))) return rc;
+    // any frame may become a keyframe, whose full cloud then takes the points of the frames merged into it: with room for
+    // them from the start the merge neither reallocates nor copies the keyframe's own points (HBM is not the constraint)
+    if ((rc = ensure_cloud(ctx, f->c[FFLINS_CLOUD_MAP_FULL], n, false, (long long) n * ctx->merge_reserve))) return rc;
     if ((rc = ensure_cloud(ctx, f->c[FFLINS_CLOUD_LIDAR_FULL], ndec))) return rc;
     if ((rc = ensure_cloud(ctx, f->c[FFLINS_CLOUD_LIDAR], ndec))) return rc;
     if ((rc = ensure_cloud(ctx, f->c[FFLINS_CLOUD_WORLD], ndec))) return rc;
@@ -909,9 +914,11 @@ int flush_frames(fflins_ctx *ctx) {
         ctx->fq[i].f->bg = true;
     }
     // (pageable sources were copied at call time, also on the copy stream: the event covers them too)
-    CK(cudaEventRecord(ctx->ev_bg_copied, cs));
+    if (staged) {   // (device-resident frames: nothing crosses the copy stream)
+        CK(cudaEventRecord(ctx->ev_bg_copied, cs));
+        CK(cudaStreamWaitEvent(bs, ctx->ev_bg_copied, 0));
+    }
     if (copy_tl) CK(cudaEventRecord(ctx->ev_tl[2], cs));
-    CK(cudaStreamWaitEvent(bs, ctx->ev_bg_copied, 0));
     if (copy_tl) CK(cudaEventRecord(ctx->ev_tl[3], bs));
     unsigned long long seq_bg;
     if ((rc = launch_chain(ctx, bs, G, &seq_bg))) return rc;
@@ -1957,12 +1964,38 @@ int fflins_knn5(fflins_ctx *ctx, const float *map_xyzi, int32_t m, const float *
     return FFLINS_OK;
 }
 
+namespace {
+// FFLINS_TRACE_HOST=1 (debug): where the host time of fflins_keyframe_merge goes; printed every 1,000 calls
+struct HostTrace {
+    bool on = getenv("FFLINS_TRACE_HOST") != nullptr;
+    double us[4] = {0, 0, 0, 0};
+    long long calls = 0;
+    std::chrono::steady_clock::time_point t;
+    void start() { if (on) t = std::chrono::steady_clock::now(); }
+    void lap(int k) {
+        if (!on) return;
+        const auto n = std::chrono::steady_clock::now();
+        us[k] += std::chrono::duration<double, std::micro>(n - t).count();
+        t = n;
+    }
+    void done() {
+        if (!on || ++calls % 1000) return;
+        std::fprintf(stderr, "[fflins] keyframe_merge host time (us): flush_frames %.1f | resolve_map %.1f | prepare %.1f | hand over %.1f\n",
+                     us[0] / calls, us[1] / calls, us[2] / calls, us[3] / calls);
+    }
+};
+HostTrace g_merge_trace;
+} // namespace
+
 int fflins_keyframe_merge(fflins_ctx *ctx, uint64_t key_id, const uint64_t *nonkey_ids, int32_t n, fflins_frame_info *out) {
     if (!ctx) return FFLINS_E_INVALID;
     REQUIRE(n >= 0 && (n == 0 || nonkey_ids), "bad argument");
     int rc;
+    g_merge_trace.start();
     if ((rc = flush_frames(ctx))) return rc; // the frames being merged may still be queued
+    g_merge_trace.lap(0);
     if ((rc = resolve_map(ctx))) return rc;  // one map job in flight at a time
+    g_merge_trace.lap(1);
     Frame *key = find_frame(ctx, key_id);
     if (!key) return fail(ctx, FFLINS_E_NOTFOUND, "unknown keyframe");
     cudaStream_t ms = ctx->map_stream;
@@ -1974,6 +2007,7 @@ int fflins_keyframe_merge(fflins_ctx *ctx, uint64_t key_id, const uint64_t *nonk
         total += nk[i]->c[FFLINS_CLOUD_MAP_FULL].n;
     }
     if ((rc = ensure_voxel_work(ctx, ctx->vox_map, ctx->vox_map_base, total))) return rc;
+    ctx->merge_reserve = std::min(std::max(ctx->merge_reserve, n + 1), (int) kMaxRefs);
     // the map stream starts once everything enqueued so far on the compute stream (the undistortion of the
     // frames being merged) is done
     CK(cudaEventRecord(ctx->ev_main_done, ctx->stream));
@@ -2066,6 +2100,7 @@ int fflins_keyframe_merge(fflins_ctx *ctx, uint64_t key_id, const uint64_t *nonk
         cudaEventRecord(ctx->ev_map_done, ms);
         ctx->launches += nl;
     };
+    g_merge_trace.lap(2);
     if (out || profiling || !ctx->map_worker.joinable()) {
         issue(); // synchronous call, profiling pass (the event list is not thread-safe) or no helper thread
     } else {
@@ -2074,6 +2109,8 @@ int fflins_keyframe_merge(fflins_ctx *ctx, uint64_t key_id, const uint64_t *nonk
         ctx->map_issued = false;
         ctx->map_cv.notify_all();
     }
+    g_merge_trace.lap(3);
+    g_merge_trace.done();
     ctx->map_job_active = true;
     ctx->map_job_key    = key_id;
     map.n               = 0;
