@@ -648,6 +648,31 @@ void fill_info(Frame *f, fflins_frame_info *out) {
 
 // Shared tail of the two lidarFrameProcessing overloads: voxel filter of the decimated cloud,
 // world projection, result read-back (one synchronisation per frame).
+// FFLINS_TRACE_HOST=1 (debug): where the host time of an entry point goes; printed every 1,000 calls
+struct HostTrace {
+    const char *what;
+    const char *lap_name[6];
+    bool on = getenv("FFLINS_TRACE_HOST") != nullptr;
+    double us[6] = {0, 0, 0, 0, 0, 0};
+    long long calls = 0;
+    std::chrono::steady_clock::time_point t;
+    void start() { if (on) t = std::chrono::steady_clock::now(); }
+    void lap(int k) {
+        if (!on) return;
+        const auto n = std::chrono::steady_clock::now();
+        us[k] += std::chrono::duration<double, std::micro>(n - t).count();
+        t = n;
+    }
+    void done() {
+        if (!on || ++calls % 1000) return;
+        std::fprintf(stderr, "[fflins] %s host time (us):", what);
+        for (int k = 0; k < 6 && lap_name[k]; k++) std::fprintf(stderr, " %s %.2f |", lap_name[k], us[k] / calls);
+        std::fprintf(stderr, "\n");
+    }
+};
+HostTrace g_merge_trace{"keyframe_merge", {"flush_frames", "resolve_map", "prepare", "hand over", nullptr, nullptr}};
+HostTrace g_enqueue_trace{"frame_process (queued)", {"check + lookup", "pack window", "stage", "pose", "buffers + queue", nullptr}};
+
 int check_window(fflins_ctx *ctx, const double *ins_t, int w) {
     REQUIRE(w >= 2 && w <= 65536, "INS window must hold 2..65536 entries");
     for (int i = 1; i < w; i++) REQUIRE(ins_t[i] > ins_t[i - 1], "INS window times must be strictly increasing");
@@ -946,6 +971,7 @@ int enqueue_frame(fflins_ctx *ctx, uint64_t id, const float *xyzi, const double 
                   int n, const double *ins_t, const double *ins_p, const double *ins_q, int w, const fflins_pose *pose_b_l,
                   double stamp, double td, fflins_frame_info *out) {
     int rc;
+    g_enqueue_trace.start();
     if ((rc = check_window(ctx, ins_t, w))) return rc;
     ctx->eval_inputs_settled = false;
     Frame *f = get_frame(ctx, id);
@@ -962,7 +988,9 @@ int enqueue_frame(fflins_ctx *ctx, uint64_t id, const float *xyzi, const double 
     q.stage_slot = -1;
     FrameItem &it = q.item;
     double *hp;
+    g_enqueue_trace.lap(0);
     if ((rc = pack_window(ctx, ins_t, ins_p, ins_q, w, &hp, &q.wslot))) return rc;
+    g_enqueue_trace.lap(1);
     it.win = hp;
     it.w   = w;
     if (on_device || n == 0) {
@@ -1036,11 +1064,13 @@ int enqueue_frame(fflins_ctx *ctx, uint64_t id, const float *xyzi, const double 
             q.n_copy = 0;
         }
     }
+    g_enqueue_trace.lap(2);
     it.ext = to12(*pose_b_l);
     pose_from_window(ins_t, ins_p, ins_q, w, it.ext, stamp, it.frame);
     std::memcpy(f->pose.R, it.frame.R, sizeof(it.frame.R));
     std::memcpy(f->pose.t, it.frame.t, sizeof(it.frame.t));
     f->td = td;
+    g_enqueue_trace.lap(3);
     if ((rc = frame_begin(ctx, f, n, ndec, &it.report))) return rc;
     it.n          = n;
     it.td         = td;
@@ -1057,6 +1087,8 @@ int enqueue_frame(fflins_ctx *ctx, uint64_t id, const float *xyzi, const double 
     it.down       = f->c[FFLINS_CLOUD_LIDAR].d;
     it.world      = f->c[FFLINS_CLOUD_WORLD].d;
     ctx->fq.push_back(q);
+    g_enqueue_trace.lap(4);
+    g_enqueue_trace.done();
     if (!out) return FFLINS_OK; // asynchronous: launched together with the next frames, read back on demand
     if ((rc = resolve_pending(ctx))) return rc;
     fill_info(f, out);
@@ -1963,29 +1995,6 @@ int fflins_knn5(fflins_ctx *ctx, const float *map_xyzi, int32_t m, const float *
     if (e != cudaSuccess) return fail(ctx, FFLINS_E_CUDA, cudaGetErrorString(e));
     return FFLINS_OK;
 }
-
-namespace {
-// FFLINS_TRACE_HOST=1 (debug): where the host time of fflins_keyframe_merge goes; printed every 1,000 calls
-struct HostTrace {
-    bool on = getenv("FFLINS_TRACE_HOST") != nullptr;
-    double us[4] = {0, 0, 0, 0};
-    long long calls = 0;
-    std::chrono::steady_clock::time_point t;
-    void start() { if (on) t = std::chrono::steady_clock::now(); }
-    void lap(int k) {
-        if (!on) return;
-        const auto n = std::chrono::steady_clock::now();
-        us[k] += std::chrono::duration<double, std::micro>(n - t).count();
-        t = n;
-    }
-    void done() {
-        if (!on || ++calls % 1000) return;
-        std::fprintf(stderr, "[fflins] keyframe_merge host time (us): flush_frames %.1f | resolve_map %.1f | prepare %.1f | hand over %.1f\n",
-                     us[0] / calls, us[1] / calls, us[2] / calls, us[3] / calls);
-    }
-};
-HostTrace g_merge_trace;
-} // namespace
 
 int fflins_keyframe_merge(fflins_ctx *ctx, uint64_t key_id, const uint64_t *nonkey_ids, int32_t n, fflins_frame_info *out) {
     if (!ctx) return FFLINS_E_INVALID;
