@@ -2505,6 +2505,82 @@ int fflins_window_chi2(fflins_ctx *ctx, int32_t n_pairs, const uint64_t *ref_ids
     return FFLINS_OK;
 }
 
+void fflins_solve_options_default(fflins_solve_options *o) {
+    if (!o) return;
+    std::memset(o, 0, sizeof(*o));
+    o->max_iterations[0]   = 5;
+    o->max_iterations[1]   = 10;
+    o->chi2_threshold      = 3.841;
+    o->function_tolerance  = 1e-6;
+    o->gradient_tolerance  = 1e-10;
+    o->parameter_tolerance = 1e-8;
+    o->initial_radius      = 1e4;
+    o->flags               = FFLINS_HUBER;
+    o->fixed_refs          = 0;
+}
+
+int fflins_window_solve(fflins_ctx *ctx, int32_t n_pairs, const uint64_t *ref_ids, double *pose_refs, double pose_cur[7],
+                        double ext[7], double *td, const fflins_solve_options *opt, const fflins_solve_prior *prior,
+                        fflins_solve_report *report) {
+    if (!ctx) return FFLINS_E_INVALID;
+    REQUIRE(n_pairs >= 1 && ref_ids && pose_refs && pose_cur && ext && td && opt, "bad argument");
+    REQUIRE(opt->max_iterations[0] >= 0 && opt->max_iterations[1] >= 0 && opt->max_iterations[0] + opt->max_iterations[1] <= 1000 &&
+                opt->initial_radius > 0,
+            "bad solve options");
+    REQUIRE(!prior || (prior->H0 && prior->b0 && prior->x0), "incomplete prior");
+    REQUIRE(!ctx->keyframes.empty(), "no keyframe in the window");
+    Frame *cur = find_frame(ctx, ctx->keyframes.back());
+    FactorParams P{};
+    int rc;
+    if ((rc = fill_factor_pairs(ctx, P, n_pairs, ref_ids, pose_refs, cur, pose_cur, ext, *td, opt->flags))) return rc;
+    if (report) std::memset(report, 0, sizeof(*report));
+    if (P.q == 0) return FFLINS_OK;   // no residual: the state stays where it is
+    SolveOptions O{};
+    O.max_iters[0]          = opt->max_iterations[0];
+    O.max_iters[1]          = opt->max_iterations[1];
+    O.chi2_threshold        = opt->chi2_threshold;
+    O.function_tolerance    = opt->function_tolerance;
+    O.gradient_tolerance    = opt->gradient_tolerance;
+    O.parameter_tolerance   = opt->parameter_tolerance;
+    O.initial_radius        = opt->initial_radius;
+    O.min_relative_decrease = 1e-3;
+    O.flags                 = opt->flags & 0x1fu;
+    O.fixed_refs            = opt->fixed_refs;
+    std::vector<double> x(7 * (size_t) n_pairs + 15);
+    SolveReport R{};
+    cudaStream_t s = ctx->stream;
+    int how;
+    {
+        ProfScope ps(ctx->prof(), "window_solve", s);
+        int64_t nl = 0;
+        how = launch_window_solve(ctx->frt, s, P, (const float *) cur->c[FFLINS_CLOUD_LIDAR].d, 1, O, prior ? prior->H0 : nullptr,
+                                  prior ? prior->b0 : nullptr, prior ? prior->x0 : nullptr, prior ? prior->c0 : 0.0, x.data(), &R, &nl);
+        ctx->launches += nl;
+    }
+    if (how < 0) return fail(ctx, FFLINS_E_CUDA, std::string("window solve: ") + cudaGetErrorString((cudaError_t) -how));
+    ctx->eval_inputs_settled = true;   // the kernel ran behind everything queued on the compute stream
+    if (report) {
+        report->status = R.status;
+        for (int k = 0; k < 2; k++) {
+            report->iterations[k]   = R.iterations[k];
+            report->successful[k]   = R.successful[k];
+            report->evaluations[k]  = R.evaluations[k];
+            report->cost_initial[k] = R.cost_initial[k];
+            report->cost_final[k]   = R.cost_final[k];
+        }
+        for (int i = 0; i < n_pairs; i++) {
+            report->n_outliers[i] = R.n_outliers[i];
+            report->n_res[i]      = R.n_res[i];
+        }
+    }
+    if (R.status != 0) return fail(ctx, FFLINS_E_CUDA, "window solve: a hand-off inside the kernel timed out");
+    std::memcpy(pose_refs, x.data(), sizeof(double) * 7 * (size_t) n_pairs);
+    std::memcpy(pose_cur, x.data() + 7 * (size_t) n_pairs, 56);
+    std::memcpy(ext, x.data() + 7 * (size_t) n_pairs + 7, 56);
+    *td = x[7 * (size_t) n_pairs + 14];
+    return FFLINS_OK;
+}
+
 int fflins_profile_enable(fflins_ctx *ctx, int on) {
     if (!ctx) return FFLINS_E_INVALID;
     if (!on && ctx->prof_on) ctx->prof_collect();

@@ -27,6 +27,7 @@
 //    after an idle period (default 1 ms), every wait in it is bounded, and the launched kernel (same evaluation code,
 //    message by value, ticket reduction) remains as the cold path and for profiling.
 #include "math_factor.cuh"
+#include "math_solve.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -653,6 +654,332 @@ __global__ void __launch_bounds__(kFactorBlock) resident_kernel(const __grid_con
     }
 }
 
+// ---- device-side window solve (fflins_window_solve) ---------------------------------------------------------------------
+// The 5 + chi2 + 10 schedule of Optimizer::optimization (optimizer.cc:85-185) over the LiDAR factors of the window and a
+// quadratic prior, WITHOUT a host round trip per iteration: one launch per keyframe, grid = 8 CTAs per (ref, cur) pair
+// (the evaluators: the same pair_prepare / eval_tiles / chi2_tiles as above) + one solver CTA that owns the state. Per
+// Levenberg-Marquardt iteration the solver broadcasts the candidate state (tagged 16-byte slots through L2, the
+// message layout of FactorMsg), the evaluators answer with their pair's 212 sums (ranks 1..7 -> rank 0 -> solver,
+// tagged 32-byte units, summed in the order of fflins_window_eval), the solver assembles the D x D normal equations
+// in shared memory (D = 6 n + 13), factors them, applies PoseManifold::Plus and decides (math_solve.cuh). Tags are
+// base + step with a base unique to the launch; every wait is bounded. All CTAs must be co-resident: at most
+// 8 * 15 + 1 = 121 CTAs of 128 threads, one per SM (the solver's shared-memory footprint is the kernel's).
+constexpr int kSolveOutWords = 48 + kSolveMaxX;   // status | 2 x 6 stage words | steps | 16 outlier counts | 16 n_res | state
+constexpr int kGatherItems   = (kMaxPairs * kRedUnits + kFactorBlock - 1) / kFactorBlock;   // 9
+
+struct SolveArgs {
+    FactorMsg init;                 // the initial state in message layout
+    const FactorSetup *setup;       // device memory
+    SolveOptions opt;
+    SolvePrior prior;               // device pointers
+    ulonglong2 *bcast;              // [kMsgWords]                        solver -> evaluators
+    Unit *part;                     // [kMaxPairs][kFactorRanks][kRedUnits] ranks 1..7 -> rank 0
+    Unit *inbox;                    // [kMaxPairs][kRedUnits]              rank 0 -> solver
+    double *h_out;                  // pinned, kSolveOutWords
+    unsigned long long *h_signal;   // pinned
+    unsigned long long base, seq, hard_ns;
+    int n, q;
+};
+
+struct ParCta {
+    double *scratch;   // shared, kWarps doubles
+    __device__ int tid() const { return threadIdx.x; }
+    __device__ int nthr() const { return kFactorBlock; }
+    __device__ void sync() const { __syncthreads(); }
+    __device__ double sum(double v) const {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+        __syncthreads();
+        double s = scratch[0];
+#pragma unroll
+        for (int w = 1; w < kWarps; w++) s += scratch[w];
+        __syncthreads();
+        return s;
+    }
+    __device__ double max(double v) const {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+        __syncthreads();
+        double s = scratch[0];
+#pragma unroll
+        for (int w = 1; w < kWarps; w++) s = fmax(s, scratch[w]);
+        __syncthreads();
+        return s;
+    }
+};
+
+// the solver CTA's side of the hand-offs; operator() is the `eval` of solve_lm
+struct SolveLink {
+    const SolveArgs &A;
+    ParCta par;
+    SolveWork *W;
+    double *red;            // shared, n x kRedStride
+    int *counts;            // shared, kMaxPairs (chi2)
+    unsigned long long step;
+    bool bad;
+
+    __device__ void broadcast(unsigned cmd, const double *x, double thr) {
+        ++step;
+        const unsigned long long tag = A.base + step;
+        const int n = A.n, t = threadIdx.x;
+        if (t < kMsgHead + 7 * n) {
+            unsigned long long w;
+            if (t == W_CMD) w = (unsigned long long) cmd | ((unsigned long long) (A.opt.flags & 0x1fu) << 32);
+            else if (t == W_NP) w = (unsigned long long) (unsigned) n;
+            else if (t == W_TD) w = d2w_dev(x[7 * n + 14]);
+            else if (t == W_THR) w = d2w_dev(thr);
+            else if (t == W_SEQ) w = tag;
+            else if (t < W_EXT) w = d2w_dev(x[7 * n + (t - W_CUR)]);
+            else if (t < kMsgHead) w = d2w_dev(x[7 * n + 7 + (t - W_EXT)]);
+            else w = d2w_dev(x[t - kMsgHead]);
+            st_slot_gpu(A.bcast + t, w, tag);
+        }
+    }
+    // every pair's answer to the last broadcast -> red / counts. Uniform result; also the barrier behind the stores.
+    __device__ bool gather(bool chi2) {
+        const unsigned long long tag = A.base + step;
+        const int items = A.n * (chi2 ? 1 : kRedUnits), tid = threadIdx.x;
+        Unit u[kGatherItems];
+        unsigned pending = 0;
+#pragma unroll
+        for (int k = 0; k < kGatherItems; k++)
+            if (tid + kFactorBlock * k < items) pending |= 1u << k;
+        const unsigned long long t0 = globaltimer_ns();
+        bool late = false;
+        while (pending && !late) {
+#pragma unroll
+            for (int k = 0; k < kGatherItems; k++)
+                if (pending & (1u << k)) {
+                    const int idx = tid + kFactorBlock * k, p = chi2 ? idx : idx / kRedUnits, uu = chi2 ? 0 : idx - p * kRedUnits;
+                    u[k] = ld_unit_gpu(A.inbox + (size_t) p * kRedUnits + uu);
+                }
+#pragma unroll
+            for (int k = 0; k < kGatherItems; k++)
+                if ((pending & (1u << k)) && u[k].tag == tag) {
+                    const int idx = tid + kFactorBlock * k, p = chi2 ? idx : idx / kRedUnits, uu = chi2 ? 0 : idx - p * kRedUnits;
+                    if (chi2) {
+                        counts[p] = (int) u[k].w[0];
+                    } else {
+                        double *dst = red + p * kRedStride + 3 * uu;
+                        dst[0] = w2d(u[k].w[0]);
+                        dst[1] = w2d(u[k].w[1]);
+                        dst[2] = w2d(u[k].w[2]);
+                    }
+                    pending &= ~(1u << k);
+                }
+            if (pending && globaltimer_ns() - t0 > A.hard_ns) late = true;
+        }
+        return !__syncthreads_or(late);
+    }
+    __device__ double operator()(const double *x, double *H, double *g) {
+        if (bad) return 0.0;
+        broadcast(kCmdEval, x, 0.0);
+        if (!gather(false)) {
+            bad = true;
+            return 0.0;
+        }
+        return solve_assemble(par, *W, A.prior, x, red, H, g);
+    }
+    __device__ bool failed() const { return bad; }
+};
+
+__host__ __device__ inline size_t solve_smem_doubles(int n) {
+    const int D = solve_dim(n), ld = solve_ld(D);
+    size_t d = 2 * (size_t) D * ld + 6 * (size_t) ld + 2 * (size_t) solve_nx(n) + (size_t) n * kRedStride + 8;
+    d += ((size_t) (D - 1) * D / 2 * sizeof(unsigned short) + 7) / 8;   // elimination table
+    d += (D + 7) / 8 + (kMaxPairs * sizeof(int) + 7) / 8;               // fixed mask, chi2 counts
+    return d;
+}
+
+constexpr int kPriorDoubles = kSolveMaxDim * kSolveMaxDim + kSolveMaxDim + kSolveMaxX;
+constexpr size_t kSolveSmemMax = 227 * 1024;
+
+__device__ void solver_cta(const SolveArgs &A, double *smem) {
+    const int n = A.n, D = solve_dim(n), ld = solve_ld(D), NX = solve_nx(n), tid = threadIdx.x;
+    SolveWork W;
+    W.n  = n;
+    W.D  = D;
+    W.ld = ld;
+    double *p = smem;
+    W.H     = p; p += (size_t) D * ld;
+    W.A     = p; p += (size_t) D * ld;
+    W.g     = p; p += ld;
+    W.gn    = p; p += ld;
+    W.dx    = p; p += ld;
+    W.rhs   = p; p += ld;
+    W.dinv  = p; p += ld;
+    W.delta = p; p += ld;
+    W.x     = p; p += NX;
+    W.xc    = p; p += NX;
+    double *red     = p; p += (size_t) n * kRedStride;
+    double *scratch = p; p += 8;
+    unsigned short *tri = reinterpret_cast<unsigned short *>(p);
+    p += ((size_t) (D - 1) * D / 2 * sizeof(unsigned short) + 7) / 8;
+    unsigned char *fixed = reinterpret_cast<unsigned char *>(p);
+    p += (D + 7) / 8;
+    int *counts = reinterpret_cast<int *>(p);
+    W.tri   = tri;
+    W.fixed = fixed;
+    solve_fill_tri(tid, kFactorBlock, D, tri);
+    solve_fill_fixed(tid, kFactorBlock, n, A.opt.flags, A.opt.fixed_refs, fixed);
+    for (int i = tid; i < NX; i += kFactorBlock) {
+        unsigned long long w;
+        if (i < 7 * n) w = A.init.w[W_REF + i];
+        else if (i < 7 * n + 7) w = A.init.w[W_CUR + (i - 7 * n)];
+        else if (i < 7 * n + 14) w = A.init.w[W_EXT + (i - 7 * n - 7)];
+        else w = A.init.w[W_TD];
+        W.x[i] = w2d(w);
+    }
+    if (tid < kMaxPairs) counts[tid] = 0;
+    __syncthreads();
+    SolveLink link{A, ParCta{scratch}, &W, red, counts, 0ull, false};
+    SolveStage st[2];
+    st[0] = solve_lm(link.par, W, A.opt, A.opt.max_iters[0], link);
+    if (!link.bad && A.opt.chi2_threshold > 0.0) {
+        // Optimizer::lidarOutlierCullingByChi2 (optimizer.cc:515-548) at the state of the first solve
+        link.broadcast(kCmdChi2, W.x, A.opt.chi2_threshold);
+        if (!link.gather(true)) link.bad = true;
+    }
+    st[1] = solve_lm(link.par, W, A.opt, A.opt.max_iters[1], link);
+    link.broadcast(kCmdRetire, W.x, 0.0);
+    // ---- results: pinned host memory, then the flag behind them
+    volatile double *out = A.h_out;
+    if (tid == 0) {
+        out[0] = link.bad ? 1.0 : 0.0;
+        for (int s = 0; s < 2; s++) {
+            out[1 + 6 * s] = st[s].iterations;
+            out[2 + 6 * s] = st[s].successful;
+            out[3 + 6 * s] = st[s].evaluations;
+            out[4 + 6 * s] = st[s].cost_initial;
+            out[5 + 6 * s] = st[s].cost_final;
+            out[6 + 6 * s] = st[s].failed;
+        }
+        out[13] = (double) link.step;
+    }
+    if (tid < kMaxPairs) {
+        out[16 + tid] = tid < n ? (double) counts[tid] : 0.0;
+        out[32 + tid] = tid < n ? red[tid * kRedStride + 211] : 0.0;
+    }
+    for (int i = tid; i < NX; i += kFactorBlock) out[48 + i] = W.x[i];
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) st_release_sys(A.h_signal, A.seq);
+}
+
+__device__ void solve_evaluator(const SolveArgs &A, double *smem, int pair, int rank) {
+    PairShared &sh = *reinterpret_cast<PairShared *>(smem + kTileDoubles);
+    double *s_red  = smem + kCols * kColStride;
+    const int tid = threadIdx.x;
+    {
+        const unsigned long long *sw = reinterpret_cast<const unsigned long long *>(A.setup);
+        unsigned long long *dst      = reinterpret_cast<unsigned long long *>(&sh.su);
+        if (tid < kSetupLocal) dst[tid] = sw[tid < kSetupCommon ? tid : kSetupCommon + kSetupPair * pair + (tid - kSetupCommon)];
+    }
+    __syncthreads();
+    const int q = sh.su.q, tiles = (q + kFactorBlock - 1) / kFactorBlock, C = ctas_with_work(tiles, kFactorRanks);
+    if (rank >= C) return;
+    Unit *part  = A.part + (size_t) pair * kFactorRanks * kRedUnits;
+    Unit *inbox = A.inbox + (size_t) pair * kRedUnits;
+    const bool mine = tid < kPairMsg;
+    const int slot  = tid < kMsgHead ? tid : kMsgHead + 7 * pair + (tid - kMsgHead);
+    for (unsigned long long step = 1;; step++) {
+        const unsigned long long tag = A.base + step;
+        // ---- the solver's next broadcast
+        ulonglong2 v = make_ulonglong2(0, 0);
+        bool late    = false;
+        if (mine) {
+            const unsigned long long t0 = globaltimer_ns();
+            unsigned spins = 0;
+            while ((v = ld_slot_gpu(A.bcast + slot)).y != tag) {
+                __nanosleep(32);
+                if ((++spins & 63u) == 0 && globaltimer_ns() - t0 > A.hard_ns) {
+                    late = true;
+                    break;
+                }
+            }
+        }
+        if (__syncthreads_or(late)) return;   // the solver is gone: never spin forever
+        if (mine) sh.msg[tid] = v.x;
+        __syncthreads();
+        if ((unsigned) sh.msg[W_CMD] == kCmdRetire) return;
+        pair_prepare(sh);
+        if (sh.cmd == kCmdChi2) {
+            const int c = chi2_tiles(sh, rank, C, tiles);
+            if (rank != 0) {
+                if (tid == 0) st_unit_gpu(part + (size_t) rank * kRedUnits, (unsigned long long) c, 0ull, 0ull, tag);
+            } else if (tid == 0) {
+                int total = c;
+                bool ok   = true;
+                const unsigned long long t0 = globaltimer_ns();
+                for (int rk = 1; rk < C && ok; rk++) {
+                    Unit u;
+                    while ((u = ld_unit_gpu(part + (size_t) rk * kRedUnits)).tag != tag)
+                        if (globaltimer_ns() - t0 > A.hard_ns) {
+                            ok = false;
+                            break;
+                        }
+                    total += (int) u.w[0];
+                }
+                if (ok) st_unit_gpu(inbox, (unsigned long long) (unsigned) total, 0ull, 0ull, tag);
+            }
+            __syncthreads();
+            continue;
+        }
+        eval_tiles(sh, smem, pair, rank, C, tiles, true, nullptr, nullptr, nullptr);
+        if (rank != 0) {
+            if (tid < kRedUnits)
+                st_unit_gpu(part + (size_t) rank * kRedUnits + tid, d2w_dev(s_red[3 * tid]), d2w_dev(s_red[3 * tid + 1]),
+                            3 * tid + 2 < kRedSize ? d2w_dev(s_red[3 * tid + 2]) : 0ull, tag);
+        } else if (tid < kRedUnits) {
+            // the pair's sums in the order of fflins_window_eval: 0 + rank 0 + rank 1 + ... (see resident_kernel)
+            const unsigned long long t0 = globaltimer_ns();
+            Unit u[kFactorRanks];
+            unsigned pending = 0;
+#pragma unroll
+            for (int rk = 1; rk < kFactorRanks; rk++)
+                if (rk < C) pending |= 1u << rk;
+            bool ok = true;
+            while (pending) {
+#pragma unroll
+                for (int rk = 1; rk < kFactorRanks; rk++)
+                    if (pending & (1u << rk)) u[rk] = ld_unit_gpu(part + (size_t) rk * kRedUnits + tid);
+#pragma unroll
+                for (int rk = 1; rk < kFactorRanks; rk++)
+                    if ((pending & (1u << rk)) && u[rk].tag == tag) pending &= ~(1u << rk);
+                if (pending && globaltimer_ns() - t0 > A.hard_ns) {
+                    ok = false;
+                    break;
+                }
+            }
+            if (ok) {
+                unsigned long long o3[3];
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    const int e  = 3 * tid + k;
+                    double total = 0.0;
+                    total += e < kRedSize ? s_red[e] : 0.0;
+#pragma unroll
+                    for (int rk = 1; rk < kFactorRanks; rk++)
+                        if (rk < C) total += w2d(u[rk].w[k]);
+                    total += 0.0;
+                    o3[k] = d2w_dev(total);
+                }
+                st_unit_gpu(inbox + tid, o3[0], o3[1], o3[2], tag);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kFactorBlock) solve_kernel(const __grid_constant__ SolveArgs A) {
+    extern __shared__ __align__(16) double smem[];
+    const int bid = blockIdx.x;
+    if (bid == A.n * kFactorRanks) solver_cta(A, smem);
+    else solve_evaluator(A, smem, bid / kFactorRanks, bid % kFactorRanks);
+}
+
 __global__ void fp64_peak_kernel(double *out, int iters) {
     double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
     const double b = 1.0000001, c = 1e-7;
@@ -691,6 +1018,13 @@ struct FactorRuntime {
     int strikes = 0;
     unsigned long long evals_this_launch = 0;
     FactorStats st{};
+    // device-side window solve (solve_kernel): hand-off buffers, pinned result block, prior staging
+    ulonglong2 *d_sbcast = nullptr;
+    Unit *d_spart = nullptr, *d_sinbox = nullptr;
+    double *h_sout = nullptr, *h_prior = nullptr, *d_prior = nullptr;
+    unsigned long long *h_ssignal = nullptr;
+    unsigned long long solve_id = 0;
+    size_t solve_smem_max = 0;
     // diagnostics (FFLINS_RES_TIMELINE=1): where a resident evaluation's round trip goes
     bool timeline = false;
     long long *h_timeline = nullptr;
@@ -715,7 +1049,28 @@ FactorRuntime *factor_runtime_create(int device) {
               cudaMallocHost((void **) &rt->h_exit, sizeof(unsigned long long) * (kMaxRefs + 16)) == cudaSuccess &&
               cudaMalloc((void **) &rt->d_row, sizeof(ulonglong2) * kMaxRefs * kRowSlots) == cudaSuccess &&
               cudaMalloc((void **) &rt->d_part, sizeof(Unit) * kMaxRefs * kFactorRanks * kRedUnits) == cudaSuccess &&
-              cudaStreamCreateWithFlags(&rt->res_stream, cudaStreamNonBlocking) == cudaSuccess;
+              cudaStreamCreateWithFlags(&rt->res_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaMalloc((void **) &rt->d_sbcast, sizeof(ulonglong2) * 128) == cudaSuccess &&
+              cudaMalloc((void **) &rt->d_spart, sizeof(Unit) * kMaxPairs * kFactorRanks * kRedUnits) == cudaSuccess &&
+              cudaMalloc((void **) &rt->d_sinbox, sizeof(Unit) * kMaxPairs * kRedUnits) == cudaSuccess &&
+              cudaMalloc((void **) &rt->d_prior, sizeof(double) * kPriorDoubles) == cudaSuccess &&
+              cudaMallocHost((void **) &rt->h_prior, sizeof(double) * kPriorDoubles) == cudaSuccess &&
+              cudaMallocHost((void **) &rt->h_sout, sizeof(double) * (kSolveOutWords + 8)) == cudaSuccess;
+    if (ok) {
+        rt->h_ssignal = reinterpret_cast<unsigned long long *>(rt->h_sout + kSolveOutWords);
+        std::memset(rt->h_sout, 0, sizeof(double) * (kSolveOutWords + 8));
+        ok = cudaMemset(rt->d_sbcast, 0, sizeof(ulonglong2) * 128) == cudaSuccess &&
+             cudaMemset(rt->d_spart, 0, sizeof(Unit) * kMaxPairs * kFactorRanks * kRedUnits) == cudaSuccess &&
+             cudaMemset(rt->d_sinbox, 0, sizeof(Unit) * kMaxPairs * kRedUnits) == cudaSuccess;
+        cudaFuncAttributes fa{};
+        if (ok && cudaFuncGetAttributes(&fa, solve_kernel) == cudaSuccess) {
+            rt->solve_smem_max = kSolveSmemMax - fa.sharedSizeBytes;
+            if (cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) rt->solve_smem_max) != cudaSuccess) {
+                cudaGetLastError();
+                rt->solve_smem_max = 48 * 1024;   // the default limit: small windows only
+            }
+        }
+    }
     if (ok) {
         rt->wb.counts  = rt->wb.tickets + kMaxRefs;
         rt->h_signal   = reinterpret_cast<unsigned long long *>(rt->h_red + kMaxRefs * kRedSize);
@@ -1087,6 +1442,12 @@ void factor_runtime_destroy(FactorRuntime *rt) {
     if (rt->h_res) cudaFreeHost(rt->h_res);
     if (rt->h_exit) cudaFreeHost(rt->h_exit);
     if (rt->h_red) cudaFreeHost(rt->h_red);
+    if (rt->h_prior) cudaFreeHost(rt->h_prior);
+    if (rt->h_sout) cudaFreeHost(rt->h_sout);
+    cudaFree(rt->d_sbcast);
+    cudaFree(rt->d_spart);
+    cudaFree(rt->d_sinbox);
+    cudaFree(rt->d_prior);
     cudaFree(rt->d_setup);
     cudaFree(rt->wb.partials);
     cudaFree(rt->wb.tickets);
@@ -1108,6 +1469,84 @@ int launch_factor_eval(FactorRuntime *rt, cudaStream_t s, const FactorParams &p,
 int launch_chi2(FactorRuntime *rt, cudaStream_t s, const FactorParams &p, const float *points, int stride4, double threshold,
                 bool resident, FactorResults *res, int64_t *launches) {
     return run(rt, s, p, points, stride4, kCmdChi2, threshold, nullptr, nullptr, nullptr, false, nullptr, resident, res, launches);
+}
+
+int launch_window_solve(FactorRuntime *rt, cudaStream_t s, const FactorParams &p, const float *points, int stride4,
+                        const SolveOptions &opt, const double *H0, const double *b0, const double *x0, double c0, double *x_out,
+                        SolveReport *rep, int64_t *launches) {
+    const int n = p.n_pairs;
+    if (n <= 0 || n > kMaxPairs || p.q <= 0) return -(int) cudaErrorInvalidValue;
+    const int D = solve_dim(n), NX = solve_nx(n);
+    const size_t smem = std::max(kFactorSmem, solve_smem_doubles(n) * sizeof(double));
+    if (smem > rt->solve_smem_max) return -(int) cudaErrorInvalidValue;
+    FactorSetup su;
+    fill_setup(p, points, stride4, su);
+    cudaError_t e = push_setup(rt, s, su);
+    if (e != cudaSuccess) return -(int) e;
+    SolveArgs A{};
+    fill_msg(rt, p, kCmdEval, 0.0, 0, A.init);
+    A.setup = rt->d_setup + (rt->gen % kSetupRing);
+    A.opt   = opt;
+    A.opt.flags = (opt.flags | p.flags) & 0x1fu;
+    if (H0) {
+        double *h = rt->h_prior;
+        std::memcpy(h, H0, sizeof(double) * D * D);
+        std::memcpy(h + (size_t) D * D, b0, sizeof(double) * D);
+        std::memcpy(h + (size_t) D * D + D, x0, sizeof(double) * NX);
+        e = cudaMemcpyAsync(rt->d_prior, h, sizeof(double) * ((size_t) D * D + D + NX), cudaMemcpyHostToDevice, s);
+        if (e != cudaSuccess) return -(int) e;
+        A.prior = SolvePrior{rt->d_prior, rt->d_prior + (size_t) D * D, rt->d_prior + (size_t) D * D + D, c0};
+    } else {
+        A.prior = SolvePrior{nullptr, nullptr, nullptr, 0.0};
+    }
+    A.bcast    = rt->d_sbcast;
+    A.part     = rt->d_spart;
+    A.inbox    = rt->d_sinbox;
+    A.h_out    = rt->h_sout;
+    A.h_signal = rt->h_ssignal;
+    A.base     = (++rt->solve_id) << 20;
+    A.seq      = rt->solve_id;
+    A.hard_ns  = 200000000ull;
+    A.n        = n;
+    A.q        = p.q;
+    solve_kernel<<<n * kFactorRanks + 1, kFactorBlock, smem, s>>>(A);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return -(int) e;
+    if (launches) (*launches)++;
+    // the result block is written straight into pinned memory with the flag released behind it: poll, do not synchronise
+    unsigned spins = 0;
+    while (__atomic_load_n(rt->h_ssignal, __ATOMIC_ACQUIRE) != A.seq) {
+        if ((++spins & 0xfffu) == 0) {
+            e = cudaStreamQuery(s);
+            if (e == cudaSuccess) break;
+            if (e != cudaErrorNotReady) return -(int) e;
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    if (__atomic_load_n(rt->h_ssignal, __ATOMIC_ACQUIRE) != A.seq) return -(int) cudaErrorLaunchFailure;   // ended without an answer
+    const volatile double *o = rt->h_sout;
+    if (rep) {
+        std::memset(rep, 0, sizeof(*rep));
+        rep->status = (int) o[0];
+        for (int k = 0; k < 2; k++) {
+            rep->iterations[k]   = (int) o[1 + 6 * k];
+            rep->successful[k]   = (int) o[2 + 6 * k];
+            rep->evaluations[k]  = (int) o[3 + 6 * k];
+            rep->cost_initial[k] = o[4 + 6 * k];
+            rep->cost_final[k]   = o[5 + 6 * k];
+            rep->failed[k]       = (int) o[6 + 6 * k];
+        }
+        rep->steps = (int) o[13];
+        for (int i = 0; i < n; i++) {
+            rep->n_outliers[i] = (int) o[16 + i];
+            rep->n_res[i]      = (int) (o[32 + i] + 0.5);
+        }
+    }
+    if (x_out)
+        for (int i = 0; i < NX; i++) x_out[i] = o[48 + i];
+    return 0;
 }
 
 double measure_fp64_tflops(cudaStream_t s) {

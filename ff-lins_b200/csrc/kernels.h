@@ -296,6 +296,28 @@ int launch_factor_eval(FactorRuntime *rt, cudaStream_t s, const FactorParams &p,
 // K7: outlier flags are set in p.pair[i].outlier; per-pair counts land in res->counts. Same return convention.
 int launch_chi2(FactorRuntime *rt, cudaStream_t s, const FactorParams &p, const float *points, int stride4, double threshold,
                 bool resident, FactorResults *res, int64_t *launches);
+// ---- device-side window solve (k_factor.cu: solve_kernel, math_solve.cuh): Optimizer::optimization (optimizer.cc:85-185)
+// over the LiDAR factors of the window and a quadratic prior, one launch per keyframe.
+struct SolveOptions {
+    int max_iters[2];            // optimizer.cc:87-88
+    double chi2_threshold;       // <= 0: no cull between the two solves
+    double function_tolerance, gradient_tolerance, parameter_tolerance, initial_radius, min_relative_decrease;
+    unsigned flags;              // FFLINS_HUBER / FFLINS_CONST_* as in fflins_window_eval
+    unsigned fixed_refs;         // bit p: reference pose p is held constant
+};
+struct SolveReport {
+    int status;                  // 0 ok, 1 a hand-off inside the kernel timed out
+    int iterations[2], successful[2], evaluations[2], failed[2];
+    double cost_initial[2], cost_final[2];
+    int steps;                   // broadcasts of the solver CTA (evaluations + chi2 + retire)
+    int n_outliers[kMaxRefs], n_res[kMaxRefs];
+};
+// State layout x: n reference poses, the current pose, the extrinsic (7 doubles each: t, q = x y z w), td; the prior
+// (host pointers, H0 == nullptr: none) is 0.5 d^T H0 d - b0^T d + c0 over the tangent [6 n | 6 | 6 | 1], d = x (-) x0.
+// Synchronous: returns after the result has arrived in pinned memory. 0 ok, < 0 cudaError_t negated.
+int launch_window_solve(FactorRuntime *rt, cudaStream_t s, const FactorParams &p, const float *points, int stride4,
+                        const SolveOptions &opt, const double *H0, const double *b0, const double *x0, double c0, double *x_out,
+                        SolveReport *rep, int64_t *launches);
 // fp64 FMA throughput of the device (the roofline of K6): TFLOP/s of a register-resident DFMA loop on every SM.
 double measure_fp64_tflops(cudaStream_t s);
 

@@ -25,7 +25,8 @@ EXPORTS = [
     "fflins_features_download", "fflins_features_set_outlier", "fflins_factor_eval_batch", "fflins_factor_eval",
     "fflins_window_eval", "fflins_window_chi2", "fflins_profile_enable", "fflins_profile_reset", "fflins_profile_get",
     "fflins_launch_count", "fflins_timer_start", "fflins_timer_stop", "fflins_reproject_window",
-    "fflins_eval_stats_get", "fflins_measure_fp64", "fflins_host_buffer_done",
+    "fflins_eval_stats_get", "fflins_measure_fp64", "fflins_host_buffer_done", "fflins_solve_options_default",
+    "fflins_window_solve",
 ]
 
 
@@ -51,6 +52,22 @@ class Pose(C.Structure):
 
     def numpy(self):
         return np.array(self.R[:]).reshape(3, 3), np.array(self.t[:])
+
+
+class SolveOptions(C.Structure):
+    _fields_ = [("max_iterations", C.c_int32 * 2), ("chi2_threshold", C.c_double), ("function_tolerance", C.c_double),
+                ("gradient_tolerance", C.c_double), ("parameter_tolerance", C.c_double), ("initial_radius", C.c_double),
+                ("flags", C.c_uint32), ("fixed_refs", C.c_uint32)]
+
+
+class SolvePrior(C.Structure):
+    _fields_ = [("H0", C.c_void_p), ("b0", C.c_void_p), ("x0", C.c_void_p), ("c0", C.c_double)]
+
+
+class SolveReport(C.Structure):
+    _fields_ = [("status", C.c_int32), ("iterations", C.c_int32 * 2), ("successful", C.c_int32 * 2),
+                ("evaluations", C.c_int32 * 2), ("cost_initial", C.c_double * 2), ("cost_final", C.c_double * 2),
+                ("n_outliers", C.c_int32 * 16), ("n_res", C.c_int32 * 16)]
 
 
 class FrameInfo(C.Structure):
@@ -86,6 +103,7 @@ def load():
         L.fflins_launch_count.restype = C.c_int64
         L.fflins_destroy.restype = None
         L.fflins_config_default.restype = None
+        L.fflins_solve_options_default.restype = None
         _LIB = L
     return _LIB
 
@@ -442,6 +460,37 @@ class Context:
         self._ck(self.L.fflins_window_chi2(self.h, prep["n"], prep["ids_p"], prep["refs_p"], prep["cur_p"], prep["ext_p"],
                                            C.c_double(td), C.c_double(threshold), _p(cnt)))
         return cnt[:prep["n"]]
+
+    def solve_options(self, **kw):
+        o = SolveOptions()
+        self.L.fflins_solve_options_default(C.byref(o))
+        for k, v in kw.items():
+            if k == "max_iterations":
+                o.max_iterations[0], o.max_iterations[1] = int(v[0]), int(v[1])
+            else:
+                setattr(o, k, v)
+        return o
+
+    def window_solve(self, ref_ids, pose_refs, pose_cur, ext, td, options=None, prior=None):
+        """fflins_window_solve: the 5 + chi2 + 10 Levenberg-Marquardt schedule on the device, one launch.
+        prior = (H0 [D, D], b0 [D], x0 [7 n + 15], c0) or None. Returns (pose_refs, pose_cur, ext, td, report)."""
+        ids = np.array(list(ref_ids), np.uint64)
+        n = len(ids)
+        refs = np.array(_c(pose_refs, np.float64).reshape(n, 7), copy=True)
+        cur, ex = np.array(_pose7(pose_cur), copy=True), np.array(_pose7(ext), copy=True)
+        tdv = C.c_double(td)
+        opt = options if options is not None else self.solve_options()
+        rep = SolveReport()
+        pr, keep = None, None
+        if prior is not None:
+            H0, b0, x0, c0 = prior
+            keep = (_c(H0, np.float64), _c(b0, np.float64), _c(x0, np.float64))
+            D = 6 * n + 13
+            assert keep[0].shape == (D, D) and keep[1].shape == (D,) and keep[2].shape == (7 * n + 15,)
+            pr = SolvePrior(keep[0].ctypes.data, keep[1].ctypes.data, keep[2].ctypes.data, float(c0))
+        self._ck(self.L.fflins_window_solve(self.h, n, _p(ids), _p(refs), _p(cur), _p(ex), C.byref(tdv), C.byref(opt),
+                                            C.byref(pr) if pr is not None else None, C.byref(rep)))
+        return refs, cur, ex, tdv.value, rep
 
     def window_chi2(self, ref_ids, pose_refs, pose_cur, ext, td, threshold=3.841):
         ids = np.array(list(ref_ids), np.uint64)

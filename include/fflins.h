@@ -235,6 +235,45 @@ int fflins_window_chi2(fflins_ctx *ctx, int32_t n_pairs, const uint64_t *ref_ids
                        const double pose_cur[7], const double ext[7], double td, double threshold,
                        int32_t *n_outliers);
 
+/* ---- the window solve on the device ----------------------------------------------------- */
+/* Optimizer::optimization (optimizer.cc:85-185) over the LiDAR factors of the window: Levenberg-Marquardt with
+ * max_iterations[0] iterations, the chi2 cull (optimizer.cc:515-548), max_iterations[1] iterations, as ONE kernel
+ * launch: evaluation (lidar_factor.cc:41-118), J^T J reduction (marginalization_info.cc:181-210), assembly of the
+ * window's normal equations, factorisation, PoseManifold::Plus (pose_manifold.cc:35-50) and the accept / reject
+ * decision all happen on the device; only the final state returns. fflins_window_eval remains the entry point for a
+ * host solver (Ceres) that wants the blocks of every iteration.
+ * State: n reference poses, the current pose, the extrinsic (7 doubles: t, q = x y z w), td. Tangent vector
+ * [ref 0 .. ref n-1 | cur | ext | td], D = 6 n + 13. Everything that is not a LiDAR factor enters as a quadratic
+ * prior 0.5 d^T H0 d - b0^T d + c0 with d = x (-) x0 as in MarginalizationFactor::Evaluate
+ * (marginalization_factor.cc:37-91; H0 = J0^T J0, b0 = -J0^T e0, c0 = 0.5 e0^T e0). */
+typedef struct fflins_solve_options {
+    int32_t  max_iterations[2];    /* 5, 10 (optimizer.cc:87-88)                                        */
+    double   chi2_threshold;       /* 3.841 (optimizer.cc:516); <= 0: no cull between the two solves    */
+    double   function_tolerance;   /* 1e-6  \                                                           */
+    double   gradient_tolerance;   /* 1e-10  > Ceres defaults; 0 disables the early exit                */
+    double   parameter_tolerance;  /* 1e-8  /                                                           */
+    double   initial_radius;       /* 1e4                                                               */
+    uint32_t flags;                /* FFLINS_HUBER | FFLINS_CONST_*                                      */
+    uint32_t fixed_refs;           /* bit i: reference pose i is held constant                          */
+} fflins_solve_options;
+void fflins_solve_options_default(fflins_solve_options *o);
+typedef struct fflins_solve_prior {
+    const double *H0;              /* D x D, symmetric, row-major */
+    const double *b0;              /* D                           */
+    const double *x0;              /* 7 n + 15: linearisation point in the state layout */
+    double        c0;
+} fflins_solve_prior;
+typedef struct fflins_solve_report {
+    int32_t status;                /* 0 ok */
+    int32_t iterations[2], successful[2], evaluations[2];
+    double  cost_initial[2], cost_final[2];
+    int32_t n_outliers[16], n_res[16];
+} fflins_solve_report;
+/* pose_refs [7 n], pose_cur, ext, td: in = initial state, out = solution. prior and report may be NULL. */
+int fflins_window_solve(fflins_ctx *ctx, int32_t n_pairs, const uint64_t *ref_ids, double *pose_refs, double pose_cur[7],
+                        double ext[7], double *td, const fflins_solve_options *opt, const fflins_solve_prior *prior,
+                        fflins_solve_report *report);
+
 /* ---- measurement ------------------------------------------------------------------------- */
 /* Per-kernel CUDA-event timing on the context's stream (off by default). */
 int fflins_profile_enable(fflins_ctx *ctx, int on);

@@ -52,6 +52,24 @@ def test_struct_layouts_match_the_header(tmp_path):
                      api.FrameInfo.pose.offset, api.Config.max_points_per_frame.offset]
 
 
+def test_solve_struct_layouts_match_the_header(tmp_path):
+    from fflins import api
+    prog = tmp_path / "sizes2.c"
+    prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "fflins.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n",'
+                    'sizeof(fflins_solve_options),sizeof(fflins_solve_prior),sizeof(fflins_solve_report),'
+                    'offsetof(fflins_solve_options,flags),offsetof(fflins_solve_report,cost_initial),'
+                    'offsetof(fflins_solve_report,n_res));return 0;}\n')
+    exe = tmp_path / "sizes2"
+    subprocess.check_call(["gcc" if not os.path.exists("/usr/bin/gcc") else "/usr/bin/gcc", "-I", os.path.join(ROOT, "include"),
+                           str(prog), "-o", str(exe)])
+    sizes = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    assert sizes == [C.sizeof(api.SolveOptions), C.sizeof(api.SolvePrior), C.sizeof(api.SolveReport), api.SolveOptions.flags.offset,
+                     api.SolveReport.cost_initial.offset, api.SolveReport.n_res.offset]
+    o = api.SolveOptions()
+    api.load().fflins_solve_options_default(C.byref(o))
+    assert (o.max_iterations[0], o.max_iterations[1], o.chi2_threshold, o.flags) == (5, 10, 3.841, 1)   # optimizer.cc:87-88, 516
+
+
 def test_header_is_plain_c(tmp_path):
     prog = tmp_path / "c89.c"
     prog.write_text('#include "fflins.h"\nint main(void){fflins_config c; fflins_config_default(&c); return c.window_size == 10 ? 0 : 1;}\n')

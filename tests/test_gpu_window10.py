@@ -411,3 +411,119 @@ def test_resident_quiet_mode_matches_launched(tmp_path):
     out = subprocess.run([sys.executable, str(script), root], env=dict(os.environ, FFLINS_QUIET="1"), capture_output=True, text=True,
                          timeout=900)
     assert out.returncode == 0 and "QUIET_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
+# ---- fflins_window_solve: the 5 + chi2 + 10 schedule on the device (one launch per keyframe) ------------------------------
+def _solve_setup(c, seq, keys, seed, trans=0.03, rot=0.004):
+    import lm_ref
+    rng = np.random.default_rng(seed)
+    c.associate()
+    pose_refs, pose_cur, ext, td = window_params(seq, keys, rng)
+    refs = [k["id"] for k in keys[:-1]]
+    n = len(refs)
+    x = np.concatenate([pose_refs.reshape(-1), pose_cur, ext, [td]])
+    for k in range(n + 1):   # a solver has something to do: every pose starts off its optimum
+        x[7 * k:7 * k + 7] = lm_ref.pose_plus(x[7 * k:7 * k + 7], np.concatenate([rng.normal(size=3) * trans, rng.normal(size=3) * rot]))
+    return rng, refs, n, x
+
+
+def _clear_outliers(c, refs):
+    for r in refs:
+        c.set_outlier(r, np.zeros(len(c.features(r)["outlier"]), np.uint8))
+
+
+def _dense_prior(rng, n, x0, weight):
+    D = 6 * n + 13
+    J0 = rng.normal(size=(D + 5, D)) * np.sqrt(weight)
+    e0 = rng.normal(size=D + 5) * 0.1
+    return J0.T @ J0, -J0.T @ e0, x0.copy(), 0.5 * e0 @ e0
+
+
+def _host_lm(c, refs, n, x, flags, prior, fixed_refs=0, **kw):
+    """The same solve driven from the host: numpy LM (tests/lm_ref.py) over fflins_window_eval / fflins_window_chi2."""
+    import lm_ref
+
+    def ev(xx):
+        o = c.window_eval(refs, xx[:7 * n].reshape(n, 7), xx[7 * n:7 * n + 7], xx[7 * n + 7:7 * n + 14], float(xx[7 * n + 14]), flags)
+        return o["H"], o["b"], o["cost"]
+
+    def chi2(xx, thr):
+        return c.window_chi2(refs, xx[:7 * n].reshape(n, 7), xx[7 * n:7 * n + 7], xx[7 * n + 7:7 * n + 14], float(xx[7 * n + 14]), thr)
+    return lm_ref.window_solve(ev, chi2, n, x, flags, prior=prior, fixed_refs=fixed_refs, **kw)
+
+
+def _device_solve(c, refs, n, x, flags, prior, fixed_refs=0, **kw):
+    opt = c.solve_options(flags=flags, fixed_refs=fixed_refs, **kw)
+    pr, pc, ex, td, rep = c.window_solve(refs, x[:7 * n].reshape(n, 7), x[7 * n:7 * n + 7], x[7 * n + 7:7 * n + 14], float(x[7 * n + 14]),
+                                         options=opt, prior=prior)
+    return np.concatenate([pr.reshape(-1), pc, ex, [td]]), rep
+
+
+def _check_solve(c, seq, keys, seed, flags, with_prior, fixed_refs=0, weight=400.0):
+    rng, refs, n, x = _solve_setup(c, seq, keys, seed)
+    prior = _dense_prior(rng, n, x, weight) if with_prior else None
+    _clear_outliers(c, refs)
+    xd, rep = _device_solve(c, refs, n, x, flags, prior, fixed_refs)
+    out_d = [c.features(r)["outlier"].copy() for r in refs]
+    _clear_outliers(c, refs)
+    xh, (s0, s1), counts = _host_lm(c, refs, n, x, flags, prior, fixed_refs)
+    out_h = [c.features(r)["outlier"].copy() for r in refs]
+    _clear_outliers(c, refs)
+    assert rep.status == 0
+    assert [rep.iterations[0], rep.successful[0], rep.evaluations[0]] == [s0["iterations"], s0["successful"], s0["evaluations"]]
+    assert [rep.iterations[1], rep.successful[1], rep.evaluations[1]] == [s1["iterations"], s1["successful"], s1["evaluations"]]
+    assert s0["successful"] >= 1 and rep.cost_final[1] < rep.cost_initial[0]
+    assert list(rep.n_outliers[:n]) == list(counts) and all(np.array_equal(a, b) for a, b in zip(out_d, out_h))
+    assert abs(rep.cost_initial[0] - s0["cost_initial"]) <= 1e-9 * s0["cost_initial"]
+    assert abs(rep.cost_final[1] - s1["cost_final"]) <= 1e-9 * s1["cost_final"]
+    assert np.max(np.abs(xd - xh)) <= 1e-9, np.max(np.abs(xd - xh))   # fp64 state: <= 1e-9 absolute (m, quaternion units, s)
+    return xd, rep, x
+
+
+def test_window_solve_full_window_with_prior(window10):
+    """The benched shape: 10 references, every pose, the extrinsic and td free, a dense prior (D = 73)."""
+    c, seq, keys = window10
+    xd, rep, x0 = _check_solve(c, seq, keys, 41, 1, True)
+    assert np.max(np.abs(xd - x0)) > 1e-4
+
+
+def test_window_solve_registration_only(window10):
+    """References, extrinsic and td constant, no prior: scan-to-window registration of the newest keyframe."""
+    c, seq, keys = window10
+    xd, rep, x0 = _check_solve(c, seq, keys, 42, 1 | 2 | 8 | 16, False)
+    n = len(keys) - 1
+    assert np.array_equal(xd[:7 * n], x0[:7 * n]) and np.array_equal(xd[7 * n + 7:], x0[7 * n + 7:])
+    truth = seq.imu_pose7(keys[-1]["fr"]["stamp"])
+    assert np.linalg.norm(xd[7 * n:7 * n + 3] - truth[:3]) < np.linalg.norm(x0[7 * n:7 * n + 3] - truth[:3])
+
+
+def test_window_solve_gauge_fixed_and_ext_const(window10):
+    c, seq, keys = window10
+    _check_solve(c, seq, keys, 43, 1 | 8 | 16, True, fixed_refs=0b1, weight=25.0)
+
+
+def test_window_solve_14_references(window15):
+    """D = 97: the largest window the context accepts."""
+    c, seq, keys = window15
+    _check_solve(c, seq, keys, 44, 1, True)
+
+
+def test_window_solve_is_deterministic_and_coexists_with_the_resident_kernel(window10):
+    c, seq, keys = window10
+    rng, refs, n, x = _solve_setup(c, seq, keys, 45)
+    prior = _dense_prior(rng, n, x, 400.0)
+    args = (refs, x[:7 * n].reshape(n, 7), x[7 * n:7 * n + 7], x[7 * n + 7:7 * n + 14], float(x[7 * n + 14]))
+    _clear_outliers(c, refs)
+    before = c.window_eval(*args, 1)           # (starts the resident evaluation kernel)
+    xa, ra = _device_solve(c, refs, n, x, 1, prior)
+    _clear_outliers(c, refs)
+    xb, rb = _device_solve(c, refs, n, x, 1, prior)
+    _clear_outliers(c, refs)
+    after = c.window_eval(*args, 1)
+    assert bits_equal(xa, xb) and ra.cost_final[1] == rb.cost_final[1] and list(ra.n_outliers) == list(rb.n_outliers)
+    for k in ("H", "b", "cost", "n_res"):
+        assert bits_equal(before[k], after[k])
+    # tolerances off: the schedule runs to its iteration limits (what bench.py times)
+    xc, rc = _device_solve(c, refs, n, x, 1, prior, function_tolerance=0.0, gradient_tolerance=0.0, parameter_tolerance=0.0)
+    _clear_outliers(c, refs)
+    assert rc.iterations[0] == 5 and rc.iterations[1] == 10 and rc.evaluations[0] + rc.evaluations[1] <= 17
