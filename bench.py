@@ -244,6 +244,8 @@ class NativeSession:
         L.drv_error.argtypes = [ctypes.c_void_p]
         L.drv_last_assoc.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.drv_last_nres.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        L.drv_set_solve.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.drv_last_solve.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.drv_eval_roundtrip_us.restype = ctypes.c_double
         L.drv_eval_roundtrip_us.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
         self._pose = api.Pose.make(seq.R_bl, seq.t_bl)
@@ -280,6 +282,14 @@ class NativeSession:
         out = (ctypes.c_int32 * 16)()
         k = self.L.drv_last_nres(self.h, out)
         return int(sum(out[i] for i in range(min(k, 16))))
+
+    def set_solve(self, on):
+        self.L.drv_set_solve(self.h, 1 if on else 0)
+
+    def last_solve(self):
+        it, ev = (ctypes.c_int32 * 2)(), (ctypes.c_int32 * 2)()
+        st = self.L.drv_last_solve(self.h, it, ev)
+        return {"status": st, "iterations": [it[0], it[1]], "evaluations": [ev[0], ev[1]]}
 
     def eval_roundtrip_us(self):
         v = self.L.drv_eval_roundtrip_us(self.h, 20, 200)
@@ -438,6 +448,29 @@ def run_ours(args, rank, world, local_rank):
     value = frames_total / (dev_ms / 1e3)
     e2e_value = frames_total / (e2e_dev_ms / 1e3)
 
+    # the same steps with each keyframe's 6 + chi2 + 11 evaluations replaced by ONE fflins_window_solve (the LM loop on the
+    # device: assembly, factorisation and the manifold update included, which the round-trip sequence leaves to its caller)
+    device_solve = None
+    if native and not args.no_device_solve:
+        nsess.set_solve(True)
+        for _ in range(warm):
+            step("dev")
+        ds_ms, _, ds_launches, ds_rep = timed("dev", args.steps, 3)
+        for _ in range(warm):
+            step("host")
+        ds_e2e_ms, _, _, ds_e2e_rep = timed("host", args.steps, 3)
+        device_solve = {"value": round(frames_total / (ds_ms / 1e3), 2), "ms_per_step": round(ds_ms / args.steps, 4),
+                        "e2e": round(frames_total / (ds_e2e_ms / 1e3), 2), "e2e_ms_per_step": round(ds_e2e_ms / args.steps, 4),
+                        "unit": "frames/s", "gpu_launches": int(ds_launches), "last_solve": nsess.last_solve(),
+                        "ms_per_step_repetitions": ds_rep, "e2e_ms_per_step_repetitions": ds_e2e_rep,
+                        "note": "labelled extra figure, not the headline: each keyframe's solve is one fflins_window_solve call "
+                                "(5 + chi2 + 10 Levenberg-Marquardt iterations at their limits, every pose / extrinsic / td free, "
+                                "diagonal prior, D = 6 n + 13) - evaluation, reduction, assembly, factorisation and "
+                                "PoseManifold::Plus on the device, one host round trip per keyframe instead of 16"}
+        nsess.set_solve(False)
+        for _ in range(3):
+            step("dev")
+
     # per-stage CUDA-event breakdown (separate pass: event pairs around every kernel group)
     stages, roof = {}, None
     if rank == 0:
@@ -583,6 +616,7 @@ def run_ours(args, rank, world, local_rank):
             "roofline": roof,
             "stages": stages,
             "roofline_batched": batched,
+            "device_solve": device_solve,
             "shim": shim,
             "cpu_baseline": cpu,
             "workload_sizes": {"Q": q_last, "M": last_m, "M_window": m_window},
@@ -852,6 +886,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-batched", action="store_true", help="skip the batched per-kernel roofline pass")
     ap.add_argument("--no-shim", action="store_true", help="skip the drop-in (C++ shim) figure")
+    ap.add_argument("--no-device-solve", action="store_true", help="skip the fflins_window_solve figure")
     ap.add_argument("--frames", type=int, default=None, help="distinct synthetic frames to cycle over (default: one lap)")
     ap.add_argument("--prefill", type=int, default=None, help="untimed keyframes that fill the window (default 11)")
     ap.add_argument("--settle", type=float, default=0.5, help="seconds of untimed steps before the timed region (0 for profiler runs)")

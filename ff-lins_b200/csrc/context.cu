@@ -2572,6 +2572,7 @@ int fflins_window_solve(fflins_ctx *ctx, int32_t n_pairs, const uint64_t *ref_id
             report->n_outliers[i] = R.n_outliers[i];
             report->n_res[i]      = R.n_res[i];
         }
+        std::memcpy(report->phase_cycles, R.phase_cycles, sizeof(report->phase_cycles));
     }
     if (R.status != 0) return fail(ctx, FFLINS_E_CUDA, "window solve: a hand-off inside the kernel timed out");
     std::memcpy(pose_refs, x.data(), sizeof(double) * 7 * (size_t) n_pairs);

@@ -662,10 +662,15 @@ __global__ void __launch_bounds__(kFactorBlock) resident_kernel(const __grid_con
 // message layout of FactorMsg), the evaluators answer with their pair's 212 sums (ranks 1..7 -> rank 0 -> solver,
 // tagged 32-byte units, summed in the order of fflins_window_eval), the solver assembles the D x D normal equations
 // in shared memory (D = 6 n + 13), factors them, applies PoseManifold::Plus and decides (math_solve.cuh). Tags are
-// base + step with a base unique to the launch; every wait is bounded. All CTAs must be co-resident: at most
-// 8 * 15 + 1 = 121 CTAs of 128 threads, one per SM (the solver's shared-memory footprint is the kernel's).
-constexpr int kSolveOutWords = 48 + kSolveMaxX;   // status | 2 x 6 stage words | steps | 16 outlier counts | 16 n_res | state
-constexpr int kGatherItems   = (kMaxPairs * kRedUnits + kFactorBlock - 1) / kFactorBlock;   // 9
+// base + step with a base unique to the launch; every wait is bounded. The evaluators (solve_eval_kernel: 8 n CTAs of
+// 128 threads, compute stream) and the solver (solve_ctl_kernel: ONE CTA of 512 threads with the normal equations in
+// its shared memory, its own stream) are two kernels that must be co-resident: with four warps the solver's
+// dependent shared-memory chains ran at one warp per scheduler (84 us per iteration), with 16 warps the parallel loops
+// hide their latency and the barriers of the elimination are what is left.
+constexpr int kSolveOutWords = 48 + kSolveMaxX + 8;   // status | 2 x 6 stage words | steps | 16 outlier counts | 16 n_res | state | 8 phase cycles
+constexpr int kCtlThreads    = 512;
+constexpr int kCtlWarps      = kCtlThreads / 32;
+constexpr int kGatherItems   = (kMaxPairs * kRedUnits + kCtlThreads - 1) / kCtlThreads;   // 3
 
 struct SolveArgs {
     FactorMsg init;                 // the initial state in message layout
@@ -681,32 +686,72 @@ struct SolveArgs {
     int n, q;
 };
 
-struct ParCta {
-    double *scratch;   // shared, kWarps doubles
+struct ParCta {   // the solver CTA: kCtlThreads threads
+    double *scratch;   // shared, kCtlWarps doubles
+    long long *tl;     // shared, 9: cycles per phase (thread 0), [8] = last stamp
+    __device__ void stamp(int k) const {
+        if (threadIdx.x == 0) {
+            const long long now = clock64();
+            tl[k] += now - tl[8];
+            tl[8] = now;
+        }
+    }
     __device__ int tid() const { return threadIdx.x; }
-    __device__ int nthr() const { return kFactorBlock; }
+    __device__ int nthr() const { return kCtlThreads; }
     __device__ void sync() const { __syncthreads(); }
-    __device__ double sum(double v) const {
+    __device__ int lanes() const { return 32; }
+    __device__ void syncwarp() const { __syncwarp(); }
+    __device__ int warp() const { return threadIdx.x >> 5; }
+    __device__ int nwarps() const { return kCtlWarps; }
+    __device__ int lane() const { return threadIdx.x & 31; }
+    __device__ double warp_sum(double v) const {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    }
+    // butterfly within the warps, then the same butterfly over the warps' sums: a fixed tree, the same value in every thread
+    __device__ double sum(double v) const {
+        v = warp_sum(v);
         if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
         __syncthreads();
-        double s = scratch[0];
-#pragma unroll
-        for (int w = 1; w < kWarps; w++) s += scratch[w];
+        double s = (threadIdx.x & 31) < kCtlWarps ? scratch[threadIdx.x & 31] : 0.0;
         __syncthreads();
-        return s;
+        return warp_sum(s);
     }
     __device__ double max(double v) const {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
         if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
         __syncthreads();
-        double s = scratch[0];
-#pragma unroll
-        for (int w = 1; w < kWarps; w++) s = fmax(s, scratch[w]);
+        double s = (threadIdx.x & 31) < kCtlWarps ? scratch[threadIdx.x & 31] : 0.0;   // (only ever called with values >= 0)
         __syncthreads();
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s = fmax(s, __shfl_xor_sync(0xffffffffu, s, o));
         return s;
+    }
+    // back substitution by the first warp: lane l keeps y_r for r = l, l + 32, l + 64, l + 96 in registers, x_k travels by
+    // shuffle from its owner, the column entries A[r][k] are fetched before x_k is known. Same operations per entry and in
+    // the same order as ParSerial::backsub.
+    __device__ void backsub(int D, int ld, const double *A, const double *dinv, double *rhs, double *x_out) const {
+        if (threadIdx.x < 32) {
+            const int lane = threadIdx.x;
+            double y[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) y[j] = lane + 32 * j < D ? rhs[lane + 32 * j] : 0.0;
+            for (int k = D - 1; k >= 0; k--) {
+                double c[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) c[j] = lane + 32 * j < k ? A[(lane + 32 * j) * ld + k] : 0.0;
+                const int owner = k & 31, slot = k >> 5;
+                double mine = slot == 0 ? y[0] : (slot == 1 ? y[1] : (slot == 2 ? y[2] : y[3]));
+                const double xk = __shfl_sync(0xffffffffu, mine * dinv[k], owner);
+                if (lane == 0) x_out[k] = xk;
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (lane + 32 * j < k) y[j] -= c[j] * xk;
+            }
+        }
+        __syncthreads();
     }
 };
 
@@ -745,20 +790,20 @@ struct SolveLink {
         unsigned pending = 0;
 #pragma unroll
         for (int k = 0; k < kGatherItems; k++)
-            if (tid + kFactorBlock * k < items) pending |= 1u << k;
+            if (tid + kCtlThreads * k < items) pending |= 1u << k;
         const unsigned long long t0 = globaltimer_ns();
         bool late = false;
         while (pending && !late) {
 #pragma unroll
             for (int k = 0; k < kGatherItems; k++)
                 if (pending & (1u << k)) {
-                    const int idx = tid + kFactorBlock * k, p = chi2 ? idx : idx / kRedUnits, uu = chi2 ? 0 : idx - p * kRedUnits;
+                    const int idx = tid + kCtlThreads * k, p = chi2 ? idx : idx / kRedUnits, uu = chi2 ? 0 : idx - p * kRedUnits;
                     u[k] = ld_unit_gpu(A.inbox + (size_t) p * kRedUnits + uu);
                 }
 #pragma unroll
             for (int k = 0; k < kGatherItems; k++)
                 if ((pending & (1u << k)) && u[k].tag == tag) {
-                    const int idx = tid + kFactorBlock * k, p = chi2 ? idx : idx / kRedUnits, uu = chi2 ? 0 : idx - p * kRedUnits;
+                    const int idx = tid + kCtlThreads * k, p = chi2 ? idx : idx / kRedUnits, uu = chi2 ? 0 : idx - p * kRedUnits;
                     if (chi2) {
                         counts[p] = (int) u[k].w[0];
                     } else {
@@ -780,16 +825,19 @@ struct SolveLink {
             bad = true;
             return 0.0;
         }
-        return solve_assemble(par, *W, A.prior, x, red, H, g);
+        par.stamp(0);
+        const double cost = solve_assemble(par, *W, A.prior, x, red, H, g);
+        par.stamp(1);
+        return cost;
     }
     __device__ bool failed() const { return bad; }
 };
 
 __host__ __device__ inline size_t solve_smem_doubles(int n) {
     const int D = solve_dim(n), ld = solve_ld(D);
-    size_t d = 2 * (size_t) D * ld + 6 * (size_t) ld + 2 * (size_t) solve_nx(n) + (size_t) n * kRedStride + 8;
+    size_t d = 2 * (size_t) D * ld + 6 * (size_t) ld + 2 * (size_t) solve_nx(n) + (size_t) n * kRedStride + kCtlWarps + 9;
     d += ((size_t) (D - 1) * D / 2 * sizeof(unsigned short) + 7) / 8;   // elimination table
-    d += (D + 7) / 8 + (kMaxPairs * sizeof(int) + 7) / 8;               // fixed mask, chi2 counts
+    d += 2 * ((D + 7) / 8) + (kMaxPairs * sizeof(int) + 7) / 8 + 1;     // fixed mask, free index list, chi2 counts, Df
     return d;
 }
 
@@ -814,17 +862,22 @@ __device__ void solver_cta(const SolveArgs &A, double *smem) {
     W.x     = p; p += NX;
     W.xc    = p; p += NX;
     double *red     = p; p += (size_t) n * kRedStride;
-    double *scratch = p; p += 8;
+    double *scratch = p; p += kCtlWarps;
+    long long *tl   = reinterpret_cast<long long *>(p); p += 9;
     unsigned short *tri = reinterpret_cast<unsigned short *>(p);
     p += ((size_t) (D - 1) * D / 2 * sizeof(unsigned short) + 7) / 8;
     unsigned char *fixed = reinterpret_cast<unsigned char *>(p);
     p += (D + 7) / 8;
+    unsigned char *free_idx = reinterpret_cast<unsigned char *>(p);
+    p += (D + 7) / 8;
     int *counts = reinterpret_cast<int *>(p);
+    p += (kMaxPairs * sizeof(int) + 7) / 8;
+    int *s_df = reinterpret_cast<int *>(p);
     W.tri   = tri;
     W.fixed = fixed;
-    solve_fill_tri(tid, kFactorBlock, D, tri);
-    solve_fill_fixed(tid, kFactorBlock, n, A.opt.flags, A.opt.fixed_refs, fixed);
-    for (int i = tid; i < NX; i += kFactorBlock) {
+    solve_fill_tri(tid, kCtlThreads, D, tri);
+    solve_fill_fixed(tid, kCtlThreads, n, A.opt.flags, A.opt.fixed_refs, fixed);
+    for (int i = tid; i < NX; i += kCtlThreads) {
         unsigned long long w;
         if (i < 7 * n) w = A.init.w[W_REF + i];
         else if (i < 7 * n + 7) w = A.init.w[W_CUR + (i - 7 * n)];
@@ -832,9 +885,15 @@ __device__ void solver_cta(const SolveArgs &A, double *smem) {
         else w = A.init.w[W_TD];
         W.x[i] = w2d(w);
     }
-    if (tid < kMaxPairs) counts[tid] = 0;
     __syncthreads();
-    SolveLink link{A, ParCta{scratch}, &W, red, counts, 0ull, false};
+    if (tid == 0) *s_df = solve_fill_free(D, fixed, free_idx);
+    if (tid < kMaxPairs) counts[tid] = 0;
+    if (tid < 8) tl[tid] = 0;
+    if (tid == 8) tl[8] = clock64();
+    __syncthreads();
+    W.free_idx = free_idx;
+    W.Df       = *s_df;
+    SolveLink link{A, ParCta{scratch, tl}, &W, red, counts, 0ull, false};
     SolveStage st[2];
     st[0] = solve_lm(link.par, W, A.opt, A.opt.max_iters[0], link);
     if (!link.bad && A.opt.chi2_threshold > 0.0) {
@@ -862,7 +921,8 @@ __device__ void solver_cta(const SolveArgs &A, double *smem) {
         out[16 + tid] = tid < n ? (double) counts[tid] : 0.0;
         out[32 + tid] = tid < n ? red[tid * kRedStride + 211] : 0.0;
     }
-    for (int i = tid; i < NX; i += kFactorBlock) out[48 + i] = W.x[i];
+    for (int i = tid; i < NX; i += kCtlThreads) out[48 + i] = W.x[i];
+    if (tid < 8) out[48 + kSolveMaxX + tid] = (double) tl[tid];
     __threadfence_system();
     __syncthreads();
     if (tid == 0) st_release_sys(A.h_signal, A.seq);
@@ -973,11 +1033,13 @@ __device__ void solve_evaluator(const SolveArgs &A, double *smem, int pair, int 
     }
 }
 
-__global__ void __launch_bounds__(kFactorBlock) solve_kernel(const __grid_constant__ SolveArgs A) {
+__global__ void __launch_bounds__(kFactorBlock) solve_eval_kernel(const __grid_constant__ SolveArgs A) {
     extern __shared__ __align__(16) double smem[];
-    const int bid = blockIdx.x;
-    if (bid == A.n * kFactorRanks) solver_cta(A, smem);
-    else solve_evaluator(A, smem, bid / kFactorRanks, bid % kFactorRanks);
+    solve_evaluator(A, smem, blockIdx.x / kFactorRanks, blockIdx.x % kFactorRanks);
+}
+__global__ void __launch_bounds__(kCtlThreads, 1) solve_ctl_kernel(const __grid_constant__ SolveArgs A) {
+    extern __shared__ __align__(16) double smem[];
+    solver_cta(A, smem);
 }
 
 __global__ void fp64_peak_kernel(double *out, int iters) {
@@ -1025,6 +1087,8 @@ struct FactorRuntime {
     unsigned long long *h_ssignal = nullptr;
     unsigned long long solve_id = 0;
     size_t solve_smem_max = 0;
+    cudaStream_t solve_stream = nullptr;
+    cudaEvent_t solve_go = nullptr, solve_done = nullptr;
     // diagnostics (FFLINS_RES_TIMELINE=1): where a resident evaluation's round trip goes
     bool timeline = false;
     long long *h_timeline = nullptr;
@@ -1063,9 +1127,13 @@ FactorRuntime *factor_runtime_create(int device) {
              cudaMemset(rt->d_spart, 0, sizeof(Unit) * kMaxPairs * kFactorRanks * kRedUnits) == cudaSuccess &&
              cudaMemset(rt->d_sinbox, 0, sizeof(Unit) * kMaxPairs * kRedUnits) == cudaSuccess;
         cudaFuncAttributes fa{};
-        if (ok && cudaFuncGetAttributes(&fa, solve_kernel) == cudaSuccess) {
+        ok = ok && cudaStreamCreateWithFlags(&rt->solve_stream, cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&rt->solve_go, cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&rt->solve_done, cudaEventDisableTiming) == cudaSuccess &&
+             cudaFuncSetAttribute(solve_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kFactorSmem) == cudaSuccess;
+        if (ok && cudaFuncGetAttributes(&fa, solve_ctl_kernel) == cudaSuccess) {
             rt->solve_smem_max = kSolveSmemMax - fa.sharedSizeBytes;
-            if (cudaFuncSetAttribute(solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) rt->solve_smem_max) != cudaSuccess) {
+            if (cudaFuncSetAttribute(solve_ctl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) rt->solve_smem_max) != cudaSuccess) {
                 cudaGetLastError();
                 rt->solve_smem_max = 48 * 1024;   // the default limit: small windows only
             }
@@ -1442,6 +1510,9 @@ void factor_runtime_destroy(FactorRuntime *rt) {
     if (rt->h_res) cudaFreeHost(rt->h_res);
     if (rt->h_exit) cudaFreeHost(rt->h_exit);
     if (rt->h_red) cudaFreeHost(rt->h_red);
+    if (rt->solve_stream) cudaStreamDestroy(rt->solve_stream);
+    if (rt->solve_go) cudaEventDestroy(rt->solve_go);
+    if (rt->solve_done) cudaEventDestroy(rt->solve_done);
     if (rt->h_prior) cudaFreeHost(rt->h_prior);
     if (rt->h_sout) cudaFreeHost(rt->h_sout);
     cudaFree(rt->d_sbcast);
@@ -1477,7 +1548,7 @@ int launch_window_solve(FactorRuntime *rt, cudaStream_t s, const FactorParams &p
     const int n = p.n_pairs;
     if (n <= 0 || n > kMaxPairs || p.q <= 0) return -(int) cudaErrorInvalidValue;
     const int D = solve_dim(n), NX = solve_nx(n);
-    const size_t smem = std::max(kFactorSmem, solve_smem_doubles(n) * sizeof(double));
+    const size_t smem = solve_smem_doubles(n) * sizeof(double);
     if (smem > rt->solve_smem_max) return -(int) cudaErrorInvalidValue;
     FactorSetup su;
     fill_setup(p, points, stride4, su);
@@ -1509,15 +1580,22 @@ int launch_window_solve(FactorRuntime *rt, cudaStream_t s, const FactorParams &p
     A.hard_ns  = 200000000ull;
     A.n        = n;
     A.q        = p.q;
-    solve_kernel<<<n * kFactorRanks + 1, kFactorBlock, smem, s>>>(A);
+    // evaluators on the compute stream (behind the association), the solver on its own stream behind the same point; the
+    // compute stream continues when the solver has finished (its farewell broadcast ends the evaluators)
+    if ((e = cudaEventRecord(rt->solve_go, s)) != cudaSuccess || (e = cudaStreamWaitEvent(rt->solve_stream, rt->solve_go, 0)) != cudaSuccess)
+        return -(int) e;
+    solve_eval_kernel<<<n * kFactorRanks, kFactorBlock, kFactorSmem, s>>>(A);
+    solve_ctl_kernel<<<1, kCtlThreads, smem, rt->solve_stream>>>(A);
     e = cudaGetLastError();
     if (e != cudaSuccess) return -(int) e;
-    if (launches) (*launches)++;
+    if ((e = cudaEventRecord(rt->solve_done, rt->solve_stream)) != cudaSuccess || (e = cudaStreamWaitEvent(s, rt->solve_done, 0)) != cudaSuccess)
+        return -(int) e;
+    if (launches) (*launches) += 2;
     // the result block is written straight into pinned memory with the flag released behind it: poll, do not synchronise
     unsigned spins = 0;
     while (__atomic_load_n(rt->h_ssignal, __ATOMIC_ACQUIRE) != A.seq) {
         if ((++spins & 0xfffu) == 0) {
-            e = cudaStreamQuery(s);
+            e = cudaStreamQuery(rt->solve_stream);
             if (e == cudaSuccess) break;
             if (e != cudaErrorNotReady) return -(int) e;
         }
@@ -1544,6 +1622,8 @@ int launch_window_solve(FactorRuntime *rt, cudaStream_t s, const FactorParams &p
             rep->n_res[i]      = (int) (o[32 + i] + 0.5);
         }
     }
+    if (rep)
+        for (int i = 0; i < 8; i++) rep->phase_cycles[i] = o[48 + kSolveMaxX + i];
     if (x_out)
         for (int i = 0; i < NX; i++) x_out[i] = o[48 + i];
     return 0;

@@ -311,6 +311,9 @@ struct SolveReport {
     double cost_initial[2], cost_final[2];
     int steps;                   // broadcasts of the solver CTA (evaluations + chi2 + retire)
     int n_outliers[kMaxRefs], n_res[kMaxRefs];
+    // diagnostics: SM cycles of the solver CTA per phase, summed over the solve: 0 waiting for the evaluators (broadcast ->
+    // all sums gathered), 1 assembly, 2 damped copy, 3 elimination + back substitution, 4 model decrease, 5 Plus
+    double phase_cycles[8];
 };
 // State layout x: n reference poses, the current pose, the extrinsic (7 doubles each: t, q = x y z w), td; the prior
 // (host pointers, H0 == nullptr: none) is 0.5 d^T H0 d - b0^T d + c0 over the tangent [6 n | 6 | 6 | 1], d = x (-) x0.

@@ -29,6 +29,15 @@ __host__ __device__ inline int solve_dim(int n) { return 6 * n + 13; }
 __host__ __device__ inline int solve_nx(int n) { return 7 * n + 15; }
 __host__ __device__ inline int solve_ld(int D) { return D | 1; }          // odd: column walks touch distinct banks
 
+// read-only global data (the prior): the non-coherent path tells the compiler that the shared-memory stores around it do not alias
+__host__ __device__ inline double solve_ldg(const double *p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+
 struct SolvePrior {              // 0.5 d^T H0 d - b0^T d + c0 with d = x (-) x0; H0 == nullptr: none
     const double *H0, *b0, *x0;
     double c0;
@@ -41,6 +50,8 @@ struct SolveWork {
     double *dx, *rhs, *dinv, *delta;
     double *x, *xc;              // state | candidate
     unsigned char *fixed;        // D
+    unsigned char *free_idx;     // the Df free entries of the tangent vector, ascending (constant blocks never enter the factorisation)
+    int Df;
     const unsigned short *tri;   // (r << 8 | c), r >= c, row by row: the first m (m + 1) / 2 entries cover an m x m triangle
 };
 
@@ -50,6 +61,36 @@ struct ParSerial {
     __host__ __device__ void sync() const {}
     __host__ __device__ double sum(double v) const { return v; }
     __host__ __device__ double max(double v) const { return v; }
+    __host__ __device__ int lanes() const { return 1; }       // threads of a warp
+    __host__ __device__ void syncwarp() const {}
+    __host__ __device__ int warp() const { return 0; }
+    __host__ __device__ int nwarps() const { return 1; }
+    __host__ __device__ int lane() const { return 0; }
+    __host__ __device__ double warp_sum(double v) const { return v; }   // over the lanes of the caller's warp, in every lane
+    __host__ __device__ void stamp(int) const {}                        // diagnostics: end of phase k (see SolveReport::phase_cycles)
+    // U x = D^-1 y for the unit-diagonal upper factor left by solve_spd (rows of A above the diagonal, dinv): x_k =
+    // y_k dinv_k, then y_r -= A[r][k] x_k for r < k, k = D-1 .. 0. Called by every thread; ends with a barrier.
+    __host__ __device__ void backsub(int D, int ld, const double *A, const double *dinv, double *rhs, double *x_out) const {
+        for (int k = D - 1; k >= 0; k--) {
+            const double xk = rhs[k] * dinv[k];
+            x_out[k]        = xk;
+            for (int r = 0; r < k; r++) rhs[r] -= A[r * ld + k] * xk;
+        }
+    }
+};
+
+// (row, col) of a flat index that advances by a fixed stride, without a division per element
+struct RowCol {
+    int i, j, di, dj, D;
+    __host__ __device__ RowCol(int start, int stride, int D_) : i(start / D_), j(start % D_), di(stride / D_), dj(stride % D_), D(D_) {}
+    __host__ __device__ void next() {
+        i += di;
+        j += dj;
+        if (j >= D) {
+            j -= D;
+            i++;
+        }
+    }
 };
 
 // Rotation::rotvec2quaternion (rotation.cc:61-65)
@@ -99,6 +140,14 @@ __host__ __device__ inline void solve_fill_fixed(int tid, int nthr, int n, unsig
     }
 }
 
+// one thread, after solve_fill_fixed
+__host__ __device__ inline int solve_fill_free(int D, const unsigned char *fixed, unsigned char *free_idx) {
+    int nf = 0;
+    for (int i = 0; i < D; i++)
+        if (!fixed[i]) free_idx[nf++] = (unsigned char) i;
+    return nf;
+}
+
 // The normal equations at x: prior + the pairs' reduced 19 x 19 blocks (red: n x kRedStride, the layout of kRedSize),
 // in the order host.cc's linearize adds them (prior first, then the pairs in window order). Returns the cost.
 #pragma nv_exec_check_disable
@@ -114,20 +163,21 @@ __host__ __device__ double solve_assemble(const Par &par, const SolveWork &W, co
         }
     }
     par.sync();
-    for (int e = tid; e < D * D; e += nt) {
-        const int i = e / D, j = e - i * D;
-        H[i * ld + j] = prior ? P.H0[e] : 0.0;
+    {
+        RowCol rc(tid, nt, D);
+        for (int e = tid; e < D * D; e += nt, rc.next()) H[rc.i * ld + rc.j] = prior ? solve_ldg(P.H0 + e) : 0.0;
     }
     double cpart = 0.0;
-    for (int i = tid; i < D; i += nt) {
+    for (int i = par.warp(); i < D; i += par.nwarps()) {   // one warp per row of H0, the lanes across it
         double gi = 0.0;
         if (prior) {
             double s = 0.0;
-            for (int j = 0; j < D; j++) s += P.H0[j * D + i] * W.delta[j];   // H0 is symmetric: walk the column, coalesced
-            gi = P.b0[i] - s;
+            for (int j = par.lane(); j < D; j += par.lanes()) s += solve_ldg(P.H0 + i * D + j) * W.delta[j];
+            gi = P.b0[i] - par.warp_sum(s);
             cpart -= 0.5 * W.delta[i] * (P.b0[i] + gi);                      // 0.5 d^T H0 d - b0^T d
         }
-        g[i] = gi;
+        if (par.lane() == 0) g[i] = gi;
+        else cpart = 0.0;
     }
     par.sync();
     double cost = (prior ? P.c0 : 0.0) + par.sum(cpart);
@@ -148,12 +198,17 @@ __host__ __device__ double solve_assemble(const Par &par, const SolveWork &W, co
 }
 
 // A x = rhs for a symmetric positive definite A (upper triangle used, overwritten): right-looking elimination
-// A = L D L^T with the right-hand side carried along, then back substitution. One barrier per column: the pivot row
+// A = L D L^T with the right-hand side carried along, then back substitution (Par::backsub: D dependent steps; on the
+// device one warp with the right-hand side in registers and a shuffle per step). One barrier per column: the pivot row
 // is final when its step starts and is not written during it. Returns false when a pivot is not positive.
+// Measured on B200 (tools/solve_bench.py, D = 73, 512 threads): ~1,000 cycles per column, i.e. the dependent chain
+// barrier -> pivot -> division -> one or two passes of the update; three attempts to shorten it lost (next pivot and its
+// reciprocal carried in registers so that the division overlaps the update: +17 %; four entries per thread and pass with
+// the operands fetched first: +27 %; single-precision reciprocal + two Newton steps instead of the division: +7 %).
 #pragma nv_exec_check_disable
 template <class Par>
-__host__ __device__ bool solve_spd(const Par &par, const SolveWork &W, double *A, double *rhs, double *x_out) {
-    const int D = W.D, ld = W.ld, tid = par.tid(), nt = par.nthr();
+__host__ __device__ bool solve_spd(const Par &par, const SolveWork &W, int D, double *A, double *rhs, double *x_out) {
+    const int ld = W.ld, tid = par.tid(), nt = par.nthr();
     for (int k = 0; k < D; k++) {
         const double pivot = A[k * ld + k];
         if (!(pivot > 0.0) || !(pivot < DBL_MAX)) return false;   // the same value in every thread
@@ -173,12 +228,8 @@ __host__ __device__ bool solve_spd(const Par &par, const SolveWork &W, double *A
         }
         par.sync();
     }
-    for (int k = D - 1; k >= 0; k--) {
-        const double xk = rhs[k] * W.dinv[k];
-        if (tid == 0) x_out[k] = xk;
-        for (int r = tid; r < k; r += nt) rhs[r] -= A[r * ld + k] * xk;
-        par.sync();
-    }
+    par.stamp(6);
+    par.backsub(D, ld, A, W.dinv, rhs, x_out);
     return true;
 }
 
@@ -208,30 +259,42 @@ __host__ __device__ SolveStage solve_lm(const Par &par, SolveWork &W, const Solv
             if (!W.fixed[i]) gm = fmax(gm, fabs(W.g[i]));
         gm = par.max(gm);
         if (gm < O.gradient_tolerance) break;
-        // constant columns carry no information: pin them; damping diag(H) / radius on the others
-        for (int e = tid; e < D * D; e += nt) {
-            const int j = e / D, i = e - j * D;
-            double v    = W.H[j * ld + i];
-            if (W.fixed[i] || W.fixed[j]) v = i == j ? 1.0 : 0.0;
-            else if (i == j) v += fmin(fmax(v, 1e-6), 1e32) / radius;
-            W.A[j * ld + i] = v;
+        // the free rows and columns, compacted (constant blocks carry no information); damping diag(H) / radius
+        const int Df = W.Df;
+        {
+            RowCol rc(tid, nt, Df > 0 ? Df : 1);
+            for (int e = tid; e < Df * Df; e += nt, rc.next()) {
+                const int i = W.free_idx[rc.i], j = W.free_idx[rc.j];
+                double v    = W.H[i * ld + j];
+                if (i == j) v += fmin(fmax(v, 1e-6), 1e32) / radius;
+                W.A[rc.i * ld + rc.j] = v;
+            }
         }
-        for (int i = tid; i < D; i += nt) W.rhs[i] = W.fixed[i] ? 0.0 : W.g[i];
+        for (int a = tid; a < Df; a += nt) W.rhs[a] = W.g[W.free_idx[a]];
+        for (int i = tid; i < D; i += nt) W.dx[i] = 0.0;
         par.sync();
-        const bool ok = solve_spd(par, W, W.A, W.rhs, W.dx);
+        par.stamp(2);
+        const bool ok = solve_spd(par, W, Df, W.A, W.rhs, W.delta);
+        if (ok)
+            for (int a = tid; a < Df; a += nt) W.dx[W.free_idx[a]] = W.delta[a];
         par.sync();
+        par.stamp(3);
         double mpart = 0.0, dpart = 0.0;
         if (ok) {
-            for (int i = tid; i < D; i += nt) {
+            for (int i = par.warp(); i < D; i += par.nwarps()) {   // one warp per row of H
                 if (W.fixed[i]) continue;
                 double hd = 0.0;
-                for (int j = 0; j < D; j++)
-                    if (!W.fixed[j]) hd += W.H[j * ld + i] * W.dx[j];
-                mpart += W.dx[i] * (W.g[i] - 0.5 * hd);   // model decrease dx^T (b - 0.5 H dx)
-                dpart += W.dx[i] * W.dx[i];
+                for (int j = par.lane(); j < D; j += par.lanes())
+                    if (!W.fixed[j]) hd += W.H[i * ld + j] * W.dx[j];
+                hd = par.warp_sum(hd);
+                if (par.lane() == 0) {
+                    mpart += W.dx[i] * (W.g[i] - 0.5 * hd);   // model decrease dx^T (b - 0.5 H dx)
+                    dpart += W.dx[i] * W.dx[i];
+                }
             }
         }
         const double model = par.sum(mpart), dn = par.sum(dpart);
+        par.stamp(4);
         if (!ok || !(model > 0.0)) {
             radius /= decrease;
             decrease *= 2.0;
@@ -249,6 +312,7 @@ __host__ __device__ SolveStage solve_lm(const Par &par, SolveWork &W, const Solv
             }
         }
         par.sync();
+        par.stamp(5);
         const double cost_n = eval(W.xc, W.A, W.gn);
         S.evaluations++;
         if (eval.failed()) {

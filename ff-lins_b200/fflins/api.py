@@ -67,7 +67,7 @@ class SolvePrior(C.Structure):
 class SolveReport(C.Structure):
     _fields_ = [("status", C.c_int32), ("iterations", C.c_int32 * 2), ("successful", C.c_int32 * 2),
                 ("evaluations", C.c_int32 * 2), ("cost_initial", C.c_double * 2), ("cost_final", C.c_double * 2),
-                ("n_outliers", C.c_int32 * 16), ("n_res", C.c_int32 * 16)]
+                ("n_outliers", C.c_int32 * 16), ("n_res", C.c_int32 * 16), ("phase_cycles", C.c_double * 8)]
 
 
 class FrameInfo(C.Structure):

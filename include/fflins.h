@@ -268,6 +268,9 @@ typedef struct fflins_solve_report {
     int32_t iterations[2], successful[2], evaluations[2];
     double  cost_initial[2], cost_final[2];
     int32_t n_outliers[16], n_res[16];
+    double  phase_cycles[8];       /* diagnostics: SM cycles of the solver CTA summed over the solve: 0 waiting for the
+                                    * evaluations, 1 assembly, 2 damped copy, 3 factorisation + substitution, 4 model
+                                    * decrease, 5 Plus */
 } fflins_solve_report;
 /* pose_refs [7 n], pose_cur, ext, td: in = initial state, out = solution. prior and report may be NULL. */
 int fflins_window_solve(fflins_ctx *ctx, int32_t n_pairs, const uint64_t *ref_ids, double *pose_refs, double pose_cur[7],

@@ -120,11 +120,12 @@ int solve_host_run(int n, int q, const float *points, const int8_t *type, uint8_
     const int D = solve_dim(n), ld = solve_ld(D), NX = solve_nx(n);
     std::vector<double> H((size_t) D * ld), A((size_t) D * ld), g(ld), gn(ld), dx(ld), rhs(ld), dinv(ld), delta(ld), xs(x, x + NX), xc(NX);
     std::vector<unsigned short> tri((size_t) (D - 1) * D / 2 + 1);
-    std::vector<unsigned char> fixed(D);
+    std::vector<unsigned char> fixed(D), free_idx(D);
     solve_fill_tri(0, 1, D, tri.data());
     solve_fill_fixed(0, 1, n, O.flags, O.fixed_refs, fixed.data());
+    const int Df = solve_fill_free(D, fixed.data(), free_idx.data());
     SolveWork W{n, D, ld, H.data(), A.data(), g.data(), gn.data(), dx.data(), rhs.data(), dinv.data(), delta.data(), xs.data(), xc.data(),
-                fixed.data(), tri.data()};
+                fixed.data(), free_idx.data(), Df, tri.data()};
     HostEval eval{P, &W, SolvePrior{H0, b0, x0, c0}, std::vector<double>((size_t) n * kRedStride)};
     SolveStage st[2];
     st[0] = solve_lm(ParSerial{}, W, O, O.max_iters[0], eval);
@@ -154,7 +155,7 @@ int solve_host_spd(int n, const double *A_in, const double *b, double *x) {
     SolveWork W{};
     W.n = n; W.D = D; W.ld = ld; W.dinv = dinv.data(); W.tri = tri.data();
     rhs.resize(ld);
-    return solve_spd(ParSerial{}, W, A.data(), rhs.data(), x) ? 0 : 1;
+    return solve_spd(ParSerial{}, W, D, A.data(), rhs.data(), x) ? 0 : 1;
 }
 
 } // extern "C"

@@ -9,6 +9,7 @@
 //   per keyframe   fflins_keyframe_merge (out = NULL) -> fflins_frame_release x (K - 1) -> fflins_keyframe_add ->
 //                  fflins_frame_set_motion -> fflins_associate -> n0 x fflins_window_eval -> fflins_window_chi2 ->
 //                  n1 x fflins_window_eval -> fflins_reproject_window -> fflins_keyframe_remove_oldest (window full)
+//   drv_set_solve(1): the n0 + chi2 + n1 sequence is ONE fflins_window_solve (the Levenberg-Marquardt loop on the device)
 #include "../include/fflins.h"
 
 #include <chrono>
@@ -55,6 +56,10 @@ typedef struct drv_session {
     int last_pairs;                        // pairs of the last window evaluation (the oldest keyframe may have left since)
     std::vector<double> H, b, cost;
     int32_t n_res[16];
+    int use_solve;                         // 1: the keyframe's solve runs on the device (fflins_window_solve)
+    double prior_w[4];                     // weights of the diagonal prior: pose t, pose theta, td, (spare)
+    std::vector<double> H0, b0, x0;
+    fflins_solve_report report;
     char err[256];
 } drv_session;
 
@@ -79,7 +84,21 @@ drv_session *drv_create(fflins_ctx *ctx, const fflins_pose *pose_bl, const doubl
     s->b.resize(19 * 16);
     s->cost.resize(2 * 16);
     s->err[0] = 0;
+    s->use_solve = 0;
+    s->prior_w[0] = 1.0 / (0.05 * 0.05);
+    s->prior_w[1] = 1.0 / (0.01 * 0.01);
+    s->prior_w[2] = 1.0 / (1e-3 * 1e-3);
+    s->prior_w[3] = 0;
+    std::memset(&s->report, 0, sizeof(s->report));
     return s;
+}
+void drv_set_solve(drv_session *s, int on) { s->use_solve = on; }
+int drv_last_solve(const drv_session *s, int32_t *iters2, int32_t *evals2) {
+    iters2[0] = s->report.iterations[0];
+    iters2[1] = s->report.iterations[1];
+    evals2[0] = s->report.evaluations[0];
+    evals2[1] = s->report.evaluations[1];
+    return s->report.status;
 }
 void drv_destroy(drv_session *s) { delete s; }
 const char *drv_error(const drv_session *s) { return s->err; }
@@ -148,11 +167,43 @@ static int keyframe_work(drv_session *s, uint64_t fid, const drv_frame &fr) {
         double pose_refs[7 * 16];
         const double *pose_cur;
         const int n = window_args(s, ids, pose_refs, &pose_cur);
-        for (int it = 0; it < s->n0; it++)
-            DRV_CK(fflins_window_eval(s->ctx, n, ids, pose_refs, pose_cur, s->ext7, fr.td, s->flags, s->H.data(), s->b.data(), s->cost.data(), s->n_res));
-        DRV_CK(fflins_window_chi2(s->ctx, n, ids, pose_refs, pose_cur, s->ext7, fr.td, s->chi2_threshold, s->chi2_outliers));
-        for (int it = 0; it < s->n1; it++)
-            DRV_CK(fflins_window_eval(s->ctx, n, ids, pose_refs, pose_cur, s->ext7, fr.td, s->flags, s->H.data(), s->b.data(), s->cost.data(), s->n_res));
+        if (s->use_solve) {
+            // the same schedule as ONE call: n0 LM iterations, the chi2 cull, n1 LM iterations on the device, every pose of
+            // the window, the extrinsic and td free, tied to where they start by a diagonal prior (what the inertial
+            // factors and the marginalization prior do in the full problem). Tolerances off: the iteration limits are
+            // the work, as in the round-trip sequence below. The solution is dropped (the sequence replays the same poses).
+            const int D = 6 * n + 13, NX = 7 * n + 15;
+            s->H0.assign((size_t) D * D, 0.0);
+            s->b0.assign(D, 0.0);
+            s->x0.resize(NX);
+            for (int i = 0; i < D; i++) s->H0[(size_t) i * D + i] = i == D - 1 ? s->prior_w[2] : ((i % 6) < 3 ? s->prior_w[0] : s->prior_w[1]);
+            double refs[7 * 16], cur7[7], ext7[7], td = fr.td;
+            std::memcpy(refs, pose_refs, sizeof(double) * 7 * n);
+            std::memcpy(cur7, pose_cur, sizeof(cur7));
+            std::memcpy(ext7, s->ext7, sizeof(ext7));
+            std::memcpy(s->x0.data(), refs, sizeof(double) * 7 * n);
+            std::memcpy(s->x0.data() + 7 * n, cur7, sizeof(cur7));
+            std::memcpy(s->x0.data() + 7 * n + 7, ext7, sizeof(ext7));
+            s->x0[7 * n + 14] = td;
+            fflins_solve_options opt;
+            fflins_solve_options_default(&opt);
+            opt.max_iterations[0]   = s->n0;
+            opt.max_iterations[1]   = s->n1;
+            opt.chi2_threshold      = s->chi2_threshold;
+            opt.function_tolerance  = 0;
+            opt.gradient_tolerance  = 0;
+            opt.parameter_tolerance = 0;
+            opt.flags               = s->flags;
+            fflins_solve_prior prior{s->H0.data(), s->b0.data(), s->x0.data(), 0.0};
+            DRV_CK(fflins_window_solve(s->ctx, n, ids, refs, cur7, ext7, &td, &opt, &prior, &s->report));
+            for (int i = 0; i < n; i++) s->n_res[i] = s->report.n_res[i];
+        } else {
+            for (int it = 0; it < s->n0; it++)
+                DRV_CK(fflins_window_eval(s->ctx, n, ids, pose_refs, pose_cur, s->ext7, fr.td, s->flags, s->H.data(), s->b.data(), s->cost.data(), s->n_res));
+            DRV_CK(fflins_window_chi2(s->ctx, n, ids, pose_refs, pose_cur, s->ext7, fr.td, s->chi2_threshold, s->chi2_outliers));
+            for (int it = 0; it < s->n1; it++)
+                DRV_CK(fflins_window_eval(s->ctx, n, ids, pose_refs, pose_cur, s->ext7, fr.td, s->flags, s->H.data(), s->b.data(), s->cost.data(), s->n_res));
+        }
         s->last_td = fr.td;
         s->last_pairs = n;
         // updateParametersFromOptimizer: re-project every keyframe of the window (optimizer.cc:203-218)
