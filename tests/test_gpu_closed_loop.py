@@ -3,7 +3,9 @@ must differ by less than 1 mm ATE"), in the reduced form the scope allows withou
 (SURVEY.md §8f row 1): every new keyframe's pose is solved by the same dense LM (fflins.window_solver)
 against the window of older keyframes; the loop is closed (solved pose -> setPose + re-projection ->
 next association). The loop runs twice on the same raw frames: once with every LiDAR operation on the
-GPU through the C-ABI, once with the CPU oracle. ATE = RMS position difference over the keyframes."""
+GPU through the C-ABI, once with the CPU oracle. ATE = RMS position difference over the keyframes.
+A third run replaces the host LM by fflins_window_solve (the whole 5 + chi2 + 10 schedule on the device, one
+launch per keyframe) on a full window of 10 references."""
 import numpy as np
 import pytest
 
@@ -19,7 +21,7 @@ def _init_guess(seq, stamp, k):
     return seq.imu_pose7(stamp, rng, 0.02, 0.003)     # 2 cm, ~0.17 deg off the INS pose
 
 
-def run_gpu(seq, frames):
+def run_gpu(seq, frames, K=K, WINDOW=WINDOW, device_solve=False):
     from fflins import api
     from fflins.window_solver import WindowSolver, lidar_pose
     c = api.Context(api.default_config(point_filter_num=seq.filter_num, window_size=WINDOW))
@@ -51,7 +53,13 @@ def run_gpu(seq, frames):
 
             def cull(pose, e, td):
                 return c.window_chi2(refs, pose_refs, pose, e, td)
-            sol = WindowSolver(evaluate, cull).solve(_init_guess(seq, fr["stamp"], len(traj)), ext, fr["td"])
+            if device_solve:
+                opt = c.solve_options(flags=flags, function_tolerance=1e-14, parameter_tolerance=1e-14)
+                _, pc, _, _, rep = c.window_solve(refs, pose_refs, _init_guess(seq, fr["stamp"], len(traj)), ext, fr["td"], options=opt)
+                assert rep.status == 0 and rep.successful[0] >= 1
+                sol = dict(pose=pc, outliers=int(sum(rep.n_outliers[:len(refs)])))
+            else:
+                sol = WindowSolver(evaluate, cull).solve(_init_guess(seq, fr["stamp"], len(traj)), ext, fr["td"])
             poses7[i] = sol["pose"]
             stats.append((int(sum(st.num_features[:st.n_refs])), sol["outliers"]))
         R, t = lidar_pose(poses7[i], ext)
@@ -63,7 +71,7 @@ def run_gpu(seq, frames):
     return np.array(traj), stats
 
 
-def run_cpu(seq, frames, O):
+def run_cpu(seq, frames, O, K=K, WINDOW=WINDOW):
     from fflins.window_solver import WindowSolver, lidar_pose
     ext = seq.ext7()
     nonkeys, keys, traj, stats = [], [], [], []
@@ -140,3 +148,23 @@ def test_closed_loop_ate_below_1mm(oracle):
     assert ate < 1e-3, "trajectory must agree within 1 mm"
     assert err_truth < 0.05, "the solve must pull the 2 cm initial error down to the noise level"
     assert all(s[0] > 200 for s in g_stats)
+
+
+def test_closed_loop_with_the_device_solve_window10(oracle):
+    """The same loop with each keyframe's solve as ONE fflins_window_solve call, on a full window of 10 references
+    (13 keyframes of 3 frames), against the CPU-oracle loop with the host LM: two different LM controls (Ceres-style
+    trust region on the device, plain lambda damping in window_solver.py) must land on the same optimum."""
+    from fflins import synth
+    seq = synth.Sequence("robot")
+    k, window, n_frames = 3, 10, 39
+    frames = [seq.frame(i) for i in range(n_frames)]
+    g_traj, g_stats = run_gpu(seq, frames, K=k, WINDOW=window, device_solve=True)
+    c_traj, c_stats = run_cpu(seq, frames, oracle, K=k, WINDOW=window)
+    assert g_traj.shape == c_traj.shape == (n_frames // k, 3)
+    ate = float(np.sqrt(np.mean(np.sum((g_traj - c_traj) ** 2, axis=1))))
+    truth = np.stack([seq.imu_pose7(frames[i]["stamp"])[:3] for i in range(k - 1, n_frames, k)])
+    err_truth = float(np.sqrt(np.mean(np.sum((g_traj - truth) ** 2, axis=1))))
+    print(f"closed loop, device solve, window 10: ATE(device-solved GPU loop vs host-LM CPU oracle loop) = {ate * 1e3:.6f} mm over "
+          f"{len(g_traj)} keyframes; RMS vs ground truth = {err_truth * 1e3:.2f} mm; features/outliers GPU {g_stats[-3:]} CPU {c_stats[-3:]}")
+    assert ate < 1e-3, "trajectory must agree within 1 mm"
+    assert err_truth < 0.05
