@@ -191,23 +191,6 @@ def test_window10_resident_retires_and_restarts(window10):
     assert s1["resident_evals"] >= s0["resident_evals"] + 50
 
 
-def test_window10_remove_newest(window10, oracle):
-    """removeNewestLidarFrame (lidar_map.cc:175-188): the newest keyframe leaves the window, the previous one becomes
-    the current frame of the next association."""
-    from fflins import api
-    c, seq, keys = window10
-    ids = c.keyframe_ids()
-    assert ids == [k["id"] for k in keys]
-    rid = c.keyframe_remove_newest()
-    assert rid == keys[-1]["id"] and c.keyframe_ids() == ids[:-1]
-    with pytest.raises(api.FflinsError):
-        c.frame_info(rid)
-    st, planes = _check_association(c, oracle, keys[:-1])
-    assert st.n_refs == 9 and planes > 500
-    total, _ = _check_factors(c, oracle, seq, keys[:-1], 1, 81)
-    assert total > 500
-
-
 # ------------------------------------------------------------------------------------------------ 14 refs
 def test_window15_all_pairs(window15, oracle):
     c, seq, keys = window15
@@ -527,3 +510,21 @@ def test_window_solve_is_deterministic_and_coexists_with_the_resident_kernel(win
     xc, rc = _device_solve(c, refs, n, x, 1, prior, function_tolerance=0.0, gradient_tolerance=0.0, parameter_tolerance=0.0)
     _clear_outliers(c, refs)
     assert rc.iterations[0] == 5 and rc.iterations[1] == 10 and rc.evaluations[0] + rc.evaluations[1] <= 17
+
+
+# ---- mutates the shared window10 fixture: keep it the LAST test of this file that uses it --------------------------------
+def test_window10_remove_newest(window10, oracle):
+    """removeNewestLidarFrame (lidar_map.cc:175-188): the newest keyframe leaves the window, the previous one becomes
+    the current frame of the next association."""
+    from fflins import api
+    c, seq, keys = window10
+    ids = c.keyframe_ids()
+    assert ids == [k["id"] for k in keys]
+    rid = c.keyframe_remove_newest()
+    assert rid == keys[-1]["id"] and c.keyframe_ids() == ids[:-1]
+    with pytest.raises(api.FflinsError):
+        c.frame_info(rid)
+    st, planes = _check_association(c, oracle, keys[:-1])
+    assert st.n_refs == 9 and planes > 500
+    total, _ = _check_factors(c, oracle, seq, keys[:-1], 1, 81)
+    assert total > 500
