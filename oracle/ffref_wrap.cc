@@ -1,0 +1,167 @@
+/* C wrapper around the REFERENCE's own hot-path sources, compiled where they lie under /root/reference by
+ * oracle/Makefile `ffref` into oracle/_ref/libff_ref.so: factors/lidar_factor.cc (LidarFactor::Evaluate),
+ * common/misc.cc (getInsWindowIndex, getPoseFromInsWindow, statePoseInterpolation, stateToPoseWithExtrinsic,
+ * insMechanization), common/rotation.cc and lidar/pointcloud.cc (relativeProjection, pointProjection,
+ * pointCloudProjection, planeEstimation). Eigen / PCL / Ceres / TBB / glog are not installed here: the sources are
+ * compiled against the stand-in headers of oracle/refshim/ (see mini_eigen.h for what that does and does not pin).
+ * The only logic restated in this file is the per-point loop of LidarMap::lidarFrameProcessing (lidar_map.cc:222-243),
+ * whose translation unit needs the whole map / kd-tree / VoxelGrid stack. Argument layouts are those of oracle.h so
+ * that tests can call both sides with the same arrays. Test infrastructure only. */
+#include "common/misc.h"
+#include "common/rotation.h"
+#include "factors/lidar_factor.h"
+#include "lidar/pointcloud.h"
+
+#include <cstring>
+
+namespace {
+typedef std::deque<std::pair<IMU, IntegrationState>> InsWindow;
+
+InsWindow make_window(const double *ins_t, const double *ins_p, const double *ins_q, int w) {
+    InsWindow win;
+    for (int k = 0; k < w; k++) {
+        IMU imu;
+        imu.time = ins_t[k];
+        imu.dt   = 0;
+        IntegrationState st;
+        st.time = ins_t[k];
+        st.p    = Vector3d(ins_p[3 * k], ins_p[3 * k + 1], ins_p[3 * k + 2]);
+        st.q    = Quaterniond(ins_q[4 * k + 3], ins_q[4 * k], ins_q[4 * k + 1], ins_q[4 * k + 2]); /* arrays are xyzw */
+        win.emplace_back(imu, st);
+    }
+    return win;
+}
+Pose make_pose(const double *R, const double *t) {
+    Pose p;
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) p.R(r, c) = R[3 * r + c];
+    p.t = Vector3d(t[0], t[1], t[2]);
+    return p;
+}
+void store_pose(const Pose &p, double *R, double *t) {
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) R[3 * r + c] = p.R(r, c);
+    for (int i = 0; i < 3; i++) t[i] = p.t[i];
+}
+PointType make_point(const float *xyzi) {
+    PointType p;
+    p.x = xyzi[0], p.y = xyzi[1], p.z = xyzi[2], p.intensity = xyzi[3];
+    return p;
+}
+} // namespace
+
+extern "C" {
+
+int ffref_ins_window_index(const double *ins_t, int w, double time) {
+    static const double zero3[3] = {0, 0, 0}, q[4] = {0, 0, 0, 1};
+    InsWindow win;
+    for (int k = 0; k < w; k++) {
+        InsWindow one = make_window(ins_t + k, zero3, q, 1);
+        win.push_back(one.front());
+    }
+    return (int) MISC::getInsWindowIndex(win, time);
+}
+
+int ffref_pose_from_ins_window(const double *ins_t, const double *ins_p, const double *ins_q, int w, const double *R_bl,
+                               const double *t_bl, double time, double *R, double *t) {
+    InsWindow win = make_window(ins_t, ins_p, ins_q, w);
+    Pose pose;
+    bool ok = MISC::getPoseFromInsWindow(win, make_pose(R_bl, t_bl), time, pose);
+    store_pose(pose, R, t);
+    return ok ? 1 : 0;
+}
+
+void ffref_state_to_pose(const double *p, const double *q, const double *R_bl, const double *t_bl, double *R, double *t) {
+    IntegrationState st;
+    st.p = Vector3d(p[0], p[1], p[2]);
+    st.q = Quaterniond(q[3], q[0], q[1], q[2]);
+    store_pose(MISC::stateToPoseWithExtrinsic(st, make_pose(R_bl, t_bl)), R, t);
+}
+
+/* the per-point loop of LidarMap::lidarFrameProcessing (lidar_map.cc:222-243) over the reference's own
+ * MISC::getPoseFromInsWindow and PointCloudCommon::relativeProjection; returns the number of fallbacks */
+int ffref_undistort(const float *xyzi, const double *time, int n, const double *ins_t, const double *ins_p,
+                    const double *ins_q, int w, const double *R_bl, const double *t_bl, double stamp, double td,
+                    float *out_xyzi, double *pose_R, double *pose_t) {
+    InsWindow win = make_window(ins_t, ins_p, ins_q, w);
+    Pose pose_b_l = make_pose(R_bl, t_bl), lidar_pose;
+    MISC::getPoseFromInsWindow(win, pose_b_l, stamp, lidar_pose);
+    store_pose(lidar_pose, pose_R, pose_t);
+    int fallbacks = 0;
+    for (int k = 0; k < n; k++) {
+        PointType point = make_point(xyzi + 4 * k);
+        Pose curr_pose;
+        if (!MISC::getPoseFromInsWindow(win, pose_b_l, time[k] + td, curr_pose)) fallbacks++;
+        PointType out       = lidar::PointCloudCommon::relativeProjection(lidar_pose, curr_pose, point);
+        out_xyzi[4 * k]     = out.x;
+        out_xyzi[4 * k + 1] = out.y;
+        out_xyzi[4 * k + 2] = out.z;
+        out_xyzi[4 * k + 3] = out.intensity;
+    }
+    return fallbacks;
+}
+
+void ffref_project(const double *R, const double *t, const float *src, int n, float *dst) {
+    PointCloudPtr a(new PointCloud), b(new PointCloud);
+    a->resize(n);
+    for (int k = 0; k < n; k++) a->points[k] = make_point(src + 4 * k);
+    lidar::PointCloudCommon::pointCloudProjection(make_pose(R, t), a, b);
+    for (int k = 0; k < n; k++) {
+        dst[4 * k]     = b->points[k].x;
+        dst[4 * k + 1] = b->points[k].y;
+        dst[4 * k + 2] = b->points[k].z;
+        dst[4 * k + 3] = b->points[k].intensity;
+    }
+}
+
+int ffref_plane_estimation(const float *pts, double threshold, double *unit_normal, double *norm_inverse, double *distance) {
+    PointVector points;
+    for (int k = 0; k < 5; k++) points.push_back(make_point(pts + 4 * k));
+    Vector3d n;
+    std::vector<double> dist;
+    bool ok = lidar::PointCloudCommon::planeEstimation(points, threshold, n, *norm_inverse, dist);
+    for (int i = 0; i < 3; i++) unit_normal[i] = n[i];
+    for (size_t i = 0; i < 5; i++) distance[i] = i < dist.size() ? dist[i] : 0.0;
+    return ok ? 1 : 0;
+}
+
+/* motion = {v0, w0, td0, v1, w1, td1}; parameters = {pose_ref, pose_cur, ext, td} (7, 7, 7, 1) */
+int ffref_lidar_factor_evaluate(const float *point_xyz, const double *n, double d, double std, const double *motion,
+                                const double *const *parameters, double *residuals, double **jacobians) {
+    PointType p;
+    p.x = point_xyz[0], p.y = point_xyz[1], p.z = point_xyz[2];
+    LidarFactor f(p, Vector3d(n[0], n[1], n[2]), d, std, Vector3d(motion[0], motion[1], motion[2]),
+                  Vector3d(motion[3], motion[4], motion[5]), motion[6], Vector3d(motion[7], motion[8], motion[9]),
+                  Vector3d(motion[10], motion[11], motion[12]), motion[13]);
+    return f.Evaluate(parameters, residuals, jacobians) ? 1 : 0;
+}
+
+/* MISC::insMechanization (misc.cc:138-184), iswithearth = false: state = {p, q xyzw, v, bg, ba} (16 doubles) updated in
+ * place; imu = {time, dt, dtheta[3], dvel[3]} */
+void ffref_ins_mechanization(const double *gravity, const double *imu_pre, const double *imu_cur, double *state16,
+                             double *state_time) {
+    IntegrationConfiguration cfg{};
+    cfg.iswithearth = false;
+    cfg.gravity     = Vector3d(gravity[0], gravity[1], gravity[2]);
+    auto ld         = [](const double *a) {
+        IMU m;
+        m.time   = a[0];
+        m.dt     = a[1];
+        m.dtheta = Vector3d(a[2], a[3], a[4]);
+        m.dvel   = Vector3d(a[5], a[6], a[7]);
+        m.odovel = 0;
+        return m;
+    };
+    IntegrationState st;
+    st.time = *state_time;
+    st.p    = Vector3d(state16[0], state16[1], state16[2]);
+    st.q    = Quaterniond(state16[6], state16[3], state16[4], state16[5]);
+    st.v    = Vector3d(state16[7], state16[8], state16[9]);
+    st.bg   = Vector3d(state16[10], state16[11], state16[12]);
+    st.ba   = Vector3d(state16[13], state16[14], state16[15]);
+    MISC::insMechanization(cfg, ld(imu_pre), ld(imu_cur), st);
+    *state_time = st.time;
+    for (int i = 0; i < 3; i++) state16[i] = st.p[i], state16[7 + i] = st.v[i];
+    state16[3] = st.q.x(), state16[4] = st.q.y(), state16[5] = st.q.z(), state16[6] = st.q.w();
+}
+}

@@ -1,0 +1,516 @@
+/* Stand-in for the few Eigen headers the reference's hot-path sources include (<Eigen/Geometry>, <Eigen/Eigenvalues>):
+ * Eigen is not installed in this image, so the reference's OWN source files (lidar_factor.cc, rotation.cc,
+ * pointcloud.cc, the pose part of misc.cc) are compiled where they lie against this header (oracle/Makefile `ffref`).
+ *
+ * What this pins and what it does not. The reference's statements - which products, in which grouping, with which signs
+ * and indices - are the reference's own text. The primitives underneath (fixed-size products, quaternion <-> matrix /
+ * angle-axis, normalisation, the 5 x 3 pivoted QR solve) are written here from Eigen 3.4's documented behaviour, eagerly
+ * evaluated (no expression templates, no vectorisation): a k-sum runs in ascending k from the first product. Real Eigen
+ * may group a sum differently (packet code, scalar factors pulled through a product), so agreement with real Eigen is
+ * expected at the rounding level, not bit for bit. The 5 x 3 solve uses column-pivoted Householder reflections written
+ * independently of oracle/oracle.cc. Test infrastructure only: nothing under ff-lins_b200/ includes or links this. */
+#ifndef FFLINS_ORACLE_MINI_EIGEN_H
+#define FFLINS_ORACLE_MINI_EIGEN_H
+
+#include <algorithm>
+#include <cmath>
+#include <cstddef>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <ostream>
+
+#define EIGEN_MAKE_ALIGNED_OPERATOR_NEW
+#define EIGEN_ALIGN16 alignas(16)
+
+namespace Eigen {
+
+enum { ColMajor = 0, RowMajor = 1 };
+template <class T> using aligned_allocator = std::allocator<T>;
+
+template <class T, int R, int C, int Opt = ColMajor> struct Matrix;
+template <class T> struct Quaternion;
+template <class T> struct AngleAxis;
+
+namespace mini {
+template <int R, int C, int Opt> constexpr int at(int r, int c) { return (Opt & RowMajor) ? r * C + c : c * R + r; }
+
+/* writable view of BR x BC coefficients of some storage: what block<>(), row() and Map hand out */
+template <class T, int BR, int BC> struct View {
+    T *p;
+    int rs, cs; /* strides of a row step and of a column step */
+    T &operator()(int r, int c) const { return p[r * rs + c * cs]; }
+    template <int O> const View &operator=(const Matrix<T, BR, BC, O> &m) const {
+        for (int r = 0; r < BR; r++)
+            for (int c = 0; c < BC; c++) (*this)(r, c) = m(r, c);
+        return *this;
+    }
+    /* Eigen lets a column vector be assigned to a row view (and the reverse) */
+    template <int O, int X = BR, class = typename std::enable_if<(X == 1 || BC == 1) && BR != BC>::type>
+    const View &operator=(const Matrix<T, BC, BR, O> &m) const {
+        for (int r = 0; r < BR; r++)
+            for (int c = 0; c < BC; c++) (*this)(r, c) = m(c, r);
+        return *this;
+    }
+    operator Matrix<T, BR, BC>() const {
+        Matrix<T, BR, BC> m;
+        for (int r = 0; r < BR; r++)
+            for (int c = 0; c < BC; c++) m(r, c) = (*this)(r, c);
+        return m;
+    }
+};
+
+template <class T, int R, int C> struct CommaInit {
+    Matrix<T, R, C> *m;
+    int k;
+    CommaInit &operator,(T v) {
+        (*m)(k / C, k % C) = v; /* Eigen's comma initialiser fills row by row */
+        k++;
+        return *this;
+    }
+};
+} // namespace mini
+
+/* a 1 x 1 result is a scalar (Eigen: inner products convert implicitly) */
+template <class D, class T, bool one> struct ScalarConv {};
+template <class D, class T> struct ScalarConv<D, T, true> {
+    operator T() const { return static_cast<const D *>(this)->m[0]; }
+};
+
+template <class T, int R, int C, int Opt> struct Matrix : ScalarConv<Matrix<T, R, C, Opt>, T, R * C == 1> {
+    T m[R * C];
+    typedef T Scalar;
+
+    Matrix() {
+        for (int i = 0; i < R * C; i++) m[i] = T(0);
+    }
+    template <int O2> Matrix(const Matrix<T, R, C, O2> &o) {
+        for (int r = 0; r < R; r++)
+            for (int c = 0; c < C; c++) (*this)(r, c) = o(r, c);
+    }
+    Matrix(T a, T b) {
+        static_assert(R * C == 2, "two-coefficient constructor");
+        m[0] = a, m[1] = b;
+    }
+    Matrix(T a, T b, T c) {
+        static_assert(R * C == 3, "three-coefficient constructor");
+        m[0] = a, m[1] = b, m[2] = c;
+    }
+    explicit Matrix(const Quaternion<T> &q) { *this = q.toRotationMatrix(); }
+
+    static Matrix Zero() { return Matrix(); }
+    static Matrix Identity() {
+        Matrix r;
+        for (int i = 0; i < (R < C ? R : C); i++) r(i, i) = T(1);
+        return r;
+    }
+    static Matrix UnitX() { Matrix r; r.m[0] = T(1); return r; }
+    static Matrix UnitY() { Matrix r; r.m[1] = T(1); return r; }
+    static Matrix UnitZ() { Matrix r; r.m[2] = T(1); return r; }
+
+    int rows() const { return R; }
+    int cols() const { return C; }
+    T *data() { return m; }
+    const T *data() const { return m; }
+    T &operator()(int r, int c) { return m[mini::at<R, C, Opt>(r, c)]; }
+    const T &operator()(int r, int c) const { return m[mini::at<R, C, Opt>(r, c)]; }
+    T &operator()(int i) { return m[i]; }
+    const T &operator()(int i) const { return m[i]; }
+    T &operator[](int i) { return m[i]; }
+    const T &operator[](int i) const { return m[i]; }
+    T &x() { return m[0]; }
+    T &y() { return m[1]; }
+    T &z() { return m[2]; }
+    const T &x() const { return m[0]; }
+    const T &y() const { return m[1]; }
+    const T &z() const { return m[2]; }
+
+    void setZero() { for (int i = 0; i < R * C; i++) m[i] = T(0); }
+    void setOnes() { for (int i = 0; i < R * C; i++) m[i] = T(1); }
+    Matrix &operator*=(T s) { for (int i = 0; i < R * C; i++) m[i] = m[i] * s; return *this; }
+    Matrix &operator/=(T s) { for (int i = 0; i < R * C; i++) m[i] = m[i] / s; return *this; }
+    Matrix &operator+=(const Matrix &o) { for (int i = 0; i < R * C; i++) m[i] = m[i] + o.m[i]; return *this; }
+    Matrix &operator-=(const Matrix &o) { for (int i = 0; i < R * C; i++) m[i] = m[i] - o.m[i]; return *this; }
+
+    mini::CommaInit<T, R, C> operator<<(T v) {
+        static_assert(Opt == ColMajor, "comma initialiser: default storage only");
+        (*this)(0, 0) = v;
+        return mini::CommaInit<T, R, C>{reinterpret_cast<Matrix<T, R, C> *>(this), 1};
+    }
+
+    Matrix<T, C, R> transpose() const {
+        Matrix<T, C, R> t;
+        for (int r = 0; r < R; r++)
+            for (int c = 0; c < C; c++) t(c, r) = (*this)(r, c);
+        return t;
+    }
+    template <class U> Matrix<U, R, C> cast() const {
+        Matrix<U, R, C> o;
+        for (int r = 0; r < R; r++)
+            for (int c = 0; c < C; c++) o(r, c) = static_cast<U>((*this)(r, c));
+        return o;
+    }
+    T squaredNorm() const {
+        T s = m[0] * m[0];
+        for (int i = 1; i < R * C; i++) s = s + m[i] * m[i];
+        return s;
+    }
+    T norm() const { return std::sqrt(squaredNorm()); }
+    T stableNorm() const { return norm(); }
+    /* Eigen 3.4 MatrixBase::normalized(): divide by sqrt(squaredNorm) when that is positive */
+    Matrix normalized() const {
+        T n2 = squaredNorm();
+        if (n2 > T(0)) {
+            Matrix o = *this;
+            o /= std::sqrt(n2);
+            return o;
+        }
+        return *this;
+    }
+    void normalize() { *this = normalized(); }
+    T dot(const Matrix &o) const {
+        T s = m[0] * o.m[0];
+        for (int i = 1; i < R * C; i++) s = s + m[i] * o.m[i];
+        return s;
+    }
+    Matrix cross(const Matrix &o) const {
+        static_assert(R * C == 3, "cross product of 3-vectors");
+        return Matrix(m[1] * o.m[2] - m[2] * o.m[1], m[2] * o.m[0] - m[0] * o.m[2], m[0] * o.m[1] - m[1] * o.m[0]);
+    }
+
+    template <int BR, int BC> mini::View<T, BR, BC> block(int r, int c) {
+        return mini::View<T, BR, BC>{&(*this)(r, c), mini::at<R, C, Opt>(1, 0) - mini::at<R, C, Opt>(0, 0),
+                                     (C > 1 ? mini::at<R, C, Opt>(0, 1) : 1) - mini::at<R, C, Opt>(0, 0)};
+    }
+    mini::View<T, 1, C> row(int r) { return block<1, C>(r, 0); }
+    mini::View<T, R, 1> col(int c) { return block<R, 1>(0, c); }
+
+    struct ColPivQR;
+    ColPivQR colPivHouseholderQr() const { return ColPivQR{*this}; }
+};
+
+/* ---- arithmetic (eager; a k-sum starts from its first product and adds in ascending k) ---- */
+template <class T, int R, int C, int O1, int O2>
+Matrix<T, R, C> operator+(const Matrix<T, R, C, O1> &a, const Matrix<T, R, C, O2> &b) {
+    Matrix<T, R, C> o;
+    for (int r = 0; r < R; r++)
+        for (int c = 0; c < C; c++) o(r, c) = a(r, c) + b(r, c);
+    return o;
+}
+template <class T, int R, int C, int O1, int O2>
+Matrix<T, R, C> operator-(const Matrix<T, R, C, O1> &a, const Matrix<T, R, C, O2> &b) {
+    Matrix<T, R, C> o;
+    for (int r = 0; r < R; r++)
+        for (int c = 0; c < C; c++) o(r, c) = a(r, c) - b(r, c);
+    return o;
+}
+template <class T, int R, int C, int O> Matrix<T, R, C> operator-(const Matrix<T, R, C, O> &a) {
+    Matrix<T, R, C> o;
+    for (int r = 0; r < R; r++)
+        for (int c = 0; c < C; c++) o(r, c) = -a(r, c);
+    return o;
+}
+template <class T, int R, int C, int O> Matrix<T, R, C> operator*(const Matrix<T, R, C, O> &a, T s) {
+    Matrix<T, R, C> o;
+    for (int r = 0; r < R; r++)
+        for (int c = 0; c < C; c++) o(r, c) = a(r, c) * s;
+    return o;
+}
+template <class T, int R, int C, int O> Matrix<T, R, C> operator*(T s, const Matrix<T, R, C, O> &a) {
+    Matrix<T, R, C> o;
+    for (int r = 0; r < R; r++)
+        for (int c = 0; c < C; c++) o(r, c) = s * a(r, c);
+    return o;
+}
+template <class T, int R, int C, int O> Matrix<T, R, C> operator/(const Matrix<T, R, C, O> &a, T s) {
+    Matrix<T, R, C> o;
+    for (int r = 0; r < R; r++)
+        for (int c = 0; c < C; c++) o(r, c) = a(r, c) / s;
+    return o;
+}
+template <class T, int R, int K, int C, int O1, int O2>
+Matrix<T, R, C> operator*(const Matrix<T, R, K, O1> &a, const Matrix<T, K, C, O2> &b) {
+    Matrix<T, R, C> o;
+    for (int r = 0; r < R; r++)
+        for (int c = 0; c < C; c++) {
+            T s = a(r, 0) * b(0, c);
+            for (int k = 1; k < K; k++) s = s + a(r, k) * b(k, c);
+            o(r, c) = s;
+        }
+    return o;
+}
+template <class T, int R, int C, int O> std::ostream &operator<<(std::ostream &os, const Matrix<T, R, C, O> &a) {
+    for (int r = 0; r < R; r++) {
+        for (int c = 0; c < C; c++) os << (c ? " " : "") << a(r, c);
+        if (r + 1 < R) os << "\n";
+    }
+    return os;
+}
+
+typedef Matrix<double, 2, 1> Vector2d;
+typedef Matrix<double, 3, 1> Vector3d;
+typedef Matrix<float, 3, 1> Vector3f;
+typedef Matrix<double, 4, 1> Vector4d;
+typedef Matrix<double, 3, 3> Matrix3d;
+typedef Matrix<double, 4, 4> Matrix4d;
+typedef Matrix<float, 3, 3> Matrix3f;
+
+/* ---- Map: a view of caller memory with the matrix type's storage order ---- */
+template <class M> struct Map;
+template <class T, int R, int C, int Opt> struct Map<Matrix<T, R, C, Opt>> {
+    T *p;
+    explicit Map(T *ptr) : p(ptr) {}
+    typedef Matrix<T, R, C> Plain;
+    T &operator()(int r, int c) const { return p[mini::at<R, C, Opt>(r, c)]; }
+    Plain eval() const {
+        Plain o;
+        for (int r = 0; r < R; r++)
+            for (int c = 0; c < C; c++) o(r, c) = (*this)(r, c);
+        return o;
+    }
+    operator Plain() const { return eval(); }
+    void setZero() const { for (int i = 0; i < R * C; i++) p[i] = T(0); }
+    template <int O> const Map &operator=(const Matrix<T, R, C, O> &m) const {
+        for (int r = 0; r < R; r++)
+            for (int c = 0; c < C; c++) (*this)(r, c) = m(r, c);
+        return *this;
+    }
+    const Map &operator=(const Map &o) const {
+        for (int i = 0; i < R * C; i++) p[i] = o.p[i];
+        return *this;
+    }
+    template <class M2> const Map &operator=(const Map<M2> &o) const { return *this = o.eval(); }
+    template <class U> Matrix<U, R, C> cast() const { return eval().template cast<U>(); }
+    T squaredNorm() const { return eval().squaredNorm(); }
+    T norm() const { return eval().norm(); }
+    template <int BR, int BC> mini::View<T, BR, BC> block(int r, int c) const {
+        return mini::View<T, BR, BC>{&(*this)(r, c), mini::at<R, C, Opt>(1, 0) - mini::at<R, C, Opt>(0, 0),
+                                     (C > 1 ? mini::at<R, C, Opt>(0, 1) : 1) - mini::at<R, C, Opt>(0, 0)};
+    }
+};
+/* const maps (pcl's getVector3fMap() const) */
+template <class T, int R, int C, int Opt> struct Map<const Matrix<T, R, C, Opt>> {
+    const T *p;
+    explicit Map(const T *ptr) : p(ptr) {}
+    typedef Matrix<T, R, C> Plain;
+    const T &operator()(int r, int c) const { return p[mini::at<R, C, Opt>(r, c)]; }
+    Plain eval() const {
+        Plain o;
+        for (int r = 0; r < R; r++)
+            for (int c = 0; c < C; c++) o(r, c) = (*this)(r, c);
+        return o;
+    }
+    operator Plain() const { return eval(); }
+    template <class U> Matrix<U, R, C> cast() const { return eval().template cast<U>(); }
+    T squaredNorm() const { return eval().squaredNorm(); }
+};
+template <class M1, class M2> typename Map<M1>::Plain operator-(const Map<M1> &a, const Map<M2> &b) {
+    return a.eval() - b.eval();
+}
+template <class M1, class M2> typename Map<M1>::Plain operator+(const Map<M1> &a, const Map<M2> &b) {
+    return a.eval() + b.eval();
+}
+
+/* ---- AngleAxis / Quaternion: Eigen 3.4 Geometry module formulas (generic, non-vectorised paths) ---- */
+template <class T> struct AngleAxis {
+    T a;
+    Matrix<T, 3, 1> ax;
+    AngleAxis() : a(0) {}
+    template <int O> AngleAxis(T angle, const Matrix<T, 3, 1, O> &axis) : a(angle), ax(axis) {}
+    /* AngleAxis::operator=(QuaternionBase): n = |vec|; angle = 2 atan2(n, |w|), axis = vec / (w < 0 ? -n : n) */
+    explicit AngleAxis(const Quaternion<T> &q) {
+        T n = q.vec().norm();
+        if (n < std::numeric_limits<T>::epsilon()) n = q.vec().stableNorm();
+        if (n != T(0)) {
+            a = T(2) * std::atan2(n, std::abs(q.w()));
+            if (q.w() < T(0)) n = -n;
+            ax = q.vec() / n;
+        } else {
+            a  = T(0);
+            ax = Matrix<T, 3, 1>(T(1), T(0), T(0));
+        }
+    }
+    T angle() const { return a; }
+    const Matrix<T, 3, 1> &axis() const { return ax; }
+    Quaternion<T> operator*(const AngleAxis &o) const { return Quaternion<T>(*this) * Quaternion<T>(o); }
+    Quaternion<T> operator*(const Quaternion<T> &o) const { return Quaternion<T>(*this) * o; }
+};
+
+template <class T> struct Quaternion {
+    T c[4]; /* x, y, z, w as Eigen stores them */
+    Quaternion() { c[0] = c[1] = c[2] = c[3] = T(0); }
+    Quaternion(T w, T x, T y, T z) { c[0] = x, c[1] = y, c[2] = z, c[3] = w; }
+    /* from angle-axis: w = cos(a/2), vec = sin(a/2) * axis */
+    explicit Quaternion(const AngleAxis<T> &aa) {
+        T ha = T(0.5) * aa.angle();
+        c[3] = std::cos(ha);
+        Matrix<T, 3, 1> v = std::sin(ha) * aa.axis();
+        c[0] = v[0], c[1] = v[1], c[2] = v[2];
+    }
+    /* from a rotation matrix (quaternionbase_assign_impl<Other,3,3>, Shoemake's branches) */
+    explicit Quaternion(const Matrix<T, 3, 3> &mat) {
+        T t = mat(0, 0) + mat(1, 1) + mat(2, 2);
+        if (t > T(0)) {
+            t    = std::sqrt(t + T(1.0));
+            c[3] = T(0.5) * t;
+            t    = T(0.5) / t;
+            c[0] = (mat(2, 1) - mat(1, 2)) * t;
+            c[1] = (mat(0, 2) - mat(2, 0)) * t;
+            c[2] = (mat(1, 0) - mat(0, 1)) * t;
+        } else {
+            int i = 0;
+            if (mat(1, 1) > mat(0, 0)) i = 1;
+            if (mat(2, 2) > mat(i, i)) i = 2;
+            int j = (i + 1) % 3, k = (j + 1) % 3;
+            t    = std::sqrt(mat(i, i) - mat(j, j) - mat(k, k) + T(1.0));
+            c[i] = T(0.5) * t;
+            t    = T(0.5) / t;
+            c[3] = (mat(k, j) - mat(j, k)) * t;
+            c[j] = (mat(j, i) + mat(i, j)) * t;
+            c[k] = (mat(k, i) + mat(i, k)) * t;
+        }
+    }
+    T &w() { return c[3]; }
+    T &x() { return c[0]; }
+    T &y() { return c[1]; }
+    T &z() { return c[2]; }
+    const T &w() const { return c[3]; }
+    const T &x() const { return c[0]; }
+    const T &y() const { return c[1]; }
+    const T &z() const { return c[2]; }
+    Matrix<T, 3, 1> vec() const { return Matrix<T, 3, 1>(c[0], c[1], c[2]); }
+    Matrix<T, 4, 1> coeffs() const {
+        Matrix<T, 4, 1> v;
+        for (int i = 0; i < 4; i++) v[i] = c[i];
+        return v;
+    }
+    T squaredNorm() const { return coeffs().squaredNorm(); }
+    T norm() const { return coeffs().norm(); }
+    void normalize() {
+        T n = norm(); /* coeffs().normalize() */
+        T n2 = squaredNorm();
+        if (n2 > T(0))
+            for (int i = 0; i < 4; i++) c[i] = c[i] / n;
+    }
+    Quaternion normalized() const { Quaternion q = *this; q.normalize(); return q; }
+    Quaternion conjugate() const { return Quaternion(c[3], -c[0], -c[1], -c[2]); }
+    Quaternion operator*(const AngleAxis<T> &aa) const { return *this * Quaternion(aa); }
+    Quaternion &operator*=(const Quaternion &o) { *this = *this * o; return *this; }
+    /* QuaternionBase::inverse(): conjugate / squaredNorm when that is positive, else zero */
+    Quaternion inverse() const {
+        T n2 = squaredNorm();
+        if (n2 > T(0)) {
+            Quaternion q = conjugate();
+            for (int i = 0; i < 4; i++) q.c[i] = q.c[i] / n2;
+            return q;
+        }
+        return Quaternion();
+    }
+    /* quat_product, generic path */
+    Quaternion operator*(const Quaternion &b) const {
+        const Quaternion &a = *this;
+        return Quaternion(a.w() * b.w() - a.x() * b.x() - a.y() * b.y() - a.z() * b.z(),
+                          a.w() * b.x() + a.x() * b.w() + a.y() * b.z() - a.z() * b.y(),
+                          a.w() * b.y() + a.y() * b.w() + a.z() * b.x() - a.x() * b.z(),
+                          a.w() * b.z() + a.z() * b.w() + a.x() * b.y() - a.y() * b.x());
+    }
+    /* QuaternionBase::toRotationMatrix() */
+    Matrix<T, 3, 3> toRotationMatrix() const {
+        Matrix<T, 3, 3> res;
+        const T tx = T(2) * x(), ty = T(2) * y(), tz = T(2) * z();
+        const T twx = tx * w(), twy = ty * w(), twz = tz * w();
+        const T txx = tx * x(), txy = ty * x(), txz = tz * x();
+        const T tyy = ty * y(), tyz = tz * y(), tzz = tz * z();
+        res(0, 0) = T(1) - (tyy + tzz);
+        res(0, 1) = txy - twz;
+        res(0, 2) = txz + twy;
+        res(1, 0) = txy + twz;
+        res(1, 1) = T(1) - (txx + tzz);
+        res(1, 2) = tyz - twx;
+        res(2, 0) = txz - twy;
+        res(2, 1) = tyz + twx;
+        res(2, 2) = T(1) - (txx + tyy);
+        return res;
+    }
+    Matrix<T, 3, 1> operator*(const Matrix<T, 3, 1> &v) const {
+        /* QuaternionBase::_transformVector: v + w * uv + vec x uv, uv = 2 vec x v */
+        Matrix<T, 3, 1> uv = vec().cross(v);
+        uv += uv;
+        return v + w() * uv + vec().cross(uv);
+    }
+};
+
+typedef Quaternion<double> Quaterniond;
+typedef AngleAxis<double> AngleAxisd;
+
+/* ---- A.colPivHouseholderQr().solve(b) for a tall fixed-size A: Householder reflections with column pivoting on the
+ * largest remaining column norm, then back substitution through the permutation (least squares). Written here from the
+ * textbook algorithm, independently of oracle.cc's restatement. ---- */
+template <class T, int R, int C, int Opt> struct Matrix<T, R, C, Opt>::ColPivQR {
+    Matrix<T, R, C, Opt> A;
+    Matrix<T, C, 1> solve(const Matrix<T, R, 1> &rhs) const {
+        T a[R][C], b[R];
+        int perm[C];
+        for (int r = 0; r < R; r++) {
+            b[r] = rhs[r];
+            for (int c = 0; c < C; c++) a[r][c] = A(r, c);
+        }
+        for (int c = 0; c < C; c++) perm[c] = c;
+        int rank = 0;
+        T maxnorm2 = T(0);
+        for (int c = 0; c < C; c++) {
+            T s = T(0);
+            for (int r = 0; r < R; r++) s += a[r][c] * a[r][c];
+            maxnorm2 = std::max(maxnorm2, s);
+        }
+        const T thresh = std::numeric_limits<T>::epsilon() * T(R) * std::sqrt(maxnorm2);
+        for (int k = 0; k < C; k++) {
+            int best = k;
+            T bestn = T(-1);
+            for (int c = k; c < C; c++) {
+                T s = T(0);
+                for (int r = k; r < R; r++) s += a[r][c] * a[r][c];
+                if (s > bestn) bestn = s, best = c;
+            }
+            if (best != k) {
+                std::swap(perm[k], perm[best]);
+                for (int r = 0; r < R; r++) std::swap(a[r][k], a[r][best]);
+            }
+            T nrm = std::sqrt(bestn);
+            if (!(nrm > thresh)) break;
+            rank++;
+            T alpha = a[k][k] > T(0) ? -nrm : nrm;
+            T v[R];
+            for (int r = 0; r < R; r++) v[r] = r < k ? T(0) : a[r][k];
+            v[k] -= alpha;
+            T vv = T(0);
+            for (int r = k; r < R; r++) vv += v[r] * v[r];
+            if (vv > T(0)) {
+                for (int c = k; c < C; c++) {
+                    T d = T(0);
+                    for (int r = k; r < R; r++) d += v[r] * a[r][c];
+                    d = T(2) * d / vv;
+                    for (int r = k; r < R; r++) a[r][c] -= d * v[r];
+                }
+                T d = T(0);
+                for (int r = k; r < R; r++) d += v[r] * b[r];
+                d = T(2) * d / vv;
+                for (int r = k; r < R; r++) b[r] -= d * v[r];
+            }
+        }
+        T y[C];
+        for (int c = 0; c < C; c++) y[c] = T(0);
+        for (int k = rank - 1; k >= 0; k--) {
+            T s = b[k];
+            for (int c = k + 1; c < rank; c++) s -= a[k][c] * y[c];
+            y[k] = s / a[k][k];
+        }
+        Matrix<T, C, 1> x;
+        for (int c = 0; c < C; c++) x[perm[c]] = y[c];
+        return x;
+    }
+};
+
+} // namespace Eigen
+#endif

@@ -1,0 +1,143 @@
+"""Generates tests/golden/ffref_reference_sources.npz: outputs of the REFERENCE'S OWN source files for the hot path -
+factors/lidar_factor.cc, common/misc.cc, common/rotation.cc, lidar/pointcloud.cc - compiled where they lie under
+/root/reference into oracle/_ref/libff_ref.so (oracle/Makefile `ref`; Eigen / PCL / Ceres / TBB / glog are stand-in headers
+under oracle/refshim/, see refshim/mini_eigen.h for what that pins). Run in the build container, where /root/reference exists:
+
+  make -C oracle && python tests/golden/make_golden_ffref.py
+
+Contents (inputs + reference outputs), all seeded:
+  und_*      a 1,500-point frame through the per-point loop of lidarFrameProcessing (MISC::getPoseFromInsWindow +
+             PointCloudCommon::relativeProjection), 40 of the point times outside the INS window (fallback branch)
+  pw_*       getPoseFromInsWindow / getInsWindowIndex at 64 times incl. the window's edges and entries
+  fac_*      LidarFactor::Evaluate: 96 residuals, residual + the four Jacobian blocks
+  pl_*       planeEstimation on 400 five-point sets (planes, noisy planes, scatter, near-collinear)
+  prj_*      pointCloudProjection of 2,000 points
+  mech_*     MISC::insMechanization over 200 IMU epochs (iswithearth = false)
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "ff-lins_b200"))
+sys.path.insert(0, ROOT)
+
+from fflins import synth  # noqa: E402
+from oracle import pyref as R  # noqa: E402
+
+
+def rand_pose7(rng, span=10.0):
+    q = rng.normal(size=4)
+    q /= np.linalg.norm(q)
+    return np.concatenate([rng.uniform(-span, span, 3), q])
+
+
+def main():
+    assert R.available(), "build oracle/_ref/libff_ref.so first (make -C oracle, needs /root/reference)"
+    rng = np.random.default_rng(20261020)
+    out = {}
+
+    # ---- undistortion loop
+    seq = synth.Sequence("lili", n_points=1500, ins_entries=200)
+    fr = seq.frame(7)
+    time = np.array(fr["time"], np.float64)
+    lo, hi = fr["ins_t"][0] - fr["td"], fr["ins_t"][-1] - fr["td"]
+    time[:20] = lo - rng.uniform(1e-4, 0.05, 20)       # before the window: index 0 -> window.back() pose
+    time[20:40] = hi + rng.uniform(0.0, 0.05, 20)      # at / behind the last entry: ditto
+    und, pR, pt, fb = R.undistort(fr["xyzi"], time, fr["ins_t"], fr["ins_p"], fr["ins_q"], seq.R_bl, seq.t_bl, fr["stamp"],
+                                  fr["td"])
+    assert fb == 40
+    out.update(und_xyzi=np.asarray(fr["xyzi"], np.float32), und_time=time, und_ins_t=fr["ins_t"], und_ins_p=fr["ins_p"],
+               und_ins_q=fr["ins_q"], und_R_bl=np.asarray(seq.R_bl, np.float64), und_t_bl=np.asarray(seq.t_bl, np.float64),
+               und_stamp=float(fr["stamp"]), und_td=float(fr["td"]), und_out=und, und_pose_R=pR, und_pose_t=pt,
+               und_fallbacks=fb, und_filter_num=seq.filter_num)
+
+    # ---- pose / index queries
+    it = np.asarray(fr["ins_t"], np.float64)
+    times = np.concatenate([[it[0] - 1e-3, it[0], it[-1], it[-1] + 1e-3, np.nextafter(it[-1], 0), it[1], it[len(it) // 2]],
+                            rng.uniform(it[0], it[-1], 57)])
+    pw_ok, pw_R, pw_t, pw_idx = [], [], [], []
+    for tm in times:
+        ok, Rm, tv = R.pose_from_ins_window(it, fr["ins_p"], fr["ins_q"], seq.R_bl, seq.t_bl, tm)
+        pw_ok.append(ok), pw_R.append(Rm), pw_t.append(tv)
+        pw_idx.append(R.ins_window_index(it, tm))
+    out.update(pw_times=times, pw_ok=np.array(pw_ok), pw_R=np.array(pw_R), pw_t=np.array(pw_t), pw_index=np.array(pw_idx))
+
+    # ---- LidarFactor::Evaluate
+    n = 96
+    fac = dict(point=rng.uniform(-30, 30, (n, 3)).astype(np.float32), normal=np.zeros((n, 3)), d=rng.uniform(-5, 5, n),
+               std=np.full(n, 0.1), motion=np.zeros((n, 14)), pose_ref=np.zeros((n, 7)), pose_cur=np.zeros((n, 7)),
+               ext=np.zeros((n, 7)), td=rng.normal(size=n) * 0.01, r=np.zeros(n), J=np.zeros((n, 22)))
+    for i in range(n):
+        nv = rng.normal(size=3)
+        fac["normal"][i] = nv / np.linalg.norm(nv)
+        fac["motion"][i] = np.concatenate([rng.normal(size=3), rng.normal(size=3) * 0.3, [rng.normal() * 0.01],
+                                           rng.normal(size=3), rng.normal(size=3) * 0.3, [rng.normal() * 0.01]])
+        fac["pose_ref"][i], fac["pose_cur"][i], fac["ext"][i] = rand_pose7(rng), rand_pose7(rng), rand_pose7(rng, 0.3)
+        if i % 3 == 0:      # nearby poses, as in a window
+            fac["pose_cur"][i, :3] = fac["pose_ref"][i, :3] + rng.normal(size=3) * 0.3
+            q = fac["pose_ref"][i, 3:] + rng.normal(size=4) * 0.02
+            fac["pose_cur"][i, 3:] = q / np.linalg.norm(q)
+        r, J = R.lidar_factor_evaluate(fac["point"][i], fac["normal"][i], fac["d"][i], fac["std"][i], fac["motion"][i],
+                                       fac["pose_ref"][i], fac["pose_cur"][i], fac["ext"][i], fac["td"][i])
+        fac["r"][i] = r
+        fac["J"][i] = np.concatenate(J)
+    out.update({"fac_" + k: v for k, v in fac.items()})
+
+    # ---- planeEstimation
+    m = 400
+    pts = np.zeros((m, 5, 4), np.float32)
+    for i in range(m):
+        c = rng.uniform(-20, 20, 3)
+        nv = rng.normal(size=3)
+        nv /= np.linalg.norm(nv)
+        u = rng.normal(size=(5, 3))
+        u -= np.outer(u @ nv, nv)
+        mode = i % 5
+        if mode == 3:
+            p = rng.uniform(-5, 5, (5, 3)) + c
+        elif mode == 4:
+            a = rng.uniform(-3, 3, 5)
+            p = c + np.outer(a, rng.normal(size=3)) + 1e-3 * rng.normal(size=(5, 3))
+        else:
+            p = c + u * rng.uniform(0.2, 1.5) + np.outer(rng.normal(size=5) * [0.001, 0.03, 0.09][mode], nv)
+        pts[i, :, :3] = p
+        pts[i, :, 3] = rng.uniform(0, 255, 5)
+    pl_ok, pl_n, pl_ninv, pl_dist = np.zeros(m, bool), np.zeros((m, 3)), np.zeros(m), np.zeros((m, 5))
+    for i in range(m):
+        pl_ok[i], pl_n[i], pl_ninv[i], pl_dist[i] = R.plane_estimation(pts[i], 0.1)
+    assert 0 < pl_ok.sum() < m
+    out.update(pl_points=pts, pl_ok=pl_ok, pl_normal=pl_n, pl_norm_inverse=pl_ninv, pl_distance=pl_dist)
+
+    # ---- pointCloudProjection
+    src = rng.uniform(-80, 80, (2000, 4)).astype(np.float32)
+    pose = rand_pose7(rng, 200.0)
+    Rw, _ = R.state_to_pose(np.zeros(3), pose[3:], np.eye(3), np.zeros(3))
+    out.update(prj_src=src, prj_R=Rw, prj_t=pose[:3], prj_dst=R.project(Rw, pose[:3], src), prj_q=pose[3:])
+
+    # ---- insMechanization
+    k = 200
+    g = np.array([0.0, 0.0, -9.8])
+    imu = np.zeros((k + 1, 8))
+    imu[:, 0] = 100.0 + 0.005 * np.arange(k + 1)
+    imu[:, 1] = 0.005
+    imu[:, 2:5] = rng.normal(size=(k + 1, 3)) * 0.002 + [0.001, -0.0005, 0.002]
+    imu[:, 5:8] = rng.normal(size=(k + 1, 3)) * 0.01 + [0.0, 0.0, 9.8 * 0.005]
+    st = np.concatenate([[1.0, -2.0, 0.5], rand_pose7(rng)[3:], [0.4, -0.2, 0.05], [1e-4, -2e-4, 5e-5], [2e-3, 1e-3, -3e-3]])
+    states = np.zeros((k + 1, 16))
+    states[0] = st
+    tm = imu[0, 0]
+    for i in range(1, k + 1):
+        st, tm = R.ins_mechanization(g, imu[i - 1], imu[i], st, tm)
+        states[i] = st
+    out.update(mech_gravity=g, mech_imu=imu, mech_states=states)
+
+    path = os.path.join(HERE, "ffref_reference_sources.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()
