@@ -1,7 +1,8 @@
 /*
  * oracle.cc — CPU restatement of the FF-LINS LiDAR hot path. TEST INFRASTRUCTURE ONLY
- * (see oracle.h for who may load it and for the parity status: "parity unpinned" for the
- * Eigen / PCL / Ceres arithmetic, pinned for kNN against the reference's own ikd-Tree).
+ * (see oracle.h for who may load it and for the parity status: pinned against the reference's own
+ * lidar_factor.cc / misc.cc / rotation.cc / pointcloud.cc / lidar_map.cc / ikd-Tree compiled into oracle/_ref/;
+ * "parity unpinned" only for what lives inside Eigen / PCL / Ceres themselves).
  *
  * Written from the reference's behaviour, not its text: each function cites the upstream
  * file:line it follows (paths relative to the FF-LINS tree). Build with

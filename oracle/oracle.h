@@ -6,12 +6,20 @@
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
  * it; the product library (ff-lins_b200/) never links, imports or calls it.
  *
- * PARITY STATUS: the reference ships no tests or golden vectors for this path and cannot be
- * compiled here (Eigen, PCL, Ceres, TBB absent) => "parity unpinned" for everything that
- * lives in Eigen/PCL/Ceres. What IS pinned: (1) kNN semantics against the reference's own
- * vendored ikd-Tree compiled from /root/reference into oracle/_ref/ (oracle/Makefile),
- * (2) the QR plane fit and quaternion algebra against LAPACK/scipy, (3) LidarFactor
- * Jacobians by central differences, (4) hand-computable KATs (tests/test_oracle_*.py).
+ * PARITY STATUS: the reference ships no tests or golden vectors for this path, and its third-party
+ * libraries (Eigen, PCL, Ceres, TBB, glog, yaml-cpp) are absent here. Pinned against the reference's OWN
+ * SOURCE FILES compiled where they lie under /root/reference into oracle/_ref/ (oracle/Makefile `ref`):
+ *   (1) kNN: the vendored ikd-Tree (libikd_ref.so), bit-identical neighbours and distances;
+ *   (2) lidar_factor.cc, misc.cc, rotation.cc, pointcloud.cc and lidar_map.cc + ikd-Tree (libff_ref.so, built against
+ *       the stand-in headers of oracle/refshim/): the undistortion loop, frame poses, projections, merge, every
+ *       output of LidarFactor::Evaluate, feature types, the five nearest points and the counters of
+ *       updateLidarFeaturesInMap are bit-identical to this oracle; plane parameters agree to 1e-11 (the 5 x 3
+ *       pivoted-QR solve is written independently on either side); tests/test_reference_sources.py,
+ *       committed outputs tests/golden/ffref_*.npz.
+ * Still "parity unpinned": what lives INSIDE the absent libraries - Eigen's own evaluation order of small products
+ * and its QR / quaternion kernels (modelled in refshim/mini_eigen.h), PCL's VoxelGrid (restated, twice, from its
+ * published algorithm: summation order inside a voxel is implementation-defined in PCL), Ceres' Huber corrector.
+ * Those are cross-checked against LAPACK / scipy / finite differences / closed forms (tests/test_oracle.py).
  */
 #ifndef FFLINS_ORACLE_H
 #define FFLINS_ORACLE_H

@@ -115,3 +115,99 @@ def ins_mechanization(gravity, imu_pre, imu_cur, state16, state_time):
     tm = np.array([state_time], np.float64)
     lib().ffref_ins_mechanization(_P(g), _P(a), _P(b), _P(s), _P(tm))
     return s, float(tm[0])
+
+
+class RefLidarMap:
+    """The reference's own lidar::LidarMap (lidar_map.cc compiled from /root/reference, oracle/ffref_map_wrap.cc), driven in
+    the order ff_lins.cc drives it. Keyframes are addressed by their index in the window (0 = oldest, -1 = newest)."""
+    CLOUD_LIDAR, CLOUD_WORLD, CLOUD_MAP, CLOUD_MAP_FULL, CLOUD_LIDAR_FULL = range(5)
+
+    def __init__(self, point_filter_num, point_std=0.1, window_size=10, downsample=0.5, frame_rate=10.0, plane_threshold=0.1,
+                 min_keyframe_translation=0.3):
+        L = lib()
+        L.ffref_map_create.restype = C.c_void_p
+        L.ffref_map_create.argtypes = [C.c_double, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]
+        L.ffref_map_frame.argtypes = [C.c_void_p, fp, dp, C.c_int, dp, dp, dp, C.c_int, dp, dp, C.c_double, C.c_double]
+        for name in ("ffref_map_destroy", "ffref_map_keyframe", "ffref_map_update_features", "ffref_map_remove_oldest",
+                     "ffref_map_remove_newest", "ffref_map_window"):
+            getattr(L, name).argtypes = [C.c_void_p]
+        L.ffref_map_set_pose.argtypes = [C.c_void_p, C.c_int, dp, dp]
+        L.ffref_map_get_pose.argtypes = [C.c_void_p, C.c_int, dp, dp]
+        L.ffref_map_cloud.argtypes = [C.c_void_p, C.c_int, C.c_int, fp, C.c_int]
+        L.ffref_map_features.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32), dp, dp, fp, C.POINTER(C.c_int32), dp,
+                                         C.POINTER(C.c_uint8)]
+        L.ffref_map_counts.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        self.L = L
+        self.h = L.ffref_map_create(point_std, window_size, downsample, frame_rate, plane_threshold, min_keyframe_translation,
+                                    point_filter_num)
+
+    def close(self):
+        if self.h:
+            self.L.ffref_map_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _key(self, k):
+        n = self.window()
+        return k + n if k < 0 else k
+
+    def frame(self, xyzi, time, ins_t, ins_p, ins_q, R_bl, t_bl, stamp, td):
+        """lidarFrameProcessing on a new frame; returns the size of its down-sampled cloud."""
+        xyzi, time = _f(xyzi), _d(time)
+        ins_t, ins_p, ins_q, R_bl, t_bl = _d(ins_t), _d(ins_p), _d(ins_q), _d(R_bl).reshape(-1), _d(t_bl)
+        return self.L.ffref_map_frame(self.h, _F(xyzi), _P(time), len(xyzi), _P(ins_t), _P(ins_p), _P(ins_q), len(ins_t),
+                                      _P(R_bl), _P(t_bl), float(stamp), float(td))
+
+    def keyframe(self):
+        """The newest pending frame becomes a keyframe (merge, addNewKeyFrame, updateLidarFeaturesInMap)."""
+        return self.L.ffref_map_keyframe(self.h)
+
+    def update_features(self):
+        self.L.ffref_map_update_features(self.h)
+
+    def remove_oldest(self):
+        self.L.ffref_map_remove_oldest(self.h)
+
+    def remove_newest(self):
+        self.L.ffref_map_remove_newest(self.h)
+
+    def window(self):
+        return self.L.ffref_map_window(self.h)
+
+    def set_pose(self, k, R, t):
+        R, t = _d(R).reshape(-1), _d(t)
+        self.L.ffref_map_set_pose(self.h, self._key(k), _P(R), _P(t))
+
+    def pose(self, k):
+        R, t = np.zeros(9), np.zeros(3)
+        self.L.ffref_map_get_pose(self.h, self._key(k), _P(R), _P(t))
+        return R.reshape(3, 3), t
+
+    def cloud(self, k, which):
+        n = self.L.ffref_map_cloud(self.h, self._key(k), which, None, 0)
+        out = np.zeros((n, 4), np.float32)
+        if n:
+            self.L.ffref_map_cloud(self.h, self._key(k), which, _F(out), n)
+        return out
+
+    def features(self, k):
+        k = self._key(k)
+        i32 = C.POINTER(C.c_int32)
+        n = self.L.ffref_map_features(self.h, k, None, None, None, None, None, None, None)
+        out = dict(type=np.zeros(n, np.int32), normal=np.zeros((n, 3)), d=np.zeros(n), nearest=np.zeros((n, 5, 4), np.float32),
+                   n_nearest=np.zeros(n, np.int32), std=np.zeros(n), outlier=np.zeros(n, np.uint8))
+        if n:
+            self.L.ffref_map_features(self.h, k, out["type"].ctypes.data_as(i32), _P(out["normal"]), _P(out["d"]),
+                                      _F(out["nearest"]), out["n_nearest"].ctypes.data_as(i32), _P(out["std"]),
+                                      out["outlier"].ctypes.data_as(C.POINTER(C.c_uint8)))
+        return out
+
+    def counts(self):
+        a, b = C.c_int32(), C.c_int32()
+        self.L.ffref_map_counts(self.h, C.byref(a), C.byref(b))
+        return a.value, b.value

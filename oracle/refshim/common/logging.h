@@ -10,6 +10,9 @@ struct FflinsNullLog {
 #define LOGW (FflinsNullLog())
 #define LOGE (FflinsNullLog())
 #define LOGF (FflinsNullLog())
+namespace absl {
+template <class... A> std::string StrFormat(const char *, const A &...) { return std::string(); }
+} // namespace absl
 class Logging {
 public:
     static std::string doubleData(double v) { return std::to_string(v); }

@@ -304,6 +304,7 @@ template <class T, int R, int C, int Opt> struct Map<const Matrix<T, R, C, Opt>>
     operator Plain() const { return eval(); }
     template <class U> Matrix<U, R, C> cast() const { return eval().template cast<U>(); }
     T squaredNorm() const { return eval().squaredNorm(); }
+    T norm() const { return eval().norm(); }
 };
 template <class M1, class M2> typename Map<M1>::Plain operator-(const Map<M1> &a, const Map<M2> &b) {
     return a.eval() - b.eval();
@@ -331,6 +332,8 @@ template <class T> struct AngleAxis {
             ax = Matrix<T, 3, 1>(T(1), T(0), T(0));
         }
     }
+    /* AngleAxis::fromRotationMatrix: through the quaternion */
+    explicit AngleAxis(const Matrix<T, 3, 3> &m) { *this = AngleAxis(Quaternion<T>(m)); }
     T angle() const { return a; }
     const Matrix<T, 3, 1> &axis() const { return ax; }
     Quaternion<T> operator*(const AngleAxis &o) const { return Quaternion<T>(*this) * Quaternion<T>(o); }

@@ -2,6 +2,14 @@
 #ifndef FFLINS_ORACLE_REFSHIM_PCL_POINT_CLOUD_H
 #define FFLINS_ORACLE_REFSHIM_PCL_POINT_CLOUD_H
 #include "point_types.h"
+/* headers the real PCL / Eigen headers pull in transitively and the reference relies on */
+#include <deque>
+#include <iostream>
+#include <map>
+#include <mutex>
+#include <numeric>
+#include <string>
+#include <unordered_map>
 namespace pcl {
 template <class P> struct PointCloud {
     typedef std::shared_ptr<PointCloud<P>> Ptr;
@@ -9,6 +17,11 @@ template <class P> struct PointCloud {
     size_t size() const { return points.size(); }
     void resize(size_t n) { points.resize(n); }
     void reserve(size_t n) { points.reserve(n); }
+    bool empty() const { return points.empty(); }
+    PointCloud &operator+=(const PointCloud &o) {
+        points.insert(points.end(), o.points.begin(), o.points.end());
+        return *this;
+    }
     P &operator[](size_t i) { return points[i]; }
     const P &operator[](size_t i) const { return points[i]; }
 };

@@ -19,7 +19,22 @@
     Eigen::Map<Eigen::Vector3f> getVector3fMap() { return Eigen::Map<Eigen::Vector3f>(data); }                        \
     Eigen::Map<const Eigen::Vector3f> getVector3fMap() const { return Eigen::Map<const Eigen::Vector3f>(data); }
 #define POINT_CLOUD_REGISTER_POINT_STRUCT(name, fields)
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <unistd.h>
 namespace pcl {
+/* the reference's ikd_Tree.cc instantiates its tree for these two as well (ikd_Tree.cc:1507-1510) */
+struct EIGEN_ALIGN16 PointXYZ {
+    PCL_ADD_POINT4D;
+    PointXYZ() { data[0] = data[1] = data[2] = 0.f, data[3] = 1.f; }
+};
+struct EIGEN_ALIGN16 PointXYZINormal {
+    PCL_ADD_POINT4D;
+    float normal_x = 0, normal_y = 0, normal_z = 0, pad2_ = 0;
+    float intensity = 0, curvature = 0, pad3_[2] = {0, 0};
+    PointXYZINormal() { data[0] = data[1] = data[2] = 0.f, data[3] = 1.f; }
+};
 struct EIGEN_ALIGN16 PointXYZI {
     PCL_ADD_POINT4D;
     union {

@@ -11,6 +11,12 @@ public:
     T begin() const { return b_; }
     T end() const { return e_; }
 };
+/* task_group::run executes the task at once (LidarMap uses it to allocate / release kd-trees off the critical path) */
+class task_group {
+public:
+    template <class F> void run(const F &f) { f(); }
+    void wait() {}
+};
 template <class R, class F> void parallel_for(const R &range, const F &body) { body(range); }
 } // namespace tbb
 #endif

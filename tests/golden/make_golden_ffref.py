@@ -13,6 +13,12 @@ Contents (inputs + reference outputs), all seeded:
   pl_*       planeEstimation on 400 five-point sets (planes, noisy planes, scatter, near-collinear)
   prj_*      pointCloudProjection of 2,000 points
   mech_*     MISC::insMechanization over 200 IMU epochs (iswithearth = false)
+
+and tests/golden/ffref_lidar_map.npz: the reference's own lidar::LidarMap (lidar_map.cc + the vendored ikd-Tree) driven
+over 3 keyframes x 2 frames of the `robot` sequence (2,000 points per frame): per frame the undistorted cloud and pose,
+per keyframe the down-sampled / world / map clouds, and per (reference, newest) pair of every association the
+LidarFeatures (type, unit normal, norm inverse, the five nearest map points in the kd-tree's order) and the counters.
+The VoxelGrid under it is the stand-in of oracle/refshim/pcl/filters/voxel_grid.h (PCL is not installed).
 """
 import os
 import sys
@@ -135,6 +141,46 @@ def main():
     out.update(mech_gravity=g, mech_imu=imu, mech_states=states)
 
     path = os.path.join(HERE, "ffref_reference_sources.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+    lidar_map_golden()
+
+
+MAP_SEQ = dict(name="robot", n_points=2000, n_keys=3, frames_per_key=2)
+
+
+def lidar_map_golden():
+    seq = synth.Sequence(MAP_SEQ["name"], n_points=MAP_SEQ["n_points"])
+    ref = R.RefLidarMap(seq.filter_num)
+    out = dict(filter_num=seq.filter_num, n_keys=MAP_SEQ["n_keys"], frames_per_key=MAP_SEQ["frames_per_key"],
+               R_bl=np.asarray(seq.R_bl, np.float64), t_bl=np.asarray(seq.t_bl, np.float64))
+    fi = 0
+    for k in range(MAP_SEQ["n_keys"]):
+        for j in range(MAP_SEQ["frames_per_key"]):
+            fr = seq.frame(fi)
+            args = (fr["xyzi"], fr["time"], fr["ins_t"], fr["ins_p"], fr["ins_q"], seq.R_bl, seq.t_bl, fr["stamp"], fr["td"])
+            ref.frame(*args)
+            und, pR, pt, fb = R.undistort(*args)        # the same loop over the same reference functions
+            assert fb == 0
+            out[f"f{fi}_und"], out[f"f{fi}_R"], out[f"f{fi}_t"] = und, pR, pt
+            fi += 1
+        ref.keyframe()
+        cur = fi - 1
+        Rk, tk = ref.pose(-1)
+        assert Rk.tobytes() == out[f"f{cur}_R"].tobytes() and tk.tobytes() == out[f"f{cur}_t"].tobytes()
+        assert ref.cloud(-1, ref.CLOUD_LIDAR_FULL).tobytes() == out[f"f{cur}_und"][::seq.filter_num].tobytes()
+        out[f"k{k}_down"] = ref.cloud(-1, ref.CLOUD_LIDAR)
+        out[f"k{k}_world"] = ref.cloud(-1, ref.CLOUD_WORLD)
+        out[f"k{k}_map"] = ref.cloud(-1, ref.CLOUD_MAP)
+        out[f"k{k}_map_full_n"] = len(ref.cloud(-1, ref.CLOUD_MAP_FULL))
+        if k >= 1:
+            out[f"k{k}_counts"] = np.array(ref.counts())
+            for i in range(k):
+                ft = ref.features(i)
+                for name in ("type", "normal", "d", "nearest", "n_nearest", "std"):
+                    out[f"k{k}_r{i}_{name}"] = ft[name]
+    ref.close()
+    path = os.path.join(HERE, "ffref_lidar_map.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")
 
