@@ -10,6 +10,7 @@
 #include "common/misc.h"
 #include "common/rotation.h"
 #include "factors/lidar_factor.h"
+#include "factors/residual_block_info.h"
 #include "lidar/pointcloud.h"
 
 #include <cstring>
@@ -134,6 +135,30 @@ int ffref_lidar_factor_evaluate(const float *point_xyz, const double *n, double 
                   Vector3d(motion[3], motion[4], motion[5]), motion[6], Vector3d(motion[7], motion[8], motion[9]),
                   Vector3d(motion[10], motion[11], motion[12]), motion[13]);
     return f.Evaluate(parameters, residuals, jacobians) ? 1 : 0;
+}
+
+/* ResidualBlockInfo::Evaluate (residual_block_info.cc:33-80) over a LidarFactor with ceres::HuberLoss(delta) (delta <= 0:
+ * no loss function): corrected residual and the four corrected Jacobian blocks [7, 7, 7, 1] -> J22 */
+void ffref_residual_block_evaluate(const float *point_xyz, const double *n, double d, double std, const double *motion,
+                                   const double *const *parameters, double huber_delta, double *residual, double *J22) {
+    PointType p;
+    p.x = point_xyz[0], p.y = point_xyz[1], p.z = point_xyz[2];
+    auto factor = std::make_shared<LidarFactor>(p, Vector3d(n[0], n[1], n[2]), d, std, Vector3d(motion[0], motion[1], motion[2]),
+                                                Vector3d(motion[3], motion[4], motion[5]), motion[6],
+                                                Vector3d(motion[7], motion[8], motion[9]),
+                                                Vector3d(motion[10], motion[11], motion[12]), motion[13]);
+    std::shared_ptr<ceres::LossFunction> loss;
+    if (huber_delta > 0) loss = std::make_shared<ceres::HuberLoss>(huber_delta);
+    std::vector<double *> blocks;
+    for (int i = 0; i < 4; i++) blocks.push_back(const_cast<double *>(parameters[i]));
+    ResidualBlockInfo info(factor, loss, blocks, std::vector<int>{});
+    info.Evaluate();
+    residual[0] = info.residuals()[0];
+    int o       = 0;
+    for (int b = 0; b < 4; b++) {
+        const auto &J = info.jacobians()[b];
+        for (int j = 0; j < J.cols(); j++) J22[o++] = J(0, j);
+    }
 }
 
 /* MISC::insMechanization (misc.cc:138-184), iswithearth = false: state = {p, q xyzw, v, bg, ba} (16 doubles) updated in

@@ -10,15 +10,15 @@
  * libraries (Eigen, PCL, Ceres, TBB, glog, yaml-cpp) are absent here. Pinned against the reference's OWN
  * SOURCE FILES compiled where they lie under /root/reference into oracle/_ref/ (oracle/Makefile `ref`):
  *   (1) kNN: the vendored ikd-Tree (libikd_ref.so), bit-identical neighbours and distances;
- *   (2) lidar_factor.cc, misc.cc, rotation.cc, pointcloud.cc and lidar_map.cc + ikd-Tree (libff_ref.so, built against
+ *   (2) lidar_factor.cc, residual_block_info.cc, misc.cc, rotation.cc, pointcloud.cc and lidar_map.cc + ikd-Tree (libff_ref.so, built against
  *       the stand-in headers of oracle/refshim/): the undistortion loop, frame poses, projections, merge, every
- *       output of LidarFactor::Evaluate, feature types, the five nearest points and the counters of
+ *       output of LidarFactor::Evaluate and of the Huber corrector (ResidualBlockInfo::Evaluate), feature types, the five nearest points and the counters of
  *       updateLidarFeaturesInMap are bit-identical to this oracle; plane parameters agree to 1e-11 (the 5 x 3
  *       pivoted-QR solve is written independently on either side); tests/test_reference_sources.py,
  *       committed outputs tests/golden/ffref_*.npz.
  * Still "parity unpinned": what lives INSIDE the absent libraries - Eigen's own evaluation order of small products
  * and its QR / quaternion kernels (modelled in refshim/mini_eigen.h), PCL's VoxelGrid (restated, twice, from its
- * published algorithm: summation order inside a voxel is implementation-defined in PCL), Ceres' Huber corrector.
+ * published algorithm: summation order inside a voxel is implementation-defined in PCL), ceres::HuberLoss' rho values.
  * Those are cross-checked against LAPACK / scipy / finite differences / closed forms (tests/test_oracle.py).
  */
 #ifndef FFLINS_ORACLE_H

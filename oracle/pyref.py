@@ -211,3 +211,17 @@ class RefLidarMap:
         a, b = C.c_int32(), C.c_int32()
         self.L.ffref_map_counts(self.h, C.byref(a), C.byref(b))
         return a.value, b.value
+
+
+def residual_block_evaluate(point_xyz, normal, d, std, motion, pose_ref, pose_cur, ext, td, huber_delta):
+    """ResidualBlockInfo::Evaluate (residual_block_info.cc:33-80) on a LidarFactor with ceres::HuberLoss(huber_delta)
+    (<= 0: no loss): corrected residual and the 22 corrected Jacobian entries [pose_ref 7 | pose_cur 7 | ext 7 | td]."""
+    L = lib()
+    L.ffref_residual_block_evaluate.argtypes = [fp, dp, C.c_double, C.c_double, dp, C.POINTER(dp), C.c_double, dp, dp]
+    L.ffref_residual_block_evaluate.restype = None
+    params = [_d(pose_ref), _d(pose_cur), _d(ext), np.array([td], np.float64)]
+    par = (dp * 4)(*[_P(p) for p in params])
+    res, J = np.zeros(1), np.zeros(22)
+    pt, nn, mo = _f(point_xyz), _d(normal), _d(motion)
+    L.ffref_residual_block_evaluate(_F(pt), _P(nn), float(d), float(std), _P(mo), par, float(huber_delta), _P(res), _P(J))
+    return float(res[0]), J

@@ -20,6 +20,7 @@
 #include <limits>
 #include <memory>
 #include <ostream>
+#include <vector>
 
 #define EIGEN_MAKE_ALIGNED_OPERATOR_NEW
 #define EIGEN_ALIGN16 alignas(16)
@@ -191,45 +192,49 @@ template <class T, int R, int C, int Opt> struct Matrix : ScalarConv<Matrix<T, R
 };
 
 /* ---- arithmetic (eager; a k-sum starts from its first product and adds in ascending k) ---- */
-template <class T, int R, int C, int O1, int O2>
+template <class T, int R, int C, int O1, int O2, class = typename std::enable_if<(R > 0 && C > 0)>::type>
 Matrix<T, R, C> operator+(const Matrix<T, R, C, O1> &a, const Matrix<T, R, C, O2> &b) {
     Matrix<T, R, C> o;
     for (int r = 0; r < R; r++)
         for (int c = 0; c < C; c++) o(r, c) = a(r, c) + b(r, c);
     return o;
 }
-template <class T, int R, int C, int O1, int O2>
+template <class T, int R, int C, int O1, int O2, class = typename std::enable_if<(R > 0 && C > 0)>::type>
 Matrix<T, R, C> operator-(const Matrix<T, R, C, O1> &a, const Matrix<T, R, C, O2> &b) {
     Matrix<T, R, C> o;
     for (int r = 0; r < R; r++)
         for (int c = 0; c < C; c++) o(r, c) = a(r, c) - b(r, c);
     return o;
 }
-template <class T, int R, int C, int O> Matrix<T, R, C> operator-(const Matrix<T, R, C, O> &a) {
+template <class T, int R, int C, int O, class = typename std::enable_if<(R > 0 && C > 0)>::type>
+Matrix<T, R, C> operator-(const Matrix<T, R, C, O> &a) {
     Matrix<T, R, C> o;
     for (int r = 0; r < R; r++)
         for (int c = 0; c < C; c++) o(r, c) = -a(r, c);
     return o;
 }
-template <class T, int R, int C, int O> Matrix<T, R, C> operator*(const Matrix<T, R, C, O> &a, T s) {
+template <class T, int R, int C, int O, class = typename std::enable_if<(R > 0 && C > 0)>::type>
+Matrix<T, R, C> operator*(const Matrix<T, R, C, O> &a, T s) {
     Matrix<T, R, C> o;
     for (int r = 0; r < R; r++)
         for (int c = 0; c < C; c++) o(r, c) = a(r, c) * s;
     return o;
 }
-template <class T, int R, int C, int O> Matrix<T, R, C> operator*(T s, const Matrix<T, R, C, O> &a) {
+template <class T, int R, int C, int O, class = typename std::enable_if<(R > 0 && C > 0)>::type>
+Matrix<T, R, C> operator*(T s, const Matrix<T, R, C, O> &a) {
     Matrix<T, R, C> o;
     for (int r = 0; r < R; r++)
         for (int c = 0; c < C; c++) o(r, c) = s * a(r, c);
     return o;
 }
-template <class T, int R, int C, int O> Matrix<T, R, C> operator/(const Matrix<T, R, C, O> &a, T s) {
+template <class T, int R, int C, int O, class = typename std::enable_if<(R > 0 && C > 0)>::type>
+Matrix<T, R, C> operator/(const Matrix<T, R, C, O> &a, T s) {
     Matrix<T, R, C> o;
     for (int r = 0; r < R; r++)
         for (int c = 0; c < C; c++) o(r, c) = a(r, c) / s;
     return o;
 }
-template <class T, int R, int K, int C, int O1, int O2>
+template <class T, int R, int K, int C, int O1, int O2, class = typename std::enable_if<(R > 0 && K > 0 && C > 0)>::type>
 Matrix<T, R, C> operator*(const Matrix<T, R, K, O1> &a, const Matrix<T, K, C, O2> &b) {
     Matrix<T, R, C> o;
     for (int r = 0; r < R; r++)
@@ -247,6 +252,89 @@ template <class T, int R, int C, int O> std::ostream &operator<<(std::ostream &o
     }
     return os;
 }
+
+/* ---- run-time sized matrices (Eigen::Dynamic): the surface residual_block_info.cc uses - resize, data, squaredNorm,
+ * scalar and matrix products, differences, transpose - evaluated eagerly in the order the C++ expression groups them ---- */
+enum { Dynamic = -1 };
+template <class T, int Opt> struct DynBase {
+    int r = 0, c = 0;
+    std::vector<T> v;
+    int rows() const { return r; }
+    int cols() const { return c; }
+    T *data() { return v.data(); }
+    const T *data() const { return v.data(); }
+    T &operator()(int i, int j) { return v[(Opt & RowMajor) ? i * c + j : j * r + i]; }
+    const T &operator()(int i, int j) const { return v[(Opt & RowMajor) ? i * c + j : j * r + i]; }
+    void resize(int rows, int cols) { r = rows, c = cols, v.assign((size_t) rows * cols, T(0)); }
+    T squaredNorm() const {
+        T s = T(0);
+        for (size_t i = 0; i < v.size(); i++) s = i ? s + v[i] * v[i] : v[i] * v[i];
+        return s;
+    }
+};
+template <class T, int Opt> struct Matrix<T, Dynamic, Dynamic, Opt> : DynBase<T, Opt> {
+    Matrix() {}
+    template <int O2> Matrix(const DynBase<T, O2> &o) { *this = o; }
+    template <int O2> Matrix &operator=(const DynBase<T, O2> &o) {
+        this->resize(o.r, o.c);
+        for (int i = 0; i < o.r; i++)
+            for (int j = 0; j < o.c; j++) (*this)(i, j) = o(i, j);
+        return *this;
+    }
+    Matrix &operator*=(T s) { for (auto &x : this->v) x = x * s; return *this; }
+    Matrix<T, Dynamic, Dynamic> transpose() const {
+        Matrix<T, Dynamic, Dynamic> t;
+        t.resize(this->c, this->r);
+        for (int i = 0; i < this->r; i++)
+            for (int j = 0; j < this->c; j++) t(j, i) = (*this)(i, j);
+        return t;
+    }
+};
+template <class T, int Opt> struct Matrix<T, Dynamic, 1, Opt> : DynBase<T, ColMajor> {
+    Matrix() {}
+    template <int O2> Matrix(const DynBase<T, O2> &o) { this->r = o.r, this->c = o.c, this->v = o.v; }
+    void resize(int n) { DynBase<T, ColMajor>::resize(n, 1); }
+    void resize(int n, int m) { DynBase<T, ColMajor>::resize(n, m); }
+    int size() const { return this->r; }
+    T &operator[](int i) { return this->v[i]; }
+    const T &operator[](int i) const { return this->v[i]; }
+    using DynBase<T, ColMajor>::operator();
+    T &operator()(int i) { return this->v[i]; }
+    Matrix &operator*=(T s) { for (auto &x : this->v) x = x * s; return *this; }
+    Matrix<T, Dynamic, Dynamic> transpose() const {
+        Matrix<T, Dynamic, Dynamic> t;
+        t.resize(1, this->r);
+        for (int i = 0; i < this->r; i++) t(0, i) = this->v[i];
+        return t;
+    }
+};
+template <class T, int O1, int O2> Matrix<T, Dynamic, Dynamic> operator*(const DynBase<T, O1> &a, const DynBase<T, O2> &b) {
+    Matrix<T, Dynamic, Dynamic> o;
+    o.resize(a.r, b.c);
+    for (int i = 0; i < a.r; i++)
+        for (int j = 0; j < b.c; j++) {
+            T s = a(i, 0) * b(0, j);
+            for (int k = 1; k < a.c; k++) s = s + a(i, k) * b(k, j);
+            o(i, j) = s;
+        }
+    return o;
+}
+template <class T, int O> Matrix<T, Dynamic, Dynamic> operator*(T s, const DynBase<T, O> &a) {
+    Matrix<T, Dynamic, Dynamic> o;
+    o.resize(a.r, a.c);
+    for (int i = 0; i < a.r; i++)
+        for (int j = 0; j < a.c; j++) o(i, j) = s * a(i, j);
+    return o;
+}
+template <class T, int O1, int O2> Matrix<T, Dynamic, Dynamic> operator-(const DynBase<T, O1> &a, const DynBase<T, O2> &b) {
+    Matrix<T, Dynamic, Dynamic> o;
+    o.resize(a.r, a.c);
+    for (int i = 0; i < a.r; i++)
+        for (int j = 0; j < a.c; j++) o(i, j) = a(i, j) - b(i, j);
+    return o;
+}
+typedef Matrix<double, Dynamic, 1> VectorXd;
+typedef Matrix<double, Dynamic, Dynamic> MatrixXd;
 
 typedef Matrix<double, 2, 1> Vector2d;
 typedef Matrix<double, 3, 1> Vector3d;

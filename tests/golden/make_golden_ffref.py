@@ -10,6 +10,8 @@ Contents (inputs + reference outputs), all seeded:
              PointCloudCommon::relativeProjection), 40 of the point times outside the INS window (fallback branch)
   pw_*       getPoseFromInsWindow / getInsWindowIndex at 64 times incl. the window's edges and entries
   fac_*      LidarFactor::Evaluate: 96 residuals, residual + the four Jacobian blocks
+  rb_*       ResidualBlockInfo::Evaluate (the reference's corrector, residual_block_info.cc:49-77) over the same factors
+             with ceres::HuberLoss(1.0) (the loss itself is the stand-in of oracle/refshim/ceres/ceres.h)
   pl_*       planeEstimation on 400 five-point sets (planes, noisy planes, scatter, near-collinear)
   prj_*      pointCloudProjection of 2,000 points
   mech_*     MISC::insMechanization over 200 IMU epochs (iswithearth = false)
@@ -91,6 +93,17 @@ def main():
         fac["r"][i] = r
         fac["J"][i] = np.concatenate(J)
     out.update({"fac_" + k: v for k, v in fac.items()})
+
+    # ---- ResidualBlockInfo::Evaluate with ceres::HuberLoss(1.0): the plane offsets are moved so that the residuals spread
+    # over both branches of the loss (|r| = 0, 0.4, 3, 12 sigma)
+    rb_d, rb_r, rb_J = fac["d"].copy(), np.zeros(n), np.zeros((n, 22))
+    for i in range(n):
+        rb_d[i] = fac["d"][i] - fac["std"][i] * fac["r"][i] + fac["std"][i] * [0.0, 0.4, -3.0, 12.0][i % 4]
+        rb_r[i], rb_J[i] = R.residual_block_evaluate(fac["point"][i], fac["normal"][i], rb_d[i], fac["std"][i],
+                                                     fac["motion"][i], fac["pose_ref"][i], fac["pose_cur"][i], fac["ext"][i],
+                                                     fac["td"][i], 1.0)
+    assert (np.abs(rb_r) > 1).sum() >= n // 3 and (np.abs(rb_r) < 1).sum() >= n // 3
+    out.update(rb_d=rb_d, rb_r=rb_r, rb_J=rb_J)
 
     # ---- planeEstimation
     m = 400
