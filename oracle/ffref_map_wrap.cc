@@ -8,15 +8,22 @@
 #include "lidar/lidar_map.h"
 
 #include "common/misc.h"
+#include "factors/lidar_factor.h"
 
 #include <yaml-cpp/yaml.h>
 
 #include <cstring>
 
 namespace {
+struct FactorRef {
+    std::unique_ptr<LidarFactor> factor;
+    lidar::LidarFeature::Ptr feature;
+    int pair;
+};
 struct Session {
     std::unique_ptr<lidar::LidarMap> map;
     std::vector<lidar::LidarFrame::Ptr> pending; /* frames since the last keyframe, oldest first */
+    std::vector<FactorRef> factors;               /* the residual blocks of the current solve (addLidarFactors) */
 };
 typedef std::deque<std::pair<IMU, IntegrationState>> InsWindow;
 
@@ -160,5 +167,145 @@ void ffref_map_counts(void *h, int32_t *num_features, int32_t *num_covered) {
     auto cur      = static_cast<Session *>(h)->map->keyframes().back();
     *num_features = cur->numFeatures();
     *num_covered  = cur->numCovered();
+}
+
+/* ---- the solver-facing part, as Optimizer drives it (ff_lins/optimizer.cc) ------------------------------------------- */
+
+/* LidarFrame::setVelocity / setAngularVelocity (ff_lins.cc sets them when a keyframe's time node is created) */
+void ffref_map_set_motion(void *h, int key, const double *v, const double *omega) {
+    auto f = static_cast<Session *>(h)->map->keyframes()[key];
+    f->setVelocity(Vector3d(v[0], v[1], v[2]));
+    f->setAngularVelocity(Vector3d(omega[0], omega[1], omega[2]));
+}
+
+/* Optimizer::addLidarFactors (optimizer.cc:437-478): one LidarFactor per PLANE, non-outlier feature of every
+ * (reference, newest) pair, built from the frames' velocity / angular velocity / time delay. Returns their number. */
+int ffref_map_add_factors(void *h) {
+    auto *s = static_cast<Session *>(h);
+    s->factors.clear();
+    const auto &keys = s->map->keyframes();
+    auto cur         = keys.back();
+    const auto &points_lidar = cur->pointCloudLidar()->points;
+    for (size_t i = 0; i + 1 < keys.size(); i++) {
+        auto ref             = keys[i];
+        const auto &features = ref->features();
+        for (size_t k = 0; k < features.size(); k++) {
+            const auto &feature = features[k];
+            if (!feature || (feature->featureType() != lidar::LidarFeature::FEATURE_PLANE) || feature->isOutlier()) continue;
+            FactorRef fr;
+            fr.factor.reset(new LidarFactor(points_lidar[k], feature->unitNormalVector(), feature->normInverse(),
+                                            feature->pointStd(), ref->velocity(), ref->angularVelocity(), ref->timeDelay(),
+                                            cur->velocity(), cur->angularVelocity(), cur->timeDelay()));
+            fr.feature = feature;
+            fr.pair    = (int) i;
+            s->factors.push_back(std::move(fr));
+        }
+    }
+    return (int) s->factors.size();
+}
+
+/* What one solver iteration asks of the LiDAR residual blocks: LidarFactor::Evaluate (residual + the four Jacobian
+ * blocks) of every block, the robust-loss correction Ceres applies (HuberLoss(huber_delta) through the corrector of
+ * residual_block_info.cc:49-77, restated inline; huber_delta <= 0: none) and the accumulation of J^T J, J^T r and the
+ * cost per pair over the 19 tangent columns (6 + 6 + 6 + 1: the quaternion's fourth column is zero). Parallel over the
+ * blocks like Ceres' evaluator (num_threads). pose_refs: n x 7; H: n x 19 x 19; b: n x 19; cost: n. */
+void ffref_map_evaluate_factors(void *h, const double *pose_refs, const double *pose_cur, const double *ext, double td,
+                                double huber_delta, double *H, double *b, double *cost) {
+    auto *s       = static_cast<Session *>(h);
+    const int n   = (int) s->map->keyframes().size() - 1;
+    const size_t m = s->factors.size();
+    static const int col[19] = {0, 1, 2, 3, 4, 5, 7, 8, 9, 10, 11, 12, 14, 15, 16, 17, 18, 19, 21};
+    ceres::HuberLoss loss(huber_delta > 0 ? huber_delta : 1.0);
+    std::memset(H, 0, sizeof(double) * n * 361);
+    std::memset(b, 0, sizeof(double) * n * 19);
+    std::memset(cost, 0, sizeof(double) * n);
+#pragma omp parallel
+    {
+        std::vector<double> Hl((size_t) n * 361, 0.0), bl((size_t) n * 19, 0.0), cl(n, 0.0);
+#pragma omp for schedule(static)
+        for (size_t k = 0; k < m; k++) {
+            const FactorRef &fr        = s->factors[k];
+            const double *parameters[4] = {pose_refs + 7 * fr.pair, pose_cur, ext, &td};
+            double r, J[22];
+            double *jac[4] = {J, J + 7, J + 14, J + 21};
+            fr.factor->Evaluate(parameters, &r, jac);
+            double rho0 = r * r;
+            if (huber_delta > 0) {
+                double rho[3];
+                const double sq_norm = r * r;
+                loss.Evaluate(sq_norm, rho);
+                rho0                   = rho[0];
+                const double sqrt_rho1 = std::sqrt(rho[1]);
+                double residual_scaling, alpha_sq_norm;
+                if ((sq_norm == 0.0) || (rho[2] <= 0.0)) {
+                    residual_scaling = sqrt_rho1;
+                    alpha_sq_norm    = 0.0;
+                } else {
+                    const double D     = 1.0 + 2.0 * sq_norm * rho[2] / rho[1];
+                    const double alpha = 1.0 - std::sqrt(D);
+                    residual_scaling   = sqrt_rho1 / (1 - alpha);
+                    alpha_sq_norm      = alpha / sq_norm;
+                }
+                for (int i = 0; i < 22; i++) J[i] = sqrt_rho1 * (J[i] - alpha_sq_norm * r * (r * J[i]));
+                r *= residual_scaling;
+            }
+            double v[19];
+            for (int i = 0; i < 19; i++) v[i] = J[col[i]];
+            double *Hp = Hl.data() + (size_t) fr.pair * 361, *bp = bl.data() + (size_t) fr.pair * 19;
+            for (int i = 0; i < 19; i++) {
+                for (int j = i; j < 19; j++) Hp[19 * i + j] += v[i] * v[j];
+                bp[i] -= v[i] * r;
+            }
+            cl[fr.pair] += 0.5 * rho0;
+        }
+#pragma omp critical
+        {
+            for (size_t i = 0; i < Hl.size(); i++) H[i] += Hl[i];
+            for (size_t i = 0; i < bl.size(); i++) b[i] += bl[i];
+            for (int i = 0; i < n; i++) cost[i] += cl[i];
+        }
+    }
+    for (int p = 0; p < n; p++)
+        for (int i = 0; i < 19; i++)
+            for (int j = 0; j < i; j++) H[p * 361 + 19 * i + j] = H[p * 361 + 19 * j + i];
+}
+
+/* Optimizer::lidarOutlierCullingByChi2 (optimizer.cc:515-548): residual-only Evaluate of every block, setOutlier() above
+ * the threshold (tbb::parallel_for in the reference). Returns the number of new outliers; per_pair (n) optional. */
+int ffref_map_chi2(void *h, const double *pose_refs, const double *pose_cur, const double *ext, double td, double threshold,
+                   int32_t *per_pair) {
+    auto *s        = static_cast<Session *>(h);
+    const size_t m = s->factors.size();
+    const int n    = (int) s->map->keyframes().size() - 1;
+    std::vector<uint8_t> is_outlier(m, 0);
+    auto culling_function = [&](const tbb::blocked_range<size_t> &range) {
+        for (size_t k = range.begin(); k != range.end(); k++) {
+            const FactorRef &fr         = s->factors[k];
+            const double *parameters[4] = {pose_refs + 7 * fr.pair, pose_cur, ext, &td};
+            double residual;
+            fr.factor->Evaluate(parameters, &residual, nullptr);
+            double cost = residual * residual;
+            if (cost > threshold) {
+                fr.feature->setOutlier();
+                is_outlier[k] = 1;
+            }
+        }
+    };
+    tbb::parallel_for(tbb::blocked_range<size_t>(0, m), culling_function);
+    int total = 0;
+    if (per_pair) std::memset(per_pair, 0, sizeof(int32_t) * n);
+    for (size_t k = 0; k < m; k++)
+        if (is_outlier[k]) {
+            total++;
+            if (per_pair) per_pair[s->factors[k].pair]++;
+        }
+    return total;
+}
+
+/* the world clouds of the window after the solver moved the poses (ff_lins.cc updateParametersFromOptimizer:
+ * pointCloudProjection(pose, lidar, world) per keyframe) */
+void ffref_map_reproject(void *h) {
+    for (auto &f : static_cast<Session *>(h)->map->keyframes())
+        lidar::PointCloudCommon::pointCloudProjection(f->pose(), f->pointCloudLidar(), f->pointCloudWorld());
 }
 }

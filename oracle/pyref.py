@@ -9,7 +9,9 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 PATH = os.path.join(HERE, "_ref", "libff_ref.so")
+PATH_OMP = os.path.join(HERE, "_ref", "libff_ref_omp.so")   # -O3, TBB sites as OpenMP tasks: the CPU-baseline build
 _L = None
+_LOMP = None
 dp = C.POINTER(C.c_double)
 fp = C.POINTER(C.c_float)
 
@@ -18,8 +20,16 @@ def available():
     return os.path.exists(PATH)
 
 
-def lib():
-    global _L
+def omp_available():
+    return os.path.exists(PATH_OMP)
+
+
+def lib(omp=False):
+    global _L, _LOMP
+    if omp:
+        if _LOMP is None:
+            _LOMP = C.CDLL(PATH_OMP)
+        return _LOMP
     if _L is None:
         L = C.CDLL(PATH)
         L.ffref_ins_window_index.argtypes = [dp, C.c_int, C.c_double]
@@ -123,8 +133,14 @@ class RefLidarMap:
     CLOUD_LIDAR, CLOUD_WORLD, CLOUD_MAP, CLOUD_MAP_FULL, CLOUD_LIDAR_FULL = range(5)
 
     def __init__(self, point_filter_num, point_std=0.1, window_size=10, downsample=0.5, frame_rate=10.0, plane_threshold=0.1,
-                 min_keyframe_translation=0.3):
-        L = lib()
+                 min_keyframe_translation=0.3, omp=False):
+        L = lib(omp)
+        L.ffref_map_set_motion.argtypes = [C.c_void_p, C.c_int, dp, dp]
+        L.ffref_map_add_factors.argtypes = [C.c_void_p]
+        L.ffref_map_evaluate_factors.argtypes = [C.c_void_p, dp, dp, dp, C.c_double, C.c_double, dp, dp, dp]
+        L.ffref_map_evaluate_factors.restype = None
+        L.ffref_map_chi2.argtypes = [C.c_void_p, dp, dp, dp, C.c_double, C.c_double, C.POINTER(C.c_int32)]
+        L.ffref_map_reproject.argtypes = [C.c_void_p]
         L.ffref_map_create.restype = C.c_void_p
         L.ffref_map_create.argtypes = [C.c_double, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]
         L.ffref_map_frame.argtypes = [C.c_void_p, fp, dp, C.c_int, dp, dp, dp, C.c_int, dp, dp, C.c_double, C.c_double]
@@ -206,6 +222,34 @@ class RefLidarMap:
                                       _F(out["nearest"]), out["n_nearest"].ctypes.data_as(i32), _P(out["std"]),
                                       out["outlier"].ctypes.data_as(C.POINTER(C.c_uint8)))
         return out
+
+    # ---- the solver-facing part (optimizer.cc:437-548)
+    def set_motion(self, k, v, omega):
+        v, omega = _d(v), _d(omega)
+        self.L.ffref_map_set_motion(self.h, self._key(k), _P(v), _P(omega))
+
+    def add_factors(self):
+        """addLidarFactors: one LidarFactor per PLANE, non-outlier feature of every (reference, newest) pair."""
+        return self.L.ffref_map_add_factors(self.h)
+
+    def evaluate_factors(self, pose_refs, pose_cur, ext, td, huber_delta=1.0, out=None):
+        n = self.window() - 1
+        pose_refs, pose_cur, ext = _d(pose_refs), _d(pose_cur), _d(ext)
+        H, b, cost = out if out is not None else (np.zeros((n, 19, 19)), np.zeros((n, 19)), np.zeros(n))
+        self.L.ffref_map_evaluate_factors(self.h, _P(pose_refs), _P(pose_cur), _P(ext), float(td), float(huber_delta), _P(H),
+                                          _P(b), _P(cost))
+        return H, b, cost
+
+    def chi2(self, pose_refs, pose_cur, ext, td, threshold=3.841):
+        n = self.window() - 1
+        pose_refs, pose_cur, ext = _d(pose_refs), _d(pose_cur), _d(ext)
+        per = np.zeros(n, np.int32)
+        total = self.L.ffref_map_chi2(self.h, _P(pose_refs), _P(pose_cur), _P(ext), float(td), float(threshold),
+                                      per.ctypes.data_as(C.POINTER(C.c_int32)))
+        return total, per
+
+    def reproject(self):
+        self.L.ffref_map_reproject(self.h)
 
     def counts(self):
         a, b = C.c_int32(), C.c_int32()

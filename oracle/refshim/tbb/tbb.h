@@ -17,6 +17,39 @@ public:
     template <class F> void run(const F &f) { f(); }
     void wait() {}
 };
+/* parallel_for: serial by default (the parity builds). With -DFFLINS_REFSHIM_OPENMP -fopenmp (the CPU-baseline build,
+ * oracle/_ref/libff_ref_omp.so) the range is cut into chunks that run as OpenMP tasks; a parallel_for reached from
+ * inside another one (updateLidarFeaturesInMap -> findFeaturesInMap) adds its chunks to the same team, as TBB's
+ * work-stealing scheduler would. The bodies are independent per index, so results do not depend on the partition. */
+#ifdef FFLINS_REFSHIM_OPENMP
+} // namespace tbb
+#include <omp.h>
+namespace tbb {
+template <class R, class F> void parallel_for(const R &range, const F &body) {
+    const auto b = range.begin(), e = range.end();
+    if (!(b < e)) return;
+    const size_t n = (size_t) (e - b);
+    const size_t threads = (size_t) omp_get_max_threads();
+    size_t grain = n / (8 * threads);
+    if (grain < 16) grain = n < 64 ? 1 : 16;
+    const size_t chunks = (n + grain - 1) / grain;
+    auto run = [&]() {
+#pragma omp taskloop grainsize(1) default(shared)
+        for (size_t c = 0; c < chunks; c++) {
+            const size_t lo = c * grain, hi = lo + grain < n ? lo + grain : n;
+            body(R(b + lo, b + hi));
+        }
+    };
+    if (omp_in_parallel()) {
+        run();
+    } else {
+#pragma omp parallel
+#pragma omp single
+        run();
+    }
+}
+#else
 template <class R, class F> void parallel_for(const R &range, const F &body) { body(range); }
+#endif
 } // namespace tbb
 #endif
