@@ -850,9 +850,10 @@ def ref_sources_run(frames, seq, steps, prefill=PREFILL_KEYS):
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
+    threads_used = sess.map.threads
     sess.close()
     return {"value": round(FRAMES_PER_KEY * steps / dt, 3), "unit": "frames/s", "ms_per_step": round(dt * 1e3 / steps, 2),
-            "cores": os.cpu_count(), "steps": steps,
+            "cores": threads_used, "steps": steps,
             "stage_ms_per_step": {k: round(v * 1e3 / steps, 3) for k, v in sess.t.items()},
             "note": "the reference's OWN lidar::LidarMap / ikd-Tree / PointCloudCommon / MISC / LidarFactor sources compiled "
                     "where they lie (-O3 -ffp-contract=off), tbb::parallel_for sites as OpenMP tasks, Eigen / PCL / Ceres as the "

@@ -13,6 +13,9 @@
 #include <yaml-cpp/yaml.h>
 
 #include <cstring>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 namespace {
 struct FactorRef {
@@ -64,6 +67,17 @@ void *ffref_map_create(double point_to_plane_std, int window_size, double downsa
     return s;
 }
 void ffref_map_destroy(void *h) { delete static_cast<Session *>(h); }
+
+/* worker threads of the OpenMP build (launchers such as torchrun export OMP_NUM_THREADS=1); returns what is in effect */
+int ffref_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void) n;
+    return 1;
+#endif
+}
 
 /* LidarMap::lidarFrameProcessing(ins_window, pose_b_l, frame) (lidar_map.cc:213-273) on a new LidarFrame; the frame joins
  * the pending list. Returns the number of points of the frame's down-sampled cloud. */

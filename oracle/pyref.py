@@ -133,7 +133,7 @@ class RefLidarMap:
     CLOUD_LIDAR, CLOUD_WORLD, CLOUD_MAP, CLOUD_MAP_FULL, CLOUD_LIDAR_FULL = range(5)
 
     def __init__(self, point_filter_num, point_std=0.1, window_size=10, downsample=0.5, frame_rate=10.0, plane_threshold=0.1,
-                 min_keyframe_translation=0.3, omp=False):
+                 min_keyframe_translation=0.3, omp=False, threads=None):
         L = lib(omp)
         L.ffref_map_set_motion.argtypes = [C.c_void_p, C.c_int, dp, dp]
         L.ffref_map_add_factors.argtypes = [C.c_void_p]
@@ -154,6 +154,7 @@ class RefLidarMap:
                                          C.POINTER(C.c_uint8)]
         L.ffref_map_counts.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         self.L = L
+        self.threads = L.ffref_set_threads(int(threads or os.cpu_count() or 1)) if omp else 1
         self.h = L.ffref_map_create(point_std, window_size, downsample, frame_rate, plane_threshold, min_keyframe_translation,
                                     point_filter_num)
 
