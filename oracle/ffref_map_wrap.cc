@@ -142,6 +142,21 @@ void ffref_map_get_pose(void *h, int key, double *R, double *t) {
     for (int i = 0; i < 3; i++) t[i] = p.t[i];
 }
 
+/* LidarMap::keyframeSelection (lidar_map.cc:75-98) for a candidate frame with the given pose and stamp against the newest
+ * keyframe; stats = {interval, translation, rotation [rad]} as the reference records them (statisticParameters). */
+int ffref_map_keyframe_selection(void *h, const double *R, const double *t, double stamp, double *stats) {
+    auto *s = static_cast<Session *>(h);
+    PointCloudCustomPtr raw(new PointCloudCustom);
+    auto frame = lidar::LidarFrame::createFrame(stamp, stamp, raw);
+    frame->setPose(make_pose(R, t));
+    bool is_key = s->map->keyframeSelection(frame);
+    const auto &sp = s->map->statisticParameters();
+    stats[0] = sp[4];
+    stats[1] = sp[5];
+    stats[2] = sp[6] / R2D;
+    return is_key ? 1 : 0;
+}
+
 /* which: 0 lidar (down-sampled), 1 world, 2 map, 3 map full, 4 lidar full (decimated). Returns the point count. */
 int ffref_map_cloud(void *h, int key, int which, float *out, int cap) {
     auto f = static_cast<Session *>(h)->map->keyframes()[key];

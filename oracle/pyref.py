@@ -205,6 +205,14 @@ class RefLidarMap:
         self.L.ffref_map_get_pose(self.h, self._key(k), _P(R), _P(t))
         return R.reshape(3, 3), t
 
+    def keyframe_selection(self, R, t, stamp):
+        """LidarMap::keyframeSelection of a candidate frame against the newest keyframe -> (is_keyframe, stats[3])."""
+        self.L.ffref_map_keyframe_selection.argtypes = [C.c_void_p, dp, dp, C.c_double, dp]
+        R, t = _d(R).reshape(-1), _d(t)
+        st = np.zeros(3)
+        ok = self.L.ffref_map_keyframe_selection(self.h, _P(R), _P(t), float(stamp), _P(st))
+        return bool(ok), st
+
     def cloud(self, k, which):
         n = self.L.ffref_map_cloud(self.h, self._key(k), which, None, 0)
         out = np.zeros((n, 4), np.float32)

@@ -164,7 +164,7 @@ MAP_SEQ = dict(name="robot", n_points=2000, n_keys=3, frames_per_key=2)
 
 def lidar_map_golden():
     seq = synth.Sequence(MAP_SEQ["name"], n_points=MAP_SEQ["n_points"])
-    ref = R.RefLidarMap(seq.filter_num)
+    ref = R.RefLidarMap(seq.filter_num, min_keyframe_translation=0.4)
     out = dict(filter_num=seq.filter_num, n_keys=MAP_SEQ["n_keys"], frames_per_key=MAP_SEQ["frames_per_key"],
                R_bl=np.asarray(seq.R_bl, np.float64), t_bl=np.asarray(seq.t_bl, np.float64))
     fi = 0
@@ -192,6 +192,26 @@ def lidar_map_golden():
                 ft = ref.features(i)
                 for name in ("type", "normal", "d", "nearest", "n_nearest", "std"):
                     out[f"k{k}_r{i}_{name}"] = ft[name]
+    # ---- keyframeSelection (lidar_map.cc:75-98) of 48 candidate poses / stamps against the newest keyframe, with the
+    # AT128 configuration's thresholds (0.4 m; 10 deg and 0.475 s are constants of lidar_map.h)
+    rng = np.random.default_rng(7)
+    Rk, tk = ref.pose(-1)
+    stamp_k = seq.frame(fi - 1)["stamp"]
+    cand_R, cand_t, cand_stamp, cand_key, cand_stats = [], [], [], [], []
+    for i in range(48):
+        ang = [0.02, 0.1, 0.17, 0.18, 0.3, 3.0][i % 6] * (1 if i % 2 else -1)
+        ax = rng.normal(size=3)
+        ax /= np.linalg.norm(ax)
+        q = np.concatenate([ax * np.sin(ang / 2), [np.cos(ang / 2)]])
+        dR, _ = R.state_to_pose(np.zeros(3), q, np.eye(3), np.zeros(3))
+        Rc = Rk @ dR
+        tc = tk + rng.normal(size=3) * [0.05, 0.2, 0.24, 0.5][i % 4]
+        st = stamp_k + [0.1, 0.3, 0.47, 0.48, 0.6][i % 5]
+        ok, stats = ref.keyframe_selection(Rc, tc, st)
+        cand_R.append(Rc), cand_t.append(tc), cand_stamp.append(st), cand_key.append(ok), cand_stats.append(stats)
+    assert 5 < sum(cand_key) < 48
+    out.update(ks_key_R=Rk, ks_key_t=tk, ks_key_stamp=stamp_k, ks_R=np.array(cand_R), ks_t=np.array(cand_t),
+               ks_stamp=np.array(cand_stamp), ks_is_key=np.array(cand_key), ks_stats=np.array(cand_stats))
     ref.close()
     path = os.path.join(HERE, "ffref_lidar_map.npz")
     np.savez_compressed(path, **out)
