@@ -10,6 +10,7 @@
 #include "common/misc.h"
 #include "common/rotation.h"
 #include "factors/lidar_factor.h"
+#include "factors/pose_manifold.h"
 #include "factors/residual_block_info.h"
 #include "lidar/pointcloud.h"
 
@@ -159,6 +160,15 @@ void ffref_residual_block_evaluate(const float *point_xyz, const double *n, doub
         const auto &J = info.jacobians()[b];
         for (int j = 0; j < J.cols(); j++) J22[o++] = J(0, j);
     }
+}
+
+/* PoseManifold (factors/pose_manifold.cc:35-83): Plus, Minus and the two Jacobians (7 x 6 and 6 x 7, row-major) */
+void ffref_pose_plus(const double *x, const double *delta, double *x_plus_delta) { PoseManifold().Plus(x, delta, x_plus_delta); }
+void ffref_pose_minus(const double *y, const double *x, double *y_minus_x) { PoseManifold().Minus(y, x, y_minus_x); }
+void ffref_pose_jacobians(const double *x, double *plus_7x6, double *minus_6x7) {
+    PoseManifold m;
+    m.PlusJacobian(x, plus_7x6);
+    m.MinusJacobian(x, minus_6x7);
 }
 
 /* MISC::insMechanization (misc.cc:138-184), iswithearth = false: state = {p, q xyzw, v, bg, ba} (16 doubles) updated in

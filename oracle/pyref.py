@@ -278,3 +278,28 @@ def residual_block_evaluate(point_xyz, normal, d, std, motion, pose_ref, pose_cu
     pt, nn, mo = _f(point_xyz), _d(normal), _d(motion)
     L.ffref_residual_block_evaluate(_F(pt), _P(nn), float(d), float(std), _P(mo), par, float(huber_delta), _P(res), _P(J))
     return float(res[0]), J
+
+
+def pose_plus(x, delta):
+    """PoseManifold::Plus (pose_manifold.cc:35-51): x = [t, q xyzw], delta = [dt, rotation vector]."""
+    x, delta = _d(x), _d(delta)
+    out = np.zeros(7)
+    lib().ffref_pose_plus.restype = None
+    lib().ffref_pose_plus(_P(x), _P(delta), _P(out))
+    return out
+
+
+def pose_minus(y, x):
+    y, x = _d(y), _d(x)
+    out = np.zeros(6)
+    lib().ffref_pose_minus.restype = None
+    lib().ffref_pose_minus(_P(y), _P(x), _P(out))
+    return out
+
+
+def pose_jacobians(x):
+    x = _d(x)
+    jp, jm = np.zeros((7, 6)), np.zeros((6, 7))
+    lib().ffref_pose_jacobians.restype = None
+    lib().ffref_pose_jacobians(_P(x), _P(jp), _P(jm))
+    return jp, jm

@@ -27,6 +27,16 @@ public:
         sizes_         = std::vector<int>{Ns...};
     }
 };
+class Manifold {
+public:
+    virtual ~Manifold() {}
+    virtual int AmbientSize() const = 0;
+    virtual int TangentSize() const = 0;
+    virtual bool Plus(const double *x, const double *delta, double *x_plus_delta) const = 0;
+    virtual bool PlusJacobian(const double *x, double *jacobian) const = 0;
+    virtual bool Minus(const double *y, const double *x, double *y_minus_x) const = 0;
+    virtual bool MinusJacobian(const double *x, double *jacobian) const = 0;
+};
 class LossFunction {
 public:
     virtual ~LossFunction() {}

@@ -60,6 +60,14 @@ template <class T, int BR, int BC> struct View {
             for (int c = 0; c < BC; c++) m(r, c) = (*this)(r, c);
         return m;
     }
+    void setZero() const {
+        for (int r = 0; r < BR; r++)
+            for (int c = 0; c < BC; c++) (*this)(r, c) = T(0);
+    }
+    void setIdentity() const {
+        for (int r = 0; r < BR; r++)
+            for (int c = 0; c < BC; c++) (*this)(r, c) = r == c ? T(1) : T(0);
+    }
 };
 
 template <class T, int R, int C> struct CommaInit {
@@ -376,6 +384,10 @@ template <class T, int R, int C, int Opt> struct Map<Matrix<T, R, C, Opt>> {
         return mini::View<T, BR, BC>{&(*this)(r, c), mini::at<R, C, Opt>(1, 0) - mini::at<R, C, Opt>(0, 0),
                                      (C > 1 ? mini::at<R, C, Opt>(0, 1) : 1) - mini::at<R, C, Opt>(0, 0)};
     }
+    template <int N> mini::View<T, N, C> topRows() const { return block<N, C>(0, 0); }
+    template <int N> mini::View<T, N, C> bottomRows() const { return block<N, C>(R - N, 0); }
+    template <int N> mini::View<T, R, N> leftCols() const { return block<R, N>(0, 0); }
+    template <int N> mini::View<T, R, N> rightCols() const { return block<R, N>(0, C - N); }
 };
 /* const maps (pcl's getVector3fMap() const) */
 template <class T, int R, int C, int Opt> struct Map<const Matrix<T, R, C, Opt>> {
@@ -534,6 +546,20 @@ template <class T> struct Quaternion {
 
 typedef Quaternion<double> Quaterniond;
 typedef AngleAxis<double> AngleAxisd;
+
+/* maps of quaternions stored x, y, z, w in caller memory (pose_manifold.cc): the const map is a copy that behaves as a
+ * Quaternion, the mutable one accepts an assignment */
+template <class T> struct Map<const Quaternion<T>> : Quaternion<T> {
+    explicit Map(const T *p) : Quaternion<T>(p[3], p[0], p[1], p[2]) {}
+};
+template <class T> struct Map<Quaternion<T>> {
+    T *p;
+    explicit Map(T *ptr) : p(ptr) {}
+    const Map &operator=(const Quaternion<T> &q) const {
+        p[0] = q.x(), p[1] = q.y(), p[2] = q.z(), p[3] = q.w();
+        return *this;
+    }
+};
 
 /* ---- A.colPivHouseholderQr().solve(b) for a tall fixed-size A: Householder reflections with column pivoting on the
  * largest remaining column norm, then back substitution through the permutation (least squares). Written here from the

@@ -15,6 +15,7 @@ Contents (inputs + reference outputs), all seeded:
   pl_*       planeEstimation on 400 five-point sets (planes, noisy planes, scatter, near-collinear)
   prj_*      pointCloudProjection of 2,000 points
   mech_*     MISC::insMechanization over 200 IMU epochs (iswithearth = false)
+  pm_*       PoseManifold::Plus / Minus and their Jacobians (pose_manifold.cc:35-83) on 64 poses and increments
 
 and tests/golden/ffref_lidar_map.npz: the reference's own lidar::LidarMap (lidar_map.cc + the vendored ikd-Tree) driven
 over 3 keyframes x 2 frames of the `robot` sequence (2,000 points per frame): per frame the undistorted cloud and pose,
@@ -152,6 +153,16 @@ def main():
         st, tm = R.ins_mechanization(g, imu[i - 1], imu[i], st, tm)
         states[i] = st
     out.update(mech_gravity=g, mech_imu=imu, mech_states=states)
+
+    # ---- PoseManifold::Plus / Minus (pose_manifold.cc:35-83)
+    pm_x = np.array([rand_pose7(rng) for _ in range(64)])
+    pm_d = rng.normal(size=(64, 6)) * np.array([1, 1, 1, 0.3, 0.3, 0.3])
+    pm_d[:8, 3:] *= 1e-6        # small rotations
+    pm_d[8, 3:] = 0.0           # none: AngleAxis of a zero vector
+    pm_plus = np.array([R.pose_plus(a, b) for a, b in zip(pm_x, pm_d)])
+    pm_minus = np.array([R.pose_minus(a, b) for a, b in zip(pm_plus, pm_x)])
+    jp, jm = R.pose_jacobians(pm_x[0])
+    out.update(pm_x=pm_x, pm_delta=pm_d, pm_plus=pm_plus, pm_minus=pm_minus, pm_plus_jacobian=jp, pm_minus_jacobian=jm)
 
     path = os.path.join(HERE, "ffref_reference_sources.npz")
     np.savez_compressed(path, **out)
