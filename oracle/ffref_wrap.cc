@@ -10,6 +10,7 @@
 #include "common/misc.h"
 #include "common/rotation.h"
 #include "factors/lidar_factor.h"
+#include "factors/marginalization_info.h"
 #include "factors/pose_manifold.h"
 #include "factors/residual_block_info.h"
 #include "lidar/pointcloud.h"
@@ -160,6 +161,61 @@ void ffref_residual_block_evaluate(const float *point_xyz, const double *n, doub
         const auto &J = info.jacobians()[b];
         for (int j = 0; j < J.cols(); j++) J22[o++] = J(0, j);
     }
+}
+
+/* MarginalizationInfo (factors/marginalization_info.cc:26-260) over the LiDAR residual blocks of ONE (oldest reference,
+ * newest) pair, as Optimizer::marginalization (optimizer.cc:221-404) builds them for the LiDAR share: one
+ * ResidualBlockInfo(LidarFactor, HuberLoss(delta), {pose_ref, pose_cur, ext, td}, marginalize {0}) per valid feature;
+ * marginalization() = evaluate, constructEquation (J^T J / -J^T e over local sizes), schurElimination, linearization.
+ * Outputs the prior on the remaining blocks in the fixed order [pose_cur 6 | ext 6 | td 1] (the reference's own order
+ * follows an unordered_map): J0 (13 x 13, row-major, columns permuted to that order) and e0 (13). Returns 0 when the
+ * reference reports the marginalization as invalid. */
+int ffref_marginalize_lidar_pair(int n, const float *point_xyz, const double *normal, const double *d, double std,
+                                 const double *motion, const double *pose_ref, const double *pose_cur, const double *ext,
+                                 double td, double huber_delta, double *J0, double *e0) {
+    double blocks[4][7];
+    std::memcpy(blocks[0], pose_ref, 7 * sizeof(double));
+    std::memcpy(blocks[1], pose_cur, 7 * sizeof(double));
+    std::memcpy(blocks[2], ext, 7 * sizeof(double));
+    blocks[3][0] = td;
+    std::unordered_map<long, long> ids;
+    std::unordered_map<long, double *> address;
+    for (long i = 0; i < 4; i++) {
+        ids[reinterpret_cast<long>(blocks[i])] = i;
+        address[i]                            = blocks[i];
+    }
+    auto info = std::make_shared<MarginalizationInfo>();
+    info->updateParamtersIds(ids);
+    std::shared_ptr<ceres::LossFunction> loss;
+    if (huber_delta > 0) loss = std::make_shared<ceres::HuberLoss>(huber_delta);
+    for (int k = 0; k < n; k++) {
+        PointType p;
+        p.x = point_xyz[3 * k], p.y = point_xyz[3 * k + 1], p.z = point_xyz[3 * k + 2];
+        auto factor = std::make_shared<LidarFactor>(
+            p, Vector3d(normal[3 * k], normal[3 * k + 1], normal[3 * k + 2]), d[k], std, Vector3d(motion[0], motion[1], motion[2]),
+            Vector3d(motion[3], motion[4], motion[5]), motion[6], Vector3d(motion[7], motion[8], motion[9]),
+            Vector3d(motion[10], motion[11], motion[12]), motion[13]);
+        info->addResidualBlockInfo(std::make_shared<ResidualBlockInfo>(
+            factor, loss, std::vector<double *>{blocks[0], blocks[1], blocks[2], blocks[3]}, std::vector<int>{0}));
+    }
+    if (!info->marginalization()) return 0;
+    std::vector<double *> kept = info->getParamterBlocks(address);
+    const int m = info->marginalizedSize(), rdim = info->remainedSize();
+    if (m != 6 || rdim != 13 || kept.size() != 3) return 0;
+    int col_of[13]; /* reference column -> canonical column */
+    for (size_t i = 0; i < kept.size(); i++) {
+        const int at    = info->remainedBlockIndex()[i] - m;
+        const int local = MarginalizationInfo::localSize(info->remainedBlockSize()[i]);
+        const int base  = kept[i] == blocks[1] ? 0 : kept[i] == blocks[2] ? 6 : 12;
+        for (int j = 0; j < local; j++) col_of[at + j] = base + j;
+    }
+    const auto &J = info->linearizedJacobians();
+    const auto &e = info->linearizedResiduals();
+    for (int i = 0; i < 13; i++) {
+        e0[i] = e[i];
+        for (int j = 0; j < 13; j++) J0[13 * i + col_of[j]] = J(i, j);
+    }
+    return 1;
 }
 
 /* PoseManifold (factors/pose_manifold.cc:35-83): Plus, Minus and the two Jacobians (7 x 6 and 6 x 7, row-major) */

@@ -303,3 +303,18 @@ def pose_jacobians(x):
     lib().ffref_pose_jacobians.restype = None
     lib().ffref_pose_jacobians(_P(x), _P(jp), _P(jm))
     return jp, jm
+
+
+def marginalize_lidar_pair(point_xyz, normal, d, std, motion, pose_ref, pose_cur, ext, td, huber_delta=1.0):
+    """MarginalizationInfo (marginalization_info.cc) over the LidarFactor blocks of one (oldest reference, newest) pair with
+    the reference pose marginalized: the prior (J0 13 x 13, e0 13) on [pose_cur 6 | ext 6 | td 1]."""
+    L = lib()
+    L.ffref_marginalize_lidar_pair.argtypes = [C.c_int, fp, dp, dp, C.c_double, dp, dp, dp, dp, C.c_double, C.c_double, dp, dp]
+    pt, nn, dd, mo = _f(point_xyz).reshape(-1, 3), _d(normal), _d(d), _d(motion)
+    pr, pc, ex = _d(pose_ref), _d(pose_cur), _d(ext)
+    J0, e0 = np.zeros((13, 13)), np.zeros(13)
+    ok = L.ffref_marginalize_lidar_pair(len(pt), _F(pt), _P(nn), _P(dd), float(std), _P(mo), _P(pr), _P(pc), _P(ex), float(td),
+                                        float(huber_delta), _P(J0), _P(e0))
+    if not ok:
+        raise RuntimeError("the reference reports the marginalization as invalid")
+    return J0, e0

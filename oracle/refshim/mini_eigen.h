@@ -261,28 +261,77 @@ template <class T, int R, int C, int O> std::ostream &operator<<(std::ostream &o
     return os;
 }
 
-/* ---- run-time sized matrices (Eigen::Dynamic): the surface residual_block_info.cc uses - resize, data, squaredNorm,
- * scalar and matrix products, differences, transpose - evaluated eagerly in the order the C++ expression groups them ---- */
+/* ---- run-time sized matrices (Eigen::Dynamic): the surface residual_block_info.cc and marginalization_info.cc use -
+ * resize, Zero, blocks / segments / column ranges as views, sums, differences, products, transpose, the coefficient-wise
+ * array operations of the eigenvalue cut-off, asDiagonal and a symmetric eigen-solver - evaluated eagerly in the order the
+ * C++ expression groups them. The eigen-solver is a cyclic Jacobi iteration (Eigen tridiagonalises and runs QR sweeps):
+ * eigenvalues agree to rounding, eigenvectors up to sign / rotation inside degenerate subspaces, so what is compared
+ * downstream are the products that do not depend on that choice (J0^T J0, J0^T e0). ---- */
 enum { Dynamic = -1 };
+template <class T> struct DynView;
 template <class T, int Opt> struct DynBase {
     int r = 0, c = 0;
     std::vector<T> v;
     int rows() const { return r; }
     int cols() const { return c; }
+    int size() const { return r * c; }
     T *data() { return v.data(); }
     const T *data() const { return v.data(); }
     T &operator()(int i, int j) { return v[(Opt & RowMajor) ? i * c + j : j * r + i]; }
     const T &operator()(int i, int j) const { return v[(Opt & RowMajor) ? i * c + j : j * r + i]; }
     void resize(int rows, int cols) { r = rows, c = cols, v.assign((size_t) rows * cols, T(0)); }
+    void setZero() { std::fill(v.begin(), v.end(), T(0)); }
+    void setZero(int rows, int cols) { resize(rows, cols); }
     T squaredNorm() const {
         T s = T(0);
         for (size_t i = 0; i < v.size(); i++) s = i ? s + v[i] * v[i] : v[i] * v[i];
         return s;
     }
+    DynView<T> block(int i, int j, int nr, int nc) {
+        return DynView<T>{&(*this)(i, j), nr, nc, (Opt & RowMajor) ? c : 1, (Opt & RowMajor) ? 1 : r};
+    }
+    DynView<T> block(int i, int j, int nr, int nc) const { return const_cast<DynBase *>(this)->block(i, j, nr, nc); }
+    DynView<T> leftCols(int n) const { return block(0, 0, r, n); }
+    DynView<T> middleCols(int j, int n) const { return block(0, j, r, n); }
+    DynView<T> segment(int i, int n) const { return block(i, 0, n, 1); }
+};
+/* a window onto a DynBase (block, segment, leftCols): readable as a matrix, assignable, += / -= */
+template <class T> struct DynView {
+    T *p;
+    int r, c, rs, cs;
+    T &operator()(int i, int j) const { return p[i * rs + j * cs]; }
+    Matrix<T, Dynamic, Dynamic> eval() const;
+    Matrix<T, Dynamic, Dynamic> transpose() const;
+    template <int O> const DynView &operator=(const DynBase<T, O> &m) const {
+        for (int i = 0; i < r; i++)
+            for (int j = 0; j < c; j++) (*this)(i, j) = m(i, j);
+        return *this;
+    }
+    template <int O> const DynView &operator+=(const DynBase<T, O> &m) const {
+        for (int i = 0; i < r; i++)
+            for (int j = 0; j < c; j++) (*this)(i, j) = (*this)(i, j) + m(i, j);
+        return *this;
+    }
+    template <int O> const DynView &operator-=(const DynBase<T, O> &m) const {
+        for (int i = 0; i < r; i++)
+            for (int j = 0; j < c; j++) (*this)(i, j) = (*this)(i, j) - m(i, j);
+        return *this;
+    }
+};
+template <class T> struct ArrayX;
+template <class T> struct DiagX {
+    std::vector<T> d;
 };
 template <class T, int Opt> struct Matrix<T, Dynamic, Dynamic, Opt> : DynBase<T, Opt> {
     Matrix() {}
+    Matrix(int rows, int cols) { this->resize(rows, cols); }
     template <int O2> Matrix(const DynBase<T, O2> &o) { *this = o; }
+    Matrix(const DynView<T> &w) {
+        this->resize(w.r, w.c);
+        for (int i = 0; i < w.r; i++)
+            for (int j = 0; j < w.c; j++) (*this)(i, j) = w(i, j);
+    }
+    static Matrix Zero(int rows, int cols) { return Matrix(rows, cols); }
     template <int O2> Matrix &operator=(const DynBase<T, O2> &o) {
         this->resize(o.r, o.c);
         for (int i = 0; i < o.r; i++)
@@ -290,6 +339,11 @@ template <class T, int Opt> struct Matrix<T, Dynamic, Dynamic, Opt> : DynBase<T,
         return *this;
     }
     Matrix &operator*=(T s) { for (auto &x : this->v) x = x * s; return *this; }
+    template <int O2> Matrix &operator+=(const DynBase<T, O2> &o) {
+        for (int i = 0; i < o.r; i++)
+            for (int j = 0; j < o.c; j++) (*this)(i, j) = (*this)(i, j) + o(i, j);
+        return *this;
+    }
     Matrix<T, Dynamic, Dynamic> transpose() const {
         Matrix<T, Dynamic, Dynamic> t;
         t.resize(this->c, this->r);
@@ -300,22 +354,46 @@ template <class T, int Opt> struct Matrix<T, Dynamic, Dynamic, Opt> : DynBase<T,
 };
 template <class T, int Opt> struct Matrix<T, Dynamic, 1, Opt> : DynBase<T, ColMajor> {
     Matrix() {}
+    explicit Matrix(int n) { this->resize(n); }
     template <int O2> Matrix(const DynBase<T, O2> &o) { this->r = o.r, this->c = o.c, this->v = o.v; }
+    Matrix(const DynView<T> &w) {
+        this->resize(w.r);
+        for (int i = 0; i < w.r; i++) this->v[i] = w(i, 0);
+    }
+    explicit Matrix(const ArrayX<T> &a);
+    static Matrix Zero(int n) { return Matrix(n); }
     void resize(int n) { DynBase<T, ColMajor>::resize(n, 1); }
     void resize(int n, int m) { DynBase<T, ColMajor>::resize(n, m); }
+    void setZero() { DynBase<T, ColMajor>::setZero(); }
+    void setZero(int n) { resize(n); }
     int size() const { return this->r; }
     T &operator[](int i) { return this->v[i]; }
     const T &operator[](int i) const { return this->v[i]; }
     using DynBase<T, ColMajor>::operator();
     T &operator()(int i) { return this->v[i]; }
+    const T &operator()(int i) const { return this->v[i]; }
     Matrix &operator*=(T s) { for (auto &x : this->v) x = x * s; return *this; }
+    template <int O2> Matrix &operator+=(const DynBase<T, O2> &o) {
+        for (int i = 0; i < this->r; i++) this->v[i] = this->v[i] + o(i, 0);
+        return *this;
+    }
     Matrix<T, Dynamic, Dynamic> transpose() const {
         Matrix<T, Dynamic, Dynamic> t;
         t.resize(1, this->r);
         for (int i = 0; i < this->r; i++) t(0, i) = this->v[i];
         return t;
     }
+    ArrayX<T> array() const;
+    Matrix cwiseSqrt() const {
+        Matrix o(this->r);
+        for (int i = 0; i < this->r; i++) o[i] = std::sqrt(this->v[i]);
+        return o;
+    }
+    DiagX<T> asDiagonal() const { return DiagX<T>{this->v}; }
 };
+template <class T> Matrix<T, Dynamic, Dynamic> DynView<T>::eval() const { return Matrix<T, Dynamic, Dynamic>(*this); }
+template <class T> Matrix<T, Dynamic, Dynamic> DynView<T>::transpose() const { return eval().transpose(); }
+
 template <class T, int O1, int O2> Matrix<T, Dynamic, Dynamic> operator*(const DynBase<T, O1> &a, const DynBase<T, O2> &b) {
     Matrix<T, Dynamic, Dynamic> o;
     o.resize(a.r, b.c);
@@ -334,6 +412,7 @@ template <class T, int O> Matrix<T, Dynamic, Dynamic> operator*(T s, const DynBa
         for (int j = 0; j < a.c; j++) o(i, j) = s * a(i, j);
     return o;
 }
+template <class T, int O> Matrix<T, Dynamic, Dynamic> operator-(const DynBase<T, O> &a) { return T(-1) * a; }
 template <class T, int O1, int O2> Matrix<T, Dynamic, Dynamic> operator-(const DynBase<T, O1> &a, const DynBase<T, O2> &b) {
     Matrix<T, Dynamic, Dynamic> o;
     o.resize(a.r, a.c);
@@ -341,8 +420,107 @@ template <class T, int O1, int O2> Matrix<T, Dynamic, Dynamic> operator-(const D
         for (int j = 0; j < a.c; j++) o(i, j) = a(i, j) - b(i, j);
     return o;
 }
+template <class T, int O1, int O2> Matrix<T, Dynamic, Dynamic> operator+(const DynBase<T, O1> &a, const DynBase<T, O2> &b) {
+    Matrix<T, Dynamic, Dynamic> o;
+    o.resize(a.r, a.c);
+    for (int i = 0; i < a.r; i++)
+        for (int j = 0; j < a.c; j++) o(i, j) = a(i, j) + b(i, j);
+    return o;
+}
+template <class T, int O> Matrix<T, Dynamic, Dynamic> operator+(const DynView<T> &a, const DynBase<T, O> &b) { return a.eval() + b; }
+/* diag * M scales rows, M * diag scales columns */
+template <class T, int O> Matrix<T, Dynamic, Dynamic> operator*(const DiagX<T> &d, const DynBase<T, O> &a) {
+    Matrix<T, Dynamic, Dynamic> o;
+    o.resize(a.r, a.c);
+    for (int i = 0; i < a.r; i++)
+        for (int j = 0; j < a.c; j++) o(i, j) = d.d[i] * a(i, j);
+    return o;
+}
+template <class T, int O> Matrix<T, Dynamic, Dynamic> operator*(const DynBase<T, O> &a, const DiagX<T> &d) {
+    Matrix<T, Dynamic, Dynamic> o;
+    o.resize(a.r, a.c);
+    for (int i = 0; i < a.r; i++)
+        for (int j = 0; j < a.c; j++) o(i, j) = a(i, j) * d.d[j];
+    return o;
+}
+/* coefficient-wise arrays: (a > eps).select(b, 0), a.inverse() */
+template <class T> struct BoolX {
+    std::vector<char> m;
+    ArrayX<T> select(const ArrayX<T> &a, T other) const;
+};
+template <class T> struct ArrayX {
+    std::vector<T> a;
+    BoolX<T> operator>(T x) const {
+        BoolX<T> b;
+        for (T v : a) b.m.push_back(v > x);
+        return b;
+    }
+    ArrayX inverse() const {
+        ArrayX o;
+        for (T v : a) o.a.push_back(T(1) / v);
+        return o;
+    }
+};
+template <class T> ArrayX<T> BoolX<T>::select(const ArrayX<T> &a, T other) const {
+    ArrayX<T> o;
+    for (size_t i = 0; i < m.size(); i++) o.a.push_back(m[i] ? a.a[i] : other);
+    return o;
+}
+template <class T, int Opt> ArrayX<T> Matrix<T, Dynamic, 1, Opt>::array() const { return ArrayX<T>{this->v}; }
+template <class T, int Opt> Matrix<T, Dynamic, 1, Opt>::Matrix(const ArrayX<T> &a) {
+    this->r = (int) a.a.size(), this->c = 1, this->v = a.a;
+}
 typedef Matrix<double, Dynamic, 1> VectorXd;
 typedef Matrix<double, Dynamic, Dynamic> MatrixXd;
+
+/* symmetric eigen-decomposition, eigenvalues ascending (cyclic Jacobi rotations on the lower / upper symmetric part) */
+template <class M> class SelfAdjointEigenSolver {
+    MatrixXd vec_;
+    VectorXd val_;
+public:
+    template <int O> explicit SelfAdjointEigenSolver(const DynBase<double, O> &A) {
+        const int n = A.r;
+        MatrixXd a(n, n), V(n, n);
+        for (int i = 0; i < n; i++)
+            for (int j = 0; j < n; j++) a(i, j) = 0.5 * (A(i, j) + A(j, i)), V(i, j) = i == j ? 1.0 : 0.0;
+        for (int sweep = 0; sweep < 100; sweep++) {
+            double off = 0.0, diag = 0.0;
+            for (int i = 0; i < n; i++)
+                for (int j = 0; j < n; j++) (i == j ? diag : off) += a(i, j) * a(i, j);
+            if (off <= 1e-30 * diag || off == 0.0) break;
+            for (int p = 0; p < n - 1; p++)
+                for (int q = p + 1; q < n; q++) {
+                    if (a(p, q) == 0.0) continue;
+                    const double theta = (a(q, q) - a(p, p)) / (2.0 * a(p, q));
+                    const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+                    const double cs = 1.0 / std::sqrt(t * t + 1.0), sn = t * cs;
+                    for (int k = 0; k < n; k++) {
+                        const double akp = a(k, p), akq = a(k, q);
+                        a(k, p) = cs * akp - sn * akq, a(k, q) = sn * akp + cs * akq;
+                    }
+                    for (int k = 0; k < n; k++) {
+                        const double apk = a(p, k), aqk = a(q, k);
+                        a(p, k) = cs * apk - sn * aqk, a(q, k) = sn * apk + cs * aqk;
+                    }
+                    for (int k = 0; k < n; k++) {
+                        const double vkp = V(k, p), vkq = V(k, q);
+                        V(k, p) = cs * vkp - sn * vkq, V(k, q) = sn * vkp + cs * vkq;
+                    }
+                }
+        }
+        std::vector<int> order(n);
+        for (int i = 0; i < n; i++) order[i] = i;
+        std::sort(order.begin(), order.end(), [&](int x, int y) { return a(x, x) < a(y, y); });
+        val_.resize(n);
+        vec_.resize(n, n);
+        for (int k = 0; k < n; k++) {
+            val_[k] = a(order[k], order[k]);
+            for (int i = 0; i < n; i++) vec_(i, k) = V(i, order[k]);
+        }
+    }
+    const VectorXd &eigenvalues() const { return val_; }
+    const MatrixXd &eigenvectors() const { return vec_; }
+};
 
 typedef Matrix<double, 2, 1> Vector2d;
 typedef Matrix<double, 3, 1> Vector3d;

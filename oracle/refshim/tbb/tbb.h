@@ -3,6 +3,7 @@
 #ifndef FFLINS_ORACLE_REFSHIM_TBB_H
 #define FFLINS_ORACLE_REFSHIM_TBB_H
 #include <cstddef>
+#include <vector>
 namespace tbb {
 template <class T> class blocked_range {
     T b_, e_;
@@ -11,6 +12,12 @@ public:
     T begin() const { return b_; }
     T end() const { return e_; }
 };
+/* marginalization_info.cc:139-140 builds per-thread partial sums when there are more factors than threads; the stand-in
+ * reports "unlimited" concurrency so that the serial branch (the same accumulation, in factor order) is the one taken */
+namespace info {
+inline int default_concurrency() { return 1 << 30; }
+} // namespace info
+template <class T> using concurrent_vector = std::vector<T>;
 /* task_group::run executes the task at once (LidarMap uses it to allocate / release kd-trees off the critical path) */
 class task_group {
 public:

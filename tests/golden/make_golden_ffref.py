@@ -15,6 +15,9 @@ Contents (inputs + reference outputs), all seeded:
   pl_*       planeEstimation on 400 five-point sets (planes, noisy planes, scatter, near-collinear)
   prj_*      pointCloudProjection of 2,000 points
   mech_*     MISC::insMechanization over 200 IMU epochs (iswithearth = false)
+  mg_*       MarginalizationInfo::marginalization (marginalization_info.cc:43-260) over the 240 LidarFactor residual blocks
+             of one (oldest reference, newest) pair with HuberLoss(1.0), the reference pose marginalized: the prior J0, e0
+             on [pose_cur | ext | td] (eigenvectors come from the stand-in's Jacobi solver: compare J0^T J0 and J0^T e0)
   pm_*       PoseManifold::Plus / Minus and their Jacobians (pose_manifold.cc:35-83) on 64 poses and increments
 
 and tests/golden/ffref_lidar_map.npz: the reference's own lidar::LidarMap (lidar_map.cc + the vendored ikd-Tree) driven
@@ -163,6 +166,25 @@ def main():
     pm_minus = np.array([R.pose_minus(a, b) for a, b in zip(pm_plus, pm_x)])
     jp, jm = R.pose_jacobians(pm_x[0])
     out.update(pm_x=pm_x, pm_delta=pm_d, pm_plus=pm_plus, pm_minus=pm_minus, pm_plus_jacobian=jp, pm_minus_jacobian=jm)
+
+    # ---- MarginalizationInfo over the LidarFactor blocks of one (oldest reference, newest) pair (marginalization_info.cc)
+    m = 240
+    mg = dict(point=rng.uniform(-20, 20, (m, 3)).astype(np.float32), normal=rng.normal(size=(m, 3)), d=rng.uniform(-1, 1, m),
+              motion=rng.normal(size=14) * np.array([1, 1, 1, .3, .3, .3, .01] * 2), pose_ref=rand_pose7(rng), ext=rand_pose7(rng, 0.2),
+              td=0.004)
+    mg["normal"] /= np.linalg.norm(mg["normal"], axis=1, keepdims=True)
+    mg["pose_cur"] = mg["pose_ref"].copy()
+    mg["pose_cur"][:3] += rng.normal(size=3) * 0.3
+    q = mg["pose_ref"][3:] + rng.normal(size=4) * 0.02
+    mg["pose_cur"][3:] = q / np.linalg.norm(q)
+    for i in range(m):      # residuals of 0 .. 3 sigma around the planes: both branches of the loss
+        r, _ = R.lidar_factor_evaluate(mg["point"][i], mg["normal"][i], mg["d"][i], 0.1, mg["motion"], mg["pose_ref"],
+                                       mg["pose_cur"], mg["ext"], mg["td"], want_jac=None)
+        mg["d"][i] += 0.1 * (rng.normal() * 1.5 - r)
+    J0, e0 = R.marginalize_lidar_pair(mg["point"], mg["normal"], mg["d"], 0.1, mg["motion"], mg["pose_ref"], mg["pose_cur"],
+                                      mg["ext"], mg["td"], 1.0)
+    out.update({"mg_" + k: v for k, v in mg.items()})
+    out.update(mg_J0=J0, mg_e0=e0)
 
     path = os.path.join(HERE, "ffref_reference_sources.npz")
     np.savez_compressed(path, **out)
