@@ -25,7 +25,7 @@ EXPORTS = [
     "fflins_features_download", "fflins_features_set_outlier", "fflins_factor_eval_batch", "fflins_factor_eval",
     "fflins_window_eval", "fflins_window_chi2", "fflins_profile_enable", "fflins_profile_reset", "fflins_profile_get",
     "fflins_launch_count", "fflins_timer_start", "fflins_timer_stop", "fflins_reproject_window",
-    "fflins_eval_stats_get", "fflins_measure_fp64", "fflins_host_buffer_done", "fflins_solve_options_default",
+    "fflins_eval_stats_get", "fflins_measure_fp64", "fflins_host_buffer_done", "fflins_host_prefetch", "fflins_solve_options_default",
     "fflins_window_solve",
 ]
 
@@ -177,6 +177,11 @@ class Context:
                                                  _p(ins_q), len(ins_t), C.byref(pose), C.c_double(stamp),
                                                  C.c_double(td), C.byref(info) if sync else None))
         return info
+
+    def host_prefetch(self, rec):
+        """Announce a raw frame (32-byte records, page-locked) ahead of frame_process_aos: its copy starts now."""
+        assert rec.dtype.itemsize == 32 and rec.flags["C_CONTIGUOUS"]
+        self._ck(self.L.fflins_host_prefetch(self.h, _p(rec), len(rec)))
 
     def frame_process_dev(self, fid, d_xyzi, d_time, n, ins_t, ins_p, ins_q, pose_bl, stamp, td, sync=True):
         """d_xyzi / d_time are raw device addresses (ints); the INS window arrays are host numpy arrays.

@@ -117,6 +117,13 @@ int         fflins_host_unregister(void *ptr);
 /* Returns once no queued or in-flight host-to-device copy of this context still reads the caller's point buffer `ptr`
  * (asynchronous frames): after it the buffer may be freed, overwritten or un-registered. Cheap when the copy is long done. */
 int         fflins_host_buffer_done(fflins_ctx *ctx, const void *ptr);
+/* Announce a raw frame (n 32-byte PointXYZIT records in page-locked memory) before its fflins_frame_process_aos call: the
+ * host-to-device copy starts now, behind the copies already queued, and the later call with the same pointer and count
+ * finds the records on the device. The counterpart of LINS::addNewLidarFrame (ff_lins.cc): the sensor callback hands a
+ * frame over while the fusion thread is still solving the previous keyframe. One announcement at a time (a new one, or
+ * a frame that is never processed, drops the old one); pageable buffers are ignored. The buffer must stay valid and
+ * unchanged until the frame has been processed (fflins_host_buffer_done). */
+int         fflins_host_prefetch(fflins_ctx *ctx, const void *points32, int32_t n);
 
 /* ---- per frame: LidarMap::lidarFrameProcessing (lidar_map.cc:213-273) ------------------ */
 /* `out` may be NULL = ASYNCHRONOUS mode: the call only QUEUES the frame (INS window packed, frame pose

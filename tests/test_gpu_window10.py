@@ -528,3 +528,65 @@ def test_window10_remove_newest(window10, oracle):
     assert st.n_refs == 9 and planes > 500
     total, _ = _check_factors(c, oracle, seq, keys[:-1], 1, 81)
     assert total > 500
+
+
+# ---- fflins_host_prefetch: a raw frame announced ahead of its fflins_frame_process_aos call -------------------------------------
+def test_host_prefetch_is_transparent():
+    """An announced frame (its copy already on the copy stream) gives bit-identical clouds to a frame first seen by
+    fflins_frame_process_aos; announcements that are replaced, never consumed or overtaken by the staging ring are harmless."""
+    from fflins import api, synth
+    seq = synth.Sequence("robot")
+    c = api.Context(api.default_config(point_filter_num=seq.filter_num))
+    frames = [seq.frame(i) for i in range(6)]
+    recs = []
+    for fr in frames:
+        rec = np.ascontiguousarray(synth.pack_aos(fr["xyzi"], fr["time"])).copy()
+        api.host_register(rec)
+        recs.append(rec)
+
+    def process(fid, i, sync):
+        fr = frames[i]
+        return c.frame_process_aos(fid, recs[i], fr["ins_t"], fr["ins_p"], fr["ins_q"], seq.R_bl, seq.t_bl, fr["stamp"], fr["td"],
+                                   sync=sync)
+    want = [process(100 + i, i, True) for i in range(6)]
+    which_all = (api.CLOUD_LIDAR_FULL, api.CLOUD_LIDAR, api.CLOUD_WORLD, api.CLOUD_MAP_FULL)
+    # (1) announce, then process synchronously
+    c.host_prefetch(recs[0])
+    info = process(200, 0, True)
+    assert (info.n_down, info.n_dec) == (want[0].n_down, want[0].n_dec)
+    for which in which_all:
+        assert bits_equal(c.download(200, which), c.download(100, which))
+    # (2) the bench's pattern: the newest frame of an interval announced ahead, the interval queued asynchronously, merged
+    c.host_prefetch(recs[4])
+    for i in range(5):
+        process(300 + i, i, False)
+    a = c.keyframe_merge(304, [300, 301, 302, 303])
+    b = c.keyframe_merge(104, [100, 101, 102, 103])
+    assert a.n_map == b.n_map and a.n_down == want[4].n_down
+    for i in range(5):
+        for which in which_all[:3]:
+            assert bits_equal(c.download(300 + i, which), c.download(100 + i, which)), (i, which)
+    assert bits_equal(c.download(304, api.CLOUD_MAP), c.download(104, api.CLOUD_MAP))
+    # (3) an announcement replaced by another one, and one that is never consumed while the staging ring wraps over it
+    c.host_prefetch(recs[1])
+    c.host_prefetch(recs[2])
+    info = process(400, 1, True)          # not the announced buffer: copied as usual
+    for which in which_all:
+        assert bits_equal(c.download(400, which), c.download(101, which))
+    for k in range(20):                   # recs[2] stays announced; 20 more frames walk the ring past its slot
+        info = process(500 + k, k % 6, True)
+        assert info.n_down == want[k % 6].n_down
+        c.release(500 + k)
+    info = process(401, 2, True)          # the dropped announcement is simply copied again
+    for which in which_all:
+        assert bits_equal(c.download(401, which), c.download(102, which))
+    # (4) a changed point count under the same pointer is not taken for the announced frame
+    c.host_prefetch(recs[3])
+    fr = frames[3]
+    half = len(recs[3]) // 2
+    info = c.frame_process_aos(402, recs[3][:half], fr["ins_t"], fr["ins_p"], fr["ins_q"], seq.R_bl, seq.t_bl, fr["stamp"], fr["td"])
+    assert info.n_raw == half
+    c.synchronize()
+    for rec in recs:
+        api.host_unregister(rec)
+    c.close()

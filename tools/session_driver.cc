@@ -60,6 +60,9 @@ typedef struct drv_session {
     double prior_w[4];                     // weights of the diagonal prior: pose t, pose theta, td, (spare)
     std::vector<double> H0, b0, x0;
     fflins_solve_report report;
+    int prefetch;                          // 1: host-buffer mode announces the next interval's newest frame one interval ahead
+    const struct drv_frame *run_frames;    // the frame list, its length and the mode of the drv_run in progress
+    int run_n, run_mode;
     char err[256];
 } drv_session;
 
@@ -85,6 +88,9 @@ drv_session *drv_create(fflins_ctx *ctx, const fflins_pose *pose_bl, const doubl
     s->cost.resize(2 * 16);
     s->err[0] = 0;
     s->use_solve = 0;
+    s->prefetch = 0;
+    s->run_frames = nullptr;
+    s->run_n = s->run_mode = 0;
     s->prior_w[0] = 1.0 / (0.05 * 0.05);
     s->prior_w[1] = 1.0 / (0.01 * 0.01);
     s->prior_w[2] = 1.0 / (1e-3 * 1e-3);
@@ -93,6 +99,9 @@ drv_session *drv_create(fflins_ctx *ctx, const fflins_pose *pose_bl, const doubl
     return s;
 }
 void drv_set_solve(drv_session *s, int on) { s->use_solve = on; }
+// host-buffer mode: announce the newest frame of the NEXT keyframe interval (fflins_host_prefetch) as soon as the current
+// interval's copies are queued - what a sensor callback does that hands frames over while the fusion thread is solving
+void drv_set_prefetch(drv_session *s, int on) { s->prefetch = on; }
 int drv_last_solve(const drv_session *s, int32_t *iters2, int32_t *evals2) {
     iters2[0] = s->report.iterations[0];
     iters2[1] = s->report.iterations[1];
@@ -152,6 +161,10 @@ static int window_args(drv_session *s, uint64_t *ids, double *pose_refs, const d
 
 static int keyframe_work(drv_session *s, uint64_t fid, const drv_frame &fr) {
     DRV_CK(fflins_keyframe_merge(s->ctx, fid, s->nonkeys.data(), (int32_t) s->nonkeys.size(), nullptr));
+    if (s->prefetch && s->run_mode == 1 && s->run_frames) { // (the cursor already points behind this keyframe)
+        const drv_frame &nx = s->run_frames[(s->cursor + s->K - 1) % s->run_n];
+        DRV_CK(fflins_host_prefetch(s->ctx, nx.pts, nx.n));
+    }
     for (uint64_t nk : s->nonkeys) DRV_CK(fflins_frame_release(s->ctx, nk));
     s->nonkeys.clear();
     DRV_CK(fflins_keyframe_add(s->ctx, fid));
@@ -228,6 +241,9 @@ static int keyframe_work(drv_session *s, uint64_t fid, const drv_frame &fr) {
 // `steps` keyframe intervals (K frames each), cycling over the caller's frames. mode 0: points resident in device memory
 // (fflins_frame_process_dev), mode 1: raw 32-byte records in page-locked host memory (fflins_frame_process_aos).
 int drv_run(drv_session *s, int mode, const drv_frame *frames, int n_frames, int steps) {
+    s->run_frames = frames;
+    s->run_n      = n_frames;
+    s->run_mode   = mode;
     for (int st = 0; st < steps; st++) {
         for (int k = 0; k < s->K; k++) {
             const drv_frame &fr = frames[s->cursor % n_frames];
