@@ -440,7 +440,12 @@ def run_ours(args, rank, world, local_rank):
         nsess.set_prefetch(True)
         for _ in range(warm):
             step("host")
+        if os.environ.get("DRV_TRACE"):
+            nsess.L.drv_trace_dump(1)
         pf_dev_ms, pf_wall_ms, _, pf_rep_ms = timed("host", args.steps, repeats)
+        if os.environ.get("DRV_TRACE"):
+            print("--- host-buffer steps, next interval's newest frame announced ahead", file=sys.stderr)
+            nsess.L.drv_trace_dump(1)
         nsess.set_prefetch(False)
         step("host")        # (consumes the last announcement)
         if pf_dev_ms < e2e_dev_ms:
