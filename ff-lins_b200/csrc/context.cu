@@ -94,7 +94,8 @@ struct ProfRec {
 };
 
 constexpr int kWinRing   = 2 * kFrameBatch;  // pinned INS-window slots
-constexpr int kStageRing = kFrameBatch;      // device staging slots for host-resident points
+constexpr int kStageRing = 2 * kFrameBatch;  // device staging slots for host-resident points (a batch + the frames announced ahead)
+constexpr int kMaxAnnounced = kFrameBatch;   // raw frames announced ahead of their processing (fflins_host_prefetch)
 constexpr int kGuardRing = 8;
 constexpr unsigned long long kQueued = ~0ull;
 constexpr int kItemScratch = 32;             // ints per batch item: [0..3] counters, [16..31] voxel meta
@@ -208,12 +209,15 @@ struct fflins_ctx : public Profiler {
     cudaStream_t copy_stream = nullptr;
     cudaStream_t bg_stream = nullptr;   // kernels of the background frames of a split batch (the copy stream only copies)
     int stage_next = 0;
-    // a raw frame announced ahead of its fflins_frame_process_aos call (fflins_host_prefetch): its copy is already on the
-    // copy stream, in staging slot pf_slot (guard kQueued until the frame is queued or the announcement is dropped)
-    const void *pf_host = nullptr;
-    size_t pf_bytes = 0;
-    int pf_slot = -1;
-    char *pf_dev = nullptr;
+    // raw frames announced ahead of their fflins_frame_process_aos call (fflins_host_prefetch): their copies are already on
+    // the copy stream, in staging slot `slot` (guard kQueued until the frame is queued or the announcement is dropped)
+    struct Announced {
+        const void *host;
+        size_t bytes;
+        int slot;
+        char *dev;
+    };
+    std::vector<Announced> announced;
     cudaEvent_t ev_copied = nullptr;  // copy stream: the host-to-device copies the compute stream waits for are done
     cudaEvent_t ev_bg_done = nullptr; // background stream: the background part of the last split batch is done
     cudaEvent_t ev_bg_copied = nullptr; // copy stream: the copies of that part have arrived
@@ -548,7 +552,7 @@ int ensure_stage(fflins_ctx *ctx, size_t bytes) {
     }
     ctx->stage_cap = cap;
     for (auto &g : ctx->stage_guard) g = 0;
-    ctx->pf_host = nullptr, ctx->pf_slot = -1;   // (the ring moved: an announced frame is copied again when it is processed)
+    ctx->announced.clear();   // (the ring moved: an announced frame is copied again when it is processed)
     return FFLINS_OK;
 }
 
@@ -558,10 +562,12 @@ int stage_acquire(fflins_ctx *ctx, size_t bytes, char **ptr, int *slot) {
     int rc;
     if ((rc = ensure_stage(ctx, bytes))) return rc;
     const int k = ctx->stage_next;
-    if (ctx->pf_slot == k) { // the ring came round to an announced frame that was never processed: the announcement is dropped
-        ctx->stage_guard[k] = 0;   // (its copy is on the copy stream like every later writer of the slot: FIFO)
-        ctx->pf_host = nullptr, ctx->pf_slot = -1;
-    }
+    for (size_t a = 0; a < ctx->announced.size(); a++)
+        if (ctx->announced[a].slot == k) { // the ring came round to an announced frame that was never processed: dropped
+            ctx->stage_guard[k] = 0;       // (its copy is on the copy stream like every later writer of the slot: FIFO)
+            ctx->announced.erase(ctx->announced.begin() + a);
+            break;
+        }
     if (ctx->stage_guard[k] == kQueued && (rc = flush_frames(ctx))) return rc;
     ctx->stage_next = (k + 1) % kStageRing;
     // (copies are FIFO on the copy stream, so waiting here also covers a copy that is issued later, at flush time)
@@ -1011,12 +1017,15 @@ int enqueue_frame(fflins_ctx *ctx, uint64_t id, const float *xyzi, const double 
     } else { // host-resident points: every host-to-device copy goes to the copy stream
         size_t bytes = aos ? (size_t) n * 32 : (size_t) n * 24;
         char *pts;
-        if (aos && ctx->pf_slot >= 0 && ctx->pf_host == aos && ctx->pf_bytes == bytes) {
+        int ann = -1;
+        for (size_t a = 0; aos && a < ctx->announced.size(); a++)
+            if (ctx->announced[a].host == aos && ctx->announced[a].bytes == bytes) ann = (int) a;
+        if (ann >= 0) {
             // announced ahead (fflins_host_prefetch): the records are already in, or on their way into, a staging slot
-            q.stage_slot = ctx->pf_slot;
+            q.stage_slot = ctx->announced[ann].slot;
             q.n_copy     = 0;
-            it.aos       = ctx->pf_dev;
-            ctx->pf_host = nullptr, ctx->pf_slot = -1;
+            it.aos       = ctx->announced[ann].dev;
+            ctx->announced.erase(ctx->announced.begin() + ann);
         } else {
         if ((rc = stage_acquire(ctx, bytes + 256, &pts, &q.stage_slot))) return rc;
         if (aos) {
@@ -1603,19 +1612,22 @@ int fflins_host_prefetch(fflins_ctx *ctx, const void *points32, int32_t n) {
     for (const QueuedFrame &q : ctx->fq)
         for (int c = 0; c < q.n_copy; c++)
             if (q.h_src[c] == points32) return FFLINS_OK;   // already queued
-    if (ctx->pf_slot >= 0) { // one announcement at a time: the previous one is dropped (its copy stays harmless, FIFO)
-        ctx->stage_guard[ctx->pf_slot] = 0;
-        ctx->pf_host = nullptr, ctx->pf_slot = -1;
-    }
     const size_t bytes = (size_t) n * 32;
+    for (size_t a = 0; a < ctx->announced.size(); a++)
+        if (ctx->announced[a].host == points32) { // announced again (same buffer): the older announcement is dropped
+            ctx->stage_guard[ctx->announced[a].slot] = 0;
+            ctx->announced.erase(ctx->announced.begin() + a);
+            break;
+        }
+    if ((int) ctx->announced.size() >= kMaxAnnounced) { // at most half the staging ring is held by announcements
+        ctx->stage_guard[ctx->announced.front().slot] = 0;
+        ctx->announced.erase(ctx->announced.begin());
+    }
     char *pts;
     int slot, rc;
     if ((rc = stage_acquire(ctx, bytes + 256, &pts, &slot))) return rc;
     CK(cudaMemcpyAsync(pts, points32, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
-    ctx->pf_host  = points32;
-    ctx->pf_bytes = bytes;
-    ctx->pf_slot  = slot;
-    ctx->pf_dev   = pts;
+    ctx->announced.push_back({points32, bytes, slot, pts});
     return FFLINS_OK;
 }
 

@@ -120,8 +120,9 @@ int         fflins_host_buffer_done(fflins_ctx *ctx, const void *ptr);
 /* Announce a raw frame (n 32-byte PointXYZIT records in page-locked memory) before its fflins_frame_process_aos call: the
  * host-to-device copy starts now, behind the copies already queued, and the later call with the same pointer and count
  * finds the records on the device. The counterpart of LINS::addNewLidarFrame (ff_lins.cc): the sensor callback hands a
- * frame over while the fusion thread is still solving the previous keyframe. One announcement at a time (a new one, or
- * a frame that is never processed, drops the old one); pageable buffers are ignored. The buffer must stay valid and
+ * frame over while the fusion thread is still solving the previous keyframe. Up to 8 frames may be announced (beyond
+ * that, and for a buffer announced twice, the oldest announcement is dropped; one that is never processed is dropped when
+ * its staging slot is needed); pageable buffers are ignored. The buffer must stay valid and
  * unchanged until the frame has been processed (fflins_host_buffer_done). */
 int         fflins_host_prefetch(fflins_ctx *ctx, const void *points32, int32_t n);
 

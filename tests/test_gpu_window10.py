@@ -567,13 +567,29 @@ def test_host_prefetch_is_transparent():
         for which in which_all[:3]:
             assert bits_equal(c.download(300 + i, which), c.download(100 + i, which)), (i, which)
     assert bits_equal(c.download(304, api.CLOUD_MAP), c.download(104, api.CLOUD_MAP))
-    # (3) an announcement replaced by another one, and one that is never consumed while the staging ring wraps over it
+    # (2b) the whole next interval announced, newest first; processed oldest first
+    for i in (4, 3, 2, 1, 0):
+        c.host_prefetch(recs[i])
+    for i in range(5):
+        process(600 + i, i, False)
+    a = c.keyframe_merge(604, [600, 601, 602, 603])
+    assert a.n_map == b.n_map
+    for i in range(5):
+        for which in which_all[:3]:
+            assert bits_equal(c.download(600 + i, which), c.download(100 + i, which)), (i, which)
+    assert bits_equal(c.download(604, api.CLOUD_MAP), c.download(104, api.CLOUD_MAP))
+    # (3) a buffer announced twice, one announced but not the one processed next, and one that is never consumed while the
+    # staging ring wraps over it
+    c.host_prefetch(recs[1])
     c.host_prefetch(recs[1])
     c.host_prefetch(recs[2])
-    info = process(400, 1, True)          # not the announced buffer: copied as usual
+    info = process(400, 1, True)          # announced (twice): taken from its staging slot
     for which in which_all:
         assert bits_equal(c.download(400, which), c.download(101, which))
-    for k in range(20):                   # recs[2] stays announced; 20 more frames walk the ring past its slot
+    info = process(403, 3, True)          # never announced: copied as usual
+    for which in which_all:
+        assert bits_equal(c.download(403, which), c.download(103, which))
+    for k in range(40):                   # recs[2] stays announced; 40 more frames walk the ring past its slot
         info = process(500 + k, k % 6, True)
         assert info.n_down == want[k % 6].n_down
         c.release(500 + k)

@@ -60,7 +60,7 @@ typedef struct drv_session {
     double prior_w[4];                     // weights of the diagonal prior: pose t, pose theta, td, (spare)
     std::vector<double> H0, b0, x0;
     fflins_solve_report report;
-    int prefetch;                          // 1: host-buffer mode announces the next interval's newest frame one interval ahead
+    int prefetch;                          // host-buffer mode announces frames of the next interval one interval ahead (1: newest, 2: all)
     const struct drv_frame *run_frames;    // the frame list, its length and the mode of the drv_run in progress
     int run_n, run_mode;
     char err[256];
@@ -162,8 +162,13 @@ static int window_args(drv_session *s, uint64_t *ids, double *pose_refs, const d
 static int keyframe_work(drv_session *s, uint64_t fid, const drv_frame &fr) {
     DRV_CK(fflins_keyframe_merge(s->ctx, fid, s->nonkeys.data(), (int32_t) s->nonkeys.size(), nullptr));
     if (s->prefetch && s->run_mode == 1 && s->run_frames) { // (the cursor already points behind this keyframe)
-        const drv_frame &nx = s->run_frames[(s->cursor + s->K - 1) % s->run_n];
-        DRV_CK(fflins_host_prefetch(s->ctx, nx.pts, nx.n));
+        // prefetch = 1: the newest frame of the next interval (the one its association waits for); 2: all its frames,
+        // newest first
+        const int ahead = s->prefetch >= 2 ? s->K : 1;
+        for (int a = 0; a < ahead; a++) {
+            const drv_frame &nx = s->run_frames[(s->cursor + s->K - 1 - a) % s->run_n];
+            DRV_CK(fflins_host_prefetch(s->ctx, nx.pts, nx.n));
+        }
     }
     for (uint64_t nk : s->nonkeys) DRV_CK(fflins_frame_release(s->ctx, nk));
     s->nonkeys.clear();
