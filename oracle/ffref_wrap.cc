@@ -13,6 +13,8 @@
 #include "factors/marginalization_info.h"
 #include "factors/pose_manifold.h"
 #include "factors/residual_block_info.h"
+#include "preintegration/preintegration_factor.h"
+#include "preintegration/preintegration_normal.h"
 #include "lidar/pointcloud.h"
 
 #include <cstring>
@@ -216,6 +218,71 @@ int ffref_marginalize_lidar_pair(int n, const float *point_xyz, const double *no
         for (int j = 0; j < 13; j++) J0[13 * i + col_of[j]] = J(i, j);
     }
     return 1;
+}
+
+/* ---- IMU preintegration: PreintegrationNormal (preintegration/preintegration_base.cc, preintegration_normal.cc) driven
+ * through PreintegrationFactor::Evaluate (preintegration_factor.h:45-70), the cost function the optimizer adds per time node.
+ * imu = {time, dt, dtheta[3], dvel[3]}; state16 = {p, q xyzw, v, bg, ba}; noise = {acc_vrw, gyr_arw, gyr_bias_std,
+ * acc_bias_std, corr_time, gravity}. ---- */
+namespace {
+struct PreintProbe : PreintegrationNormal {
+    using PreintegrationNormal::PreintegrationNormal;
+    const Eigen::MatrixXd &cov() const { return covariance_; }
+    const Eigen::MatrixXd &jac() const { return jacobian_; }
+};
+IMU ld_imu(const double *a) {
+    IMU m;
+    m.time   = a[0];
+    m.dt     = a[1];
+    m.dtheta = Vector3d(a[2], a[3], a[4]);
+    m.dvel   = Vector3d(a[5], a[6], a[7]);
+    m.odovel = 0;
+    return m;
+}
+void st_state(const IntegrationState &st, double *o) {
+    for (int i = 0; i < 3; i++) o[i] = st.p[i], o[7 + i] = st.v[i], o[10 + i] = st.bg[i], o[13 + i] = st.ba[i];
+    o[3] = st.q.x(), o[4] = st.q.y(), o[5] = st.q.z(), o[6] = st.q.w();
+}
+} // namespace
+
+void *ffref_preint_create(const double *noise, const double *imu0, const double *state16, double time) {
+    auto par          = std::make_shared<IntegrationParameters>();
+    par->acc_vrw      = noise[0];
+    par->gyr_arw      = noise[1];
+    par->gyr_bias_std = noise[2];
+    par->acc_bias_std = noise[3];
+    par->corr_time    = noise[4];
+    par->gravity      = noise[5];
+    IntegrationState st;
+    st.time = time;
+    st.p    = Vector3d(state16[0], state16[1], state16[2]);
+    st.q    = Quaterniond(state16[6], state16[3], state16[4], state16[5]);
+    st.v    = Vector3d(state16[7], state16[8], state16[9]);
+    st.bg   = Vector3d(state16[10], state16[11], state16[12]);
+    st.ba   = Vector3d(state16[13], state16[14], state16[15]);
+    return new std::shared_ptr<PreintProbe>(std::make_shared<PreintProbe>(par, ld_imu(imu0), st));
+}
+void ffref_preint_destroy(void *h) { delete static_cast<std::shared_ptr<PreintProbe> *>(h); }
+void ffref_preint_add(void *h, const double *imu) { (*static_cast<std::shared_ptr<PreintProbe> *>(h))->addNewImu(ld_imu(imu)); }
+void ffref_preint_states(void *h, double *current16, double *delta16, double *delta_time) {
+    auto &p = *static_cast<std::shared_ptr<PreintProbe> *>(h);
+    st_state(p->currentState(), current16);
+    st_state(p->deltaState(), delta16);
+    *delta_time = p->deltaTime();
+}
+void ffref_preint_matrices(void *h, double *cov, double *jac) {
+    auto &p = *static_cast<std::shared_ptr<PreintProbe> *>(h);
+    for (int i = 0; i < 15; i++)
+        for (int j = 0; j < 15; j++) cov[15 * i + j] = p->cov()(i, j), jac[15 * i + j] = p->jac()(i, j);
+}
+/* residuals 15; Jacobians row-major 15 x 7, 15 x 9, 15 x 7, 15 x 9 (NULL: not requested) */
+void ffref_preint_evaluate(void *h, const double *pose0, const double *mix0, const double *pose1, const double *mix1,
+                           double *residuals, double *J0, double *J1, double *J2, double *J3) {
+    auto &p = *static_cast<std::shared_ptr<PreintProbe> *>(h);
+    PreintegrationFactor factor(p);
+    const double *parameters[4] = {pose0, mix0, pose1, mix1};
+    double *jacobians[4]        = {J0, J1, J2, J3};
+    factor.Evaluate(parameters, residuals, (J0 || J1 || J2 || J3) ? jacobians : nullptr);
 }
 
 /* PoseManifold (factors/pose_manifold.cc:35-83): Plus, Minus and the two Jacobians (7 x 6 and 6 x 7, row-major) */

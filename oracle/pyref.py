@@ -318,3 +318,52 @@ def marginalize_lidar_pair(point_xyz, normal, d, std, motion, pose_ref, pose_cur
     if not ok:
         raise RuntimeError("the reference reports the marginalization as invalid")
     return J0, e0
+
+
+class RefPreintegration:
+    """PreintegrationNormal of the reference (preintegration_base.cc, preintegration_normal.cc) through PreintegrationFactor.
+    imu = [time, dt, dtheta(3), dvel(3)]; state16 = [p, q xyzw, v, bg, ba]; noise = [acc_vrw, gyr_arw, gyr_bias_std,
+    acc_bias_std, corr_time, gravity]."""
+
+    def __init__(self, noise, imu0, state16, time):
+        L = self.L = lib()
+        L.ffref_preint_create.restype = C.c_void_p
+        L.ffref_preint_create.argtypes = [dp, dp, dp, C.c_double]
+        L.ffref_preint_destroy.argtypes = [C.c_void_p]
+        L.ffref_preint_add.argtypes = [C.c_void_p, dp]
+        L.ffref_preint_states.argtypes = [C.c_void_p, dp, dp, dp]
+        L.ffref_preint_matrices.argtypes = [C.c_void_p, dp, dp]
+        L.ffref_preint_evaluate.argtypes = [C.c_void_p, dp, dp, dp, dp, dp, dp, dp, dp, dp]
+        for name in ("ffref_preint_destroy", "ffref_preint_add", "ffref_preint_states", "ffref_preint_matrices", "ffref_preint_evaluate"):
+            getattr(L, name).restype = None
+        n, i0, s = _d(noise), _d(imu0), _d(state16)
+        self.h = L.ffref_preint_create(_P(n), _P(i0), _P(s), float(time))
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.ffref_preint_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def add(self, imu):
+        m = _d(imu)
+        self.L.ffref_preint_add(self.h, _P(m))
+
+    def states(self):
+        cur, dlt, dt = np.zeros(16), np.zeros(16), np.zeros(1)
+        self.L.ffref_preint_states(self.h, _P(cur), _P(dlt), _P(dt))
+        return cur, dlt, float(dt[0])
+
+    def matrices(self):
+        cov, jac = np.zeros((15, 15)), np.zeros((15, 15))
+        self.L.ffref_preint_matrices(self.h, _P(cov), _P(jac))
+        return cov, jac
+
+    def evaluate(self, pose0, mix0, pose1, mix1):
+        a = [_d(x) for x in (pose0, mix0, pose1, mix1)]
+        r = np.zeros(15)
+        J = [np.zeros((15, 7)), np.zeros((15, 9)), np.zeros((15, 7)), np.zeros((15, 9))]
+        self.L.ffref_preint_evaluate(self.h, _P(a[0]), _P(a[1]), _P(a[2]), _P(a[3]), _P(r), *[_P(j) for j in J])
+        return r, J

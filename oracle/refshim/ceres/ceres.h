@@ -17,6 +17,8 @@ public:
     const std::vector<int> &parameter_block_sizes() const { return sizes_; }
     int num_residuals() const { return num_residuals_; }
 protected:
+    std::vector<int> *mutable_parameter_block_sizes() { return &sizes_; }
+    void set_num_residuals(int n) { num_residuals_ = n; }
     std::vector<int> sizes_;
     int num_residuals_ = 0;
 };

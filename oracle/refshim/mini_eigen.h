@@ -33,6 +33,7 @@ template <class T> using aligned_allocator = std::allocator<T>;
 template <class T, int R, int C, int Opt = ColMajor> struct Matrix;
 template <class T> struct Quaternion;
 template <class T> struct AngleAxis;
+template <class M> struct Map;
 
 namespace mini {
 template <int R, int C, int Opt> constexpr int at(int r, int c) { return (Opt & RowMajor) ? r * C + c : c * R + r; }
@@ -67,6 +68,11 @@ template <class T, int BR, int BC> struct View {
     void setIdentity() const {
         for (int r = 0; r < BR; r++)
             for (int c = 0; c < BC; c++) (*this)(r, c) = r == c ? T(1) : T(0);
+    }
+    const View &operator*=(T s) const {
+        for (int r = 0; r < BR; r++)
+            for (int c = 0; c < BC; c++) (*this)(r, c) = (*this)(r, c) * s;
+        return *this;
     }
 };
 
@@ -192,6 +198,12 @@ template <class T, int R, int C, int Opt> struct Matrix : ScalarConv<Matrix<T, R
         return mini::View<T, BR, BC>{&(*this)(r, c), mini::at<R, C, Opt>(1, 0) - mini::at<R, C, Opt>(0, 0),
                                      (C > 1 ? mini::at<R, C, Opt>(0, 1) : 1) - mini::at<R, C, Opt>(0, 0)};
     }
+    template <int BR, int BC> Matrix<T, BR, BC> bottomRightCorner() const {
+        Matrix<T, BR, BC> o;
+        for (int r = 0; r < BR; r++)
+            for (int c = 0; c < BC; c++) o(r, c) = (*this)(R - BR + r, C - BC + c);
+        return o;
+    }
     mini::View<T, 1, C> row(int r) { return block<1, C>(r, 0); }
     mini::View<T, R, 1> col(int c) { return block<R, 1>(0, c); }
 
@@ -234,6 +246,10 @@ Matrix<T, R, C> operator*(T s, const Matrix<T, R, C, O> &a) {
     for (int r = 0; r < R; r++)
         for (int c = 0; c < C; c++) o(r, c) = s * a(r, c);
     return o;
+}
+template <class T, int R, int C, int O, class = typename std::enable_if<(R > 0 && C > 0) && !std::is_same<T, int>::value>::type>
+Matrix<T, R, C> operator*(int s, const Matrix<T, R, C, O> &a) {
+    return T(s) * a;
 }
 template <class T, int R, int C, int O, class = typename std::enable_if<(R > 0 && C > 0)>::type>
 Matrix<T, R, C> operator/(const Matrix<T, R, C, O> &a, T s) {
@@ -294,6 +310,15 @@ template <class T, int Opt> struct DynBase {
     DynView<T> leftCols(int n) const { return block(0, 0, r, n); }
     DynView<T> middleCols(int j, int n) const { return block(0, j, r, n); }
     DynView<T> segment(int i, int n) const { return block(i, 0, n, 1); }
+    template <int BR, int BC> mini::View<T, BR, BC> block(int i, int j) const {
+        DynBase *self = const_cast<DynBase *>(this);
+        return mini::View<T, BR, BC>{&(*self)(i, j), (Opt & RowMajor) ? c : 1, (Opt & RowMajor) ? 1 : r};
+    }
+    void setIdentity(int rows, int cols) {
+        resize(rows, cols);
+        for (int i = 0; i < (rows < cols ? rows : cols); i++) (*this)(i, i) = T(1);
+    }
+    Matrix<T, Dynamic, Dynamic> inverse() const;   /* Gauss-Jordan with partial pivoting (Eigen: PartialPivLU) */
 };
 /* a window onto a DynBase (block, segment, leftCols): readable as a matrix, assignable, += / -= */
 template <class T> struct DynView {
@@ -303,6 +328,12 @@ template <class T> struct DynView {
     Matrix<T, Dynamic, Dynamic> eval() const;
     Matrix<T, Dynamic, Dynamic> transpose() const;
     template <int O> const DynView &operator=(const DynBase<T, O> &m) const {
+        for (int i = 0; i < r; i++)
+            for (int j = 0; j < c; j++) (*this)(i, j) = m(i, j);
+        return *this;
+    }
+    template <int R2, int C2, int O, class = typename std::enable_if<(R2 > 0 && C2 > 0)>::type>
+    const DynView &operator=(const Matrix<T, R2, C2, O> &m) const {
         for (int i = 0; i < r; i++)
             for (int j = 0; j < c; j++) (*this)(i, j) = m(i, j);
         return *this;
@@ -330,6 +361,12 @@ template <class T, int Opt> struct Matrix<T, Dynamic, Dynamic, Opt> : DynBase<T,
         this->resize(w.r, w.c);
         for (int i = 0; i < w.r; i++)
             for (int j = 0; j < w.c; j++) (*this)(i, j) = w(i, j);
+    }
+    template <class M> Matrix(const Map<M> &mp) {
+        auto f = mp.eval();
+        this->resize(f.rows(), f.cols());
+        for (int i = 0; i < f.rows(); i++)
+            for (int j = 0; j < f.cols(); j++) (*this)(i, j) = f(i, j);
     }
     static Matrix Zero(int rows, int cols) { return Matrix(rows, cols); }
     template <int O2> Matrix &operator=(const DynBase<T, O2> &o) {
@@ -470,8 +507,51 @@ template <class T, int Opt> ArrayX<T> Matrix<T, Dynamic, 1, Opt>::array() const 
 template <class T, int Opt> Matrix<T, Dynamic, 1, Opt>::Matrix(const ArrayX<T> &a) {
     this->r = (int) a.a.size(), this->c = 1, this->v = a.a;
 }
+template <class T, int Opt> Matrix<T, Dynamic, Dynamic> DynBase<T, Opt>::inverse() const {
+    const int n = r;
+    Matrix<T, Dynamic, Dynamic> a(n, n), inv(n, n);
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++) a(i, j) = (*this)(i, j), inv(i, j) = i == j ? T(1) : T(0);
+    for (int k = 0; k < n; k++) {
+        int piv = k;
+        for (int i = k + 1; i < n; i++)
+            if (std::fabs(a(i, k)) > std::fabs(a(piv, k))) piv = i;
+        if (piv != k)
+            for (int j = 0; j < n; j++) std::swap(a(k, j), a(piv, j)), std::swap(inv(k, j), inv(piv, j));
+        const T d = a(k, k);
+        for (int j = 0; j < n; j++) a(k, j) = a(k, j) / d, inv(k, j) = inv(k, j) / d;
+        for (int i = 0; i < n; i++) {
+            if (i == k) continue;
+            const T f = a(i, k);
+            if (f == T(0)) continue;
+            for (int j = 0; j < n; j++) a(i, j) = a(i, j) - f * a(k, j), inv(i, j) = inv(i, j) - f * inv(k, j);
+        }
+    }
+    return inv;
+}
 typedef Matrix<double, Dynamic, 1> VectorXd;
 typedef Matrix<double, Dynamic, Dynamic> MatrixXd;
+
+/* Cholesky factor A = L L^T (lower), of the symmetric part of the argument */
+template <class M> class LLT {
+    MatrixXd L_;
+public:
+    template <int O> explicit LLT(const DynBase<double, O> &A) {
+        const int n = A.r;
+        L_.resize(n, n);
+        for (int j = 0; j < n; j++) {
+            double s = 0.5 * (A(j, j) + A(j, j));
+            for (int k = 0; k < j; k++) s -= L_(j, k) * L_(j, k);
+            L_(j, j) = std::sqrt(s);
+            for (int i = j + 1; i < n; i++) {
+                double t = 0.5 * (A(i, j) + A(j, i));
+                for (int k = 0; k < j; k++) t -= L_(i, k) * L_(j, k);
+                L_(i, j) = t / L_(j, j);
+            }
+        }
+    }
+    const MatrixXd &matrixL() const { return L_; }
+};
 
 /* symmetric eigen-decomposition, eigenvalues ascending (cyclic Jacobi rotations on the lower / upper symmetric part) */
 template <class M> class SelfAdjointEigenSolver {
@@ -562,6 +642,17 @@ template <class T, int R, int C, int Opt> struct Map<Matrix<T, R, C, Opt>> {
         return mini::View<T, BR, BC>{&(*this)(r, c), mini::at<R, C, Opt>(1, 0) - mini::at<R, C, Opt>(0, 0),
                                      (C > 1 ? mini::at<R, C, Opt>(0, 1) : 1) - mini::at<R, C, Opt>(0, 0)};
     }
+    DynView<T> block(int i, int j, int nr, int nc) const {
+        return DynView<T>{&(*this)(i, j), nr, nc, mini::at<R, C, Opt>(1, 0) - mini::at<R, C, Opt>(0, 0),
+                          (C > 1 ? mini::at<R, C, Opt>(0, 1) : 1) - mini::at<R, C, Opt>(0, 0)};
+    }
+    template <int O> const Map &operator=(const DynBase<T, O> &m) const {
+        for (int r = 0; r < R; r++)
+            for (int c = 0; c < C; c++) (*this)(r, c) = m(r, c);
+        return *this;
+    }
+    int rows() const { return R; }
+    int cols() const { return C; }
     template <int N> mini::View<T, N, C> topRows() const { return block<N, C>(0, 0); }
     template <int N> mini::View<T, N, C> bottomRows() const { return block<N, C>(R - N, 0); }
     template <int N> mini::View<T, R, N> leftCols() const { return block<R, N>(0, 0); }
@@ -589,6 +680,10 @@ template <class M1, class M2> typename Map<M1>::Plain operator-(const Map<M1> &a
 }
 template <class M1, class M2> typename Map<M1>::Plain operator+(const Map<M1> &a, const Map<M2> &b) {
     return a.eval() + b.eval();
+}
+
+template <class T, int O, class M> Matrix<T, Dynamic, Dynamic> operator*(const DynBase<T, O> &a, const Map<M> &b) {
+    return a * Matrix<T, Dynamic, Dynamic>(b);
 }
 
 /* ---- AngleAxis / Quaternion: Eigen 3.4 Geometry module formulas (generic, non-vectorised paths) ---- */
@@ -619,63 +714,61 @@ template <class T> struct AngleAxis {
 };
 
 template <class T> struct Quaternion {
-    T c[4]; /* x, y, z, w as Eigen stores them */
-    Quaternion() { c[0] = c[1] = c[2] = c[3] = T(0); }
-    Quaternion(T w, T x, T y, T z) { c[0] = x, c[1] = y, c[2] = z, c[3] = w; }
+    Matrix<T, 4, 1> cf; /* x, y, z, w as Eigen stores them */
+    Quaternion() { cf.m[0] = cf.m[1] = cf.m[2] = cf.m[3] = T(0); }
+    Quaternion(T w, T x, T y, T z) { cf.m[0] = x, cf.m[1] = y, cf.m[2] = z, cf.m[3] = w; }
     /* from angle-axis: w = cos(a/2), vec = sin(a/2) * axis */
     explicit Quaternion(const AngleAxis<T> &aa) {
         T ha = T(0.5) * aa.angle();
-        c[3] = std::cos(ha);
+        cf.m[3] = std::cos(ha);
         Matrix<T, 3, 1> v = std::sin(ha) * aa.axis();
-        c[0] = v[0], c[1] = v[1], c[2] = v[2];
+        cf.m[0] = v[0], cf.m[1] = v[1], cf.m[2] = v[2];
     }
     /* from a rotation matrix (quaternionbase_assign_impl<Other,3,3>, Shoemake's branches) */
     explicit Quaternion(const Matrix<T, 3, 3> &mat) {
         T t = mat(0, 0) + mat(1, 1) + mat(2, 2);
         if (t > T(0)) {
             t    = std::sqrt(t + T(1.0));
-            c[3] = T(0.5) * t;
+            cf.m[3] = T(0.5) * t;
             t    = T(0.5) / t;
-            c[0] = (mat(2, 1) - mat(1, 2)) * t;
-            c[1] = (mat(0, 2) - mat(2, 0)) * t;
-            c[2] = (mat(1, 0) - mat(0, 1)) * t;
+            cf.m[0] = (mat(2, 1) - mat(1, 2)) * t;
+            cf.m[1] = (mat(0, 2) - mat(2, 0)) * t;
+            cf.m[2] = (mat(1, 0) - mat(0, 1)) * t;
         } else {
             int i = 0;
             if (mat(1, 1) > mat(0, 0)) i = 1;
             if (mat(2, 2) > mat(i, i)) i = 2;
             int j = (i + 1) % 3, k = (j + 1) % 3;
             t    = std::sqrt(mat(i, i) - mat(j, j) - mat(k, k) + T(1.0));
-            c[i] = T(0.5) * t;
+            cf.m[i] = T(0.5) * t;
             t    = T(0.5) / t;
-            c[3] = (mat(k, j) - mat(j, k)) * t;
-            c[j] = (mat(j, i) + mat(i, j)) * t;
-            c[k] = (mat(k, i) + mat(i, k)) * t;
+            cf.m[3] = (mat(k, j) - mat(j, k)) * t;
+            cf.m[j] = (mat(j, i) + mat(i, j)) * t;
+            cf.m[k] = (mat(k, i) + mat(i, k)) * t;
         }
     }
-    T &w() { return c[3]; }
-    T &x() { return c[0]; }
-    T &y() { return c[1]; }
-    T &z() { return c[2]; }
-    const T &w() const { return c[3]; }
-    const T &x() const { return c[0]; }
-    const T &y() const { return c[1]; }
-    const T &z() const { return c[2]; }
-    Matrix<T, 3, 1> vec() const { return Matrix<T, 3, 1>(c[0], c[1], c[2]); }
-    Matrix<T, 4, 1> coeffs() const {
-        Matrix<T, 4, 1> v;
-        for (int i = 0; i < 4; i++) v[i] = c[i];
-        return v;
-    }
+    T &w() { return cf.m[3]; }
+    T &x() { return cf.m[0]; }
+    T &y() { return cf.m[1]; }
+    T &z() { return cf.m[2]; }
+    const T &w() const { return cf.m[3]; }
+    const T &x() const { return cf.m[0]; }
+    const T &y() const { return cf.m[1]; }
+    const T &z() const { return cf.m[2]; }
+    Matrix<T, 3, 1> vec() const { return Matrix<T, 3, 1>(cf.m[0], cf.m[1], cf.m[2]); }
+    Matrix<T, 4, 1> &coeffs() { return cf; }
+    const Matrix<T, 4, 1> &coeffs() const { return cf; }
+    void setIdentity() { cf.m[0] = cf.m[1] = cf.m[2] = T(0), cf.m[3] = T(1); }
     T squaredNorm() const { return coeffs().squaredNorm(); }
     T norm() const { return coeffs().norm(); }
     void normalize() {
         T n = norm(); /* coeffs().normalize() */
         T n2 = squaredNorm();
         if (n2 > T(0))
-            for (int i = 0; i < 4; i++) c[i] = c[i] / n;
+            for (int i = 0; i < 4; i++) cf.m[i] = cf.m[i] / n;
     }
     Quaternion normalized() const { Quaternion q = *this; q.normalize(); return q; }
-    Quaternion conjugate() const { return Quaternion(c[3], -c[0], -c[1], -c[2]); }
+    Quaternion conjugate() const { return Quaternion(cf.m[3], -cf.m[0], -cf.m[1], -cf.m[2]); }
     Quaternion operator*(const AngleAxis<T> &aa) const { return *this * Quaternion(aa); }
     Quaternion &operator*=(const Quaternion &o) { *this = *this * o; return *this; }
     /* QuaternionBase::inverse(): conjugate / squaredNorm when that is positive, else zero */
@@ -683,7 +776,7 @@ template <class T> struct Quaternion {
         T n2 = squaredNorm();
         if (n2 > T(0)) {
             Quaternion q = conjugate();
-            for (int i = 0; i < 4; i++) q.c[i] = q.c[i] / n2;
+            for (int i = 0; i < 4; i++) q.cf.m[i] = q.cf.m[i] / n2;
             return q;
         }
         return Quaternion();

@@ -18,6 +18,9 @@ Contents (inputs + reference outputs), all seeded:
   mg_*       MarginalizationInfo::marginalization (marginalization_info.cc:43-260) over the 240 LidarFactor residual blocks
              of one (oldest reference, newest) pair with HuberLoss(1.0), the reference pose marginalized: the prior J0, e0
              on [pose_cur | ext | td] (eigenvectors come from the stand-in's Jacobi solver: compare J0^T J0 and J0^T e0)
+  pre_*      PreintegrationNormal (preintegration_base.cc, preintegration_normal.cc) over 60 IMU epochs: integrated and
+             preintegrated states, covariance, bias Jacobian, and PreintegrationFactor::Evaluate (whitened residual and the
+             four Jacobian blocks) at a displaced pair of states
   pm_*       PoseManifold::Plus / Minus and their Jacobians (pose_manifold.cc:35-83) on 64 poses and increments
 
 and tests/golden/ffref_lidar_map.npz: the reference's own lidar::LidarMap (lidar_map.cc + the vendored ikd-Tree) driven
@@ -156,6 +159,31 @@ def main():
         st, tm = R.ins_mechanization(g, imu[i - 1], imu[i], st, tm)
         states[i] = st
     out.update(mech_gravity=g, mech_imu=imu, mech_states=states)
+
+    # ---- PreintegrationNormal through PreintegrationFactor::Evaluate (preintegration_base.cc, preintegration_normal.cc)
+    from fflins import host
+    G = host.GRAVITY
+    pseq = synth.Sequence("robot", n_points=100)
+    bg, ba = np.array([1e-4, -2e-4, 5e-5]), np.array([2e-3, 1e-3, -3e-3])
+    t, dt, dth, dv = pseq.imu_samples(200, 260, gravity=G, bg=bg, ba=ba)        # 0.3 s at 200 Hz
+    p0, q0, v0 = pseq.body_state(t[0] - synth.GPS_T0)
+    p1, q1, v1 = pseq.body_state(t[-1] - synth.GPS_T0)
+    nz = host.imu_noise(g=G)
+    noise = np.array([nz.acc_vrw, nz.gyr_arw, nz.gyr_bias_std, nz.acc_bias_std, nz.corr_time, nz.gravity])
+    imu = np.column_stack([t, dt, dth, dv])
+    state0 = np.concatenate([p0, q0, v0, bg, ba])
+    pre = R.RefPreintegration(noise, imu[0], state0, t[0])
+    for row in imu[1:]:
+        pre.add(row)
+    cur, dlt, dtime = pre.states()
+    cov, jac = pre.matrices()
+    pose0, mix0 = np.concatenate([p0, q0]), np.concatenate([v0, bg + rng.normal(0, 1e-4, 3), ba])
+    pose1, mix1 = np.concatenate([p1 + rng.normal(0, 0.01, 3), q1]), np.concatenate([v1 + rng.normal(0, 0.01, 3), bg, ba + rng.normal(0, 1e-3, 3)])
+    r, J = pre.evaluate(pose0, mix0, pose1, mix1)
+    out.update(pre_noise=noise, pre_imu=imu, pre_state0=state0, pre_current=cur, pre_delta=dlt, pre_delta_time=dtime, pre_cov=cov,
+               pre_jac=jac, pre_pose0=pose0, pre_mix0=mix0, pre_pose1=pose1, pre_mix1=mix1, pre_r=r, pre_J0=J[0], pre_J1=J[1],
+               pre_J2=J[2], pre_J3=J[3])
+    del pre
 
     # ---- PoseManifold::Plus / Minus (pose_manifold.cc:35-83)
     pm_x = np.array([rand_pose7(rng) for _ in range(64)])
