@@ -220,6 +220,65 @@ int ffref_marginalize_lidar_pair(int n, const float *point_xyz, const double *no
     return 1;
 }
 
+/* ---- the INS window as LINS keeps it (ff_lins.cc: insMechanization per IMU epoch, push_back) with the reference's own
+ * MISC::getImuSeriesFromTo (misc.cc:282-336) and MISC::redoInsMechanization (misc.cc:186-236), iswithearth = false.
+ * imu rows = {time, dt, dtheta[3], dvel[3]}; states = {p, q xyzw, v, bg, ba}. Outputs: the IMU series between two times
+ * (interpolated at both ends) and, after re-mechanizing from `updated` with `reserved` epochs kept, the window's epochs. ---- */
+int ffref_ins_window_scenario(const double *gravity, const double *imu, int n, const double *state16, double time0,
+                              double series_start, double series_end, double *series_out, int series_cap, int *series_ok,
+                              const double *updated16, double updated_time, int reserved, double *win_time, double *win_state16,
+                              int win_cap) {
+    IntegrationConfiguration cfg{};
+    cfg.iswithearth = false;
+    cfg.gravity     = Vector3d(gravity[0], gravity[1], gravity[2]);
+    auto ld_state   = [](const double *s, double t) {
+        IntegrationState st;
+        st.time = t;
+        st.p    = Vector3d(s[0], s[1], s[2]);
+        st.q    = Quaterniond(s[6], s[3], s[4], s[5]);
+        st.v    = Vector3d(s[7], s[8], s[9]);
+        st.bg   = Vector3d(s[10], s[11], s[12]);
+        st.ba   = Vector3d(s[13], s[14], s[15]);
+        return st;
+    };
+    auto ld = [](const double *a) {
+        IMU m;
+        m.time   = a[0];
+        m.dt     = a[1];
+        m.dtheta = Vector3d(a[2], a[3], a[4]);
+        m.dvel   = Vector3d(a[5], a[6], a[7]);
+        m.odovel = 0;
+        return m;
+    };
+    std::deque<std::pair<IMU, IntegrationState>> window;
+    IntegrationState st = ld_state(state16, time0);
+    window.emplace_back(ld(imu), st);
+    for (int k = 1; k < n; k++) {
+        MISC::insMechanization(cfg, ld(imu + 8 * (k - 1)), ld(imu + 8 * k), st);
+        window.emplace_back(ld(imu + 8 * k), st);
+    }
+    std::vector<IMU> series;
+    *series_ok = MISC::getImuSeriesFromTo(window, series_start, series_end, series) ? 1 : 0;
+    int ns     = 0;
+    for (const IMU &m : series) {
+        if (ns >= series_cap) break;
+        double *o = series_out + 8 * ns++;
+        o[0] = m.time, o[1] = m.dt;
+        for (int i = 0; i < 3; i++) o[2 + i] = m.dtheta[i], o[5 + i] = m.dvel[i];
+    }
+    MISC::redoInsMechanization(cfg, ld_state(updated16, updated_time), (size_t) reserved, window);
+    int nw = 0;
+    for (const auto &e : window) {
+        if (nw >= win_cap) break;
+        win_time[nw] = e.second.time;
+        double *o    = win_state16 + 16 * nw++;
+        for (int i = 0; i < 3; i++) o[i] = e.second.p[i], o[7 + i] = e.second.v[i], o[10 + i] = e.second.bg[i], o[13 + i] = e.second.ba[i];
+        o[3] = e.second.q.x(), o[4] = e.second.q.y(), o[5] = e.second.q.z(), o[6] = e.second.q.w();
+    }
+    (void) ns;
+    return (int) series.size() * 100000 + (int) window.size();   /* series count, window size */
+}
+
 /* ---- IMU preintegration: PreintegrationNormal (preintegration/preintegration_base.cc, preintegration_normal.cc) driven
  * through PreintegrationFactor::Evaluate (preintegration_factor.h:45-70), the cost function the optimizer adds per time node.
  * imu = {time, dt, dtheta[3], dvel[3]}; state16 = {p, q xyzw, v, bg, ba}; noise = {acc_vrw, gyr_arw, gyr_bias_std,

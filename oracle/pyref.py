@@ -367,3 +367,21 @@ class RefPreintegration:
         J = [np.zeros((15, 7)), np.zeros((15, 9)), np.zeros((15, 7)), np.zeros((15, 9))]
         self.L.ffref_preint_evaluate(self.h, _P(a[0]), _P(a[1]), _P(a[2]), _P(a[3]), _P(r), *[_P(j) for j in J])
         return r, J
+
+
+def ins_window_scenario(gravity, imu, state16, series_start, series_end, updated16, updated_time, reserved):
+    """An INS window built as LINS builds it (insMechanization per epoch), then MISC::getImuSeriesFromTo(start, end) and
+    MISC::redoInsMechanization(updated, reserved): returns (series_ok, series rows [time, dt, dtheta, dvel], window times,
+    window states16 after the redo)."""
+    L = lib()
+    L.ffref_ins_window_scenario.argtypes = [dp, dp, C.c_int, dp, C.c_double, C.c_double, C.c_double, dp, C.c_int,
+                                            C.POINTER(C.c_int), dp, C.c_double, C.c_int, dp, dp, C.c_int]
+    g, imu, s0, up = _d(gravity), _d(imu), _d(state16), _d(updated16)
+    n = len(imu)
+    series, ok = np.zeros((n + 4, 8)), C.c_int()
+    wt, ws = np.zeros(n + 4), np.zeros((n + 4, 16))
+    code = L.ffref_ins_window_scenario(_P(g), _P(imu), n, _P(s0), float(imu[0, 0]), float(series_start), float(series_end),
+                                       _P(series), n + 4, C.byref(ok), _P(up), float(updated_time), int(reserved), _P(wt), _P(ws),
+                                       n + 4)
+    ns, nw = code // 100000, code % 100000
+    return bool(ok.value), series[:ns], wt[:nw], ws[:nw]

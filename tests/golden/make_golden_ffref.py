@@ -21,6 +21,8 @@ Contents (inputs + reference outputs), all seeded:
   pre_*      PreintegrationNormal (preintegration_base.cc, preintegration_normal.cc) over 60 IMU epochs: integrated and
              preintegrated states, covariance, bias Jacobian, and PreintegrationFactor::Evaluate (whitened residual and the
              four Jacobian blocks) at a displaced pair of states
+  iw_*       an INS window of 401 epochs built by insMechanization, MISC::getImuSeriesFromTo between two off-epoch times and
+             MISC::redoInsMechanization from an updated state with 50 reserved epochs (misc.cc:186-336)
   pm_*       PoseManifold::Plus / Minus and their Jacobians (pose_manifold.cc:35-83) on 64 poses and increments
 
 and tests/golden/ffref_lidar_map.npz: the reference's own lidar::LidarMap (lidar_map.cc + the vendored ikd-Tree) driven
@@ -184,6 +186,20 @@ def main():
                pre_jac=jac, pre_pose0=pose0, pre_mix0=mix0, pre_pose1=pose1, pre_mix1=mix1, pre_r=r, pre_J0=J[0], pre_J1=J[1],
                pre_J2=J[2], pre_J3=J[3])
     del pre
+
+    # ---- the INS window: getImuSeriesFromTo (both ends between epochs) and redoInsMechanization (misc.cc:186-336)
+    t, dt, dth, dv = pseq.imu_samples(0, 400, gravity=G)
+    wimu = np.column_stack([t, dt, dth, dv])
+    p0, q0, v0 = pseq.body_state(t[0] - synth.GPS_T0)
+    ws0 = np.concatenate([p0, q0, v0, np.zeros(6)])
+    s_a, s_b = t[120] + 0.0013, t[180] + 0.0027
+    tu = t[300] + 0.002
+    pu, qu, vu = pseq.body_state(tu - synth.GPS_T0)
+    upd = np.concatenate([pu + 0.01, qu, vu - 0.02, [1e-4, 0, -1e-4], [1e-3, 2e-3, 0]])
+    ok, series, wt, wstates = R.ins_window_scenario([0, 0, G], wimu, ws0, s_a, s_b, upd, tu, 50)
+    assert ok and len(series) > 50 and len(wt) < len(wimu)
+    out.update(iw_gravity=G, iw_imu=wimu, iw_state0=ws0, iw_series_from=s_a, iw_series_to=s_b, iw_series=series, iw_updated=upd,
+               iw_updated_time=tu, iw_reserved=50, iw_times=wt, iw_states=wstates)
 
     # ---- PoseManifold::Plus / Minus (pose_manifold.cc:35-83)
     pm_x = np.array([rand_pose7(rng) for _ in range(64)])
