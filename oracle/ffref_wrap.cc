@@ -10,6 +10,7 @@
 #include "common/misc.h"
 #include "common/rotation.h"
 #include "factors/lidar_factor.h"
+#include "factors/marginalization_factor.h"
 #include "factors/marginalization_info.h"
 #include "factors/pose_manifold.h"
 #include "factors/residual_block_info.h"
@@ -174,7 +175,8 @@ void ffref_residual_block_evaluate(const float *point_xyz, const double *n, doub
  * reference reports the marginalization as invalid. */
 int ffref_marginalize_lidar_pair(int n, const float *point_xyz, const double *normal, const double *d, double std,
                                  const double *motion, const double *pose_ref, const double *pose_cur, const double *ext,
-                                 double td, double huber_delta, double *J0, double *e0) {
+                                 double td, double huber_delta, double *J0, double *e0, const double *eval_cur,
+                                 const double *eval_ext, double eval_td, double *eval_residuals, double *eval_jacobian) {
     double blocks[4][7];
     std::memcpy(blocks[0], pose_ref, 7 * sizeof(double));
     std::memcpy(blocks[1], pose_cur, 7 * sizeof(double));
@@ -216,6 +218,31 @@ int ffref_marginalize_lidar_pair(int n, const float *point_xyz, const double *no
     for (int i = 0; i < 13; i++) {
         e0[i] = e[i];
         for (int j = 0; j < 13; j++) J0[13 * i + col_of[j]] = J(i, j);
+    }
+    if (eval_cur) {
+        /* MarginalizationFactor::Evaluate (marginalization_factor.cc:37-91) of that prior at displaced parameter blocks:
+         * residuals e0 + J0 dx (13) and the Jacobian with respect to the TANGENT of [pose_cur | ext | td] (13 x 13,
+         * row-major: the leftCols(local) of every block, canonical column order) */
+        MarginalizationFactor prior(info);
+        double cur7[7], ext7[7], tdv[1] = {eval_td};
+        std::memcpy(cur7, eval_cur, sizeof(cur7));
+        std::memcpy(ext7, eval_ext, sizeof(ext7));
+        std::vector<const double *> params;
+        std::vector<std::vector<double>> jac(kept.size());
+        std::vector<double *> jp;
+        for (size_t i = 0; i < kept.size(); i++) {
+            params.push_back(kept[i] == blocks[1] ? cur7 : kept[i] == blocks[2] ? ext7 : tdv);
+            jac[i].assign((size_t) 13 * info->remainedBlockSize()[i], 0.0);
+            jp.push_back(jac[i].data());
+        }
+        prior.Evaluate(params.data(), eval_residuals, jp.data());
+        for (size_t i = 0; i < kept.size(); i++) {
+            const int size  = info->remainedBlockSize()[i];
+            const int local = MarginalizationInfo::localSize(size);
+            const int base  = kept[i] == blocks[1] ? 0 : kept[i] == blocks[2] ? 6 : 12;
+            for (int r = 0; r < 13; r++)
+                for (int j = 0; j < local; j++) eval_jacobian[13 * r + base + j] = jac[i][(size_t) r * size + j];
+        }
     }
     return 1;
 }

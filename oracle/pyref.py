@@ -305,19 +305,30 @@ def pose_jacobians(x):
     return jp, jm
 
 
-def marginalize_lidar_pair(point_xyz, normal, d, std, motion, pose_ref, pose_cur, ext, td, huber_delta=1.0):
+def marginalize_lidar_pair(point_xyz, normal, d, std, motion, pose_ref, pose_cur, ext, td, huber_delta=1.0, evaluate_at=None):
     """MarginalizationInfo (marginalization_info.cc) over the LidarFactor blocks of one (oldest reference, newest) pair with
-    the reference pose marginalized: the prior (J0 13 x 13, e0 13) on [pose_cur 6 | ext 6 | td 1]."""
+    the reference pose marginalized: the prior (J0 13 x 13, e0 13) on [pose_cur 6 | ext 6 | td 1]. evaluate_at = (pose_cur7,
+    ext7, td): additionally MarginalizationFactor::Evaluate (marginalization_factor.cc:37-91) of that prior there -> also
+    returns (residuals 13, tangent Jacobian 13 x 13)."""
     L = lib()
-    L.ffref_marginalize_lidar_pair.argtypes = [C.c_int, fp, dp, dp, C.c_double, dp, dp, dp, dp, C.c_double, C.c_double, dp, dp]
+    L.ffref_marginalize_lidar_pair.argtypes = [C.c_int, fp, dp, dp, C.c_double, dp, dp, dp, dp, C.c_double, C.c_double, dp, dp,
+                                               dp, dp, C.c_double, dp, dp]
     pt, nn, dd, mo = _f(point_xyz).reshape(-1, 3), _d(normal), _d(d), _d(motion)
     pr, pc, ex = _d(pose_ref), _d(pose_cur), _d(ext)
     J0, e0 = np.zeros((13, 13)), np.zeros(13)
+    if evaluate_at is None:
+        ok = L.ffref_marginalize_lidar_pair(len(pt), _F(pt), _P(nn), _P(dd), float(std), _P(mo), _P(pr), _P(pc), _P(ex), float(td),
+                                            float(huber_delta), _P(J0), _P(e0), None, None, 0.0, None, None)
+        if not ok:
+            raise RuntimeError("the reference reports the marginalization as invalid")
+        return J0, e0
+    ec, ee = _d(evaluate_at[0]), _d(evaluate_at[1])
+    res, jac = np.zeros(13), np.zeros((13, 13))
     ok = L.ffref_marginalize_lidar_pair(len(pt), _F(pt), _P(nn), _P(dd), float(std), _P(mo), _P(pr), _P(pc), _P(ex), float(td),
-                                        float(huber_delta), _P(J0), _P(e0))
+                                        float(huber_delta), _P(J0), _P(e0), _P(ec), _P(ee), float(evaluate_at[2]), _P(res), _P(jac))
     if not ok:
         raise RuntimeError("the reference reports the marginalization as invalid")
-    return J0, e0
+    return J0, e0, res, jac
 
 
 class RefPreintegration:

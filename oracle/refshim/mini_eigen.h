@@ -338,6 +338,11 @@ template <class T> struct DynView {
             for (int j = 0; j < c; j++) (*this)(i, j) = m(i, j);
         return *this;
     }
+    const DynView &operator=(const DynView &m) const {
+        for (int i = 0; i < r; i++)
+            for (int j = 0; j < c; j++) (*this)(i, j) = m(i, j);
+        return *this;
+    }
     template <int O> const DynView &operator+=(const DynBase<T, O> &m) const {
         for (int i = 0; i < r; i++)
             for (int j = 0; j < c; j++) (*this)(i, j) = (*this)(i, j) + m(i, j);
@@ -420,6 +425,13 @@ template <class T, int Opt> struct Matrix<T, Dynamic, 1, Opt> : DynBase<T, ColMa
         for (int i = 0; i < this->r; i++) t(0, i) = this->v[i];
         return t;
     }
+    template <int N> Matrix<T, N, 1> head() const {
+        Matrix<T, N, 1> o;
+        for (int i = 0; i < N; i++) o[i] = this->v[i];
+        return o;
+    }
+    template <int N> mini::View<T, N, 1> segment(int i) { return mini::View<T, N, 1>{&this->v[i], 1, 1}; }
+    using DynBase<T, ColMajor>::segment;
     ArrayX<T> array() const;
     Matrix cwiseSqrt() const {
         Matrix o(this->r);
@@ -822,6 +834,29 @@ typedef AngleAxis<double> AngleAxisd;
  * Quaternion, the mutable one accepts an assignment */
 template <class T> struct Map<const Quaternion<T>> : Quaternion<T> {
     explicit Map(const T *p) : Quaternion<T>(p[3], p[0], p[1], p[2]) {}
+};
+/* maps of run-time sized vectors / row-major matrices over caller memory (marginalization_factor.cc) */
+template <class T> struct Map<const Matrix<T, Dynamic, 1>> : Matrix<T, Dynamic, 1> {
+    Map(const T *p, int n) {
+        this->resize(n);
+        for (int i = 0; i < n; i++) this->v[i] = p[i];
+    }
+};
+template <class T> struct Map<Matrix<T, Dynamic, 1>> {
+    T *p;
+    int n;
+    Map(T *ptr, int size) : p(ptr), n(size) {}
+    template <int O> const Map &operator=(const DynBase<T, O> &m) const {
+        for (int i = 0; i < n; i++) p[i] = m(i, 0);
+        return *this;
+    }
+};
+template <class T> struct Map<Matrix<T, Dynamic, Dynamic, RowMajor>> {
+    T *p;
+    int r, c;
+    Map(T *ptr, int rows, int cols) : p(ptr), r(rows), c(cols) {}
+    void setZero() const { for (int i = 0; i < r * c; i++) p[i] = T(0); }
+    DynView<T> leftCols(int n) const { return DynView<T>{p, r, n, c, 1}; }
 };
 template <class T> struct Map<Quaternion<T>> {
     T *p;

@@ -23,6 +23,7 @@ Contents (inputs + reference outputs), all seeded:
              four Jacobian blocks) at a displaced pair of states
   iw_*       an INS window of 401 epochs built by insMechanization, MISC::getImuSeriesFromTo between two off-epoch times and
              MISC::redoInsMechanization from an updated state with 50 reserved epochs (misc.cc:186-336)
+  mgf_*      MarginalizationFactor::Evaluate (marginalization_factor.cc:37-91) of that prior at displaced parameter blocks
   pm_*       PoseManifold::Plus / Minus and their Jacobians (pose_manifold.cc:35-83) on 64 poses and increments
 
 and tests/golden/ffref_lidar_map.npz: the reference's own lidar::LidarMap (lidar_map.cc + the vendored ikd-Tree) driven
@@ -229,6 +230,16 @@ def main():
                                       mg["ext"], mg["td"], 1.0)
     out.update({"mg_" + k: v for k, v in mg.items()})
     out.update(mg_J0=J0, mg_e0=e0)
+    # MarginalizationFactor::Evaluate (marginalization_factor.cc:37-91) of that prior at displaced blocks; the extrinsic's
+    # quaternion is handed over with its sign flipped (dq.w() < 0 branch of the pose difference)
+    ecur = R.pose_plus(mg["pose_cur"], rng.normal(size=6) * np.array([.05, .05, .05, .02, .02, .02]))
+    eext = R.pose_plus(mg["ext"], rng.normal(size=6) * np.array([.01, .01, .01, .005, .005, .005]))
+    eext[3:] *= -1
+    etd = mg["td"] + 0.002
+    J0b, e0b, eres, ejac = R.marginalize_lidar_pair(mg["point"], mg["normal"], mg["d"], 0.1, mg["motion"], mg["pose_ref"],
+                                                    mg["pose_cur"], mg["ext"], mg["td"], 1.0, evaluate_at=(ecur, eext, etd))
+    assert np.array_equal(J0b, J0) and np.array_equal(e0b, e0)
+    out.update(mgf_pose_cur=ecur, mgf_ext=eext, mgf_td=etd, mgf_residuals=eres, mgf_jacobian=ejac)
 
     path = os.path.join(HERE, "ffref_reference_sources.npz")
     np.savez_compressed(path, **out)
