@@ -20,6 +20,8 @@
 
 #include <cstring>
 
+#include "lidar_converter.h"
+
 namespace {
 typedef std::deque<std::pair<IMU, IntegrationState>> InsWindow;
 
@@ -245,6 +247,57 @@ int ffref_marginalize_lidar_pair(int n, const float *point_xyz, const double *no
         }
     }
     return 1;
+}
+
+/* ---- ROS/lidar/lidar_converter.cc (LidarConverter): Livox CustomMsg and Velodyne / Ouster / Hesai PointCloud2 to the
+ * reference's PointXYZIT records. Messages are the stand-ins of oracle/refshim (decoded arrays instead of a byte blob).
+ * out32: 32-byte records {x, y, z, pad, intensity, pad, time}. kind: 2 Velodyne, 3 Ouster, 4 Hesai (lidar/lidar.h LidarType). */
+namespace {
+int store_cloud(const PointCloudCustomPtr &cloud, void *out32, int cap) {
+    int n = 0;
+    for (const auto &p : cloud->points) {
+        if (n >= cap) break;
+        char *o = static_cast<char *>(out32) + 32 * (size_t) n++;
+        std::memset(o, 0, 32);
+        std::memcpy(o, &p.x, 4), std::memcpy(o + 4, &p.y, 4), std::memcpy(o + 8, &p.z, 4);
+        std::memcpy(o + 16, &p.intensity, 4);
+        std::memcpy(o + 24, &p.time, 8);
+    }
+    return (int) cloud->size();
+}
+} // namespace
+int ffref_convert_livox(const void *pts19, int n, uint32_t sec, uint32_t nsec, int scan_line, double min_range, double max_range,
+                        int to_gps_time, void *out32, int cap, double *start, double *end) {
+    auto msg = std::make_shared<livox_ros_driver::CustomMsg>();
+    msg->header.stamp.sec = sec, msg->header.stamp.nsec = nsec;
+    msg->points.resize(n);
+    for (int k = 0; k < n; k++) {   /* packed rows: uint32 offset, 3 floats, 3 bytes */
+        const char *r = static_cast<const char *>(pts19) + 19 * (size_t) k;
+        auto &p       = msg->points[k];
+        std::memcpy(&p.offset_time, r, 4), std::memcpy(&p.x, r + 4, 4), std::memcpy(&p.y, r + 8, 4), std::memcpy(&p.z, r + 12, 4);
+        p.reflectivity = (uint8_t) r[16], p.tag = (uint8_t) r[17], p.line = (uint8_t) r[18];
+    }
+    LidarConverter conv(scan_line, min_range, max_range);
+    PointCloudCustomPtr cloud(new PointCloudCustom);
+    conv.livoxPointCloudConvertion(msg, cloud, *start, *end, to_gps_time != 0);
+    return store_cloud(cloud, out32, cap);
+}
+int ffref_convert_generic(int kind, const float *xyzi, const double *time, int n, uint32_t sec, uint32_t nsec, double min_range,
+                          double max_range, int to_gps_time, void *out32, int cap, double *start, double *end) {
+    auto msg = std::make_shared<sensor_msgs::PointCloud2>();
+    msg->header.stamp.sec = sec, msg->header.stamp.nsec = nsec;
+    for (int k = 0; k < n; k++) {
+        msg->x.push_back(xyzi[4 * k]), msg->y.push_back(xyzi[4 * k + 1]), msg->z.push_back(xyzi[4 * k + 2]);
+        msg->intensity.push_back(xyzi[4 * k + 3]);
+        msg->time.push_back(time[k]);
+    }
+    LidarConverter conv(128, min_range, max_range);
+    PointCloudCustomPtr cloud(new PointCloudCustom);
+    sensor_msgs::PointCloud2ConstPtr cmsg = msg;
+    if (kind == 2) conv.velodynePointCloudConvertion(cmsg, cloud, *start, *end, to_gps_time != 0);
+    else if (kind == 3) conv.ousterPointCloudConvertion(cmsg, cloud, *start, *end, to_gps_time != 0);
+    else conv.hesaiPointCloudConvertion(cmsg, cloud, *start, *end, to_gps_time != 0);
+    return store_cloud(cloud, out32, cap);
 }
 
 /* ---- the INS window as LINS keeps it (ff_lins.cc: insMechanization per IMU epoch, push_back) with the reference's own

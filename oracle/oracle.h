@@ -10,7 +10,7 @@
  * libraries (Eigen, PCL, Ceres, TBB, glog, yaml-cpp) are absent here. Pinned against the reference's OWN
  * SOURCE FILES compiled where they lie under /root/reference into oracle/_ref/ (oracle/Makefile `ref`):
  *   (1) kNN: the vendored ikd-Tree (libikd_ref.so), bit-identical neighbours and distances;
- *   (2) lidar_factor.cc, residual_block_info.cc, marginalization_info.cc, marginalization_factor.cc, pose_manifold.cc, preintegration_base.cc, preintegration_normal.cc, misc.cc, rotation.cc, pointcloud.cc and lidar_map.cc + ikd-Tree (libff_ref.so, built against
+ *   (2) lidar_factor.cc, residual_block_info.cc, marginalization_info.cc, marginalization_factor.cc, pose_manifold.cc, preintegration_base.cc, preintegration_normal.cc, lidar_converter.cc, misc.cc, rotation.cc, pointcloud.cc and lidar_map.cc + ikd-Tree (libff_ref.so, built against
  *       the stand-in headers of oracle/refshim/): the undistortion loop, frame poses, projections, merge, every
  *       output of LidarFactor::Evaluate and of the Huber corrector (ResidualBlockInfo::Evaluate), feature types, the five nearest points and the counters of
  *       updateLidarFeaturesInMap are bit-identical to this oracle; plane parameters agree to 1e-11 (the 5 x 3

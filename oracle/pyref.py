@@ -396,3 +396,38 @@ def ins_window_scenario(gravity, imu, state16, series_start, series_end, updated
                                        n + 4)
     ns, nw = code // 100000, code % 100000
     return bool(ok.value), series[:ns], wt[:nw], ws[:nw]
+
+
+REC32 = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("pad", "<f4"), ("intensity", "<f4"), ("pad2", "<f4"), ("time", "<f8")])
+LIVOX19 = np.dtype([("offset_time", "<u4"), ("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("reflectivity", "u1"), ("tag", "u1"),
+                    ("line", "u1")])
+
+
+def convert_livox(points19, sec, nsec, scan_line, min_range, max_range, to_gps_time=False):
+    """LidarConverter::livoxPointCloudConvertion (ROS/lidar/lidar_converter.cc:36-68) on a CustomMsg with stamp (sec, nsec)
+    and the packed points (LIVOX19 records). Returns (32-byte records, start, end)."""
+    L = lib()
+    L.ffref_convert_livox.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_double, C.c_double, C.c_int,
+                                      C.c_void_p, C.c_int, dp, dp]
+    pts = np.ascontiguousarray(points19, LIVOX19)
+    n = len(pts)
+    out = np.zeros(max(n, 1), REC32)
+    s, e = np.zeros(1), np.zeros(1)
+    m = L.ffref_convert_livox(pts.ctypes.data, n, int(sec), int(nsec), int(scan_line), float(min_range), float(max_range),
+                              int(to_gps_time), out.ctypes.data, n, _P(s), _P(e))
+    return out[:m].copy(), float(s[0]), float(e[0])
+
+
+def convert_generic(kind, xyzi, time, sec, nsec, min_range, max_range, to_gps_time=False):
+    """velodyne (kind 2) / ouster (3) / hesai (4) PointCloudConvertion (lidar_converter.cc:70-213); `time` is the sensor's
+    per-point time field in its own unit (s relative, ns relative, absolute s)."""
+    L = lib()
+    L.ffref_convert_generic.argtypes = [C.c_int, fp, dp, C.c_int, C.c_uint32, C.c_uint32, C.c_double, C.c_double, C.c_int,
+                                        C.c_void_p, C.c_int, dp, dp]
+    xyzi, time = _f(xyzi).reshape(-1, 4), _d(time)
+    n = len(xyzi)
+    out = np.zeros(max(n, 1), REC32)
+    s, e = np.zeros(1), np.zeros(1)
+    m = L.ffref_convert_generic(int(kind), _F(xyzi), _P(time), n, int(sec), int(nsec), float(min_range), float(max_range),
+                                int(to_gps_time), out.ctypes.data, n, _P(s), _P(e))
+    return out[:m].copy(), float(s[0]), float(e[0])

@@ -18,6 +18,8 @@ template <class P> struct PointCloud {
     void resize(size_t n) { points.resize(n); }
     void reserve(size_t n) { points.reserve(n); }
     bool empty() const { return points.empty(); }
+    void clear() { points.clear(); }
+    void push_back(const P &p) { points.push_back(p); }
     PointCloud &operator+=(const PointCloud &o) {
         points.insert(points.end(), o.points.begin(), o.points.end());
         return *this;

@@ -24,6 +24,8 @@ Contents (inputs + reference outputs), all seeded:
   iw_*       an INS window of 401 epochs built by insMechanization, MISC::getImuSeriesFromTo between two off-epoch times and
              MISC::redoInsMechanization from an updated state with 50 reserved epochs (misc.cc:186-336)
   mgf_*      MarginalizationFactor::Evaluate (marginalization_factor.cc:37-91) of that prior at displaced parameter blocks
+  cv_*       LidarConverter (ROS/lidar/lidar_converter.cc:36-232): a Livox CustomMsg (tag / line / range filters) and
+             Velodyne / Ouster / Hesai clouds with their three time conventions, with and without the GPS-time conversion
   pm_*       PoseManifold::Plus / Minus and their Jacobians (pose_manifold.cc:35-83) on 64 poses and increments
 
 and tests/golden/ffref_lidar_map.npz: the reference's own lidar::LidarMap (lidar_map.cc + the vendored ikd-Tree) driven
@@ -57,6 +59,7 @@ def main():
     rng = np.random.default_rng(20261020)
     out = {}
 
+    rng = np.random.default_rng(20261020 + 1)   # (one generator per section: adding a section leaves the others unchanged)
     # ---- undistortion loop
     seq = synth.Sequence("lili", n_points=1500, ins_entries=200)
     fr = seq.frame(7)
@@ -72,6 +75,7 @@ def main():
                und_stamp=float(fr["stamp"]), und_td=float(fr["td"]), und_out=und, und_pose_R=pR, und_pose_t=pt,
                und_fallbacks=fb, und_filter_num=seq.filter_num)
 
+    rng = np.random.default_rng(20261020 + 2)   # (one generator per section: adding a section leaves the others unchanged)
     # ---- pose / index queries
     it = np.asarray(fr["ins_t"], np.float64)
     times = np.concatenate([[it[0] - 1e-3, it[0], it[-1], it[-1] + 1e-3, np.nextafter(it[-1], 0), it[1], it[len(it) // 2]],
@@ -83,6 +87,7 @@ def main():
         pw_idx.append(R.ins_window_index(it, tm))
     out.update(pw_times=times, pw_ok=np.array(pw_ok), pw_R=np.array(pw_R), pw_t=np.array(pw_t), pw_index=np.array(pw_idx))
 
+    rng = np.random.default_rng(20261020 + 3)   # (one generator per section: adding a section leaves the others unchanged)
     # ---- LidarFactor::Evaluate
     n = 96
     fac = dict(point=rng.uniform(-30, 30, (n, 3)).astype(np.float32), normal=np.zeros((n, 3)), d=rng.uniform(-5, 5, n),
@@ -104,6 +109,7 @@ def main():
         fac["J"][i] = np.concatenate(J)
     out.update({"fac_" + k: v for k, v in fac.items()})
 
+    rng = np.random.default_rng(20261020 + 4)   # (one generator per section: adding a section leaves the others unchanged)
     # ---- ResidualBlockInfo::Evaluate with ceres::HuberLoss(1.0): the plane offsets are moved so that the residuals spread
     # over both branches of the loss (|r| = 0, 0.4, 3, 12 sigma)
     rb_d, rb_r, rb_J = fac["d"].copy(), np.zeros(n), np.zeros((n, 22))
@@ -115,6 +121,7 @@ def main():
     assert (np.abs(rb_r) > 1).sum() >= n // 3 and (np.abs(rb_r) < 1).sum() >= n // 3
     out.update(rb_d=rb_d, rb_r=rb_r, rb_J=rb_J)
 
+    rng = np.random.default_rng(20261020 + 5)   # (one generator per section: adding a section leaves the others unchanged)
     # ---- planeEstimation
     m = 400
     pts = np.zeros((m, 5, 4), np.float32)
@@ -140,12 +147,14 @@ def main():
     assert 0 < pl_ok.sum() < m
     out.update(pl_points=pts, pl_ok=pl_ok, pl_normal=pl_n, pl_norm_inverse=pl_ninv, pl_distance=pl_dist)
 
+    rng = np.random.default_rng(20261020 + 6)   # (one generator per section: adding a section leaves the others unchanged)
     # ---- pointCloudProjection
     src = rng.uniform(-80, 80, (2000, 4)).astype(np.float32)
     pose = rand_pose7(rng, 200.0)
     Rw, _ = R.state_to_pose(np.zeros(3), pose[3:], np.eye(3), np.zeros(3))
     out.update(prj_src=src, prj_R=Rw, prj_t=pose[:3], prj_dst=R.project(Rw, pose[:3], src), prj_q=pose[3:])
 
+    rng = np.random.default_rng(20261020 + 7)   # (one generator per section: adding a section leaves the others unchanged)
     # ---- insMechanization
     k = 200
     g = np.array([0.0, 0.0, -9.8])
@@ -163,6 +172,7 @@ def main():
         states[i] = st
     out.update(mech_gravity=g, mech_imu=imu, mech_states=states)
 
+    rng = np.random.default_rng(20261020 + 8)   # (one generator per section: adding a section leaves the others unchanged)
     # ---- PreintegrationNormal through PreintegrationFactor::Evaluate (preintegration_base.cc, preintegration_normal.cc)
     from fflins import host
     G = host.GRAVITY
@@ -188,6 +198,7 @@ def main():
                pre_J2=J[2], pre_J3=J[3])
     del pre
 
+    rng = np.random.default_rng(20261020 + 9)   # (one generator per section: adding a section leaves the others unchanged)
     # ---- the INS window: getImuSeriesFromTo (both ends between epochs) and redoInsMechanization (misc.cc:186-336)
     t, dt, dth, dv = pseq.imu_samples(0, 400, gravity=G)
     wimu = np.column_stack([t, dt, dth, dv])
@@ -202,6 +213,35 @@ def main():
     out.update(iw_gravity=G, iw_imu=wimu, iw_state0=ws0, iw_series_from=s_a, iw_series_to=s_b, iw_series=series, iw_updated=upd,
                iw_updated_time=tu, iw_reserved=50, iw_times=wt, iw_states=wstates)
 
+    rng = np.random.default_rng(20261020 + 10)   # (one generator per section: adding a section leaves the others unchanged)
+    # ---- LidarConverter (ROS/lidar/lidar_converter.cc): Livox CustomMsg and Velodyne / Ouster / Hesai clouds
+    n = 1500
+    lv = np.zeros(n, R.LIVOX19)
+    lv["offset_time"] = np.sort(rng.integers(0, 100_000_000, n))
+    xyz = rng.normal(size=(n, 3)) * [20, 20, 3]
+    xyz[::50] = 0.0                                     # invalid returns: inside the minimum range
+    lv["x"], lv["y"], lv["z"] = xyz[:, 0], xyz[:, 1], xyz[:, 2]
+    lv["reflectivity"] = rng.integers(0, 255, n)
+    lv["tag"] = rng.choice([0x00, 0x10, 0x20, 0x30, 0x05, 0x15], n)
+    lv["line"] = rng.integers(0, 8, n)
+    sec, nsec = 1_690_000_123, 456_789_012
+    out.update(cv_livox=lv, cv_sec=sec, cv_nsec=nsec)
+    for gps in (0, 1):
+        rec, s0, e0 = R.convert_livox(lv, sec, nsec, 6, 1.0, 100.0, bool(gps))
+        out.update({f"cv_livox_out{gps}": rec, f"cv_livox_span{gps}": np.array([s0, e0])})
+    gx = np.concatenate([rng.normal(size=(n, 3)) * [30, 30, 4], rng.uniform(0, 255, (n, 1))], 1).astype(np.float32)
+    gx[::40, :3] = 0.1
+    stamp = sec + 1e-9 * nsec
+    times = {2: np.sort(rng.uniform(0, 0.1, n)).astype(np.float32).astype(np.float64),
+             3: np.sort(rng.integers(0, 100_000_000, n)).astype(np.float64), 4: stamp + np.sort(rng.uniform(0, 0.1, n))}
+    out.update(cv_xyzi=gx)
+    for kind in (2, 3, 4):
+        out[f"cv_time{kind}"] = times[kind]
+        for gps in (0, 1):
+            rec, s0, e0 = R.convert_generic(kind, gx, times[kind], sec, nsec, 1.0, 100.0, bool(gps))
+            out.update({f"cv_kind{kind}_out{gps}": rec, f"cv_kind{kind}_span{gps}": np.array([s0, e0])})
+
+    rng = np.random.default_rng(20261020 + 11)   # (one generator per section: adding a section leaves the others unchanged)
     # ---- PoseManifold::Plus / Minus (pose_manifold.cc:35-83)
     pm_x = np.array([rand_pose7(rng) for _ in range(64)])
     pm_d = rng.normal(size=(64, 6)) * np.array([1, 1, 1, 0.3, 0.3, 0.3])
@@ -212,6 +252,7 @@ def main():
     jp, jm = R.pose_jacobians(pm_x[0])
     out.update(pm_x=pm_x, pm_delta=pm_d, pm_plus=pm_plus, pm_minus=pm_minus, pm_plus_jacobian=jp, pm_minus_jacobian=jm)
 
+    rng = np.random.default_rng(20261020 + 12)   # (one generator per section: adding a section leaves the others unchanged)
     # ---- MarginalizationInfo over the LidarFactor blocks of one (oldest reference, newest) pair (marginalization_info.cc)
     m = 240
     mg = dict(point=rng.uniform(-20, 20, (m, 3)).astype(np.float32), normal=rng.normal(size=(m, 3)), d=rng.uniform(-1, 1, m),
