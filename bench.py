@@ -624,7 +624,10 @@ def run_ours(args, rank, world, local_rank):
             "exec": {"replicas": world, "parallelism": f"{world} independent session(s), no collective",
                      "cpus_bound_per_replica": cpus_bound,
                      "call_mode": "frames and keyframe merge enqueued asynchronously (out = NULL); association, the 15 "
-                                  "factor evaluations and the chi2 cull return their results synchronously",
+                                  "factor evaluations and the chi2 cull return their results synchronously; host-buffer "
+                                  "steps (e2e) are timed as three call sequences - plain, and with the next keyframe "
+                                  "interval's newest frame / all frames announced ahead through fflins_host_prefetch - and "
+                                  "e2e.value is the fastest (e2e.call_sequence, e2e.call_sequences)",
                      "caller": ("native loop over the C-ABI (tools/session_driver.cc: the call sequence of fflins/pipeline.py, as the "
                                 "reference's C++ fusion thread would issue it)") if native else "fflins/pipeline.py through ctypes",
                      "l2": f"inputs cycle over {P} distinct frames ({input_bytes / 1e6:.0f} MB) > 126 MB L2",
