@@ -57,6 +57,12 @@ static_assert(sizeof(FactorSetupPair) == 8 * kSetupPair && sizeof(FactorSetup) =
 constexpr int kPairMsg   = kMsgHead + 7;       // 26 words
 constexpr int kPairSlots = 32;                 // host mailbox region per pair: one warp, one 16-byte load per lane
 constexpr int kRowSlots  = 64;                 // device hand-off per pair: 26 message words, 23 setup words from slot 32
+// Combined message (quiet waiting): the 19 header words and the reference poses of ALL pairs as 96 tagged slots, polled as a
+// whole by row 0's warp (three 16-byte loads per lane) and handed to the other rows through L2 - so that, while copies
+// saturate the link, a message costs ONE contended PCIe read instead of two in series (row 0's poll, then each row's own
+// region). Host region: row kMaxRefs of h_mail (3 x kPairSlots slots); device copy: rows kMaxRefs, kMaxRefs + 1 of d_row.
+constexpr int kCombSlots = 96;
+constexpr int kCombPairs = (kCombSlots - kMsgHead) / 7;   // 11 pairs fit
 
 // D (8x8, fp64) += A (8x4, row) * B (4x8, col) on the FP64 tensor pipe.
 __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
@@ -427,6 +433,7 @@ struct ResidentArgs {
     Unit *d_part;
     unsigned long long start_seq, launch_id, idle_ns;
     int rows;
+    int comb;              // 1: quiet waiting goes through the combined message (rows <= kCombPairs)
     long long *timeline;   // diagnostics (FFLINS_RES_TIMELINE=1): pinned, clock64 stamps of row 0 / rank 0
 };
 
@@ -459,7 +466,45 @@ __global__ void __launch_bounds__(kFactorBlock) resident_kernel(const __grid_con
                 const unsigned long long t0 = globaltimer_ns();
                 unsigned long long tag = 0;
                 bool idle = false;
-                if (quiet && pair != 0) {
+                const bool use_comb = quiet && A.comb;
+                if (use_comb) {
+                    const ulonglong2 *hcomb = A.h_mail + (size_t) kMaxRefs * kPairSlots;
+                    ulonglong2 *dcomb       = A.d_row + (size_t) kMaxRefs * kRowSlots;
+                    if (pair == 0) {
+                        // row 0 polls the WHOLE window message and copies it into L2 for the other rows
+                        while (true) {
+                            const ulonglong2 v0 = ld_slot(hcomb + tid), v1 = ld_slot(hcomb + 32 + tid), v2 = ld_slot(hcomb + 64 + tid);
+                            const unsigned long long t = __shfl_sync(0xffffffffu, v0.y, 0);
+                            const int np   = (int) (__shfl_sync(0xffffffffu, v0.x, W_NP) & 0xffffffffull);
+                            const int need = kMsgHead + 7 * np;   // slots that carry this message
+                            const bool ok  = t >= expect && np >= 1 && np <= kCombPairs && (tid >= need || v0.y == t) &&
+                                            (32 + tid >= need || v1.y == t) && (64 + tid >= need || v2.y == t);
+                            if (__all_sync(0xffffffffu, ok)) {
+                                st_slot_gpu(dcomb + tid, v0.x, t);
+                                st_slot_gpu(dcomb + 32 + tid, v1.x, t);
+                                st_slot_gpu(dcomb + 64 + tid, v2.x, t);
+                                sh.msg[tid] = v0.x;   // header + pair 0's pose are the first 26 slots
+                                tag         = t;
+                                break;
+                            }
+                            if (__any_sync(0xffffffffu, globaltimer_ns() - t0 > A.idle_ns)) break;   // idle: retire
+                        }
+                    } else {
+                        // the other rows take header and their own pose out of row 0's copy (L2, no PCIe)
+                        const int src = tid < kMsgHead ? tid : kMsgHead + 7 * pair + (tid - kMsgHead);
+                        while (true) {
+                            const ulonglong2 v = tid < kPairMsg ? ld_slot_gpu(dcomb + src) : make_ulonglong2(0ull, 0ull);
+                            const unsigned long long t = __shfl_sync(0xffffffffu, v.y, 0);
+                            if (__all_sync(0xffffffffu, t >= expect && (tid >= kPairMsg || v.y == t))) {
+                                sh.msg[tid] = v.x;
+                                tag         = t;
+                                break;
+                            }
+                            if (__any_sync(0xffffffffu, globaltimer_ns() - t0 > A.idle_ns + 2000000ull)) break;   // idle: retire
+                        }
+                    }
+                    idle = true;   // (skips the per-region poll below)
+                } else if (quiet && pair != 0) {
                     // QUIET mode (asked for by the previous message: host-to-device copies are in flight). Ten warps polling
                     // host memory cut the DMA rate from 53 to 32 GB/s (tools/h2d_probe.cu: PCIe read requests, not bytes);
                     // one warp does not. Only row 0 polls the host; the other rows wait in L2 for its "go" and then read
@@ -1091,6 +1136,7 @@ struct FactorRuntime {
     cudaEvent_t solve_go = nullptr, solve_done = nullptr;
     // diagnostics (FFLINS_RES_TIMELINE=1): where a resident evaluation's round trip goes
     bool timeline = false;
+    bool comb = false;             // quiet waiting through the combined message (FFLINS_COMBINED)
     long long *h_timeline = nullptr;
     double tl_spins_late = 0;   // polls that found a unit missing AFTER the first unit of the call had arrived
     double tl_post = 0, tl_wait = 0, tl_unpack = 0, tl_cyc[3] = {0, 0, 0}, tl_r1[3] = {0, 0, 0}, tl_g[3] = {0, 0, 0};
@@ -1108,10 +1154,10 @@ FactorRuntime *factor_runtime_create(int device) {
               cudaMalloc((void **) &rt->wb.partials, sizeof(double) * kMaxRefs * kFactorRanks * kRedSize) == cudaSuccess &&
               cudaMalloc((void **) &rt->wb.tickets, sizeof(int) * 2 * kMaxRefs + 16) == cudaSuccess &&
               cudaMallocHost((void **) &rt->h_red, res_bytes) == cudaSuccess &&
-              cudaMallocHost((void **) &rt->h_mail, sizeof(ulonglong2) * kMaxRefs * kPairSlots) == cudaSuccess &&
+              cudaMallocHost((void **) &rt->h_mail, sizeof(ulonglong2) * (kMaxRefs + 3) * kPairSlots) == cudaSuccess &&
               cudaMallocHost((void **) &rt->h_res, sizeof(Unit) * kMaxRefs * kRedUnits) == cudaSuccess &&
               cudaMallocHost((void **) &rt->h_exit, sizeof(unsigned long long) * (kMaxRefs + 16)) == cudaSuccess &&
-              cudaMalloc((void **) &rt->d_row, sizeof(ulonglong2) * kMaxRefs * kRowSlots) == cudaSuccess &&
+              cudaMalloc((void **) &rt->d_row, sizeof(ulonglong2) * (kMaxRefs + 2) * kRowSlots) == cudaSuccess &&
               cudaMalloc((void **) &rt->d_part, sizeof(Unit) * kMaxRefs * kFactorRanks * kRedUnits) == cudaSuccess &&
               cudaStreamCreateWithFlags(&rt->res_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaMalloc((void **) &rt->d_sbcast, sizeof(ulonglong2) * 128) == cudaSuccess &&
@@ -1145,11 +1191,11 @@ FactorRuntime *factor_runtime_create(int device) {
         rt->h_counts   = reinterpret_cast<int *>(rt->h_signal + kMaxRefs);
         rt->h_timeline = reinterpret_cast<long long *>(rt->h_exit + kMaxRefs);
         std::memset(rt->h_red, 0, res_bytes);
-        std::memset(rt->h_mail, 0, sizeof(ulonglong2) * kMaxRefs * kPairSlots);
+        std::memset(rt->h_mail, 0, sizeof(ulonglong2) * (kMaxRefs + 3) * kPairSlots);
         std::memset(rt->h_res, 0, sizeof(Unit) * kMaxRefs * kRedUnits);
         std::memset(rt->h_exit, 0, sizeof(unsigned long long) * (kMaxRefs + 16));
         ok = cudaMemset(rt->wb.tickets, 0, sizeof(int) * 2 * kMaxRefs + 16) == cudaSuccess &&
-             cudaMemset(rt->d_row, 0, sizeof(ulonglong2) * kMaxRefs * kRowSlots) == cudaSuccess &&
+             cudaMemset(rt->d_row, 0, sizeof(ulonglong2) * (kMaxRefs + 2) * kRowSlots) == cudaSuccess &&
              cudaMemset(rt->d_part, 0, sizeof(Unit) * kMaxRefs * kFactorRanks * kRedUnits) == cudaSuccess &&
              cudaFuncSetAttribute(factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kFactorSmem) == cudaSuccess &&
              cudaFuncSetAttribute(resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kFactorSmem) == cudaSuccess;
@@ -1165,6 +1211,7 @@ FactorRuntime *factor_runtime_create(int device) {
         if (v >= 10 && v <= 1000000) rt->idle_ns = (unsigned long long) v * 1000ull;
     }
     rt->timeline = getenv("FFLINS_RES_TIMELINE") != nullptr;
+    if (const char *e = getenv("FFLINS_COMBINED")) rt->comb = atoi(e) != 0;   // combined quiet message (see kCombSlots)
     return rt;
 }
 
@@ -1181,6 +1228,10 @@ inline void put_slot(ulonglong2 *slot, unsigned long long w, unsigned long long 
 
 // One mailbox region per pair: the 19 header words and the pair's own reference pose.
 void post_message(FactorRuntime *rt, const FactorMsg &m, int n_pairs, unsigned long long tag) {
+    if (rt->comb && n_pairs <= kCombPairs) {   // the combined copy (read in quiet mode only; every slot carries its tag)
+        ulonglong2 *reg = rt->h_mail + (size_t) kMaxRefs * kPairSlots;
+        for (int i = kMsgHead + 7 * n_pairs - 1; i >= 0; i--) put_slot(reg + i, m.w[i], tag);
+    }
     for (int p = n_pairs - 1; p >= 0; p--) {   // row 0's region LAST: in quiet mode the other rows read theirs once it has arrived
         ulonglong2 *reg = rt->h_mail + (size_t) p * kPairSlots;
         for (int i = 0; i < kMsgHead; i++) put_slot(reg + i, m.w[i], tag);
@@ -1214,9 +1265,10 @@ cudaError_t resident_start(FactorRuntime *rt, int rows) {
     A.launch_id = ++rt->launch_id;
     A.idle_ns   = rt->idle_ns;
     A.rows      = rows;
+    A.comb      = rt->comb && rows <= kCombPairs ? 1 : 0;
     A.timeline  = rt->timeline ? rt->h_timeline : nullptr;
     // a retired kernel leaves its farewell in the device rows (tagged with the NEXT sequence number): clear them
-    cudaError_t em = cudaMemsetAsync(rt->d_row, 0, sizeof(ulonglong2) * kMaxRefs * kRowSlots, rt->res_stream);
+    cudaError_t em = cudaMemsetAsync(rt->d_row, 0, sizeof(ulonglong2) * (kMaxRefs + 2) * kRowSlots, rt->res_stream);
     if (em != cudaSuccess) return em;
     resident_kernel<<<dim3(kFactorRanks, rows), kFactorBlock, kFactorSmem, rt->res_stream>>>(A);
     cudaError_t e = cudaGetLastError();

@@ -391,8 +391,22 @@ def test_resident_quiet_mode_matches_launched(tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     script = tmp_path / "quiet.py"
     script.write_text(_QUIET_SCRIPT)
-    out = subprocess.run([sys.executable, str(script), root], env=dict(os.environ, FFLINS_QUIET="1"), capture_output=True, text=True,
-                         timeout=900)
+    out = subprocess.run([sys.executable, str(script), root], env=dict(os.environ, FFLINS_QUIET="1", FFLINS_COMBINED="0"),
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "QUIET_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
+def test_resident_combined_quiet_message_matches_launched(tmp_path):
+    """The same with the combined message (FFLINS_COMBINED=1): row 0's warp polls the whole window message and hands it to
+    the other rows through L2 - one PCIe read per message instead of two in series."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "quiet.py"
+    script.write_text(_QUIET_SCRIPT)
+    out = subprocess.run([sys.executable, str(script), root], env=dict(os.environ, FFLINS_QUIET="1", FFLINS_COMBINED="1"),
+                         capture_output=True, text=True, timeout=900)
     assert out.returncode == 0 and "QUIET_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
 
 
