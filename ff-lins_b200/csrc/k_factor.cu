@@ -1136,7 +1136,7 @@ struct FactorRuntime {
     cudaEvent_t solve_go = nullptr, solve_done = nullptr;
     // diagnostics (FFLINS_RES_TIMELINE=1): where a resident evaluation's round trip goes
     bool timeline = false;
-    bool comb = false;             // quiet waiting through the combined message (FFLINS_COMBINED)
+    bool comb = true;              // quiet waiting through the combined message (FFLINS_COMBINED=0: per-row regions)
     long long *h_timeline = nullptr;
     double tl_spins_late = 0;   // polls that found a unit missing AFTER the first unit of the call had arrived
     double tl_post = 0, tl_wait = 0, tl_unpack = 0, tl_cyc[3] = {0, 0, 0}, tl_r1[3] = {0, 0, 0}, tl_g[3] = {0, 0, 0};
